@@ -1,0 +1,171 @@
+"""ctypes binding of libasep.so (include/asep.h) with DLPack tensor exchange.
+
+PyTorch is only the tensor container: tensors are handed to the library as the ``DLTensor``
+inside the DLPack capsule produced by ``torch.utils.dlpack.to_dlpack``.  There is no CPU
+fallback: if the shared library is missing the import fails loudly, and every compute call
+fails with ``RuntimeError`` when no sm_100 device is present.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional
+
+import torch
+from torch.utils import dlpack as _torch_dlpack
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libasep.so")
+
+PREC_FP32 = 0
+PREC_BF16 = 1
+
+
+class AsepError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libasep error {code}: {msg}")
+        self.code = code
+
+
+class DLDevice(ctypes.Structure):
+    _fields_ = [("device_type", ctypes.c_int32), ("device_id", ctypes.c_int32)]
+
+
+class DLDataType(ctypes.Structure):
+    _fields_ = [("code", ctypes.c_uint8), ("bits", ctypes.c_uint8), ("lanes", ctypes.c_uint16)]
+
+
+class DLTensor(ctypes.Structure):
+    _fields_ = [("data", ctypes.c_void_p), ("device", DLDevice), ("ndim", ctypes.c_int32), ("dtype", DLDataType),
+                ("shape", ctypes.POINTER(ctypes.c_int64)), ("strides", ctypes.POINTER(ctypes.c_int64)),
+                ("byte_offset", ctypes.c_uint64)]
+
+
+class GlowCfg(ctypes.Structure):
+    _fields_ = [("H", ctypes.c_int32), ("W", ctypes.c_int32), ("C", ctypes.c_int32), ("L", ctypes.c_int32),
+                ("K", ctypes.c_int32), ("n_filters", ctypes.c_int32), ("learntop", ctypes.c_int32),
+                ("minval", ctypes.c_float), ("maxval", ctypes.c_float)]
+
+
+_P = ctypes.POINTER(DLTensor)
+_V = ctypes.c_void_p
+_I = ctypes.c_int
+_F = ctypes.c_float
+_U64 = ctypes.c_uint64
+
+# name -> argtypes; every function returns int status unless listed in _RESTYPES
+_SIGNATURES = {
+    "asep_init": [_I],
+    "asep_glow_create": [ctypes.POINTER(GlowCfg), ctypes.POINTER(_V)],
+    "asep_glow_destroy": [_V],
+    "asep_glow_set_param": [_V, ctypes.c_char_p, _P],
+    "asep_glow_get_param": [_V, ctypes.c_char_p, _P],
+    "asep_glow_prepare": [_V, _I],
+    "asep_glow_init_actnorm": [_V, _P, _V],
+    "asep_glow_forward": [_V, _P, _P, _P, _V],
+    "asep_glow_inverse": [_V, _P, _P, _V],
+    "asep_glow_log_prob": [_V, _P, _P, _V],
+    "asep_glow_grad_log_prob": [_V, _P, _P, _P, _V],
+    "asep_glow_sample": [_V, _P, _P, _V],
+    "asep_actnorm": [_P, _P, _P, _P, _I, _V],
+    "asep_inv1x1": [_P, _P, _P, _V],
+    "asep_coupling": [_P, _P, _P, _P, _I, _V],
+    "asep_squeeze": [_P, _P, _I, _V],
+    "asep_glow_coupling_nn": [_V, _I, _I, _P, _P, _V],
+    "asep_glow_coupling_nn_backward": [_V, _I, _I, _P, _P, _P, _V],
+    "asep_langevin_step": [_P, _P, _P, _P, _P, _P, _P, _F, _F, _F, _U64, _U64, _U64, _P, _V],
+    "asep_mixing_db": [_P, _P, _P, _P, _P, _V],
+    "asep_philox_normal": [_P, _U64, _U64, _U64, _U64, _V],
+    "asep_basis_glow_inner": [_V, _V, _P, _P, _P, _I, _F, _F, _F, _P, _P, _U64, _U64, _U64, _P, _P, _V],
+    "asep_tc_set_cluster": [_I],
+}
+_RESTYPES = {"asep_last_error": ctypes.c_char_p, "asep_abi_version": ctypes.c_int, "asep_launch_count": ctypes.c_int64}
+EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + list(_RESTYPES))
+
+_lib = None
+_initialised_device: Optional[int] = None
+
+
+def load() -> ctypes.CDLL:
+    """dlopen libasep.so and declare the prototypes (no CUDA call is made here)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `make` (or __graft_entry__.build()). "
+            "audiosourcesep_b200 has no CPU or PyTorch fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, args in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = ctypes.c_int
+    for name, res in _RESTYPES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = []
+        fn.restype = res
+    _lib = lib
+    return lib
+
+
+def check(status: int):
+    if status != 0:
+        raise AsepError(status, load().asep_last_error().decode("utf-8", "replace"))
+
+
+def init(device: Optional[int] = None) -> int:
+    """asep_init on ``device`` (default: torch's current CUDA device)."""
+    global _initialised_device
+    if not torch.cuda.is_available():
+        raise RuntimeError("audiosourcesep_b200 needs a CUDA (sm_100a) device; there is no CPU fallback")
+    if device is None:
+        device = torch.cuda.current_device()
+    if _initialised_device != device:
+        check(load().asep_init(int(device)))
+        _initialised_device = device
+    return device
+
+
+def launch_count() -> int:
+    return int(load().asep_launch_count())
+
+
+# ------------------------------------------------------------------ DLPack plumbing
+_PyCapsule_GetPointer = ctypes.pythonapi.PyCapsule_GetPointer
+_PyCapsule_GetPointer.restype = ctypes.c_void_p
+_PyCapsule_GetPointer.argtypes = [ctypes.py_object, ctypes.c_char_p]
+_PyCapsule_GetName = ctypes.pythonapi.PyCapsule_GetName
+_PyCapsule_GetName.restype = ctypes.c_char_p
+_PyCapsule_GetName.argtypes = [ctypes.py_object]
+
+
+class DL:
+    """Keeps a DLPack capsule alive and exposes the ``DLTensor*`` inside it."""
+
+    __slots__ = ("capsule", "ptr", "tensor")
+
+    def __init__(self, t: Optional[torch.Tensor]):
+        self.tensor = t
+        if t is None:
+            self.capsule = None
+            self.ptr = ctypes.cast(None, _P)
+            return
+        self.capsule = _torch_dlpack.to_dlpack(t)
+        name = _PyCapsule_GetName(self.capsule)
+        addr = _PyCapsule_GetPointer(self.capsule, name)
+        if name == b"dltensor":
+            off = 0                       # DLManagedTensor starts with its DLTensor
+        elif name == b"dltensor_versioned":
+            off = 8 + 8 + 8 + 8           # DLPackVersion(2xu32) + manager_ctx + deleter + flags(u64)
+        else:
+            raise RuntimeError(f"unexpected DLPack capsule {name!r}")
+        self.ptr = ctypes.cast(addr + off, _P)
+
+
+def dl(t: Optional[torch.Tensor]) -> DL:
+    return DL(t)
+
+
+def stream_ptr(stream: Optional[torch.cuda.Stream] = None) -> ctypes.c_void_p:
+    s = torch.cuda.current_stream() if stream is None else stream
+    return ctypes.c_void_p(s.cuda_stream)

@@ -1,0 +1,478 @@
+// extern "C" surface of libasep.so (include/asep.h).  Everything below the ABI is C++/CUDA; errors
+// cross as status codes + asep_last_error().
+#include <cstdarg>
+#include <cstring>
+#include <memory>
+
+#include "glow_model.h"
+
+namespace asep {
+
+std::atomic<long long> g_launch_count{0};
+static thread_local std::string g_last_error;
+static int g_device = -1;
+
+std::string strfmt(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  return std::string(buf);
+}
+void set_last_error(const std::string& m) { g_last_error = m; }
+
+static int64_t check_contiguous(const DLTensor* t, const char* what) {
+  int64_t n = 1;
+  for (int i = 0; i < t->ndim; ++i) n *= t->shape[i];
+  if (t->strides != nullptr) {
+    int64_t expect = 1;
+    for (int i = t->ndim - 1; i >= 0; --i) {
+      if (t->shape[i] != 1 && t->strides[i] != expect)
+        throw Error(ASEP_ERR_BAD_LAYOUT, strfmt("%s: tensor is not row-major contiguous", what));
+      expect *= t->shape[i];
+    }
+  }
+  return n;
+}
+
+static TView view_any(const DLTensor* t, const char* what, int device, bool allow_host, uint8_t code, uint8_t bits) {
+  ASEP_CHECK(t != nullptr, ASEP_ERR_BAD_ARG, "%s: NULL tensor", what);
+  ASEP_CHECK(t->ndim >= 0 && t->ndim <= 8, ASEP_ERR_BAD_SHAPE, "%s: unsupported rank %d", what, t->ndim);
+  ASEP_CHECK(t->dtype.code == code && t->dtype.bits == bits && t->dtype.lanes == 1, ASEP_ERR_BAD_DTYPE,
+             "%s: expected %s%d, got dtype code %d bits %d", what, code == kDLFloat ? "float" : "int", bits,
+             t->dtype.code, t->dtype.bits);
+  TView v;
+  v.ndim = t->ndim;
+  for (int i = 0; i < t->ndim; ++i) v.shape[i] = t->shape[i];
+  v.numel = check_contiguous(t, what);
+  const bool dev = t->device.device_type == kDLCUDA || t->device.device_type == kDLCUDAManaged;
+  const bool host = t->device.device_type == kDLCPU || t->device.device_type == kDLCUDAHost;
+  ASEP_CHECK(dev || (allow_host && host), ASEP_ERR_BAD_DEVICE, "%s: tensor must live on the CUDA device", what);
+  if (dev && t->device.device_type == kDLCUDA)
+    ASEP_CHECK(device < 0 || t->device.device_id == device, ASEP_ERR_BAD_DEVICE, "%s: tensor on cuda:%d, handle on cuda:%d",
+               what, t->device.device_id, device);
+  v.on_device = dev;
+  v.raw = static_cast<char*>(t->data) + t->byte_offset;
+  ASEP_CHECK(v.numel == 0 || v.raw != nullptr, ASEP_ERR_BAD_ARG, "%s: NULL data pointer", what);
+  ASEP_CHECK((reinterpret_cast<uintptr_t>(v.raw) & 15) == 0, ASEP_ERR_BAD_LAYOUT, "%s: data must be 16-byte aligned", what);
+  v.f32 = static_cast<float*>(v.raw);
+  return v;
+}
+TView view_f32(const DLTensor* t, const char* what, int device, bool allow_host) {
+  return view_any(t, what, device, allow_host, kDLFloat, 32);
+}
+TView view_i32(const DLTensor* t, const char* what, int device) { return view_any(t, what, device, false, kDLInt, 32); }
+
+void expect_shape(const TView& v, const char* what, std::initializer_list<int64_t> shp) {
+  bool ok = v.ndim == (int)shp.size();
+  int i = 0;
+  if (ok)
+    for (auto s : shp) ok = ok && (s < 0 || v.shape[i++] == s);
+  if (!ok) {
+    std::string got = "[", want = "[";
+    for (int j = 0; j < v.ndim; ++j) got += std::to_string(v.shape[j]) + (j + 1 < v.ndim ? "," : "");
+    int j = 0;
+    for (auto s : shp) want += (s < 0 ? std::string("N") : std::to_string(s)) + (++j < (int)shp.size() ? "," : "");
+    throw Error(ASEP_ERR_BAD_SHAPE, strfmt("%s: shape %s], expected %s]", what, got.c_str(), want.c_str()));
+  }
+}
+
+}  // namespace asep
+
+using namespace asep;
+
+struct asep_glow_s {
+  std::unique_ptr<GlowModel> model;
+};
+
+#define ASEP_API_BEGIN try {
+#define ASEP_API_END                                   \
+  return ASEP_OK;                                      \
+  }                                                    \
+  catch (const ::asep::Error& e) {                     \
+    ::asep::set_last_error(e.what());                  \
+    return e.code;                                     \
+  }                                                    \
+  catch (const std::exception& e) {                    \
+    ::asep::set_last_error(e.what());                  \
+    return ASEP_ERR_CUDA;                              \
+  }
+
+static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+extern "C" {
+
+const char* asep_last_error(void) { return g_last_error.c_str(); }
+int asep_abi_version(void) { return ASEP_ABI_VERSION; }
+int64_t asep_launch_count(void) { return (int64_t)g_launch_count.load(); }
+
+int asep_init(int device) {
+  ASEP_API_BEGIN
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  ASEP_CHECK(e == cudaSuccess && count > 0, ASEP_ERR_CUDA,
+             "no CUDA device available (%s); libasep has no CPU fallback", cudaGetErrorString(e));
+  ASEP_CHECK(device >= 0 && device < count, ASEP_ERR_BAD_ARG, "device %d out of range (%d devices)", device, count);
+  CUDA_CHECK(cudaSetDevice(device));
+  int major = 0, minor = 0;
+  CUDA_CHECK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+  CUDA_CHECK(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device));
+  ASEP_CHECK(major == 10, ASEP_ERR_UNSUPPORTED, "libasep is built for sm_100a only; device is sm_%d%d", major, minor);
+  g_device = device;
+  ASEP_API_END
+}
+
+// ------------------------------------------------------------------ Glow
+int asep_glow_create(const asep_glow_cfg* cfg, asep_glow_t* out) {
+  ASEP_API_BEGIN
+  ASEP_CHECK(cfg != nullptr && out != nullptr, ASEP_ERR_BAD_ARG, "NULL argument");
+  ASEP_CHECK(g_device >= 0, ASEP_ERR_STATE, "asep_init() has not been called");
+  auto h = new asep_glow_s();
+  try {
+    h->model.reset(new GlowModel(*cfg, g_device));
+  } catch (...) {
+    delete h;
+    throw;
+  }
+  *out = h;
+  ASEP_API_END
+}
+
+int asep_glow_destroy(asep_glow_t h) {
+  ASEP_API_BEGIN
+  if (h) {
+    cudaDeviceSynchronize();
+    delete h;
+  }
+  ASEP_API_END
+}
+
+int asep_glow_set_param(asep_glow_t h, const char* name, const DLTensor* value) {
+  ASEP_API_BEGIN
+  ASEP_CHECK(h && name, ASEP_ERR_BAD_ARG, "NULL argument");
+  TView v = view_f32(value, name, h->model->device(), /*allow_host=*/true);
+  std::vector<int64_t> shape(v.shape, v.shape + v.ndim);
+  h->model->set_param(name, v.f32, shape, v.on_device);
+  ASEP_API_END
+}
+
+int asep_glow_get_param(asep_glow_t h, const char* name, DLTensor* out) {
+  ASEP_API_BEGIN
+  ASEP_CHECK(h && name, ASEP_ERR_BAD_ARG, "NULL argument");
+  const Param& p = h->model->get_param(name);
+  TView v = view_f32(out, name, h->model->device(), true);
+  ASEP_CHECK(v.numel == p.numel(), ASEP_ERR_BAD_SHAPE, "parameter '%s' has %lld elements, output has %lld", name,
+             (long long)p.numel(), (long long)v.numel);
+  if (v.on_device) CUDA_CHECK(cudaMemcpy(v.f32, p.dev, (size_t)v.numel * sizeof(float), cudaMemcpyDeviceToDevice));
+  else std::memcpy(v.f32, p.host.data(), (size_t)v.numel * sizeof(float));
+  ASEP_API_END
+}
+
+int asep_glow_prepare(asep_glow_t h, int precision) {
+  ASEP_API_BEGIN
+  ASEP_CHECK(h, ASEP_ERR_BAD_ARG, "NULL handle");
+  h->model->prepare(precision);
+  ASEP_API_END
+}
+
+static int batch_of(const TView& x, const GlowModel& m, const char* what) {
+  const auto& c = m.cfg();
+  expect_shape(x, what, {-1, c.H, c.W, c.C});
+  return (int)x.shape[0];
+}
+static void expect_latent(const TView& z, const GlowModel& m, int N, const char* what) {
+  ASEP_CHECK(z.numel == (int64_t)N * m.latent_dims() && z.ndim >= 1 && z.shape[0] == N, ASEP_ERR_BAD_SHAPE,
+             "%s: expected [%d, latent = %d] elements", what, N, m.latent_dims());
+}
+
+int asep_glow_init_actnorm(asep_glow_t h, const DLTensor* minibatch, void* stream) {
+  ASEP_API_BEGIN
+  ASEP_CHECK(h, ASEP_ERR_BAD_ARG, "NULL handle");
+  TView x = view_f32(minibatch, "minibatch", h->model->device());
+  int N = batch_of(x, *h->model, "minibatch");   // ActNorm asserts, flow_tfp_bijectors.py:218-220
+  h->model->init_actnorm(x.f32, N, as_stream(stream));
+  ASEP_API_END
+}
+
+int asep_glow_forward(asep_glow_t h, const DLTensor* x, DLTensor* z, DLTensor* fldj, void* stream) {
+  ASEP_API_BEGIN
+  ASEP_CHECK(h, ASEP_ERR_BAD_ARG, "NULL handle");
+  GlowModel& m = *h->model;
+  TView xv = view_f32(x, "x", m.device());
+  int N = batch_of(xv, m, "x");
+  TView zv = view_f32(z, "z", m.device());
+  expect_latent(zv, m, N, "z");
+  TView lv = view_f32(fldj, "fldj", m.device());
+  expect_shape(lv, "fldj", {N});
+  m.forward(xv.f32, zv.f32, lv.f32, N, as_stream(stream));
+  ASEP_API_END
+}
+
+int asep_glow_inverse(asep_glow_t h, const DLTensor* z, DLTensor* x, void* stream) {
+  ASEP_API_BEGIN
+  ASEP_CHECK(h, ASEP_ERR_BAD_ARG, "NULL handle");
+  GlowModel& m = *h->model;
+  TView xv = view_f32(x, "x", m.device());
+  int N = batch_of(xv, m, "x");
+  TView zv = view_f32(z, "z", m.device());
+  expect_latent(zv, m, N, "z");
+  m.inverse(zv.f32, xv.f32, N, as_stream(stream));
+  ASEP_API_END
+}
+
+int asep_glow_log_prob(asep_glow_t h, const DLTensor* x, DLTensor* logp, void* stream) {
+  ASEP_API_BEGIN
+  ASEP_CHECK(h, ASEP_ERR_BAD_ARG, "NULL handle");
+  GlowModel& m = *h->model;
+  TView xv = view_f32(x, "x", m.device());
+  int N = batch_of(xv, m, "x");
+  TView lv = view_f32(logp, "logp", m.device());
+  expect_shape(lv, "logp", {N});
+  m.log_prob(xv.f32, lv.f32, N, as_stream(stream));
+  ASEP_API_END
+}
+
+int asep_glow_grad_log_prob(asep_glow_t h, const DLTensor* x, DLTensor* grad, DLTensor* logp, void* stream) {
+  ASEP_API_BEGIN
+  ASEP_CHECK(h, ASEP_ERR_BAD_ARG, "NULL handle");
+  GlowModel& m = *h->model;
+  TView xv = view_f32(x, "x", m.device());
+  int N = batch_of(xv, m, "x");
+  TView gv = view_f32(grad, "grad", m.device());
+  expect_shape(gv, "grad", {N, m.cfg().H, m.cfg().W, m.cfg().C});
+  float* lp = nullptr;
+  if (logp != nullptr) {
+    TView lv = view_f32(logp, "logp", m.device());
+    expect_shape(lv, "logp", {N});
+    lp = lv.f32;
+  }
+  m.grad_log_prob(xv.f32, gv.f32, lp, N, as_stream(stream));
+  ASEP_API_END
+}
+
+int asep_glow_sample(asep_glow_t h, const DLTensor* eps, DLTensor* x, void* stream) {
+  ASEP_API_BEGIN
+  ASEP_CHECK(h, ASEP_ERR_BAD_ARG, "NULL handle");
+  GlowModel& m = *h->model;
+  TView xv = view_f32(x, "x", m.device());
+  int N = batch_of(xv, m, "x");
+  TView ev = view_f32(eps, "eps", m.device());
+  expect_latent(ev, m, N, "eps");
+  m.sample(ev.f32, xv.f32, N, as_stream(stream));
+  ASEP_API_END
+}
+
+int asep_glow_coupling_nn(asep_glow_t h, int block, int step, const DLTensor* state, DLTensor* r, void* stream) {
+  ASEP_API_BEGIN
+  ASEP_CHECK(h, ASEP_ERR_BAD_ARG, "NULL handle");
+  GlowModel& m = *h->model;
+  ASEP_CHECK(block >= 0 && block < m.cfg().L, ASEP_ERR_BAD_ARG, "block out of range");
+  const Level& lv = m.level(block);
+  TView sv = view_f32(state, "state", m.device());
+  expect_shape(sv, "state", {-1, lv.H, lv.W, lv.C});
+  TView rv = view_f32(r, "r", m.device());
+  expect_shape(rv, "r", {sv.shape[0], lv.H, lv.W, lv.C});
+  m.coupling_nn(block, step, sv.f32, rv.f32, (int)sv.shape[0], as_stream(stream));
+  ASEP_API_END
+}
+
+int asep_glow_coupling_nn_backward(asep_glow_t h, int block, int step, const DLTensor* state, const DLTensor* gr,
+                                   DLTensor* gxb, void* stream) {
+  ASEP_API_BEGIN
+  ASEP_CHECK(h, ASEP_ERR_BAD_ARG, "NULL handle");
+  GlowModel& m = *h->model;
+  ASEP_CHECK(block >= 0 && block < m.cfg().L, ASEP_ERR_BAD_ARG, "block out of range");
+  const Level& lv = m.level(block);
+  TView sv = view_f32(state, "state", m.device());
+  expect_shape(sv, "state", {-1, lv.H, lv.W, lv.C});
+  TView gv = view_f32(gr, "gr", m.device());
+  expect_shape(gv, "gr", {sv.shape[0], lv.H, lv.W, lv.C});
+  TView ov = view_f32(gxb, "gxb", m.device());
+  expect_shape(ov, "gxb", {sv.shape[0], lv.H, lv.W, lv.C / 2});
+  m.coupling_nn_backward(block, step, sv.f32, gv.f32, ov.f32, (int)sv.shape[0], as_stream(stream));
+  ASEP_API_END
+}
+
+// ------------------------------------------------------------------ single bijectors
+static void nhwc(const TView& v, const char* what, int& N, int& H, int& W, int& C) {
+  ASEP_CHECK(v.ndim == 4, ASEP_ERR_BAD_SHAPE, "%s: expected a [N,H,W,C] tensor", what);
+  N = (int)v.shape[0]; H = (int)v.shape[1]; W = (int)v.shape[2]; C = (int)v.shape[3];
+}
+
+int asep_actnorm(const DLTensor* x, const DLTensor* log_scale, const DLTensor* shift, DLTensor* y, int inverse,
+                 void* stream) {
+  ASEP_API_BEGIN
+  TView xv = view_f32(x, "x", g_device), yv = view_f32(y, "y", g_device);
+  int N, H, W, C;
+  nhwc(xv, "x", N, H, W, C);
+  expect_shape(yv, "y", {N, H, W, C});
+  TView ls = view_f32(log_scale, "log_scale", g_device), sh = view_f32(shift, "shift", g_device);
+  expect_shape(ls, "log_scale", {C});
+  expect_shape(sh, "shift", {C});
+  launch_actnorm(xv.f32, ls.f32, sh.f32, yv.f32, (long long)N * H * W, C, inverse, as_stream(stream));
+  ASEP_API_END
+}
+
+int asep_inv1x1(const DLTensor* x, const DLTensor* w, DLTensor* y, void* stream) {
+  ASEP_API_BEGIN
+  TView xv = view_f32(x, "x", g_device), yv = view_f32(y, "y", g_device), wv = view_f32(w, "w", g_device);
+  int N, H, W, C;
+  nhwc(xv, "x", N, H, W, C);
+  expect_shape(yv, "y", {N, H, W, C});
+  expect_shape(wv, "w", {C, C});
+  ASEP_CHECK(xv.raw != yv.raw, ASEP_ERR_BAD_ARG, "inv1x1 cannot run in place");
+  launch_chanmix(xv.f32, wv.f32, yv.f32, (long long)N * H * W, C, as_stream(stream));
+  ASEP_API_END
+}
+
+int asep_coupling(const DLTensor* x, const DLTensor* r, DLTensor* y, DLTensor* logdet, int inverse, void* stream) {
+  ASEP_API_BEGIN
+  TView xv = view_f32(x, "x", g_device), rv = view_f32(r, "r", g_device), yv = view_f32(y, "y", g_device);
+  int N, H, W, C;
+  nhwc(xv, "x", N, H, W, C);
+  ASEP_CHECK(C % 2 == 0, ASEP_ERR_BAD_SHAPE, "coupling needs an even channel count");   // flow_tfp_bijectors.py:130
+  expect_shape(rv, "r", {N, H, W, C});
+  expect_shape(yv, "y", {N, H, W, C});
+  TView lv = view_f32(logdet, "logdet", g_device);
+  expect_shape(lv, "logdet", {N});
+  cudaStream_t s = as_stream(stream);
+  double* acc = nullptr;
+  CUDA_CHECK(cudaMalloc(&acc, std::max(N, 1) * sizeof(double)));
+  CUDA_CHECK(cudaMemsetAsync(acc, 0, std::max(N, 1) * sizeof(double), s));
+  float* sc = nullptr;
+  try {
+    if (!inverse) {
+      launch_post_pre(xv.f32, rv.f32, yv.f32, nullptr, acc, (long long)N * H * W, H * W, C, s);
+    } else {
+      // identity ActNorm / 1x1 constants: the inverse kernel then reduces to the coupling inverse
+      std::vector<float> id((size_t)step_const_floats(C), 0.f);
+      for (int i = 0; i < C; ++i) { id[i] = 1.f; id[2 * C + i * C + i] = 1.f; id[2 * C + C * C + i * C + i] = 1.f; }
+      CUDA_CHECK(cudaMalloc(&sc, id.size() * sizeof(float)));
+      CUDA_CHECK(cudaMemcpyAsync(sc, id.data(), id.size() * sizeof(float), cudaMemcpyHostToDevice, s));
+      launch_inv_step(xv.f32, rv.f32, yv.f32, sc, acc, (long long)N * H * W, H * W, C, s);
+    }
+    launch_finish(acc, lv.f32, 0.0, 1.0, N, s);
+    CUDA_CHECK(cudaStreamSynchronize(s));
+  } catch (...) {
+    cudaFree(acc);
+    if (sc) cudaFree(sc);
+    throw;
+  }
+  cudaFree(acc);
+  if (sc) cudaFree(sc);
+  ASEP_API_END
+}
+
+int asep_squeeze(const DLTensor* x, DLTensor* y, int inverse, void* stream) {
+  ASEP_API_BEGIN
+  TView xv = view_f32(x, "x", g_device), yv = view_f32(y, "y", g_device);
+  int N, H, W, C;
+  nhwc(inverse ? yv : xv, inverse ? "y" : "x", N, H, W, C);      // the unsqueezed side
+  ASEP_CHECK(H % 2 == 0 && W % 2 == 0, ASEP_ERR_BAD_SHAPE, "Squeeze needs even H and W");   // :165-166
+  expect_shape(inverse ? xv : yv, inverse ? "x" : "y", {N, H / 2, W / 2, 4 * C});
+  launch_squeeze(xv.f32, yv.f32, N, H, W, C, 0, 0.f, 0.f, inverse, as_stream(stream));
+  ASEP_API_END
+}
+
+// ------------------------------------------------------------------ Langevin
+int asep_langevin_step(DLTensor* x1, DLTensor* x2, const DLTensor* s1, const DLTensor* s2, const DLTensor* mixed,
+                       const DLTensor* n1, const DLTensor* n2, float eta, float lambda, float noise_scale,
+                       uint64_t seed, uint64_t step, uint64_t elem_offset, DLTensor* nan_count, void* stream) {
+  ASEP_API_BEGIN
+  TView a = view_f32(x1, "x1", g_device), b = view_f32(x2, "x2", g_device);
+  TView sa = view_f32(s1, "s1", g_device), sb = view_f32(s2, "s2", g_device), mx = view_f32(mixed, "mixed", g_device);
+  ASEP_CHECK(a.numel == b.numel && a.numel == sa.numel && a.numel == sb.numel && a.numel == mx.numel,
+             ASEP_ERR_BAD_SHAPE, "langevin: all tensors must have the same number of elements");
+  ASEP_CHECK((n1 == nullptr) == (n2 == nullptr), ASEP_ERR_BAD_ARG, "inject both noise tensors or neither");
+  const float *p1 = nullptr, *p2 = nullptr;
+  if (n1) {
+    TView na = view_f32(n1, "n1", g_device), nb = view_f32(n2, "n2", g_device);
+    ASEP_CHECK(na.numel == a.numel && nb.numel == a.numel, ASEP_ERR_BAD_SHAPE, "noise shape mismatch");
+    p1 = na.f32; p2 = nb.f32;
+  }
+  int* nanp = nullptr;
+  if (nan_count) nanp = static_cast<int*>(view_i32(nan_count, "nan_count", g_device).raw);
+  launch_langevin(a.f32, b.f32, sa.f32, sb.f32, mx.f32, p1, p2, eta, lambda, noise_scale, seed, step, elem_offset,
+                  nanp, a.numel, as_stream(stream));
+  ASEP_API_END
+}
+
+int asep_mixing_db(const DLTensor* x1, const DLTensor* x2, DLTensor* g, DLTensor* w1, DLTensor* w2, void* stream) {
+  ASEP_API_BEGIN
+  TView a = view_f32(x1, "x1", g_device), b = view_f32(x2, "x2", g_device), gv = view_f32(g, "g", g_device);
+  TView wa = view_f32(w1, "w1", g_device), wb = view_f32(w2, "w2", g_device);
+  ASEP_CHECK(a.numel == b.numel && a.numel == gv.numel && a.numel == wa.numel && a.numel == wb.numel,
+             ASEP_ERR_BAD_SHAPE, "mixing: element counts differ");
+  launch_mixing_db(a.f32, b.f32, gv.f32, wa.f32, wb.f32, a.numel, as_stream(stream));
+  ASEP_API_END
+}
+
+int asep_philox_normal(DLTensor* out, uint64_t seed, uint64_t step, uint64_t stream_id, uint64_t elem_offset,
+                       void* stream) {
+  ASEP_API_BEGIN
+  TView o = view_f32(out, "out", g_device);
+  launch_philox_normal(o.f32, seed, step, stream_id, elem_offset, o.numel, as_stream(stream));
+  ASEP_API_END
+}
+
+int asep_basis_glow_inner(asep_glow_t m1, asep_glow_t m2, const DLTensor* mixed, DLTensor* x1, DLTensor* x2, int T,
+                          float eta, float lambda, float noise_scale, const DLTensor* noise1, const DLTensor* noise2,
+                          uint64_t seed, uint64_t step0, uint64_t elem_offset, DLTensor* per_step,
+                          DLTensor* nan_count, void* stream) {
+  ASEP_API_BEGIN
+  ASEP_CHECK(m1 && m2, ASEP_ERR_BAD_ARG, "NULL handle");
+  GlowModel &g1 = *m1->model, &g2 = *m2->model;
+  const int dev = g1.device();
+  TView a = view_f32(x1, "x1", dev), b = view_f32(x2, "x2", dev), mx = view_f32(mixed, "mixed", dev);
+  const int N = batch_of(a, g1, "x1");
+  ASEP_CHECK(batch_of(b, g2, "x2") == N && mx.numel == a.numel, ASEP_ERR_BAD_SHAPE, "x1, x2, mixed must match");
+  ASEP_CHECK((noise1 == nullptr) == (noise2 == nullptr), ASEP_ERR_BAD_ARG, "inject both noise tensors or neither");
+  const float *nz1 = nullptr, *nz2 = nullptr;
+  if (noise1) {
+    TView na = view_f32(noise1, "noise1", dev), nb = view_f32(noise2, "noise2", dev);
+    ASEP_CHECK(na.numel == (int64_t)T * a.numel && nb.numel == na.numel, ASEP_ERR_BAD_SHAPE, "noise must be [T, ...]");
+    nz1 = na.f32; nz2 = nb.f32;
+  }
+  float* dump = nullptr;
+  if (per_step) {
+    TView d = view_f32(per_step, "per_step", dev);
+    ASEP_CHECK(d.numel == (int64_t)T * 2 * a.numel, ASEP_ERR_BAD_SHAPE, "per_step must be [T, 2, ...]");
+    dump = d.f32;
+  }
+  int* nanp = nullptr;
+  if (nan_count) nanp = static_cast<int*>(view_i32(nan_count, "nan_count", dev).raw);
+  cudaStream_t s = as_stream(stream);
+  float *s1 = nullptr, *s2 = nullptr;
+  CUDA_CHECK(cudaMalloc(&s1, (size_t)a.numel * sizeof(float)));
+  CUDA_CHECK(cudaMalloc(&s2, (size_t)a.numel * sizeof(float)));
+  try {
+    for (int t = 0; t < T; ++t) {
+      g1.grad_log_prob(a.f32, s1, nullptr, N, s);     // run_basis_sep.py:174-175
+      g2.grad_log_prob(b.f32, s2, nullptr, N, s);
+      launch_langevin(a.f32, b.f32, s1, s2, mx.f32, nz1 ? nz1 + (size_t)t * a.numel : nullptr,
+                      nz2 ? nz2 + (size_t)t * a.numel : nullptr, eta, lambda, noise_scale, seed, step0 + t,
+                      elem_offset, nanp, a.numel, s);
+      if (dump) {
+        CUDA_CHECK(cudaMemcpyAsync(dump + (size_t)(2 * t) * a.numel, a.f32, (size_t)a.numel * sizeof(float),
+                                   cudaMemcpyDeviceToDevice, s));
+        CUDA_CHECK(cudaMemcpyAsync(dump + (size_t)(2 * t + 1) * a.numel, b.f32, (size_t)a.numel * sizeof(float),
+                                   cudaMemcpyDeviceToDevice, s));
+      }
+    }
+    CUDA_CHECK(cudaStreamSynchronize(s));
+  } catch (...) {
+    cudaFree(s1); cudaFree(s2);
+    throw;
+  }
+  cudaFree(s1); cudaFree(s2);
+  ASEP_API_END
+}
+
+int asep_tc_set_cluster(int cluster_size) {
+  ASEP_API_BEGIN
+  nn_tc_set_cluster(cluster_size);
+  ASEP_API_END
+}
+
+}  // extern "C"

@@ -1,0 +1,238 @@
+// CUDA-core fp32 implementation of ShiftAndLogScaleConvNet (flow_tfk_layers.py:73-84) and of its
+// data gradient.  This is the ASEP_PREC_FP32 "exact" mode: plain fp32 FMAs in the reference's
+// operator order (conv+bias -> ReLU -> inference BatchNorm affine -> ...).  It exists so that the
+// tcgen05 path can be checked on the device at full size and so that tight-tolerance parity
+// (round trip <= 1e-4) has an arithmetic that is not rounded to bf16.  It is NOT tuned.
+#include "kernels.h"
+
+namespace asep {
+namespace {
+
+// a1[p][f] = relu(c1[f] + sum_{tap,ci} xb[p+off(tap)][ci] * K1[tap][ci][f])
+__global__ void __launch_bounds__(256) k_conv1(const float* __restrict__ state, const float* __restrict__ k1,
+                                               const float* __restrict__ c1, float* __restrict__ a1, int N, int H,
+                                               int W, int C, int F) {
+  const int Ch = C / 2;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)N * H * W * F;
+  if (idx >= total) return;
+  int f = idx % F;
+  long long p = idx / F;
+  int w = p % W;
+  int h = (p / W) % H;
+  float acc = c1[f];
+  for (int dy = -1; dy <= 1; ++dy) {
+    int hh = h + dy;
+    if (hh < 0 || hh >= H) continue;
+    for (int dx = -1; dx <= 1; ++dx) {
+      int ww = w + dx;
+      if (ww < 0 || ww >= W) continue;
+      const float* xin = state + (p + (long long)dy * W + dx) * C + Ch;
+      const float* kk = k1 + ((dy + 1) * 3 + (dx + 1)) * Ch * F + f;
+      for (int ci = 0; ci < Ch; ++ci) acc = fmaf(xin[ci], kk[ci * F], acc);
+    }
+  }
+  a1[idx] = fmaxf(acc, 0.f);
+}
+
+// Tiled SGEMM  out[M,Nn] = epi( (sa[k]*A[m][k]+oa[k]) . B[k][n] )
+//   kEpi 0: relu(acc + bias[n])        kEpi 1: acc * scale[n] * (mask[m][n] > 0)
+template <int kEpi>
+__global__ void __launch_bounds__(256) k_sgemm(const float* __restrict__ A, const float* __restrict__ sa,
+                                               const float* __restrict__ oa, const float* __restrict__ B,
+                                               const float* __restrict__ vec, const float* __restrict__ mask,
+                                               float* __restrict__ out, long long M, int Nn, int K) {
+  constexpr int BM = 64, BN = 64, BK = 16;
+  __shared__ float As[BK][BM + 1];
+  __shared__ float Bs[BK][BN];
+  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+  const long long m0 = (long long)blockIdx.y * BM;
+  const int n0 = blockIdx.x * BN;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < K; k0 += BK) {
+    for (int i = threadIdx.x; i < BM * BK; i += 256) {
+      int mm = i / BK, kk = i % BK;
+      long long m = m0 + mm;
+      float v = 0.f;
+      if (m < M) {
+        v = A[m * K + k0 + kk];
+        if (sa != nullptr) v = sa[k0 + kk] * v + oa[k0 + kk];
+      }
+      As[kk][mm] = v;
+    }
+    for (int i = threadIdx.x; i < BK * BN; i += 256) {
+      int kk = i / BN, nn = i % BN;
+      Bs[kk][nn] = B[(long long)(k0 + kk) * Nn + n0 + nn];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    long long m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int n = n0 + tx * 4 + j;
+      float v = acc[i][j];
+      if constexpr (kEpi == 0) v = fmaxf(v + vec[n], 0.f);
+      else v = (mask[m * Nn + n] > 0.f) ? v * vec[n] : 0.f;
+      out[m * Nn + n] = v;
+    }
+  }
+}
+
+// r[p][c] = c3[c] + sum_{tap valid} sum_k (g2[k]*a2[q][k]+b2[k]) * K3[tap][k][c]    (one warp per pixel)
+template <int C>
+__global__ void __launch_bounds__(256) k_conv3(const float* __restrict__ a2, const float* __restrict__ g2,
+                                               const float* __restrict__ b2, const float* __restrict__ k3,
+                                               const float* __restrict__ c3, float* __restrict__ r, int N, int H,
+                                               int W, int F) {
+  const int lane = threadIdx.x & 31;
+  long long p = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  long long M = (long long)N * H * W;
+  if (p >= M) return;
+  int w = p % W;
+  int h = (p / W) % H;
+  float acc[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) acc[c] = 0.f;
+  for (int dy = -1; dy <= 1; ++dy) {
+    int hh = h + dy;
+    if (hh < 0 || hh >= H) continue;
+    for (int dx = -1; dx <= 1; ++dx) {
+      int ww = w + dx;
+      if (ww < 0 || ww >= W) continue;
+      const float* hin = a2 + (p + (long long)dy * W + dx) * F;
+      const float* kk = k3 + (long long)((dy + 1) * 3 + (dx + 1)) * F * C;
+      for (int k = lane; k < F; k += 32) {
+        float hv = g2[k] * hin[k] + b2[k];
+#pragma unroll
+        for (int c = 0; c < C; ++c) acc[c] = fmaf(hv, kk[k * C + c], acc[c]);
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    float v = warp_sum(acc[c]);
+    if (lane == 0) r[p * C + c] = v + c3[c];
+  }
+}
+
+// gp2[p][k] = g2[k] * [a2[p][k] > 0] * sum_{tap} sum_c gr[p - off(tap)][c] * K3[tap][k][c]
+__global__ void __launch_bounds__(256) k_conv3_bwd(const float* __restrict__ gr, const float* __restrict__ k3,
+                                                   const float* __restrict__ g2, const float* __restrict__ a2,
+                                                   float* __restrict__ gp2, int N, int H, int W, int C, int F) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)N * H * W * F;
+  if (idx >= total) return;
+  int k = idx % F;
+  long long p = idx / F;
+  if (!(a2[idx] > 0.f)) { gp2[idx] = 0.f; return; }
+  int w = p % W;
+  int h = (p / W) % H;
+  float acc = 0.f;
+  for (int dy = -1; dy <= 1; ++dy) {
+    int hh = h - dy;
+    if (hh < 0 || hh >= H) continue;
+    for (int dx = -1; dx <= 1; ++dx) {
+      int ww = w - dx;
+      if (ww < 0 || ww >= W) continue;
+      const float* g = gr + (p - (long long)dy * W - dx) * C;
+      const float* kk = k3 + ((long long)((dy + 1) * 3 + (dx + 1)) * F + k) * C;
+      for (int c = 0; c < C; ++c) acc = fmaf(g[c], kk[c], acc);
+    }
+  }
+  gp2[idx] = acc * g2[k];
+}
+
+// gxb[p][ci] = sum_{tap} sum_f gp1[p - off(tap)][f] * K1[tap][ci][f]     (one warp per pixel)
+template <int Ch>
+__global__ void __launch_bounds__(256) k_conv1_bwd(const float* __restrict__ gp1, const float* __restrict__ k1,
+                                                   float* __restrict__ gxb, int N, int H, int W, int F) {
+  const int lane = threadIdx.x & 31;
+  long long p = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  long long M = (long long)N * H * W;
+  if (p >= M) return;
+  int w = p % W;
+  int h = (p / W) % H;
+  float acc[Ch];
+#pragma unroll
+  for (int c = 0; c < Ch; ++c) acc[c] = 0.f;
+  for (int dy = -1; dy <= 1; ++dy) {
+    int hh = h - dy;
+    if (hh < 0 || hh >= H) continue;
+    for (int dx = -1; dx <= 1; ++dx) {
+      int ww = w - dx;
+      if (ww < 0 || ww >= W) continue;
+      const float* g = gp1 + (p - (long long)dy * W - dx) * F;
+      const float* kk = k1 + (long long)((dy + 1) * 3 + (dx + 1)) * Ch * F;
+      for (int f = lane; f < F; f += 32) {
+        float gv = g[f];
+#pragma unroll
+        for (int c = 0; c < Ch; ++c) acc[c] = fmaf(gv, kk[c * F + f], acc[c]);
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < Ch; ++c) {
+    float v = warp_sum(acc[c]);
+    if (lane == 0) gxb[p * Ch + c] = v;
+  }
+}
+
+}  // namespace
+
+#define DISPATCH_NNC(C, ...)                                                                 \
+  switch (C) {                                                                               \
+    case 1: { constexpr int kC = 1; __VA_ARGS__; } break;                                    \
+    case 2: { constexpr int kC = 2; __VA_ARGS__; } break;                                    \
+    case 4: { constexpr int kC = 4; __VA_ARGS__; } break;                                    \
+    case 8: { constexpr int kC = 8; __VA_ARGS__; } break;                                    \
+    case 16: { constexpr int kC = 16; __VA_ARGS__; } break;                                  \
+    case 32: { constexpr int kC = 32; __VA_ARGS__; } break;                                  \
+    default: throw Error(ASEP_ERR_UNSUPPORTED, strfmt("channel count %d not built", C));     \
+  }
+
+void nn_fp32_forward(const NNWeightsF32& w, const float* state, float* a1, float* a2, float* r, int N, int H, int W,
+                     int C, int F, cudaStream_t s) {
+  long long M = (long long)N * H * W;
+  if (M == 0) return;
+  ASEP_CHECK(F % 64 == 0, ASEP_ERR_UNSUPPORTED, "n_filters must be a multiple of 64 (got %d)", F);
+  k_conv1<<<cdiv(M * F, 256), 256, 0, s>>>(state, w.k1, w.c1, a1, N, H, W, C, F);
+  ASEP_LAUNCH_CHECK();
+  dim3 grid(F / 64, cdiv(M, 64));
+  k_sgemm<0><<<grid, 256, 0, s>>>(a1, w.g1, w.b1, w.k2, w.c2, nullptr, a2, M, F, F);
+  ASEP_LAUNCH_CHECK();
+  DISPATCH_NNC(C, (k_conv3<kC><<<cdiv(M * 32, 256), 256, 0, s>>>(a2, w.g2, w.b2, w.k3, w.c3, r, N, H, W, F)));
+  ASEP_LAUNCH_CHECK();
+}
+
+void nn_fp32_backward(const NNWeightsF32& w, const float* a1, const float* a2, const float* gr, float* t1, float* t2,
+                      float* gxb, int N, int H, int W, int C, int F, cudaStream_t s) {
+  long long M = (long long)N * H * W;
+  if (M == 0) return;
+  // t2 = gp2 = conv3^T(gr) * g2 * [p2 > 0]
+  k_conv3_bwd<<<cdiv(M * F, 256), 256, 0, s>>>(gr, w.k3, w.g2, a2, t2, N, H, W, C, F);
+  ASEP_LAUNCH_CHECK();
+  // t1 = gp1 = (gp2 . K2^T) * g1 * [p1 > 0]
+  dim3 grid(F / 64, cdiv(M, 64));
+  k_sgemm<1><<<grid, 256, 0, s>>>(t2, nullptr, nullptr, w.k2t, w.g1, a1, t1, M, F, F);
+  ASEP_LAUNCH_CHECK();
+  DISPATCH_NNC(C / 2, (k_conv1_bwd<kC><<<cdiv(M * 32, 256), 256, 0, s>>>(t1, w.k1, gxb, N, H, W, F)));
+  ASEP_LAUNCH_CHECK();
+}
+
+}  // namespace asep

@@ -1,0 +1,637 @@
+// Fused coupling network on the 5th-generation tensor cores (sm_100a).
+//
+// One launch evaluates ShiftAndLogScaleConvNet (flow_tfk_layers.py:73-84) for one Glow step as a
+// chain of three GEMMs per 128-pixel tile, never spilling the 512-wide hidden activations to HBM:
+//
+//   stage 1  conv 3x3 (C/2 -> 512) as implicit GEMM: A = im2col(xb) built in shared memory by the
+//            worker warps as split-bf16 [hi | lo] (K = 2*9*C/2), B = K1 (bf16)           N = 512
+//   stage 2  conv 1x1 (512 -> 512): A = relu(p1) (bf16, written by the epilogue straight into the
+//            SWIZZLE_128B K-major operand layout), B = diag(g1') K2                        N = 512
+//   stage 3  conv 3x3 (512 -> C) as GEMM + col2im: A = relu(p2), B = [diag(g2') K3[tap]]_tap, N = 9C;
+//            the 9 per-tap partial outputs G[p][tap][c] go to global memory (fp32) and a cheap
+//            gather kernel sums G[p+off(tap)][tap] over the in-bounds taps ("same" zero padding,
+//            with the BatchNorm offset b2' handled per tap so borders stay exact).
+//
+// BatchNorm runs in inference mode in the reference, so its affine is folded
+// into the next GEMM's weights on the host (nn_tc_prepare).
+//
+// Pipeline per CTA (192 threads, persistent over tiles, 1 CTA / SM):
+//   warp 0    producer: streams pre-swizzled bf16 weight tile images (32 KB) with TMA bulk copies
+//             (cp.async.bulk -> UBLKCP) into a 3-stage ring; with a cluster of CS CTAs every CTA
+//             loads 1/CS of each image and multicasts it to all CS rings (L2 traffic / CS).
+//   warp 1    MMA issuer: one elected thread issues tcgen05.mma (M=128, N<=256, K=16) with A and B
+//             SWIZZLE_128B shared-memory descriptors, fp32 accumulators in TMEM (512 columns);
+//             tcgen05.commit releases ring slots (multicast to the cluster) and signals epilogues.
+//   warps 2-5 workers: build the stage-1 operand, run the epilogues (tcgen05.ld 32x32b -> bias +
+//             ReLU (+ mask bits for the backward pass) -> bf16 -> swizzled st.shared), write G.
+//
+// The data-gradient kernel is the same pipeline with transposed weights:
+//   stage 1  conv3^T: A = im2col(gr) (split-bf16, K = 2*9*C), B = diag(g2') K3^T, epilogue = ReLU mask 2
+//   stage 2  B = diag(g1') K2^T, epilogue = ReLU mask 1
+//   stage 3  conv1^T as GEMM + col2im: B = K1 (N = 9*C/2), gather sums G'[p-off(tap)][tap].
+#include "nn_tc.h"
+
+#include <cooperative_groups.h>
+#include <cstring>
+
+namespace asep {
+
+namespace cg = cooperative_groups;
+
+namespace {
+
+constexpr int kF = kTcF;
+constexpr int kTileM = 128;
+constexpr int kPanelBytes = kTileM * 128;        // one 64-wide bf16 K panel of the A operand
+constexpr int kNumPanels = kF / 64;              // 8
+constexpr int kARegionBytes = kNumPanels * kPanelBytes;   // 128 KB
+constexpr int kStageRows = 256;
+constexpr int kStageBytes = kStageRows * 128;    // 32 KB weight tile image
+constexpr int kStages = 3;
+constexpr int kBarBytes = 256;
+constexpr int kSmemBytes = kARegionBytes + kStages * kStageBytes + kBarBytes + 1024;  // + alignment slack
+constexpr int kThreadsTC = 192;
+constexpr int kTmemCols = 512;
+
+struct TCParams {
+  const float* src;      // fwd: state [M, C]; bwd: gr [M, C]
+  int src_stride;        // floats per pixel row
+  int src_off;           // first channel used
+  int src_ch;            // channels used (fwd C/2, bwd C)
+  int tap_sign;          // +1: A row p reads pixel p+off(tap) (fwd); -1: p-off(tap) (bwd)
+  const __nv_bfloat16* wimg;
+  int k1_steps, k1_panels, n3p;
+  const float* bias1;    // fwd only
+  const float* bias2;
+  uint32_t* mask1;       // fwd: optional output; bwd: input
+  uint32_t* mask2;
+  float* out;            // [M, n3p]
+  int H, W;
+  long long M;
+  int tiles_per_cta_round;   // grid size (all CTAs advance together)
+  int num_rounds;
+};
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// TMA bulk copy global -> shared (this CTA only)
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+// TMA bulk copy global -> the same shared offset of every CTA in `mask`
+__device__ __forceinline__ void bulk_g2s_mc(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar,
+                                            uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::
+          "r"(dst),
+      "l"(src), "r"(bytes), "r"(bar), "h"(mask)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+
+// D[tmem] (+)= A[smem] . B[smem]^T, bf16 x bf16 -> fp32, M = 128
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::
+                   "r"(bar),
+               "h"(mask)
+               : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+// start>>4 [0,14) | LBO>>4 [16,30) = 1 | SBO>>4 [32,46) = 64 (8 rows x 128 B) | version [46,48) = 1 |
+// layout_type [61,64) = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 [4,6)=1, a/b_format BF16 [7,10)=[10,13)=1,
+// a/b K-major, n_dim = N>>3 at [17,23), m_dim = M>>4 at [24,29)
+__host__ __device__ constexpr uint32_t make_idesc(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+
+// byte offset of element (row, k) inside the 128-row A region made of 64-wide SWIZZLE_128B panels
+__device__ __forceinline__ uint32_t a_offset(int row, int k) {
+  return (uint32_t)((k >> 6) * kPanelBytes + row * 128 + ((((k & 63) >> 3) ^ (row & 7)) << 4) + ((k & 7) << 1));
+}
+
+template <int CS, bool kBwd>
+__global__ void __launch_bounds__(kThreadsTC, 1) k_nn_tc(const TCParams prm) {
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B operands need 1024-byte alignment
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + kARegionBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kARegionBytes + kStages * kStageBytes);
+  // bars[0..2] full, [3..5] empty, [6] a_ready, [7] acc_ready, [8] tmem slot
+  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[kStages]);
+  const uint32_t a_ready = smem_u32(&bars[2 * kStages]), acc_ready = smem_u32(&bars[2 * kStages + 1]);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(&bars[2 * kStages + 2]);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t cta_rank = 0;
+  if constexpr (CS > 1) cta_rank = cg::this_cluster().block_rank();
+  constexpr uint16_t kMcMask = (uint16_t)((1u << CS) - 1);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(full0 + 8 * i, 1);
+      mbar_init(empty0 + 8 * i, CS);
+    }
+    mbar_init(a_ready, 128);
+    mbar_init(acc_ready, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
+  tc_fence_before();
+  if constexpr (CS > 1) cg::this_cluster().sync(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int n_img1 = 2 * prm.k1_panels;
+  const int n_img = n_img1 + 2 * kNumPanels + kNumPanels;
+  const uint32_t img3_bytes = (uint32_t)prm.n3p * 128u;
+
+  if (warp == 0) {
+    // ===================== producer =====================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int round = 0; round < prm.num_rounds; ++round) {
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(prm.wimg);
+        for (int i = 0; i < n_img; ++i) {
+          const uint32_t bytes = (i < n_img - kNumPanels) ? (uint32_t)kStageBytes : img3_bytes;
+          mbar_wait(empty0 + 8 * stage, phase ^ 1);
+          mbar_expect_tx(full0 + 8 * stage, bytes);
+          const uint32_t dst = smem_u32(sB + stage * kStageBytes);
+          if constexpr (CS == 1) {
+            bulk_g2s(dst, src, bytes, full0 + 8 * stage);
+          } else {
+            const uint32_t part = bytes / CS;
+            bulk_g2s_mc(dst + cta_rank * part, src + cta_rank * part, part, full0 + 8 * stage, kMcMask);
+          }
+          src += bytes;
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, a_phase = 0;
+      const uint32_t a_base = smem_u32(sA);
+      constexpr uint32_t idesc256 = make_idesc(256);
+      const uint32_t idesc3 = make_idesc(prm.n3p);
+      for (int round = 0; round < prm.num_rounds; ++round) {
+        for (int gemm = 0; gemm < 3; ++gemm) {
+          mbar_wait(a_ready, a_phase);
+          a_phase ^= 1;
+          tc_fence_after();
+          const int halves = gemm < 2 ? 2 : 1;
+          const int panels = gemm == 0 ? prm.k1_panels : kNumPanels;
+          const uint32_t idesc = gemm < 2 ? idesc256 : idesc3;
+          for (int half = 0; half < halves; ++half) {
+            const uint32_t d_tmem = tmem_base + (uint32_t)(half * 256);
+            for (int kp = 0; kp < panels; ++kp) {
+              mbar_wait(full0 + 8 * stage, phase);
+              tc_fence_after();
+              const int steps = gemm == 0 ? min(4, prm.k1_steps - 4 * kp) : 4;
+              const uint64_t da = make_desc(a_base + kp * kPanelBytes);
+              const uint64_t db = make_desc(smem_u32(sB + stage * kStageBytes));
+              for (int k = 0; k < steps; ++k) {
+                // advance 16 bf16 = 32 bytes along K inside the swizzled panel: +2 in the >>4 address field
+                umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kp | k) != 0);
+              }
+              if constexpr (CS == 1) umma_commit(empty0 + 8 * stage);
+              else umma_commit_mc(empty0 + 8 * stage, kMcMask);
+              if (++stage == kStages) { stage = 0; phase ^= 1; }
+            }
+          }
+          umma_commit(acc_ready);
+        }
+      }
+    }
+  } else {
+    // ===================== workers: operand build + epilogues =====================
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    uint32_t acc_phase = 0;
+    const int K1h = 9 * prm.src_ch;
+    const int k1_pad = prm.k1_steps * 16;
+    for (int round = 0; round < prm.num_rounds; ++round) {
+      const long long tile = (long long)round * prm.tiles_per_cta_round + blockIdx.x;
+      const long long p = tile * kTileM + row;
+      const bool valid = p < prm.M;
+      // ---- stage-1 operand: split-bf16 im2col row
+      {
+        int w = 0, h = 0;
+        if (valid) { w = (int)(p % prm.W); h = (int)((p / prm.W) % prm.H); }
+        for (int tap = 0; tap < 9; ++tap) {
+          const int dy = (tap / 3 - 1) * prm.tap_sign, dx = (tap % 3 - 1) * prm.tap_sign;
+          const int hh = h + dy, ww = w + dx;
+          const bool ok = valid && hh >= 0 && hh < prm.H && ww >= 0 && ww < prm.W;
+          const float* s = prm.src + (p + (long long)dy * prm.W + dx) * prm.src_stride + prm.src_off;
+          for (int ci = 0; ci < prm.src_ch; ++ci) {
+            const float v = ok ? __ldg(s + ci) : 0.f;
+            const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+            const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+            const int k = tap * prm.src_ch + ci;
+            *reinterpret_cast<__nv_bfloat16*>(sA + a_offset(row, k)) = hi;
+            *reinterpret_cast<__nv_bfloat16*>(sA + a_offset(row, K1h + k)) = lo;
+          }
+        }
+        for (int k = 2 * K1h; k < k1_pad; ++k)
+          *reinterpret_cast<__nv_bfloat16*>(sA + a_offset(row, k)) = __float2bfloat16_rn(0.f);
+      }
+      fence_proxy_async();
+      mbar_arrive(a_ready);
+
+      // ---- epilogues of stage 1 and stage 2: TMEM -> (bias, relu | mask) -> bf16 -> swizzled smem
+      for (int gemm = 0; gemm < 2; ++gemm) {
+        mbar_wait(acc_ready, acc_phase);
+        acc_phase ^= 1;
+        tc_fence_after();
+        const float* bias = gemm == 0 ? prm.bias1 : prm.bias2;
+        // forward: stage 1 -> mask1, stage 2 -> mask2; backward: stage 1 applies mask2, stage 2 mask1
+        uint32_t* mask = kBwd ? (gemm == 0 ? prm.mask2 : prm.mask1) : (gemm == 0 ? prm.mask1 : prm.mask2);
+#pragma unroll 1
+        for (int j = 0; j < kF / 32; ++j) {
+          uint32_t v[32];
+          tmem_ld32(t_lane + (uint32_t)(j * 32), v);
+          tmem_ld_wait();
+          float f[32];
+          if constexpr (!kBwd) {
+            uint32_t bits = 0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + j * 32) + q);
+              f[4 * q + 0] = __uint_as_float(v[4 * q + 0]) + b4.x;
+              f[4 * q + 1] = __uint_as_float(v[4 * q + 1]) + b4.y;
+              f[4 * q + 2] = __uint_as_float(v[4 * q + 2]) + b4.z;
+              f[4 * q + 3] = __uint_as_float(v[4 * q + 3]) + b4.w;
+            }
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              bits |= (f[c] > 0.f ? 1u : 0u) << c;
+              f[c] = fmaxf(f[c], 0.f);
+            }
+            if (mask != nullptr && valid) mask[p * (kF / 32) + j] = bits;
+          } else {
+            const uint32_t bits = valid ? mask[p * (kF / 32) + j] : 0u;
+#pragma unroll
+            for (int c = 0; c < 32; ++c) f[c] = ((bits >> c) & 1u) ? __uint_as_float(v[c]) : 0.f;
+          }
+          // 32 columns = 4 chunks of 8 bf16 (16 B) inside panel j/2
+          uint8_t* base = sA + (j >> 1) * kPanelBytes + row * 128;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int chunk = (j & 1) * 4 + q;
+            uint4 pk;
+            pk.x = pack_bf16(f[8 * q + 0], f[8 * q + 1]);
+            pk.y = pack_bf16(f[8 * q + 2], f[8 * q + 3]);
+            pk.z = pack_bf16(f[8 * q + 4], f[8 * q + 5]);
+            pk.w = pack_bf16(f[8 * q + 6], f[8 * q + 7]);
+            *reinterpret_cast<uint4*>(base + ((chunk ^ (row & 7)) << 4)) = pk;
+          }
+        }
+        tc_fence_before();
+        fence_proxy_async();
+        mbar_arrive(a_ready);
+      }
+
+      // ---- epilogue of stage 3: TMEM -> global fp32 G[p][0..n3p)
+      mbar_wait(acc_ready, acc_phase);
+      acc_phase ^= 1;
+      tc_fence_after();
+      for (int j = 0; j < prm.n3p / 16; ++j) {
+        uint32_t v[16];
+        tmem_ld16(t_lane + (uint32_t)(j * 16), v);
+        tmem_ld_wait();
+        if (valid) {
+          float4* o = reinterpret_cast<float4*>(prm.out + p * prm.n3p + j * 16);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            o[q] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
+                               __uint_as_float(v[4 * q + 3]));
+        }
+      }
+      tc_fence_before();
+    }
+  }
+
+  // ---- teardown
+  tc_fence_before();
+  if constexpr (CS > 1) cg::this_cluster().sync(); else __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// r[p][c] = c3[c] + sum_{tap in bounds} (G[p+off(tap)][tap*C+c] + const3[tap][c])
+__global__ void __launch_bounds__(256) k_gather_fwd(const float* __restrict__ G, const float* __restrict__ const3,
+                                                    const float* __restrict__ c3, float* __restrict__ r, int H, int W,
+                                                    int C, int n3p, long long total) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = idx % C;
+  const long long p = idx / C;
+  const int w = p % W, h = (p / W) % H;
+  float acc = c3[c];
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+    const int hh = h + dy, ww = w + dx;
+    if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
+    acc += G[(p + (long long)dy * W + dx) * n3p + tap * C + c] + const3[tap * C + c];
+  }
+  r[idx] = acc;
+}
+
+// gxb[p][ci] = sum_{tap: p-off in bounds} G'[p-off(tap)][tap*Ch+ci]
+__global__ void __launch_bounds__(256) k_gather_bwd(const float* __restrict__ G, float* __restrict__ gxb, int H, int W,
+                                                    int Ch, int n3p, long long total) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = idx % Ch;
+  const long long p = idx / Ch;
+  const int w = p % W, h = (p / W) % H;
+  float acc = 0.f;
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+    const int hh = h - dy, ww = w - dx;
+    if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
+    acc += G[(p - (long long)dy * W - dx) * n3p + tap * Ch + c];
+  }
+  gxb[idx] = acc;
+}
+
+int g_cluster = 1;
+int g_num_sms = 0;
+
+inline int pad16(int n) { return (n + 15) / 16 * 16; }
+
+// ------------------------------------------------------------------ host: weight tile images
+// Writes one image of `rows` rows x 64 k (bf16, SWIZZLE_128B K-major) for rows n0.., k0..
+template <typename Fn>
+void write_image(std::vector<__nv_bfloat16>& dst, int rows, int n0, int n_valid, int k0, int k_valid, Fn&& get) {
+  const size_t base = dst.size();
+  dst.resize(base + (size_t)rows * 64, __float2bfloat16(0.f));
+  for (int r = 0; r < rows; ++r) {
+    for (int k = 0; k < 64; ++k) {
+      float v = 0.f;
+      if (r < n_valid && k < k_valid) v = get(n0 + r, k0 + k);
+      const size_t off = (size_t)r * 64 + (size_t)((((k >> 3) ^ (r & 7)) << 3) + (k & 7));
+      dst[base + off] = __float2bfloat16(v);
+    }
+  }
+}
+
+template <typename F1, typename F2, typename F3>
+void build_stage_set(TCStageSet& set, int K1, int N3, F1&& b1, F2&& b2, F3&& b3) {
+  set.k1_steps = (K1 + 15) / 16;
+  set.k1_panels = (K1 + 63) / 64;
+  set.n3p = pad16(N3);
+  ASEP_CHECK(set.k1_panels <= kNumPanels && set.n3p <= 256, ASEP_ERR_UNSUPPORTED,
+             "coupling network shape outside the tcgen05 kernel (K1=%d, N3=%d)", K1, N3);
+  std::vector<__nv_bfloat16> img;
+  for (int half = 0; half < 2; ++half)
+    for (int kp = 0; kp < set.k1_panels; ++kp)
+      write_image(img, kStageRows, half * 256, 256, kp * 64, std::min(64, K1 - kp * 64), b1);
+  for (int half = 0; half < 2; ++half)
+    for (int kp = 0; kp < kNumPanels; ++kp) write_image(img, kStageRows, half * 256, 256, kp * 64, 64, b2);
+  for (int kp = 0; kp < kNumPanels; ++kp) write_image(img, set.n3p, 0, N3, kp * 64, 64, b3);
+  set.bytes = img.size() * sizeof(__nv_bfloat16);
+  CUDA_CHECK(cudaMalloc(&set.img, set.bytes));
+  CUDA_CHECK(cudaMemcpy(set.img, img.data(), set.bytes, cudaMemcpyHostToDevice));
+}
+
+float* upload(const std::vector<float>& v) {
+  float* d = nullptr;
+  CUDA_CHECK(cudaMalloc(&d, v.size() * sizeof(float)));
+  CUDA_CHECK(cudaMemcpy(d, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice));
+  return d;
+}
+
+template <int CS, bool kBwd>
+void launch_tc(const TCParams& prm, int grid, cudaStream_t s) {
+  auto kern = k_nn_tc<CS, kBwd>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreadsTC);
+  cfg.dynamicSmemBytes = kSmemBytes;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, prm));
+  ASEP_LAUNCH_CHECK();
+}
+
+template <bool kBwd>
+void run_tc(TCParams prm, cudaStream_t s) {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    CUDA_CHECK(cudaGetDevice(&dev));
+    CUDA_CHECK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int cs = g_cluster;
+  const long long tiles = (prm.M + kTileM - 1) / kTileM;
+  int grid = (int)std::min<long long>(tiles, g_num_sms);
+  grid = (grid + cs - 1) / cs * cs;          // whole clusters; surplus CTAs run masked tiles
+  if (grid > g_num_sms) grid = g_num_sms / cs * cs;
+  prm.tiles_per_cta_round = grid;
+  prm.num_rounds = (int)((tiles + grid - 1) / grid);
+  switch (cs) {
+    case 1: launch_tc<1, kBwd>(prm, grid, s); break;
+    case 2: launch_tc<2, kBwd>(prm, grid, s); break;
+    case 4: launch_tc<4, kBwd>(prm, grid, s); break;
+    default: throw Error(ASEP_ERR_BAD_ARG, strfmt("cluster size %d not built (1, 2, 4)", cs));
+  }
+}
+
+}  // namespace
+
+void nn_tc_set_cluster(int cluster_size) {
+  ASEP_CHECK(cluster_size == 1 || cluster_size == 2 || cluster_size == 4, ASEP_ERR_BAD_ARG,
+             "cluster size must be 1, 2 or 4");
+  g_cluster = cluster_size;
+}
+int nn_tc_get_cluster() { return g_cluster; }
+
+size_t nn_tc_g_floats(long long M, int C) { return (size_t)M * (size_t)pad16(9 * C); }
+
+void nn_tc_prepare(NNWeightsTC& w, const float* k1, const float* c1, const float* g1, const float* b1,
+                   const float* k2, const float* c2, const float* g2, const float* b2, const float* k3,
+                   const float* c3, int C, int F) {
+  ASEP_CHECK(F == kF, ASEP_ERR_UNSUPPORTED, "the tcgen05 coupling kernel is built for n_filters = %d (got %d)", kF, F);
+  nn_tc_release(w);
+  const int Ch = C / 2;
+  // ---------------- forward
+  {
+    const int K1h = 9 * Ch;
+    auto f1 = [&](int n, int k) { return k1[(size_t)(k % K1h) * F + n]; };              // K1[tap][ci][n]; [hi | lo]
+    auto f2 = [&](int n, int k) { return g1[k] * k2[(size_t)k * F + n]; };              // diag(g1') K2
+    auto f3 = [&](int n, int k) {                                                       // n = tap*C + c
+      const int tap = n / C, c = n % C;
+      return g2[k] * k3[((size_t)tap * F + k) * C + c];
+    };
+    build_stage_set(w.fwd, 2 * K1h, 9 * C, f1, f2, f3);
+  }
+  // ---------------- backward (data gradient)
+  {
+    const int K1h = 9 * C;
+    auto f1 = [&](int n, int k) {                                                       // k = tap*C + c ; [hi | lo]
+      const int kk = k % K1h, tap = kk / C, c = kk % C;
+      return g2[n] * k3[((size_t)tap * F + n) * C + c];
+    };
+    auto f2 = [&](int n, int k) { return g1[n] * k2[(size_t)n * F + k]; };              // diag(g1') K2^T
+    auto f3 = [&](int n, int k) { return k1[(size_t)n * F + k]; };                      // n = tap*Ch + ci
+    build_stage_set(w.bwd, 2 * K1h, 9 * Ch, f1, f2, f3);
+  }
+  std::vector<float> bias1(c1, c1 + F), bias2(F), const3((size_t)9 * C), vc3(c3, c3 + C);
+  for (int n = 0; n < F; ++n) {
+    double a = c2[n];
+    for (int k = 0; k < F; ++k) a += (double)b1[k] * (double)k2[(size_t)k * F + n];
+    bias2[n] = (float)a;
+  }
+  for (int tap = 0; tap < 9; ++tap)
+    for (int c = 0; c < C; ++c) {
+      double a = 0.0;
+      for (int k = 0; k < F; ++k) a += (double)b2[k] * (double)k3[((size_t)tap * F + k) * C + c];
+      const3[(size_t)tap * C + c] = (float)a;
+    }
+  w.bias1 = upload(bias1);
+  w.bias2 = upload(bias2);
+  w.const3 = upload(const3);
+  w.c3 = upload(vc3);
+}
+
+void nn_tc_release(NNWeightsTC& w) {
+  if (w.fwd.img) cudaFree(w.fwd.img);
+  if (w.bwd.img) cudaFree(w.bwd.img);
+  if (w.bias1) cudaFree(w.bias1);
+  if (w.bias2) cudaFree(w.bias2);
+  if (w.const3) cudaFree(w.const3);
+  if (w.c3) cudaFree(w.c3);
+  w = NNWeightsTC{};
+}
+
+void nn_tc_forward(const NNWeightsTC& w, const NNScratchTC& sc, const float* state, float* r, uint32_t* mask1,
+                   uint32_t* mask2, int N, int H, int W, int C, cudaStream_t s) {
+  const long long M = (long long)N * H * W;
+  if (M == 0) return;
+  TCParams prm{};
+  prm.src = state; prm.src_stride = C; prm.src_off = C / 2; prm.src_ch = C / 2; prm.tap_sign = 1;
+  prm.wimg = w.fwd.img; prm.k1_steps = w.fwd.k1_steps; prm.k1_panels = w.fwd.k1_panels; prm.n3p = w.fwd.n3p;
+  prm.bias1 = w.bias1; prm.bias2 = w.bias2; prm.mask1 = mask1; prm.mask2 = mask2;
+  prm.out = sc.G; prm.H = H; prm.W = W; prm.M = M;
+  run_tc<false>(prm, s);
+  const long long total = M * C;
+  k_gather_fwd<<<cdiv(total, 256), 256, 0, s>>>(sc.G, w.const3, w.c3, r, H, W, C, w.fwd.n3p, total);
+  ASEP_LAUNCH_CHECK();
+}
+
+void nn_tc_backward(const NNWeightsTC& w, const NNScratchTC& sc, const float* gr, const uint32_t* mask1,
+                    const uint32_t* mask2, float* gxb, int N, int H, int W, int C, cudaStream_t s) {
+  const long long M = (long long)N * H * W;
+  if (M == 0) return;
+  TCParams prm{};
+  prm.src = gr; prm.src_stride = C; prm.src_off = 0; prm.src_ch = C; prm.tap_sign = -1;
+  prm.wimg = w.bwd.img; prm.k1_steps = w.bwd.k1_steps; prm.k1_panels = w.bwd.k1_panels; prm.n3p = w.bwd.n3p;
+  prm.bias1 = nullptr; prm.bias2 = nullptr;
+  prm.mask1 = const_cast<uint32_t*>(mask1); prm.mask2 = const_cast<uint32_t*>(mask2);
+  prm.out = sc.G; prm.H = H; prm.W = W; prm.M = M;
+  run_tc<true>(prm, s);
+  const long long total = M * (C / 2);
+  k_gather_bwd<<<cdiv(total, 256), 256, 0, s>>>(sc.G, gxb, H, W, C / 2, w.bwd.n3p, total);
+  ASEP_LAUNCH_CHECK();
+}
+
+}  // namespace asep

@@ -1,0 +1,52 @@
+// tcgen05 / TMEM / TMA implementation of ShiftAndLogScaleConvNet and of its data gradient
+// (ASEP_PREC_BF16).  See nn_tc.cu for the kernel design.
+#pragma once
+#include <vector>
+#include "common.cuh"
+
+namespace asep {
+
+constexpr int kTcF = 512;   // hidden width the tcgen05 kernel is built for (configs/melspec_glow.yml:10)
+
+struct TCStageSet {
+  __nv_bfloat16* img = nullptr;  // weight tile images in consumption order (device)
+  int k1_steps = 0;              // K=16 MMA steps of stage 1
+  int k1_panels = 0;             // 64-wide K panels of stage 1
+  int n3p = 0;                   // padded N of stage 3 (multiple of 16)
+  size_t bytes = 0;
+};
+
+struct NNWeightsTC {
+  TCStageSet fwd, bwd;
+  float* bias1 = nullptr;   // c1                                   [F]
+  float* bias2 = nullptr;   // c2 + b1' . K2                        [F]
+  float* const3 = nullptr;  // [9][C]  sum_k b2'[k] K3[tap][k][c]   (border-aware BN offset of conv3)
+  float* c3 = nullptr;      // [C]
+};
+
+struct NNScratchTC {
+  float* G = nullptr;        // [M, n3p] fp32 per-tap partial outputs of the small-N stage
+  uint32_t* mask1 = nullptr; // [M, F/32] relu masks of p1 (scratch for one step)
+  uint32_t* mask2 = nullptr;
+};
+
+// Host-side preparation: builds the bf16 SWIZZLE_128B tile images for both directions.
+// k1 [3,3,Ch,F], k2 [F,F] (in,out), k3 [3,3,F,C]; g*/b* folded BatchNorm scale/offset.
+void nn_tc_prepare(NNWeightsTC& w, const float* k1, const float* c1, const float* g1, const float* b1,
+                   const float* k2, const float* c2, const float* g2, const float* b2, const float* k3,
+                   const float* c3, int C, int F);
+void nn_tc_release(NNWeightsTC& w);
+
+// state [N,H,W,C] (network input = channels C/2..C) -> r [M,C] (conv3 output incl. bias).
+// mask1/mask2 (may be NULL) receive the ReLU masks needed by the backward pass.
+void nn_tc_forward(const NNWeightsTC& w, const NNScratchTC& sc, const float* state, float* r, uint32_t* mask1,
+                   uint32_t* mask2, int N, int H, int W, int C, cudaStream_t s);
+// gr [M,C] -> gxb [M,C/2] using the masks written by nn_tc_forward on the same input.
+void nn_tc_backward(const NNWeightsTC& w, const NNScratchTC& sc, const float* gr, const uint32_t* mask1,
+                    const uint32_t* mask2, float* gxb, int N, int H, int W, int C, cudaStream_t s);
+
+size_t nn_tc_g_floats(long long M, int C);   // capacity needed for NNScratchTC::G
+void nn_tc_set_cluster(int cluster_size);    // 1, 2 or 4 CTAs sharing each weight tile by TMA multicast
+int nn_tc_get_cluster();
+
+}  // namespace asep

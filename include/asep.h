@@ -1,0 +1,144 @@
+/*
+ * asep.h -- C ABI of libasep.so, the B200 (sm_100a) implementation of the
+ * SamArgt/AudioSourceSep separation hot path.
+ *
+ * This is the drop-in boundary: plain C, no torch / CUDA types in the signatures
+ * (a stream crosses as `void*` holding a cudaStream_t; NULL = the legacy default stream).
+ * Tensors cross as DLPack `DLTensor*` (asep_dlpack.h): float32, row-major contiguous NHWC
+ * unless stated, resident on the CUDA device the handle was created on; `set_param`
+ * additionally accepts host (kDLCPU) tensors.  The caller owns every tensor it passes;
+ * the library never retains a pointer beyond the call (parameters are copied).
+ *
+ * Every function returns 0 on success or a negative asep_status; asep_last_error() holds
+ * the message (thread-local).  Handles are not thread-safe.
+ *
+ * Each entry point cites the reference interface it replaces (path:line under the
+ * reference repository SamArgt/AudioSourceSep).
+ */
+#ifndef ASEP_H_
+#define ASEP_H_
+
+#include <stdint.h>
+#include "asep_dlpack.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ASEP_ABI_VERSION 1
+
+typedef enum {
+  ASEP_OK = 0,
+  ASEP_ERR_BAD_ARG = -1,     /* NULL pointer, unknown name, bad enum            */
+  ASEP_ERR_BAD_SHAPE = -2,   /* shape contract violated (reference asserts)     */
+  ASEP_ERR_BAD_DTYPE = -3,   /* not float32 (or int32 for sigma_idx)            */
+  ASEP_ERR_BAD_LAYOUT = -4,  /* non-contiguous / misaligned                     */
+  ASEP_ERR_BAD_DEVICE = -5,  /* tensor not on the handle's CUDA device          */
+  ASEP_ERR_CUDA = -6,        /* CUDA runtime / driver error                     */
+  ASEP_ERR_NAN = -7,         /* NaN detected by a --debug style check           */
+  ASEP_ERR_STATE = -8,       /* call order violated (e.g. prepare() missing)    */
+  ASEP_ERR_UNSUPPORTED = -9  /* configuration outside the built kernels         */
+} asep_status;
+
+/* Arithmetic the coupling / score network contractions run in. */
+typedef enum {
+  ASEP_PREC_FP32 = 0, /* CUDA-core fp32 kernels: bit-level "exact" mode used as the on-device checker   */
+  ASEP_PREC_BF16 = 1  /* tcgen05 (UMMA) bf16 x bf16 -> fp32 TMEM accumulation: the production path      */
+} asep_precision;
+
+const char* asep_last_error(void);
+int asep_abi_version(void);
+/* Selects the device, checks it is sm_100, creates the library context. */
+int asep_init(int device);
+/* Number of kernels this library has launched since asep_init (all handles). */
+int64_t asep_launch_count(void);
+
+/* ------------------------------------------------------------------ Glow prior
+ * Replaces flow_models/flow_builder.py:60-146 (build_glow) and the TFP distribution it
+ * returns (log_prob / sample), plus run_basis_sep.py:73-79 (compute_grad_logprob). */
+typedef struct {
+  int32_t H, W, C;      /* data_shape, flow_builder.py:60                                  */
+  int32_t L, K;         /* blocks, steps per block (configs/melspec_glow.yml:8-9)          */
+  int32_t n_filters;    /* hidden width of ShiftAndLogScaleConvNet (flow_tfk_layers.py:46) */
+  int32_t learntop;     /* learnable diagonal-Gaussian prior, flow_builder.py:130-141      */
+  float minval, maxval; /* SpecPreprocessing(minval, maxval, use_logit=False)              */
+} asep_glow_cfg;
+
+typedef struct asep_glow_s* asep_glow_t;
+
+int asep_glow_create(const asep_glow_cfg* cfg, asep_glow_t* out);
+int asep_glow_destroy(asep_glow_t h);
+/* Parameter names: see audiosourcesep_b200/weights.py ("b{b}/s{k}/actnorm/log_scale", ...).
+ * Mirrors tf.Variable assignment / checkpoint restore (train_utils.py:62-75). */
+int asep_glow_set_param(asep_glow_t h, const char* name, const DLTensor* value);
+int asep_glow_get_param(asep_glow_t h, const char* name, DLTensor* out);
+/* Derives the per-step constants (W, W^-1 in double, folded bf16 GEMM operands, constant
+ * log-det terms).  Must be called after parameters change and before any compute call. */
+int asep_glow_prepare(asep_glow_t h, int precision);
+/* ActNorm data-dependent init incl. the raw-minibatch quirk of the 3/4-block classes
+ * (flow_tfp_bijectors.py:222-240, flow_glow.py:44-49,156-174).  minibatch: [N,H,W,C] raw data. */
+int asep_glow_init_actnorm(asep_glow_t h, const DLTensor* minibatch, void* stream);
+/* Chain([glow, SpecPreprocessing]).forward + forward_log_det_jacobian (flow_builder.py:127,
+ * flow_glow.py:176-209).  x [N,H,W,C] -> z [N,H/2^L,W/2^L,C*4^L], fldj [N]. */
+int asep_glow_forward(asep_glow_t h, const DLTensor* x, DLTensor* z, DLTensor* fldj, void* stream);
+/* Chain.inverse (flow_glow.py:187-196): z -> x. */
+int asep_glow_inverse(asep_glow_t h, const DLTensor* z, DLTensor* x, void* stream);
+/* TransformedDistribution.log_prob (flow_builder.py:140-141): x -> logp [N]. */
+int asep_glow_log_prob(asep_glow_t h, const DLTensor* x, DLTensor* logp, void* stream);
+/* compute_grad_logprob (run_basis_sep.py:73-79): grad [N,H,W,C]; logp may be NULL. */
+int asep_glow_grad_log_prob(asep_glow_t h, const DLTensor* x, DLTensor* grad, DLTensor* logp, void* stream);
+/* prior.sample -> Chain.inverse with the standard-normal draw injected: eps [N,latent]. */
+int asep_glow_sample(asep_glow_t h, const DLTensor* eps, DLTensor* x, void* stream);
+
+/* ------------------------------------------------------------------ single bijectors
+ * Stateless kernels behind the reference's Bijector classes, so each can be unit-tested the
+ * way unittest_flow_models.py:25-51 does.  `inverse` != 0 selects _inverse. */
+/* ActNorm (flow_tfp_bijectors.py:242-253): log_scale, shift [C] device tensors. */
+int asep_actnorm(const DLTensor* x, const DLTensor* log_scale, const DLTensor* shift, DLTensor* y,
+                 int inverse, void* stream);
+/* Invertible1x1Conv (flow_tfp_bijectors.py:299-317): w [C,C] is W (forward) or W^-1 (inverse). */
+int asep_inv1x1(const DLTensor* x, const DLTensor* w, DLTensor* y, void* stream);
+/* AffineCouplingLayerSplit given the raw NN output r=[raw_log_s | t] (flow_tfp_bijectors.py:134-153);
+ * logdet [N] (float32) is overwritten with sum tanh(raw) (forward) / its negative (inverse). */
+int asep_coupling(const DLTensor* x, const DLTensor* r, DLTensor* y, DLTensor* logdet, int inverse, void* stream);
+/* Squeeze (flow_tfp_bijectors.py:170-180). */
+int asep_squeeze(const DLTensor* x, DLTensor* y, int inverse, void* stream);
+/* ShiftAndLogScaleConvNet of step (block,step) of a prepared model (flow_tfk_layers.py:73-84):
+ * state [N,Hb,Wb,Cb] (the second half of the channels is the network input) -> r [N,Hb,Wb,Cb]
+ * = conv3 output before tanh/split. */
+int asep_glow_coupling_nn(asep_glow_t h, int block, int step, const DLTensor* state, DLTensor* r, void* stream);
+/* Data gradient of the same network: gr [N,Hb,Wb,Cb] -> gxb [N,Hb,Wb,Cb/2]. */
+int asep_glow_coupling_nn_backward(asep_glow_t h, int block, int step, const DLTensor* state, const DLTensor* gr,
+                                   DLTensor* gxb, void* stream);
+
+/* ------------------------------------------------------------------ BASIS Langevin
+ * One fused update of run_basis_sep.py:163-181 for both sources (dB mixing, :131-147):
+ *   x_k <- x_k + eta*(s_k + lambda*softmax_k*(mixed - g(x1,x2))) + noise_scale*n_k
+ * x1,x2 are updated in place from the OLD states.  n1/n2: injected standard normals, or NULL
+ * for in-kernel Philox4x32-10 + Box-Muller keyed by (seed, step, global element index).
+ * elem_offset = global index of element 0 (segment sharding keeps draws identical for any
+ * number of GPUs).  nan_count: optional int32[1] device counter incremented per NaN. */
+int asep_langevin_step(DLTensor* x1, DLTensor* x2, const DLTensor* s1, const DLTensor* s2, const DLTensor* mixed,
+                       const DLTensor* n1, const DLTensor* n2, float eta, float lambda, float noise_scale,
+                       uint64_t seed, uint64_t step, uint64_t elem_offset, DLTensor* nan_count, void* stream);
+/* Mixing function g and its gradient (run_basis_sep.py:131-147), for tests. */
+int asep_mixing_db(const DLTensor* x1, const DLTensor* x2, DLTensor* g, DLTensor* w1, DLTensor* w2, void* stream);
+/* Standard normal draws of the in-kernel generator (for tests / reproducibility audits). */
+int asep_philox_normal(DLTensor* out, uint64_t seed, uint64_t step, uint64_t stream_id, uint64_t elem_offset,
+                       void* stream);
+/* T inner steps at one noise level with two Glow priors (run_basis_sep.py:152-181, model_type
+ * 'glow').  noise1/noise2: NULL or [T,N,H,W,C] injected draws; per_step: NULL or
+ * [T,2,N,H,W,C] state dump for parity tests. */
+int asep_basis_glow_inner(asep_glow_t m1, asep_glow_t m2, const DLTensor* mixed, DLTensor* x1, DLTensor* x2,
+                          int T, float eta, float lambda, float noise_scale, const DLTensor* noise1,
+                          const DLTensor* noise2, uint64_t seed, uint64_t step0, uint64_t elem_offset,
+                          DLTensor* per_step, DLTensor* nan_count, void* stream);
+
+/* Number of CTAs (1, 2 or 4) of a thread-block cluster that share each weight tile of the tcgen05 coupling
+ * kernel through TMA multicast.  Tuning knob; results are identical for every value. */
+int asep_tc_set_cluster(int cluster_size);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ASEP_H_ */

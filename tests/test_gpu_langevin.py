@@ -1,0 +1,115 @@
+"""GPU parity tests of the fused Langevin update and the BASIS inner loop vs the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from audiosourcesep_b200 import GlowConfig, synthetic
+from audiosourcesep_b200.weights import init_glow_params
+from oracle import basis_oracle as bo
+from oracle.glow_oracle import GlowOracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def test_mixing_db_matches_oracle():
+    from audiosourcesep_b200 import ops
+    g, grad_g = bo.mixing_process("melspec", "dB")
+    rng = np.random.default_rng(0)
+    a = rng.uniform(-0.5, 1.5, (3, 8, 4, 1)).astype(np.float32)
+    b = rng.uniform(-0.5, 1.5, (3, 8, 4, 1)).astype(np.float32)
+    gg, w1, w2 = ops.mixing_db(torch.as_tensor(a), torch.as_tensor(b))
+    ga, gb = grad_g(a, b)
+    np.testing.assert_allclose(_np(gg), g(a, b), rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(_np(w1), ga, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(_np(w2), gb, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("sigma_idx", [0, 4, 9])
+def test_langevin_step_matches_oracle_with_injected_noise(sigma_idx):
+    from audiosourcesep_b200 import ops
+    sig = bo.get_sigmas(1.0, 0.01, 10, "logarithmic")
+    eta, lam, ns = bo.step_constants(sig, sigma_idx)
+    g, grad_g = bo.mixing_process("melspec", "dB")
+    rng = np.random.default_rng(sigma_idx)
+    shp = (4, 96, 64, 1)
+    x1, x2, mixed = (rng.uniform(0, 1, shp).astype(np.float32) for _ in range(3))
+    s1, s2, n1, n2 = (rng.standard_normal(shp).astype(np.float32) for _ in range(4))
+    y1, y2 = bo.langevin_update(x1, x2, s1, s2, mixed, n1, n2, eta, lam, ns, g, grad_g)
+    t1, t2 = torch.as_tensor(x1).cuda(), torch.as_tensor(x2).cuda()
+    nan = torch.zeros(1, dtype=torch.int32, device="cuda")
+    ops.langevin_step(t1, t2, torch.as_tensor(s1), torch.as_tensor(s2), torch.as_tensor(mixed), float(eta), float(lam),
+                      float(ns), n1=torch.as_tensor(n1), n2=torch.as_tensor(n2), nan_count=nan)
+    for got, want in ((t1, y1), (t2, y2)):
+        rel = np.linalg.norm(_np(got) - want) / np.linalg.norm(want)
+        assert rel <= 1e-5, rel                      # gate: per-step state relative error <= 1e-3
+    assert nan.item() == 0
+    # NaN flag (the reference's --debug asserts, run_basis_sep.py:183-191)
+    bad = torch.full(shp, float("nan"), device="cuda")
+    ops.langevin_step(t1, t2, bad, torch.as_tensor(s2), torch.as_tensor(mixed), float(eta), float(lam), float(ns),
+                      n1=torch.as_tensor(n1), n2=torch.as_tensor(n2), nan_count=nan)
+    assert nan.item() > 0
+
+
+def test_philox_noise_is_standard_normal_and_shard_invariant():
+    from audiosourcesep_b200 import ops
+    n = 30 * 6144
+    full = ops.philox_normal((n,), seed=7, step=3, stream_id=1)
+    v = _np(full).astype(np.float64)
+    assert abs(v.mean()) < 0.01 and abs(v.std() - 1.0) < 0.01
+    assert abs(((v - v.mean()) ** 3).mean()) < 0.03 and abs((v ** 4).mean() - 3.0) < 0.08
+    # sharding segments over ranks gives the same draws (elem_offset = global index of the shard)
+    half = n // 2
+    lo = ops.philox_normal((half,), seed=7, step=3, stream_id=1, elem_offset=0)
+    hi = ops.philox_normal((n - half,), seed=7, step=3, stream_id=1, elem_offset=half)
+    assert torch.equal(torch.cat([lo, hi]), full)
+    other = ops.philox_normal((n,), seed=7, step=4, stream_id=1)
+    assert abs(np.corrcoef(v, _np(other))[0, 1]) < 0.01
+    assert not torch.equal(ops.philox_normal((n,), seed=7, step=3, stream_id=2), full)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_basis_glow_inner_loop_vs_oracle(precision):
+    """Three Langevin steps with two Glow priors and injected noise: per-step state error <= 1e-3."""
+    from audiosourcesep_b200 import ops, _lib
+    from audiosourcesep_b200.glow import Glow
+    # BASIS states are normalised [0,1]: SpecPreprocessing(minval=0, maxval=1)
+    cfg = GlowConfig(H=96, W=64, C=1, L=3, K=3, n_filters=512, minval=0.0, maxval=1.0)
+    prec = {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16}[precision]
+    p1, p2 = init_glow_params(cfg, seed=2), init_glow_params(cfg, seed=3)
+    o1, o2 = GlowOracle(cfg, p1), GlowOracle(cfg, p2)
+    m1, m2 = Glow(cfg, p1, precision=prec), Glow(cfg, p2, precision=prec)
+    n_mixed, T = 3, 3
+    mixed, _, _ = synthetic.basis_problem(n_mixed)
+    x1, x2 = synthetic.langevin_init(n_mixed, seed=4)
+    sig = bo.get_sigmas(1.0, 0.01, 10, "logarithmic")
+    sigma_idx = 6
+    eta, lam, ns = bo.step_constants(sig, sigma_idx)
+    rng = np.random.default_rng(3)
+    noise = rng.standard_normal((T, 2, n_mixed, 96, 64, 1)).astype(np.float32)
+    steps = []
+    # oracle loop at a single noise level (basis_inner_loop)
+    g, grad_g = bo.mixing_process("melspec", "dB")
+    a, b = x1.copy(), x2.copy()
+    for t in range(T):
+        s1 = o1.grad_log_prob(a)[0].numpy().astype(np.float32)
+        s2 = o2.grad_log_prob(b)[0].numpy().astype(np.float32)
+        a, b = bo.langevin_update(a, b, s1, s2, mixed, noise[t, 0], noise[t, 1], eta, lam, ns, g, grad_g)
+        steps.append((a.copy(), b.copy()))
+    t1, t2 = torch.as_tensor(x1).cuda(), torch.as_tensor(x2).cuda()
+    dump = torch.empty((T, 2, n_mixed, 96, 64, 1), device="cuda")
+    nan = torch.zeros(1, dtype=torch.int32, device="cuda")
+    ops.basis_glow_inner(m1, m2, torch.as_tensor(mixed), t1, t2, T, float(eta), float(lam), float(ns),
+                         noise1=torch.as_tensor(noise[:, 0]), noise2=torch.as_tensor(noise[:, 1]),
+                         per_step=dump, nan_count=nan)
+    assert nan.item() == 0
+    for t in range(T):
+        for k in range(2):
+            want = steps[t][k]
+            got = _np(dump[t, k])
+            rel = np.linalg.norm(got - want) / np.linalg.norm(want)
+            assert rel <= 1e-3, (t, k, rel)
+    assert torch.equal(dump[T - 1, 0], t1) and torch.equal(dump[T - 1, 1], t2)
