@@ -68,7 +68,10 @@ void expect_shape(const TView& v, const char* what, std::initializer_list<int64_
   bool ok = v.ndim == (int)shp.size();
   int i = 0;
   if (ok)
-    for (auto s : shp) ok = ok && (s < 0 || v.shape[i++] == s);
+    for (auto s : shp) {
+      ok = ok && (s < 0 || v.shape[i] == s);
+      ++i;
+    }
   if (!ok) {
     std::string got = "[", want = "[";
     for (int j = 0; j < v.ndim; ++j) got += std::to_string(v.shape[j]) + (j + 1 < v.ndim ? "," : "");

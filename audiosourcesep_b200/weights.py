@@ -104,13 +104,25 @@ def _inv1x1_init(rng, C):
     return p, l, np.triu(u, k=1), np.log(np.abs(s)), np.sign(s)
 
 
-def init_glow_params(cfg: GlowConfig, seed: int = 2, mode: str = "perturbed") -> Dict[str, np.ndarray]:
-    """Generate a full parameter set.  ``mode`` in {'faithful', 'perturbed'}."""
+def init_glow_params(cfg: GlowConfig, seed: int = 2, mode: str = "perturbed", coupling_gain: float = None,
+                     actnorm_jitter: float = None) -> Dict[str, np.ndarray]:
+    """Generate a full parameter set.  ``mode`` in {'faithful', 'perturbed'}.
+
+    ``coupling_gain`` scales conv3 (strength of the couplings) and ``actnorm_jitter`` the ActNorm
+    parameters of the perturbed mode.  A ReLU coupling network is positively homogeneous, so strong
+    un-normalised couplings make a 120-step flow grow geometrically; the defaults are therefore
+    0.5 / 0.1 for shallow test models (K <= 8) and 0.1 / 0.03 for deep ones (checked with the
+    oracle: the melspec model stays O(1), log_prob ~ -3.5e4 nats).
+    """
     if mode not in ("faithful", "perturbed"):
         raise ValueError("mode must be 'faithful' or 'perturbed'")
     rng = np.random.Generator(np.random.PCG64(seed))
     F = cfg.n_filters
     pert = mode == "perturbed"
+    if coupling_gain is None:
+        coupling_gain = 0.5 if cfg.K <= 8 else 0.1
+    if actnorm_jitter is None:
+        actnorm_jitter = 0.1 if cfg.K <= 8 else 0.03
     out: Dict[str, np.ndarray] = {}
     for b in range(cfg.L):
         _, _, C = cfg.level_shape(b)
@@ -122,14 +134,14 @@ def init_glow_params(cfg: GlowConfig, seed: int = 2, mode: str = "perturbed") ->
                 l = l + np.tril(rng.normal(0, 0.02, (C, C)), -1)
                 u = u + np.triu(rng.normal(0, 0.02, (C, C)), 1)
                 log_s = log_s + rng.normal(0, 0.05, C)
-                out[pre + "actnorm/log_scale"] = rng.normal(0, 0.1, C)
-                out[pre + "actnorm/shift"] = rng.normal(0, 0.1, C)
+                out[pre + "actnorm/log_scale"] = rng.normal(0, actnorm_jitter, C)
+                out[pre + "actnorm/shift"] = rng.normal(0, actnorm_jitter, C)
                 out[pre + "nn/conv1/kernel"] = rng.normal(0, np.sqrt(2.0 / (9 * Ch)), (3, 3, Ch, F))
                 out[pre + "nn/conv1/bias"] = rng.normal(0, 0.1, F)
                 out[pre + "nn/conv2/kernel"] = rng.normal(0, np.sqrt(2.0 / F), (F, F))
                 out[pre + "nn/conv2/bias"] = rng.normal(0, 0.1, F)
-                out[pre + "nn/conv3/kernel"] = rng.normal(0, 0.5 / np.sqrt(9 * F), (3, 3, F, C))
-                out[pre + "nn/conv3/bias"] = rng.normal(0, 0.05, C)
+                out[pre + "nn/conv3/kernel"] = rng.normal(0, coupling_gain / np.sqrt(9 * F), (3, 3, F, C))
+                out[pre + "nn/conv3/bias"] = rng.normal(0, 0.1 * coupling_gain, C)
                 for bn in ("bn1", "bn2"):
                     out[pre + f"nn/{bn}/gamma"] = rng.normal(1.0, 0.1, F)
                     out[pre + f"nn/{bn}/beta"] = rng.normal(0.0, 0.1, F)

@@ -71,45 +71,64 @@ def test_philox_noise_is_standard_normal_and_shard_invariant():
     assert not torch.equal(ops.philox_normal((n,), seed=7, step=3, stream_id=2), full)
 
 
+@pytest.mark.parametrize("weights,sigma_idx", [("faithful", 0), ("faithful", 9), ("perturbed", 6), ("perturbed", 9)])
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
-def test_basis_glow_inner_loop_vs_oracle(precision):
-    """Three Langevin steps with two Glow priors and injected noise: per-step state error <= 1e-3."""
+def test_basis_glow_inner_loop_vs_oracle(precision, weights, sigma_idx):
+    """Langevin steps with two Glow priors and injected noise.  Gate: per-step state relative error
+    <= 1e-3 (each CUDA step starts from the oracle's previous state); the free-running drift over the
+    T steps is reported and loosely bounded.
+
+    ``faithful`` = the reference's random init (zero conv3, ActNorm initialised from a minibatch) at the
+    largest and smallest step size; ``perturbed`` = non-trivial couplings.  With perturbed random weights
+    and the largest step sizes (eta = 0.2) one update moves the state by more than its own norm and the
+    piecewise-constant ReLU gradient makes ANY two arithmetics diverge (fp32 vs fp64 already differ by
+    5e-4 per step there), so the perturbed cases use the annealed end of the schedule."""
     from audiosourcesep_b200 import ops, _lib
     from audiosourcesep_b200.glow import Glow
     # BASIS states are normalised [0,1]: SpecPreprocessing(minval=0, maxval=1) (SURVEY.md App. B)
     cfg = GlowConfig(H=96, W=64, C=1, L=3, K=3, n_filters=512, minval=0.0, maxval=1.0)
     prec = {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16}[precision]
-    p1, p2 = init_glow_params(cfg, seed=2), init_glow_params(cfg, seed=3)
+    p1, p2 = init_glow_params(cfg, seed=2, mode=weights), init_glow_params(cfg, seed=3, mode=weights)
+    if weights == "faithful":
+        p1.update(GlowOracle(cfg, p1).init_actnorm(synthetic.normalise(synthetic.mel_patches_db(8, seed=9))))
+        p2.update(GlowOracle(cfg, p2).init_actnorm(synthetic.normalise(synthetic.mel_patches_db(8, seed=10))))
     o1, o2 = GlowOracle(cfg, p1), GlowOracle(cfg, p2)
     m1, m2 = Glow(cfg, p1, precision=prec), Glow(cfg, p2, precision=prec)
     n_mixed, T = 3, 3
     mixed, _, _ = synthetic.basis_problem(n_mixed)
     x1, x2 = synthetic.langevin_init(n_mixed, seed=4)
     sig = bo.get_sigmas(1.0, 0.01, 10, "logarithmic")
-    sigma_idx = 6
     eta, lam, ns = bo.step_constants(sig, sigma_idx)
     rng = np.random.default_rng(3)
     noise = rng.standard_normal((T, 2, n_mixed, 96, 64, 1)).astype(np.float32)
-    steps = []
-    # oracle loop at a single noise level (basis_inner_loop)
     g, grad_g = bo.mixing_process("melspec", "dB")
     a, b = x1.copy(), x2.copy()
+    states = [(a.copy(), b.copy())]
     for t in range(T):
         s1 = o1.grad_log_prob(a)[0].numpy().astype(np.float32)
         s2 = o2.grad_log_prob(b)[0].numpy().astype(np.float32)
         a, b = bo.langevin_update(a, b, s1, s2, mixed, noise[t, 0], noise[t, 1], eta, lam, ns, g, grad_g)
-        steps.append((a.copy(), b.copy()))
+        states.append((a.copy(), b.copy()))
+    nan = torch.zeros(1, dtype=torch.int32, device="cuda")
+    worst = 0.0
+    for t in range(T):     # synchronised: one CUDA step from the oracle's state
+        t1, t2 = torch.as_tensor(states[t][0]).cuda(), torch.as_tensor(states[t][1]).cuda()
+        ops.basis_glow_inner(m1, m2, torch.as_tensor(mixed), t1, t2, 1, float(eta), float(lam), float(ns),
+                             noise1=torch.as_tensor(noise[t:t + 1, 0]), noise2=torch.as_tensor(noise[t:t + 1, 1]),
+                             nan_count=nan)
+        for got, want in ((t1, states[t + 1][0]), (t2, states[t + 1][1])):
+            rel = float(np.linalg.norm(_np(got) - want) / np.linalg.norm(want))
+            worst = max(worst, rel)
+    print(f"[{precision}, {weights}, sigma_idx={sigma_idx}] worst per-step state relative error = {worst:.3e}")
+    assert worst <= 1e-3, worst
+    assert nan.item() == 0
+    # free-running T steps inside the library, with the per-step dump
     t1, t2 = torch.as_tensor(x1).cuda(), torch.as_tensor(x2).cuda()
     dump = torch.empty((T, 2, n_mixed, 96, 64, 1), device="cuda")
-    nan = torch.zeros(1, dtype=torch.int32, device="cuda")
     ops.basis_glow_inner(m1, m2, torch.as_tensor(mixed), t1, t2, T, float(eta), float(lam), float(ns),
                          noise1=torch.as_tensor(noise[:, 0]), noise2=torch.as_tensor(noise[:, 1]),
                          per_step=dump, nan_count=nan)
-    assert nan.item() == 0
-    for t in range(T):
-        for k in range(2):
-            want = steps[t][k]
-            got = _np(dump[t, k])
-            rel = np.linalg.norm(got - want) / np.linalg.norm(want)
-            assert rel <= 1e-3, (t, k, rel)
+    drift = max(float(np.linalg.norm(_np(dump[T - 1, k]) - states[T][k]) / np.linalg.norm(states[T][k])) for k in range(2))
+    print(f"[{precision}, {weights}, sigma_idx={sigma_idx}] free-running drift after {T} steps = {drift:.3e}")
+    assert drift <= 5e-3
     assert torch.equal(dump[T - 1, 0], t1) and torch.equal(dump[T - 1, 1], t2)
