@@ -48,8 +48,9 @@ constexpr int kARegionBytes = kNumPanels * kPanelBytes;   // 128 KB
 constexpr int kStageRows = 256;
 constexpr int kStageBytes = kStageRows * 128;    // 32 KB weight tile image
 constexpr int kStages = 3;
-constexpr int kBarBytes = 256;
-constexpr int kSmemBytes = kARegionBytes + kStages * kStageBytes + kBarBytes + 1024;  // + alignment slack
+constexpr int kBiasBytes = kF * 4;                // one fp32 bias vector staged in shared memory
+constexpr int kBarBytes = 128;
+constexpr int kSmemBytes = kARegionBytes + kStages * kStageBytes + kBiasBytes + kBarBytes;   // 231,552 B
 constexpr int kThreadsTC = 192;
 constexpr int kTmemCols = 512;
 
@@ -68,6 +69,8 @@ struct TCParams {
   float* out;            // [M, n3p]
   int H, W;
   long long M;
+  int dbg_flags;             // debug: 1 skip MMA, 2 skip operand build, 4 skip G store, 8 skip epilogue 1/2 bodies
+  int dbg_shift;             // debug: load only bytes >> dbg_shift of every weight image (timing experiments)
   int tiles_per_cta_round;   // grid size (all CTAs advance together)
   int num_rounds;
 };
@@ -194,14 +197,90 @@ __device__ __forceinline__ uint32_t a_offset(int row, int k) {
   return (uint32_t)((k >> 6) * kPanelBytes + row * 128 + ((((k & 63) >> 3) ^ (row & 7)) << 4) + ((k & 7) << 1));
 }
 
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// Stage-1 operand row: im2col of SC channels over the 3x3 taps as split-bf16 [hi | lo].
+// All global loads of a tap group are issued before any is consumed (memory-level parallelism).
+template <int SC>
+__device__ __forceinline__ void build_a1_row(uint8_t* sA, int row, const float* __restrict__ src, long long p,
+                                             bool valid, int h, int w, int H, int W, int stride, int off, int sign,
+                                             int k1_pad) {
+  constexpr int K1h = 9 * SC;
+  constexpr int TG = SC >= 16 ? 3 : 9;                 // taps per load group (register budget)
+#pragma unroll
+  for (int t0 = 0; t0 < 9; t0 += TG) {
+    float v[TG][SC];
+#pragma unroll
+    for (int tt = 0; tt < TG; ++tt) {
+      const int tap = t0 + tt;
+      const int dy = (tap / 3 - 1) * sign, dx = (tap % 3 - 1) * sign;
+      const int hh = h + dy, ww = w + dx;
+      const bool ok = valid && hh >= 0 && hh < H && ww >= 0 && ww < W;
+      const float* s = src + (p + (long long)dy * W + dx) * stride + off;
+      if constexpr (SC % 4 == 0) {
+#pragma unroll
+        for (int q = 0; q < SC / 4; ++q) {
+          float4 t = ok ? __ldg(reinterpret_cast<const float4*>(s) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+          v[tt][4 * q] = t.x; v[tt][4 * q + 1] = t.y; v[tt][4 * q + 2] = t.z; v[tt][4 * q + 3] = t.w;
+        }
+      } else if constexpr (SC == 2) {
+        float2 t = ok ? __ldg(reinterpret_cast<const float2*>(s)) : make_float2(0.f, 0.f);
+        v[tt][0] = t.x; v[tt][1] = t.y;
+      } else {
+#pragma unroll
+        for (int ci = 0; ci < SC; ++ci) v[tt][ci] = ok ? __ldg(s + ci) : 0.f;
+      }
+    }
+#pragma unroll
+    for (int tt = 0; tt < TG; ++tt) {
+      const int k0 = (t0 + tt) * SC;
+      float lo[SC];
+      uint32_t hp[(SC + 1) / 2], lp[(SC + 1) / 2];
+#pragma unroll
+      for (int ci = 0; ci < SC; ++ci) lo[ci] = v[tt][ci] - __bfloat162float(__float2bfloat16_rn(v[tt][ci]));
+      if constexpr (SC == 1) {
+        *reinterpret_cast<__nv_bfloat16*>(sA + a_offset(row, k0)) = __float2bfloat16_rn(v[tt][0]);
+        *reinterpret_cast<__nv_bfloat16*>(sA + a_offset(row, K1h + k0)) = __float2bfloat16_rn(lo[0]);
+      } else {
+#pragma unroll
+        for (int q = 0; q < SC / 2; ++q) {
+          hp[q] = pack_bf16(v[tt][2 * q], v[tt][2 * q + 1]);
+          lp[q] = pack_bf16(lo[2 * q], lo[2 * q + 1]);
+        }
+        if constexpr (SC == 2) {
+          *reinterpret_cast<uint32_t*>(sA + a_offset(row, k0)) = hp[0];
+          *reinterpret_cast<uint32_t*>(sA + a_offset(row, K1h + k0)) = lp[0];
+        } else if constexpr (SC == 4) {
+          *reinterpret_cast<uint2*>(sA + a_offset(row, k0)) = make_uint2(hp[0], hp[1]);
+          *reinterpret_cast<uint2*>(sA + a_offset(row, K1h + k0)) = make_uint2(lp[0], lp[1]);
+        } else {
+#pragma unroll
+          for (int q = 0; q < SC / 8; ++q) {
+            *reinterpret_cast<uint4*>(sA + a_offset(row, k0 + 8 * q)) =
+                make_uint4(hp[4 * q], hp[4 * q + 1], hp[4 * q + 2], hp[4 * q + 3]);
+            *reinterpret_cast<uint4*>(sA + a_offset(row, K1h + k0 + 8 * q)) =
+                make_uint4(lp[4 * q], lp[4 * q + 1], lp[4 * q + 2], lp[4 * q + 3]);
+          }
+        }
+      }
+    }
+  }
+  for (int k = 2 * K1h; k < k1_pad; ++k)
+    *reinterpret_cast<__nv_bfloat16*>(sA + a_offset(row, k)) = __float2bfloat16_rn(0.f);
+}
+
 template <int CS, bool kBwd>
 __global__ void __launch_bounds__(kThreadsTC, 1) k_nn_tc(const TCParams prm) {
-  extern __shared__ uint8_t smem_raw[];
-  // SWIZZLE_128B operands need 1024-byte alignment
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // SWIZZLE_128B operands need 1024-byte alignment; the kernel uses no static shared memory, so the dynamic
+  // window starts at the CTA's shared base (checked below rather than assumed).
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();
   uint8_t* sA = smem;
   uint8_t* sB = smem + kARegionBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kARegionBytes + kStages * kStageBytes);
+  float* sBias = reinterpret_cast<float*>(smem + kARegionBytes + kStages * kStageBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kARegionBytes + kStages * kStageBytes + kBiasBytes);
   // bars[0..2] full, [3..5] empty, [6] a_ready, [7] acc_ready, [8] tmem slot
   const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[kStages]);
   const uint32_t a_ready = smem_u32(&bars[2 * kStages]), acc_ready = smem_u32(&bars[2 * kStages + 1]);
@@ -240,11 +319,13 @@ __global__ void __launch_bounds__(kThreadsTC, 1) k_nn_tc(const TCParams prm) {
         for (int i = 0; i < n_img; ++i) {
           const uint32_t bytes = (i < n_img - kNumPanels) ? (uint32_t)kStageBytes : img3_bytes;
           mbar_wait(empty0 + 8 * stage, phase ^ 1);
-          mbar_expect_tx(full0 + 8 * stage, bytes);
           const uint32_t dst = smem_u32(sB + stage * kStageBytes);
           if constexpr (CS == 1) {
-            bulk_g2s(dst, src, bytes, full0 + 8 * stage);
+            const uint32_t ld_bytes = (bytes >> prm.dbg_shift) & ~15u;
+            mbar_expect_tx(full0 + 8 * stage, ld_bytes);
+            bulk_g2s(dst, src, ld_bytes, full0 + 8 * stage);
           } else {
+            mbar_expect_tx(full0 + 8 * stage, bytes);
             const uint32_t part = bytes / CS;
             bulk_g2s_mc(dst + cta_rank * part, src + cta_rank * part, part, full0 + 8 * stage, kMcMask);
           }
@@ -276,7 +357,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) k_nn_tc(const TCParams prm) {
               const int steps = gemm == 0 ? min(4, prm.k1_steps - 4 * kp) : 4;
               const uint64_t da = make_desc(a_base + kp * kPanelBytes);
               const uint64_t db = make_desc(smem_u32(sB + stage * kStageBytes));
-              for (int k = 0; k < steps; ++k) {
+              for (int k = 0; k < steps && !(prm.dbg_flags & 1); ++k) {
                 // advance 16 bf16 = 32 bytes along K inside the swizzled panel: +2 in the >>4 address field
                 umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kp | k) != 0);
               }
@@ -293,84 +374,105 @@ __global__ void __launch_bounds__(kThreadsTC, 1) k_nn_tc(const TCParams prm) {
     // ===================== workers: operand build + epilogues =====================
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
+    const int wtid = threadIdx.x - 64;                        // 0..127 among the worker threads
     const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
     uint32_t acc_phase = 0;
-    const int K1h = 9 * prm.src_ch;
     const int k1_pad = prm.k1_steps * 16;
+    // each worker keeps one float4 of each bias vector in registers for the whole kernel
+    float4 b1v = make_float4(0.f, 0.f, 0.f, 0.f), b2v = b1v;
+    if constexpr (!kBwd) {
+      b1v = __ldg(reinterpret_cast<const float4*>(prm.bias1) + wtid);
+      b2v = __ldg(reinterpret_cast<const float4*>(prm.bias2) + wtid);
+    }
     for (int round = 0; round < prm.num_rounds; ++round) {
       const long long tile = (long long)round * prm.tiles_per_cta_round + blockIdx.x;
       const long long p = tile * kTileM + row;
       const bool valid = p < prm.M;
+      // pull the next tile's input rows towards L2 while this tile is being processed
+      {
+        const long long pn = p + (long long)prm.tiles_per_cta_round * kTileM;
+        if (pn < prm.M) asm volatile("prefetch.global.L2 [%0];" ::"l"(prm.src + pn * prm.src_stride));
+      }
       // ---- stage-1 operand: split-bf16 im2col row
       {
         int w = 0, h = 0;
         if (valid) { w = (int)(p % prm.W); h = (int)((p / prm.W) % prm.H); }
-        for (int tap = 0; tap < 9; ++tap) {
-          const int dy = (tap / 3 - 1) * prm.tap_sign, dx = (tap % 3 - 1) * prm.tap_sign;
-          const int hh = h + dy, ww = w + dx;
-          const bool ok = valid && hh >= 0 && hh < prm.H && ww >= 0 && ww < prm.W;
-          const float* s = prm.src + (p + (long long)dy * prm.W + dx) * prm.src_stride + prm.src_off;
-          for (int ci = 0; ci < prm.src_ch; ++ci) {
-            const float v = ok ? __ldg(s + ci) : 0.f;
-            const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-            const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
-            const int k = tap * prm.src_ch + ci;
-            *reinterpret_cast<__nv_bfloat16*>(sA + a_offset(row, k)) = hi;
-            *reinterpret_cast<__nv_bfloat16*>(sA + a_offset(row, K1h + k)) = lo;
-          }
+        if (!(prm.dbg_flags & 2)) switch (prm.src_ch) {
+          case 1: build_a1_row<1>(sA, row, prm.src, p, valid, h, w, prm.H, prm.W, prm.src_stride, prm.src_off, prm.tap_sign, k1_pad); break;
+          case 2: build_a1_row<2>(sA, row, prm.src, p, valid, h, w, prm.H, prm.W, prm.src_stride, prm.src_off, prm.tap_sign, k1_pad); break;
+          case 4: build_a1_row<4>(sA, row, prm.src, p, valid, h, w, prm.H, prm.W, prm.src_stride, prm.src_off, prm.tap_sign, k1_pad); break;
+          case 8: build_a1_row<8>(sA, row, prm.src, p, valid, h, w, prm.H, prm.W, prm.src_stride, prm.src_off, prm.tap_sign, k1_pad); break;
+          default: build_a1_row<16>(sA, row, prm.src, p, valid, h, w, prm.H, prm.W, prm.src_stride, prm.src_off, prm.tap_sign, k1_pad); break;
         }
-        for (int k = 2 * K1h; k < k1_pad; ++k)
-          *reinterpret_cast<__nv_bfloat16*>(sA + a_offset(row, k)) = __float2bfloat16_rn(0.f);
       }
+      if constexpr (!kBwd) reinterpret_cast<float4*>(sBias)[wtid] = b1v;
       fence_proxy_async();
       mbar_arrive(a_ready);
 
       // ---- epilogues of stage 1 and stage 2: TMEM -> (bias, relu | mask) -> bf16 -> swizzled smem
       for (int gemm = 0; gemm < 2; ++gemm) {
+        // forward: stage 1 -> mask1, stage 2 -> mask2; backward: stage 1 applies mask2, stage 2 mask1
+        uint32_t* mask = kBwd ? (gemm == 0 ? prm.mask2 : prm.mask1) : (gemm == 0 ? prm.mask1 : prm.mask2);
+        uint32_t mk[kF / 32];
+        if constexpr (kBwd) {                                  // fetch this row's 512 mask bits before waiting
+#pragma unroll
+          for (int q = 0; q < kF / 128; ++q) {
+            uint4 t = valid ? __ldg(reinterpret_cast<const uint4*>(mask + p * (kF / 32)) + q) : make_uint4(0, 0, 0, 0);
+            mk[4 * q] = t.x; mk[4 * q + 1] = t.y; mk[4 * q + 2] = t.z; mk[4 * q + 3] = t.w;
+          }
+        }
+        if constexpr (!kBwd) named_bar_sync(1, 128);           // bias vector of this stage is in sBias
         mbar_wait(acc_ready, acc_phase);
         acc_phase ^= 1;
         tc_fence_after();
-        const float* bias = gemm == 0 ? prm.bias1 : prm.bias2;
-        // forward: stage 1 -> mask1, stage 2 -> mask2; backward: stage 1 applies mask2, stage 2 mask1
-        uint32_t* mask = kBwd ? (gemm == 0 ? prm.mask2 : prm.mask1) : (gemm == 0 ? prm.mask1 : prm.mask2);
-#pragma unroll 1
-        for (int j = 0; j < kF / 32; ++j) {
-          uint32_t v[32];
-          tmem_ld32(t_lane + (uint32_t)(j * 32), v);
+#pragma unroll
+        for (int jj = 0; jj < ((prm.dbg_flags & 8) ? 0 : kF / 64); ++jj) {   // 64 accumulator columns per iteration
+          uint32_t v[2][32];
+          tmem_ld32(t_lane + (uint32_t)(jj * 64), v[0]);
+          tmem_ld32(t_lane + (uint32_t)(jj * 64 + 32), v[1]);
           tmem_ld_wait();
-          float f[32];
-          if constexpr (!kBwd) {
-            uint32_t bits = 0;
+          uint8_t* base = sA + jj * kPanelBytes + row * 128;   // 64 columns = one K panel of the next stage
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + j * 32) + q);
-              f[4 * q + 0] = __uint_as_float(v[4 * q + 0]) + b4.x;
-              f[4 * q + 1] = __uint_as_float(v[4 * q + 1]) + b4.y;
-              f[4 * q + 2] = __uint_as_float(v[4 * q + 2]) + b4.z;
-              f[4 * q + 3] = __uint_as_float(v[4 * q + 3]) + b4.w;
+          for (int hf = 0; hf < 2; ++hf) {
+            const int j = 2 * jj + hf;
+            float f[32];
+            if constexpr (!kBwd) {
+              uint32_t bits = 0;
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const float4 b4 = reinterpret_cast<const float4*>(sBias + j * 32)[q];
+                f[4 * q + 0] = __uint_as_float(v[hf][4 * q + 0]) + b4.x;
+                f[4 * q + 1] = __uint_as_float(v[hf][4 * q + 1]) + b4.y;
+                f[4 * q + 2] = __uint_as_float(v[hf][4 * q + 2]) + b4.z;
+                f[4 * q + 3] = __uint_as_float(v[hf][4 * q + 3]) + b4.w;
+              }
+#pragma unroll
+              for (int cidx = 0; cidx < 32; ++cidx) {
+                bits |= (f[cidx] > 0.f ? 1u : 0u) << cidx;
+                f[cidx] = fmaxf(f[cidx], 0.f);
+              }
+              if (mask != nullptr && valid) mask[p * (kF / 32) + j] = bits;
+            } else {
+              const uint32_t bits = mk[j];
+#pragma unroll
+              for (int cidx = 0; cidx < 32; ++cidx) f[cidx] = ((bits >> cidx) & 1u) ? __uint_as_float(v[hf][cidx]) : 0.f;
             }
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
-              bits |= (f[c] > 0.f ? 1u : 0u) << c;
-              f[c] = fmaxf(f[c], 0.f);
+            for (int q = 0; q < 4; ++q) {
+              const int chunk = hf * 4 + q;
+              uint4 pk;
+              pk.x = pack_bf16(f[8 * q + 0], f[8 * q + 1]);
+              pk.y = pack_bf16(f[8 * q + 2], f[8 * q + 3]);
+              pk.z = pack_bf16(f[8 * q + 4], f[8 * q + 5]);
+              pk.w = pack_bf16(f[8 * q + 6], f[8 * q + 7]);
+              *reinterpret_cast<uint4*>(base + ((chunk ^ (row & 7)) << 4)) = pk;
             }
-            if (mask != nullptr && valid) mask[p * (kF / 32) + j] = bits;
-          } else {
-            const uint32_t bits = valid ? mask[p * (kF / 32) + j] : 0u;
-#pragma unroll
-            for (int c = 0; c < 32; ++c) f[c] = ((bits >> c) & 1u) ? __uint_as_float(v[c]) : 0.f;
           }
-          // 32 columns = 4 chunks of 8 bf16 (16 B) inside panel j/2
-          uint8_t* base = sA + (j >> 1) * kPanelBytes + row * 128;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int chunk = (j & 1) * 4 + q;
-            uint4 pk;
-            pk.x = pack_bf16(f[8 * q + 0], f[8 * q + 1]);
-            pk.y = pack_bf16(f[8 * q + 2], f[8 * q + 3]);
-            pk.z = pack_bf16(f[8 * q + 4], f[8 * q + 5]);
-            pk.w = pack_bf16(f[8 * q + 6], f[8 * q + 7]);
-            *reinterpret_cast<uint4*>(base + ((chunk ^ (row & 7)) << 4)) = pk;
+        }
+        if constexpr (!kBwd) {
+          if (gemm == 0) {                                     // swap in the stage-2 bias once everyone is done
+            named_bar_sync(1, 128);
+            reinterpret_cast<float4*>(sBias)[wtid] = b2v;
           }
         }
         tc_fence_before();
@@ -386,7 +488,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) k_nn_tc(const TCParams prm) {
         uint32_t v[16];
         tmem_ld16(t_lane + (uint32_t)(j * 16), v);
         tmem_ld_wait();
-        if (valid) {
+        if (valid && !(prm.dbg_flags & 4)) {
           float4* o = reinterpret_cast<float4*>(prm.out + p * prm.n3p + j * 16);
 #pragma unroll
           for (int q = 0; q < 4; ++q)
@@ -527,6 +629,8 @@ void run_tc(TCParams prm, cudaStream_t s) {
   grid = (grid + cs - 1) / cs * cs;          // whole clusters; surplus CTAs run masked tiles
   if (grid > g_num_sms) grid = g_num_sms / cs * cs;
   prm.tiles_per_cta_round = grid;
+  if (const char* e = getenv("ASEP_TC_DBG_SHIFT")) prm.dbg_shift = atoi(e);
+  if (const char* e = getenv("ASEP_TC_DBG_FLAGS")) prm.dbg_flags = atoi(e);
   prm.num_rounds = (int)((tiles + grid - 1) / grid);
   switch (cs) {
     case 1: launch_tc<1, kBwd>(prm, grid, s); break;
