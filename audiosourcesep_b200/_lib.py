@@ -78,6 +78,9 @@ _SIGNATURES = {
     "asep_philox_normal": [_P, _U64, _U64, _U64, _U64, _V],
     "asep_basis_glow_inner": [_V, _V, _P, _P, _P, _I, _F, _F, _F, _P, _P, _U64, _U64, _U64, _P, _P, _V],
     "asep_tc_set_cluster": [_I],
+    "asep_tc_profile": [_I],
+    "asep_tc_profile_read": [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64),
+                             ctypes.POINTER(ctypes.c_double)],
 }
 _RESTYPES = {"asep_last_error": ctypes.c_char_p, "asep_abi_version": ctypes.c_int, "asep_launch_count": ctypes.c_int64}
 EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + list(_RESTYPES))
@@ -128,6 +131,17 @@ def init(device: Optional[int] = None) -> int:
 
 def launch_count() -> int:
     return int(load().asep_launch_count())
+
+
+def tc_profile(on: bool) -> None:
+    check(load().asep_tc_profile(int(on)))
+
+
+def tc_profile_read():
+    """(summed kernel ms, launches, algorithmic FLOPs) of the tcgen05 launches recorded since tc_profile(True)."""
+    ms, n, fl = ctypes.c_double(), ctypes.c_int64(), ctypes.c_double()
+    check(load().asep_tc_profile_read(ctypes.byref(ms), ctypes.byref(n), ctypes.byref(fl)))
+    return ms.value, n.value, fl.value
 
 
 # ------------------------------------------------------------------ DLPack plumbing

@@ -478,4 +478,18 @@ int asep_tc_set_cluster(int cluster_size) {
   ASEP_API_END
 }
 
+int asep_tc_profile(int on) {
+  ASEP_API_BEGIN
+  nn_tc_profile(on);
+  ASEP_API_END
+}
+
+int asep_tc_profile_read(double* total_ms, int64_t* launches, double* flops) {
+  ASEP_API_BEGIN
+  long long n = 0;
+  nn_tc_profile_read(total_ms, &n, flops);
+  if (launches) *launches = (int64_t)n;
+  ASEP_API_END
+}
+
 }  // extern "C"

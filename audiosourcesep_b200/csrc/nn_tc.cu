@@ -548,6 +548,14 @@ __global__ void __launch_bounds__(256) k_gather_bwd(const float* __restrict__ G,
 int g_cluster = 1;
 int g_num_sms = 0;
 
+// ---- optional per-launch timing of the tensor-core kernel (bench.py's roofline leg): a CUDA event pair
+// on the launching stream around every k_nn_tc launch while profiling is on.
+struct ProfRec { cudaEvent_t a, b; };
+bool g_prof_on = false;
+std::vector<ProfRec> g_prof_recs, g_prof_pool;
+double g_prof_flops = 0.0;
+double g_next_flops = 0.0;   // algorithmic FLOPs of the launch being issued (set by nn_tc_forward/backward)
+
 inline int pad16(int n) { return (n + 15) / 16 * 16; }
 
 // ------------------------------------------------------------------ host: weight tile images
@@ -612,8 +620,19 @@ void launch_tc(const TCParams& prm, int grid, cudaStream_t s) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  ProfRec rec{};
+  if (g_prof_on) {
+    if (!g_prof_pool.empty()) { rec = g_prof_pool.back(); g_prof_pool.pop_back(); }
+    else { CUDA_CHECK(cudaEventCreate(&rec.a)); CUDA_CHECK(cudaEventCreate(&rec.b)); }
+    CUDA_CHECK(cudaEventRecord(rec.a, s));
+  }
   CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, prm));
   ASEP_LAUNCH_CHECK();
+  if (g_prof_on) {
+    CUDA_CHECK(cudaEventRecord(rec.b, s));
+    g_prof_recs.push_back(rec);
+    g_prof_flops += g_next_flops;
+  }
 }
 
 template <bool kBwd>
@@ -648,6 +667,27 @@ void nn_tc_set_cluster(int cluster_size) {
   g_cluster = cluster_size;
 }
 int nn_tc_get_cluster() { return g_cluster; }
+
+void nn_tc_profile(int on) {
+  g_prof_on = on != 0;
+  if (g_prof_on) {
+    for (auto& r : g_prof_recs) g_prof_pool.push_back(r);
+    g_prof_recs.clear();
+    g_prof_flops = 0.0;
+  }
+}
+void nn_tc_profile_read(double* total_ms, long long* launches, double* flops) {
+  double ms = 0.0;
+  for (auto& r : g_prof_recs) {
+    CUDA_CHECK(cudaEventSynchronize(r.b));
+    float t = 0.f;
+    CUDA_CHECK(cudaEventElapsedTime(&t, r.a, r.b));
+    ms += t;
+  }
+  if (total_ms) *total_ms = ms;
+  if (launches) *launches = (long long)g_prof_recs.size();
+  if (flops) *flops = g_prof_flops;
+}
 
 size_t nn_tc_g_floats(long long M, int C) { return (size_t)M * (size_t)pad16(9 * C); }
 
@@ -716,6 +756,7 @@ void nn_tc_forward(const NNWeightsTC& w, const NNScratchTC& sc, const float* sta
   prm.wimg = w.fwd.img; prm.k1_steps = w.fwd.k1_steps; prm.k1_panels = w.fwd.k1_panels; prm.n3p = w.fwd.n3p;
   prm.bias1 = w.bias1; prm.bias2 = w.bias2; prm.mask1 = mask1; prm.mask2 = mask2;
   prm.out = sc.G; prm.H = H; prm.W = W; prm.M = M;
+  g_next_flops = 2.0 * (double)M * (9.0 * (C / 2) * kF + (double)kF * kF + 9.0 * kF * C);   // conv MACs x 2, unpadded
   run_tc<false>(prm, s);
   const long long total = M * C;
   k_gather_fwd<<<cdiv(total, 256), 256, 0, s>>>(sc.G, w.const3, w.c3, r, H, W, C, w.fwd.n3p, total);
@@ -732,6 +773,7 @@ void nn_tc_backward(const NNWeightsTC& w, const NNScratchTC& sc, const float* gr
   prm.bias1 = nullptr; prm.bias2 = nullptr;
   prm.mask1 = const_cast<uint32_t*>(mask1); prm.mask2 = const_cast<uint32_t*>(mask2);
   prm.out = sc.G; prm.H = H; prm.W = W; prm.M = M;
+  g_next_flops = 2.0 * (double)M * (9.0 * (C / 2) * kF + (double)kF * kF + 9.0 * kF * C);
   run_tc<true>(prm, s);
   const long long total = M * (C / 2);
   k_gather_bwd<<<cdiv(total, 256), 256, 0, s>>>(sc.G, gxb, H, W, C / 2, w.bwd.n3p, total);

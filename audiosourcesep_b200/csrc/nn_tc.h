@@ -48,5 +48,8 @@ void nn_tc_backward(const NNWeightsTC& w, const NNScratchTC& sc, const float* gr
 size_t nn_tc_g_floats(long long M, int C);   // capacity needed for NNScratchTC::G
 void nn_tc_set_cluster(int cluster_size);    // 1, 2 or 4 CTAs sharing each weight tile by TMA multicast
 int nn_tc_get_cluster();
+// CUDA-event timing of every tensor-core kernel launch (on its own stream) while switched on.
+void nn_tc_profile(int on);
+void nn_tc_profile_read(double* total_ms, long long* launches, double* flops);
 
 }  // namespace asep

@@ -1,0 +1,389 @@
+#!/usr/bin/env python
+"""Benchmark of the separation hot path (driver contract: one JSON line on stdout from rank 0).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B]
+
+Headline metric (BASELINE.json): Glow ``log_prob`` samples/s on synthetic mel-spectrogram patches of
+the ``configs/melspec_glow.yml`` shape (96x64x1, L=3, K=40, 512 filters, learnable top prior),
+random-init ("perturbed") weights.  One *step* = one ``log_prob`` pass over one batch of B patches per
+GPU.  The second half of the metric, BASIS Langevin segment-steps/s with two Glow priors, is measured in
+the same run and reported under ``"basis"``.
+
+* ``value``  : whole-job samples/s, inputs resident in HBM, device time by CUDA events (per step, with
+               an L2 flush between steps outside the events), max over ranks.
+* ``e2e``    : the same metric through the public API (``Glow.log_prob`` -> C ABI) with the batch in
+               PINNED HOST memory: H2D copy + compute + D2H of the [B] log-probabilities inside the
+               timed region, every step.
+* ``roofline``: the dominant kernel (k_nn_tc, the fused tcgen05 coupling network): algorithmic conv
+               FLOPs of the recorded launches / their summed CUDA-event time (events on the launching
+               stream, recorded during the timed region) vs the measured sustained bf16 peak.
+* ``cpu_baseline`` / ``--impl reference``: the reference-faithful CPU graph (oracle/glow_oracle.py,
+               torch-CPU fp32, coupling network evaluated twice as the TFP graph does) on the host
+               cores, on a bounded sample of the same workload.  TensorFlow 2.2 cannot be installed in
+               this image, so kind = "port".
+
+Multi-GPU (torchrun, one rank per GPU): the batch dimension shards with no data-path collective
+("weak": B patches per GPU); NCCL is used only for the barrier and the max-over-ranks timing.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+F_GLOW = 48.22e9          # FLOP per patch per coupling-network pass
+D_PATCH = 96 * 64
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"bf16_sustained": float(p.get("bf16_tflops_sustained", 1378.1)), "bf16_burst": float(p.get("bf16_tflops", 1643.9)),
+                "hbm": float(p.get("hbm_gbs", 6551.0)), "source": "measured"}
+    return {"bf16_sustained": 1400.0, "bf16_burst": 1590.0, "hbm": 6650.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi SM clock / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._pump, daemon=True)
+        self.thread.start()
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.strip().split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------ CPU reference arm
+def _cpu_model(K: int):
+    import torch
+    from audiosourcesep_b200 import GlowConfig
+    from audiosourcesep_b200.weights import init_glow_params
+    from oracle.glow_oracle import GlowOracle
+    cfg = GlowConfig(K=K)
+    return cfg, GlowOracle(cfg, init_glow_params(cfg, seed=2), dtype=torch.float32)
+
+
+def cpu_log_prob_rate(sample: int, K: int = 40, repeats: int = 1):
+    """samples/s of the reference-faithful CPU graph on `sample` patches (all host threads)."""
+    import torch
+    from audiosourcesep_b200 import synthetic
+    _, oracle = _cpu_model(K)
+    x = torch.as_tensor(synthetic.mel_patches_db(sample, seed=0))
+    best = None
+    with torch.no_grad():
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            oracle.log_prob_reference_graph(x)
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+    return sample / best, best
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's own CPU implementation of the path.  The TF graph cannot run
+    here (TensorFlow 2.2 / TFP 0.9 absent, no wheel, Python 3.12), so the reference-faithful port in
+    oracle/ is timed with every host thread torch-CPU will use; rank 0 only."""
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = torch.get_num_threads()
+    sample = args.cpu_sample
+    _, oracle = _cpu_model(args.K)
+    from audiosourcesep_b200 import synthetic
+    x = torch.as_tensor(synthetic.mel_patches_db(sample, seed=0))
+    times = []
+    with torch.no_grad():
+        for i in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            oracle.log_prob_reference_graph(x)
+            dt = time.perf_counter() - t0
+            if i >= args.warmup:
+                times.append(dt)
+    ms = 1e3 * float(np.mean(times))
+    value = sample / (ms * 1e-3)
+    desc = (f"{sample} patches per step, reference-faithful graph (coupling network evaluated twice), torch-CPU fp32, "
+            f"{cores} threads of {os.cpu_count()} logical cores")
+    line = {
+        "impl": "reference", "metric": "glow_log_prob_samples_per_s", "value": value, "unit": "samples/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": _config(args, per_gpu_batch=sample, note="bounded CPU sample of the same workload"),
+        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def _config(args, per_gpu_batch, note=None):
+    c = {"workload": f"glow_log_prob melspec_glow.yml (96x64x1, L=3, K={args.K}, n_filters=512, learntop), "
+                     f"{per_gpu_batch} patches per GPU per step",
+         "per_gpu_batch": per_gpu_batch, "global_batch": per_gpu_batch * args.gpus,
+         "weights": "random-init (perturbed generator, seed 2)",
+         "cache": "L2 flushed (512 MiB write) between timed steps, outside the CUDA-event brackets",
+         "sharding": "patches sharded over ranks, no data-path collective"}
+    if note:
+        c["note"] = note
+    return c
+
+
+# ------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run --nproc-per-node N")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: audiosourcesep_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from audiosourcesep_b200 import GlowConfig, _lib, ops, synthetic
+    from audiosourcesep_b200.glow import Glow
+    from audiosourcesep_b200.weights import init_glow_params
+    from oracle import basis_oracle as bo
+
+    dev = torch.device("cuda", local_rank)
+    peaks = _peaks()
+    cfg = GlowConfig(K=args.K)
+    params = init_glow_params(cfg, seed=2)
+    model = Glow(cfg, params, precision=_lib.PREC_BF16, device=local_rank)
+    ops.set_tc_cluster(args.cluster)
+    B = args.batch
+    base = synthetic.mel_patches_db(min(B, 64), seed=100 + rank)
+    reps = (B + base.shape[0] - 1) // base.shape[0]
+    # distinct patches: cyclic shifts of the seeded base set along time
+    host = np.concatenate([np.roll(base, 3 * i, axis=2) for i in range(reps)], axis=0)[:B]
+    x_host = torch.as_tensor(np.ascontiguousarray(host)).pin_memory()
+    x_dev = x_host.to(dev)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed_loop(step_fn, steps, warmup, profile=False):
+        for _ in range(warmup):
+            step_fn()
+        barrier()
+        evs = []
+        if profile:
+            _lib.tc_profile(True)
+        n0 = _lib.launch_count()
+        for _ in range(steps):
+            flush.fill_(1)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            step_fn()
+            b.record()
+            evs.append((a, b))
+        barrier()
+        launches = _lib.launch_count() - n0
+        prof = None
+        if profile:
+            prof = _lib.tc_profile_read()
+            _lib.tc_profile(False)
+        total_ms = sum(a.elapsed_time(b) for a, b in evs)
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), launches, prof
+
+    # ---- 1. device-resident throughput (value) with the kernel-level CUDA events for the roofline
+    out = {}
+
+    def step_dev():
+        out["lp"] = model.log_prob(x_dev)
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    total_ms, launches, prof = timed_loop(step_dev, args.steps, args.warmup, profile=True)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = total_ms / args.steps
+    value = world * B * args.steps / (total_ms * 1e-3)
+    lp = out["lp"].float().cpu().numpy()
+    if not np.all(np.isfinite(lp)):
+        raise SystemExit("non-finite log_prob in the benchmark batch")
+
+    # ---- 2. end to end through the public API with host buffers
+    def step_e2e():
+        out["lp_host"] = model.log_prob(x_host.to(dev, non_blocking=True)).cpu()
+
+    e2e_ms, _, _ = timed_loop(step_e2e, args.steps, args.warmup)
+    e2e_value = world * B * args.steps / (e2e_ms * 1e-3)
+
+    # ---- 3. BASIS Langevin segment-steps/s with two Glow priors (second half of the metric)
+    basis = None
+    if args.basis_segments > 0:
+        nseg = args.basis_segments
+        bcfg = GlowConfig(K=args.K, minval=0.0, maxval=1.0)
+        m1 = Glow(bcfg, init_glow_params(bcfg, seed=2), precision=_lib.PREC_BF16, device=local_rank)
+        m2 = Glow(bcfg, init_glow_params(bcfg, seed=3), precision=_lib.PREC_BF16, device=local_rank)
+        mixed, _, _ = synthetic.basis_problem(min(nseg, 32), seed1=10 + rank, seed2=50 + rank)
+        mixed = np.concatenate([mixed] * ((nseg + mixed.shape[0] - 1) // mixed.shape[0]))[:nseg]
+        x1, x2 = synthetic.langevin_init(nseg, seed=4 + rank)
+        mixed_d = torch.as_tensor(mixed).to(dev)
+        t1, t2 = torch.as_tensor(x1).to(dev), torch.as_tensor(x2).to(dev)
+        sig = bo.get_sigmas(1.0, 0.01, 10, "logarithmic")
+        eta, lam, ns = bo.step_constants(sig, 9)
+        T = args.basis_T
+        stepno = [0]
+
+        def step_basis():
+            ops.basis_glow_inner(m1, m2, mixed_d, t1, t2, T, float(eta), float(lam), float(ns), seed=1,
+                                 step0=stepno[0], elem_offset=rank * nseg * D_PATCH)
+            stepno[0] += T
+
+        b_ms, b_launches, _ = timed_loop(step_basis, max(1, args.steps // 2), 1)
+        nsteps = max(1, args.steps // 2)
+        basis = {"metric": "basis_glow_segment_steps_per_s", "value": world * nseg * T * nsteps / (b_ms * 1e-3),
+                 "unit": "segment-steps/s", "segments_per_gpu": nseg, "langevin_steps_per_call": T,
+                 "ms_per_langevin_step": b_ms / (nsteps * T), "gpu_launches": b_launches,
+                 "alg_tflops": world * nseg * T * nsteps * 4 * F_GLOW * (args.K / 40.0) / (b_ms * 1e-3) / 1e12,
+                 "note": "2 priors x (forward + data-gradient) = 4 F_glow algorithmic FLOP per segment-step; in-kernel "
+                         "Philox noise; sigma index 9 of the 10-level schedule"}
+        if not (torch.isfinite(t1).all() and torch.isfinite(t2).all()):
+            basis["note"] += "; WARNING non-finite state"
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel
+    k_ms, k_launches, k_flops = prof
+    achieved = k_flops / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
+    roofline = {"bound": "tensor", "kernel": "k_nn_tc<fwd> (fused conv3x3 -> conv1x1 -> conv3x3 coupling network)",
+                "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+                "frac": achieved / peaks["bf16_sustained"], "peak_source": f"{peaks['source']} sustained bf16 (kernel timed inside a long step)",
+                "traffic": None, "launches": k_launches, "avg_launch_ms": k_ms / max(1, k_launches),
+                "kernel_share_of_step": k_ms / total_ms if total_ms > 0 else None,
+                "alg_flops_per_launch": k_flops / max(1, k_launches)}
+    prof_path = os.path.join(ROOT, "profiles", "ncu_summary.json")
+    if os.path.exists(prof_path):
+        try:
+            with open(prof_path) as f:
+                roofline["traffic"] = json.load(f).get("k_nn_tc_dram_bytes_per_launch")
+        except Exception:
+            pass
+
+    # ---- CPU baseline on a bounded sample (rank 0, N=1 only)
+    cpu = None
+    if world == 1 and args.cpu_sample > 0:
+        import torch as _t
+        _, probe = cpu_log_prob_rate(2, args.K)                      # size the sample for ~15 s of CPU work
+        args.cpu_sample = int(min(64, max(args.cpu_sample, round(15.0 / (probe / 2.0)))))
+        rate, secs = cpu_log_prob_rate(args.cpu_sample, args.K)
+        cpu = {"value": rate, "unit": "samples/s", "cores": _t.get_num_threads(), "kind": "port",
+               "sample": f"{args.cpu_sample} patches, one pass of the reference-faithful graph (coupling network evaluated "
+                         f"twice as in the TFP graph), torch-CPU fp32, {secs:.1f} s on {_t.get_num_threads()} threads "
+                         f"({os.cpu_count()} logical cores)"}
+
+    line = {
+        "metric": "glow_log_prob_samples_per_s", "value": value, "unit": "samples/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": _config(args, per_gpu_batch=B),
+        "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(x_host.numel() * 4),
+                "d2h_bytes_per_step": int(B * 4), "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "clocks": clocks,
+        "alg_tflops": value * F_GLOW * (args.K / 40.0) / 1e12,
+        "basis": basis,
+        "tc_cluster": args.cluster,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--batch", type=int, default=2048, help="patches per GPU per step")
+    ap.add_argument("--K", type=int, default=40, help="flow steps per block (40 = configs/melspec_glow.yml)")
+    ap.add_argument("--cluster", type=int, default=1, help="TMA-multicast cluster size of the tcgen05 kernel")
+    ap.add_argument("--basis-segments", type=int, default=256, help="segments per GPU of the BASIS leg (0 = skip)")
+    ap.add_argument("--basis-T", type=int, default=2)
+    ap.add_argument("--cpu-sample", type=int, default=4, help="patches of the CPU baseline sample (0 = skip)")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -138,6 +138,12 @@ int asep_basis_glow_inner(asep_glow_t m1, asep_glow_t m2, const DLTensor* mixed,
  * kernel through TMA multicast.  Tuning knob; results are identical for every value. */
 int asep_tc_set_cluster(int cluster_size);
 
+/* Measurement aid (bench.py roofline leg): while on, every launch of the tcgen05 coupling kernel is bracketed
+ * by a CUDA event pair on its own stream.  _read synchronises those events and returns the summed kernel time,
+ * the launch count and the algorithmic FLOPs (2 x conv MACs, unpadded) of the recorded launches. */
+int asep_tc_profile(int on);
+int asep_tc_profile_read(double* total_ms, int64_t* launches, double* flops);
+
 #ifdef __cplusplus
 }
 #endif
