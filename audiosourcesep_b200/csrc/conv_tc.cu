@@ -1,0 +1,320 @@
+// Implicit-GEMM convolution of the NCSN score networks on tcgen05 / TMEM, fed by TMA (sm_100a).
+//
+//   out[n,h,w,co] = bias[co] + add[n,h,w,co] + sum_{tap,ci} xin[n, h+dy(tap)*dil, w+dx(tap)*dil, ci] * K[tap][ci][co]
+//
+// GEMM view per CTA tile: M = 128 consecutive pixels of one image (= 128/W full image rows, so the tile is a
+// rectangle), N = Cout (128..384, all output channels at once: the activation tile is read once), K = taps*Cin
+// walked as (tap, 64-channel panel) steps.
+//   * A operand: the bf16 NHWC activation tensor is described by ONE 4-D tensor map (C, W, H, N); the tile of
+//     tap (dy,dx) is the box [64 ch, W, 128/W rows, 1 image] whose start coordinate is shifted by (dx*dil,
+//     dy*dil): TMA zero-fills everything outside the image, which is exactly Keras 'same' padding, for any
+//     dilation, with no im2col buffer and no index arithmetic on the SMs (cp.async.bulk.tensor -> UTMALDG).
+//   * B operand: host-pre-swizzled bf16 weight tile images [Cout x 64] per (tap, panel), streamed with bulk
+//     copies (UBLKCP) into the same ring stage.
+//   * D: fp32 accumulators in TMEM (Cout columns; two buffers when Cout <= 256 so the epilogue of tile i
+//     overlaps the MMAs of tile i+1).
+// Warp roles (192 threads, persistent, 1 CTA/SM): warp 0 = TMA producer, warp 1 = MMA issuer (one thread,
+// tcgen05.mma M=128 N<=256 K=16, SWIZZLE_128B descriptors), warps 2-5 = epilogue (tcgen05.ld -> + bias + residual
+// -> fp32 NHWC stores).
+#include "conv_tc.h"
+
+#include <cuda.h>
+#include <map>
+#include <tuple>
+
+#include "tc_ptx.cuh"
+
+namespace asep {
+
+namespace {
+
+constexpr int kTileM = 128;
+constexpr int kABytes = kTileM * 128;      // one 64-channel bf16 panel of 128 pixels
+constexpr int kThreads = 192;
+constexpr int kMaxStages = 6;
+constexpr int kSmemBudget = 227 * 1024 - 1024;
+
+struct ConvParams {
+  const __nv_bfloat16* wimg;
+  const float* bias;
+  const float* add;
+  float* out;
+  int Cout, kpanels, taps, dil, H, W, rows_per_tile, tiles_per_img, num_tiles;
+  int nsplit, ncols, nbuf, stages, stage_bytes, b_bytes;
+};
+
+__global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__ CUtensorMap tmap, const ConvParams prm) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + prm.stages * prm.stage_bytes);
+  // bars: [0,S) full  [S,2S) empty  [2S,2S+2) acc_ready  [2S+2,2S+4) acc_empty  [2S+4] tmem slot
+  const int S = prm.stages;
+  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[S]);
+  const uint32_t accr0 = smem_u32(&bars[2 * S]), acce0 = smem_u32(&bars[2 * S + 2]);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(&bars[2 * S + 4]);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < S; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(accr0 + 8 * i, 1); mbar_init(acce0 + 8 * i, 128); }
+    fence_barrier_init();
+    tma_prefetch_desc(&tmap);
+  }
+  if (warp == 2) tmem_alloc(smem_u32(tmem_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int kiters = prm.taps * prm.kpanels;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < prm.num_tiles; tile += gridDim.x) {
+        const int n = tile / prm.tiles_per_img;
+        const int h0 = (tile % prm.tiles_per_img) * prm.rows_per_tile;
+        const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(prm.wimg);
+        for (int tap = 0; tap < prm.taps; ++tap) {
+          const int dy = prm.taps == 9 ? (tap / 3 - 1) * prm.dil : 0;
+          const int dx = prm.taps == 9 ? (tap % 3 - 1) * prm.dil : 0;
+          for (int kp = 0; kp < prm.kpanels; ++kp) {
+            mbar_wait(empty0 + 8 * stage, phase ^ 1);
+            const uint32_t fb = full0 + 8 * stage;
+            const uint32_t sa = smem_u32(smem + stage * prm.stage_bytes);
+            mbar_expect_tx(fb, (uint32_t)(kABytes + prm.b_bytes));
+            tma_load_4d(sa, &tmap, kp * 64, dx, h0 + dy, n, fb);
+            bulk_g2s(sa + kABytes, wsrc, (uint32_t)prm.b_bytes, fb);
+            wsrc += prm.b_bytes;
+            if (++stage == (uint32_t)S) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      uint32_t use[2] = {0, 0};
+      const uint32_t idesc = make_idesc(prm.ncols);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < prm.num_tiles; tile += gridDim.x, ++it) {
+        const int buf = prm.nbuf == 2 ? (it & 1) : 0;
+        mbar_wait(acce0 + 8 * buf, (use[buf] & 1) ^ 1);       // epilogue has drained this accumulator buffer
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 256);
+        for (int ki = 0; ki < kiters; ++ki) {
+          mbar_wait(full0 + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * prm.stage_bytes);
+          const uint64_t da = make_desc(sa);
+          const uint64_t db = make_desc(sa + kABytes);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            for (int sp = 0; sp < prm.nsplit; ++sp) {
+              umma_bf16(d_tmem + (uint32_t)(sp * prm.ncols), da + (uint64_t)(2 * k),
+                        db + (uint64_t)(sp * prm.ncols * 8 + 2 * k), idesc, (ki | k) != 0);
+            }
+          }
+          umma_commit(empty0 + 8 * stage);
+          if (++stage == (uint32_t)S) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(accr0 + 8 * buf);
+        ++use[buf];
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    uint32_t use[2] = {0, 0};
+    int it = 0;
+    for (int tile = blockIdx.x; tile < prm.num_tiles; tile += gridDim.x, ++it) {
+      const int buf = prm.nbuf == 2 ? (it & 1) : 0;
+      mbar_wait(accr0 + 8 * buf, use[buf] & 1);
+      ++use[buf];
+      tc_fence_after();
+      const long long p = (long long)tile * kTileM + row;
+      const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * 256);
+      float* orow = prm.out + p * prm.Cout;
+      const float* arow = prm.add ? prm.add + p * prm.Cout : nullptr;
+      for (int j = 0; j < prm.Cout / 32; ++j) {
+        uint32_t v[32];
+        tmem_ld32(t_lane + (uint32_t)(j * 32), v);
+        float4 a4[8];
+        if (arow) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) a4[q] = reinterpret_cast<const float4*>(arow + j * 32)[q];
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          float4 o = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
+                                 __uint_as_float(v[4 * q + 3]));
+          if (prm.bias) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(prm.bias + j * 32) + q);
+            o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
+          }
+          if (arow) { o.x += a4[q].x; o.y += a4[q].y; o.z += a4[q].z; o.w += a4[q].w; }
+          reinterpret_cast<float4*>(orow + j * 32)[q] = o;
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(acce0 + 8 * buf);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+    ASEP_CHECK(p != nullptr && qres == cudaDriverEntryPointSuccess, ASEP_ERR_CUDA,
+               "cuTensorMapEncodeTiled is not available from the driver");
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+std::map<std::tuple<const void*, int, int, int, int>, CUtensorMap> g_maps;
+
+const CUtensorMap& activation_map(const __nv_bfloat16* x, int N, int H, int W, int C) {
+  auto key = std::make_tuple((const void*)x, N, H, W, C);
+  auto it = g_maps.find(key);
+  if (it != g_maps.end()) return it->second;
+  if (g_maps.size() > 4096) g_maps.clear();
+  CUtensorMap m;
+  const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  const cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  const cuuint32_t box[4] = {64, (cuuint32_t)W, (cuuint32_t)(kTileM / W), 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(x), dims, strides, box,
+                           estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  ASEP_CHECK(r == CUDA_SUCCESS, ASEP_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for [%d,%d,%d,%d]", (int)r, N, H, W, C);
+  return g_maps.emplace(key, m).first->second;
+}
+
+int g_sms = 0;
+struct ProfRec { cudaEvent_t a, b; };
+bool g_prof_on = false;
+std::vector<ProfRec> g_recs, g_pool;
+double g_flops = 0.0;
+
+}  // namespace
+
+bool conv_tc_supported(int Cin, int Cout, int H, int W) {
+  if (Cin % 64 != 0 || Cin <= 0) return false;
+  if (!(Cout == 128 || Cout == 192 || Cout == 256 || Cout == 384)) return false;
+  if (W <= 0 || W > 128 || kTileM % W != 0) return false;
+  return H % (kTileM / W) == 0;
+}
+
+void conv_tc_prepare(ConvWeightsTC& w, const float* kernel, const float* bias, int ksize, int Cin, int Cout,
+                     int dilation) {
+  conv_tc_release(w);
+  ASEP_CHECK(ksize == 1 || ksize == 3, ASEP_ERR_UNSUPPORTED, "conv kernel size %d (1 or 3 expected)", ksize);
+  ASEP_CHECK(Cin % 64 == 0, ASEP_ERR_UNSUPPORTED, "tcgen05 conv needs Cin %% 64 == 0 (got %d)", Cin);
+  const int taps = ksize * ksize, kpanels = Cin / 64;
+  std::vector<__nv_bfloat16> img((size_t)taps * kpanels * Cout * 64);
+  size_t base = 0;
+  for (int tap = 0; tap < taps; ++tap)
+    for (int kp = 0; kp < kpanels; ++kp) {
+      for (int r = 0; r < Cout; ++r)
+        for (int k = 0; k < 64; ++k) {
+          const float v = kernel[((size_t)tap * Cin + kp * 64 + k) * Cout + r];       // HWIO
+          const size_t off = (size_t)r * 64 + (size_t)((((k >> 3) ^ (r & 7)) << 3) + (k & 7));
+          img[base + off] = __float2bfloat16(v);
+        }
+      base += (size_t)Cout * 64;
+    }
+  w.bytes = img.size() * sizeof(__nv_bfloat16);
+  CUDA_CHECK(cudaMalloc(&w.img, w.bytes));
+  CUDA_CHECK(cudaMemcpy(w.img, img.data(), w.bytes, cudaMemcpyHostToDevice));
+  if (bias) {
+    CUDA_CHECK(cudaMalloc(&w.bias, (size_t)Cout * sizeof(float)));
+    CUDA_CHECK(cudaMemcpy(w.bias, bias, (size_t)Cout * sizeof(float), cudaMemcpyHostToDevice));
+  }
+  w.Cin = Cin; w.Cout = Cout; w.ksize = ksize; w.dil = dilation;
+}
+
+void conv_tc_release(ConvWeightsTC& w) {
+  if (w.img) cudaFree(w.img);
+  if (w.bias) cudaFree(w.bias);
+  w = ConvWeightsTC{};
+}
+
+void conv_tc_forward(const ConvWeightsTC& w, const __nv_bfloat16* xin, const float* add, float* out, int N, int H,
+                     int W, cudaStream_t s) {
+  if (N == 0) return;
+  ASEP_CHECK(conv_tc_supported(w.Cin, w.Cout, H, W), ASEP_ERR_UNSUPPORTED,
+             "tcgen05 conv: unsupported shape Cin=%d Cout=%d H=%d W=%d", w.Cin, w.Cout, H, W);
+  if (g_sms == 0) {
+    int dev = 0;
+    CUDA_CHECK(cudaGetDevice(&dev));
+    CUDA_CHECK(cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  ConvParams prm{};
+  prm.wimg = w.img; prm.bias = w.bias; prm.add = add; prm.out = out;
+  prm.Cout = w.Cout; prm.kpanels = w.Cin / 64; prm.taps = w.ksize * w.ksize; prm.dil = w.dil;
+  prm.H = H; prm.W = W; prm.rows_per_tile = kTileM / W; prm.tiles_per_img = H / prm.rows_per_tile;
+  prm.num_tiles = N * prm.tiles_per_img;
+  prm.nsplit = w.Cout > 256 ? 2 : 1;
+  prm.ncols = w.Cout / prm.nsplit;
+  prm.nbuf = w.Cout <= 256 ? 2 : 1;
+  prm.b_bytes = w.Cout * 128;
+  prm.stage_bytes = kABytes + prm.b_bytes;
+  prm.stages = std::min(kMaxStages, kSmemBudget / prm.stage_bytes);
+  const int smem_bytes = prm.stages * prm.stage_bytes + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_CHECK(cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  const CUtensorMap& tmap = activation_map(xin, N, H, W, w.Cin);
+  const int grid = std::min(prm.num_tiles, g_sms);
+  ProfRec rec{};
+  if (g_prof_on) {
+    if (!g_pool.empty()) { rec = g_pool.back(); g_pool.pop_back(); }
+    else { CUDA_CHECK(cudaEventCreate(&rec.a)); CUDA_CHECK(cudaEventCreate(&rec.b)); }
+    CUDA_CHECK(cudaEventRecord(rec.a, s));
+  }
+  k_conv_tc<<<grid, kThreads, smem_bytes, s>>>(tmap, prm);
+  ASEP_LAUNCH_CHECK();
+  if (g_prof_on) {
+    CUDA_CHECK(cudaEventRecord(rec.b, s));
+    g_recs.push_back(rec);
+    g_flops += 2.0 * (double)N * H * W * prm.taps * w.Cin * w.Cout;
+  }
+}
+
+void conv_tc_profile(int on) {
+  g_prof_on = on != 0;
+  if (g_prof_on) {
+    for (auto& r : g_recs) g_pool.push_back(r);
+    g_recs.clear();
+    g_flops = 0.0;
+  }
+}
+
+void conv_tc_profile_read(double* total_ms, long long* launches, double* flops) {
+  double ms = 0.0;
+  for (auto& r : g_recs) {
+    CUDA_CHECK(cudaEventSynchronize(r.b));
+    float t = 0.f;
+    CUDA_CHECK(cudaEventElapsedTime(&t, r.a, r.b));
+    ms += t;
+  }
+  if (total_ms) *total_ms = ms;
+  if (launches) *launches = (long long)g_recs.size();
+  if (flops) *flops = g_flops;
+}
+
+}  // namespace asep

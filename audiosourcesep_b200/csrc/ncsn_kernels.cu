@@ -1,0 +1,314 @@
+// HBM-bound kernels of the NCSN score networks: conditional instance-norm++ statistics and coefficients,
+// normalise + ELU + bf16 cast (the producer of every tcgen05 convolution operand), 5x5 'same' average / max
+// pooling, 2x2 average pooling, bilinear x2 up-sampling, the 1-channel begin convolution and the 1-channel end
+// convolution.  Reference: ncsn/score_network.py:7-221, ncsn/score_network_v2.py:6-199 (layer semantics restated
+// in oracle/ncsn_oracle.py).  All tensors NHWC; channels are the fastest index so every warp access is coalesced.
+#include "ncsn_kernels.h"
+
+namespace asep {
+
+namespace {
+
+constexpr float kInEps = 1e-3f;     // tfa.InstanceNormalization epsilon
+constexpr double kPlusEps = 1e-5;   // score_network.py:205
+
+__device__ __forceinline__ float elu(float v) { return v > 0.f ? v : expm1f(v); }
+
+// ---- per-(n,c) sum and sum of squares over H*W.  grid (chunks, N); thread t owns channel t % C.
+__global__ void __launch_bounds__(384) k_in_stats(const float* __restrict__ x, double* __restrict__ sums, int HW, int C,
+                                                  int rows_per_block) {
+  extern __shared__ float red[];                // [2][blockDim]
+  const int n = blockIdx.y;
+  const int c = threadIdx.x % C, r0 = threadIdx.x / C, rstep = blockDim.x / C;
+  const int rbeg = blockIdx.x * rows_per_block, rend = min(HW, rbeg + rows_per_block);
+  float s = 0.f, ss = 0.f;
+  if (r0 < rstep) {
+    const float* base = x + ((size_t)n * HW) * C + c;
+    for (int r = rbeg + r0; r < rend; r += rstep) {
+      const float v = base[(size_t)r * C];
+      s += v;
+      ss = fmaf(v, v, ss);
+    }
+  }
+  red[threadIdx.x] = s;
+  red[blockDim.x + threadIdx.x] = ss;
+  __syncthreads();
+  if (threadIdx.x < C) {
+    float a = 0.f, b = 0.f;
+    for (int g = 0; g < rstep; ++g) { a += red[g * C + threadIdx.x]; b += red[blockDim.x + g * C + threadIdx.x]; }
+    atomicAdd(sums + ((size_t)n * C + threadIdx.x) * 2, (double)a);
+    atomicAdd(sums + ((size_t)n * C + threadIdx.x) * 2 + 1, (double)b);
+  }
+}
+
+// ---- out = gamma*(gin*(x-mu)*rsqrt(var+eps)+bin) + alpha*mu_tilde + beta  ==  a*x + b per (n,c).  grid N.
+__global__ void __launch_bounds__(512) k_in_coef(const double* __restrict__ sums, const float* __restrict__ gab,
+                                                 int gab_stride_n, const int* __restrict__ idx,
+                                                 const float* __restrict__ in_gamma, const float* __restrict__ in_beta,
+                                                 float2* __restrict__ coef, int HW, int C) {
+  __shared__ double sh[2][16];
+  __shared__ double stat[2];
+  const int n = blockIdx.x, c = threadIdx.x;
+  double mu = 0.0, var = 0.0;
+  if (c < C) {
+    mu = sums[((size_t)n * C + c) * 2] / HW;
+    var = sums[((size_t)n * C + c) * 2 + 1] / HW - mu * mu;
+    if (var < 0.0) var = 0.0;
+  }
+  // cross-channel mean / population variance of the per-channel means
+  double a = c < C ? mu : 0.0, b = c < C ? mu * mu : 0.0;
+  for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+  if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = a; sh[1][threadIdx.x >> 5] = b; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double ta = 0.0, tb = 0.0;
+    for (int i = 0; i < (blockDim.x + 31) / 32; ++i) { ta += sh[0][i]; tb += sh[1][i]; }
+    const double m = ta / C;
+    double v = tb / C - m * m;
+    if (v < 0.0) v = 0.0;
+    stat[0] = m;
+    stat[1] = v;
+  }
+  __syncthreads();
+  if (c >= C) return;
+  const double mt = (mu - stat[0]) / sqrt(stat[1] + kPlusEps);
+  const float* row = gab + (size_t)(idx ? idx[n] : 0) * gab_stride_n;      // [gamma | alpha | beta]
+  const float gamma = row[c], alpha = row[C + c], beta = row[2 * C + c];
+  const float rs = rsqrtf((float)var + kInEps);
+  const float gi = in_gamma[c], bi = in_beta[c];
+  const float aa = gamma * gi * rs;
+  const float bb = gamma * (bi - gi * (float)mu * rs) + alpha * (float)mt + beta;
+  coef[(size_t)n * C + c] = make_float2(aa, bb);
+}
+
+// ---- y_bf16 = act(a*x+b), 8 channels per thread
+__global__ void __launch_bounds__(256) k_prep(const float* __restrict__ x, const float2* __restrict__ coef,
+                                              __nv_bfloat16* __restrict__ y, long long nvec, int HWC, int C, int do_elu) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nvec) return;
+  const long long e = i * 8;
+  const float4 v0 = reinterpret_cast<const float4*>(x + e)[0], v1 = reinterpret_cast<const float4*>(x + e)[1];
+  float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+  if (coef) {
+    const int n = (int)(e / HWC), c0 = (int)(e % C);
+    const float2* cf = coef + (size_t)n * C + c0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { const float2 ab = __ldg(cf + k); v[k] = fmaf(ab.x, v[k], ab.y); }
+  }
+  if (do_elu) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = elu(v[k]);
+  }
+  uint4 o;
+  __nv_bfloat162 t;
+  t = __floats2bfloat162_rn(v[0], v[1]); o.x = *reinterpret_cast<uint32_t*>(&t);
+  t = __floats2bfloat162_rn(v[2], v[3]); o.y = *reinterpret_cast<uint32_t*>(&t);
+  t = __floats2bfloat162_rn(v[4], v[5]); o.z = *reinterpret_cast<uint32_t*>(&t);
+  t = __floats2bfloat162_rn(v[6], v[7]); o.w = *reinterpret_cast<uint32_t*>(&t);
+  reinterpret_cast<uint4*>(y + e)[0] = o;
+}
+
+// ---- 5x5 stride-1 'same' pooling: average over the in-bounds taps / max ignoring out-of-bounds taps
+template <bool kMax>
+__global__ void __launch_bounds__(256) k_pool5(const float* __restrict__ x, float* __restrict__ y, int H, int W, int C4,
+                                               long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = (int)(i % C4);
+  long long p = i / C4;
+  const int w = (int)(p % W), h = (int)((p / W) % H);
+  const long long img = p / ((long long)W * H);
+  const float4* base = reinterpret_cast<const float4*>(x) + img * H * W * C4 + c;
+  float4 acc = kMax ? make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY) : make_float4(0.f, 0.f, 0.f, 0.f);
+  int cnt = 0;
+  for (int dy = -2; dy <= 2; ++dy) {
+    const int hh = h + dy;
+    if (hh < 0 || hh >= H) continue;
+    for (int dx = -2; dx <= 2; ++dx) {
+      const int ww = w + dx;
+      if (ww < 0 || ww >= W) continue;
+      const float4 v = __ldg(base + ((long long)hh * W + ww) * C4);
+      if (kMax) { acc.x = fmaxf(acc.x, v.x); acc.y = fmaxf(acc.y, v.y); acc.z = fmaxf(acc.z, v.z); acc.w = fmaxf(acc.w, v.w); }
+      else { acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w; }
+      ++cnt;
+    }
+  }
+  if (!kMax) { const float r = 1.f / (float)cnt; acc.x *= r; acc.y *= r; acc.z *= r; acc.w *= r; }
+  reinterpret_cast<float4*>(y)[i] = acc;
+}
+
+// ---- 2x2 stride-2 average pooling (H, W = output size)
+__global__ void __launch_bounds__(256) k_avgpool2(const float* __restrict__ x, float* __restrict__ y, int H, int W, int C4,
+                                                  long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = (int)(i % C4);
+  long long p = i / C4;
+  const int w = (int)(p % W), h = (int)((p / W) % H);
+  const long long img = p / ((long long)W * H);
+  const float4* base = reinterpret_cast<const float4*>(x) + (img * 2 * H * 2 * W) * C4 + c;
+  const long long r0 = ((long long)(2 * h) * 2 * W + 2 * w) * C4, r1 = r0 + (long long)2 * W * C4;
+  const float4 a = __ldg(base + r0), b = __ldg(base + r0 + C4), d = __ldg(base + r1), e = __ldg(base + r1 + C4);
+  reinterpret_cast<float4*>(y)[i] = make_float4(0.25f * (a.x + b.x + d.x + e.x), 0.25f * (a.y + b.y + d.y + e.y),
+                                                0.25f * (a.z + b.z + d.z + e.z), 0.25f * (a.w + b.w + d.w + e.w));
+}
+
+// ---- y[N,2h,2w,C] = add + bilinear_x2(x[N,h,w,C]) (half-pixel centres, edge clamp; tf.image.resize bilinear)
+__global__ void __launch_bounds__(256) k_resize2x_add(const float* __restrict__ x, const float* __restrict__ add,
+                                                      float* __restrict__ y, int h, int w, int C4, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int H = 2 * h, W = 2 * w;
+  const int c = (int)(i % C4);
+  long long p = i / C4;
+  const int ox = (int)(p % W), oy = (int)((p / W) % H);
+  const long long img = p / ((long long)W * H);
+  const float sy = fmaxf(0.f, (oy + 0.5f) * 0.5f - 0.5f), sx = fmaxf(0.f, (ox + 0.5f) * 0.5f - 0.5f);
+  const int y0 = (int)sy, x0 = (int)sx;
+  const int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
+  const float fy = sy - y0, fx = sx - x0;
+  const float4* base = reinterpret_cast<const float4*>(x) + img * h * w * C4 + c;
+  const float4 a = __ldg(base + ((long long)y0 * w + x0) * C4), b = __ldg(base + ((long long)y0 * w + x1) * C4);
+  const float4 d = __ldg(base + ((long long)y1 * w + x0) * C4), e = __ldg(base + ((long long)y1 * w + x1) * C4);
+  float4 o;
+  o.x = (1.f - fy) * ((1.f - fx) * a.x + fx * b.x) + fy * ((1.f - fx) * d.x + fx * e.x);
+  o.y = (1.f - fy) * ((1.f - fx) * a.y + fx * b.y) + fy * ((1.f - fx) * d.y + fx * e.y);
+  o.z = (1.f - fy) * ((1.f - fx) * a.z + fx * b.z) + fy * ((1.f - fx) * d.z + fx * e.z);
+  o.w = (1.f - fy) * ((1.f - fx) * a.w + fx * b.w) + fy * ((1.f - fx) * d.w + fx * e.w);
+  if (add) { const float4 t = reinterpret_cast<const float4*>(add)[i]; o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
+  reinterpret_cast<float4*>(y)[i] = o;
+}
+
+// ---- mode 0: y = elu(x); mode 1: y = x + z
+__global__ void __launch_bounds__(256) k_ew(const float* __restrict__ x, const float* __restrict__ z, float* __restrict__ y,
+                                            long long nvec, int mode) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nvec) return;
+  float4 v = reinterpret_cast<const float4*>(x)[i];
+  if (mode == 0) { v.x = elu(v.x); v.y = elu(v.y); v.z = elu(v.z); v.w = elu(v.w); }
+  else { const float4 t = reinterpret_cast<const float4*>(z)[i]; v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
+  reinterpret_cast<float4*>(y)[i] = v;
+}
+
+// ---- begin_conv: 3x3 'same', 1 -> Cout channels, bias; v1 rescales the input 2x-1 first (score_network.py:277-280)
+__global__ void __launch_bounds__(256) k_begin_conv(const float* __restrict__ x, const float* __restrict__ k,
+                                                    const float* __restrict__ bias, float* __restrict__ y, int H, int W,
+                                                    int C4, int rescale, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = (int)(i % C4);
+  long long p = i / C4;
+  const int w = (int)(p % W), h = (int)((p / W) % H);
+  float4 acc = __ldg(reinterpret_cast<const float4*>(bias) + c);
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    const int hh = h + tap / 3 - 1, ww = w + tap % 3 - 1;
+    if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
+    float v = __ldg(x + p + (long long)(tap / 3 - 1) * W + (tap % 3 - 1));
+    if (rescale) v = 2.f * v - 1.f;
+    const float4 kk = __ldg(reinterpret_cast<const float4*>(k) + tap * C4 + c);
+    acc.x = fmaf(v, kk.x, acc.x); acc.y = fmaf(v, kk.y, acc.y); acc.z = fmaf(v, kk.z, acc.z); acc.w = fmaf(v, kk.w, acc.w);
+  }
+  reinterpret_cast<float4*>(y)[i] = acc;
+}
+
+// ---- end_conv: 3x3 'same', C -> 1 channel, bias, optional division by sigma[idx[n]]; one warp per pixel
+__global__ void __launch_bounds__(256) k_end_conv(const __nv_bfloat16* __restrict__ x, const float* __restrict__ k,
+                                                  float bias, const float* __restrict__ sigmas, const int* __restrict__ idx,
+                                                  float* __restrict__ y, int H, int W, int C, long long pixels) {
+  const long long p = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (p >= pixels) return;
+  const int w = (int)(p % W), h = (int)((p / W) % H);
+  float acc = 0.f;
+  for (int tap = 0; tap < 9; ++tap) {
+    const int hh = h + tap / 3 - 1, ww = w + tap % 3 - 1;
+    if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
+    const __nv_bfloat162* row = reinterpret_cast<const __nv_bfloat162*>(x + (p + (long long)(tap / 3 - 1) * W + (tap % 3 - 1)) * C);
+    const float2* kr = reinterpret_cast<const float2*>(k + (size_t)tap * C);
+    for (int c2 = lane; c2 < C / 2; c2 += 32) {
+      const float2 v = __bfloat1622float2(row[c2]);
+      const float2 kk = __ldg(kr + c2);
+      acc = fmaf(v.x, kk.x, acc);
+      acc = fmaf(v.y, kk.y, acc);
+    }
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) {
+    float o = acc + bias;
+    if (sigmas) o /= sigmas[idx[p / ((long long)H * W)]];
+    y[p] = o;
+  }
+}
+
+}  // namespace
+
+void launch_in_stats(const float* x, double* sums, int N, int HW, int C, cudaStream_t s) {
+  CUDA_CHECK(cudaMemsetAsync(sums, 0, (size_t)N * C * 2 * sizeof(double), s));
+  ASEP_CHECK(C <= 384, ASEP_ERR_UNSUPPORTED, "instance-norm statistics: C = %d > 384", C);
+  const int threads = C * (384 / C);
+  const int rows = 256;
+  dim3 grid((HW + rows - 1) / rows, N);
+  k_in_stats<<<grid, threads, 2 * threads * sizeof(float), s>>>(x, sums, HW, C, rows);
+  ASEP_LAUNCH_CHECK();
+}
+
+void launch_in_coef(const double* sums, const float* gab, int gab_stride_n, const int* idx, const float* in_gamma,
+                    const float* in_beta, float2* coef, int N, int HW, int C, cudaStream_t s) {
+  const int threads = (C + 31) / 32 * 32;
+  ASEP_CHECK(threads <= 512, ASEP_ERR_UNSUPPORTED, "instance-norm coefficients: C = %d > 512", C);
+  k_in_coef<<<N, threads, 0, s>>>(sums, gab, gab_stride_n, idx, in_gamma, in_beta, coef, HW, C);
+  ASEP_LAUNCH_CHECK();
+}
+
+void launch_prep(const float* x, const float2* coef, __nv_bfloat16* y, int N, int HW, int C, int do_elu, cudaStream_t s) {
+  ASEP_CHECK(C % 8 == 0, ASEP_ERR_UNSUPPORTED, "prep: C %% 8 != 0");
+  const long long nvec = (long long)N * HW * C / 8;
+  k_prep<<<cdiv(nvec, 256), 256, 0, s>>>(x, coef, y, nvec, HW * C, C, do_elu);
+  ASEP_LAUNCH_CHECK();
+}
+
+void launch_pool5(const float* x, float* y, int N, int H, int W, int C, int is_max, cudaStream_t s) {
+  const long long total = (long long)N * H * W * (C / 4);
+  if (is_max) k_pool5<true><<<cdiv(total, 256), 256, 0, s>>>(x, y, H, W, C / 4, total);
+  else k_pool5<false><<<cdiv(total, 256), 256, 0, s>>>(x, y, H, W, C / 4, total);
+  ASEP_LAUNCH_CHECK();
+}
+
+void launch_avgpool2(const float* x, float* y, int N, int Hout, int Wout, int C, cudaStream_t s) {
+  const long long total = (long long)N * Hout * Wout * (C / 4);
+  k_avgpool2<<<cdiv(total, 256), 256, 0, s>>>(x, y, Hout, Wout, C / 4, total);
+  ASEP_LAUNCH_CHECK();
+}
+
+void launch_resize2x_add(const float* x, const float* add, float* y, int N, int h, int w, int C, cudaStream_t s) {
+  const long long total = (long long)N * 4 * h * w * (C / 4);
+  k_resize2x_add<<<cdiv(total, 256), 256, 0, s>>>(x, add, y, h, w, C / 4, total);
+  ASEP_LAUNCH_CHECK();
+}
+
+void launch_elu(const float* x, float* y, long long n, cudaStream_t s) {
+  k_ew<<<cdiv(n / 4, 256), 256, 0, s>>>(x, nullptr, y, n / 4, 0);
+  ASEP_LAUNCH_CHECK();
+}
+
+void launch_add(const float* x, const float* z, float* y, long long n, cudaStream_t s) {
+  k_ew<<<cdiv(n / 4, 256), 256, 0, s>>>(x, z, y, n / 4, 1);
+  ASEP_LAUNCH_CHECK();
+}
+
+void launch_begin_conv(const float* x, const float* k, const float* bias, float* y, int N, int H, int W, int Cout,
+                       int rescale, cudaStream_t s) {
+  const long long total = (long long)N * H * W * (Cout / 4);
+  k_begin_conv<<<cdiv(total, 256), 256, 0, s>>>(x, k, bias, y, H, W, Cout / 4, rescale, total);
+  ASEP_LAUNCH_CHECK();
+}
+
+void launch_end_conv(const __nv_bfloat16* x, const float* k, float bias, const float* sigmas, const int* idx, float* y,
+                     int N, int H, int W, int C, cudaStream_t s) {
+  const long long pixels = (long long)N * H * W;
+  k_end_conv<<<cdiv(pixels * 32, 256), 256, 0, s>>>(x, k, bias, sigmas, idx, y, H, W, C, pixels);
+  ASEP_LAUNCH_CHECK();
+}
+
+}  // namespace asep

@@ -1,0 +1,295 @@
+#include "ncsn_model.h"
+
+#include <cstring>
+
+namespace asep {
+
+NcsnModel::NcsnModel(const asep_ncsn_cfg& cfg, int device) : cfg_(cfg), device_(device), v1_(cfg.version == 1) {
+  ASEP_CHECK(cfg.version == 1 || cfg.version == 2, ASEP_ERR_BAD_ARG, "NCSN version must be 1 or 2");
+  ASEP_CHECK(cfg.C == 1, ASEP_ERR_UNSUPPORTED, "the score networks of the separation path take 1-channel patches");
+  ASEP_CHECK(cfg.ngf % 64 == 0, ASEP_ERR_UNSUPPORTED, "n_filters must be a multiple of 64 (got %d)", cfg.ngf);
+  ASEP_CHECK(conv_tc_supported(cfg.ngf, cfg.ngf, cfg.H, cfg.W) && cfg.H % 2 == 0 && cfg.W % 2 == 0 &&
+                 conv_tc_supported(2 * cfg.ngf, 2 * cfg.ngf, cfg.H / 2, cfg.W / 2),
+             ASEP_ERR_UNSUPPORTED, "patch %dx%d with %d filters is outside the tcgen05 convolution tiling", cfg.H, cfg.W,
+             cfg.ngf);
+}
+
+NcsnModel::~NcsnModel() {
+  for (auto& kv : params_)
+    if (kv.second.dev) cudaFree(kv.second.dev);
+  for (auto& kv : convs_) conv_tc_release(kv.second);
+  for (auto& kv : gab_)
+    if (kv.second) cudaFree(kv.second);
+  if (sigmas_dev_) cudaFree(sigmas_dev_);
+  if (arena_) cudaFree(arena_);
+}
+
+void NcsnModel::set_param(const std::string& name, const float* src, const std::vector<int64_t>& shape, bool on_device) {
+  int64_t n = 1;
+  for (auto v : shape) n *= v;
+  NcsnParam& p = params_[name];
+  if (p.dev && (int64_t)p.host.size() != n) { cudaFree(p.dev); p.dev = nullptr; }
+  p.shape = shape;
+  p.host.resize((size_t)n);
+  if (on_device) CUDA_CHECK(cudaMemcpy(p.host.data(), src, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost));
+  else std::memcpy(p.host.data(), src, (size_t)n * sizeof(float));
+  if (!p.dev) CUDA_CHECK(cudaMalloc(&p.dev, std::max<int64_t>(n, 1) * sizeof(float)));
+  CUDA_CHECK(cudaMemcpy(p.dev, p.host.data(), (size_t)n * sizeof(float), cudaMemcpyHostToDevice));
+  prepared_ = false;
+}
+
+void NcsnModel::set_sigmas(const float* sigmas, int n) {
+  if (sigmas_dev_) cudaFree(sigmas_dev_);
+  CUDA_CHECK(cudaMalloc(&sigmas_dev_, (size_t)n * sizeof(float)));
+  CUDA_CHECK(cudaMemcpy(sigmas_dev_, sigmas, (size_t)n * sizeof(float), cudaMemcpyHostToDevice));
+  n_sigmas_ = n;
+}
+
+int64_t NcsnModel::num_params() const {
+  int64_t n = 0;
+  for (auto& kv : params_) n += (int64_t)kv.second.host.size();
+  return n;
+}
+
+const NcsnParam& NcsnModel::param(const std::string& name) const {
+  auto it = params_.find(name);
+  ASEP_CHECK(it != params_.end(), ASEP_ERR_STATE, "score network parameter '%s' has not been set", name.c_str());
+  return it->second;
+}
+
+void NcsnModel::prepare() {
+  CUDA_CHECK(cudaSetDevice(device_));
+  for (auto& kv : convs_) conv_tc_release(kv.second);
+  convs_.clear();
+  for (auto& kv : gab_)
+    if (kv.second) cudaFree(kv.second);
+  gab_.clear();
+  for (auto& kv : params_) {
+    const std::string& name = kv.first;
+    const size_t pos = name.rfind('/');
+    const std::string leaf = name.substr(pos + 1), layer = name.substr(0, pos);
+    if (leaf == "kernel") {
+      if (layer == "begin_conv" || layer == "end_conv") continue;      // CUDA-core kernels (1 channel on one side)
+      const auto& sh = kv.second.shape;
+      ASEP_CHECK(sh.size() == 4 && sh[0] == sh[1], ASEP_ERR_BAD_SHAPE, "%s: expected a [k,k,Cin,Cout] kernel", name.c_str());
+      const int dil = layer.rfind("Res3_", 0) == 0 ? 2 : (layer.rfind("Res4_", 0) == 0 ? 4 : 1);   // score_network.py:259-268
+      const float* bias = has(layer + "/bias") ? param(layer + "/bias").host.data() : nullptr;
+      conv_tc_prepare(convs_[layer], kv.second.host.data(), bias, (int)sh[0], (int)sh[2], (int)sh[3], dil);
+    } else if (!v1_ && leaf == "gamma") {
+      // v2 InstanceNorm2dPlus: pack the three per-channel vectors as one [gamma | alpha | beta] row
+      const int C = (int)kv.second.host.size();
+      std::vector<float> row((size_t)3 * C);
+      std::memcpy(row.data(), kv.second.host.data(), C * sizeof(float));
+      std::memcpy(row.data() + C, param(layer + "/alpha").host.data(), C * sizeof(float));
+      std::memcpy(row.data() + 2 * C, param(layer + "/beta").host.data(), C * sizeof(float));
+      float* d = nullptr;
+      CUDA_CHECK(cudaMalloc(&d, row.size() * sizeof(float)));
+      CUDA_CHECK(cudaMemcpy(d, row.data(), row.size() * sizeof(float), cudaMemcpyHostToDevice));
+      gab_[layer] = d;
+    }
+  }
+  if (!v1_) ASEP_CHECK(sigmas_dev_ != nullptr, ASEP_ERR_STATE, "NCSN v2 needs the noise levels (asep_ncsn_set_sigmas)");
+  prepared_ = true;
+  // dry run: checks that every parameter the graph needs is present
+  dry_ = true; N_ = 1; arena_off_ = 0;
+  run(nullptr, nullptr, nullptr);
+  dry_ = false;
+}
+
+// ------------------------------------------------------------------ per-call allocation (bump arena sized by a dry run)
+void* NcsnModel::take(size_t bytes) {
+  const size_t al = (bytes + 1023) & ~(size_t)1023;
+  void* p = dry_ ? nullptr : arena_ + arena_off_;
+  if (!dry_) ASEP_CHECK(arena_off_ + al <= arena_cap_, ASEP_ERR_STATE, "score-network arena overflow");
+  arena_off_ += al;
+  return p;
+}
+NcsnModel::T NcsnModel::new_t(int H, int W, int C) {
+  T t;
+  t.H = H; t.W = W; t.C = C;
+  t.p = static_cast<float*>(take((size_t)N_ * H * W * C * sizeof(float)));
+  return t;
+}
+__nv_bfloat16* NcsnModel::new_bf(int H, int W, int C) {
+  return static_cast<__nv_bfloat16*>(take((size_t)N_ * H * W * C * sizeof(__nv_bfloat16)));
+}
+
+// ------------------------------------------------------------------ layers
+const float2* NcsnModel::norm_coef(const T& x, const std::string& name) {
+  double* sums = static_cast<double*>(take((size_t)N_ * x.C * 2 * sizeof(double)));
+  float2* coef = static_cast<float2*>(take((size_t)N_ * x.C * sizeof(float2)));
+  const NcsnParam& ig = param(name + "/in_gamma");
+  const NcsnParam& ib = param(name + "/in_beta");
+  const float* gab = nullptr;
+  int stride = 0;
+  if (v1_) {
+    const NcsnParam& e = param(name + "/embed");
+    ASEP_CHECK(e.shape.size() == 2 && e.shape[1] == 3 * x.C, ASEP_ERR_BAD_SHAPE, "%s/embed: expected [classes, %d]",
+               name.c_str(), 3 * x.C);
+    gab = e.dev;
+    stride = 3 * x.C;
+  } else {
+    auto it = gab_.find(name);
+    ASEP_CHECK(it != gab_.end(), ASEP_ERR_STATE, "norm layer '%s' has no parameters", name.c_str());
+    gab = it->second;
+  }
+  ASEP_CHECK((int)ig.host.size() == x.C && (int)ib.host.size() == x.C, ASEP_ERR_BAD_SHAPE, "%s: channel mismatch", name.c_str());
+  if (dry_) return coef;
+  launch_in_stats(x.p, sums, N_, x.H * x.W, x.C, s_);
+  launch_in_coef(sums, gab, stride, v1_ ? idx_ : nullptr, ig.dev, ib.dev, coef, N_, x.H * x.W, x.C, s_);
+  return coef;
+}
+
+__nv_bfloat16* NcsnModel::prep(const T& x, const float2* coef, bool elu) {
+  __nv_bfloat16* y = new_bf(x.H, x.W, x.C);
+  if (!dry_) launch_prep(x.p, coef, y, N_, x.H * x.W, x.C, elu ? 1 : 0, s_);
+  return y;
+}
+
+NcsnModel::T NcsnModel::conv(const std::string& name, const __nv_bfloat16* xin, int H, int W, const float* add) {
+  auto it = convs_.find(name);
+  ASEP_CHECK(it != convs_.end(), ASEP_ERR_STATE, "convolution '%s' has no kernel parameter", name.c_str());
+  const ConvWeightsTC& w = it->second;
+  T out = new_t(H, W, w.Cout);
+  if (!dry_) conv_tc_forward(w, xin, add, out.p, N_, H, W, s_);
+  return out;
+}
+
+// (Conditional)ResidualBlock: score_network.py:165-178 / score_network_v2.py:156-171
+NcsnModel::T NcsnModel::res_block(const T& x, const std::string& name, int cout, bool down, int dilation) {
+  (void)cout; (void)dilation;
+  const float2* c1 = norm_coef(x, name + "/norm1");
+  __nv_bfloat16* h = prep(x, c1, true);
+  T o1 = conv(name + "/conv1", h, x.H, x.W, nullptr);
+  const float2* c2 = norm_coef(o1, name + "/norm2");
+  __nv_bfloat16* h2 = prep(o1, c2, true);
+  const float* sc = x.p;
+  if (has(name + "/shortcut/kernel")) {
+    __nv_bfloat16* xr = prep(x, nullptr, false);
+    sc = conv(name + "/shortcut", xr, x.H, x.W, nullptr).p;
+  }
+  T o2 = conv(name + "/conv2", h2, x.H, x.W, sc);        // shortcut + output fused into the epilogue
+  const bool pool = down && name.rfind("Res2_", 0) == 0;  // only the undilated 'down' block pools (score_network.py:141-144)
+  if (!pool) return o2;
+  // avg_pool2(shortcut) + avg_pool2(output) == avg_pool2(shortcut + output)
+  T out = new_t(x.H / 2, x.W / 2, o2.C);
+  if (!dry_) launch_avgpool2(o2.p, out.p, N_, out.H, out.W, out.C, s_);
+  return out;
+}
+
+// (Cond)RCUBlock: score_network.py:47-54 (norm -> conv, no activation: quirk Q8) / score_network_v2.py:41-47
+NcsnModel::T NcsnModel::rcu(T x, const std::string& prefix, int n_blocks, int n_stages) {
+  for (int i = 0; i < n_blocks; ++i) {
+    const T residual = x;
+    for (int j = 0; j < n_stages; ++j) {
+      const std::string sfx = "_" + std::to_string(i + 1) + "_" + std::to_string(j + 1);
+      const float2* c = v1_ ? norm_coef(x, prefix + "/norm" + sfx) : nullptr;
+      __nv_bfloat16* h = prep(x, c, false);
+      x = conv(prefix + "/conv" + sfx, h, x.H, x.W, j == n_stages - 1 ? residual.p : nullptr);
+    }
+  }
+  return x;
+}
+
+// (Cond)CRPBlock: score_network.py:20-28 (norm -> 5x5 avg-pool -> conv) / score_network_v2.py:15-25 (5x5 max-pool -> conv)
+NcsnModel::T NcsnModel::crp(T x, const std::string& prefix) {
+  T acc = new_t(x.H, x.W, x.C);
+  if (!dry_) launch_elu(x.p, acc.p, (long long)N_ * x.H * x.W * x.C, s_);
+  T path = acc;
+  for (int i = 0; i < 2; ++i) {
+    const std::string sfx = "_" + std::to_string(i + 1);
+    // avg over the in-bounds taps commutes with the per-(n,c) affine of the norm: pool first, normalise while casting
+    const float2* c = v1_ ? norm_coef(path, prefix + "/norm" + sfx) : nullptr;
+    T pooled = new_t(x.H, x.W, x.C);
+    if (!dry_) launch_pool5(path.p, pooled.p, N_, x.H, x.W, x.C, v1_ ? 0 : 1, s_);
+    __nv_bfloat16* h = prep(pooled, c, false);
+    path = conv(prefix + "/conv" + sfx, h, x.H, x.W, nullptr);
+    T sum = new_t(x.H, x.W, x.C);
+    if (!dry_) launch_add(acc.p, path.p, sum.p, (long long)N_ * x.H * x.W * x.C, s_);
+    acc = sum;
+  }
+  return acc;
+}
+
+// (Cond)MSFBlock: score_network.py:70-79 / score_network_v2.py:61-69
+NcsnModel::T NcsnModel::msf(const std::vector<T>& xs, const std::string& prefix, int H, int W, int features) {
+  (void)features;
+  T sums;
+  // same-resolution branches first so their sum can ride in the convolution epilogue
+  for (int pass = 0; pass < 2; ++pass)
+    for (size_t i = 0; i < xs.size(); ++i) {
+      const T& xi = xs[i];
+      const bool same = xi.H == H && xi.W == W;
+      if (same != (pass == 0)) continue;
+      const std::string sfx = "_" + std::to_string(i + 1);
+      const float2* c = v1_ ? norm_coef(xi, prefix + "/norm" + sfx) : nullptr;
+      __nv_bfloat16* h = prep(xi, c, false);
+      if (same) {
+        sums = conv(prefix + "/conv" + sfx, h, xi.H, xi.W, sums.p);
+      } else {
+        ASEP_CHECK(2 * xi.H == H && 2 * xi.W == W, ASEP_ERR_UNSUPPORTED, "MSF resize other than x2");
+        T low = conv(prefix + "/conv" + sfx, h, xi.H, xi.W, nullptr);
+        T up = new_t(H, W, low.C);
+        if (!dry_) launch_resize2x_add(low.p, sums.p, up.p, N_, xi.H, xi.W, low.C, s_);
+        sums = up;
+      }
+    }
+  return sums;
+}
+
+// (Cond)RefineBlock: score_network.py:103-118 / score_network_v2.py:93-107
+NcsnModel::T NcsnModel::refine(const std::vector<T>& xs, const std::string& name, int features, bool end, int H, int W) {
+  std::vector<T> hs;
+  for (size_t i = 0; i < xs.size(); ++i) hs.push_back(rcu(xs[i], name + "/RCU_" + std::to_string(i + 1), 2, 2));
+  T h = xs.size() > 1 ? msf(hs, name + "/MSF", H, W, features) : hs[0];
+  h = crp(h, name + "/CRP");
+  return rcu(h, name + "/RCU_output", end ? 3 : 1, 2);
+}
+
+void NcsnModel::run(const float* x, const int* idx, float* score) {
+  const int H = cfg_.H, W = cfg_.W, ngf = cfg_.ngf;
+  idx_ = idx;
+  T out = new_t(H, W, ngf);
+  const NcsnParam& bk = param("begin_conv/kernel");
+  const NcsnParam& bb = param("begin_conv/bias");
+  ASEP_CHECK((int64_t)bk.host.size() == 9 * ngf && (int)bb.host.size() == ngf, ASEP_ERR_BAD_SHAPE, "begin_conv shape");
+  if (!dry_) launch_begin_conv(x, bk.dev, bb.dev, out.p, N_, H, W, ngf, v1_ ? 1 : 0, s_);   // 2x-1 only in v1 (Q10)
+  T l1 = res_block(res_block(out, "Res1_1", ngf, false, 0), "Res1_2", ngf, false, 0);
+  T l2 = res_block(res_block(l1, "Res2_1", 2 * ngf, true, 0), "Res2_2", 2 * ngf, false, 0);
+  T l3 = res_block(res_block(l2, "Res3_1", 2 * ngf, true, 2), "Res3_2", 2 * ngf, false, 2);
+  T l4 = res_block(res_block(l3, "Res4_1", 2 * ngf, true, 4), "Res4_2", 2 * ngf, false, 4);
+  T r1 = refine({l4}, "refine1", 2 * ngf, false, l4.H, l4.W);
+  T r2 = refine({l3, r1}, "refine2", 2 * ngf, false, l3.H, l3.W);
+  T r3 = refine({l2, r2}, "refine3", ngf, false, l2.H, l2.W);
+  T o = refine({l1, r3}, "refine4", ngf, true, l1.H, l1.W);
+  const float2* c = norm_coef(o, "normalizer");
+  __nv_bfloat16* h = prep(o, c, true);
+  const NcsnParam& ek = param("end_conv/kernel");
+  const NcsnParam& eb = param("end_conv/bias");
+  ASEP_CHECK((int64_t)ek.host.size() == 9 * ngf && eb.host.size() == 1, ASEP_ERR_BAD_SHAPE, "end_conv shape");
+  if (!dry_)
+    launch_end_conv(h, ek.dev, eb.host[0], v1_ ? nullptr : sigmas_dev_, v1_ ? nullptr : idx, score, N_, H, W, ngf, s_);
+}
+
+void NcsnModel::forward(const float* x, const int* idx, float* score, int N, cudaStream_t s) {
+  if (N == 0) return;
+  ASEP_CHECK(prepared_, ASEP_ERR_STATE, "asep_ncsn_prepare() must be called after setting parameters");
+  CUDA_CHECK(cudaSetDevice(device_));
+  s_ = s;
+  N_ = N;
+  dry_ = true; arena_off_ = 0;
+  run(nullptr, nullptr, nullptr);
+  const size_t need = arena_off_;
+  dry_ = false;
+  if (need > arena_cap_) {
+    CUDA_CHECK(cudaDeviceSynchronize());
+    if (arena_) cudaFree(arena_);
+    arena_ = nullptr;
+    CUDA_CHECK(cudaMalloc(&arena_, need));
+    arena_cap_ = need;
+  }
+  arena_off_ = 0;
+  run(x, idx, score);
+}
+
+}  // namespace asep

@@ -1,0 +1,77 @@
+"""Host-side mirror of ``flow_models/flow_builder.build_glow`` (reference: flow_builder.py:60-146).
+
+Returns the object the reference's scripts treat as ``tfd.TransformedDistribution``: ``log_prob(x)``,
+``sample(n)``, ``trainable_variables`` / ``variables`` and ``bijector`` (the ``Invert(Chain([glow,
+SpecPreprocessing]))`` view), all executing in libasep.so.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+import torch
+
+from .. import _lib
+from ..config import GlowConfig
+from ..glow import Glow
+from ..weights import init_glow_params
+
+
+class _InvertedChainView:
+    """``tfb.Invert(tfb.Chain([glow, preprocessing]))``: forward = chain.inverse, inverse = chain.forward."""
+
+    def __init__(self, model: Glow):
+        self._m = model
+
+    def forward(self, z):
+        return self._m.inverse(z)
+
+    def inverse(self, x):
+        return self._m.forward(x)
+
+    def inverse_log_det_jacobian(self, x, event_ndims=3):
+        return self._m.forward_log_det_jacobian(x)
+
+    def forward_log_det_jacobian(self, z, event_ndims=3):
+        return -self._m.forward_log_det_jacobian(self._m.inverse(z))
+
+
+class GlowDistribution(Glow):
+    """TransformedDistribution(prior, Invert(Chain([glow, SpecPreprocessing]))) (flow_builder.py:127-144)."""
+
+    @property
+    def bijector(self):
+        return _InvertedChainView(self)
+
+    def event_shape(self):
+        return (self.cfg.H, self.cfg.W, self.cfg.C)
+
+
+def build_glow(minibatch, data_shape, L=3, K=32, n_filters=512, learntop=True, l2_reg=None,
+               mirrored_strategy=None, data_type="image", seed: int = 0, precision: Optional[int] = None,
+               params=None, **kwargs) -> GlowDistribution:
+    """Same signature as the reference.  ``l2_reg`` is accepted and ignored exactly as the reference's
+    custom training loop ignores the Keras regulariser losses; ``mirrored_strategy`` is
+    accepted for call compatibility (data parallelism is one process per GPU here).  ``data_type`` other
+    than "melspec" (ImgPreprocessing) is outside the separation hot path.
+
+    kwargs: minval, maxval, use_logit, alpha (SpecPreprocessing, flow_tfp_bijectors.py:364-370).
+    ``params`` (name -> array) overrides the random init; ``minibatch`` (raw data units) drives the
+    data-dependent ActNorm init when given."""
+    if L not in (2, 3, 4):
+        raise ValueError("L should be 2, 3 or 4")
+    if data_type == "image":
+        raise NotImplementedError("ImgPreprocessing (MNIST/CIFAR toy data) is outside the separation hot path")
+    if kwargs.get("use_logit", False):
+        raise NotImplementedError("use_logit=True is not used by the melspec configs")
+    minval, maxval = float(kwargs.get("minval", -100.0)), float(kwargs.get("maxval", 20.0))
+    H, W, C = (int(v) for v in data_shape)
+    cfg = GlowConfig(H=H, W=W, C=C, L=L, K=K, n_filters=n_filters, learntop=bool(learntop), minval=minval, maxval=maxval)
+    if precision is None:
+        precision = _lib.PREC_BF16 if n_filters == 512 else _lib.PREC_FP32
+    flow = GlowDistribution(cfg, params if params is not None else init_glow_params(cfg, seed=seed, mode="faithful"),
+                            precision=precision)
+    if minibatch is not None and params is None:
+        flow.init_actnorm(torch.as_tensor(np.asarray(minibatch) if not torch.is_tensor(minibatch) else minibatch,
+                                          dtype=torch.float32))
+    return flow

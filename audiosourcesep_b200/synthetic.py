@@ -31,12 +31,12 @@ def mel_patches_db(n: int, seed: int, H: int = 96, W: int = 64) -> np.ndarray:
     f = _ar1(f, 0.78, 1)
     f = _ar1(f, 0.96, 2)
     db = np.clip(-46.0 + 19.0 * f, DB_MIN, DB_MAX)
-    return db.astype(np.float32)[..., None]
+    return np.ascontiguousarray(db.astype(np.float32))[..., None]
 
 
 def normalise(db: np.ndarray) -> np.ndarray:
     """(x - min) / (max - min)  (reference: run_basis_sep.py:355)."""
-    return ((db - DB_MIN) / (DB_MAX - DB_MIN)).astype(np.float32)
+    return np.ascontiguousarray((db - DB_MIN) / (DB_MAX - DB_MIN), dtype=np.float32)
 
 
 def mixture_db(a_db: np.ndarray, b_db: np.ndarray) -> np.ndarray:
