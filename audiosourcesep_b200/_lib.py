@@ -41,6 +41,11 @@ class DLTensor(ctypes.Structure):
                 ("byte_offset", ctypes.c_uint64)]
 
 
+class NcsnCfg(ctypes.Structure):
+    _fields_ = [("version", ctypes.c_int32), ("H", ctypes.c_int32), ("W", ctypes.c_int32), ("C", ctypes.c_int32),
+                ("ngf", ctypes.c_int32), ("num_classes", ctypes.c_int32)]
+
+
 class GlowCfg(ctypes.Structure):
     _fields_ = [("H", ctypes.c_int32), ("W", ctypes.c_int32), ("C", ctypes.c_int32), ("L", ctypes.c_int32),
                 ("K", ctypes.c_int32), ("n_filters", ctypes.c_int32), ("learntop", ctypes.c_int32),
@@ -77,6 +82,16 @@ _SIGNATURES = {
     "asep_mixing_db": [_P, _P, _P, _P, _P, _V],
     "asep_philox_normal": [_P, _U64, _U64, _U64, _U64, _V],
     "asep_basis_glow_inner": [_V, _V, _P, _P, _P, _I, _F, _F, _F, _P, _P, _U64, _U64, _U64, _P, _P, _V],
+    "asep_ncsn_create": [ctypes.POINTER(NcsnCfg), ctypes.POINTER(_V)],
+    "asep_ncsn_destroy": [_V],
+    "asep_ncsn_set_param": [_V, ctypes.c_char_p, _P],
+    "asep_ncsn_set_sigmas": [_V, _P],
+    "asep_ncsn_prepare": [_V],
+    "asep_ncsn_forward": [_V, _P, _P, _P, _V],
+    "asep_basis_ncsn_inner": [_V, _V, _P, _P, _P, _I, _I, _F, _F, _F, _P, _P, _U64, _U64, _U64, _P, _P, _V],
+    "asep_conv_profile": [_I],
+    "asep_conv_profile_read": [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64),
+                               ctypes.POINTER(ctypes.c_double)],
     "asep_tc_set_cluster": [_I],
     "asep_tc_profile": [_I],
     "asep_tc_profile_read": [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64),
@@ -131,6 +146,16 @@ def init(device: Optional[int] = None) -> int:
 
 def launch_count() -> int:
     return int(load().asep_launch_count())
+
+
+def conv_profile(on: bool) -> None:
+    check(load().asep_conv_profile(int(on)))
+
+
+def conv_profile_read():
+    ms, n, fl = ctypes.c_double(), ctypes.c_int64(), ctypes.c_double()
+    check(load().asep_conv_profile_read(ctypes.byref(ms), ctypes.byref(n), ctypes.byref(fl)))
+    return ms.value, n.value, fl.value
 
 
 def tc_profile(on: bool) -> None:

@@ -5,6 +5,7 @@
 #include <memory>
 
 #include "glow_model.h"
+#include "ncsn_model.h"
 
 namespace asep {
 
@@ -87,6 +88,9 @@ using namespace asep;
 
 struct asep_glow_s {
   std::unique_ptr<GlowModel> model;
+};
+struct asep_ncsn_s {
+  std::unique_ptr<NcsnModel> model;
 };
 
 #define ASEP_API_BEGIN try {
@@ -469,6 +473,150 @@ int asep_basis_glow_inner(asep_glow_t m1, asep_glow_t m2, const DLTensor* mixed,
     throw;
   }
   cudaFree(s1); cudaFree(s2);
+  ASEP_API_END
+}
+
+// ------------------------------------------------------------------ NCSN
+int asep_ncsn_create(const asep_ncsn_cfg* cfg, asep_ncsn_t* out) {
+  ASEP_API_BEGIN
+  ASEP_CHECK(cfg != nullptr && out != nullptr, ASEP_ERR_BAD_ARG, "NULL argument");
+  ASEP_CHECK(g_device >= 0, ASEP_ERR_STATE, "asep_init() has not been called");
+  auto h = new asep_ncsn_s();
+  try {
+    h->model.reset(new NcsnModel(*cfg, g_device));
+  } catch (...) {
+    delete h;
+    throw;
+  }
+  *out = h;
+  ASEP_API_END
+}
+
+int asep_ncsn_destroy(asep_ncsn_t h) {
+  ASEP_API_BEGIN
+  if (h) {
+    cudaDeviceSynchronize();
+    delete h;
+  }
+  ASEP_API_END
+}
+
+int asep_ncsn_set_param(asep_ncsn_t h, const char* name, const DLTensor* value) {
+  ASEP_API_BEGIN
+  ASEP_CHECK(h && name, ASEP_ERR_BAD_ARG, "NULL argument");
+  TView v = view_f32(value, name, h->model->device(), /*allow_host=*/true);
+  std::vector<int64_t> shape(v.shape, v.shape + v.ndim);
+  h->model->set_param(name, v.f32, shape, v.on_device);
+  ASEP_API_END
+}
+
+int asep_ncsn_set_sigmas(asep_ncsn_t h, const DLTensor* sigmas) {
+  ASEP_API_BEGIN
+  ASEP_CHECK(h, ASEP_ERR_BAD_ARG, "NULL handle");
+  TView v = view_f32(sigmas, "sigmas", h->model->device(), true);
+  std::vector<float> host((size_t)v.numel);
+  if (v.on_device) CUDA_CHECK(cudaMemcpy(host.data(), v.f32, host.size() * sizeof(float), cudaMemcpyDeviceToHost));
+  else std::memcpy(host.data(), v.f32, host.size() * sizeof(float));
+  h->model->set_sigmas(host.data(), (int)host.size());
+  ASEP_API_END
+}
+
+int asep_ncsn_prepare(asep_ncsn_t h) {
+  ASEP_API_BEGIN
+  ASEP_CHECK(h, ASEP_ERR_BAD_ARG, "NULL handle");
+  h->model->prepare();
+  ASEP_API_END
+}
+
+int asep_ncsn_forward(asep_ncsn_t h, const DLTensor* x, const DLTensor* sigma_idx, DLTensor* score, void* stream) {
+  ASEP_API_BEGIN
+  ASEP_CHECK(h, ASEP_ERR_BAD_ARG, "NULL handle");
+  NcsnModel& m = *h->model;
+  const auto& c = m.cfg();
+  TView xv = view_f32(x, "x", m.device());
+  expect_shape(xv, "x", {-1, c.H, c.W, c.C});
+  const int N = (int)xv.shape[0];
+  TView iv = view_i32(sigma_idx, "sigma_idx", m.device());
+  expect_shape(iv, "sigma_idx", {N});
+  TView sv = view_f32(score, "score", m.device());
+  expect_shape(sv, "score", {N, c.H, c.W, c.C});
+  m.forward(xv.f32, static_cast<const int*>(iv.raw), sv.f32, N, as_stream(stream));
+  ASEP_API_END
+}
+
+int asep_basis_ncsn_inner(asep_ncsn_t m1, asep_ncsn_t m2, const DLTensor* mixed, DLTensor* x1, DLTensor* x2,
+                          int sigma_idx, int T, float eta, float lambda, float noise_scale, const DLTensor* noise1,
+                          const DLTensor* noise2, uint64_t seed, uint64_t step0, uint64_t elem_offset,
+                          DLTensor* per_step, DLTensor* nan_count, void* stream) {
+  ASEP_API_BEGIN
+  ASEP_CHECK(m1 && m2, ASEP_ERR_BAD_ARG, "NULL handle");
+  NcsnModel &g1 = *m1->model, &g2 = *m2->model;
+  const int dev = g1.device();
+  const auto& c = g1.cfg();
+  TView a = view_f32(x1, "x1", dev), b = view_f32(x2, "x2", dev), mx = view_f32(mixed, "mixed", dev);
+  expect_shape(a, "x1", {-1, c.H, c.W, c.C});
+  const int N = (int)a.shape[0];
+  expect_shape(b, "x2", {N, c.H, c.W, c.C});
+  ASEP_CHECK(mx.numel == a.numel, ASEP_ERR_BAD_SHAPE, "x1, x2, mixed must match");
+  ASEP_CHECK(sigma_idx >= 0 && sigma_idx < c.num_classes, ASEP_ERR_BAD_ARG, "sigma_idx %d out of range", sigma_idx);
+  ASEP_CHECK((noise1 == nullptr) == (noise2 == nullptr), ASEP_ERR_BAD_ARG, "inject both noise tensors or neither");
+  const float *nz1 = nullptr, *nz2 = nullptr;
+  if (noise1) {
+    TView na = view_f32(noise1, "noise1", dev), nb = view_f32(noise2, "noise2", dev);
+    ASEP_CHECK(na.numel == (int64_t)T * a.numel && nb.numel == na.numel, ASEP_ERR_BAD_SHAPE, "noise must be [T, ...]");
+    nz1 = na.f32; nz2 = nb.f32;
+  }
+  float* dump = nullptr;
+  if (per_step) {
+    TView d = view_f32(per_step, "per_step", dev);
+    ASEP_CHECK(d.numel == (int64_t)T * 2 * a.numel, ASEP_ERR_BAD_SHAPE, "per_step must be [T, 2, ...]");
+    dump = d.f32;
+  }
+  int* nanp = nullptr;
+  if (nan_count) nanp = static_cast<int*>(view_i32(nan_count, "nan_count", dev).raw);
+  cudaStream_t s = as_stream(stream);
+  float *s1 = nullptr, *s2 = nullptr;
+  int* idx = nullptr;
+  CUDA_CHECK(cudaMalloc(&s1, (size_t)a.numel * sizeof(float)));
+  CUDA_CHECK(cudaMalloc(&s2, (size_t)a.numel * sizeof(float)));
+  CUDA_CHECK(cudaMalloc(&idx, (size_t)std::max(N, 1) * sizeof(int)));
+  try {
+    std::vector<int> hidx((size_t)N, sigma_idx);                  // run_basis_sep.py:167-168
+    CUDA_CHECK(cudaMemcpyAsync(idx, hidx.data(), (size_t)N * sizeof(int), cudaMemcpyHostToDevice, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    for (int t = 0; t < T; ++t) {
+      g1.forward(a.f32, idx, s1, N, s);                           // run_basis_sep.py:169-170
+      g2.forward(b.f32, idx, s2, N, s);
+      launch_langevin(a.f32, b.f32, s1, s2, mx.f32, nz1 ? nz1 + (size_t)t * a.numel : nullptr,
+                      nz2 ? nz2 + (size_t)t * a.numel : nullptr, eta, lambda, noise_scale, seed, step0 + t,
+                      elem_offset, nanp, a.numel, s);
+      if (dump) {
+        CUDA_CHECK(cudaMemcpyAsync(dump + (size_t)(2 * t) * a.numel, a.f32, (size_t)a.numel * sizeof(float),
+                                   cudaMemcpyDeviceToDevice, s));
+        CUDA_CHECK(cudaMemcpyAsync(dump + (size_t)(2 * t + 1) * a.numel, b.f32, (size_t)a.numel * sizeof(float),
+                                   cudaMemcpyDeviceToDevice, s));
+      }
+    }
+    CUDA_CHECK(cudaStreamSynchronize(s));
+  } catch (...) {
+    cudaFree(s1); cudaFree(s2); cudaFree(idx);
+    throw;
+  }
+  cudaFree(s1); cudaFree(s2); cudaFree(idx);
+  ASEP_API_END
+}
+
+int asep_conv_profile(int on) {
+  ASEP_API_BEGIN
+  conv_tc_profile(on);
+  ASEP_API_END
+}
+
+int asep_conv_profile_read(double* total_ms, int64_t* launches, double* flops) {
+  ASEP_API_BEGIN
+  long long n = 0;
+  conv_tc_profile_read(total_ms, &n, flops);
+  if (launches) *launches = (int64_t)n;
   ASEP_API_END
 }
 

@@ -1,0 +1,99 @@
+"""Python handle of one NCSN score network living in libasep.so.
+
+The object behind ``ncsn.utils.get_uncompiled_model[_v2]``: callable like the reference's Keras model,
+``model([perturbed_X, sigma_idx], training=True) -> score`` or with a dict keyed ``'perturbed_X'`` /
+``'sigma_idx'`` (reference: ncsn/utils.py:41-64, train_ncsn.py:43,52, run_basis_sep.py:167-170).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from .. import _lib
+from ..config import NCSNConfig
+from ..weights import ncsn_param_shapes
+
+
+class ScoreModel:
+    def __init__(self, cfg: NCSNConfig, params: Dict[str, np.ndarray], sigmas=None, device: Optional[int] = None,
+                 name: str = "ScoreNetwork"):
+        self.cfg = cfg
+        self.name = name
+        self.device_index = _lib.init(device)
+        self.device = torch.device("cuda", self.device_index)
+        self._lib = _lib.load()
+        self._h = ctypes.c_void_p()
+        version = 1 if cfg.version == "v1" else 2
+        c = _lib.NcsnCfg(version, cfg.H, cfg.W, cfg.C, cfg.ngf, cfg.num_classes)
+        _lib.check(self._lib.asep_ncsn_create(ctypes.byref(c), ctypes.byref(self._h)))
+        self._shapes = ncsn_param_shapes(cfg)
+        self._params = {}
+        if sigmas is not None:
+            self.set_sigmas(sigmas)
+        self.set_params(params)
+        self.prepare()
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            try:
+                self._lib.asep_ncsn_destroy(h)
+            except Exception:
+                pass
+            self._h = ctypes.c_void_p()
+
+    def set_sigmas(self, sigmas) -> None:
+        t = torch.as_tensor(np.asarray(sigmas, dtype=np.float32)).contiguous()
+        d = _lib.dl(t)
+        _lib.check(self._lib.asep_ncsn_set_sigmas(self._h, d.ptr))
+
+    def set_params(self, params: Dict[str, np.ndarray]) -> None:
+        missing = [n for n in self._shapes if n not in params]
+        if missing:
+            raise ValueError(f"score network parameters missing: {missing[:5]} ... ({len(missing)} in total)")
+        for name, shape in self._shapes.items():
+            a = np.ascontiguousarray(params[name], dtype=np.float32)
+            if tuple(a.shape) != tuple(shape):
+                raise ValueError(f"{name}: shape {a.shape}, expected {shape}")
+            t = torch.as_tensor(a)
+            d = _lib.dl(t)
+            _lib.check(self._lib.asep_ncsn_set_param(self._h, name.encode(), d.ptr))
+            self._params[name] = a
+
+    def prepare(self) -> None:
+        _lib.check(self._lib.asep_ncsn_prepare(self._h))
+
+    @property
+    def variables(self) -> Dict[str, np.ndarray]:
+        return dict(self._params)
+
+    trainable_variables = variables
+
+    def count_params(self) -> int:
+        return int(sum(v.size for v in self._params.values()))
+
+    def score(self, x: torch.Tensor, sigma_idx) -> torch.Tensor:
+        x = torch.as_tensor(x)
+        if x.dtype != torch.float32:
+            x = x.float()
+        x = x.to(self.device).contiguous()
+        idx = torch.as_tensor(sigma_idx)
+        if idx.ndim == 0:
+            idx = idx.repeat(x.shape[0])
+        idx = idx.to(device=self.device, dtype=torch.int32).contiguous()
+        out = torch.empty_like(x)
+        dx, di, do = _lib.dl(x), _lib.dl(idx), _lib.dl(out)
+        _lib.check(self._lib.asep_ncsn_forward(self._h, dx.ptr, di.ptr, do.ptr, _lib.stream_ptr()))
+        return out
+
+    def __call__(self, inputs, training: bool = True) -> torch.Tensor:
+        if isinstance(inputs, dict):
+            return self.score(inputs["perturbed_X"], inputs["sigma_idx"])
+        return self.score(inputs[0], inputs[1])
+
+    @property
+    def handle(self) -> ctypes.c_void_p:
+        return self._h

@@ -24,3 +24,34 @@ def langevin_step_constants(sigmas, sigma_idx, delta=2e-5):
     lam = np.float32(1.0 / np.float64(np.float32(sigma * sigma)))
     noise_scale = np.float32(np.sqrt(np.float32(np.float32(2.0) * eta)))
     return eta, lam, noise_scale
+
+
+def _ncsn_cfg(args, version):
+    from ..config import NCSNConfig
+    H, W, C = (args.data_shape if getattr(args, "data_shape", None) else [args.height, args.width, 1])
+    return NCSNConfig(version=version, H=int(H), W=int(W), C=int(C), ngf=int(args.n_filters),
+                      num_classes=int(args.num_classes), sigma1=float(args.sigma1), sigmaL=float(args.sigmaL),
+                      progression=getattr(args, "progression", "logarithmic"))
+
+
+def get_uncompiled_model(args, name="ScoreNetwork", params=None, seed=None):
+    """NCSN v1 ``CondRefineNetDilated`` behind the Keras-model call contract (reference: ncsn/utils.py:41-51).
+    ``params`` (name -> array) loads weights; otherwise the seeded random init is used."""
+    from ..weights import init_ncsn_params
+    from .score_model import ScoreModel
+    if getattr(args, "use_logit", False):
+        raise NotImplementedError("logit_transform=True is not used by configs/melspec_ncsnv1.yml")
+    cfg = _ncsn_cfg(args, "v1")
+    if params is None:
+        params = init_ncsn_params(cfg, seed=0 if seed is None else seed, mode="perturbed" if seed is not None else "faithful")
+    return ScoreModel(cfg, params, name=name)
+
+
+def get_uncompiled_model_v2(args, sigmas, name="ScoreNetworkv2", params=None, seed=None):
+    """NCSN v2 ``RefineNetDilated`` (reference: ncsn/utils.py:54-64); the output is divided by sigmas[idx]."""
+    from ..weights import init_ncsn_params
+    from .score_model import ScoreModel
+    cfg = _ncsn_cfg(args, "v2")
+    if params is None:
+        params = init_ncsn_params(cfg, seed=0 if seed is None else seed, mode="perturbed" if seed is not None else "faithful")
+    return ScoreModel(cfg, params, sigmas=np.asarray(sigmas, dtype=np.float32), name=name)

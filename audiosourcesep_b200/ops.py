@@ -109,5 +109,20 @@ def basis_glow_inner(m1, m2, mixed, x1, x2, T: int, eta: float, lam: float, nois
                                                  _lib.stream_ptr()))
 
 
+def basis_ncsn_inner(m1, m2, mixed, x1, x2, sigma_idx: int, T: int, eta: float, lam: float, noise_scale: float,
+                     noise1=None, noise2=None, seed: int = 0, step0: int = 0, elem_offset: int = 0,
+                     per_step: Optional[torch.Tensor] = None, nan_count: Optional[torch.Tensor] = None) -> None:
+    """T Langevin steps at noise level ``sigma_idx`` with two NCSN score networks, inside the library."""
+    mixed = _prep(mixed)
+    noise1 = None if noise1 is None else _prep(noise1)
+    noise2 = None if noise2 is None else _prep(noise2)
+    t = [_lib.dl(v) for v in (mixed, x1, x2)]
+    dn1, dn2, dps, dnan = _lib.dl(noise1), _lib.dl(noise2), _lib.dl(per_step), _lib.dl(nan_count)
+    _lib.check(_lib.load().asep_basis_ncsn_inner(m1.handle, m2.handle, t[0].ptr, t[1].ptr, t[2].ptr, int(sigma_idx),
+                                                 int(T), float(eta), float(lam), float(noise_scale), dn1.ptr, dn2.ptr,
+                                                 int(seed), int(step0), int(elem_offset), dps.ptr, dnan.ptr,
+                                                 _lib.stream_ptr()))
+
+
 def set_tc_cluster(cluster_size: int) -> None:
     _lib.check(_lib.load().asep_tc_set_cluster(int(cluster_size)))

@@ -119,7 +119,11 @@ def basis_inner_loop(mixed, x1, x2, model1, model2, sigma_idx, sigmas, g=None, g
         ops.basis_glow_inner(model1, model2, mixed, x1, x2, int(T), float(eta), float(lam), float(ns), noise1=noise1,
                              noise2=noise2, seed=seed, step0=step0, elem_offset=elem_offset, per_step=per_step,
                              nan_count=nan)
-    else:
+    elif hasattr(model1, "handle") and hasattr(model2, "handle"):
+        ops.basis_ncsn_inner(model1, model2, mixed, x1, x2, int(sigma_idx), int(T), float(eta), float(lam), float(ns),
+                             noise1=noise1, noise2=noise2, seed=seed, step0=step0, elem_offset=elem_offset,
+                             per_step=per_step, nan_count=nan)
+    else:                                                              # any callable score model (plug-in seam)
         n = x1.shape[0]
         idx = torch.full((n,), int(sigma_idx), dtype=torch.int32, device=x1.device)
         for t in range(int(T)):

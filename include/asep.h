@@ -134,6 +134,40 @@ int asep_basis_glow_inner(asep_glow_t m1, asep_glow_t m2, const DLTensor* mixed,
                           const DLTensor* noise2, uint64_t seed, uint64_t step0, uint64_t elem_offset,
                           DLTensor* per_step, DLTensor* nan_count, void* stream);
 
+/* ------------------------------------------------------------------ NCSN score networks
+ * Replaces ncsn/utils.py:41-64 (get_uncompiled_model / get_uncompiled_model_v2) and the Keras call
+ * `model([perturbed_X, sigma_idx], training=True)` on CondRefineNetDilated (ncsn/score_network.py:224-296,
+ * version 1) / RefineNetDilated (ncsn/score_network_v2.py:202-278, version 2). */
+typedef struct {
+  int32_t version;      /* 1 = CondRefineNetDilated, 2 = RefineNetDilated                          */
+  int32_t H, W, C;      /* data_shape (configs/melspec_ncsnv*.yml: 96, 64, 1)                       */
+  int32_t ngf;          /* n_filters (192 for v1, 128 for v2)                                       */
+  int32_t num_classes;  /* noise levels (rows of the v1 conditional-norm Embedding; length of sigmas) */
+} asep_ncsn_cfg;
+
+typedef struct asep_ncsn_s* asep_ncsn_t;
+
+int asep_ncsn_create(const asep_ncsn_cfg* cfg, asep_ncsn_t* out);
+int asep_ncsn_destroy(asep_ncsn_t h);
+/* Parameter names: audiosourcesep_b200/weights.py:ncsn_param_shapes ("Res1_1/conv1/kernel", ...). */
+int asep_ncsn_set_param(asep_ncsn_t h, const char* name, const DLTensor* value);
+/* Noise levels sigma_1..sigma_L (host or device float32 [L]); v2 divides its output by sigma[idx]
+ * (score_network_v2.py:275-276). */
+int asep_ncsn_set_sigmas(asep_ncsn_t h, const DLTensor* sigmas);
+/* Builds the bf16 tcgen05 weight tile images; call after parameters change. */
+int asep_ncsn_prepare(asep_ncsn_t h);
+/* score = model([x, sigma_idx], training=True): x [N,H,W,1] float32, sigma_idx [N] int32 -> score [N,H,W,1]. */
+int asep_ncsn_forward(asep_ncsn_t h, const DLTensor* x, const DLTensor* sigma_idx, DLTensor* score, void* stream);
+/* T inner Langevin steps at noise level sigma_idx with two score networks (run_basis_sep.py:152-181, model_type
+ * 'ncsn'); arguments as asep_basis_glow_inner. */
+int asep_basis_ncsn_inner(asep_ncsn_t m1, asep_ncsn_t m2, const DLTensor* mixed, DLTensor* x1, DLTensor* x2,
+                          int sigma_idx, int T, float eta, float lambda, float noise_scale, const DLTensor* noise1,
+                          const DLTensor* noise2, uint64_t seed, uint64_t step0, uint64_t elem_offset,
+                          DLTensor* per_step, DLTensor* nan_count, void* stream);
+/* Event timing of the tcgen05 convolution launches of the score networks (same contract as asep_tc_profile). */
+int asep_conv_profile(int on);
+int asep_conv_profile_read(double* total_ms, int64_t* launches, double* flops);
+
 /* Number of CTAs (1, 2 or 4) of a thread-block cluster that share each weight tile of the tcgen05 coupling
  * kernel through TMA multicast.  Tuning knob; results are identical for every value. */
 int asep_tc_set_cluster(int cluster_size);

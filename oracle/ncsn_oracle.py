@@ -58,16 +58,26 @@ def resize_bilinear(x, shape):
 
 
 class NCSNOracle:
-    def __init__(self, cfg, params: Dict[str, np.ndarray], sigmas=None, dtype=torch.float64):
+    def __init__(self, cfg, params: Dict[str, np.ndarray], sigmas=None, dtype=torch.float64,
+                 bf16_operands: bool = False):
+        """``bf16_operands=True`` rounds every tensor-core convolution operand (activations and kernels) to
+        bfloat16 before an exact fp32/fp64 accumulation -- the arithmetic contract of the CUDA path
+        (conv_tc.cu); used to separate "the kernel is wrong" from "bf16 operands are less precise"."""
         self.cfg = cfg
         self.dtype = dtype
+        self.bf16_operands = bf16_operands
         self.p = {k: torch.as_tensor(np.asarray(v), dtype=dtype) for k, v in params.items()}
         self.v1 = cfg.version == "v1"
         self.sigmas = None if sigmas is None else torch.as_tensor(np.asarray(sigmas), dtype=dtype)
 
     # ---- layers
     def conv(self, x, name, dilation=1):
-        return conv2d_same(x, self.p[name + "/kernel"], self.p.get(name + "/bias"), dilation)
+        k = self.p[name + "/kernel"]
+        if self.bf16_operands and name != "begin_conv":
+            x = x.to(torch.bfloat16).to(self.dtype)
+            if name != "end_conv":                     # the 1-channel end convolution keeps fp32 weights
+                k = k.to(torch.bfloat16).to(self.dtype)
+        return conv2d_same(x, k, self.p.get(name + "/bias"), dilation)
 
     def norm(self, x, y, name):
         """score_network.py:203-221 / score_network_v2.py:188-199."""
