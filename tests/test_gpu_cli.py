@@ -1,0 +1,81 @@
+"""End-to-end GPU test of the run_basis_sep CLI mirror: outputs contract + final-SDR parity with the oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from audiosourcesep_b200 import GlowConfig, synthetic
+from audiosourcesep_b200.weights import init_glow_params
+from oracle import basis_oracle as bo
+from oracle.glow_oracle import GlowOracle
+
+pytestmark = pytest.mark.gpu
+
+
+def test_run_basis_sep_glow_cli_contract_and_sdr(tmp_path):
+    from audiosourcesep_b200 import ops
+    from audiosourcesep_b200.run_basis_sep import build_parser, main
+    out = tmp_path / "sep"
+    n_mixed, T, L = 2, 3, 3
+    argv = ["unused1", "unused2", "--output", str(out), "--model_type", "glow", "--synthetic", "--random_init", "7",
+            "--n_mixed", str(n_mixed), "--T", str(T), "--K", "2", "--L", "3", "--n_filters", "512", "--learntop",
+            "--sigma1", "0.05", "--sigmaL", "0.01", "--num_classes", str(L), "--progression", "logarithmic", "--seed", "5"]
+    res = main(build_parser().parse_args(argv))
+    # ---- files and keys the reference writes (run_basis_sep.py:310, 425, 435-436)
+    z = np.load(out / "results.npz")
+    assert sorted(z.files) == ["gt1", "gt2", "mixed", "stft_mixture", "x1", "x2"]
+    for k in ("x1", "x2", "gt1", "gt2", "mixed"):
+        assert z[k].shape == (n_mixed, 96, 64) and z[k].dtype == np.float32
+        assert z[k].min() >= -100.0 and z[k].max() <= 20.0
+    zc = np.load(out / "results_convergence.npz")
+    assert zc["x1"].shape == (L + 1, n_mixed, 96, 64, 1) and zc["x2"].shape == (L + 1, n_mixed, 96, 64, 1)
+    log = (out / "out.log").read_text()
+    assert log.count("Sigma = ") == L and "Duration: " in log and "Data Loaded in" in log
+    assert res is not None and np.array_equal(res["x1"], z["x1"])
+    # ---- the same run on the oracle with the SAME Philox draws (keyed by seed / step / stream / element)
+    cfg = GlowConfig(H=96, W=64, C=1, L=3, K=2, n_filters=512, learntop=True, minval=0.0, maxval=1.0)
+    o1 = GlowOracle(cfg, init_glow_params(cfg, seed=7, mode="perturbed"))
+    o2 = GlowOracle(cfg, init_glow_params(cfg, seed=8, mode="perturbed"))
+    sig = bo.get_sigmas(0.05, 0.01, L, "logarithmic")
+    gt1, gt2 = synthetic.mel_patches_db(n_mixed, 0), synthetic.mel_patches_db(n_mixed, 1)
+    mixed = synthetic.normalise(synthetic.mixture_db(gt1, gt2))
+    rng = np.random.Generator(np.random.PCG64(5))
+    x1 = rng.uniform(0.0, 1.0, mixed.shape).astype(np.float32)
+    x2 = rng.uniform(0.0, 1.0, mixed.shape).astype(np.float32)
+
+    def noise(i, t):
+        step = i * T + t
+        return tuple(ops.philox_normal(mixed.shape, seed=5, step=step, stream_id=s).cpu().numpy() for s in (1, 2))
+
+    def score(o):
+        return lambda x, i: o.grad_log_prob(x)[0].numpy().astype(np.float32)
+
+    y1, y2, arr = bo.basis_run(mixed, x1, x2, score(o1), score(o2), sig, T, noise)
+    w1, w2 = bo.post_processing(y1.squeeze(-1)), bo.post_processing(y2.squeeze(-1))
+    for got, want, gt in ((z["x1"], w1, gt1), (z["x2"], w2, gt2)):
+        sdr_cuda = bo.sdr_db(synthetic.normalise(gt.squeeze(-1)), synthetic.normalise(got))
+        sdr_orac = bo.sdr_db(synthetic.normalise(gt.squeeze(-1)), synthetic.normalise(want))
+        print(f"mel-domain SDR: cuda {sdr_cuda:.3f} dB, oracle {sdr_orac:.3f} dB")
+        assert abs(sdr_cuda - sdr_orac) <= 0.1                         # north-star gate: final SDR within 0.1 dB
+        rel = np.linalg.norm(synthetic.normalise(got) - synthetic.normalise(want)) / np.linalg.norm(synthetic.normalise(want))
+        assert rel <= 1e-2, rel
+    np.testing.assert_allclose(zc["x1"][0].squeeze(-1), bo.post_processing(x1.squeeze(-1)), atol=1e-4)
+
+
+def test_run_basis_sep_ncsn_cli_runs(tmp_path):
+    from audiosourcesep_b200.run_basis_sep import build_parser, main
+    out = tmp_path / "sep_ncsn"
+    cfg_path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "configs", "melspec_ncsnv2.yml")
+    argv = ["unused1", "unused2", "--output", str(out), "--model_type", "ncsn", "--synthetic", "--random_init", "3",
+            "--n_mixed", "2", "--config", cfg_path]
+    args = build_parser().parse_args(argv)
+    from audiosourcesep_b200.run_basis_sep import merge_config
+    args = merge_config(args)
+    args.config = None
+    args.T, args.num_classes, args.sigma1 = 1, 3, 0.05     # 3 short noise levels so the test stays small
+    res = main(args)
+    z = np.load(out / "results.npz")
+    assert z["x1"].shape == (2, 96, 64) and np.all(np.isfinite(z["x1"])) and np.all(np.isfinite(z["x2"]))
+    assert np.load(out / "results_convergence.npz")["x1"].shape == (4, 2, 96, 64, 1)
+    assert res["duration_s"] > 0
