@@ -93,6 +93,7 @@ _SIGNATURES = {
     "asep_conv_profile_read": [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64),
                                ctypes.POINTER(ctypes.c_double)],
     "asep_tc_set_cluster": [_I],
+    "asep_tc_set_pair_mode": [_I],
     "asep_tc_profile": [_I],
     "asep_tc_profile_read": [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64),
                              ctypes.POINTER(ctypes.c_double)],

@@ -626,6 +626,12 @@ int asep_tc_set_cluster(int cluster_size) {
   ASEP_API_END
 }
 
+int asep_tc_set_pair_mode(int on) {
+  ASEP_API_BEGIN
+  nn_tc_set_pair_mode(on);
+  ASEP_API_END
+}
+
 int asep_tc_profile(int on) {
   ASEP_API_BEGIN
   nn_tc_profile(on);

@@ -70,6 +70,7 @@ struct TCParams {
   float* out;            // [M, n3p]
   int H, W;
   long long M;
+  long long* dbg_out;        // debug: per-tile phase timestamps of CTA 0 (clock64), 8 per round
   int dbg_flags;             // debug: 1 skip MMA, 2 skip operand build, 4 skip G store, 8 skip epilogue 1/2 bodies
   int dbg_shift;             // debug: load only bytes >> dbg_shift of every weight image (timing experiments)
   int tiles_per_cta_round;   // grid size (all CTAs advance together)
@@ -390,6 +391,356 @@ __global__ void __launch_bounds__(kThreadsTC, 1) k_nn_tc(const TCParams prm) {
   if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
 }
 
+// ===================================================================================================
+// CTA-pair variant (cta_group::2).  Two CTAs of a cluster (the two SMs of a TPC) process 256 consecutive pixels:
+// every tcgen05.mma spans both (M = 256), each CTA supplies its own 128 operand rows and streams only HALF of
+// every weight image (rows [rank*128, +128) of the 256 output channels of the instruction), so the L2 -> SM
+// weight traffic per pixel is halved and the 6-deep ring of 16 KB half images covers the L2 latency.  The leader
+// (rank 0) issues all MMAs; the peer's warp 1 relays "my half of stage s has landed" to the leader; tcgen05.commit
+// multicasts stage releases and accumulator-ready signals to both CTAs.  Eight worker warps per CTA (two per
+// TMEM lane quarter, each owning 256 of the 512 accumulator columns) run the epilogues with the TMEM loads of
+// chunk j+1 in flight while chunk j is converted.
+constexpr int kStages2 = 6;
+constexpr int kHalfStageBytes = kStageBytes / 2;      // 16 KB
+constexpr int kBarBytes2 = 256;
+constexpr int kSmemBytes2 = kARegionBytes + kStages2 * kHalfStageBytes + kBiasBytes + kBarBytes2;   // 231,680 B
+constexpr int kThreadsTC2 = 64 + 256;
+constexpr int kWorkers2 = 256;
+
+// im2col of taps [t_begin, t_end) of one operand row as split-bf16 [hi | lo]
+template <int SC>
+__device__ __forceinline__ void build_a1_taps(uint8_t* sA, int row, const float* __restrict__ src, long long p, bool valid,
+                                              int h, int w, int H, int W, int stride, int off, int sign, int t_begin,
+                                              int t_end) {
+  constexpr int K1h = 9 * SC;
+  constexpr int TG = SC >= 16 ? 3 : 5;
+  for (int t0 = t_begin; t0 < t_end; t0 += TG) {
+    float v[TG][SC];
+#pragma unroll
+    for (int tt = 0; tt < TG; ++tt) {
+      const int tap = t0 + tt;
+      const int dy = (tap / 3 - 1) * sign, dx = (tap % 3 - 1) * sign;
+      const int hh = h + dy, ww = w + dx;
+      const bool ok = valid && tap < t_end && hh >= 0 && hh < H && ww >= 0 && ww < W;
+      const float* s = src + (p + (long long)dy * W + dx) * stride + off;
+      if constexpr (SC % 4 == 0) {
+#pragma unroll
+        for (int q = 0; q < SC / 4; ++q) {
+          float4 t = ok ? __ldg(reinterpret_cast<const float4*>(s) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+          v[tt][4 * q] = t.x; v[tt][4 * q + 1] = t.y; v[tt][4 * q + 2] = t.z; v[tt][4 * q + 3] = t.w;
+        }
+      } else if constexpr (SC == 2) {
+        float2 t = ok ? __ldg(reinterpret_cast<const float2*>(s)) : make_float2(0.f, 0.f);
+        v[tt][0] = t.x; v[tt][1] = t.y;
+      } else {
+#pragma unroll
+        for (int ci = 0; ci < SC; ++ci) v[tt][ci] = ok ? __ldg(s + ci) : 0.f;
+      }
+    }
+#pragma unroll
+    for (int tt = 0; tt < TG; ++tt) {
+      if (t0 + tt >= t_end) break;
+      const int k0 = (t0 + tt) * SC;
+      float lo[SC];
+      uint32_t hp[(SC + 1) / 2], lp[(SC + 1) / 2];
+#pragma unroll
+      for (int ci = 0; ci < SC; ++ci) lo[ci] = v[tt][ci] - __bfloat162float(__float2bfloat16_rn(v[tt][ci]));
+      if constexpr (SC == 1) {
+        *reinterpret_cast<__nv_bfloat16*>(sA + a_offset(row, k0)) = __float2bfloat16_rn(v[tt][0]);
+        *reinterpret_cast<__nv_bfloat16*>(sA + a_offset(row, K1h + k0)) = __float2bfloat16_rn(lo[0]);
+      } else {
+#pragma unroll
+        for (int q = 0; q < SC / 2; ++q) {
+          hp[q] = pack_bf16(v[tt][2 * q], v[tt][2 * q + 1]);
+          lp[q] = pack_bf16(lo[2 * q], lo[2 * q + 1]);
+        }
+        if constexpr (SC == 2) {
+          *reinterpret_cast<uint32_t*>(sA + a_offset(row, k0)) = hp[0];
+          *reinterpret_cast<uint32_t*>(sA + a_offset(row, K1h + k0)) = lp[0];
+        } else if constexpr (SC == 4) {
+          *reinterpret_cast<uint2*>(sA + a_offset(row, k0)) = make_uint2(hp[0], hp[1]);
+          *reinterpret_cast<uint2*>(sA + a_offset(row, K1h + k0)) = make_uint2(lp[0], lp[1]);
+        } else {
+#pragma unroll
+          for (int q = 0; q < SC / 8; ++q) {
+            *reinterpret_cast<uint4*>(sA + a_offset(row, k0 + 8 * q)) =
+                make_uint4(hp[4 * q], hp[4 * q + 1], hp[4 * q + 2], hp[4 * q + 3]);
+            *reinterpret_cast<uint4*>(sA + a_offset(row, K1h + k0 + 8 * q)) =
+                make_uint4(lp[4 * q], lp[4 * q + 1], lp[4 * q + 2], lp[4 * q + 3]);
+          }
+        }
+      }
+    }
+  }
+}
+
+template <bool kBwd, bool kSaveMask, bool kPair>
+__global__ void __launch_bounds__(kThreadsTC2, 1) k_nn_tc2(const TCParams prm) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();
+  constexpr int S = kPair ? kStages2 : kStages;                     // ring depth
+  constexpr int kSlotBytes = kPair ? kHalfStageBytes : kStageBytes;  // 16 KB half images / 32 KB full images
+  constexpr int kRowsPerRound = kPair ? 2 * kTileM : kTileM;
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + kARegionBytes;
+  float* sBias = reinterpret_cast<float*>(smem + kARegionBytes + S * kSlotBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kARegionBytes + S * kSlotBytes + kBiasBytes);
+  // bars: [0,S) full  [S,2S) empty  [2S,3S) peer_full (leader)  [3S] a_ready (leader)  [3S+1] acc_ready  [3S+2] tmem slot
+  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[S]), peer0 = smem_u32(&bars[2 * S]);
+  const uint32_t a_ready = smem_u32(&bars[3 * S]), acc_ready = smem_u32(&bars[3 * S + 1]);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(&bars[3 * S + 2]);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t rank = 0;
+  if constexpr (kPair) rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < S; ++i) {
+      mbar_init(full0 + 8 * i, 1);
+      mbar_init(empty0 + 8 * i, 1);
+      mbar_init(peer0 + 8 * i, 1);
+    }
+    mbar_init(a_ready, kPair ? 16 : 8);   // one arrival per worker warp (of each CTA)
+    mbar_init(acc_ready, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    if constexpr (kPair) tmem_alloc2(smem_u32(tmem_slot), kTmemCols);
+    else tmem_alloc(smem_u32(tmem_slot), kTmemCols);
+  }
+  tc_fence_before();
+  if constexpr (kPair) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int n_img1 = 2 * prm.k1_panels;
+  const int n_img = n_img1 + 2 * kNumPanels + kNumPanels;
+  const uint32_t img3_bytes = (uint32_t)prm.n3p * 128u;
+
+  if (warp == 0) {
+    // ===================== producer: this CTA's half of every weight image =====================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int round = 0; round < prm.num_rounds; ++round) {
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(prm.wimg);
+        for (int i = 0; i < n_img; ++i) {
+          const uint32_t bytes = (i < n_img - kNumPanels) ? (uint32_t)kStageBytes : img3_bytes;
+          const uint32_t half = kPair ? (bytes >> 1) : bytes;
+          mbar_wait(empty0 + 8 * stage, phase ^ 1);
+          mbar_expect_tx(full0 + 8 * stage, half);
+          bulk_g2s(smem_u32(sB + stage * kSlotBytes), src + rank * half, half, full0 + 8 * stage);
+          src += bytes;
+          if (++stage == (uint32_t)S) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      if (!leader) {
+        // ===================== peer relay: tell the leader when my half of a stage has landed =====================
+        uint32_t stage = 0, phase = 0;
+        const uint32_t peer_remote = mapa_u32(peer0, 0);
+        const long long total = (long long)prm.num_rounds * n_img;
+        for (long long i = 0; i < total; ++i) {
+          mbar_wait(full0 + 8 * stage, phase);
+          mbar_arrive_cluster(peer_remote + 8 * stage);
+          if (++stage == (uint32_t)S) { stage = 0; phase ^= 1; }
+        }
+      } else {
+        // ===================== MMA issuer (leader only) =====================
+        uint32_t stage = 0, phase = 0, a_phase = 0;
+        const uint32_t a_base = smem_u32(sA);
+        constexpr uint32_t idesc256 = make_idesc_m(256, kPair ? 256 : 128);
+        const uint32_t idesc3 = make_idesc_m(prm.n3p, kPair ? 256 : 128);
+        for (int round = 0; round < prm.num_rounds; ++round) {
+          for (int gemm = 0; gemm < 3; ++gemm) {
+            if constexpr (kPair) mbar_wait_cluster(a_ready, a_phase); else mbar_wait(a_ready, a_phase);
+            a_phase ^= 1;
+            tc_fence_after();
+            const int halves = gemm < 2 ? 2 : 1;
+            const int panels = gemm == 0 ? prm.k1_panels : kNumPanels;
+            const uint32_t idesc = gemm < 2 ? idesc256 : idesc3;
+            for (int half = 0; half < halves; ++half) {
+              const uint32_t d_tmem = tmem_base + (uint32_t)(half * 256);
+              for (int kp = 0; kp < panels; ++kp) {
+                mbar_wait(full0 + 8 * stage, phase);
+                if constexpr (kPair) mbar_wait_cluster(peer0 + 8 * stage, phase);
+                tc_fence_after();
+                const int steps = gemm == 0 ? min(4, prm.k1_steps - 4 * kp) : 4;
+                const uint64_t da = make_desc(a_base + kp * kPanelBytes);
+                const uint64_t db = make_desc(smem_u32(sB + stage * kSlotBytes));
+                for (int k = 0; k < steps; ++k) {
+                  if constexpr (kPair) umma_bf16_2cta(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kp | k) != 0);
+                  else umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kp | k) != 0);
+                }
+                if constexpr (kPair) umma_commit_2cta(empty0 + 8 * stage, 3); else umma_commit(empty0 + 8 * stage);
+                if (++stage == (uint32_t)S) { stage = 0; phase ^= 1; }
+              }
+            }
+            if constexpr (kPair) umma_commit_2cta(acc_ready, 3); else umma_commit(acc_ready);
+          }
+        }
+      }
+    }
+  } else {
+    // ===================== workers: operand build + epilogues (both CTAs, 8 warps) =====================
+    const int quarter = warp & 3;                       // TMEM lane quarter this warp may access
+    const int colhalf = (warp - 2) >> 2;                // which 256 of the 512 accumulator columns
+    const int row = quarter * 32 + lane;
+    const int wtid = threadIdx.x - 64;                  // 0..255
+    const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    uint32_t a_ready_leader = a_ready;
+    if constexpr (kPair) a_ready_leader = mapa_u32(a_ready, 0);
+    uint32_t acc_phase = 0;
+    const int k1_pad = prm.k1_steps * 16;
+    float4 b1v = make_float4(0.f, 0.f, 0.f, 0.f), b2v = b1v;
+    if constexpr (!kBwd) {
+      if (wtid < kF / 4) {
+        b1v = __ldg(reinterpret_cast<const float4*>(prm.bias1) + wtid);
+        b2v = __ldg(reinterpret_cast<const float4*>(prm.bias2) + wtid);
+      }
+    }
+    auto signal_a_ready = [&]() {
+      if constexpr (kPair) fence_proxy_async_all(); else fence_proxy_async();   // my smem writes -> visible to the tensor core
+      __syncwarp();
+      if (lane == 0) {
+        if constexpr (kPair) mbar_arrive_cluster(a_ready_leader); else mbar_arrive(a_ready);
+      }
+    };
+    for (int round = 0; round < prm.num_rounds; ++round) {
+      const long long tile = (long long)round * prm.tiles_per_cta_round + (kPair ? (blockIdx.x >> 1) : blockIdx.x);
+      const long long p = tile * kRowsPerRound + (long long)rank * kTileM + row;
+      const bool valid = p < prm.M;
+      const bool stamp = prm.dbg_out != nullptr && blockIdx.x == 0 && wtid == 0;
+      long long* ts = prm.dbg_out + (long long)round * 8;
+      if (stamp) ts[0] = clock64();
+      if (colhalf == 0) {
+        const long long pn = p + (long long)prm.tiles_per_cta_round * kRowsPerRound;
+        if (pn < prm.M) asm volatile("prefetch.global.L2 [%0];" ::"l"(prm.src + pn * prm.src_stride));
+      }
+      // ---- stage-1 operand: two threads per row, taps 0-4 and 5-8 (+ zero padding of the K tail)
+      {
+        int w = 0, h = 0;
+        if (valid) { w = (int)(p % prm.W); h = (int)((p / prm.W) % prm.H); }
+        const int tb = colhalf == 0 ? 0 : 5, te = colhalf == 0 ? 5 : 9;
+        switch (prm.src_ch) {
+          case 1: build_a1_taps<1>(sA, row, prm.src, p, valid, h, w, prm.H, prm.W, prm.src_stride, prm.src_off, prm.tap_sign, tb, te); break;
+          case 2: build_a1_taps<2>(sA, row, prm.src, p, valid, h, w, prm.H, prm.W, prm.src_stride, prm.src_off, prm.tap_sign, tb, te); break;
+          case 4: build_a1_taps<4>(sA, row, prm.src, p, valid, h, w, prm.H, prm.W, prm.src_stride, prm.src_off, prm.tap_sign, tb, te); break;
+          case 8: build_a1_taps<8>(sA, row, prm.src, p, valid, h, w, prm.H, prm.W, prm.src_stride, prm.src_off, prm.tap_sign, tb, te); break;
+          default: build_a1_taps<16>(sA, row, prm.src, p, valid, h, w, prm.H, prm.W, prm.src_stride, prm.src_off, prm.tap_sign, tb, te); break;
+        }
+        if (colhalf == 1)
+          for (int k = 2 * 9 * prm.src_ch; k < k1_pad; ++k)
+            *reinterpret_cast<__nv_bfloat16*>(sA + a_offset(row, k)) = __float2bfloat16_rn(0.f);
+      }
+      if constexpr (!kBwd) {
+        if (wtid < kF / 4) reinterpret_cast<float4*>(sBias)[wtid] = b1v;
+      }
+      signal_a_ready();
+      if (stamp) ts[1] = clock64();
+
+      // ---- epilogues of stage 1 and stage 2: TMEM -> (bias, relu | mask) -> bf16 -> swizzled smem
+      for (int gemm = 0; gemm < 2; ++gemm) {
+        uint32_t* mask = kBwd ? (gemm == 0 ? prm.mask2 : prm.mask1) : (gemm == 0 ? prm.mask1 : prm.mask2);
+        uint32_t mk[8];
+        if constexpr (kBwd) {
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            uint4 t = valid ? __ldg(reinterpret_cast<const uint4*>(mask + p * (kF / 32) + colhalf * 8) + q) : make_uint4(0, 0, 0, 0);
+            mk[4 * q] = t.x; mk[4 * q + 1] = t.y; mk[4 * q + 2] = t.z; mk[4 * q + 3] = t.w;
+          }
+        }
+        if constexpr (!kBwd) named_bar_sync(1, kWorkers2);      // bias vector of this stage is in sBias
+        mbar_wait(acc_ready, acc_phase);
+        acc_phase ^= 1;
+        tc_fence_after();
+        if (stamp) ts[2 + 2 * gemm] = clock64();
+        uint32_t v[2][32];
+        const uint32_t t_col = t_lane + (uint32_t)(colhalf * 256);
+        tmem_ld32(t_col, v[0]);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {                            // 8 chunks of 32 accumulator columns
+          tmem_ld_wait();
+          if (c + 1 < 8) tmem_ld32(t_col + (uint32_t)((c + 1) * 32), v[(c + 1) & 1]);
+          const int j = colhalf * 8 + c;                         // global 32-column chunk index
+          float f[32];
+          if constexpr (!kBwd) {
+            uint32_t bits = 0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 b4 = reinterpret_cast<const float4*>(sBias + j * 32)[q];
+              f[4 * q + 0] = __uint_as_float(v[c & 1][4 * q + 0]) + b4.x;
+              f[4 * q + 1] = __uint_as_float(v[c & 1][4 * q + 1]) + b4.y;
+              f[4 * q + 2] = __uint_as_float(v[c & 1][4 * q + 2]) + b4.z;
+              f[4 * q + 3] = __uint_as_float(v[c & 1][4 * q + 3]) + b4.w;
+            }
+            if constexpr (kSaveMask) {
+#pragma unroll
+              for (int cidx = 0; cidx < 32; ++cidx) bits |= (f[cidx] > 0.f ? 1u : 0u) << cidx;
+              if (valid) mask[p * (kF / 32) + j] = bits;
+            }
+#pragma unroll
+            for (int cidx = 0; cidx < 32; ++cidx) f[cidx] = fmaxf(f[cidx], 0.f);
+          } else {
+            const uint32_t bits = mk[c];
+#pragma unroll
+            for (int cidx = 0; cidx < 32; ++cidx) f[cidx] = ((bits >> cidx) & 1u) ? __uint_as_float(v[c & 1][cidx]) : 0.f;
+          }
+          uint8_t* base = sA + (j >> 1) * kPanelBytes + row * 128;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int chunk = (j & 1) * 4 + q;
+            uint4 pk;
+            pk.x = pack_bf16(f[8 * q + 0], f[8 * q + 1]);
+            pk.y = pack_bf16(f[8 * q + 2], f[8 * q + 3]);
+            pk.z = pack_bf16(f[8 * q + 4], f[8 * q + 5]);
+            pk.w = pack_bf16(f[8 * q + 6], f[8 * q + 7]);
+            *reinterpret_cast<uint4*>(base + ((chunk ^ (row & 7)) << 4)) = pk;
+          }
+        }
+        if constexpr (!kBwd) {
+          if (gemm == 0) {                                       // swap in the stage-2 bias once everyone is done
+            named_bar_sync(1, kWorkers2);
+            if (wtid < kF / 4) reinterpret_cast<float4*>(sBias)[wtid] = b2v;
+          }
+        }
+        tc_fence_before();
+        signal_a_ready();
+        if (stamp) ts[3 + 2 * gemm] = clock64();
+      }
+
+      // ---- epilogue of stage 3: TMEM -> global fp32 G[p][0..n3p), 16-column chunks alternate between the two warps of a row
+      mbar_wait(acc_ready, acc_phase);
+      acc_phase ^= 1;
+      tc_fence_after();
+      if (stamp) ts[6] = clock64();
+      for (int j = colhalf; j < prm.n3p / 16; j += 2) {
+        uint32_t v[16];
+        tmem_ld16(t_lane + (uint32_t)(j * 16), v);
+        tmem_ld_wait();
+        if (valid) {
+          float4* o = reinterpret_cast<float4*>(prm.out + p * prm.n3p + j * 16);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            o[q] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
+                               __uint_as_float(v[4 * q + 3]));
+        }
+      }
+      tc_fence_before();
+      if (stamp) ts[7] = clock64();
+    }
+  }
+
+  tc_fence_before();
+  if constexpr (kPair) cluster_sync_all(); else __syncthreads();
+  if (warp == 2) {
+    if constexpr (kPair) tmem_dealloc2(tmem_base, kTmemCols);
+    else tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
 // r[p][c] = c3[c] + sum_{tap in bounds} (G[p+off(tap)][tap*C+c] + const3[tap][c])
 __global__ void __launch_bounds__(256) k_gather_fwd(const float* __restrict__ G, const float* __restrict__ const3,
                                                     const float* __restrict__ c3, float* __restrict__ r, int H, int W,
@@ -431,6 +782,7 @@ __global__ void __launch_bounds__(256) k_gather_bwd(const float* __restrict__ G,
 
 int g_cluster = 1;
 int g_num_sms = 0;
+int g_pair_mode = 0;    // 0: 8-worker-warp single-CTA kernel, 1: CTA-pair kernel (cta_group::2), 2: legacy 4-worker-warp kernel
 
 // ---- optional per-launch timing of the tensor-core kernel (bench.py's roofline leg): a CUDA event pair
 // on the launching stream around every k_nn_tc launch while profiling is on.
@@ -519,12 +871,81 @@ void launch_tc(const TCParams& prm, int grid, cudaStream_t s) {
   }
 }
 
+template <bool kBwd, bool kSaveMask, bool kPair>
+void launch_tc2(const TCParams& prm, int grid, cudaStream_t s) {
+  auto kern = k_nn_tc2<kBwd, kSaveMask, kPair>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes2));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreadsTC2);
+  cfg.dynamicSmemBytes = kSmemBytes2;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kPair ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  ProfRec rec{};
+  if (g_prof_on) {
+    if (!g_prof_pool.empty()) { rec = g_prof_pool.back(); g_prof_pool.pop_back(); }
+    else { CUDA_CHECK(cudaEventCreate(&rec.a)); CUDA_CHECK(cudaEventCreate(&rec.b)); }
+    CUDA_CHECK(cudaEventRecord(rec.a, s));
+  }
+  CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, prm));
+  ASEP_LAUNCH_CHECK();
+  if (g_prof_on) {
+    CUDA_CHECK(cudaEventRecord(rec.b, s));
+    g_prof_recs.push_back(rec);
+    g_prof_flops += g_next_flops;
+  }
+}
+
 template <bool kBwd>
 void run_tc(TCParams prm, cudaStream_t s) {
   if (g_num_sms == 0) {
     int dev = 0;
     CUDA_CHECK(cudaGetDevice(&dev));
     CUDA_CHECK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  if (g_pair_mode != 2) {
+    const bool pair = g_pair_mode == 1;
+    const int rows = pair ? 2 * kTileM : kTileM;
+    const long long ptiles = (prm.M + rows - 1) / rows;
+    const int pairs = (int)std::min<long long>(ptiles, pair ? g_num_sms / 2 : g_num_sms);
+    prm.tiles_per_cta_round = pairs;
+    prm.num_rounds = (int)((ptiles + pairs - 1) / pairs);
+    static long long* dbg = nullptr;
+    const bool timing = getenv("ASEP_TC_DBG_TIMING") != nullptr;
+    if (timing) {
+      if (!dbg) CUDA_CHECK(cudaMalloc(&dbg, 8 * 4096 * sizeof(long long)));
+      ASEP_CHECK(prm.num_rounds <= 4096, ASEP_ERR_BAD_ARG, "too many rounds for the timing buffer");
+      prm.dbg_out = dbg;
+    }
+    const bool save = !kBwd && prm.mask1 != nullptr;
+    if (pair) { if (save) launch_tc2<kBwd, true, true>(prm, 2 * pairs, s); else launch_tc2<kBwd, false, true>(prm, 2 * pairs, s); }
+    else { if (save) launch_tc2<kBwd, true, false>(prm, pairs, s); else launch_tc2<kBwd, false, false>(prm, pairs, s); }
+    if (timing) {
+      CUDA_CHECK(cudaStreamSynchronize(s));
+      std::vector<long long> h((size_t)8 * prm.num_rounds);
+      CUDA_CHECK(cudaMemcpy(h.data(), dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+      double d[8] = {0};
+      const int r0 = prm.num_rounds > 2 ? 1 : 0, r1 = prm.num_rounds;
+      for (int r = r0; r < r1; ++r) {
+        for (int i = 0; i < 7; ++i) d[i] += (double)(h[r * 8 + i + 1] - h[r * 8 + i]);
+        if (r + 1 < r1) d[7] += (double)(h[(r + 1) * 8] - h[r * 8 + 7]);
+      }
+      const double n = r1 - r0;
+      fprintf(stderr, "[tc2 %s M=%lld rounds=%d] cycles/tile: build %.0f | wait1 %.0f epi1 %.0f | wait2 %.0f epi2 %.0f | wait3 %.0f epi3 %.0f | gap %.0f | total %.0f\n",
+              kBwd ? "bwd" : "fwd", prm.M, prm.num_rounds, d[0] / n, d[1] / n, d[2] / n, d[3] / n, d[4] / n, d[5] / n, d[6] / n,
+              d[7] / std::max(1.0, n - 1), (double)(h[(r1 - 1) * 8 + 7] - h[r0 * 8]) / n);
+    }
+    return;
   }
   const int cs = g_cluster;
   const long long tiles = (prm.M + kTileM - 1) / kTileM;
@@ -551,6 +972,8 @@ void nn_tc_set_cluster(int cluster_size) {
   g_cluster = cluster_size;
 }
 int nn_tc_get_cluster() { return g_cluster; }
+void nn_tc_set_pair_mode(int on) { g_pair_mode = on; }
+int nn_tc_get_pair_mode() { return g_pair_mode; }
 
 void nn_tc_profile(int on) {
   g_prof_on = on != 0;

@@ -48,6 +48,9 @@ void nn_tc_backward(const NNWeightsTC& w, const NNScratchTC& sc, const float* gr
 size_t nn_tc_g_floats(long long M, int C);   // capacity needed for NNScratchTC::G
 void nn_tc_set_cluster(int cluster_size);    // 1, 2 or 4 CTAs sharing each weight tile by TMA multicast
 int nn_tc_get_cluster();
+// 1 selects the CTA-pair kernel (tcgen05 cta_group::2: two SMs share every weight image); results are identical.
+void nn_tc_set_pair_mode(int on);
+int nn_tc_get_pair_mode();
 // CUDA-event timing of every tensor-core kernel launch (on its own stream) while switched on.
 void nn_tc_profile(int on);
 void nn_tc_profile_read(double* total_ms, long long* launches, double* flops);

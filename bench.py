@@ -328,7 +328,12 @@ def run_ours(args):
     if os.path.exists(prof_path):
         try:
             with open(prof_path) as f:
-                roofline["traffic"] = json.load(f).get("k_nn_tc_dram_bytes_per_launch")
+                prof_js = json.load(f)
+            # ncu dram bytes per pixel row of the captured block-1 launch x the average rows per launch of this run
+            per_row = prof_js.get("dram_bytes_per_pixel_row")
+            rows_per_launch = B * (48 * 32 + 24 * 16 + 12 * 8) / 3.0
+            roofline["traffic"] = None if per_row is None else per_row * rows_per_launch
+            roofline["traffic_note"] = "ncu dram__bytes_read+write per pixel row of a captured block-1 launch (profiles/ncu_summary.json) x mean rows per launch"
         except Exception:
             pass
 

@@ -35,6 +35,7 @@ def main():
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--grad", action="store_true")
     ap.add_argument("--fp32", action="store_true")
+    ap.add_argument("--pair", type=int, nargs="+", default=[0])
     a = ap.parse_args()
     cfg = GlowConfig(K=a.K)
     t0 = time.time()
@@ -45,15 +46,16 @@ def main():
     for N in a.batches:
         x = torch.as_tensor(synthetic.mel_patches_db(min(N, 64), seed=0)).cuda()
         x = x.repeat((N + x.shape[0] - 1) // x.shape[0], 1, 1, 1)[:N].contiguous()
-        for cs in a.clusters:
+        for cs, pair in [(c, q) for q in a.pair for c in (a.clusters if q == 0 else [1])]:
             ops.set_tc_cluster(cs)
+            ops.set_tc_pair_mode(int(pair))
             ms = timeit(lambda: m.log_prob(x), a.iters)
             tf = N * F_GLOW * scale / (ms * 1e-3) / 1e12
-            print(f"log_prob  N={N:5d} cluster={cs}: {ms:9.3f} ms  {N / ms * 1e3:10.1f} samples/s  {tf:8.1f} TFLOP/s", flush=True)
+            print(f"log_prob  N={N:5d} cluster={cs} pair={pair}: {ms:9.3f} ms  {N / ms * 1e3:10.1f} samples/s  {tf:8.1f} TFLOP/s", flush=True)
             if a.grad:
                 ms = timeit(lambda: m.grad_log_prob(x), a.iters)
                 tf = N * 2 * F_GLOW * scale / (ms * 1e-3) / 1e12
-                print(f"grad_logp N={N:5d} cluster={cs}: {ms:9.3f} ms  {N / ms * 1e3:10.1f} samples/s  {tf:8.1f} TFLOP/s (2F alg.)", flush=True)
+                print(f"grad_logp N={N:5d} cluster={cs} pair={pair}: {ms:9.3f} ms  {N / ms * 1e3:10.1f} samples/s  {tf:8.1f} TFLOP/s (2F alg.)", flush=True)
         ops.set_tc_cluster(1)
     if a.fp32:
         m.prepare(_lib.PREC_FP32)
