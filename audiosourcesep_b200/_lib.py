@@ -72,6 +72,13 @@ _SIGNATURES = {
     "asep_glow_log_prob": [_V, _P, _P, _V],
     "asep_glow_grad_log_prob": [_V, _P, _P, _P, _V],
     "asep_glow_sample": [_V, _P, _P, _V],
+    "asep_glow_enable_training": [_V],
+    "asep_glow_num_trainable": [_V, ctypes.POINTER(ctypes.c_int64)],
+    "asep_glow_train_grads": [_V, _P, _P, _F, _I, _P, _P, _V],
+    "asep_glow_adamax_step": [_V, _P, _F, _F, _F, _F, _V],
+    "asep_glow_get_flat": [_V, _P, _V],
+    "asep_glow_set_flat": [_V, _P, _V],
+    "asep_glow_sync_host": [_V],
     "asep_actnorm": [_P, _P, _P, _P, _I, _V],
     "asep_inv1x1": [_P, _P, _P, _V],
     "asep_coupling": [_P, _P, _P, _P, _I, _V],

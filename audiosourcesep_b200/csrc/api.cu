@@ -301,6 +301,80 @@ int asep_glow_coupling_nn_backward(asep_glow_t h, int block, int step, const DLT
   ASEP_API_END
 }
 
+// ------------------------------------------------------------------ Glow training
+int asep_glow_enable_training(asep_glow_t h) {
+  ASEP_API_BEGIN
+  ASEP_CHECK(h, ASEP_ERR_BAD_ARG, "NULL handle");
+  h->model->enable_training();
+  ASEP_API_END
+}
+
+int asep_glow_num_trainable(asep_glow_t h, int64_t* out) {
+  ASEP_API_BEGIN
+  ASEP_CHECK(h && out, ASEP_ERR_BAD_ARG, "NULL argument");
+  *out = (int64_t)h->model->num_trainable();
+  ASEP_API_END
+}
+
+int asep_glow_train_grads(asep_glow_t h, const DLTensor* x, const DLTensor* noise, float sigma, int global_batch,
+                          DLTensor* grads, DLTensor* loss, void* stream) {
+  ASEP_API_BEGIN
+  ASEP_CHECK(h, ASEP_ERR_BAD_ARG, "NULL handle");
+  GlowModel& m = *h->model;
+  TView xv = view_f32(x, "x", m.device());
+  const int N = batch_of(xv, m, "x");
+  const float* nz = nullptr;
+  if (noise) {
+    TView nv = view_f32(noise, "noise", m.device());
+    ASEP_CHECK(nv.numel == xv.numel, ASEP_ERR_BAD_SHAPE, "noise must have the shape of x");
+    nz = nv.f32;
+  }
+  TView gv = view_f32(grads, "grads", m.device());
+  ASEP_CHECK(gv.numel == m.num_trainable(), ASEP_ERR_BAD_SHAPE, "grads must hold %lld elements", m.num_trainable());
+  TView lv = view_f32(loss, "loss", m.device());
+  ASEP_CHECK(lv.numel == 1, ASEP_ERR_BAD_SHAPE, "loss must hold one element");
+  m.train_grads(xv.f32, nz, sigma, N, global_batch, gv.f32, lv.f32, as_stream(stream));
+  ASEP_API_END
+}
+
+int asep_glow_adamax_step(asep_glow_t h, const DLTensor* grads, float lr, float beta1, float beta2, float eps,
+                          void* stream) {
+  ASEP_API_BEGIN
+  ASEP_CHECK(h, ASEP_ERR_BAD_ARG, "NULL handle");
+  GlowModel& m = *h->model;
+  TView gv = view_f32(grads, "grads", m.device());
+  ASEP_CHECK(gv.numel == m.num_trainable(), ASEP_ERR_BAD_SHAPE, "grads must hold %lld elements", m.num_trainable());
+  m.adamax_step(gv.f32, lr, beta1, beta2, eps, as_stream(stream));
+  ASEP_API_END
+}
+
+int asep_glow_get_flat(asep_glow_t h, DLTensor* theta, void* stream) {
+  ASEP_API_BEGIN
+  ASEP_CHECK(h, ASEP_ERR_BAD_ARG, "NULL handle");
+  GlowModel& m = *h->model;
+  TView tv = view_f32(theta, "theta", m.device());
+  ASEP_CHECK(tv.numel == m.num_trainable(), ASEP_ERR_BAD_SHAPE, "theta must hold %lld elements", m.num_trainable());
+  m.copy_flat(tv.f32, as_stream(stream));
+  ASEP_API_END
+}
+
+int asep_glow_set_flat(asep_glow_t h, const DLTensor* theta, void* stream) {
+  ASEP_API_BEGIN
+  ASEP_CHECK(h, ASEP_ERR_BAD_ARG, "NULL handle");
+  GlowModel& m = *h->model;
+  TView tv = view_f32(theta, "theta", m.device());
+  ASEP_CHECK(tv.numel == m.num_trainable(), ASEP_ERR_BAD_SHAPE, "theta must hold %lld elements", m.num_trainable());
+  m.set_flat(tv.f32, as_stream(stream));
+  ASEP_API_END
+}
+
+int asep_glow_sync_host(asep_glow_t h) {
+  ASEP_API_BEGIN
+  ASEP_CHECK(h, ASEP_ERR_BAD_ARG, "NULL handle");
+  h->model->sync_host();
+  ASEP_API_END
+}
+
 // ------------------------------------------------------------------ single bijectors
 static void nhwc(const TView& v, const char* what, int& N, int& H, int& W, int& C) {
   ASEP_CHECK(v.ndim == 4, ASEP_ERR_BAD_SHAPE, "%s: expected a [N,H,W,C] tensor", what);

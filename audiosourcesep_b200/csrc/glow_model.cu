@@ -94,6 +94,7 @@ GlowModel::GlowModel(const asep_glow_cfg& cfg, int device) : cfg_(cfg), device_(
     CUDA_CHECK(cudaMalloc(&p.dev, std::max<int64_t>(p.numel(), 1) * sizeof(float)));
     CUDA_CHECK(cudaMemcpy(p.dev, p.host.data(), p.host.size() * sizeof(float), cudaMemcpyHostToDevice));
     params_[name] = std::move(p);
+    order_.push_back(name);
   };
   for (int b = 0; b < cfg.L; ++b) {
     const int C = levels_[b].C, Ch = C / 2;
@@ -135,7 +136,10 @@ GlowModel::GlowModel(const asep_glow_cfg& cfg, int device) : cfg_(cfg), device_(
 
 GlowModel::~GlowModel() {
   for (auto& kv : params_)
-    if (kv.second.dev) cudaFree(kv.second.dev);
+    if (kv.second.dev && !kv.second.in_flat) cudaFree(kv.second.dev);
+  for (void* p : {(void*)theta_, (void*)adam_m_, (void*)adam_u_, (void*)tq2_, (void*)tdc2_, (void*)tr3_, (void*)ts3_,
+                  (void*)tstats_, (void*)ldc_, (void*)ld_total_})
+    if (p) cudaFree(p);
   for (auto& s : steps_) {
     for (float* p : {s.sc, s.g1, s.b1, s.g2, s.b2, s.k2t})
       if (p) cudaFree(p);

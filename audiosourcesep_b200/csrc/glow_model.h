@@ -8,6 +8,7 @@
 
 #include "kernels.h"
 #include "nn_tc.h"
+#include "train_kernels.h"
 
 namespace asep {
 
@@ -15,6 +16,8 @@ struct Param {
   std::vector<int64_t> shape;
   std::vector<float> host;
   float* dev = nullptr;
+  bool in_flat = false;        // dev points into the flat trainable vector (training enabled)
+  long long flat_off = -1;     // offset of a trainable parameter in the flat vector
   int64_t numel() const { int64_t n = 1; for (auto s : shape) n *= s; return n; }
 };
 
@@ -61,6 +64,22 @@ class GlowModel {
   void coupling_nn_backward(int block, int step, const float* state, const float* gr, float* gxb, int N,
                             cudaStream_t s);
 
+  // ---- training (train_glow.py:29-44, train_noisy_glow.py:30-33, train_utils.py:23-41)
+  // Moves every trainable parameter into one flat device vector (order of weights.py:glow_param_shapes filtered by
+  // is_trainable), allocates the Adamax state and the weight-gradient scratch.  Needs ASEP_PREC_FP32.
+  void enable_training();
+  long long num_trainable() const { return n_trainable_; }
+  // grads [num_trainable] (device) <- d loss / d theta with loss = sum_i -log_prob(x_i + sigma*noise_i) / global_batch
+  // over the N local samples (the SUM over data-parallel ranks is then the global-mean gradient); loss [1] likewise.
+  void train_grads(const float* x, const float* noise, float sigma, int N, int global_batch, float* grads, float* loss,
+                   cudaStream_t s);
+  // Keras Adamax update of the flat vector, then every derived constant is refreshed on the device.
+  void adamax_step(const float* grads, float lr, float beta1, float beta2, float eps, cudaStream_t s);
+  // copies the flat vector back into the host-side parameter store (get_param / prepare see the trained values)
+  void sync_host();
+  void copy_flat(float* dst, cudaStream_t s) const;         // theta -> dst (device)
+  void set_flat(const float* src, cudaStream_t s);          // src (device) -> theta, refresh constants
+
   const asep_glow_cfg& cfg() const { return cfg_; }
   int device() const { return device_; }
   const Level& level(int b) const { return levels_[b]; }
@@ -87,6 +106,15 @@ class GlowModel {
   void require_prepared() const;
   double const_logdet() const;
   void latent_slice(int b, int& Cz, int& nb, int& coff) const;
+
+  void derive_on_device(cudaStream_t s);
+  StepTrainPtrs step_ptrs(int b, int k);
+  std::vector<std::string> order_;          // parameter names in construction order
+  float *theta_ = nullptr, *adam_m_ = nullptr, *adam_u_ = nullptr;
+  long long n_trainable_ = 0, adam_t_ = 0;
+  float *tq2_ = nullptr, *tdc2_ = nullptr, *tr3_ = nullptr, *ts3_ = nullptr;
+  double *tstats_ = nullptr, *ldc_ = nullptr, *ld_total_ = nullptr;
+  bool training_ = false;
 
   asep_glow_cfg cfg_;
   int device_;

@@ -1,0 +1,186 @@
+// Glow training step: loss, gradients of every trainable parameter, Adamax update (reference: train_glow.py:29-44,
+// train_noisy_glow.py:30-33, train_utils.py:23-41).  The reverse sweep is grad_log_prob's; per flow step it adds the
+// weight gradients (train_kernels.cu).  Data-parallel training sums `grads` over ranks with an NCCL all-reduce between
+// train_grads() and adamax_step() (host side: audiosourcesep_b200/train_glow.py).
+#include <cmath>
+#include <cstring>
+
+#include "glow_model.h"
+
+namespace asep {
+
+namespace {
+bool trainable_name(const std::string& n) {
+  auto ends = [&](const char* suf) {
+    const size_t l = std::strlen(suf);
+    return n.size() >= l && n.compare(n.size() - l, l, suf) == 0;
+  };
+  return !(ends("inv1x1/P") || ends("inv1x1/sign_S") || ends("moving_mean") || ends("moving_variance"));
+}
+}  // namespace
+
+void GlowModel::enable_training() {
+  if (training_) return;
+  ASEP_CHECK(precision_ == ASEP_PREC_FP32 && prepared_, ASEP_ERR_STATE,
+             "training runs in the ASEP_PREC_FP32 mode: call asep_glow_prepare(h, ASEP_PREC_FP32) first");
+  ASEP_CHECK(cfg_.learntop, ASEP_ERR_UNSUPPORTED, "the training step expects the learnable top prior (learntop)");
+  CUDA_CHECK(cudaSetDevice(device_));
+  CUDA_CHECK(cudaDeviceSynchronize());
+  long long n = 0;
+  for (const auto& name : order_)
+    if (trainable_name(name)) { params_.at(name).flat_off = n; n += params_.at(name).numel(); }
+  n_trainable_ = n;
+  CUDA_CHECK(cudaMalloc(&theta_, (size_t)n * sizeof(float)));
+  CUDA_CHECK(cudaMalloc(&adam_m_, (size_t)n * sizeof(float)));
+  CUDA_CHECK(cudaMalloc(&adam_u_, (size_t)n * sizeof(float)));
+  CUDA_CHECK(cudaMemset(adam_m_, 0, (size_t)n * sizeof(float)));
+  CUDA_CHECK(cudaMemset(adam_u_, 0, (size_t)n * sizeof(float)));
+  for (const auto& name : order_) {
+    Param& p = params_.at(name);
+    if (p.flat_off < 0) continue;
+    CUDA_CHECK(cudaMemcpy(theta_ + p.flat_off, p.dev, (size_t)p.numel() * sizeof(float), cudaMemcpyDeviceToDevice));
+    cudaFree(p.dev);
+    p.dev = theta_ + p.flat_off;
+    p.in_flat = true;
+  }
+  const int F = cfg_.n_filters;
+  CUDA_CHECK(cudaMalloc(&tq2_, (size_t)F * F * sizeof(float)));
+  CUDA_CHECK(cudaMalloc(&tdc2_, (size_t)F * sizeof(float)));
+  CUDA_CHECK(cudaMalloc(&tr3_, (size_t)9 * F * 64 * sizeof(float)));
+  CUDA_CHECK(cudaMalloc(&ts3_, (size_t)9 * 64 * sizeof(float)));
+  CUDA_CHECK(cudaMalloc(&tstats_, (size_t)(2 * 64 + 64 * 64) * sizeof(double)));
+  CUDA_CHECK(cudaMalloc(&ldc_, steps_.size() * sizeof(double)));
+  CUDA_CHECK(cudaMalloc(&ld_total_, sizeof(double)));
+  adam_t_ = 0;
+  training_ = true;
+  prepare(ASEP_PREC_FP32);          // re-reads the parameter pointers (they moved into the flat vector)
+  derive_on_device(nullptr);
+  CUDA_CHECK(cudaDeviceSynchronize());
+}
+
+StepTrainPtrs GlowModel::step_ptrs(int b, int k) {
+  const std::string pre = "b" + std::to_string(b) + "/s" + std::to_string(k) + "/";
+  auto P = [&](const char* n) -> const Param& { return params_.at(pre + n); };
+  StepDerived& sd = step(b, k);
+  StepTrainPtrs sp{};
+  sp.C = levels_[b].C; sp.F = cfg_.n_filters;
+  sp.an_ls = P("actnorm/log_scale").dev; sp.an_shift = P("actnorm/shift").dev;
+  sp.P = P("inv1x1/P").dev; sp.L = P("inv1x1/L").dev; sp.U = P("inv1x1/U").dev;
+  sp.logS = P("inv1x1/log_S").dev; sp.signS = P("inv1x1/sign_S").dev;
+  sp.k1 = P("nn/conv1/kernel").dev; sp.c1 = P("nn/conv1/bias").dev;
+  sp.bn1_gamma = P("nn/bn1/gamma").dev; sp.bn1_beta = P("nn/bn1/beta").dev;
+  sp.bn1_mean = P("nn/bn1/moving_mean").dev; sp.bn1_var = P("nn/bn1/moving_variance").dev;
+  sp.k2 = P("nn/conv2/kernel").dev; sp.c2 = P("nn/conv2/bias").dev;
+  sp.bn2_gamma = P("nn/bn2/gamma").dev; sp.bn2_beta = P("nn/bn2/beta").dev;
+  sp.bn2_mean = P("nn/bn2/moving_mean").dev; sp.bn2_var = P("nn/bn2/moving_variance").dev;
+  sp.k3 = P("nn/conv3/kernel").dev; sp.c3 = P("nn/conv3/bias").dev;
+  sp.sc = sd.sc; sp.g1f = sd.g1; sp.b1f = sd.b1; sp.g2f = sd.g2; sp.b2f = sd.b2; sp.k2t = sd.k2t;
+  sp.o_an_ls = P("actnorm/log_scale").flat_off; sp.o_an_shift = P("actnorm/shift").flat_off;
+  sp.o_L = P("inv1x1/L").flat_off; sp.o_U = P("inv1x1/U").flat_off; sp.o_logS = P("inv1x1/log_S").flat_off;
+  sp.o_k1 = P("nn/conv1/kernel").flat_off; sp.o_c1 = P("nn/conv1/bias").flat_off;
+  sp.o_bn1_gamma = P("nn/bn1/gamma").flat_off; sp.o_bn1_beta = P("nn/bn1/beta").flat_off;
+  sp.o_k2 = P("nn/conv2/kernel").flat_off; sp.o_c2 = P("nn/conv2/bias").flat_off;
+  sp.o_bn2_gamma = P("nn/bn2/gamma").flat_off; sp.o_bn2_beta = P("nn/bn2/beta").flat_off;
+  sp.o_k3 = P("nn/conv3/kernel").flat_off; sp.o_c3 = P("nn/conv3/bias").flat_off;
+  return sp;
+}
+
+void GlowModel::derive_on_device(cudaStream_t s) {
+  for (int b = 0; b < cfg_.L; ++b)
+    for (int k = 0; k < cfg_.K; ++k)
+      launch_derive_step(step_ptrs(b, k), (double)levels_[b].H * levels_[b].W, ldc_ + (size_t)b * cfg_.K + k, s);
+  launch_sum_doubles(ldc_, (int)steps_.size(), ld_total_, s);
+}
+
+void GlowModel::train_grads(const float* x, const float* noise, float sigma, int N, int global_batch, float* grads,
+                            float* loss, cudaStream_t s) {
+  ASEP_CHECK(training_, ASEP_ERR_STATE, "asep_glow_enable_training() has not been called");
+  ASEP_CHECK(N >= 1 && global_batch >= N, ASEP_ERR_BAD_ARG, "bad batch sizes (local %d, global %d)", N, global_batch);
+  CUDA_CHECK(cudaSetDevice(device_));
+  const int L = cfg_.L, K = cfg_.K, F = cfg_.n_filters;
+  const float gs = -1.0f / (float)global_batch;      // loss = -sum log_prob / global_batch (train_glow.py:30-31)
+  ensure_work(N, true);
+  const float* xin = x;
+  if (noise != nullptr) {                              // train_noisy_glow.py:31-32: X + sigma*N(0,1) in raw data units
+    launch_axpy(x, noise, sigma, work_.gB, (long long)N * cfg_.H * cfg_.W * cfg_.C, s);
+    xin = work_.gB;
+  }
+  run_forward(xin, N, true, s);
+  const float* loc = params_.at("prior/loc").dev;
+  const float* ls = params_.at("prior/log_scale").dev;
+  launch_prior(work_.z, loc, ls, work_.acc_prior, work_.gz, N, Dl_, s);
+  // SpecPreprocessing log-det constant (flow_tfp_bijectors.py:390-396); the per-step constants come from the device
+  const double pre_const = (double)cfg_.H * cfg_.W * cfg_.C * std::log(1.0 / ((double)cfg_.maxval - (double)cfg_.minval));
+  launch_loss(work_.acc_ld, work_.acc_prior, ld_total_, pre_const, N, 1.0 / (double)global_batch, loss, s);
+  CUDA_CHECK(cudaMemsetAsync(grads, 0, (size_t)n_trainable_ * sizeof(float), s));
+  launch_prior_grads(work_.z, loc, ls, grads + params_.at("prior/loc").flat_off, grads + params_.at("prior/log_scale").flat_off,
+                     N, Dl_, gs, s);
+  float* gX_next = nullptr;
+  for (int b = L - 1; b >= 0; --b) {
+    const Level& lv = levels_[b];
+    const long long M = (long long)N * lv.H * lv.W;
+    int Cz, nb, coff;
+    latent_slice(b, Cz, nb, coff);
+    float* gy = work_.gA;
+    float* other = work_.gB;
+    if (gX_next == gy) std::swap(gy, other);
+    launch_split_merge(gy, work_.gz, gX_next, N, lv.H, lv.W, lv.C, Cz, nb, CL_, coff, Dl_, 1, s);
+    for (int k = 0; k < K; ++k) {
+      StepDerived& sd = step(b, k);
+      const StepTrainPtrs sp = step_ptrs(b, k);
+      launch_bwd_coupling(gy, work_.U[b][k], work_.R[b][k], work_.gr, work_.gu, M, lv.C, s);
+      // recompute a1, a2 from the saved step input, then gp2 (t2), gp1 (t1), gxb
+      nn_fp32_forward(sd.w32, work_.U[b][k], work_.a1, work_.a2, work_.gxb, N, lv.H, lv.W, lv.C, F, s);
+      nn_fp32_backward(sd.w32, work_.a1, work_.a2, work_.gr, work_.t1, work_.t2, work_.gxb, N, lv.H, lv.W, lv.C, F, s);
+      // ---- weight gradients of this step
+      CUDA_CHECK(cudaMemsetAsync(tq2_, 0, (size_t)F * F * sizeof(float), s));
+      CUDA_CHECK(cudaMemsetAsync(tdc2_, 0, (size_t)F * sizeof(float), s));
+      CUDA_CHECK(cudaMemsetAsync(tr3_, 0, (size_t)9 * F * lv.C * sizeof(float), s));
+      CUDA_CHECK(cudaMemsetAsync(ts3_, 0, (size_t)9 * lv.C * sizeof(float), s));
+      CUDA_CHECK(cudaMemsetAsync(tstats_, 0, (size_t)(2 * lv.C + lv.C * lv.C) * sizeof(double), s));
+      launch_wgrad_tn(work_.a1, work_.t2, tq2_, M, F, s);
+      launch_colsum(work_.t2, tdc2_, M, F, s);
+      launch_wgrad_conv3(work_.a2, work_.gr, tr3_, ts3_, N, lv.H, lv.W, lv.C, F, s);
+      launch_wgrad_conv1(work_.U[b][k], work_.t1, grads + sp.o_k1, grads + sp.o_c1, N, lv.H, lv.W, lv.C, F, gs, s);
+      launch_step_stats(work_.gu, work_.gxb, work_.U[b][k], sd.sc, tstats_, M, lv.C, s);
+      launch_finalize_step(sp, tq2_, tdc2_, tr3_, ts3_, tstats_, grads, (double)M, gs, s);
+      // ---- data gradient to the previous step
+      launch_bwd_pre(work_.gu, work_.gxb, other, sd.sc, M, lv.C, s);
+      std::swap(gy, other);
+    }
+    gX_next = gy;
+  }
+}
+
+void GlowModel::adamax_step(const float* grads, float lr, float beta1, float beta2, float eps, cudaStream_t s) {
+  ASEP_CHECK(training_, ASEP_ERR_STATE, "asep_glow_enable_training() has not been called");
+  CUDA_CHECK(cudaSetDevice(device_));
+  ++adam_t_;
+  const float lr_t = (float)((double)lr / (1.0 - std::pow((double)beta1, (double)adam_t_)));
+  launch_adamax(theta_, grads, adam_m_, adam_u_, n_trainable_, lr_t, beta1, beta2, eps, s);
+  derive_on_device(s);
+}
+
+void GlowModel::copy_flat(float* dst, cudaStream_t s) const {
+  ASEP_CHECK(training_, ASEP_ERR_STATE, "asep_glow_enable_training() has not been called");
+  CUDA_CHECK(cudaMemcpyAsync(dst, theta_, (size_t)n_trainable_ * sizeof(float), cudaMemcpyDeviceToDevice, s));
+}
+
+void GlowModel::set_flat(const float* src, cudaStream_t s) {
+  ASEP_CHECK(training_, ASEP_ERR_STATE, "asep_glow_enable_training() has not been called");
+  CUDA_CHECK(cudaMemcpyAsync(theta_, src, (size_t)n_trainable_ * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  derive_on_device(s);
+}
+
+void GlowModel::sync_host() {
+  if (!training_) return;
+  CUDA_CHECK(cudaDeviceSynchronize());
+  for (const auto& name : order_) {
+    Param& p = params_.at(name);
+    if (p.flat_off < 0) continue;
+    CUDA_CHECK(cudaMemcpy(p.host.data(), p.dev, (size_t)p.numel() * sizeof(float), cudaMemcpyDeviceToHost));
+  }
+  prepare(precision_);
+}
+
+}  // namespace asep

@@ -141,6 +141,58 @@ class Glow:
         _lib.check(self._lib.asep_glow_sample(self._h, de.ptr, dx.ptr, _lib.stream_ptr()))
         return x
 
+    # ---- training (train_glow.py:29-44; Keras Adamax, train_utils.py:29-30)
+    def enable_training(self) -> int:
+        """Switch to the fp32 mode, move the trainables into one flat device vector; returns its length."""
+        self.prepare(_lib.PREC_FP32)
+        _lib.check(self._lib.asep_glow_enable_training(self._h))
+        n = ctypes.c_int64()
+        _lib.check(self._lib.asep_glow_num_trainable(self._h, ctypes.byref(n)))
+        self.num_trainable = int(n.value)
+        return self.num_trainable
+
+    def trainable_layout(self):
+        """[(name, offset, shape)] of the flat trainable / gradient vector."""
+        out, off = [], 0
+        for name, shape in self._shapes.items():
+            if is_trainable(name):
+                n = int(np.prod(shape))
+                out.append((name, off, tuple(shape)))
+                off += n
+        return out
+
+    def train_grads(self, x: torch.Tensor, global_batch: int, noise: Optional[torch.Tensor] = None, sigma: float = 0.0):
+        """(grads [num_trainable], loss [1]) of loss = sum_i -log_prob(x_i + sigma*noise_i) / global_batch."""
+        x = _f32c(x, self.device)
+        noise = None if noise is None else _f32c(noise, self.device)
+        grads = torch.empty((self.num_trainable,), dtype=torch.float32, device=self.device)
+        loss = torch.empty((1,), dtype=torch.float32, device=self.device)
+        dx, dn, dg, dls = _lib.dl(x), _lib.dl(noise), _lib.dl(grads), _lib.dl(loss)
+        _lib.check(self._lib.asep_glow_train_grads(self._h, dx.ptr, dn.ptr, float(sigma), int(global_batch), dg.ptr,
+                                                   dls.ptr, _lib.stream_ptr()))
+        return grads, loss
+
+    def adamax_step(self, grads: torch.Tensor, lr: float = 1e-3, beta1: float = 0.9, beta2: float = 0.999,
+                    eps: float = 1e-7) -> None:
+        grads = _f32c(grads, self.device)
+        dg = _lib.dl(grads)
+        _lib.check(self._lib.asep_glow_adamax_step(self._h, dg.ptr, float(lr), float(beta1), float(beta2), float(eps),
+                                                   _lib.stream_ptr()))
+
+    def get_flat(self) -> torch.Tensor:
+        t = torch.empty((self.num_trainable,), dtype=torch.float32, device=self.device)
+        d = _lib.dl(t)
+        _lib.check(self._lib.asep_glow_get_flat(self._h, d.ptr, _lib.stream_ptr()))
+        return t
+
+    def set_flat(self, theta: torch.Tensor) -> None:
+        theta = _f32c(theta, self.device)
+        d = _lib.dl(theta)
+        _lib.check(self._lib.asep_glow_set_flat(self._h, d.ptr, _lib.stream_ptr()))
+
+    def sync_host(self) -> None:
+        _lib.check(self._lib.asep_glow_sync_host(self._h))
+
     # ---- coupling network of one step (test / profiling seam)
     def coupling_nn(self, block: int, step: int, state: torch.Tensor) -> torch.Tensor:
         state = _f32c(state, self.device)

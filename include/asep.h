@@ -90,6 +90,29 @@ int asep_glow_grad_log_prob(asep_glow_t h, const DLTensor* x, DLTensor* grad, DL
 /* prior.sample -> Chain.inverse with the standard-normal draw injected: eps [N,latent]. */
 int asep_glow_sample(asep_glow_t h, const DLTensor* eps, DLTensor* x, void* stream);
 
+/* ------------------------------------------------------------------ Glow training step
+ * Replaces train_glow.py:29-44 (loss = sum_i -log_prob(x_i) / global_batch, tape.gradient over all trainable
+ * variables, optimizer.apply_gradients with Keras Adamax, train_utils.py:29-30) and the noise-perturbed loss of
+ * train_noisy_glow.py:30-33.  Data parallelism = one process per GPU: every rank calls train_grads on its shard
+ * with the GLOBAL batch size, the host all-reduces (SUM, NCCL) `grads` and `loss`, every rank calls adamax_step. */
+/* Moves the trainables into one flat device vector (order: weights.py glow_param_shapes filtered by is_trainable),
+ * allocates optimiser state; requires asep_glow_prepare(h, ASEP_PREC_FP32). */
+int asep_glow_enable_training(asep_glow_t h);
+int asep_glow_num_trainable(asep_glow_t h, int64_t* out);
+/* x [N,H,W,C] raw data; noise NULL or [N,H,W,C] standard normals scaled by sigma and added to x in raw units
+ * (train_noisy_glow.py:31-32); grads [num_trainable] and loss [1] are device float32 outputs. */
+int asep_glow_train_grads(asep_glow_t h, const DLTensor* x, const DLTensor* noise, float sigma, int global_batch,
+                          DLTensor* grads, DLTensor* loss, void* stream);
+/* theta <- Adamax(theta, grads) with the Keras update m=b1 m+(1-b1) g; u=max(b2 u,|g|); theta -= lr/(1-b1^t) m/(u+eps);
+ * then every derived per-step constant is refreshed on the device. */
+int asep_glow_adamax_step(asep_glow_t h, const DLTensor* grads, float lr, float beta1, float beta2, float eps,
+                          void* stream);
+/* Flat trainable vector out / in (device float32 [num_trainable]); set_flat refreshes the derived constants. */
+int asep_glow_get_flat(asep_glow_t h, DLTensor* theta, void* stream);
+int asep_glow_set_flat(asep_glow_t h, const DLTensor* theta, void* stream);
+/* Copies the trained values back into the named-parameter store (get_param / prepare see them). */
+int asep_glow_sync_host(asep_glow_t h);
+
 /* ------------------------------------------------------------------ single bijectors
  * Stateless kernels behind the reference's Bijector classes, so each can be unit-tested the
  * way unittest_flow_models.py:25-51 does.  `inverse` != 0 selects _inverse. */

@@ -114,3 +114,52 @@ def test_langevin_constants_match_oracle():
         np.testing.assert_array_equal(sig, bo.get_sigmas(s1, sL, n, "logarithmic"))
         for i in (0, n // 2, n - 1):
             assert langevin_step_constants(sig, i) == bo.step_constants(sig, i)
+
+
+class _FakeFlow:
+    """Stands in for the libasep Glow handle so the data-parallel plumbing of train_glow can run on CPU/gloo:
+    gradient of 0.5*sum((theta - x_i)^2)/global_batch over the local shard."""
+
+    def __init__(self):
+        self.theta = torch.zeros(3)
+        self.device = torch.device("cpu")
+
+    def train_grads(self, batch, global_batch, noise=None, sigma=0.0):
+        diff = self.theta[None, :] - batch.reshape(batch.shape[0], -1)[:, :3]
+        return diff.sum(0) / global_batch, (0.5 * diff.pow(2).sum() / global_batch).reshape(1)
+
+    def adamax_step(self, grads, lr, beta1, beta2, eps):
+        self.theta = self.theta - lr * grads
+
+
+def _dp_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    from audiosourcesep_b200.train_glow import distributed_train_step
+    full = torch.arange(24, dtype=torch.float32).reshape(4, 6)
+    flow = _FakeFlow()
+    loss = distributed_train_step(flow, dict(lr=0.5, beta1=0.9, beta2=0.999, eps=1e-7), full[rank * 2:(rank + 1) * 2], 4)
+    q.put((rank, flow.theta.numpy().copy(), float(loss)))
+    dist.destroy_process_group()
+
+
+def test_data_parallel_train_step_world_size_2_gloo():
+    """Shards + SUM all-reduce reproduce the single-process step on the global batch (train_glow.py:31,42-54)."""
+    from audiosourcesep_b200.train_glow import distributed_train_step
+    full = torch.arange(24, dtype=torch.float32).reshape(4, 6)
+    ref = _FakeFlow()
+    loss_ref = float(distributed_train_step(ref, dict(lr=0.5, beta1=0.9, beta2=0.999, eps=1e-7), full, 4))
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    for rank, theta, loss in out:
+        np.testing.assert_allclose(theta, ref.theta.numpy(), rtol=1e-6)
+        assert abs(loss - loss_ref) <= 1e-5 * abs(loss_ref)
