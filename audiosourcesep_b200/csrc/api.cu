@@ -524,29 +524,21 @@ int asep_basis_glow_inner(asep_glow_t m1, asep_glow_t m2, const DLTensor* mixed,
   int* nanp = nullptr;
   if (nan_count) nanp = static_cast<int*>(view_i32(nan_count, "nan_count", dev).raw);
   cudaStream_t s = as_stream(stream);
-  float *s1 = nullptr, *s2 = nullptr;
-  CUDA_CHECK(cudaMalloc(&s1, (size_t)a.numel * sizeof(float)));
-  CUDA_CHECK(cudaMalloc(&s2, (size_t)a.numel * sizeof(float)));
-  try {
-    for (int t = 0; t < T; ++t) {
-      g1.grad_log_prob(a.f32, s1, nullptr, N, s);     // run_basis_sep.py:174-175
-      g2.grad_log_prob(b.f32, s2, nullptr, N, s);
-      launch_langevin(a.f32, b.f32, s1, s2, mx.f32, nz1 ? nz1 + (size_t)t * a.numel : nullptr,
-                      nz2 ? nz2 + (size_t)t * a.numel : nullptr, eta, lambda, noise_scale, seed, step0 + t,
-                      elem_offset, nanp, a.numel, s);
-      if (dump) {
-        CUDA_CHECK(cudaMemcpyAsync(dump + (size_t)(2 * t) * a.numel, a.f32, (size_t)a.numel * sizeof(float),
-                                   cudaMemcpyDeviceToDevice, s));
-        CUDA_CHECK(cudaMemcpyAsync(dump + (size_t)(2 * t + 1) * a.numel, b.f32, (size_t)a.numel * sizeof(float),
-                                   cudaMemcpyDeviceToDevice, s));
-      }
+  float* s1 = g1.score_scratch(N);
+  float* s2 = g2.score_scratch(N);
+  for (int t = 0; t < T; ++t) {
+    g1.grad_log_prob(a.f32, s1, nullptr, N, s);     // run_basis_sep.py:174-175
+    g2.grad_log_prob(b.f32, s2, nullptr, N, s);
+    launch_langevin(a.f32, b.f32, s1, s2, mx.f32, nz1 ? nz1 + (size_t)t * a.numel : nullptr,
+                    nz2 ? nz2 + (size_t)t * a.numel : nullptr, eta, lambda, noise_scale, seed, step0 + t,
+                    elem_offset, nanp, a.numel, s);
+    if (dump) {
+      CUDA_CHECK(cudaMemcpyAsync(dump + (size_t)(2 * t) * a.numel, a.f32, (size_t)a.numel * sizeof(float),
+                                 cudaMemcpyDeviceToDevice, s));
+      CUDA_CHECK(cudaMemcpyAsync(dump + (size_t)(2 * t + 1) * a.numel, b.f32, (size_t)a.numel * sizeof(float),
+                                 cudaMemcpyDeviceToDevice, s));
     }
-    CUDA_CHECK(cudaStreamSynchronize(s));
-  } catch (...) {
-    cudaFree(s1); cudaFree(s2);
-    throw;
   }
-  cudaFree(s1); cudaFree(s2);
   ASEP_API_END
 }
 
@@ -649,34 +641,22 @@ int asep_basis_ncsn_inner(asep_ncsn_t m1, asep_ncsn_t m2, const DLTensor* mixed,
   int* nanp = nullptr;
   if (nan_count) nanp = static_cast<int*>(view_i32(nan_count, "nan_count", dev).raw);
   cudaStream_t s = as_stream(stream);
-  float *s1 = nullptr, *s2 = nullptr;
-  int* idx = nullptr;
-  CUDA_CHECK(cudaMalloc(&s1, (size_t)a.numel * sizeof(float)));
-  CUDA_CHECK(cudaMalloc(&s2, (size_t)a.numel * sizeof(float)));
-  CUDA_CHECK(cudaMalloc(&idx, (size_t)std::max(N, 1) * sizeof(int)));
-  try {
-    std::vector<int> hidx((size_t)N, sigma_idx);                  // run_basis_sep.py:167-168
-    CUDA_CHECK(cudaMemcpyAsync(idx, hidx.data(), (size_t)N * sizeof(int), cudaMemcpyHostToDevice, s));
-    CUDA_CHECK(cudaStreamSynchronize(s));
-    for (int t = 0; t < T; ++t) {
-      g1.forward(a.f32, idx, s1, N, s);                           // run_basis_sep.py:169-170
-      g2.forward(b.f32, idx, s2, N, s);
-      launch_langevin(a.f32, b.f32, s1, s2, mx.f32, nz1 ? nz1 + (size_t)t * a.numel : nullptr,
-                      nz2 ? nz2 + (size_t)t * a.numel : nullptr, eta, lambda, noise_scale, seed, step0 + t,
-                      elem_offset, nanp, a.numel, s);
-      if (dump) {
-        CUDA_CHECK(cudaMemcpyAsync(dump + (size_t)(2 * t) * a.numel, a.f32, (size_t)a.numel * sizeof(float),
-                                   cudaMemcpyDeviceToDevice, s));
-        CUDA_CHECK(cudaMemcpyAsync(dump + (size_t)(2 * t + 1) * a.numel, b.f32, (size_t)a.numel * sizeof(float),
-                                   cudaMemcpyDeviceToDevice, s));
-      }
+  float* s1 = g1.score_scratch(N);
+  float* s2 = g2.score_scratch(N);
+  const int* idx = g1.index_scratch(N, sigma_idx, s);               // run_basis_sep.py:167-168
+  for (int t = 0; t < T; ++t) {
+    g1.forward(a.f32, idx, s1, N, s);                               // run_basis_sep.py:169-170
+    g2.forward(b.f32, idx, s2, N, s);
+    launch_langevin(a.f32, b.f32, s1, s2, mx.f32, nz1 ? nz1 + (size_t)t * a.numel : nullptr,
+                    nz2 ? nz2 + (size_t)t * a.numel : nullptr, eta, lambda, noise_scale, seed, step0 + t,
+                    elem_offset, nanp, a.numel, s);
+    if (dump) {
+      CUDA_CHECK(cudaMemcpyAsync(dump + (size_t)(2 * t) * a.numel, a.f32, (size_t)a.numel * sizeof(float),
+                                 cudaMemcpyDeviceToDevice, s));
+      CUDA_CHECK(cudaMemcpyAsync(dump + (size_t)(2 * t + 1) * a.numel, b.f32, (size_t)a.numel * sizeof(float),
+                                 cudaMemcpyDeviceToDevice, s));
     }
-    CUDA_CHECK(cudaStreamSynchronize(s));
-  } catch (...) {
-    cudaFree(s1); cudaFree(s2); cudaFree(idx);
-    throw;
   }
-  cudaFree(s1); cudaFree(s2); cudaFree(idx);
   ASEP_API_END
 }
 

@@ -137,6 +137,7 @@ GlowModel::GlowModel(const asep_glow_cfg& cfg, int device) : cfg_(cfg), device_(
 GlowModel::~GlowModel() {
   for (auto& kv : params_)
     if (kv.second.dev && !kv.second.in_flat) cudaFree(kv.second.dev);
+  if (score_buf_) cudaFree(score_buf_);
   for (void* p : {(void*)theta_, (void*)adam_m_, (void*)adam_u_, (void*)tq2_, (void*)tdc2_, (void*)tr3_, (void*)ts3_,
                   (void*)tstats_, (void*)ldc_, (void*)ld_total_})
     if (p) cudaFree(p);
@@ -307,6 +308,10 @@ void GlowModel::ensure_work(int N, bool save) {
   const int L = cfg_.L, K = cfg_.K, F = cfg_.n_filters;
   const bool fp32 = precision_ == ASEP_PREC_FP32;
   const long long M0 = (long long)N * levels_[0].H * levels_[0].W;
+  // per-step mask storage: 128 B per pixel per step; kept while it stays below 48 GB
+  double mask_bytes = 0.0;
+  for (int b = 0; b < L; ++b) mask_bytes += 2.0 * N * levels_[b].H * levels_[b].W * (F / 8.0) * K;
+  const bool keep_masks = mask_bytes <= 48e9;
   size_t bytes = 0;
   auto need = [&](size_t n) { bytes += (n + 255) & ~(size_t)255; };
   for (int pass = 0; pass < 2; ++pass) {
@@ -317,6 +322,7 @@ void GlowModel::ensure_work(int N, bool save) {
       work_.N = N;
       work_.save = save;
       work_.X.resize(L); work_.O.resize(L); work_.U.resize(L); work_.R.resize(L);
+      work_.M1.assign(L, {}); work_.M2.assign(L, {});
     }
     auto get = [&](size_t n_floats) -> float* {
       if (pass == 0) { need(n_floats * sizeof(float)); return nullptr; }
@@ -330,6 +336,15 @@ void GlowModel::ensure_work(int N, bool save) {
       const int nu = save ? std::max(K, 2) : 2, nr = save ? K : 1;
       for (int i = 0; i < nu; ++i) { float* u = get(st); if (pass == 1) work_.U[b].push_back(u); }
       for (int i = 0; i < nr; ++i) { float* r = get(st); if (pass == 1) work_.R[b].push_back(r); }
+      if (save && !fp32 && keep_masks) {
+        // 2 x 512 mask bits per pixel and step: the backward pass then needs no forward recompute
+        const size_t mw = (size_t)N * levels_[b].H * levels_[b].W * (F / 32);
+        for (int i = 0; i < K; ++i) {
+          uint32_t* m1 = reinterpret_cast<uint32_t*>(get(mw));
+          uint32_t* m2 = reinterpret_cast<uint32_t*>(get(mw));
+          if (pass == 1) { work_.M1[b].push_back(m1); work_.M2[b].push_back(m2); }
+        }
+      }
     }
     const size_t st0 = (size_t)M0 * levels_[0].C;
     float* z = get((size_t)N * Dl_);
@@ -364,11 +379,12 @@ void GlowModel::ensure_work(int N, bool save) {
 void GlowModel::nn_forward(int b, int k, const float* state, float* r, int N, bool save, cudaStream_t s) {
   const Level& lv = levels_[b];
   StepDerived& sd = step(b, k);
-  (void)save;
   if (precision_ == ASEP_PREC_FP32) {
     nn_fp32_forward(sd.w32, state, work_.a1, work_.a2, r, N, lv.H, lv.W, lv.C, cfg_.n_filters, s);
   } else {
-    nn_tc_forward(sd.wtc, work_.tc, state, r, nullptr, nullptr, N, lv.H, lv.W, lv.C, s);
+    uint32_t *m1 = nullptr, *m2 = nullptr;
+    if (save && !work_.M1.empty() && !work_.M1[b].empty()) { m1 = work_.M1[b][k]; m2 = work_.M2[b][k]; }
+    nn_tc_forward(sd.wtc, work_.tc, state, r, m1, m2, N, lv.H, lv.W, lv.C, s);
   }
 }
 
@@ -418,6 +434,18 @@ void GlowModel::run_forward(const float* x, int N, bool save, cudaStream_t s) {
   }
 }
 
+float* GlowModel::score_scratch(int N) {
+  const size_t need = (size_t)N * cfg_.H * cfg_.W * cfg_.C * sizeof(float);
+  if (need > score_cap_) {
+    CUDA_CHECK(cudaDeviceSynchronize());
+    if (score_buf_) cudaFree(score_buf_);
+    score_buf_ = nullptr;
+    CUDA_CHECK(cudaMalloc(&score_buf_, need));
+    score_cap_ = need;
+  }
+  return score_buf_;
+}
+
 void GlowModel::forward(const float* x, float* z, float* fldj, int N, cudaStream_t s) {
   if (N == 0) return;
   run_forward(x, N, false, s);
@@ -456,7 +484,10 @@ void GlowModel::grad_log_prob(const float* x, float* grad, float* logp, int N, c
     launch_split_merge(gy, work_.gz, gX_next, N, lv.H, lv.W, lv.C, Cz, nb, CL_, coff, Dl_, 1, s);
     for (int k = 0; k < K; ++k) {          // steps were applied K-1..0, so unwind 0..K-1
       launch_bwd_coupling(gy, work_.U[b][k], work_.R[b][k], work_.gr, work_.gu, M, lv.C, s);
-      nn_backward(b, k, work_.U[b][k], work_.gr, work_.gxb, N, s);
+      if (precision_ == ASEP_PREC_BF16 && !work_.M1.empty() && !work_.M1[b].empty())
+        nn_tc_backward(step(b, k).wtc, work_.tc, work_.gr, work_.M1[b][k], work_.M2[b][k], work_.gxb, N, lv.H, lv.W, lv.C, s);
+      else
+        nn_backward(b, k, work_.U[b][k], work_.gr, work_.gxb, N, s);
       launch_bwd_pre(work_.gu, work_.gxb, other, step(b, k).sc, M, lv.C, s);
       std::swap(gy, other);
     }

@@ -80,6 +80,9 @@ class GlowModel {
   void copy_flat(float* dst, cudaStream_t s) const;         // theta -> dst (device)
   void set_flat(const float* src, cudaStream_t s);          // src (device) -> theta, refresh constants
 
+  // persistent scratch for a score tensor [N,H,W,C] (BASIS inner loop), grown on demand
+  float* score_scratch(int N);
+
   const asep_glow_cfg& cfg() const { return cfg_; }
   int device() const { return device_; }
   const Level& level(int b) const { return levels_[b]; }
@@ -92,6 +95,7 @@ class GlowModel {
     bool save = false;
     std::vector<float*> X, O;               // per level: block input / output state
     std::vector<std::vector<float*>> U, R;  // per level, per step (save) or 2 ping-pong / 1 (no save)
+    std::vector<std::vector<uint32_t*>> M1, M2;   // tcgen05 path, save: ReLU bit masks of every step (no recompute in backward)
     float *z = nullptr, *gz = nullptr, *gA = nullptr, *gB = nullptr, *gr = nullptr, *gu = nullptr, *gxb = nullptr;
     double *acc_ld = nullptr, *acc_prior = nullptr;
     float *a1 = nullptr, *a2 = nullptr, *t1 = nullptr, *t2 = nullptr;   // fp32 NN scratch
@@ -126,6 +130,8 @@ class GlowModel {
   int precision_ = ASEP_PREC_FP32;
   DeviceArena arena_;
   Work work_;
+  float* score_buf_ = nullptr;
+  size_t score_cap_ = 0;
 };
 
 }  // namespace asep

@@ -22,6 +22,34 @@ NcsnModel::~NcsnModel() {
     if (kv.second) cudaFree(kv.second);
   if (sigmas_dev_) cudaFree(sigmas_dev_);
   if (arena_) cudaFree(arena_);
+  if (score_buf_) cudaFree(score_buf_);
+  if (idx_buf_) cudaFree(idx_buf_);
+}
+
+float* NcsnModel::score_scratch(int N) {
+  const size_t need = (size_t)N * cfg_.H * cfg_.W * cfg_.C * sizeof(float);
+  if (need > score_cap_) {
+    CUDA_CHECK(cudaDeviceSynchronize());
+    if (score_buf_) cudaFree(score_buf_);
+    score_buf_ = nullptr;
+    CUDA_CHECK(cudaMalloc(&score_buf_, need));
+    score_cap_ = need;
+  }
+  return score_buf_;
+}
+
+const int* NcsnModel::index_scratch(int N, int sigma_idx, cudaStream_t s) {
+  if ((size_t)N > idx_cap_) {
+    CUDA_CHECK(cudaDeviceSynchronize());
+    if (idx_buf_) cudaFree(idx_buf_);
+    idx_buf_ = nullptr;
+    CUDA_CHECK(cudaMalloc(&idx_buf_, (size_t)N * sizeof(int)));
+    idx_cap_ = (size_t)N;
+  }
+  CUDA_CHECK(cudaStreamSynchronize(s));            // the host staging vector may still feed an earlier copy
+  idx_host_.assign((size_t)N, sigma_idx);
+  CUDA_CHECK(cudaMemcpyAsync(idx_buf_, idx_host_.data(), (size_t)N * sizeof(int), cudaMemcpyHostToDevice, s));
+  return idx_buf_;
 }
 
 void NcsnModel::set_param(const std::string& name, const float* src, const std::vector<int64_t>& shape, bool on_device) {

@@ -29,6 +29,9 @@ class NcsnModel {
   const asep_ncsn_cfg& cfg() const { return cfg_; }
   int device() const { return device_; }
   int64_t num_params() const;
+  // persistent scratch of the BASIS inner loop: a score tensor [N,H,W,1] and a constant sigma index vector [N]
+  float* score_scratch(int N);
+  const int* index_scratch(int N, int sigma_idx, cudaStream_t s);
 
  private:
   struct T { float* p = nullptr; int H = 0, W = 0, C = 0; };   // fp32 NHWC activation (batch = N_)
@@ -61,6 +64,10 @@ class NcsnModel {
   int N_ = 0;
   const int* idx_ = nullptr;
   cudaStream_t s_ = nullptr;
+  float* score_buf_ = nullptr;
+  int* idx_buf_ = nullptr;
+  size_t score_cap_ = 0, idx_cap_ = 0;
+  std::vector<int> idx_host_;
   char* arena_ = nullptr;
   size_t arena_cap_ = 0, arena_off_ = 0;
 };

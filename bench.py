@@ -231,7 +231,9 @@ def run_ours(args):
             step_fn()
         barrier()
         evs = []
-        if profile:
+        if profile == "conv":
+            _lib.conv_profile(True)
+        elif profile:
             _lib.tc_profile(True)
         n0 = _lib.launch_count()
         for _ in range(steps):
@@ -244,7 +246,10 @@ def run_ours(args):
         barrier()
         launches = _lib.launch_count() - n0
         prof = None
-        if profile:
+        if profile == "conv":
+            prof = _lib.conv_profile_read()
+            _lib.conv_profile(False)
+        elif profile:
             prof = _lib.tc_profile_read()
             _lib.tc_profile(False)
         total_ms = sum(a.elapsed_time(b) for a, b in evs)
@@ -310,6 +315,73 @@ def run_ours(args):
         if not (torch.isfinite(t1).all() and torch.isfinite(t2).all()):
             basis["note"] += "; WARNING non-finite state"
 
+    # ---- 4. BASIS with NCSN v1 / v2 score networks (configs 4 and 5 of BASELINE.json), n_mixed = 30 segments per GPU
+    ncsn = {}
+    if args.ncsn_segments > 0:
+        from audiosourcesep_b200 import NCSNConfig
+        from audiosourcesep_b200.ncsn.score_model import ScoreModel
+        from audiosourcesep_b200.weights import init_ncsn_params
+        nseg = args.ncsn_segments
+        mixed, _, _ = synthetic.basis_problem(nseg, seed1=20 + rank, seed2=60 + rank)
+        mixed_d = torch.as_tensor(mixed).to(dev)
+        for ver, ncfg, gflop in (("v1", NCSNConfig(version="v1", ngf=192, num_classes=10, sigma1=1.0), 533.9),
+                                 ("v2", NCSNConfig(version="v2", ngf=128, num_classes=200, sigma1=30.0), 237.3)):
+            sig_n = bo.get_sigmas(ncfg.sigma1, ncfg.sigmaL, ncfg.num_classes, "logarithmic")
+            s1 = ScoreModel(ncfg, init_ncsn_params(ncfg, seed=11), sigmas=sig_n, device=local_rank)
+            s2 = ScoreModel(ncfg, init_ncsn_params(ncfg, seed=12), sigmas=sig_n, device=local_rank)
+            a1, a2 = synthetic.langevin_init(nseg, seed=7 + rank)
+            u1, u2 = torch.as_tensor(a1).to(dev), torch.as_tensor(a2).to(dev)
+            idx = ncfg.num_classes - 1
+            eta_n, lam_n, ns_n = bo.step_constants(sig_n, idx)
+            cnt = [0]
+
+            def step_ncsn():
+                ops.basis_ncsn_inner(s1, s2, mixed_d, u1, u2, idx, args.ncsn_T, float(eta_n), float(lam_n), float(ns_n),
+                                     seed=2, step0=cnt[0], elem_offset=rank * nseg * D_PATCH)
+                cnt[0] += args.ncsn_T
+
+            nst = max(2, args.steps // 2)
+            n_ms, n_launches, (c_ms, c_n, c_fl) = timed_loop(step_ncsn, nst, 2, profile="conv")
+            rate = world * nseg * args.ncsn_T * nst / (n_ms * 1e-3)
+            conv_tf = c_fl / (c_ms * 1e-3) / 1e12 if c_ms > 0 else 0.0
+            ncsn[ver] = {"metric": f"basis_ncsn_{ver}_segment_steps_per_s", "value": rate, "unit": "segment-steps/s",
+                         "segments_per_gpu": nseg, "ms_per_langevin_step": n_ms / (nst * args.ncsn_T),
+                         "gpu_launches": n_launches, "alg_tflops": rate * gflop / 1e3,
+                         "roofline": {"bound": "tensor", "kernel": "k_conv_tc (TMA-fed tcgen05 implicit-GEMM convolution)",
+                                      "achieved": conv_tf, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+                                      "frac": conv_tf / peaks["bf16_sustained"], "launches": c_n,
+                                      "kernel_share_of_step": c_ms / n_ms if n_ms > 0 else None},
+                         "finite": bool(torch.isfinite(u1).all() and torch.isfinite(u2).all())}
+            del s1, s2
+
+    # ---- 5. Glow training step (config 2): fp32 exact mode, global batch 32 per GPU, Adamax, NCCL gradient all-reduce
+    train = None
+    if args.train_batch > 0:
+        from audiosourcesep_b200 import train_glow as tg
+        tcfg = GlowConfig(K=args.K)
+        tb = args.train_batch
+        xt = torch.as_tensor(synthetic.mel_patches_db(tb, seed=300 + rank)).to(dev)
+        # the reference's own initialisation: QR/LU 1x1, Glorot conv1/conv2, zero conv3, data-dependent ActNorm
+        # (flow_builder.py:96-100); identical on every rank (same seed, rank-0-shaped minibatch)
+        tm = Glow(tcfg, init_glow_params(tcfg, seed=2, mode="faithful"), precision=_lib.PREC_FP32, device=local_rank)
+        tm.init_actnorm(torch.as_tensor(synthetic.mel_patches_db(tb, seed=300)).to(dev))
+        tm.enable_training()
+        opt = dict(lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-7)
+        last = [0.0]
+
+        def step_train():
+            last[0] = tg.distributed_train_step(tm, opt, xt, tb * world)
+
+        nst = max(2, args.steps // 3)
+        t_ms, t_launches, _ = timed_loop(step_train, nst, 1)
+        train = {"metric": "glow_train_samples_per_s", "value": world * tb * nst / (t_ms * 1e-3), "unit": "samples/s",
+                 "steps_per_s": nst / (t_ms * 1e-3), "per_gpu_batch": tb, "global_batch": tb * world, "dtype": "f32",
+                 "ms_per_step": t_ms / nst, "gpu_launches": t_launches, "allreduce_bytes_per_step": int(tm.num_trainable * 4),
+                 "alg_tflops": world * tb * nst * 3 * F_GLOW * (args.K / 40.0) / (t_ms * 1e-3) / 1e12,
+                 "loss": float(last[0].item()), "loss_finite": bool(torch.isfinite(last[0]).all()),
+                 "note": "CUDA-core fp32 exact mode (weight gradients not yet on tcgen05); NCCL all-reduce of the flat gradient"}
+        del tm
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -362,6 +434,8 @@ def run_ours(args):
         "clocks": clocks,
         "alg_tflops": value * F_GLOW * (args.K / 40.0) / 1e12,
         "basis": basis,
+        "basis_ncsn": ncsn or None,
+        "train": train,
         "tc_cluster": args.cluster,
     }
     print(json.dumps(line), flush=True)
@@ -380,6 +454,9 @@ def main():
     ap.add_argument("--cluster", type=int, default=1, help="TMA-multicast cluster size of the tcgen05 kernel")
     ap.add_argument("--basis-segments", type=int, default=256, help="segments per GPU of the BASIS leg (0 = skip)")
     ap.add_argument("--basis-T", type=int, default=2)
+    ap.add_argument("--ncsn-segments", type=int, default=30, help="segments per GPU of the NCSN-BASIS legs (0 = skip)")
+    ap.add_argument("--ncsn-T", type=int, default=2)
+    ap.add_argument("--train-batch", type=int, default=32, help="per-GPU batch of the Glow train-step leg (0 = skip)")
     ap.add_argument("--cpu-sample", type=int, default=4, help="patches of the CPU baseline sample (0 = skip)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
