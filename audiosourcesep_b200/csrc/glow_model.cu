@@ -139,7 +139,8 @@ GlowModel::~GlowModel() {
     if (kv.second.dev && !kv.second.in_flat) cudaFree(kv.second.dev);
   if (score_buf_) cudaFree(score_buf_);
   for (void* p : {(void*)theta_, (void*)adam_m_, (void*)adam_u_, (void*)tq2_, (void*)tdc2_, (void*)tr3_, (void*)ts3_,
-                  (void*)tstats_, (void*)ldc_, (void*)ld_total_})
+                  (void*)tstats_, (void*)ldc_, (void*)ld_total_, (void*)tdc1_, (void*)td1_, (void*)da1_, (void*)da2_,
+                  (void*)dgp2_, (void*)dgp1_, (void*)dcol_})
     if (p) cudaFree(p);
   for (auto& s : steps_) {
     for (float* p : {s.sc, s.g1, s.b1, s.g2, s.b2, s.k2t})

@@ -9,6 +9,7 @@
 #include "kernels.h"
 #include "nn_tc.h"
 #include "train_kernels.h"
+#include "wgrad_tc.h"
 
 namespace asep {
 
@@ -116,7 +117,10 @@ class GlowModel {
   std::vector<std::string> order_;          // parameter names in construction order
   float *theta_ = nullptr, *adam_m_ = nullptr, *adam_u_ = nullptr;
   long long n_trainable_ = 0, adam_t_ = 0;
-  float *tq2_ = nullptr, *tdc2_ = nullptr, *tr3_ = nullptr, *ts3_ = nullptr;
+  float *tq2_ = nullptr, *tdc2_ = nullptr, *tr3_ = nullptr, *ts3_ = nullptr, *tdc1_ = nullptr, *td1_ = nullptr;
+  __nv_bfloat16 *da1_ = nullptr, *da2_ = nullptr, *dgp2_ = nullptr, *dgp1_ = nullptr, *dcol_ = nullptr;   // bf16 dumps / im2col
+  long long dump_rows_ = 0;
+  void ensure_train_dumps(long long rows);
   double *tstats_ = nullptr, *ldc_ = nullptr, *ld_total_ = nullptr;
   bool training_ = false;
 

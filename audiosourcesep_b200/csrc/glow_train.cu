@@ -21,8 +21,7 @@ bool trainable_name(const std::string& n) {
 
 void GlowModel::enable_training() {
   if (training_) return;
-  ASEP_CHECK(precision_ == ASEP_PREC_FP32 && prepared_, ASEP_ERR_STATE,
-             "training runs in the ASEP_PREC_FP32 mode: call asep_glow_prepare(h, ASEP_PREC_FP32) first");
+  ASEP_CHECK(prepared_, ASEP_ERR_STATE, "call asep_glow_prepare() before asep_glow_enable_training()");
   ASEP_CHECK(cfg_.learntop, ASEP_ERR_UNSUPPORTED, "the training step expects the learnable top prior (learntop)");
   CUDA_CHECK(cudaSetDevice(device_));
   CUDA_CHECK(cudaDeviceSynchronize());
@@ -48,12 +47,14 @@ void GlowModel::enable_training() {
   CUDA_CHECK(cudaMalloc(&tdc2_, (size_t)F * sizeof(float)));
   CUDA_CHECK(cudaMalloc(&tr3_, (size_t)9 * F * 64 * sizeof(float)));
   CUDA_CHECK(cudaMalloc(&ts3_, (size_t)9 * 64 * sizeof(float)));
+  CUDA_CHECK(cudaMalloc(&tdc1_, (size_t)F * sizeof(float)));
+  CUDA_CHECK(cudaMalloc(&td1_, (size_t)F * 256 * sizeof(float)));
   CUDA_CHECK(cudaMalloc(&tstats_, (size_t)(2 * 64 + 64 * 64) * sizeof(double)));
   CUDA_CHECK(cudaMalloc(&ldc_, steps_.size() * sizeof(double)));
   CUDA_CHECK(cudaMalloc(&ld_total_, sizeof(double)));
   adam_t_ = 0;
   training_ = true;
-  prepare(ASEP_PREC_FP32);          // re-reads the parameter pointers (they moved into the flat vector)
+  prepare(precision_);              // re-reads the parameter pointers (they moved into the flat vector)
   derive_on_device(nullptr);
   CUDA_CHECK(cudaDeviceSynchronize());
 }
@@ -87,9 +88,27 @@ StepTrainPtrs GlowModel::step_ptrs(int b, int k) {
 
 void GlowModel::derive_on_device(cudaStream_t s) {
   for (int b = 0; b < cfg_.L; ++b)
-    for (int k = 0; k < cfg_.K; ++k)
-      launch_derive_step(step_ptrs(b, k), (double)levels_[b].H * levels_[b].W, ldc_ + (size_t)b * cfg_.K + k, s);
+    for (int k = 0; k < cfg_.K; ++k) {
+      const StepTrainPtrs sp = step_ptrs(b, k);
+      launch_derive_step(sp, (double)levels_[b].H * levels_[b].W, ldc_ + (size_t)b * cfg_.K + k, precision_ == ASEP_PREC_FP32 ? 1 : 0, s);
+      if (precision_ == ASEP_PREC_BF16) {              // tcgen05 operands: tile images + folded biases
+        NNWeightsTC& w = step(b, k).wtc;
+        launch_build_tc_step(sp, w.fwd.img, w.bwd.img, w.fwd.k1_panels, w.fwd.n3p, w.bwd.k1_panels, w.bwd.n3p, w.bias1,
+                             w.bias2, w.const3, w.c3, s);
+      }
+    }
   launch_sum_doubles(ldc_, (int)steps_.size(), ld_total_, s);
+}
+
+void GlowModel::ensure_train_dumps(long long rows) {
+  if (rows <= dump_rows_) return;
+  CUDA_CHECK(cudaDeviceSynchronize());
+  for (__nv_bfloat16** p : {&da1_, &da2_, &dgp2_, &dgp1_, &dcol_})
+    if (*p) { cudaFree(*p); *p = nullptr; }
+  const size_t n = (size_t)rows * cfg_.n_filters;
+  for (__nv_bfloat16** p : {&da1_, &da2_, &dgp2_, &dgp1_}) CUDA_CHECK(cudaMalloc(p, n * sizeof(__nv_bfloat16)));
+  CUDA_CHECK(cudaMalloc(&dcol_, (size_t)rows * 256 * sizeof(__nv_bfloat16)));
+  dump_rows_ = rows;
 }
 
 void GlowModel::train_grads(const float* x, const float* noise, float sigma, int N, int global_batch, float* grads,
@@ -100,6 +119,8 @@ void GlowModel::train_grads(const float* x, const float* noise, float sigma, int
   const int L = cfg_.L, K = cfg_.K, F = cfg_.n_filters;
   const float gs = -1.0f / (float)global_batch;      // loss = -sum log_prob / global_batch (train_glow.py:30-31)
   ensure_work(N, true);
+  const bool tc = precision_ == ASEP_PREC_BF16;
+  if (tc) ensure_train_dumps((long long)N * levels_[0].H * levels_[0].W);
   const float* xin = x;
   if (noise != nullptr) {                              // train_noisy_glow.py:31-32: X + sigma*N(0,1) in raw data units
     launch_axpy(x, noise, sigma, work_.gB, (long long)N * cfg_.H * cfg_.W * cfg_.C, s);
@@ -129,21 +150,45 @@ void GlowModel::train_grads(const float* x, const float* noise, float sigma, int
       StepDerived& sd = step(b, k);
       const StepTrainPtrs sp = step_ptrs(b, k);
       launch_bwd_coupling(gy, work_.U[b][k], work_.R[b][k], work_.gr, work_.gu, M, lv.C, s);
-      // recompute a1, a2 from the saved step input, then gp2 (t2), gp1 (t1), gxb
-      nn_fp32_forward(sd.w32, work_.U[b][k], work_.a1, work_.a2, work_.gxb, N, lv.H, lv.W, lv.C, F, s);
-      nn_fp32_backward(sd.w32, work_.a1, work_.a2, work_.gr, work_.t1, work_.t2, work_.gxb, N, lv.H, lv.W, lv.C, F, s);
-      // ---- weight gradients of this step
       CUDA_CHECK(cudaMemsetAsync(tq2_, 0, (size_t)F * F * sizeof(float), s));
       CUDA_CHECK(cudaMemsetAsync(tdc2_, 0, (size_t)F * sizeof(float), s));
-      CUDA_CHECK(cudaMemsetAsync(tr3_, 0, (size_t)9 * F * lv.C * sizeof(float), s));
       CUDA_CHECK(cudaMemsetAsync(ts3_, 0, (size_t)9 * lv.C * sizeof(float), s));
       CUDA_CHECK(cudaMemsetAsync(tstats_, 0, (size_t)(2 * lv.C + lv.C * lv.C) * sizeof(double), s));
-      launch_wgrad_tn(work_.a1, work_.t2, tq2_, M, F, s);
-      launch_colsum(work_.t2, tdc2_, M, F, s);
-      launch_wgrad_conv3(work_.a2, work_.gr, tr3_, ts3_, N, lv.H, lv.W, lv.C, F, s);
-      launch_wgrad_conv1(work_.U[b][k], work_.t1, grads + sp.o_k1, grads + sp.o_c1, N, lv.H, lv.W, lv.C, F, gs, s);
-      launch_step_stats(work_.gu, work_.gxb, work_.U[b][k], sd.sc, tstats_, M, lv.C, s);
-      launch_finalize_step(sp, tq2_, tdc2_, tr3_, ts3_, tstats_, grads, (double)M, gs, s);
+      if (!tc) {
+        // recompute a1, a2 from the saved step input, then gp2 (t2), gp1 (t1), gxb
+        nn_fp32_forward(sd.w32, work_.U[b][k], work_.a1, work_.a2, work_.gxb, N, lv.H, lv.W, lv.C, F, s);
+        nn_fp32_backward(sd.w32, work_.a1, work_.a2, work_.gr, work_.t1, work_.t2, work_.gxb, N, lv.H, lv.W, lv.C, F, s);
+        // ---- weight gradients of this step (CUDA-core fp32)
+        CUDA_CHECK(cudaMemsetAsync(tr3_, 0, (size_t)9 * F * lv.C * sizeof(float), s));
+        launch_wgrad_tn(work_.a1, work_.t2, tq2_, M, F, s);
+        launch_colsum(work_.t2, tdc2_, M, F, s);
+        launch_wgrad_conv3(work_.a2, work_.gr, tr3_, ts3_, N, lv.H, lv.W, lv.C, F, s);
+        launch_wgrad_conv1(work_.U[b][k], work_.t1, grads + sp.o_k1, grads + sp.o_c1, N, lv.H, lv.W, lv.C, F, gs, s);
+        launch_step_stats(work_.gu, work_.gxb, work_.U[b][k], sd.sc, tstats_, M, lv.C, s);
+        launch_finalize_step(sp, tq2_, tdc2_, tr3_, ts3_, tstats_, grads, (double)M, gs, s);
+      } else {
+        // tcgen05: recompute the forward with bf16 dumps of relu(p1), relu(p2); the backward dumps dL/dp2, dL/dp1
+        const bool saved = !work_.M1.empty() && !work_.M1[b].empty();
+        uint32_t* m1 = saved ? work_.M1[b][k] : work_.tc.mask1;
+        uint32_t* m2 = saved ? work_.M2[b][k] : work_.tc.mask2;
+        nn_tc_forward(sd.wtc, work_.tc, work_.U[b][k], work_.gxb, saved ? nullptr : m1, saved ? nullptr : m2, N, lv.H,
+                      lv.W, lv.C, s, da1_, da2_);
+        nn_tc_backward(sd.wtc, work_.tc, work_.gr, m1, m2, work_.gxb, N, lv.H, lv.W, lv.C, s, dgp2_, dgp1_);
+        const int ld3 = (9 * lv.C + 63) / 64 * 64, ld1 = (9 * (lv.C / 2) + 63) / 64 * 64;
+        CUDA_CHECK(cudaMemsetAsync(tr3_, 0, (size_t)F * ld3 * sizeof(float), s));
+        CUDA_CHECK(cudaMemsetAsync(td1_, 0, (size_t)F * ld1 * sizeof(float), s));
+        CUDA_CHECK(cudaMemsetAsync(tdc1_, 0, (size_t)F * sizeof(float), s));
+        wgrad_tc(da1_, dgp2_, F, F, tq2_, F, M, s);                                   // Q2 = a1^T gp2
+        launch_colsum_bf16(dgp2_, tdc2_, M, F, s);
+        launch_colsum_bf16(dgp1_, tdc1_, M, F, s);
+        launch_im2col_gr(work_.gr, dcol_, N, lv.H, lv.W, lv.C, ld3, s);
+        wgrad_tc(da2_, dcol_, ld3, 9 * lv.C, tr3_, ld3, M, s);                         // R3t[k][tap,c]
+        launch_s3(work_.gr, ts3_, N, lv.H, lv.W, lv.C, s);
+        launch_im2col_xb(work_.U[b][k], dcol_, N, lv.H, lv.W, lv.C, ld1, s);
+        wgrad_tc(dgp1_, dcol_, ld1, 9 * (lv.C / 2), td1_, ld1, M, s);                  // D1t[f][tap,ci]
+        launch_step_stats(work_.gu, work_.gxb, work_.U[b][k], sd.sc, tstats_, M, lv.C, s);
+        launch_finalize_step_tc(sp, tq2_, tdc2_, tr3_, ld3, ts3_, td1_, ld1, tdc1_, tstats_, grads, (double)M, gs, s);
+      }
       // ---- data gradient to the previous step
       launch_bwd_pre(work_.gu, work_.gxb, other, sd.sc, M, lv.C, s);
       std::swap(gy, other);

@@ -70,6 +70,8 @@ struct TCParams {
   float* out;            // [M, n3p]
   int H, W;
   long long M;
+  __nv_bfloat16* dump1;      // optional [M, 512] bf16 copies of the stage-1 / stage-2 epilogue outputs (training:
+  __nv_bfloat16* dump2;      //   forward a1 = relu(p1), a2 = relu(p2); backward gp2 = dL/dp2, gp1 = dL/dp1)
   long long* dbg_out;        // debug: per-tile phase timestamps of CTA 0 (clock64), 8 per round
   int dbg_flags;             // debug: 1 skip MMA, 2 skip operand build, 4 skip G store, 8 skip epilogue 1/2 bodies
   int dbg_shift;             // debug: load only bytes >> dbg_shift of every weight image (timing experiments)
@@ -689,6 +691,7 @@ __global__ void __launch_bounds__(kThreadsTC2, 1) k_nn_tc2(const TCParams prm) {
             for (int cidx = 0; cidx < 32; ++cidx) f[cidx] = ((bits >> cidx) & 1u) ? __uint_as_float(v[c & 1][cidx]) : 0.f;
           }
           uint8_t* base = sA + (j >> 1) * kPanelBytes + row * 128;
+          __nv_bfloat16* dump = gemm == 0 ? prm.dump1 : prm.dump2;
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int chunk = (j & 1) * 4 + q;
@@ -698,6 +701,7 @@ __global__ void __launch_bounds__(kThreadsTC2, 1) k_nn_tc2(const TCParams prm) {
             pk.z = pack_bf16(f[8 * q + 4], f[8 * q + 5]);
             pk.w = pack_bf16(f[8 * q + 6], f[8 * q + 7]);
             *reinterpret_cast<uint4*>(base + ((chunk ^ (row & 7)) << 4)) = pk;
+            if (dump != nullptr && valid) *reinterpret_cast<uint4*>(dump + p * kF + j * 32 + q * 8) = pk;
           }
         }
         if constexpr (!kBwd) {
@@ -1055,13 +1059,15 @@ void nn_tc_release(NNWeightsTC& w) {
 }
 
 void nn_tc_forward(const NNWeightsTC& w, const NNScratchTC& sc, const float* state, float* r, uint32_t* mask1,
-                   uint32_t* mask2, int N, int H, int W, int C, cudaStream_t s) {
+                   uint32_t* mask2, int N, int H, int W, int C, cudaStream_t s, __nv_bfloat16* dump1,
+                   __nv_bfloat16* dump2) {
   const long long M = (long long)N * H * W;
   if (M == 0) return;
   TCParams prm{};
   prm.src = state; prm.src_stride = C; prm.src_off = C / 2; prm.src_ch = C / 2; prm.tap_sign = 1;
   prm.wimg = w.fwd.img; prm.k1_steps = w.fwd.k1_steps; prm.k1_panels = w.fwd.k1_panels; prm.n3p = w.fwd.n3p;
   prm.bias1 = w.bias1; prm.bias2 = w.bias2; prm.mask1 = mask1; prm.mask2 = mask2;
+  prm.dump1 = dump1; prm.dump2 = dump2;
   prm.out = sc.G; prm.H = H; prm.W = W; prm.M = M;
   g_next_flops = 2.0 * (double)M * (9.0 * (C / 2) * kF + (double)kF * kF + 9.0 * kF * C);   // conv MACs x 2, unpadded
   run_tc<false>(prm, s);
@@ -1071,7 +1077,8 @@ void nn_tc_forward(const NNWeightsTC& w, const NNScratchTC& sc, const float* sta
 }
 
 void nn_tc_backward(const NNWeightsTC& w, const NNScratchTC& sc, const float* gr, const uint32_t* mask1,
-                    const uint32_t* mask2, float* gxb, int N, int H, int W, int C, cudaStream_t s) {
+                    const uint32_t* mask2, float* gxb, int N, int H, int W, int C, cudaStream_t s,
+                    __nv_bfloat16* dump_gp2, __nv_bfloat16* dump_gp1) {
   const long long M = (long long)N * H * W;
   if (M == 0) return;
   TCParams prm{};
@@ -1079,6 +1086,7 @@ void nn_tc_backward(const NNWeightsTC& w, const NNScratchTC& sc, const float* gr
   prm.wimg = w.bwd.img; prm.k1_steps = w.bwd.k1_steps; prm.k1_panels = w.bwd.k1_panels; prm.n3p = w.bwd.n3p;
   prm.bias1 = nullptr; prm.bias2 = nullptr;
   prm.mask1 = const_cast<uint32_t*>(mask1); prm.mask2 = const_cast<uint32_t*>(mask2);
+  prm.dump1 = dump_gp2; prm.dump2 = dump_gp1;
   prm.out = sc.G; prm.H = H; prm.W = W; prm.M = M;
   g_next_flops = 2.0 * (double)M * (9.0 * (C / 2) * kF + (double)kF * kF + 9.0 * kF * C);
   run_tc<true>(prm, s);

@@ -39,11 +39,15 @@ void nn_tc_release(NNWeightsTC& w);
 
 // state [N,H,W,C] (network input = channels C/2..C) -> r [M,C] (conv3 output incl. bias).
 // mask1/mask2 (may be NULL) receive the ReLU masks needed by the backward pass.
+// dump1/dump2 (may be NULL; 8-warp kernels only): bf16 [M,512] copies of relu(p1), relu(p2) for the weight gradients.
 void nn_tc_forward(const NNWeightsTC& w, const NNScratchTC& sc, const float* state, float* r, uint32_t* mask1,
-                   uint32_t* mask2, int N, int H, int W, int C, cudaStream_t s);
+                   uint32_t* mask2, int N, int H, int W, int C, cudaStream_t s, __nv_bfloat16* dump1 = nullptr,
+                   __nv_bfloat16* dump2 = nullptr);
 // gr [M,C] -> gxb [M,C/2] using the masks written by nn_tc_forward on the same input.
+// dump_gp2/dump_gp1 (may be NULL): bf16 [M,512] copies of dL/dp2 and dL/dp1.
 void nn_tc_backward(const NNWeightsTC& w, const NNScratchTC& sc, const float* gr, const uint32_t* mask1,
-                    const uint32_t* mask2, float* gxb, int N, int H, int W, int C, cudaStream_t s);
+                    const uint32_t* mask2, float* gxb, int N, int H, int W, int C, cudaStream_t s,
+                    __nv_bfloat16* dump_gp2 = nullptr, __nv_bfloat16* dump_gp1 = nullptr);
 
 size_t nn_tc_g_floats(long long M, int C);   // capacity needed for NNScratchTC::G
 void nn_tc_set_cluster(int cluster_size);    // 1, 2 or 4 CTAs sharing each weight tile by TMA multicast

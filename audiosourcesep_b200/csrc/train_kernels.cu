@@ -204,50 +204,77 @@ __global__ void __launch_bounds__(256) k_step_stats(const float* __restrict__ gu
 }
 
 // ------------------------------------------------------------------ per-step chain rule -> parameter gradients
-__global__ void __launch_bounds__(512) k_finalize_step(const StepTrainPtrs sp, const float* __restrict__ Q2,
-                                                       const float* __restrict__ dc2, const float* __restrict__ R3,
-                                                       const float* __restrict__ S3, const double* __restrict__ stats,
-                                                       float* __restrict__ grads, double Mpix, float gs) {
-  const int F = sp.F, C = sp.C, t = threadIdx.x;
-  __shared__ double sP[256], sL[256], sU[256], sT[256], sD[256];
-  // ---- conv2 + BN1
-  for (int i = t; i < F; i += blockDim.x) {
-    const float g1 = sp.g1f[i], b1 = sp.b1f[i];
-    float dg = 0.f, db = 0.f;
-    for (int o = 0; o < F; ++o) {
-      const float q = Q2[(size_t)i * F + o], k = sp.k2[(size_t)i * F + o], d2 = dc2[o];
-      grads[sp.o_k2 + (size_t)i * F + o] = gs * (g1 * q + b1 * d2);
-      dg = fmaf(q, k, dg);
-      db = fmaf(d2, k, db);
-    }
+// conv2 + BN1: one block per input channel i, threads over output channels o (coalesced rows of Q2 / K2)
+__global__ void __launch_bounds__(512) k_fin_conv2(const StepTrainPtrs sp, const float* __restrict__ Q2,
+                                                   const float* __restrict__ dc2, float* __restrict__ grads, float gs) {
+  const int F = sp.F, i = blockIdx.x, t = threadIdx.x;
+  __shared__ float red[2][16];
+  const float g1 = sp.g1f[i], b1 = sp.b1f[i];
+  float dg = 0.f, db = 0.f;
+  for (int o = t; o < F; o += blockDim.x) {
+    const float q = Q2[(size_t)i * F + o], k = sp.k2[(size_t)i * F + o], d2 = dc2[o];
+    grads[sp.o_k2 + (size_t)i * F + o] = gs * (g1 * q + b1 * d2);
+    dg = fmaf(q, k, dg);
+    db = fmaf(d2, k, db);
+  }
+  dg = warp_sum(dg); db = warp_sum(db);
+  if ((t & 31) == 0) { red[0][t >> 5] = dg; red[1][t >> 5] = db; }
+  __syncthreads();
+  if (t == 0) {
+    float a = 0.f, b = 0.f;
+    for (int w = 0; w < (blockDim.x + 31) / 32; ++w) { a += red[0][w]; b += red[1][w]; }
     const float s = sqrtf(sp.bn1_var[i] + (float)kBnEpsD);
-    grads[sp.o_bn1_gamma + i] = gs * (dg / s - db * sp.bn1_mean[i] / s);
-    grads[sp.o_bn1_beta + i] = gs * db;
+    grads[sp.o_bn1_gamma + i] = gs * (a / s - b * sp.bn1_mean[i] / s);
+    grads[sp.o_bn1_beta + i] = gs * b;
     grads[sp.o_c2 + i] = gs * dc2[i];
   }
-  // ---- conv3 + BN2
-  for (int k = t; k < F; k += blockDim.x) {
-    const float g2 = sp.g2f[k], b2 = sp.b2f[k];
-    float dg = 0.f, db = 0.f;
-    for (int tap = 0; tap < 9; ++tap)
-      for (int c = 0; c < C; ++c) {
-        const size_t idx = ((size_t)tap * F + k) * C + c;
-        const float r = R3[idx], s3 = S3[tap * C + c], kk = sp.k3[idx];
-        grads[sp.o_k3 + idx] = gs * (g2 * r + b2 * s3);
-        dg = fmaf(r, kk, dg);
-        db = fmaf(s3, kk, db);
-      }
-    const float s = sqrtf(sp.bn2_var[k] + (float)kBnEpsD);
-    grads[sp.o_bn2_gamma + k] = gs * (dg / s - db * sp.bn2_mean[k] / s);
-    grads[sp.o_bn2_beta + k] = gs * db;
+}
+
+// conv3 + BN2 (+ conv1 copy on the tensor-core path): one block per hidden channel k, threads over (tap, c)
+__global__ void __launch_bounds__(256) k_fin_conv3(const StepTrainPtrs sp, const float* __restrict__ R3, int r3_tap_stride,
+                                                   int r3_k_stride, const float* __restrict__ S3, const float* __restrict__ D1t,
+                                                   int d1_ld, const float* __restrict__ dc1, float* __restrict__ grads, float gs) {
+  const int F = sp.F, C = sp.C, k = blockIdx.x, t = threadIdx.x;
+  __shared__ float red[2][8];
+  const float g2 = sp.g2f[k], b2 = sp.b2f[k];
+  float dg = 0.f, db = 0.f;
+  for (int n = t; n < 9 * C; n += blockDim.x) {
+    const int tap = n / C, c = n % C;
+    const size_t idx = ((size_t)tap * F + k) * C + c;
+    const float r = R3[(size_t)tap * r3_tap_stride + (size_t)k * r3_k_stride + c], s3 = S3[n], kk = sp.k3[idx];
+    grads[sp.o_k3 + idx] = gs * (g2 * r + b2 * s3);
+    dg = fmaf(r, kk, dg);
+    db = fmaf(s3, kk, db);
   }
+  dg = warp_sum(dg); db = warp_sum(db);
+  if ((t & 31) == 0) { red[0][t >> 5] = dg; red[1][t >> 5] = db; }
+  __syncthreads();
+  if (t == 0) {
+    float a = 0.f, b = 0.f;
+    for (int w = 0; w < (blockDim.x + 31) / 32; ++w) { a += red[0][w]; b += red[1][w]; }
+    const float s = sqrtf(sp.bn2_var[k] + (float)kBnEpsD);
+    grads[sp.o_bn2_gamma + k] = gs * (a / s - b * sp.bn2_mean[k] / s);
+    grads[sp.o_bn2_beta + k] = gs * b;
+  }
+  if (D1t != nullptr) {                                        // f = k: dK1[tap][ci][f] = D1t[f][tap*Ch+ci]
+    const int Ch = C / 2;
+    for (int n = t; n < 9 * Ch; n += blockDim.x) grads[sp.o_k1 + (size_t)n * F + k] = gs * D1t[(size_t)k * d1_ld + n];
+    if (t == 0) grads[sp.o_c1 + k] = gs * dc1[k];
+  }
+}
+
+// small tensors: conv3 bias, ActNorm, LU-parameterised 1x1
+__global__ void __launch_bounds__(256) k_fin_small(const StepTrainPtrs sp, const float* __restrict__ S3,
+                                                   const double* __restrict__ stats, float* __restrict__ grads, double Mpix,
+                                                   float gs) {
+  const int C = sp.C, t = threadIdx.x;
+  __shared__ double sP[256], sL[256], sU[256], sT[256], sD[256];
   if (t < C) grads[sp.o_c3 + t] = gs * S3[4 * C + t];            // centre tap is always in bounds: sum_p gr[p][c]
-  // ---- ActNorm
   if (t < C) {
     grads[sp.o_an_shift + t] = gs * (float)stats[t];
     grads[sp.o_an_ls + t] = gs * (float)(stats[C + t] + Mpix);   // + d(H*W*sum log_scale)/d log_scale per sample
   }
-  // ---- 1x1: W = P L' U',  dL' = P^T dW U'^T,  dU' = (P L')^T dW
+  // 1x1: W = P L' U',  dL' = P^T dW U'^T,  dU' = (P L')^T dW
   if (t < C * C) {
     const int i = t / C, j = t % C;
     sP[t] = sp.P[t];
@@ -263,9 +290,9 @@ __global__ void __launch_bounds__(512) k_finalize_step(const StepTrainPtrs sp, c
     sT[t] = a;
   }
   __syncthreads();
-  double dL = 0.0, dU = 0.0;
   if (t < C * C) {
     const int i = t / C, j = t % C;
+    double dL = 0.0, dU = 0.0;
     for (int k = 0; k < C; ++k) dL += sT[i * C + k] * sU[j * C + k];          // (T U'^T)[i][j]
     for (int k = 0; k < C; ++k) dU += sL[k * C + i] * sT[k * C + j];          // (L'^T T)[i][j]
     grads[sp.o_L + t] = j < i ? gs * (float)dL : 0.f;
@@ -306,7 +333,7 @@ __global__ void k_loss(const double* __restrict__ acc_ld, const double* __restri
 }
 
 // ------------------------------------------------------------------ derived constants of one step, on the device
-__global__ void __launch_bounds__(512) k_derive_step(const StepTrainPtrs sp, double HW, double* __restrict__ ldc) {
+__global__ void __launch_bounds__(512) k_derive_step(const StepTrainPtrs sp, double HW, double* __restrict__ ldc, int need_k2t) {
   const int C = sp.C, F = sp.F, t = threadIdx.x;
   __shared__ double sP[256], sL[256], sU[256], sA[256], sLi[256], sUi[256];
   if (t < C * C) {
@@ -370,10 +397,11 @@ __global__ void __launch_bounds__(512) k_derive_step(const StepTrainPtrs sp, dou
     sp.g2f[i] = (float)g2;
     sp.b2f[i] = (float)((double)sp.bn2_beta[i] - g2 * (double)sp.bn2_mean[i]);
   }
-  for (int idx = t; idx < F * F; idx += blockDim.x) {
-    const int i = idx / F, j = idx % F;
-    sp.k2t[(size_t)j * F + i] = sp.k2[idx];
-  }
+  if (need_k2t)
+    for (int idx = t; idx < F * F; idx += blockDim.x) {
+      const int i = idx / F, j = idx % F;
+      sp.k2t[(size_t)j * F + i] = sp.k2[idx];
+    }
 }
 
 __global__ void k_sum_doubles(const double* __restrict__ v, int n, double* __restrict__ out) {
@@ -395,6 +423,188 @@ __global__ void k_adamax(float* __restrict__ theta, const float* __restrict__ g,
   m[i] = mi;
   u[i] = ui;
   theta[i] -= lr_t * mi / (ui + eps);
+}
+
+
+// ------------------------------------------------------------------ tensor-core training path helpers
+// G9[q][tap*C+c] = gr[q - off(tap)][c] (0 outside the image), bf16, row stride ld (multiple of 64, zero padded)
+__global__ void __launch_bounds__(256) k_im2col_gr(const float* __restrict__ gr, __nv_bfloat16* __restrict__ G9, int H, int W,
+                                                   int C, int ld, long long M) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int groups = ld / C + 1;                       // taps 0..8 plus padding groups
+  const long long q = idx / groups;
+  const int g = (int)(idx % groups);
+  if (q >= M) return;
+  const int c0 = g * C;
+  if (c0 >= ld) return;
+  const int w = (int)(q % W), h = (int)((q / W) % H);
+  bool ok = g < 9;
+  long long src = 0;
+  if (ok) {
+    const int dy = g / 3 - 1, dx = g % 3 - 1;
+    const int hh = h - dy, ww = w - dx;
+    ok = hh >= 0 && hh < H && ww >= 0 && ww < W;
+    src = q - (long long)dy * W - dx;
+  }
+  for (int c = 0; c < C && c0 + c < ld; ++c)
+    G9[q * ld + c0 + c] = __float2bfloat16_rn(ok ? gr[src * C + c] : 0.f);
+}
+
+// X9[p][tap*Ch+ci] = state[p + off(tap)][Ch+ci] (0 outside), bf16, row stride ld
+__global__ void __launch_bounds__(256) k_im2col_xb(const float* __restrict__ state, __nv_bfloat16* __restrict__ X9, int H, int W,
+                                                   int C, int ld, long long M) {
+  const int Ch = C / 2;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int groups = ld / Ch + 1;
+  const long long p = idx / groups;
+  const int g = (int)(idx % groups);
+  if (p >= M) return;
+  const int c0 = g * Ch;
+  if (c0 >= ld) return;
+  const int w = (int)(p % W), h = (int)((p / W) % H);
+  bool ok = g < 9;
+  long long src = 0;
+  if (ok) {
+    const int dy = g / 3 - 1, dx = g % 3 - 1;
+    const int hh = h + dy, ww = w + dx;
+    ok = hh >= 0 && hh < H && ww >= 0 && ww < W;
+    src = p + (long long)dy * W + dx;
+  }
+  for (int c = 0; c < Ch && c0 + c < ld; ++c)
+    X9[p * ld + c0 + c] = __float2bfloat16_rn(ok ? state[src * C + Ch + c] : 0.f);
+}
+
+// S3[tap][c] += sum_{p: p+off(tap) in bounds} gr[p][c].  One block per image row: the row's channel sums over all
+// columns, the first column and the last column give every tap's contribution (dx = -1 drops w = 0, dx = +1 drops
+// w = W-1; dy = -1 drops the row h = 0, dy = +1 the row h = H-1).
+__global__ void __launch_bounds__(128) k_s3(const float* __restrict__ gr, float* __restrict__ S3, int H, int W, int C) {
+  const int h = blockIdx.x % H;
+  const float* row = gr + (size_t)blockIdx.x * W * C;
+  __shared__ float part[128];
+  // threads: c = t % C, w-lane = t / C
+  const int c = threadIdx.x % C, wl = threadIdx.x / C, wstep = blockDim.x / C;
+  float s = 0.f;
+  if (wl < wstep)
+    for (int w = wl; w < W; w += wstep) s += row[(size_t)w * C + c];
+  part[threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.x < C) {
+    float all = 0.f;
+    for (int g = 0; g < wstep; ++g) all += part[g * C + threadIdx.x];
+    const float first = row[threadIdx.x], last = row[(size_t)(W - 1) * C + threadIdx.x];
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+      if (h + dy < 0 || h + dy >= H) continue;
+      const float v = all - (dx == -1 ? first : 0.f) - (dx == 1 ? last : 0.f);
+      atomicAdd(S3 + tap * C + threadIdx.x, v);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(512) k_colsum_bf16(const __nv_bfloat16* __restrict__ X, float* __restrict__ out, long long M,
+                                                     int F, int rows_per_block) {
+  const int c = threadIdx.x;
+  if (c >= F) return;
+  const long long r0 = (long long)blockIdx.x * rows_per_block, r1 = min(M, r0 + rows_per_block);
+  float s = 0.f;
+  for (long long r = r0; r < r1; ++r) s += __bfloat162float(X[r * F + c]);
+  atomicAdd(out + c, s);
+}
+
+// bf16 SWIZZLE_128B tile images + folded biases of one step, rebuilt on the device after a parameter update
+// (device twin of nn_tc_prepare in nn_tc.cu; same image order and element mapping)
+__device__ __forceinline__ size_t img_off(int r, int k) { return (size_t)r * 64 + (size_t)((((k >> 3) ^ (r & 7)) << 3) + (k & 7)); }
+
+__global__ void __launch_bounds__(256) k_build_tc_images(const StepTrainPtrs sp, __nv_bfloat16* __restrict__ fwd,
+                                                         __nv_bfloat16* __restrict__ bwd, int k1p_f, int n3p_f, int k1p_b,
+                                                         int n3p_b) {
+  const int F = sp.F, C = sp.C, Ch = C / 2;
+  const int dir = blockIdx.y;                                   // 0 forward set, 1 backward set
+  const int k1p = dir == 0 ? k1p_f : k1p_b, n3p = dir == 0 ? n3p_f : n3p_b;
+  const int K1h = dir == 0 ? 9 * Ch : 9 * C, K1 = 2 * K1h, N3 = dir == 0 ? 9 * C : 9 * Ch;
+  __nv_bfloat16* dst = dir == 0 ? fwd : bwd;
+  // work item = (image, 8-wide k chunk, row); rows vary fastest so that loads over n coalesce
+  const long long n1 = (long long)2 * k1p * 8 * 256, n2 = (long long)16 * 8 * 256, n3 = (long long)8 * 8 * n3p;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n1 + n2 + n3; e += (long long)gridDim.x * blockDim.x) {
+    float v[8];
+    size_t off;
+    if (e < n1) {
+      const int img = (int)(e / (8 * 256)), ch = (int)((e / 256) % 8), r = (int)(e % 256);
+      const int half = img / k1p, kp = img % k1p, n = half * 256 + r;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int k = kp * 64 + ch * 8 + q;
+        float x = 0.f;
+        if (k < K1) {
+          const int kh = k % K1h;
+          if (dir == 0) x = sp.k1[(size_t)kh * F + n];
+          else { const int tap = kh / C, c = kh % C; x = sp.g2f[n] * sp.k3[((size_t)tap * F + n) * C + c]; }
+        }
+        v[q] = x;
+      }
+      off = (size_t)img * 256 * 64 + (size_t)r * 64 + (size_t)((ch ^ (r & 7)) << 3);
+    } else if (e < n1 + n2) {
+      const long long e2 = e - n1;
+      const int img = (int)(e2 / (8 * 256)), ch = (int)((e2 / 256) % 8), r = (int)(e2 % 256);
+      const int half = img / 8, kp = img % 8, n = half * 256 + r;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int k = kp * 64 + ch * 8 + q;
+        v[q] = dir == 0 ? sp.g1f[k] * sp.k2[(size_t)k * F + n] : sp.g1f[n] * sp.k2[(size_t)n * F + k];
+      }
+      off = (size_t)n1 * 8 + (size_t)img * 256 * 64 + (size_t)r * 64 + (size_t)((ch ^ (r & 7)) << 3);
+    } else {
+      const long long e3 = e - n1 - n2;
+      const int kp = (int)(e3 / (8LL * n3p)), ch = (int)((e3 / n3p) % 8), r = (int)(e3 % n3p);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int k = kp * 64 + ch * 8 + q;
+        float x = 0.f;
+        if (r < N3) {
+          if (dir == 0) { const int tap = r / C, c = r % C; x = sp.g2f[k] * sp.k3[((size_t)tap * F + k) * C + c]; }
+          else x = sp.k1[(size_t)r * F + k];
+        }
+        v[q] = x;
+      }
+      off = (size_t)(n1 + n2) * 8 + (size_t)kp * n3p * 64 + (size_t)r * 64 + (size_t)((ch ^ (r & 7)) << 3);
+    }
+    uint4 pk;
+    __nv_bfloat162 t2;
+    t2 = __floats2bfloat162_rn(v[0], v[1]); pk.x = *reinterpret_cast<uint32_t*>(&t2);
+    t2 = __floats2bfloat162_rn(v[2], v[3]); pk.y = *reinterpret_cast<uint32_t*>(&t2);
+    t2 = __floats2bfloat162_rn(v[4], v[5]); pk.z = *reinterpret_cast<uint32_t*>(&t2);
+    t2 = __floats2bfloat162_rn(v[6], v[7]); pk.w = *reinterpret_cast<uint32_t*>(&t2);
+    *reinterpret_cast<uint4*>(dst + off) = pk;
+  }
+}
+
+// bias1 = c1, bias2 = c2 + b1' K2, const3[tap][c] = sum_k b2'[k] K3[tap][k][c], c3
+__global__ void __launch_bounds__(512) k_build_tc_biases(const StepTrainPtrs sp, float* __restrict__ bias1, float* __restrict__ bias2,
+                                                         float* __restrict__ const3, float* __restrict__ c3) {
+  const int F = sp.F, C = sp.C, t = threadIdx.x;
+  // fp32 with four interleaved partial sums (the host twin accumulates in double; the difference is ~1e-7 relative)
+  for (int n = t; n < F; n += blockDim.x) {
+    bias1[n] = sp.c1[n];
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    for (int k = 0; k < F; k += 4) {
+      a0 = fmaf(sp.b1f[k], sp.k2[(size_t)k * F + n], a0);
+      a1 = fmaf(sp.b1f[k + 1], sp.k2[(size_t)(k + 1) * F + n], a1);
+      a2 = fmaf(sp.b1f[k + 2], sp.k2[(size_t)(k + 2) * F + n], a2);
+      a3 = fmaf(sp.b1f[k + 3], sp.k2[(size_t)(k + 3) * F + n], a3);
+    }
+    bias2[n] = sp.c2[n] + ((a0 + a1) + (a2 + a3));
+  }
+  for (int i = t; i < 9 * C; i += blockDim.x) {
+    const int tap = i / C, c = i % C;
+    float a0 = 0.f, a1 = 0.f;
+    for (int k = 0; k < F; k += 2) {
+      a0 = fmaf(sp.b2f[k], sp.k3[((size_t)tap * F + k) * C + c], a0);
+      a1 = fmaf(sp.b2f[k + 1], sp.k3[((size_t)tap * F + k + 1) * C + c], a1);
+    }
+    const3[i] = a0 + a1;
+  }
+  if (t < C) c3[t] = sp.c3[t];
 }
 
 }  // namespace
@@ -472,7 +682,24 @@ void launch_step_stats(const float* gu, const float* gxb, const float* u, const 
 void launch_finalize_step(const StepTrainPtrs& sp, const float* Q2, const float* dc2, const float* R3, const float* S3,
                           const double* stats, float* grads, double Mpix, float gs, cudaStream_t s) {
   ASEP_CHECK(sp.C * sp.C <= 256, ASEP_ERR_UNSUPPORTED, "finalize: C > 16");
-  k_finalize_step<<<1, 512, 0, s>>>(sp, Q2, dc2, R3, S3, stats, grads, Mpix, gs);
+  k_fin_conv2<<<sp.F, 512, 0, s>>>(sp, Q2, dc2, grads, gs);
+  ASEP_LAUNCH_CHECK();
+  k_fin_conv3<<<sp.F, 256, 0, s>>>(sp, R3, sp.F * sp.C, sp.C, S3, nullptr, 0, nullptr, grads, gs);
+  ASEP_LAUNCH_CHECK();
+  k_fin_small<<<1, 256, 0, s>>>(sp, S3, stats, grads, Mpix, gs);
+  ASEP_LAUNCH_CHECK();
+}
+
+void launch_finalize_step_tc(const StepTrainPtrs& sp, const float* Q2, const float* dc2, const float* R3t, int r3_ld,
+                             const float* S3, const float* D1t, int d1_ld, const float* dc1, const double* stats,
+                             float* grads, double Mpix, float gs, cudaStream_t s) {
+  ASEP_CHECK(sp.C * sp.C <= 256, ASEP_ERR_UNSUPPORTED, "finalize: C > 16");
+  // R3t[k][tap*C + c]
+  k_fin_conv2<<<sp.F, 512, 0, s>>>(sp, Q2, dc2, grads, gs);
+  ASEP_LAUNCH_CHECK();
+  k_fin_conv3<<<sp.F, 256, 0, s>>>(sp, R3t, sp.C, r3_ld, S3, D1t, d1_ld, dc1, grads, gs);
+  ASEP_LAUNCH_CHECK();
+  k_fin_small<<<1, 256, 0, s>>>(sp, S3, stats, grads, Mpix, gs);
   ASEP_LAUNCH_CHECK();
 }
 
@@ -488,9 +715,9 @@ void launch_loss(const double* acc_ld, const double* acc_prior, const double* cs
   ASEP_LAUNCH_CHECK();
 }
 
-void launch_derive_step(const StepTrainPtrs& sp, double HW, double* ldc, cudaStream_t s) {
+void launch_derive_step(const StepTrainPtrs& sp, double HW, double* ldc, int need_k2t, cudaStream_t s) {
   ASEP_CHECK(sp.C * sp.C <= 256, ASEP_ERR_UNSUPPORTED, "derive: C > 16");
-  k_derive_step<<<1, 512, 0, s>>>(sp, HW, ldc);
+  k_derive_step<<<1, 512, 0, s>>>(sp, HW, ldc, need_k2t);
   ASEP_LAUNCH_CHECK();
 }
 
@@ -502,6 +729,42 @@ void launch_sum_doubles(const double* v, int n, double* out, cudaStream_t s) {
 void launch_adamax(float* theta, const float* g, float* m, float* u, long long n, float lr_t, float b1, float b2, float eps,
                    cudaStream_t s) {
   k_adamax<<<cdiv(n, 256), 256, 0, s>>>(theta, g, m, u, n, lr_t, b1, b2, eps);
+  ASEP_LAUNCH_CHECK();
+}
+
+void launch_im2col_gr(const float* gr, __nv_bfloat16* G9, int N, int H, int W, int C, int ld, cudaStream_t s) {
+  const long long M = (long long)N * H * W;
+  const long long total = M * (ld / C + 1);
+  k_im2col_gr<<<cdiv(total, 256), 256, 0, s>>>(gr, G9, H, W, C, ld, M);
+  ASEP_LAUNCH_CHECK();
+}
+
+void launch_im2col_xb(const float* state, __nv_bfloat16* X9, int N, int H, int W, int C, int ld, cudaStream_t s) {
+  const long long M = (long long)N * H * W;
+  const long long total = M * (ld / (C / 2) + 1);
+  k_im2col_xb<<<cdiv(total, 256), 256, 0, s>>>(state, X9, H, W, C, ld, M);
+  ASEP_LAUNCH_CHECK();
+}
+
+void launch_s3(const float* gr, float* S3, int N, int H, int W, int C, cudaStream_t s) {
+  ASEP_CHECK(C <= 128 && 128 % C == 0, ASEP_ERR_UNSUPPORTED, "s3: channel count %d", C);
+  k_s3<<<N * H, 128, 0, s>>>(gr, S3, H, W, C);
+  ASEP_LAUNCH_CHECK();
+}
+
+void launch_colsum_bf16(const __nv_bfloat16* X, float* out, long long M, int F, cudaStream_t s) {
+  ASEP_CHECK(F <= 512, ASEP_ERR_UNSUPPORTED, "colsum: F > 512");
+  const int rows = M >= 148 * 2 * 64 ? 128 : 32;
+  k_colsum_bf16<<<cdiv(M, rows), 512, 0, s>>>(X, out, M, F, rows);
+  ASEP_LAUNCH_CHECK();
+}
+
+void launch_build_tc_step(const StepTrainPtrs& sp, __nv_bfloat16* fwd_img, __nv_bfloat16* bwd_img, int k1p_f, int n3p_f,
+                          int k1p_b, int n3p_b, float* bias1, float* bias2, float* const3, float* c3, cudaStream_t s) {
+  dim3 grid(296, 2);
+  k_build_tc_images<<<grid, 256, 0, s>>>(sp, fwd_img, bwd_img, k1p_f, n3p_f, k1p_b, n3p_b);
+  ASEP_LAUNCH_CHECK();
+  k_build_tc_biases<<<1, 512, 0, s>>>(sp, bias1, bias2, const3, c3);
   ASEP_LAUNCH_CHECK();
 }
 

@@ -28,11 +28,22 @@ void launch_step_stats(const float* gu, const float* gxb, const float* u, const 
                        int C, cudaStream_t s);
 void launch_finalize_step(const StepTrainPtrs& sp, const float* Q2, const float* dc2, const float* R3, const float* S3,
                           const double* stats, float* grads, double Mpix, float gs, cudaStream_t s);
+// tensor-core path: R3t[k][tap*C+c] (row stride r3_ld) and D1t[f][tap*Ch+ci] (row stride d1_ld) come from wgrad_tc
+void launch_finalize_step_tc(const StepTrainPtrs& sp, const float* Q2, const float* dc2, const float* R3t, int r3_ld,
+                             const float* S3, const float* D1t, int d1_ld, const float* dc1, const double* stats,
+                             float* grads, double Mpix, float gs, cudaStream_t s);
+void launch_im2col_gr(const float* gr, __nv_bfloat16* G9, int N, int H, int W, int C, int ld, cudaStream_t s);
+void launch_im2col_xb(const float* state, __nv_bfloat16* X9, int N, int H, int W, int C, int ld, cudaStream_t s);
+void launch_s3(const float* gr, float* S3, int N, int H, int W, int C, cudaStream_t s);
+void launch_colsum_bf16(const __nv_bfloat16* X, float* out, long long M, int F, cudaStream_t s);
+// device twin of nn_tc_prepare: tile images of both directions + folded biases of one step
+void launch_build_tc_step(const StepTrainPtrs& sp, __nv_bfloat16* fwd_img, __nv_bfloat16* bwd_img, int k1p_f, int n3p_f,
+                          int k1p_b, int n3p_b, float* bias1, float* bias2, float* const3, float* c3, cudaStream_t s);
 void launch_prior_grads(const float* z, const float* loc, const float* ls, float* gloc, float* gls, int N, int D, float gs,
                         cudaStream_t s);
 void launch_loss(const double* acc_ld, const double* acc_prior, const double* cst, double extra_const, int N,
                  double inv_batch, float* loss, cudaStream_t s);
-void launch_derive_step(const StepTrainPtrs& sp, double HW, double* ldc, cudaStream_t s);
+void launch_derive_step(const StepTrainPtrs& sp, double HW, double* ldc, int need_k2t, cudaStream_t s);
 void launch_sum_doubles(const double* v, int n, double* out, cudaStream_t s);
 void launch_adamax(float* theta, const float* g, float* m, float* u, long long n, float lr_t, float b1, float b2, float eps,
                    cudaStream_t s);

@@ -142,9 +142,11 @@ class Glow:
         return x
 
     # ---- training (train_glow.py:29-44; Keras Adamax, train_utils.py:29-30)
-    def enable_training(self) -> int:
-        """Switch to the fp32 mode, move the trainables into one flat device vector; returns its length."""
-        self.prepare(_lib.PREC_FP32)
+    def enable_training(self, precision: Optional[int] = None) -> int:
+        """Move the trainables into one flat device vector; returns its length.  ``precision``: PREC_FP32 (CUDA-core
+        exact mode) or PREC_BF16 (tcgen05 forward / backward / weight-gradient GEMMs); default: keep the current one."""
+        if precision is not None and precision != self.precision:
+            self.prepare(precision)
         _lib.check(self._lib.asep_glow_enable_training(self._h))
         n = ctypes.c_int64()
         _lib.check(self._lib.asep_glow_num_trainable(self._h, ctypes.byref(n)))

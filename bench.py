@@ -363,7 +363,8 @@ def run_ours(args):
         xt = torch.as_tensor(synthetic.mel_patches_db(tb, seed=300 + rank)).to(dev)
         # the reference's own initialisation: QR/LU 1x1, Glorot conv1/conv2, zero conv3, data-dependent ActNorm
         # (flow_builder.py:96-100); identical on every rank (same seed, rank-0-shaped minibatch)
-        tm = Glow(tcfg, init_glow_params(tcfg, seed=2, mode="faithful"), precision=_lib.PREC_FP32, device=local_rank)
+        tprec = _lib.PREC_FP32 if args.train_fp32 else _lib.PREC_BF16
+        tm = Glow(tcfg, init_glow_params(tcfg, seed=2, mode="faithful"), precision=tprec, device=local_rank)
         tm.init_actnorm(torch.as_tensor(synthetic.mel_patches_db(tb, seed=300)).to(dev))
         tm.enable_training()
         opt = dict(lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-7)
@@ -375,11 +376,14 @@ def run_ours(args):
         nst = max(2, args.steps // 3)
         t_ms, t_launches, _ = timed_loop(step_train, nst, 1)
         train = {"metric": "glow_train_samples_per_s", "value": world * tb * nst / (t_ms * 1e-3), "unit": "samples/s",
-                 "steps_per_s": nst / (t_ms * 1e-3), "per_gpu_batch": tb, "global_batch": tb * world, "dtype": "f32",
+                 "steps_per_s": nst / (t_ms * 1e-3), "per_gpu_batch": tb, "global_batch": tb * world, "dtype": "f32" if args.train_fp32 else "bf16",
                  "ms_per_step": t_ms / nst, "gpu_launches": t_launches, "allreduce_bytes_per_step": int(tm.num_trainable * 4),
                  "alg_tflops": world * tb * nst * 3 * F_GLOW * (args.K / 40.0) / (t_ms * 1e-3) / 1e12,
                  "loss": float(last[0].item()), "loss_finite": bool(torch.isfinite(last[0]).all()),
-                 "note": "CUDA-core fp32 exact mode (weight gradients not yet on tcgen05); NCCL all-reduce of the flat gradient"}
+                 "note": ("CUDA-core fp32 exact mode" if args.train_fp32 else
+                          "tcgen05 forward / data-gradient / weight-gradient GEMMs (bf16 operands, fp32 accumulate), "
+                          "fp32 master weights + Adamax, tile images rebuilt on the device every step")
+                         + "; NCCL all-reduce of the flat gradient vector"}
         del tm
 
     if rank != 0:
@@ -457,6 +461,7 @@ def main():
     ap.add_argument("--ncsn-segments", type=int, default=30, help="segments per GPU of the NCSN-BASIS legs (0 = skip)")
     ap.add_argument("--ncsn-T", type=int, default=2)
     ap.add_argument("--train-batch", type=int, default=32, help="per-GPU batch of the Glow train-step leg (0 = skip)")
+    ap.add_argument("--train-fp32", action="store_true", help="train leg in the CUDA-core fp32 exact mode")
     ap.add_argument("--cpu-sample", type=int, default=4, help="patches of the CPU baseline sample (0 = skip)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
