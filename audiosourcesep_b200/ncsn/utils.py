@@ -55,3 +55,37 @@ def get_uncompiled_model_v2(args, sigmas, name="ScoreNetworkv2", params=None, se
     if params is None:
         params = init_ncsn_params(cfg, seed=0 if seed is None else seed, mode="perturbed" if seed is not None else "faithful")
     return ScoreModel(cfg, params, sigmas=np.asarray(sigmas, dtype=np.float32), name=name)
+
+
+def anneal_langevin_dynamics(x_mod, data_shape, model, n_samples, sigmas, n_steps_each=100, step_lr=2e-5,
+                             return_arr=False, verbose=False, noise=None, seed=0):
+    """Unconditional annealed Langevin sampler (reference: ncsn/utils.py:17-38):
+    ``x <- x + step * score(x, i) + sqrt(2 step) * N(0,1)``, ``step = step_lr * (sigma_i / sigma_L)^2``.
+
+    This is the single-source, lambda = 0 case of the fused BASIS update: the same
+    kernel runs it with a dummy second source.  ``noise`` ([L, n_steps_each, n, H, W, C] standard normals) injects
+    the draws for parity runs; otherwise Philox noise keyed by (seed, step, element) is generated in the kernel."""
+    import torch
+    from .. import ops
+    x = torch.as_tensor(np.asarray(x_mod) if not torch.is_tensor(x_mod) else x_mod, dtype=torch.float32).cuda().contiguous().clone()
+    dummy = torch.zeros_like(x)
+    zeros = torch.zeros_like(x)
+    arr = [x.cpu().numpy().copy()] if return_arr else None
+    step_no = 0
+    for i, sigma in enumerate(sigmas):
+        if verbose:
+            print("Sigma = {} ({} / {})".format(sigma, i + 1, len(sigmas)))
+        labels = torch.full((int(n_samples),), i, dtype=torch.int32, device=x.device)
+        ratio = np.float32(np.float32(sigma) / np.float32(sigmas[-1]))
+        step_size = np.float32(np.float64(step_lr) * np.float64(np.float32(ratio * ratio)))
+        noise_scale = np.float32(np.sqrt(np.float32(step_size * np.float32(2.0))))
+        for s in range(int(n_steps_each)):
+            grad = model([x, labels], training=True)
+            n1 = None if noise is None else torch.as_tensor(noise[i][s], dtype=torch.float32)
+            ops.langevin_step(x, dummy, grad, zeros, zeros, float(step_size), 0.0, float(noise_scale), n1=n1,
+                              n2=None if n1 is None else torch.zeros_like(x), seed=seed, step=step_no)
+            dummy.zero_()
+            step_no += 1
+        if return_arr:
+            arr.append(x.cpu().numpy().copy())
+    return np.stack(arr, axis=0) if return_arr else x.cpu().numpy()

@@ -103,3 +103,30 @@ def test_basis_ncsn_inner_loop_vs_oracle(version, sigma_idx, gate):
     print(f"[{version}, sigma_idx={sigma_idx}] worst per-step state relative error = {worst:.3e}")
     assert worst <= gate, worst
     assert nan.item() == 0
+
+
+def test_anneal_langevin_dynamics_matches_oracle():
+    """ncsn/utils.py:17-38 with injected noise: the unconditional sampler is the lambda = 0 case of the fused update."""
+    from audiosourcesep_b200.ncsn.utils import anneal_langevin_dynamics
+    cfg = _cfg("v1")
+    params = init_ncsn_params(cfg, seed=21, mode="perturbed")
+    model, sig = _model(cfg, params)
+    oracle = NCSNOracle(cfg, params, sigmas=sig, dtype=torch.float32)
+    sig_used = sig[-2:]
+    rng = np.random.default_rng(5)
+    x0 = rng.uniform(0, 1, (2, 96, 64, 1)).astype(np.float32)
+    noise = rng.standard_normal((2, 2, 2, 96, 64, 1)).astype(np.float32)
+
+    class Shifted:                       # the sampler labels levels 0..len(sigmas)-1; test the last two levels of the schedule
+        def __init__(self, f, off):
+            self.f, self.off = f, off
+
+        def __call__(self, inputs, training=True):
+            return self.f([inputs[0], inputs[1] + self.off], training=training)
+
+    got = anneal_langevin_dynamics(x0, [96, 64, 1], Shifted(model, 8), 2, sig_used, n_steps_each=2, step_lr=2e-5, noise=noise)
+    want = bo.anneal_langevin_dynamics(x0.copy(), lambda x, i: oracle.score(x, np.full((2,), i + 8)).numpy().astype(np.float32),
+                                       sig_used, 2, 2e-5, lambda i, s: noise[i][s])
+    rel = np.linalg.norm(got - want) / np.linalg.norm(want)
+    print(f"annealed Langevin sampler relative state error = {rel:.3e}")
+    assert rel <= 1e-3, rel
