@@ -745,7 +745,445 @@ __global__ void __launch_bounds__(kThreadsTC2, 1) k_nn_tc2(const TCParams prm) {
   }
 }
 
+// im2col of up to five taps [t_begin, t_end) of one operand row, split in a LOAD half (global -> registers, issued
+// while the worker is idle) and a STORE half (split-bf16 [hi | lo] -> swizzled shared memory, once the panels are free)
+template <int SC>
+__device__ __forceinline__ void a1_load(float (&v)[20], const float* __restrict__ src, long long p, bool valid, int h, int w,
+                                        int H, int W, int stride, int off, int sign, int t_begin, int t_end) {
+  static_assert(SC <= 4, "register prefetch is sized for <= 4 source channels");
+#pragma unroll
+  for (int tt = 0; tt < 5; ++tt) {
+    const int tap = t_begin + tt;
+    const int dy = (tap / 3 - 1) * sign, dx = (tap % 3 - 1) * sign;
+    const int hh = h + dy, ww = w + dx;
+    const bool ok = valid && tap < t_end && hh >= 0 && hh < H && ww >= 0 && ww < W;
+    const float* s = src + (p + (long long)dy * W + dx) * stride + off;
+    if constexpr (SC == 4) {
+      const float4 t = ok ? __ldg(reinterpret_cast<const float4*>(s)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      v[4 * tt] = t.x; v[4 * tt + 1] = t.y; v[4 * tt + 2] = t.z; v[4 * tt + 3] = t.w;
+    } else if constexpr (SC == 2) {
+      const float2 t = ok ? __ldg(reinterpret_cast<const float2*>(s)) : make_float2(0.f, 0.f);
+      v[2 * tt] = t.x; v[2 * tt + 1] = t.y;
+    } else {
+      v[tt] = ok ? __ldg(s) : 0.f;
+    }
+  }
+}
+template <int SC>
+__device__ __forceinline__ void a1_store(uint8_t* sA, int row, const float (&v)[20], int t_begin, int t_end) {
+  constexpr int K1h = 9 * SC;
+#pragma unroll
+  for (int tt = 0; tt < 5; ++tt) {
+    if (t_begin + tt >= t_end) break;
+    const int k0 = (t_begin + tt) * SC;
+    float hi[SC], lo[SC];
+#pragma unroll
+    for (int ci = 0; ci < SC; ++ci) {
+      hi[ci] = v[tt * SC + ci];
+      lo[ci] = hi[ci] - __bfloat162float(__float2bfloat16_rn(hi[ci]));
+    }
+    if constexpr (SC == 1) {
+      *reinterpret_cast<__nv_bfloat16*>(sA + a_offset(row, k0)) = __float2bfloat16_rn(hi[0]);
+      *reinterpret_cast<__nv_bfloat16*>(sA + a_offset(row, K1h + k0)) = __float2bfloat16_rn(lo[0]);
+    } else if constexpr (SC == 2) {
+      *reinterpret_cast<uint32_t*>(sA + a_offset(row, k0)) = pack_bf16(hi[0], hi[1]);
+      *reinterpret_cast<uint32_t*>(sA + a_offset(row, K1h + k0)) = pack_bf16(lo[0], lo[1]);
+    } else {
+      *reinterpret_cast<uint2*>(sA + a_offset(row, k0)) = make_uint2(pack_bf16(hi[0], hi[1]), pack_bf16(hi[2], hi[3]));
+      *reinterpret_cast<uint2*>(sA + a_offset(row, K1h + k0)) = make_uint2(pack_bf16(lo[0], lo[1]), pack_bf16(lo[2], lo[3]));
+    }
+  }
+}
+
+// ===================================================================================================
+// K-pipelined kernel (default): the three GEMMs of a tile and their epilogues overlap panel by panel.
+//
+// Measured on B200 (tools/tc_timing.py): a tcgen05.mma with M = 128 costs max(~100, N/2) cycles, so N = 256
+// instructions are the only efficient shape and the two 256-column accumulators H0 / H1 fill all of TMEM; an
+// N-quarter variant with relu(p1) kept in TMEM ("TS" form, N = 128) was bit-exact but no faster.  This kernel keeps
+// k_nn_tc2's layout (8 x 16 KB operand panels that hold a1, then h1, then h2 in place; 3 x 32 KB weight ring; the
+// same tile-image stream) and removes the serialisation by tracking readiness per 64-column K panel:
+//
+//   * all 8 worker warps convert the SAME accumulator half, one 64-column panel at a time (32 columns per warp),
+//     and signal panel_ready[p];
+//   * S2(H0) starts when E1 has drained H0 (panels 0-3) and consumes panels 4-7 as E1 produces them;
+//   * E2(H0) runs under S2(H1), writing h2 panel p over h1 panel p as soon as S2(H1) has consumed it (cons[p]);
+//   * S3 (accumulator over the drained H0 columns) consumes h2 panels 0-3 under E2(H1) and 4-7 as they arrive;
+//   * after S3 the workers first build the next tile's a1 so that S1(H1) of the next tile runs under E3.
+constexpr int kBarBytes4 = 256;
+constexpr int kSmemBytes4 = kARegionBytes + kStages * kStageBytes + kBiasBytes + kBarBytes4;   // 231,680 B
+
+template <bool kBwd, bool kSaveMask>
+__global__ void __launch_bounds__(kThreadsTC2, 1) k_nn_tc4(const TCParams prm) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();
+  constexpr int S = kStages;
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + kARegionBytes;
+  float* sBias = reinterpret_cast<float*>(smem + kARegionBytes + S * kStageBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kARegionBytes + S * kStageBytes + kBiasBytes);
+  // bars: [0,S) full  [S,2S) empty  [2S] a1_ready  [2S+1,2S+3) accfull H0/H1  [2S+3] accfree_H0  [2S+4,2S+12) panel_ready
+  //       [2S+12,2S+16) cons  [2S+16] tmem slot
+  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[S]);
+  const uint32_t a1_ready = smem_u32(&bars[2 * S]), accfull0 = smem_u32(&bars[2 * S + 1]);
+  const uint32_t accfree_h0 = smem_u32(&bars[2 * S + 3]), panel0 = smem_u32(&bars[2 * S + 4]);
+  const uint32_t cons0 = smem_u32(&bars[2 * S + 12]);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(&bars[2 * S + 16]);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < S; ++i) {
+      mbar_init(full0 + 8 * i, 1);
+      mbar_init(empty0 + 8 * i, 1);
+    }
+    mbar_init(a1_ready, 8);               // one arrival per worker warp
+    mbar_init(accfull0, 1);
+    mbar_init(accfull0 + 8, 1);
+    mbar_init(accfree_h0, 8);
+    for (int i = 0; i < 8; ++i) mbar_init(panel0 + 8 * i, 8);
+    for (int i = 0; i < 4; ++i) mbar_init(cons0 + 8 * i, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t img3_bytes = (uint32_t)prm.n3p * 128u;
+
+  if (warp == 0) {
+    // ===================== producer: weight images in the order the MMA thread consumes them =====================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      const uint8_t* w1 = reinterpret_cast<const uint8_t*>(prm.wimg);
+      const uint8_t* w2 = w1 + (size_t)2 * prm.k1_panels * kStageBytes;
+      const uint8_t* w3 = w2 + (size_t)2 * kNumPanels * kStageBytes;
+      auto push = [&](const uint8_t* src, uint32_t bytes) {
+        bytes = (bytes >> prm.dbg_shift) & ~15u;      // dbg_shift > 0: timing experiments only (wrong results)
+        mbar_wait(empty0 + 8 * stage, phase ^ 1);
+        mbar_expect_tx(full0 + 8 * stage, bytes);
+        bulk_g2s(smem_u32(sB + stage * kStageBytes), src, bytes, full0 + 8 * stage);
+        if (++stage == (uint32_t)S) { stage = 0; phase ^= 1; }
+      };
+      for (int round = 0; round < prm.num_rounds; ++round) {
+        for (int half = 1; half >= 0; --half)                       // S1(H1) is issued before S1(H0)
+          for (int kp = 0; kp < prm.k1_panels; ++kp) push(w1 + (size_t)(half * prm.k1_panels + kp) * kStageBytes, kStageBytes);
+        for (int i = 0; i < 2 * kNumPanels; ++i) push(w2 + (size_t)i * kStageBytes, kStageBytes);
+        for (int kp = 0; kp < kNumPanels; ++kp) push(w3 + (size_t)kp * img3_bytes, img3_bytes);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      const uint32_t a_base = smem_u32(sA);
+      constexpr uint32_t idesc256 = make_idesc(256);
+      const uint32_t idesc3 = make_idesc(prm.n3p);
+      // one K panel (<= 4 MMAs of K = 16): A = operand panel kp, B = the ring slot that holds the next image
+      auto kblock = [&](uint32_t d_tmem, int kp, int steps, uint32_t idesc, bool first) {
+        mbar_wait(full0 + 8 * stage, phase);
+        tc_fence_after();
+        const uint64_t da = make_desc(a_base + kp * kPanelBytes);
+        const uint64_t db = make_desc(smem_u32(sB + stage * kStageBytes));
+        for (int k = 0; k < steps; ++k) umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, !(first && k == 0));
+        umma_commit(empty0 + 8 * stage);
+        if (++stage == (uint32_t)S) { stage = 0; phase ^= 1; }
+      };
+      const uint32_t h0 = tmem_base, h1 = tmem_base + 256u;
+      for (int round = 0; round < prm.num_rounds; ++round) {
+        mbar_wait(a1_ready, round & 1);
+        tc_fence_after();
+        // ---- stage 1 (conv3x3 / conv3^T on the split-bf16 im2col rows): H1 first, H0 once E3 of the previous tile has drained it
+        for (int kp = 0; kp < prm.k1_panels; ++kp) kblock(h1, kp, min(4, prm.k1_steps - 4 * kp), idesc256, kp == 0);
+        umma_commit(accfull0 + 8);
+        if (round > 0) {
+          mbar_wait(accfree_h0, (round - 1) & 1);
+          tc_fence_after();
+        }
+        for (int kp = 0; kp < prm.k1_panels; ++kp) kblock(h0, kp, min(4, prm.k1_steps - 4 * kp), idesc256, kp == 0);
+        umma_commit(accfull0);
+        // ---- stage 2 (conv1x1), half 0: needs H0 drained (h1 panels 0-3 written), then follows E1 panel by panel
+        for (int p = 0; p < 4; ++p) mbar_wait(panel0 + 8 * p, 0);
+        tc_fence_after();
+        for (int kp = 0; kp < kNumPanels; ++kp) {
+          if (kp >= 4) {
+            mbar_wait(panel0 + 8 * kp, 0);
+            tc_fence_after();
+          }
+          kblock(h0, kp, 4, idesc256, kp == 0);
+        }
+        umma_commit(accfull0);
+        // ---- stage 2, half 1: tells E2(H0) when each of the first four h1 panels may be overwritten by h2
+        for (int kp = 0; kp < kNumPanels; ++kp) {
+          kblock(h1, kp, 4, idesc256, kp == 0);
+          if (kp < 4) umma_commit(cons0 + 8 * kp);
+        }
+        umma_commit(accfull0 + 8);
+        // ---- stage 3 (small-N GEMM on h2), accumulator over the drained H0 columns
+        for (int p = 0; p < 4; ++p) mbar_wait(panel0 + 8 * p, 1);
+        tc_fence_after();
+        for (int kp = 0; kp < kNumPanels; ++kp) {
+          if (kp >= 4) {
+            mbar_wait(panel0 + 8 * kp, 1);
+            tc_fence_after();
+          }
+          kblock(h0, kp, 4, idesc3, kp == 0);
+        }
+        umma_commit(accfull0);
+      }
+    }
+  } else {
+    // ===================== workers: operand build + epilogues (8 warps) =====================
+    const int lq = warp & 3;                            // TMEM lane quarter this warp may access
+    const int ch = (warp - 2) >> 2;                     // which 32 of the 64 columns of every panel
+    const int row = lq * 32 + lane;
+    const int wtid = threadIdx.x - 64;                  // 0..255
+    const uint32_t t_lane = tmem_base + ((uint32_t)(lq * 32) << 16);
+    uint8_t* stg = sA + kARegionBytes - ((kTileM * prm.n3p * 4 + 1023) & ~1023);   // G staging rows (host checks the fit)
+    const int k1_pad = prm.k1_steps * 16;
+    float4 b1v = make_float4(0.f, 0.f, 0.f, 0.f), b2v = b1v;
+    if constexpr (!kBwd) {
+      if (wtid < kF / 4) {
+        b1v = __ldg(reinterpret_cast<const float4*>(prm.bias1) + wtid);
+        b2v = __ldg(reinterpret_cast<const float4*>(prm.bias2) + wtid);
+        reinterpret_cast<float4*>(sBias)[wtid] = b1v;
+      }
+    }
+    auto arrive_warp = [&](uint32_t bar) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar);
+    };
+    // stage-1 operand of tile `round`: two threads per row, taps 0-4 and 5-8 (+ zero padding of the K tail).
+    // M < 2^31 (checked on the host), so the pixel coordinates come from 32-bit divisions.
+    const int tb = ch == 0 ? 0 : 5, te = ch == 0 ? 5 : 9;
+    auto row_coords = [&](int round, long long& p, bool& valid, int& h, int& w) {
+      const long long tile = (long long)round * prm.tiles_per_cta_round + blockIdx.x;
+      p = tile * kTileM + row;
+      valid = p < prm.M;
+      w = 0; h = 0;
+      if (valid) {
+        const uint32_t pu = (uint32_t)p, q = pu / (uint32_t)prm.W;
+        w = (int)(pu - q * (uint32_t)prm.W);
+        h = (int)(q % (uint32_t)prm.H);
+      }
+    };
+    auto finish_a1 = [&]() {
+      if (ch == 1)
+        for (int k = 2 * 9 * prm.src_ch; k < k1_pad; k += 2)      // both bounds are even
+          *reinterpret_cast<uint32_t*>(sA + a_offset(row, k)) = 0u;
+      fence_proxy_async();
+      if (wtid == 0) bulk_wait_read_all();          // the previous tile's G rows have left the staging area (E1 will overwrite it)
+      arrive_warp(a1_ready);
+    };
+    auto build = [&](int round) {
+      long long p; bool valid; int h, w;
+      row_coords(round, p, valid, h, w);
+      switch (prm.src_ch) {
+        case 1: build_a1_taps<1>(sA, row, prm.src, p, valid, h, w, prm.H, prm.W, prm.src_stride, prm.src_off, prm.tap_sign, tb, te); break;
+        case 2: build_a1_taps<2>(sA, row, prm.src, p, valid, h, w, prm.H, prm.W, prm.src_stride, prm.src_off, prm.tap_sign, tb, te); break;
+        case 4: build_a1_taps<4>(sA, row, prm.src, p, valid, h, w, prm.H, prm.W, prm.src_stride, prm.src_off, prm.tap_sign, tb, te); break;
+        case 8: build_a1_taps<8>(sA, row, prm.src, p, valid, h, w, prm.H, prm.W, prm.src_stride, prm.src_off, prm.tap_sign, tb, te); break;
+        default: build_a1_taps<16>(sA, row, prm.src, p, valid, h, w, prm.H, prm.W, prm.src_stride, prm.src_off, prm.tap_sign, tb, te); break;
+      }
+      finish_a1();
+    };
+    // <= 4 source channels: the next tile's taps are fetched into registers while this tile's stage 2 is running
+    const bool prefetch_regs = prm.src_ch <= 4;
+    float pre[20];
+    auto prefetch_a1 = [&](int round) {
+      long long p; bool valid; int h, w;
+      row_coords(round, p, valid, h, w);
+      switch (prm.src_ch) {
+        case 1: a1_load<1>(pre, prm.src, p, valid, h, w, prm.H, prm.W, prm.src_stride, prm.src_off, prm.tap_sign, tb, te); break;
+        case 2: a1_load<2>(pre, prm.src, p, valid, h, w, prm.H, prm.W, prm.src_stride, prm.src_off, prm.tap_sign, tb, te); break;
+        default: a1_load<4>(pre, prm.src, p, valid, h, w, prm.H, prm.W, prm.src_stride, prm.src_off, prm.tap_sign, tb, te); break;
+      }
+    };
+    auto store_a1 = [&]() {
+      switch (prm.src_ch) {
+        case 1: a1_store<1>(sA, row, pre, tb, te); break;
+        case 2: a1_store<2>(sA, row, pre, tb, te); break;
+        default: a1_store<4>(sA, row, pre, tb, te); break;
+      }
+      finish_a1();
+    };
+    build(0);
+    for (int round = 0; round < prm.num_rounds; ++round) {
+      const long long tile = (long long)round * prm.tiles_per_cta_round + blockIdx.x;
+      const long long p = tile * kTileM + row;
+      const bool valid = p < prm.M;
+      const bool stamp = prm.dbg_out != nullptr && blockIdx.x == 0 && wtid == 0;
+      long long* ts = prm.dbg_out + (long long)round * 8;
+      if (stamp) ts[0] = clock64();
+      if (ch == 0) {      // pull the tile after next towards L2
+        const long long pn = p + 2ll * prm.tiles_per_cta_round * kTileM;
+        if (pn < prm.M) asm volatile("prefetch.global.L2 [%0];" ::"l"(prm.src + pn * prm.src_stride));
+      }
+      // ---- epilogues of the two hidden layers: TMEM -> (bias, relu | mask) -> bf16 -> swizzled smem, panel by panel
+#pragma unroll
+      for (int gemm = 0; gemm < 2; ++gemm) {
+        uint32_t* mask = kBwd ? (gemm == 0 ? prm.mask2 : prm.mask1) : (gemm == 0 ? prm.mask1 : prm.mask2);
+        __nv_bfloat16* dump = gemm == 0 ? prm.dump1 : prm.dump2;
+        // mask words of a row are stored per worker: word ch*8 + panel covers columns [64*panel + 32*ch, +32), so that
+        // each thread reads / writes its 8 words as two 16-byte accesses (the layout is private to this kernel pair)
+        uint32_t mk[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+        if constexpr (kBwd) {
+          if (valid) {
+            const uint4 m0 = __ldg(reinterpret_cast<const uint4*>(mask + p * (kF / 32) + ch * 8));
+            const uint4 m1 = __ldg(reinterpret_cast<const uint4*>(mask + p * (kF / 32) + ch * 8) + 1);
+            mk[0] = m0.x; mk[1] = m0.y; mk[2] = m0.z; mk[3] = m0.w; mk[4] = m1.x; mk[5] = m1.y; mk[6] = m1.z; mk[7] = m1.w;
+          }
+        }
+        if constexpr (!kBwd) named_bar_sync(1, kWorkers2);      // bias vector of this layer is in sBias
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          // accumulator uses per tile: H0 = S1, S2, S3 (3 per tile); H1 = S1, S2 (2 per tile)
+          const uint32_t par = hh == 0 ? (uint32_t)(round + gemm) & 1u : (uint32_t)gemm;
+          mbar_wait(accfull0 + 8 * hh, par);
+          tc_fence_after();
+          uint32_t v[2][32];
+          tmem_ld32(t_lane + (uint32_t)(hh * 256 + ch * 32), v[0]);
+#pragma unroll
+          for (int pp = 0; pp < 4; ++pp) {
+            const int pn = 4 * hh + pp;                          // K panel of the next layer's operand
+            const int j = 2 * pn + ch;                           // 32-column chunk index
+            tmem_ld_wait();
+            if (pp + 1 < 4) tmem_ld32(t_lane + (uint32_t)(hh * 256 + (pp + 1) * 64 + ch * 32), v[(pp + 1) & 1]);
+            uint32_t pk[16];
+            if constexpr (!kBwd) {
+              uint32_t bits = 0;
+#pragma unroll
+              for (int c4 = 0; c4 < 8; ++c4) {
+                const float4 b4 = reinterpret_cast<const float4*>(sBias + j * 32)[c4];
+                const float f0 = __uint_as_float(v[pp & 1][4 * c4 + 0]) + b4.x, f1 = __uint_as_float(v[pp & 1][4 * c4 + 1]) + b4.y;
+                const float f2 = __uint_as_float(v[pp & 1][4 * c4 + 2]) + b4.z, f3 = __uint_as_float(v[pp & 1][4 * c4 + 3]) + b4.w;
+                if constexpr (kSaveMask) {
+                  bits |= (f0 > 0.f ? 1u : 0u) << (4 * c4) | (f1 > 0.f ? 1u : 0u) << (4 * c4 + 1) |
+                          (f2 > 0.f ? 1u : 0u) << (4 * c4 + 2) | (f3 > 0.f ? 1u : 0u) << (4 * c4 + 3);
+                }
+                // relu after rounding == rounding after relu (round-to-nearest keeps sign and zero)
+                const __nv_bfloat162 z2 = __floats2bfloat162_rn(0.f, 0.f);
+                __nv_bfloat162 a = __hmax2(__floats2bfloat162_rn(f0, f1), z2), b = __hmax2(__floats2bfloat162_rn(f2, f3), z2);
+                pk[2 * c4] = *reinterpret_cast<uint32_t*>(&a);
+                pk[2 * c4 + 1] = *reinterpret_cast<uint32_t*>(&b);
+              }
+              if constexpr (kSaveMask) mk[pn] = bits;
+            } else {
+              const uint32_t bits = mk[pn];
+#pragma unroll
+              for (int c2 = 0; c2 < 16; ++c2) {
+                const float f0 = ((bits >> (2 * c2)) & 1u) ? __uint_as_float(v[pp & 1][2 * c2]) : 0.f;
+                const float f1 = ((bits >> (2 * c2 + 1)) & 1u) ? __uint_as_float(v[pp & 1][2 * c2 + 1]) : 0.f;
+                pk[c2] = pack_bf16(f0, f1);
+              }
+            }
+            if (dump != nullptr && valid) {
+#pragma unroll
+              for (int c4 = 0; c4 < 4; ++c4)
+                *reinterpret_cast<uint4*>(dump + p * kF + j * 32 + c4 * 8) = make_uint4(pk[4 * c4], pk[4 * c4 + 1], pk[4 * c4 + 2], pk[4 * c4 + 3]);
+            }
+            // h2 panel pn replaces h1 panel pn in place: S2(H1) must have consumed it (h2 panels 4-7: S2 is complete)
+            if (gemm == 1 && hh == 0) mbar_wait(cons0 + 8 * pn, round & 1);
+            uint8_t* base = sA + pn * kPanelBytes + row * 128;
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4)
+              *reinterpret_cast<uint4*>(base + (((ch * 4 + c4) ^ (row & 7)) << 4)) =
+                  make_uint4(pk[4 * c4], pk[4 * c4 + 1], pk[4 * c4 + 2], pk[4 * c4 + 3]);
+            // the proxy fence is the expensive part of a hand-over: H0 panels are only needed all together, H1 panels
+            // (which the next GEMM follows panel by panel) are handed over in pairs
+            if (hh == 0 ? pp == 3 : (pp & 1)) {
+              fence_proxy_async();
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) {
+                if (hh == 0) {
+#pragma unroll
+                  for (int q = 0; q < 4; ++q) mbar_arrive(panel0 + 8 * q);
+                } else {
+                  mbar_arrive(panel0 + 8 * (pn - 1));
+                  mbar_arrive(panel0 + 8 * pn);
+                }
+              }
+            }
+          }
+          // idle until S2(H1) completes: fetch the next tile's taps
+          if (gemm == 1 && hh == 0 && prefetch_regs && round + 1 < prm.num_rounds) prefetch_a1(round + 1);
+        }
+        if constexpr (kSaveMask) {
+          if (valid) {
+            uint4* mo = reinterpret_cast<uint4*>(mask + p * (kF / 32) + ch * 8);
+            mo[0] = make_uint4(mk[0], mk[1], mk[2], mk[3]);
+            mo[1] = make_uint4(mk[4], mk[5], mk[6], mk[7]);
+          }
+        }
+        if constexpr (!kBwd) {                                   // swap in the other layer's bias once everyone is done
+          named_bar_sync(1, kWorkers2);
+          if (wtid < kF / 4) reinterpret_cast<float4*>(sBias)[wtid] = gemm == 0 ? b2v : b1v;
+        }
+        if (stamp) ts[1 + gemm] = clock64();
+      }
+
+      // ---- all MMAs of this tile are complete: the operand panels are free -> build the next tile's rows first,
+      //      so that its stage-1 MMAs (H1 half) run while this tile's small-N accumulator is drained
+      mbar_wait(accfull0, (uint32_t)(round + 2) & 1u);
+      tc_fence_after();
+      if (stamp) ts[3] = clock64();
+      // drain the small-N accumulator: TMEM -> registers -> fp32 staging rows in the (now free) tail of the operand
+      // panels -> ONE TMA bulk store of the tile's contiguous G rows.  (Direct st.global of 16 B per row costs one
+      // LSU wavefront each: ~2000 cycles per tile.)  Two 16-column chunks per wait; the two warps of a lane quarter
+      // alternate chunks.
+      {
+        // staging / global layout of one tile of G: [n3p/4 float4 columns][128 rows][4 floats] (private to this kernel and
+        // the gather kernels): consecutive lanes write consecutive 16-byte words, free of bank conflicts
+        uint8_t* stg_row = stg + (size_t)row * 16;
+        for (int j = ch; j < prm.n3p / 16; j += 4) {
+          uint32_t v[2][16];
+          const bool two = j + 2 < prm.n3p / 16;
+          tmem_ld16(t_lane + (uint32_t)(j * 16), v[0]);
+          if (two) tmem_ld16(t_lane + (uint32_t)((j + 2) * 16), v[1]);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            if (i == 1 && !two) break;
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4)
+              *reinterpret_cast<uint4*>(stg_row + (size_t)((j + 2 * i) * 4 + c4) * (kTileM * 16)) =
+                  make_uint4(v[i][4 * c4], v[i][4 * c4 + 1], v[i][4 * c4 + 2], v[i][4 * c4 + 3]);
+          }
+        }
+        tc_fence_before();
+        arrive_warp(accfree_h0);                    // H0 is drained: S1(H0) of the next tile may overwrite it
+        fence_proxy_async();
+        named_bar_sync(2, kWorkers2);
+        if (wtid == 0) {
+          if (tile * kTileM < prm.M)          // whole tiles: the G buffer is sized for M rounded up to 128 rows
+            bulk_s2g(prm.out + tile * kTileM * prm.n3p, smem_u32(stg), (uint32_t)(kTileM * prm.n3p * 4));
+        }
+      }
+      if (stamp) ts[4] = clock64();
+      if (round + 1 < prm.num_rounds) {
+        if (prefetch_regs) store_a1(); else build(round + 1);
+      }
+      if (stamp) ts[5] = clock64();
+    }
+    if (wtid == 0) bulk_wait_all();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
+}
+
 // r[p][c] = c3[c] + sum_{tap in bounds} (G[p+off(tap)][tap*C+c] + const3[tap][c])
+// element (pixel pp, column col) of G: row-major [M][n3p] (k_nn_tc, k_nn_tc2) or, per 128-pixel tile,
+// [n3p/4 float4 columns][128 rows][4 floats] (k_nn_tc4)
+template <bool kTiled>
+__device__ __forceinline__ long long g_index(long long pp, int col, int n3p) {
+  if constexpr (!kTiled) return pp * n3p + col;
+  else return (pp >> 7) * (128ll * n3p) + (long long)(col >> 2) * 512 + (pp & 127) * 4 + (col & 3);
+}
+
+template <bool kTiled>
 __global__ void __launch_bounds__(256) k_gather_fwd(const float* __restrict__ G, const float* __restrict__ const3,
                                                     const float* __restrict__ c3, float* __restrict__ r, int H, int W,
                                                     int C, int n3p, long long total) {
@@ -760,12 +1198,13 @@ __global__ void __launch_bounds__(256) k_gather_fwd(const float* __restrict__ G,
     const int dy = tap / 3 - 1, dx = tap % 3 - 1;
     const int hh = h + dy, ww = w + dx;
     if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
-    acc += G[(p + (long long)dy * W + dx) * n3p + tap * C + c] + const3[tap * C + c];
+    acc += G[g_index<kTiled>(p + (long long)dy * W + dx, tap * C + c, n3p)] + const3[tap * C + c];
   }
   r[idx] = acc;
 }
 
 // gxb[p][ci] = sum_{tap: p-off in bounds} G'[p-off(tap)][tap*Ch+ci]
+template <bool kTiled>
 __global__ void __launch_bounds__(256) k_gather_bwd(const float* __restrict__ G, float* __restrict__ gxb, int H, int W,
                                                     int Ch, int n3p, long long total) {
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -779,14 +1218,14 @@ __global__ void __launch_bounds__(256) k_gather_bwd(const float* __restrict__ G,
     const int dy = tap / 3 - 1, dx = tap % 3 - 1;
     const int hh = h - dy, ww = w - dx;
     if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
-    acc += G[(p - (long long)dy * W - dx) * n3p + tap * Ch + c];
+    acc += G[g_index<kTiled>(p - (long long)dy * W - dx, tap * Ch + c, n3p)];
   }
   gxb[idx] = acc;
 }
 
 int g_cluster = 1;
 int g_num_sms = 0;
-int g_pair_mode = 0;    // 0: 8-worker-warp single-CTA kernel, 1: CTA-pair kernel (cta_group::2), 2: legacy 4-worker-warp kernel
+int g_pair_mode = 3;    // 3: K-pipelined kernel k_nn_tc4 (default), 0: 8-worker-warp single-CTA kernel, 1: CTA-pair kernel (cta_group::2), 2: legacy 4-worker-warp kernel
 
 // ---- optional per-launch timing of the tensor-core kernel (bench.py's roofline leg): a CUDA event pair
 // on the launching stream around every k_nn_tc launch while profiling is on.
@@ -910,12 +1349,71 @@ void launch_tc2(const TCParams& prm, int grid, cudaStream_t s) {
   }
 }
 
+template <bool kBwd, bool kSaveMask>
+void launch_tc4(const TCParams& prm, int grid, cudaStream_t s) {
+  auto kern = k_nn_tc4<kBwd, kSaveMask>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes4));
+    attr_set = true;
+  }
+  ProfRec rec{};
+  if (g_prof_on) {
+    if (!g_prof_pool.empty()) { rec = g_prof_pool.back(); g_prof_pool.pop_back(); }
+    else { CUDA_CHECK(cudaEventCreate(&rec.a)); CUDA_CHECK(cudaEventCreate(&rec.b)); }
+    CUDA_CHECK(cudaEventRecord(rec.a, s));
+  }
+  kern<<<grid, kThreadsTC2, kSmemBytes4, s>>>(prm);
+  ASEP_LAUNCH_CHECK();
+  if (g_prof_on) {
+    CUDA_CHECK(cudaEventRecord(rec.b, s));
+    g_prof_recs.push_back(rec);
+    g_prof_flops += g_next_flops;
+  }
+}
+
 template <bool kBwd>
-void run_tc(TCParams prm, cudaStream_t s) {
+bool run_tc(TCParams prm, cudaStream_t s) {   // returns true when G was written in the tiled layout
   if (g_num_sms == 0) {
     int dev = 0;
     CUDA_CHECK(cudaGetDevice(&dev));
     CUDA_CHECK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  if (g_pair_mode == 3 && prm.k1_panels * kPanelBytes + ((kTileM * prm.n3p * 4 + 1023) & ~1023) <= kARegionBytes) {
+    ASEP_CHECK(prm.M < (1ll << 31), ASEP_ERR_UNSUPPORTED, "more than 2^31 pixels in one coupling-network launch");
+    const long long tiles = (prm.M + kTileM - 1) / kTileM;
+    const int grid = (int)std::min<long long>(tiles, g_num_sms);
+    prm.tiles_per_cta_round = grid;
+    prm.num_rounds = (int)((tiles + grid - 1) / grid);
+    static long long* dbg = nullptr;
+    const bool timing = getenv("ASEP_TC_DBG_TIMING") != nullptr;
+    if (timing) {
+      if (!dbg) CUDA_CHECK(cudaMalloc(&dbg, 8 * 4096 * sizeof(long long)));
+      ASEP_CHECK(prm.num_rounds <= 4096, ASEP_ERR_BAD_ARG, "too many rounds for the timing buffer");
+      prm.dbg_out = dbg;
+    }
+    if (const char* e = getenv("ASEP_TC_DBG_SHIFT")) prm.dbg_shift = atoi(e);
+    if (const char* e = getenv("ASEP_TC_DBG_FLAGS")) prm.dbg_flags = atoi(e);
+    if (!kBwd && prm.mask1 != nullptr) launch_tc4<kBwd, true>(prm, grid, s); else launch_tc4<kBwd, false>(prm, grid, s);
+    if (timing) {
+      CUDA_CHECK(cudaStreamSynchronize(s));
+      std::vector<long long> h((size_t)8 * prm.num_rounds);
+      CUDA_CHECK(cudaMemcpy(h.data(), dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+      double d[6] = {0};
+      const int r0 = prm.num_rounds > 2 ? 1 : 0, r1 = prm.num_rounds;
+      for (int r = r0; r < r1; ++r) {
+        for (int i = 0; i < 5; ++i) d[i] += (double)(h[r * 8 + i + 1] - h[r * 8 + i]);
+        if (r + 1 < r1) d[5] += (double)(h[(r + 1) * 8] - h[r * 8 + 5]);
+      }
+      const double n = r1 - r0;
+      fprintf(stderr, "[tc4 %s M=%lld rounds=%d] cycles/tile: S1+E1 %.0f | E2 %.0f | wait S3 %.0f | E3 %.0f | build next %.0f | gap %.0f | total %.0f\n",
+              kBwd ? "bwd" : "fwd", prm.M, prm.num_rounds, d[0] / n, d[1] / n, d[2] / n, d[3] / n, d[4] / n,
+              d[5] / std::max(1.0, n - 1), (double)(h[(r1 - 1) * 8 + 5] - h[r0 * 8]) / n);
+      double ld = 0;
+      for (int r = r0; r < r1; ++r) ld += (double)(h[r * 8 + 6] - h[r * 8 + 3]);
+      fprintf(stderr, "      first E3 TMEM load complete %.0f cycles after the S3 commit was seen\n", ld / n);
+    }
+    return true;
   }
   if (g_pair_mode != 2) {
     const bool pair = g_pair_mode == 1;
@@ -949,7 +1447,7 @@ void run_tc(TCParams prm, cudaStream_t s) {
               kBwd ? "bwd" : "fwd", prm.M, prm.num_rounds, d[0] / n, d[1] / n, d[2] / n, d[3] / n, d[4] / n, d[5] / n, d[6] / n,
               d[7] / std::max(1.0, n - 1), (double)(h[(r1 - 1) * 8 + 7] - h[r0 * 8]) / n);
     }
-    return;
+    return false;
   }
   const int cs = g_cluster;
   const long long tiles = (prm.M + kTileM - 1) / kTileM;
@@ -966,6 +1464,7 @@ void run_tc(TCParams prm, cudaStream_t s) {
     case 4: launch_tc<4, kBwd>(prm, grid, s); break;
     default: throw Error(ASEP_ERR_BAD_ARG, strfmt("cluster size %d not built (1, 2, 4)", cs));
   }
+  return false;
 }
 
 }  // namespace
@@ -1000,7 +1499,7 @@ void nn_tc_profile_read(double* total_ms, long long* launches, double* flops) {
   if (flops) *flops = g_prof_flops;
 }
 
-size_t nn_tc_g_floats(long long M, int C) { return (size_t)M * (size_t)pad16(9 * C); }
+size_t nn_tc_g_floats(long long M, int C) { return (size_t)((M + kTileM - 1) / kTileM * kTileM) * (size_t)pad16(9 * C); }   // whole tiles
 
 void nn_tc_prepare(NNWeightsTC& w, const float* k1, const float* c1, const float* g1, const float* b1,
                    const float* k2, const float* c2, const float* g2, const float* b2, const float* k3,
@@ -1070,9 +1569,10 @@ void nn_tc_forward(const NNWeightsTC& w, const NNScratchTC& sc, const float* sta
   prm.dump1 = dump1; prm.dump2 = dump2;
   prm.out = sc.G; prm.H = H; prm.W = W; prm.M = M;
   g_next_flops = 2.0 * (double)M * (9.0 * (C / 2) * kF + (double)kF * kF + 9.0 * kF * C);   // conv MACs x 2, unpadded
-  run_tc<false>(prm, s);
+  const bool tiled = run_tc<false>(prm, s);
   const long long total = M * C;
-  k_gather_fwd<<<cdiv(total, 256), 256, 0, s>>>(sc.G, w.const3, w.c3, r, H, W, C, w.fwd.n3p, total);
+  if (tiled) k_gather_fwd<true><<<cdiv(total, 256), 256, 0, s>>>(sc.G, w.const3, w.c3, r, H, W, C, w.fwd.n3p, total);
+  else k_gather_fwd<false><<<cdiv(total, 256), 256, 0, s>>>(sc.G, w.const3, w.c3, r, H, W, C, w.fwd.n3p, total);
   ASEP_LAUNCH_CHECK();
 }
 
@@ -1089,9 +1589,10 @@ void nn_tc_backward(const NNWeightsTC& w, const NNScratchTC& sc, const float* gr
   prm.dump1 = dump_gp2; prm.dump2 = dump_gp1;
   prm.out = sc.G; prm.H = H; prm.W = W; prm.M = M;
   g_next_flops = 2.0 * (double)M * (9.0 * (C / 2) * kF + (double)kF * kF + 9.0 * kF * C);
-  run_tc<true>(prm, s);
+  const bool tiled = run_tc<true>(prm, s);
   const long long total = M * (C / 2);
-  k_gather_bwd<<<cdiv(total, 256), 256, 0, s>>>(sc.G, gxb, H, W, C / 2, w.bwd.n3p, total);
+  if (tiled) k_gather_bwd<true><<<cdiv(total, 256), 256, 0, s>>>(sc.G, gxb, H, W, C / 2, w.bwd.n3p, total);
+  else k_gather_bwd<false><<<cdiv(total, 256), 256, 0, s>>>(sc.G, gxb, H, W, C / 2, w.bwd.n3p, total);
   ASEP_LAUNCH_CHECK();
 }
 
