@@ -39,14 +39,19 @@ struct ConvParams {
   const float* bias;
   const float* add;
   float* out;
-  int Cout, kpanels, taps, dil, H, W, rows_per_tile, tiles_per_img, num_tiles;
-  int nsplit, ncols, nbuf, stages, stage_bytes, b_bytes;
+  double* stats;    // optional [N, Cout, 2]: per-(image, channel) sum and sum of squares of `out` (instance-norm statistics)
+  int Cout, kpanels, taps, dil, H, W, rows_per_tile, tiles_per_img, num_units;
+  int nunit;        // work units per pixel tile: Cout is processed as `nunit` column groups of `ncols` (<= 256) channels
+  int ncols, stages, stage_bytes, b_bytes;
 };
+
+constexpr int kEpiBytes = 4 * 32 * 128 + 2048;   // per epilogue warp: a 32 x 32 fp32 transpose tile; + statistics exchange
 
 __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__ CUtensorMap tmap, const ConvParams prm) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0u) __trap();
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + prm.stages * prm.stage_bytes);
+  uint8_t* epi = smem + prm.stages * prm.stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi + kEpiBytes);
   // bars: [0,S) full  [S,2S) empty  [2S,2S+2) acc_ready  [2S+2,2S+4) acc_empty  [2S+4] tmem slot
   const int S = prm.stages;
   const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[S]);
@@ -56,7 +61,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < S; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(accr0 + 8 * i, 1); mbar_init(acce0 + 8 * i, 128); }
+    for (int i = 0; i < 2; ++i) { mbar_init(accr0 + 8 * i, 1); mbar_init(acce0 + 8 * i, 4); }
     fence_barrier_init();
     tma_prefetch_desc(&tmap);
   }
@@ -67,13 +72,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
   const uint32_t tmem_base = *tmem_slot;
   const int kiters = prm.taps * prm.kpanels;
 
+  // A work unit = (128-pixel tile, column group).  Consecutive units share the activation tile (L2 locality); the
+  // two 256-column TMEM buffers alternate, so the epilogue of unit i overlaps the MMAs of unit i+1.
   if (warp == 0) {
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int tile = blockIdx.x; tile < prm.num_tiles; tile += gridDim.x) {
+      for (int unit = blockIdx.x; unit < prm.num_units; unit += gridDim.x) {
+        const int tile = unit / prm.nunit, nh = unit - tile * prm.nunit;
         const int n = tile / prm.tiles_per_img;
         const int h0 = (tile % prm.tiles_per_img) * prm.rows_per_tile;
-        const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(prm.wimg);
+        const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(prm.wimg) + (size_t)nh * prm.b_bytes;
         for (int tap = 0; tap < prm.taps; ++tap) {
           const int dy = prm.taps == 9 ? (tap / 3 - 1) * prm.dil : 0;
           const int dx = prm.taps == 9 ? (tap % 3 - 1) * prm.dil : 0;
@@ -84,7 +92,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
             mbar_expect_tx(fb, (uint32_t)(kABytes + prm.b_bytes));
             tma_load_4d(sa, &tmap, kp * 64, dx, h0 + dy, n, fb);
             bulk_g2s(sa + kABytes, wsrc, (uint32_t)prm.b_bytes, fb);
-            wsrc += prm.b_bytes;
+            wsrc += (size_t)prm.Cout * 128;
             if (++stage == (uint32_t)S) { stage = 0; phase ^= 1; }
           }
         }
@@ -93,12 +101,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
   } else if (warp == 1) {
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      uint32_t use[2] = {0, 0};
       const uint32_t idesc = make_idesc(prm.ncols);
       int it = 0;
-      for (int tile = blockIdx.x; tile < prm.num_tiles; tile += gridDim.x, ++it) {
-        const int buf = prm.nbuf == 2 ? (it & 1) : 0;
-        mbar_wait(acce0 + 8 * buf, (use[buf] & 1) ^ 1);       // epilogue has drained this accumulator buffer
+      for (int unit = blockIdx.x; unit < prm.num_units; unit += gridDim.x, ++it) {
+        const int buf = it & 1;
+        mbar_wait(acce0 + 8 * buf, ((uint32_t)(it >> 1) & 1u) ^ 1u);       // epilogue has drained this accumulator buffer
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 256);
         for (int ki = 0; ki < kiters; ++ki) {
@@ -108,56 +115,92 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
           const uint64_t da = make_desc(sa);
           const uint64_t db = make_desc(sa + kABytes);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            for (int sp = 0; sp < prm.nsplit; ++sp) {
-              umma_bf16(d_tmem + (uint32_t)(sp * prm.ncols), da + (uint64_t)(2 * k),
-                        db + (uint64_t)(sp * prm.ncols * 8 + 2 * k), idesc, (ki | k) != 0);
-            }
-          }
+          for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (ki | k) != 0);
           umma_commit(empty0 + 8 * stage);
           if (++stage == (uint32_t)S) { stage = 0; phase ^= 1; }
         }
         umma_commit(accr0 + 8 * buf);
-        ++use[buf];
       }
     }
   } else {
+    // Epilogue.  A thread owns one accumulator row (pixel), so storing it directly would touch 32 different
+    // 128-byte lines per instruction (one LSU wavefront each).  Every 32 x 32 chunk is therefore transposed through
+    // a swizzled shared-memory tile: afterwards 8 consecutive lanes hold the 8 float4 of one pixel's 32 channels, and
+    // each load of the residual / store of the result covers four full lines.
     const int quarter = warp & 3;
-    const int row = quarter * 32 + lane;
-    uint32_t use[2] = {0, 0};
+    uint8_t* tbuf = epi + quarter * (32 * 128);
+    const int c4 = lane & 7, g = lane >> 3;
     int it = 0;
-    for (int tile = blockIdx.x; tile < prm.num_tiles; tile += gridDim.x, ++it) {
-      const int buf = prm.nbuf == 2 ? (it & 1) : 0;
-      mbar_wait(accr0 + 8 * buf, use[buf] & 1);
-      ++use[buf];
+    for (int unit = blockIdx.x; unit < prm.num_units; unit += gridDim.x, ++it) {
+      const int tile = unit / prm.nunit, nh = unit - tile * prm.nunit;
+      const int buf = it & 1;
+      mbar_wait(accr0 + 8 * buf, (uint32_t)(it >> 1) & 1u);
       tc_fence_after();
-      const long long p = (long long)tile * kTileM + row;
+      const long long p0 = (long long)tile * kTileM + quarter * 32;
       const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * 256);
-      float* orow = prm.out + p * prm.Cout;
-      const float* arow = prm.add ? prm.add + p * prm.Cout : nullptr;
-      for (int j = 0; j < prm.Cout / 32; ++j) {
+      const int col0 = nh * prm.ncols;
+      for (int j = 0; j < prm.ncols / 32; ++j) {
         uint32_t v[32];
         tmem_ld32(t_lane + (uint32_t)(j * 32), v);
+        const int col = col0 + j * 32 + c4 * 4;
         float4 a4[8];
-        if (arow) {
+        if (prm.add) {
 #pragma unroll
-          for (int q = 0; q < 8; ++q) a4[q] = reinterpret_cast<const float4*>(arow + j * 32)[q];
+          for (int i = 0; i < 8; ++i) a4[i] = *reinterpret_cast<const float4*>(prm.add + (p0 + 4 * i + g) * prm.Cout + col);
         }
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (prm.bias) b4 = __ldg(reinterpret_cast<const float4*>(prm.bias + col));
         tmem_ld_wait();
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          float4 o = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
-                                 __uint_as_float(v[4 * q + 3]));
-          if (prm.bias) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(prm.bias + j * 32) + q);
-            o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
-          }
-          if (arow) { o.x += a4[q].x; o.y += a4[q].y; o.z += a4[q].z; o.w += a4[q].w; }
-          reinterpret_cast<float4*>(orow + j * 32)[q] = o;
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<uint4*>(tbuf + lane * 128 + ((q ^ (lane & 7)) << 4)) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        __syncwarp();
+        float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = 4 * i + g;
+          float4 o = *reinterpret_cast<const float4*>(tbuf + r * 128 + ((c4 ^ (r & 7)) << 4));
+          o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
+          if (prm.add) { o.x += a4[i].x; o.y += a4[i].y; o.z += a4[i].z; o.w += a4[i].w; }
+          *reinterpret_cast<float4*>(prm.out + (p0 + r) * prm.Cout + col) = o;
+          s1.x += o.x; s1.y += o.y; s1.z += o.z; s1.w += o.w;
+          s2.x = fmaf(o.x, o.x, s2.x); s2.y = fmaf(o.y, o.y, s2.y); s2.z = fmaf(o.z, o.z, s2.z); s2.w = fmaf(o.w, o.w, s2.w);
         }
+        if (prm.stats) {
+          // the next layer's instance-norm statistics ride along: 32 pixels x 4 channels per lane group -> one
+          // double atomic per (channel, moment) and warp
+#pragma unroll
+          for (int o = 8; o <= 16; o <<= 1) {
+            s1.x += __shfl_xor_sync(0xffffffffu, s1.x, o); s1.y += __shfl_xor_sync(0xffffffffu, s1.y, o);
+            s1.z += __shfl_xor_sync(0xffffffffu, s1.z, o); s1.w += __shfl_xor_sync(0xffffffffu, s1.w, o);
+            s2.x += __shfl_xor_sync(0xffffffffu, s2.x, o); s2.y += __shfl_xor_sync(0xffffffffu, s2.y, o);
+            s2.z += __shfl_xor_sync(0xffffffffu, s2.z, o); s2.w += __shfl_xor_sync(0xffffffffu, s2.w, o);
+          }
+          // combine the four warps (128 pixels) in shared memory: one double atomic per (channel, moment) and tile
+          float* red = reinterpret_cast<float*>(epi + 4 * 32 * 128) + (j & 1) * 256;
+          if (g == 0) {
+            float4* rr = reinterpret_cast<float4*>(red + quarter * 64 + c4 * 8);
+            rr[0] = make_float4(s1.x, s2.x, s1.y, s2.y);
+            rr[1] = make_float4(s1.z, s2.z, s1.w, s2.w);
+          }
+          named_bar_sync(1, 128);
+          if (quarter == 0) {
+            float2 t = reinterpret_cast<const float2*>(red)[lane];
+#pragma unroll
+            for (int w = 1; w < 4; ++w) {
+              const float2 u = reinterpret_cast<const float2*>(red + w * 64)[lane];
+              t.x += u.x; t.y += u.y;
+            }
+            double* st = prm.stats + ((size_t)(tile / prm.tiles_per_img) * prm.Cout + col0 + j * 32 + lane) * 2;
+            atomicAdd(st, (double)t.x);
+            atomicAdd(st + 1, (double)t.y);
+          }
+        }
+        __syncwarp();
       }
       tc_fence_before();
-      mbar_arrive(acce0 + 8 * buf);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acce0 + 8 * buf);
     }
   }
   tc_fence_before();
@@ -252,7 +295,7 @@ void conv_tc_release(ConvWeightsTC& w) {
 }
 
 void conv_tc_forward(const ConvWeightsTC& w, const __nv_bfloat16* xin, const float* add, float* out, int N, int H,
-                     int W, cudaStream_t s) {
+                     int W, cudaStream_t s, double* stats) {
   if (N == 0) return;
   ASEP_CHECK(conv_tc_supported(w.Cin, w.Cout, H, W), ASEP_ERR_UNSUPPORTED,
              "tcgen05 conv: unsupported shape Cin=%d Cout=%d H=%d W=%d", w.Cin, w.Cout, H, W);
@@ -262,24 +305,25 @@ void conv_tc_forward(const ConvWeightsTC& w, const __nv_bfloat16* xin, const flo
     CUDA_CHECK(cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   ConvParams prm{};
-  prm.wimg = w.img; prm.bias = w.bias; prm.add = add; prm.out = out;
+  prm.wimg = w.img; prm.bias = w.bias; prm.add = add; prm.out = out; prm.stats = stats;
+  if (stats) CUDA_CHECK(cudaMemsetAsync(stats, 0, (size_t)N * w.Cout * 2 * sizeof(double), s));
   prm.Cout = w.Cout; prm.kpanels = w.Cin / 64; prm.taps = w.ksize * w.ksize; prm.dil = w.dil;
   prm.H = H; prm.W = W; prm.rows_per_tile = kTileM / W; prm.tiles_per_img = H / prm.rows_per_tile;
-  prm.num_tiles = N * prm.tiles_per_img;
-  prm.nsplit = w.Cout > 256 ? 2 : 1;
-  prm.ncols = w.Cout / prm.nsplit;
-  prm.nbuf = w.Cout <= 256 ? 2 : 1;
-  prm.b_bytes = w.Cout * 128;
+  const int num_tiles = N * prm.tiles_per_img;
+  prm.nunit = w.Cout > 256 ? 2 : 1;
+  prm.ncols = w.Cout / prm.nunit;
+  prm.num_units = num_tiles * prm.nunit;
+  prm.b_bytes = prm.ncols * 128;
   prm.stage_bytes = kABytes + prm.b_bytes;
-  prm.stages = std::min(kMaxStages, kSmemBudget / prm.stage_bytes);
-  const int smem_bytes = prm.stages * prm.stage_bytes + 1024;
+  prm.stages = std::min(kMaxStages, (kSmemBudget - kEpiBytes) / prm.stage_bytes);
+  const int smem_bytes = prm.stages * prm.stage_bytes + kEpiBytes + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     CUDA_CHECK(cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   const CUtensorMap& tmap = activation_map(xin, N, H, W, w.Cin);
-  const int grid = std::min(prm.num_tiles, g_sms);
+  const int grid = std::min(prm.num_units, g_sms);
   ProfRec rec{};
   if (g_prof_on) {
     if (!g_pool.empty()) { rec = g_pool.back(); g_pool.pop_back(); }

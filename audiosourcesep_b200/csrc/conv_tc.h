@@ -22,8 +22,10 @@ bool conv_tc_supported(int Cin, int Cout, int H, int W);
 
 // out[n,h,w,:] = conv(xin)[n,h,w,:] + bias + add[n,h,w,:]   (add may be NULL or alias out)
 // xin: bf16 NHWC [N,H,W,Cin] (already normalised / activated), out/add: fp32 NHWC [N,H,W,Cout].
+// stats (may be NULL): [N, Cout, 2] doubles that receive the per-(image, channel) sum and sum of squares of `out`
+// (zeroed here, accumulated by the epilogue) - the statistics of the instance norm that usually follows.
 void conv_tc_forward(const ConvWeightsTC& w, const __nv_bfloat16* xin, const float* add, float* out, int N, int H,
-                     int W, cudaStream_t s);
+                     int W, cudaStream_t s, double* stats = nullptr);
 
 // profiling of the conv launches (same contract as nn_tc_profile)
 void conv_tc_profile(int on);

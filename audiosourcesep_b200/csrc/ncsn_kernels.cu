@@ -14,30 +14,51 @@ constexpr double kPlusEps = 1e-5;   // score_network.py:205
 
 __device__ __forceinline__ float elu(float v) { return v > 0.f ? v : expm1f(v); }
 
-// ---- per-(n,c) sum and sum of squares over H*W.  grid (chunks, N); thread t owns channel t % C.
-__global__ void __launch_bounds__(384) k_in_stats(const float* __restrict__ x, double* __restrict__ sums, int HW, int C,
+// ---- per-(n,c) sum and sum of squares over H*W.  grid (row slabs, N); a thread owns 4 channels (float4 loads) and
+// every (blockDim / (C/4))-th pixel of the slab, four loads in flight.
+__global__ void __launch_bounds__(256) k_in_stats(const float* __restrict__ x, double* __restrict__ sums, int HW, int C4,
                                                   int rows_per_block) {
-  extern __shared__ float red[];                // [2][blockDim]
+  __shared__ float4 red[2][256];
   const int n = blockIdx.y;
-  const int c = threadIdx.x % C, r0 = threadIdx.x / C, rstep = blockDim.x / C;
+  const int rstep = blockDim.x / C4;
+  const int c = threadIdx.x % C4, r0 = threadIdx.x / C4;
   const int rbeg = blockIdx.x * rows_per_block, rend = min(HW, rbeg + rows_per_block);
-  float s = 0.f, ss = 0.f;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f), ss = s;
   if (r0 < rstep) {
-    const float* base = x + ((size_t)n * HW) * C + c;
-    for (int r = rbeg + r0; r < rend; r += rstep) {
-      const float v = base[(size_t)r * C];
-      s += v;
-      ss = fmaf(v, v, ss);
+    const float4* base = reinterpret_cast<const float4*>(x) + ((size_t)n * HW) * C4 + c;
+    int r = rbeg + r0;
+    for (; r + 3 * rstep < rend; r += 4 * rstep) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = __ldg(base + (size_t)(r + u * rstep) * C4);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        s.x += v[u].x; s.y += v[u].y; s.z += v[u].z; s.w += v[u].w;
+        ss.x = fmaf(v[u].x, v[u].x, ss.x); ss.y = fmaf(v[u].y, v[u].y, ss.y);
+        ss.z = fmaf(v[u].z, v[u].z, ss.z); ss.w = fmaf(v[u].w, v[u].w, ss.w);
+      }
+    }
+    for (; r < rend; r += rstep) {
+      const float4 v = __ldg(base + (size_t)r * C4);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      ss.x = fmaf(v.x, v.x, ss.x); ss.y = fmaf(v.y, v.y, ss.y); ss.z = fmaf(v.z, v.z, ss.z); ss.w = fmaf(v.w, v.w, ss.w);
     }
   }
-  red[threadIdx.x] = s;
-  red[blockDim.x + threadIdx.x] = ss;
+  red[0][threadIdx.x] = s;
+  red[1][threadIdx.x] = ss;
   __syncthreads();
-  if (threadIdx.x < C) {
-    float a = 0.f, b = 0.f;
-    for (int g = 0; g < rstep; ++g) { a += red[g * C + threadIdx.x]; b += red[blockDim.x + g * C + threadIdx.x]; }
-    atomicAdd(sums + ((size_t)n * C + threadIdx.x) * 2, (double)a);
-    atomicAdd(sums + ((size_t)n * C + threadIdx.x) * 2 + 1, (double)b);
+  if (threadIdx.x < C4) {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    for (int g = 0; g < rstep; ++g) {
+      const float4 t = red[0][g * C4 + threadIdx.x], u = red[1][g * C4 + threadIdx.x];
+      a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+      b.x += u.x; b.y += u.y; b.z += u.z; b.w += u.w;
+    }
+    double* st = sums + ((size_t)n * C4 + threadIdx.x) * 8;
+    atomicAdd(st + 0, (double)a.x); atomicAdd(st + 1, (double)b.x);
+    atomicAdd(st + 2, (double)a.y); atomicAdd(st + 3, (double)b.y);
+    atomicAdd(st + 4, (double)a.z); atomicAdd(st + 5, (double)b.z);
+    atomicAdd(st + 6, (double)a.w); atomicAdd(st + 7, (double)b.w);
   }
 }
 
@@ -81,20 +102,12 @@ __global__ void __launch_bounds__(512) k_in_coef(const double* __restrict__ sums
   coef[(size_t)n * C + c] = make_float2(aa, bb);
 }
 
-// ---- y_bf16 = act(a*x+b), 8 channels per thread
-__global__ void __launch_bounds__(256) k_prep(const float* __restrict__ x, const float2* __restrict__ coef,
-                                              __nv_bfloat16* __restrict__ y, long long nvec, int HWC, int C, int do_elu) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nvec) return;
-  const long long e = i * 8;
-  const float4 v0 = reinterpret_cast<const float4*>(x + e)[0], v1 = reinterpret_cast<const float4*>(x + e)[1];
+// ---- y_bf16 = act(a*x+b).  grid (row slabs, N); a thread owns 8 channels - its 16 coefficients stay in registers -
+// and every (blockDim / (C/8))-th pixel of the slab, two pixels in flight.
+__device__ __forceinline__ uint4 prep8(const float4 v0, const float4 v1, const float (&ca)[8], const float (&cb)[8], int do_elu) {
   float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-  if (coef) {
-    const int n = (int)(e / HWC), c0 = (int)(e % C);
-    const float2* cf = coef + (size_t)n * C + c0;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { const float2 ab = __ldg(cf + k); v[k] = fmaf(ab.x, v[k], ab.y); }
-  }
+  for (int k = 0; k < 8; ++k) v[k] = fmaf(ca[k], v[k], cb[k]);
   if (do_elu) {
 #pragma unroll
     for (int k = 0; k < 8; ++k) v[k] = elu(v[k]);
@@ -105,35 +118,69 @@ __global__ void __launch_bounds__(256) k_prep(const float* __restrict__ x, const
   t = __floats2bfloat162_rn(v[2], v[3]); o.y = *reinterpret_cast<uint32_t*>(&t);
   t = __floats2bfloat162_rn(v[4], v[5]); o.z = *reinterpret_cast<uint32_t*>(&t);
   t = __floats2bfloat162_rn(v[6], v[7]); o.w = *reinterpret_cast<uint32_t*>(&t);
-  reinterpret_cast<uint4*>(y + e)[0] = o;
+  return o;
 }
 
-// ---- 5x5 stride-1 'same' pooling: average over the in-bounds taps / max ignoring out-of-bounds taps
-template <bool kMax>
-__global__ void __launch_bounds__(256) k_pool5(const float* __restrict__ x, float* __restrict__ y, int H, int W, int C4,
-                                               long long total) {
+__global__ void __launch_bounds__(256) k_prep(const float* __restrict__ x, const float2* __restrict__ coef,
+                                              __nv_bfloat16* __restrict__ y, int HW, int C8, int rows_per_block, int do_elu) {
+  const int n = blockIdx.y;
+  const int rstep = blockDim.x / C8;
+  const int c = threadIdx.x % C8, r0 = threadIdx.x / C8;
+  if (r0 >= rstep) return;
+  float ca[8], cb[8];
+  if (coef) {
+    const float4* cf = reinterpret_cast<const float4*>(coef + ((size_t)n * C8 + c) * 8);      // 8 x (a, b)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float4 t = __ldg(cf + k);
+      ca[2 * k] = t.x; cb[2 * k] = t.y; ca[2 * k + 1] = t.z; cb[2 * k + 1] = t.w;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { ca[k] = 1.f; cb[k] = 0.f; }
+  }
+  const int rbeg = blockIdx.x * rows_per_block, rend = min(HW, rbeg + rows_per_block);
+  const float4* xb = reinterpret_cast<const float4*>(x) + ((size_t)n * HW) * (2 * C8) + 2 * c;
+  uint4* yb = reinterpret_cast<uint4*>(y) + ((size_t)n * HW) * C8 + c;
+  int r = rbeg + r0;
+  for (; r + rstep < rend; r += 2 * rstep) {
+    const float4 a0 = __ldg(xb + (size_t)r * (2 * C8)), a1 = __ldg(xb + (size_t)r * (2 * C8) + 1);
+    const float4 b0 = __ldg(xb + (size_t)(r + rstep) * (2 * C8)), b1 = __ldg(xb + (size_t)(r + rstep) * (2 * C8) + 1);
+    yb[(size_t)r * C8] = prep8(a0, a1, ca, cb, do_elu);
+    yb[(size_t)(r + rstep) * C8] = prep8(b0, b1, ca, cb, do_elu);
+  }
+  for (; r < rend; r += rstep) {
+    const float4 a0 = __ldg(xb + (size_t)r * (2 * C8)), a1 = __ldg(xb + (size_t)r * (2 * C8) + 1);
+    yb[(size_t)r * C8] = prep8(a0, a1, ca, cb, do_elu);
+  }
+}
+
+// ---- 5x5 stride-1 'same' pooling, separable: average over the in-bounds taps / max ignoring out-of-bounds taps.
+// Pass kAxis = 0 reduces along W (sums / maxima of up to 5 taps), pass kAxis = 1 along H and, for the average, divides
+// by the number of in-bounds taps of the whole window (rows in bounds x columns in bounds).
+template <bool kMax, int kAxis>
+__global__ void __launch_bounds__(256) k_pool5_1d(const float* __restrict__ x, float* __restrict__ y, int H, int W, int C4,
+                                                  long long total) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
-  const int c = (int)(i % C4);
-  long long p = i / C4;
+  const long long p = i / C4;
   const int w = (int)(p % W), h = (int)((p / W) % H);
-  const long long img = p / ((long long)W * H);
-  const float4* base = reinterpret_cast<const float4*>(x) + img * H * W * C4 + c;
+  const float4* base = reinterpret_cast<const float4*>(x) + i;
+  const int pos = kAxis == 0 ? w : h, lim = kAxis == 0 ? W : H;
+  const long long step = kAxis == 0 ? (long long)C4 : (long long)W * C4;
   float4 acc = kMax ? make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY) : make_float4(0.f, 0.f, 0.f, 0.f);
-  int cnt = 0;
-  for (int dy = -2; dy <= 2; ++dy) {
-    const int hh = h + dy;
-    if (hh < 0 || hh >= H) continue;
-    for (int dx = -2; dx <= 2; ++dx) {
-      const int ww = w + dx;
-      if (ww < 0 || ww >= W) continue;
-      const float4 v = __ldg(base + ((long long)hh * W + ww) * C4);
-      if (kMax) { acc.x = fmaxf(acc.x, v.x); acc.y = fmaxf(acc.y, v.y); acc.z = fmaxf(acc.z, v.z); acc.w = fmaxf(acc.w, v.w); }
-      else { acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w; }
-      ++cnt;
-    }
+#pragma unroll
+  for (int d = -2; d <= 2; ++d) {
+    if (pos + d < 0 || pos + d >= lim) continue;
+    const float4 v = __ldg(base + d * step);
+    if (kMax) { acc.x = fmaxf(acc.x, v.x); acc.y = fmaxf(acc.y, v.y); acc.z = fmaxf(acc.z, v.z); acc.w = fmaxf(acc.w, v.w); }
+    else { acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w; }
   }
-  if (!kMax) { const float r = 1.f / (float)cnt; acc.x *= r; acc.y *= r; acc.z *= r; acc.w *= r; }
+  if (!kMax && kAxis == 1) {
+    const int ch = min(h + 2, H - 1) - max(h - 2, 0) + 1, cw = min(w + 2, W - 1) - max(w - 2, 0) + 1;
+    const float r = 1.f / (float)(ch * cw);
+    acc.x *= r; acc.y *= r; acc.z *= r; acc.w *= r;
+  }
   reinterpret_cast<float4*>(y)[i] = acc;
 }
 
@@ -245,11 +292,12 @@ __global__ void __launch_bounds__(256) k_end_conv(const __nv_bfloat16* __restric
 
 void launch_in_stats(const float* x, double* sums, int N, int HW, int C, cudaStream_t s) {
   CUDA_CHECK(cudaMemsetAsync(sums, 0, (size_t)N * C * 2 * sizeof(double), s));
-  ASEP_CHECK(C <= 384, ASEP_ERR_UNSUPPORTED, "instance-norm statistics: C = %d > 384", C);
-  const int threads = C * (384 / C);
-  const int rows = 256;
+  ASEP_CHECK(C % 4 == 0 && C / 4 <= 256, ASEP_ERR_UNSUPPORTED, "instance-norm statistics: C = %d (multiple of 4, <= 1024)", C);
+  const int C4 = C / 4;
+  const int threads = C4 * (256 / C4);
+  const int rows = 32;
   dim3 grid((HW + rows - 1) / rows, N);
-  k_in_stats<<<grid, threads, 2 * threads * sizeof(float), s>>>(x, sums, HW, C, rows);
+  k_in_stats<<<grid, threads, 0, s>>>(x, sums, HW, C4, rows);
   ASEP_LAUNCH_CHECK();
 }
 
@@ -262,16 +310,24 @@ void launch_in_coef(const double* sums, const float* gab, int gab_stride_n, cons
 }
 
 void launch_prep(const float* x, const float2* coef, __nv_bfloat16* y, int N, int HW, int C, int do_elu, cudaStream_t s) {
-  ASEP_CHECK(C % 8 == 0, ASEP_ERR_UNSUPPORTED, "prep: C %% 8 != 0");
-  const long long nvec = (long long)N * HW * C / 8;
-  k_prep<<<cdiv(nvec, 256), 256, 0, s>>>(x, coef, y, nvec, HW * C, C, do_elu);
+  ASEP_CHECK(C % 8 == 0 && C / 8 <= 256, ASEP_ERR_UNSUPPORTED, "prep: C = %d (multiple of 8, <= 2048)", C);
+  const int C8 = C / 8;
+  const int threads = C8 * (256 / C8);
+  const int rows = 32;
+  dim3 grid((HW + rows - 1) / rows, N);
+  k_prep<<<grid, threads, 0, s>>>(x, coef, y, HW, C8, rows, do_elu);
   ASEP_LAUNCH_CHECK();
 }
 
-void launch_pool5(const float* x, float* y, int N, int H, int W, int C, int is_max, cudaStream_t s) {
+void launch_pool5(const float* x, float* tmp, float* y, int N, int H, int W, int C, int is_max, cudaStream_t s) {
   const long long total = (long long)N * H * W * (C / 4);
-  if (is_max) k_pool5<true><<<cdiv(total, 256), 256, 0, s>>>(x, y, H, W, C / 4, total);
-  else k_pool5<false><<<cdiv(total, 256), 256, 0, s>>>(x, y, H, W, C / 4, total);
+  if (is_max) {
+    k_pool5_1d<true, 0><<<cdiv(total, 256), 256, 0, s>>>(x, tmp, H, W, C / 4, total);
+    k_pool5_1d<true, 1><<<cdiv(total, 256), 256, 0, s>>>(tmp, y, H, W, C / 4, total);
+  } else {
+    k_pool5_1d<false, 0><<<cdiv(total, 256), 256, 0, s>>>(x, tmp, H, W, C / 4, total);
+    k_pool5_1d<false, 1><<<cdiv(total, 256), 256, 0, s>>>(tmp, y, H, W, C / 4, total);
+  }
   ASEP_LAUNCH_CHECK();
 }
 

@@ -14,7 +14,8 @@ void launch_in_coef(const double* sums, const float* gab, int gab_stride_n, cons
 // y (bf16) = act(coef.a * x + coef.b); coef may be NULL (plain cast); do_elu applies ELU(alpha=1)
 void launch_prep(const float* x, const float2* coef, __nv_bfloat16* y, int N, int HW, int C, int do_elu, cudaStream_t s);
 // 5x5 stride-1 'same' pooling: average over in-bounds taps (Keras AveragePooling2D) or max (MaxPooling2D)
-void launch_pool5(const float* x, float* y, int N, int H, int W, int C, int is_max, cudaStream_t s);
+// (separable: tmp is a scratch tensor of the same size)
+void launch_pool5(const float* x, float* tmp, float* y, int N, int H, int W, int C, int is_max, cudaStream_t s);
 // AveragePooling2D(2): [N,2Hout,2Wout,C] -> [N,Hout,Wout,C]
 void launch_avgpool2(const float* x, float* y, int N, int Hout, int Wout, int C, cudaStream_t s);
 // y[N,2h,2w,C] = add + tf.image.resize(x[N,h,w,C], bilinear, half-pixel centres); add may be NULL

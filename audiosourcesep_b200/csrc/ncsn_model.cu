@@ -144,7 +144,7 @@ __nv_bfloat16* NcsnModel::new_bf(int H, int W, int C) {
 
 // ------------------------------------------------------------------ layers
 const float2* NcsnModel::norm_coef(const T& x, const std::string& name) {
-  double* sums = static_cast<double*>(take((size_t)N_ * x.C * 2 * sizeof(double)));
+  double* sums = x.sums ? x.sums : static_cast<double*>(take((size_t)N_ * x.C * 2 * sizeof(double)));
   float2* coef = static_cast<float2*>(take((size_t)N_ * x.C * sizeof(float2)));
   const NcsnParam& ig = param(name + "/in_gamma");
   const NcsnParam& ib = param(name + "/in_beta");
@@ -163,7 +163,7 @@ const float2* NcsnModel::norm_coef(const T& x, const std::string& name) {
   }
   ASEP_CHECK((int)ig.host.size() == x.C && (int)ib.host.size() == x.C, ASEP_ERR_BAD_SHAPE, "%s: channel mismatch", name.c_str());
   if (dry_) return coef;
-  launch_in_stats(x.p, sums, N_, x.H * x.W, x.C, s_);
+  if (!x.sums) launch_in_stats(x.p, sums, N_, x.H * x.W, x.C, s_);   // conv outputs arrive with their statistics
   launch_in_coef(sums, gab, stride, v1_ ? idx_ : nullptr, ig.dev, ib.dev, coef, N_, x.H * x.W, x.C, s_);
   return coef;
 }
@@ -174,12 +174,13 @@ __nv_bfloat16* NcsnModel::prep(const T& x, const float2* coef, bool elu) {
   return y;
 }
 
-NcsnModel::T NcsnModel::conv(const std::string& name, const __nv_bfloat16* xin, int H, int W, const float* add) {
+NcsnModel::T NcsnModel::conv(const std::string& name, const __nv_bfloat16* xin, int H, int W, const float* add, bool stats) {
   auto it = convs_.find(name);
   ASEP_CHECK(it != convs_.end(), ASEP_ERR_STATE, "convolution '%s' has no kernel parameter", name.c_str());
   const ConvWeightsTC& w = it->second;
   T out = new_t(H, W, w.Cout);
-  if (!dry_) conv_tc_forward(w, xin, add, out.p, N_, H, W, s_);
+  if (stats) out.sums = static_cast<double*>(take((size_t)N_ * w.Cout * 2 * sizeof(double)));
+  if (!dry_) conv_tc_forward(w, xin, add, out.p, N_, H, W, s_, out.sums);
   return out;
 }
 
@@ -188,16 +189,17 @@ NcsnModel::T NcsnModel::res_block(const T& x, const std::string& name, int cout,
   (void)cout; (void)dilation;
   const float2* c1 = norm_coef(x, name + "/norm1");
   __nv_bfloat16* h = prep(x, c1, true);
-  T o1 = conv(name + "/conv1", h, x.H, x.W, nullptr);
+  T o1 = conv(name + "/conv1", h, x.H, x.W, nullptr, true);                   // norm2 follows
   const float2* c2 = norm_coef(o1, name + "/norm2");
   __nv_bfloat16* h2 = prep(o1, c2, true);
   const float* sc = x.p;
   if (has(name + "/shortcut/kernel")) {
     __nv_bfloat16* xr = prep(x, nullptr, false);
-    sc = conv(name + "/shortcut", xr, x.H, x.W, nullptr).p;
+    sc = conv(name + "/shortcut", xr, x.H, x.W, nullptr, false).p;
   }
-  T o2 = conv(name + "/conv2", h2, x.H, x.W, sc);        // shortcut + output fused into the epilogue
   const bool pool = down && name.rfind("Res2_", 0) == 0;  // only the undilated 'down' block pools (score_network.py:141-144)
+  // shortcut + output fused into the epilogue; an unpooled block output feeds norm layers (next block / RCU / MSF)
+  T o2 = conv(name + "/conv2", h2, x.H, x.W, sc, !pool);
   if (!pool) return o2;
   // avg_pool2(shortcut) + avg_pool2(output) == avg_pool2(shortcut + output)
   T out = new_t(x.H / 2, x.W / 2, o2.C);
@@ -213,7 +215,7 @@ NcsnModel::T NcsnModel::rcu(T x, const std::string& prefix, int n_blocks, int n_
       const std::string sfx = "_" + std::to_string(i + 1) + "_" + std::to_string(j + 1);
       const float2* c = v1_ ? norm_coef(x, prefix + "/norm" + sfx) : nullptr;
       __nv_bfloat16* h = prep(x, c, false);
-      x = conv(prefix + "/conv" + sfx, h, x.H, x.W, j == n_stages - 1 ? residual.p : nullptr);
+      x = conv(prefix + "/conv" + sfx, h, x.H, x.W, j == n_stages - 1 ? residual.p : nullptr, v1_);
     }
   }
   return x;
@@ -228,10 +230,10 @@ NcsnModel::T NcsnModel::crp(T x, const std::string& prefix) {
     const std::string sfx = "_" + std::to_string(i + 1);
     // avg over the in-bounds taps commutes with the per-(n,c) affine of the norm: pool first, normalise while casting
     const float2* c = v1_ ? norm_coef(path, prefix + "/norm" + sfx) : nullptr;
-    T pooled = new_t(x.H, x.W, x.C);
-    if (!dry_) launch_pool5(path.p, pooled.p, N_, x.H, x.W, x.C, v1_ ? 0 : 1, s_);
+    T pooled = new_t(x.H, x.W, x.C), ptmp = new_t(x.H, x.W, x.C);
+    if (!dry_) launch_pool5(path.p, ptmp.p, pooled.p, N_, x.H, x.W, x.C, v1_ ? 0 : 1, s_);
     __nv_bfloat16* h = prep(pooled, c, false);
-    path = conv(prefix + "/conv" + sfx, h, x.H, x.W, nullptr);
+    path = conv(prefix + "/conv" + sfx, h, x.H, x.W, nullptr, v1_ && i == 0);
     T sum = new_t(x.H, x.W, x.C);
     if (!dry_) launch_add(acc.p, path.p, sum.p, (long long)N_ * x.H * x.W * x.C, s_);
     acc = sum;
@@ -253,10 +255,10 @@ NcsnModel::T NcsnModel::msf(const std::vector<T>& xs, const std::string& prefix,
       const float2* c = v1_ ? norm_coef(xi, prefix + "/norm" + sfx) : nullptr;
       __nv_bfloat16* h = prep(xi, c, false);
       if (same) {
-        sums = conv(prefix + "/conv" + sfx, h, xi.H, xi.W, sums.p);
+        sums = conv(prefix + "/conv" + sfx, h, xi.H, xi.W, sums.p, false);
       } else {
         ASEP_CHECK(2 * xi.H == H && 2 * xi.W == W, ASEP_ERR_UNSUPPORTED, "MSF resize other than x2");
-        T low = conv(prefix + "/conv" + sfx, h, xi.H, xi.W, nullptr);
+        T low = conv(prefix + "/conv" + sfx, h, xi.H, xi.W, nullptr, false);
         T up = new_t(H, W, low.C);
         if (!dry_) launch_resize2x_add(low.p, sums.p, up.p, N_, xi.H, xi.W, low.C, s_);
         sums = up;

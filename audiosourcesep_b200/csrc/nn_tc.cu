@@ -84,9 +84,6 @@ __device__ __forceinline__ uint32_t a_offset(int row, int k) {
   return (uint32_t)((k >> 6) * kPanelBytes + row * 128 + ((((k & 63) >> 3) ^ (row & 7)) << 4) + ((k & 7) << 1));
 }
 
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
 
 // Stage-1 operand row: im2col of SC channels over the 3x3 taps as split-bf16 [hi | lo].
 // All global loads of a tap group are issued before any is consumed (memory-level parallelism).
