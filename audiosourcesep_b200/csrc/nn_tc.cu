@@ -1220,6 +1220,49 @@ __global__ void __launch_bounds__(256) k_gather_bwd(const float* __restrict__ G,
   gxb[idx] = acc;
 }
 
+// Vector forms for the tiled G layout: one thread per (pixel, group of V = 4 or 2 consecutive channels); every tap is
+// one 16- or 8-byte load (the channels of a tap are contiguous inside a float4 column because C % V == 0).
+template <int V, bool kFwd>
+__global__ void __launch_bounds__(256) k_gather_vec(const float* __restrict__ G, const float* __restrict__ const3,
+                                                    const float* __restrict__ c3, float* __restrict__ out, int H, int W,
+                                                    int C, int n3p, long long total) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int CV = C / V;
+  const int cv = (int)(idx % CV);
+  const long long p = idx / CV;
+  const int w = (int)(p % W), h = (int)((p / W) % H);
+  float acc[V];
+#pragma unroll
+  for (int v = 0; v < V; ++v) acc[v] = kFwd ? c3[cv * V + v] : 0.f;
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    const int dy = (tap / 3 - 1) * (kFwd ? 1 : -1), dx = (tap % 3 - 1) * (kFwd ? 1 : -1);
+    const int hh = h + dy, ww = w + dx;
+    if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
+    const long long pp = p + (long long)dy * W + dx;
+    const int col = tap * C + cv * V;
+    const float* g = G + (pp >> 7) * (128ll * n3p) + (long long)(col >> 2) * 512 + (pp & 127) * 4 + (col & 3);
+    if constexpr (V == 4) {
+      float4 t = __ldg(reinterpret_cast<const float4*>(g));
+      if constexpr (kFwd) {      // same association as the scalar kernel: acc += (G + const3)
+        const float4 k = __ldg(reinterpret_cast<const float4*>(const3 + col));
+        t.x += k.x; t.y += k.y; t.z += k.z; t.w += k.w;
+      }
+      acc[0] += t.x; acc[1] += t.y; acc[2] += t.z; acc[3] += t.w;
+    } else {
+      float2 t = __ldg(reinterpret_cast<const float2*>(g));
+      if constexpr (kFwd) {
+        const float2 k = __ldg(reinterpret_cast<const float2*>(const3 + col));
+        t.x += k.x; t.y += k.y;
+      }
+      acc[0] += t.x; acc[1] += t.y;
+    }
+  }
+  if constexpr (V == 4) reinterpret_cast<float4*>(out)[idx] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  else reinterpret_cast<float2*>(out)[idx] = make_float2(acc[0], acc[1]);
+}
+
 int g_cluster = 1;
 int g_num_sms = 0;
 int g_pair_mode = 3;    // 3: K-pipelined kernel k_nn_tc4 (default), 0: 8-worker-warp single-CTA kernel, 1: CTA-pair kernel (cta_group::2), 2: legacy 4-worker-warp kernel
@@ -1568,7 +1611,8 @@ void nn_tc_forward(const NNWeightsTC& w, const NNScratchTC& sc, const float* sta
   g_next_flops = 2.0 * (double)M * (9.0 * (C / 2) * kF + (double)kF * kF + 9.0 * kF * C);   // conv MACs x 2, unpadded
   const bool tiled = run_tc<false>(prm, s);
   const long long total = M * C;
-  if (tiled) k_gather_fwd<true><<<cdiv(total, 256), 256, 0, s>>>(sc.G, w.const3, w.c3, r, H, W, C, w.fwd.n3p, total);
+  if (tiled && C % 4 == 0) k_gather_vec<4, true><<<cdiv(total / 4, 256), 256, 0, s>>>(sc.G, w.const3, w.c3, r, H, W, C, w.fwd.n3p, total / 4);
+  else if (tiled) k_gather_fwd<true><<<cdiv(total, 256), 256, 0, s>>>(sc.G, w.const3, w.c3, r, H, W, C, w.fwd.n3p, total);
   else k_gather_fwd<false><<<cdiv(total, 256), 256, 0, s>>>(sc.G, w.const3, w.c3, r, H, W, C, w.fwd.n3p, total);
   ASEP_LAUNCH_CHECK();
 }
@@ -1588,7 +1632,9 @@ void nn_tc_backward(const NNWeightsTC& w, const NNScratchTC& sc, const float* gr
   g_next_flops = 2.0 * (double)M * (9.0 * (C / 2) * kF + (double)kF * kF + 9.0 * kF * C);
   const bool tiled = run_tc<true>(prm, s);
   const long long total = M * (C / 2);
-  if (tiled) k_gather_bwd<true><<<cdiv(total, 256), 256, 0, s>>>(sc.G, gxb, H, W, C / 2, w.bwd.n3p, total);
+  if (tiled && (C / 2) % 4 == 0) k_gather_vec<4, false><<<cdiv(total / 4, 256), 256, 0, s>>>(sc.G, nullptr, nullptr, gxb, H, W, C / 2, w.bwd.n3p, total / 4);
+  else if (tiled && (C / 2) % 2 == 0) k_gather_vec<2, false><<<cdiv(total / 2, 256), 256, 0, s>>>(sc.G, nullptr, nullptr, gxb, H, W, C / 2, w.bwd.n3p, total / 2);
+  else if (tiled) k_gather_bwd<true><<<cdiv(total, 256), 256, 0, s>>>(sc.G, gxb, H, W, C / 2, w.bwd.n3p, total);
   else k_gather_bwd<false><<<cdiv(total, 256), 256, 0, s>>>(sc.G, gxb, H, W, C / 2, w.bwd.n3p, total);
   ASEP_LAUNCH_CHECK();
 }

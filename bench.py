@@ -14,7 +14,7 @@ the same run and reported under ``"basis"``.
 * ``e2e``    : the same metric through the public API (``Glow.log_prob`` -> C ABI) with the batch in
                PINNED HOST memory: H2D copy + compute + D2H of the [B] log-probabilities inside the
                timed region, every step.
-* ``roofline``: the dominant kernel (k_nn_tc, the fused tcgen05 coupling network): algorithmic conv
+* ``roofline``: the dominant kernel (k_nn_tc4, the fused tcgen05 coupling network): algorithmic conv
                FLOPs of the recorded launches / their summed CUDA-event time (events on the launching
                stream, recorded during the timed region) vs the measured sustained bf16 peak.
 * ``cpu_baseline`` / ``--impl reference``: the reference-faithful CPU graph (oracle/glow_oracle.py,
@@ -394,7 +394,7 @@ def run_ours(args):
     # ---- roofline of the dominant kernel
     k_ms, k_launches, k_flops = prof
     achieved = k_flops / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
-    roofline = {"bound": "tensor", "kernel": "k_nn_tc<fwd> (fused conv3x3 -> conv1x1 -> conv3x3 coupling network)",
+    roofline = {"bound": "tensor", "kernel": "k_nn_tc4<fwd> (fused conv3x3 -> conv1x1 -> conv3x3 coupling network, K-pipelined tcgen05)",
                 "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                 "frac": achieved / peaks["bf16_sustained"], "peak_source": f"{peaks['source']} sustained bf16 (kernel timed inside a long step)",
                 "traffic": None, "launches": k_launches, "avg_launch_ms": k_ms / max(1, k_launches),

@@ -194,8 +194,9 @@ int asep_conv_profile_read(double* total_ms, int64_t* launches, double* flops);
 /* Number of CTAs (1, 2 or 4) of a thread-block cluster that share each weight tile of the tcgen05 coupling
  * kernel through TMA multicast.  Tuning knob; results are identical for every value. */
 int asep_tc_set_cluster(int cluster_size);
-/* 1 selects the CTA-pair form of the coupling kernel (tcgen05 cta_group::2, M = 256 across the two SMs of a TPC,
- * each CTA streams half of every weight image); 0 the single-CTA form.  Results are identical. */
+/* Variant of the tcgen05 coupling kernel: 3 (default) the K-pipelined single-CTA kernel k_nn_tc4; 0 the serial
+ * 8-worker-warp kernel k_nn_tc2; 1 its CTA-pair form (tcgen05 cta_group::2, M = 256 across the two SMs of a TPC,
+ * each CTA streams half of every weight image); 2 the first 4-worker-warp kernel.  Results are bit-identical. */
 int asep_tc_set_pair_mode(int on);
 
 /* Measurement aid (bench.py roofline leg): while on, every launch of the tcgen05 coupling kernel is bracketed
