@@ -138,6 +138,12 @@ GlowModel::~GlowModel() {
   for (auto& kv : params_)
     if (kv.second.dev && !kv.second.in_flat) cudaFree(kv.second.dev);
   if (score_buf_) cudaFree(score_buf_);
+  if (tgraph_.exec) cudaGraphExecDestroy(tgraph_.exec);
+  if (tg_stream_) cudaStreamDestroy(tg_stream_);
+  if (tg_ev_in_) cudaEventDestroy(tg_ev_in_);
+  if (tg_ev_out_) cudaEventDestroy(tg_ev_out_);
+  for (void* p : {(void*)tg_x_, (void*)tg_noise_, (void*)tg_grads_, (void*)tg_loss_})
+    if (p) cudaFree(p);
   for (void* p : {(void*)theta_, (void*)adam_m_, (void*)adam_u_, (void*)tq2_, (void*)tdc2_, (void*)tr3_, (void*)ts3_,
                   (void*)tstats_, (void*)ldc_, (void*)ld_total_, (void*)tdc1_, (void*)td1_, (void*)da1_, (void*)da2_,
                   (void*)dgp2_, (void*)dgp1_, (void*)dcol_})

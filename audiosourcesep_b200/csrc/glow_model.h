@@ -121,6 +121,23 @@ class GlowModel {
   __nv_bfloat16 *da1_ = nullptr, *da2_ = nullptr, *dgp2_ = nullptr, *dgp1_ = nullptr, *dcol_ = nullptr;   // bf16 dumps / im2col
   long long dump_rows_ = 0;
   void ensure_train_dumps(long long rows);
+  // The train step is ~5800 small launches at the reference's batch size (32): after a first eager call (which sizes
+  // every scratch buffer) it is captured once per (N, global_batch, sigma, noisy) into a CUDA graph that works on
+  // private staging buffers and is replayed on a private stream.
+  void train_grads_body(const float* x, const float* noise, float sigma, int N, int global_batch, float* grads,
+                        float* loss, cudaStream_t s);
+  struct TrainGraph {
+    cudaGraphExec_t exec = nullptr;
+    int N = 0, global_batch = 0;
+    float sigma = 0.f;
+    bool noisy = false;
+    long long launches = 0;
+  } tgraph_;
+  float *tg_x_ = nullptr, *tg_noise_ = nullptr, *tg_grads_ = nullptr, *tg_loss_ = nullptr;
+  size_t tg_x_cap_ = 0;
+  cudaStream_t tg_stream_ = nullptr;
+  cudaEvent_t tg_ev_in_ = nullptr, tg_ev_out_ = nullptr;
+  long long tg_calls_ = 0;      // largest batch size that has run eagerly (its scratch exists)
   double *tstats_ = nullptr, *ldc_ = nullptr, *ld_total_ = nullptr;
   bool training_ = false;
 

@@ -116,6 +116,65 @@ void GlowModel::train_grads(const float* x, const float* noise, float sigma, int
   ASEP_CHECK(training_, ASEP_ERR_STATE, "asep_glow_enable_training() has not been called");
   ASEP_CHECK(N >= 1 && global_batch >= N, ASEP_ERR_BAD_ARG, "bad batch sizes (local %d, global %d)", N, global_batch);
   CUDA_CHECK(cudaSetDevice(device_));
+  const bool use_graph = precision_ == ASEP_PREC_BF16 && !nn_tc_profile_enabled() && getenv("ASEP_NO_GRAPH") == nullptr &&
+                         getenv("ASEP_TC_DBG_TIMING") == nullptr;
+  if (!use_graph || N > tg_calls_) {             // the first call of a batch size runs eagerly: it allocates the scratch
+    train_grads_body(x, noise, sigma, N, global_batch, grads, loss, s);
+    if (use_graph) tg_calls_ = N;                 // (largest batch whose scratch exists)
+    return;
+  }
+  const size_t nx = (size_t)N * cfg_.H * cfg_.W * cfg_.C;
+  if (tg_stream_ == nullptr) {
+    CUDA_CHECK(cudaStreamCreateWithFlags(&tg_stream_, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaEventCreateWithFlags(&tg_ev_in_, cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventCreateWithFlags(&tg_ev_out_, cudaEventDisableTiming));
+    CUDA_CHECK(cudaMalloc(&tg_grads_, (size_t)n_trainable_ * sizeof(float)));
+    CUDA_CHECK(cudaMalloc(&tg_loss_, sizeof(float)));
+  }
+  if (nx > tg_x_cap_) {
+    CUDA_CHECK(cudaDeviceSynchronize());
+    if (tg_x_) cudaFree(tg_x_);
+    if (tg_noise_) cudaFree(tg_noise_);
+    CUDA_CHECK(cudaMalloc(&tg_x_, nx * sizeof(float)));
+    CUDA_CHECK(cudaMalloc(&tg_noise_, nx * sizeof(float)));
+    tg_x_cap_ = nx;
+    if (tgraph_.exec) { cudaGraphExecDestroy(tgraph_.exec); tgraph_.exec = nullptr; }     // staging pointers changed
+  }
+  // inputs -> staging (on the caller's stream), then the private stream takes over
+  CUDA_CHECK(cudaMemcpyAsync(tg_x_, x, nx * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  if (noise) CUDA_CHECK(cudaMemcpyAsync(tg_noise_, noise, nx * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  CUDA_CHECK(cudaEventRecord(tg_ev_in_, s));
+  CUDA_CHECK(cudaStreamWaitEvent(tg_stream_, tg_ev_in_, 0));
+  TrainGraph& g = tgraph_;
+  if (g.exec == nullptr || g.N != N || g.global_batch != global_batch || g.sigma != sigma || g.noisy != (noise != nullptr)) {
+    if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+    cudaGraph_t graph = nullptr;
+    const long long c0 = g_launch_count.load();
+    CUDA_CHECK(cudaStreamBeginCapture(tg_stream_, cudaStreamCaptureModeRelaxed));
+    try {
+      train_grads_body(tg_x_, noise ? tg_noise_ : nullptr, sigma, N, global_batch, tg_grads_, tg_loss_, tg_stream_);
+    } catch (...) {
+      cudaStreamEndCapture(tg_stream_, &graph);
+      if (graph) cudaGraphDestroy(graph);
+      throw;
+    }
+    CUDA_CHECK(cudaStreamEndCapture(tg_stream_, &graph));
+    g.launches = g_launch_count.load() - c0;
+    CUDA_CHECK(cudaGraphInstantiate(&g.exec, graph, 0));
+    CUDA_CHECK(cudaGraphDestroy(graph));
+    g.N = N; g.global_batch = global_batch; g.sigma = sigma; g.noisy = noise != nullptr;
+  } else {
+    g_launch_count.fetch_add(g.launches);      // the replay launches the same kernels
+  }
+  CUDA_CHECK(cudaGraphLaunch(g.exec, tg_stream_));
+  CUDA_CHECK(cudaMemcpyAsync(grads, tg_grads_, (size_t)n_trainable_ * sizeof(float), cudaMemcpyDeviceToDevice, tg_stream_));
+  CUDA_CHECK(cudaMemcpyAsync(loss, tg_loss_, sizeof(float), cudaMemcpyDeviceToDevice, tg_stream_));
+  CUDA_CHECK(cudaEventRecord(tg_ev_out_, tg_stream_));
+  CUDA_CHECK(cudaStreamWaitEvent(s, tg_ev_out_, 0));
+}
+
+void GlowModel::train_grads_body(const float* x, const float* noise, float sigma, int N, int global_batch, float* grads,
+                                 float* loss, cudaStream_t s) {
   const int L = cfg_.L, K = cfg_.K, F = cfg_.n_filters;
   const float gs = -1.0f / (float)global_batch;      // loss = -sum log_prob / global_batch (train_glow.py:30-31)
   ensure_work(N, true);

@@ -1526,6 +1526,7 @@ void nn_tc_profile(int on) {
     g_prof_flops = 0.0;
   }
 }
+bool nn_tc_profile_enabled() { return g_prof_on; }
 void nn_tc_profile_read(double* total_ms, long long* launches, double* flops) {
   double ms = 0.0;
   for (auto& r : g_prof_recs) {

@@ -57,6 +57,7 @@ void nn_tc_set_pair_mode(int on);
 int nn_tc_get_pair_mode();
 // CUDA-event timing of every tensor-core kernel launch (on its own stream) while switched on.
 void nn_tc_profile(int on);
+bool nn_tc_profile_enabled();
 void nn_tc_profile_read(double* total_ms, long long* launches, double* flops);
 
 }  // namespace asep

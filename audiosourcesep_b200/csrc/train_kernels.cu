@@ -477,28 +477,39 @@ __global__ void __launch_bounds__(256) k_im2col_xb(const float* __restrict__ sta
 // S3[tap][c] += sum_{p: p+off(tap) in bounds} gr[p][c].  One block per image row: the row's channel sums over all
 // columns, the first column and the last column give every tap's contribution (dx = -1 drops w = 0, dx = +1 drops
 // w = W-1; dy = -1 drops the row h = 0, dy = +1 the row h = H-1).
-__global__ void __launch_bounds__(128) k_s3(const float* __restrict__ gr, float* __restrict__ S3, int H, int W, int C) {
-  const int h = blockIdx.x % H;
-  const float* row = gr + (size_t)blockIdx.x * W * C;
+__global__ void __launch_bounds__(128) k_s3(const float* __restrict__ gr, float* __restrict__ S3, int H, int W, int C,
+                                            int num_rows) {
   __shared__ float part[128];
-  // threads: c = t % C, w-lane = t / C
+  // threads: c = t % C, w-lane = t / C; a block walks image rows blockIdx.x, +gridDim.x, ... and keeps the nine
+  // per-tap sums of its rows in registers (threads < C), so each block issues 9*C atomics in total
   const int c = threadIdx.x % C, wl = threadIdx.x / C, wstep = blockDim.x / C;
-  float s = 0.f;
-  if (wl < wstep)
-    for (int w = wl; w < W; w += wstep) s += row[(size_t)w * C + c];
-  part[threadIdx.x] = s;
-  __syncthreads();
-  if (threadIdx.x < C) {
-    float all = 0.f;
-    for (int g = 0; g < wstep; ++g) all += part[g * C + threadIdx.x];
-    const float first = row[threadIdx.x], last = row[(size_t)(W - 1) * C + threadIdx.x];
+  float acc[9];
 #pragma unroll
-    for (int tap = 0; tap < 9; ++tap) {
-      const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-      if (h + dy < 0 || h + dy >= H) continue;
-      const float v = all - (dx == -1 ? first : 0.f) - (dx == 1 ? last : 0.f);
-      atomicAdd(S3 + tap * C + threadIdx.x, v);
+  for (int tap = 0; tap < 9; ++tap) acc[tap] = 0.f;
+  for (int r = blockIdx.x; r < num_rows; r += gridDim.x) {
+    const int h = r % H;
+    const float* row = gr + (size_t)r * W * C;
+    float s = 0.f;
+    if (wl < wstep)
+      for (int w = wl; w < W; w += wstep) s += row[(size_t)w * C + c];
+    __syncthreads();
+    part[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x < C) {
+      float all = 0.f;
+      for (int g = 0; g < wstep; ++g) all += part[g * C + threadIdx.x];
+      const float first = row[threadIdx.x], last = row[(size_t)(W - 1) * C + threadIdx.x];
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+        if (h + dy < 0 || h + dy >= H) continue;
+        acc[tap] += all - (dx == -1 ? first : 0.f) - (dx == 1 ? last : 0.f);
+      }
     }
+  }
+  if (threadIdx.x < C) {
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) atomicAdd(S3 + tap * C + threadIdx.x, acc[tap]);
   }
 }
 
@@ -579,32 +590,47 @@ __global__ void __launch_bounds__(256) k_build_tc_images(const StepTrainPtrs sp,
   }
 }
 
-// bias1 = c1, bias2 = c2 + b1' K2, const3[tap][c] = sum_k b2'[k] K3[tap][k][c], c3
+// bias1 = c1, bias2 = c2 + b1' K2, const3[tap][c] = sum_k b2'[k] K3[tap][k][c], c3.
+// grid 16 blocks x 512 threads = (16 k-groups x 32 outputs): every thread reduces a 32-long k slice, the 16 slices are
+// combined in a fixed order through shared memory (fp32; the host twin accumulates in double, difference ~1e-7 relative).
 __global__ void __launch_bounds__(512) k_build_tc_biases(const StepTrainPtrs sp, float* __restrict__ bias1, float* __restrict__ bias2,
                                                          float* __restrict__ const3, float* __restrict__ c3) {
+  __shared__ float part[16][33];
   const int F = sp.F, C = sp.C, t = threadIdx.x;
-  // fp32 with four interleaved partial sums (the host twin accumulates in double; the difference is ~1e-7 relative)
-  for (int n = t; n < F; n += blockDim.x) {
-    bias1[n] = sp.c1[n];
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    for (int k = 0; k < F; k += 4) {
-      a0 = fmaf(sp.b1f[k], sp.k2[(size_t)k * F + n], a0);
-      a1 = fmaf(sp.b1f[k + 1], sp.k2[(size_t)(k + 1) * F + n], a1);
-      a2 = fmaf(sp.b1f[k + 2], sp.k2[(size_t)(k + 2) * F + n], a2);
-      a3 = fmaf(sp.b1f[k + 3], sp.k2[(size_t)(k + 3) * F + n], a3);
+  const int ol = t & 31, kg = t >> 5;
+  {
+    const int n = blockIdx.x * 32 + ol;                 // 16 blocks x 32 = 512 = F columns of K2
+    float a = 0.f;
+    if (n < F)
+      for (int k = kg; k < F; k += 16) a = fmaf(sp.b1f[k], sp.k2[(size_t)k * F + n], a);
+    part[kg][ol] = a;
+    __syncthreads();
+    if (kg == 0 && n < F) {
+      float sum = 0.f;
+#pragma unroll
+      for (int g = 0; g < 16; ++g) sum += part[g][ol];
+      bias2[n] = sp.c2[n] + sum;
+      bias1[n] = sp.c1[n];
     }
-    bias2[n] = sp.c2[n] + ((a0 + a1) + (a2 + a3));
+    __syncthreads();
   }
-  for (int i = t; i < 9 * C; i += blockDim.x) {
-    const int tap = i / C, c = i % C;
-    float a0 = 0.f, a1 = 0.f;
-    for (int k = 0; k < F; k += 2) {
-      a0 = fmaf(sp.b2f[k], sp.k3[((size_t)tap * F + k) * C + c], a0);
-      a1 = fmaf(sp.b2f[k + 1], sp.k3[((size_t)tap * F + k + 1) * C + c], a1);
+  {
+    const int i = blockIdx.x * 32 + ol;                 // 9*C <= 144 outputs: blocks 0..4
+    float a = 0.f;
+    if (i < 9 * C) {
+      const int tap = i / C, c = i % C;
+      for (int k = kg; k < F; k += 16) a = fmaf(sp.b2f[k], sp.k3[((size_t)tap * F + k) * C + c], a);
     }
-    const3[i] = a0 + a1;
+    part[kg][ol] = a;
+    __syncthreads();
+    if (kg == 0 && i < 9 * C) {
+      float sum = 0.f;
+#pragma unroll
+      for (int g = 0; g < 16; ++g) sum += part[g][ol];
+      const3[i] = sum;
+    }
   }
-  if (t < C) c3[t] = sp.c3[t];
+  if (blockIdx.x == 0 && t < C) c3[t] = sp.c3[t];
 }
 
 }  // namespace
@@ -748,7 +774,7 @@ void launch_im2col_xb(const float* state, __nv_bfloat16* X9, int N, int H, int W
 
 void launch_s3(const float* gr, float* S3, int N, int H, int W, int C, cudaStream_t s) {
   ASEP_CHECK(C <= 128 && 128 % C == 0, ASEP_ERR_UNSUPPORTED, "s3: channel count %d", C);
-  k_s3<<<N * H, 128, 0, s>>>(gr, S3, H, W, C);
+  k_s3<<<std::min(N * H, 296), 128, 0, s>>>(gr, S3, H, W, C, N * H);
   ASEP_LAUNCH_CHECK();
 }
 
@@ -764,7 +790,7 @@ void launch_build_tc_step(const StepTrainPtrs& sp, __nv_bfloat16* fwd_img, __nv_
   dim3 grid(296, 2);
   k_build_tc_images<<<grid, 256, 0, s>>>(sp, fwd_img, bwd_img, k1p_f, n3p_f, k1p_b, n3p_b);
   ASEP_LAUNCH_CHECK();
-  k_build_tc_biases<<<1, 512, 0, s>>>(sp, bias1, bias2, const3, c3);
+  k_build_tc_biases<<<16, 512, 0, s>>>(sp, bias1, bias2, const3, c3);   // F = 512 (checked by nn_tc_prepare)
   ASEP_LAUNCH_CHECK();
 }
 
