@@ -374,7 +374,7 @@ def run_ours(args):
             last[0] = tg.distributed_train_step(tm, opt, xt, tb * world)
 
         nst = max(2, args.steps // 3)
-        t_ms, t_launches, _ = timed_loop(step_train, nst, 1)
+        t_ms, t_launches, _ = timed_loop(step_train, nst, 3)     # eager (sizes the scratch), graph capture, first replay
         train = {"metric": "glow_train_samples_per_s", "value": world * tb * nst / (t_ms * 1e-3), "unit": "samples/s",
                  "steps_per_s": nst / (t_ms * 1e-3), "per_gpu_batch": tb, "global_batch": tb * world, "dtype": "f32" if args.train_fp32 else "bf16",
                  "ms_per_step": t_ms / nst, "gpu_launches": t_launches, "allreduce_bytes_per_step": int(tm.num_trainable * 4),
@@ -382,7 +382,8 @@ def run_ours(args):
                  "loss": float(last[0].item()), "loss_finite": bool(torch.isfinite(last[0]).all()),
                  "note": ("CUDA-core fp32 exact mode" if args.train_fp32 else
                           "tcgen05 forward / data-gradient / weight-gradient GEMMs (bf16 operands, fp32 accumulate), "
-                          "fp32 master weights + Adamax, tile images rebuilt on the device every step")
+                          "fp32 master weights + Adamax, tile images rebuilt on the device every step, gradient pass replayed as a CUDA graph; "
+                          "the loss value is that of the reference's own (quirk Q1/Q7) initialisation on synthetic patches, see DESIGN.md section 5")
                          + "; NCCL all-reduce of the flat gradient vector"}
         del tm
 
