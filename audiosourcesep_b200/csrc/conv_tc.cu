@@ -39,6 +39,7 @@ struct ConvParams {
   const float* bias;
   const float* add;
   float* out;
+  __nv_bfloat16* out_bf16;   // optional bf16 copy of `out` (the next convolution's operand when no norm intervenes)
   double* stats;    // optional [N, Cout, 2]: per-(image, channel) sum and sum of squares of `out` (instance-norm statistics)
   int Cout, kpanels, taps, dil, H, W, rows_per_tile, tiles_per_img, num_units;
   int nunit;        // work units per pixel tile: Cout is processed as `nunit` column groups of `ncols` (<= 256) channels
@@ -163,6 +164,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
           o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
           if (prm.add) { o.x += a4[i].x; o.y += a4[i].y; o.z += a4[i].z; o.w += a4[i].w; }
           *reinterpret_cast<float4*>(prm.out + (p0 + r) * prm.Cout + col) = o;
+          if (prm.out_bf16)
+            *reinterpret_cast<uint2*>(prm.out_bf16 + (p0 + r) * prm.Cout + col) = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
           s1.x += o.x; s1.y += o.y; s1.z += o.z; s1.w += o.w;
           s2.x = fmaf(o.x, o.x, s2.x); s2.y = fmaf(o.y, o.y, s2.y); s2.z = fmaf(o.z, o.z, s2.z); s2.w = fmaf(o.w, o.w, s2.w);
         }
@@ -208,6 +211,146 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
   if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Swapped-operand form for Cout = 128.  A tcgen05.mma with M = 128 costs max(~100, N/2) cycles, so an N = 128
+// instruction runs the tensor pipe at 64 %.  (Measured gain over the plain form is small, ~2 %: these layers are bound by
+// the ~64 B/cycle at which an SM ingests operands from L2, not by the tensor pipe.  A cta_group::2 variant that halves
+// the weight ingest per SM was bit-exact but 1.8-2.3x slower and is not kept.)  Here the WEIGHTS are the M = 128 operand (A = [Cout x 64] tile image) and
+// 256 PIXELS are N (B = the TMA activation box, K-major rows of 64 channels): D[co][pixel] with lanes = output
+// channels.  An epilogue thread then owns one channel: stores / residual loads of one pixel are 128 contiguous bytes
+// across the warp (no transpose), the bias is a per-thread scalar and the instance-norm statistics are per-thread sums.
+constexpr int kSwPixels = 256;
+constexpr int kSwStageBytes = 128 * 128 + kSwPixels * 128;       // weights 16 KB + activations 32 KB
+
+__global__ void __launch_bounds__(kThreads, 1) k_conv_tc_sw(const __grid_constant__ CUtensorMap tmap, const ConvParams prm) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + prm.stages * kSwStageBytes);
+  const int S = prm.stages;
+  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[S]);
+  const uint32_t accr0 = smem_u32(&bars[2 * S]), acce0 = smem_u32(&bars[2 * S + 2]);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(&bars[2 * S + 4]);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < S; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(accr0 + 8 * i, 1); mbar_init(acce0 + 8 * i, 4); }
+    fence_barrier_init();
+    tma_prefetch_desc(&tmap);
+  }
+  if (warp == 2) tmem_alloc(smem_u32(tmem_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int kiters = prm.taps * prm.kpanels;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int unit = blockIdx.x; unit < prm.num_units; unit += gridDim.x) {
+        const int n = unit / prm.tiles_per_img;
+        const int h0 = (unit % prm.tiles_per_img) * prm.rows_per_tile;
+        const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(prm.wimg);
+        for (int tap = 0; tap < prm.taps; ++tap) {
+          const int dy = prm.taps == 9 ? (tap / 3 - 1) * prm.dil : 0;
+          const int dx = prm.taps == 9 ? (tap % 3 - 1) * prm.dil : 0;
+          for (int kp = 0; kp < prm.kpanels; ++kp) {
+            mbar_wait(empty0 + 8 * stage, phase ^ 1);
+            const uint32_t fb = full0 + 8 * stage;
+            const uint32_t sa = smem_u32(smem + stage * kSwStageBytes);
+            mbar_expect_tx(fb, (uint32_t)kSwStageBytes);
+            bulk_g2s(sa, wsrc, 128 * 128, fb);
+            tma_load_4d(sa + 128 * 128, &tmap, kp * 64, dx, h0 + dy, n, fb);
+            wsrc += 128 * 128;
+            if (++stage == (uint32_t)S) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      constexpr uint32_t idesc = make_idesc(kSwPixels);
+      int it = 0;
+      for (int unit = blockIdx.x; unit < prm.num_units; unit += gridDim.x, ++it) {
+        const int buf = it & 1;
+        mbar_wait(acce0 + 8 * buf, ((uint32_t)(it >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 256);
+        for (int ki = 0; ki < kiters; ++ki) {
+          mbar_wait(full0 + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * kSwStageBytes);
+          const uint64_t da = make_desc(sa);                    // weights: 128 rows (output channels) x 64 k
+          const uint64_t db = make_desc(sa + 128 * 128);        // activations: 256 rows (pixels) x 64 k
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (ki | k) != 0);
+          umma_commit(empty0 + 8 * stage);
+          if (++stage == (uint32_t)S) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(accr0 + 8 * buf);
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int co = quarter * 32 + lane;                         // this thread's output channel
+    const float bias = prm.bias ? __ldg(prm.bias + co) : 0.f;
+    int it = 0;
+    for (int unit = blockIdx.x; unit < prm.num_units; unit += gridDim.x, ++it) {
+      const int buf = it & 1;
+      mbar_wait(accr0 + 8 * buf, (uint32_t)(it >> 1) & 1u);
+      tc_fence_after();
+      const long long p0 = (long long)unit * kSwPixels;
+      const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * 256);
+      float s1 = 0.f, s2 = 0.f;
+      for (int j = 0; j < kSwPixels / 32; ++j) {
+        uint32_t v[32];
+        tmem_ld32(t_lane + (uint32_t)(j * 32), v);
+        const long long pj = p0 + j * 32;
+        float a[32];
+        if (prm.add) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) a[i] = prm.add[(pj + i) * 128 + co];
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float o = __uint_as_float(v[i]) + bias;
+          if (prm.add) o += a[i];
+          prm.out[(pj + i) * 128 + co] = o;
+          s1 += o;
+          s2 = fmaf(o, o, s2);
+          v[i] = __float_as_uint(o);
+        }
+        if (prm.out_bf16) {
+          // pack channel pairs: the even lane stores (co, co+1) of pixel i, the odd lane those of pixel i+1
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const bool odd = lane & 1;
+            const float mine = __uint_as_float(odd ? v[i + 1] : v[i]);          // even: pixel i, odd: pixel i+1
+            const float send = __uint_as_float(odd ? v[i] : v[i + 1]);          // what the partner lane needs
+            const float got = __shfl_xor_sync(0xffffffffu, send, 1);
+            const uint32_t pk = (lane & 1) ? pack_bf16(got, mine) : pack_bf16(mine, got);
+            *reinterpret_cast<uint32_t*>(prm.out_bf16 + (pj + i + (lane & 1)) * 128 + (co & ~1)) = pk;
+          }
+        }
+      }
+      if (prm.stats) {
+        double* st = prm.stats + ((size_t)(unit / prm.tiles_per_img) * 128 + co) * 2;
+        atomicAdd(st, (double)s1);
+        atomicAdd(st + 1, (double)s2);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acce0 + 8 * buf);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
 // ------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -226,17 +369,17 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
-std::map<std::tuple<const void*, int, int, int, int>, CUtensorMap> g_maps;
+std::map<std::tuple<const void*, int, int, int, int, int>, CUtensorMap> g_maps;
 
-const CUtensorMap& activation_map(const __nv_bfloat16* x, int N, int H, int W, int C) {
-  auto key = std::make_tuple((const void*)x, N, H, W, C);
+const CUtensorMap& activation_map(const __nv_bfloat16* x, int N, int H, int W, int C, int pixels = kTileM) {
+  auto key = std::make_tuple((const void*)x, N, H, W, C, pixels);
   auto it = g_maps.find(key);
   if (it != g_maps.end()) return it->second;
   if (g_maps.size() > 4096) g_maps.clear();
   CUtensorMap m;
   const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
   const cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-  const cuuint32_t box[4] = {64, (cuuint32_t)W, (cuuint32_t)(kTileM / W), 1};
+  const cuuint32_t box[4] = {64, (cuuint32_t)W, (cuuint32_t)(pixels / W), 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(x), dims, strides, box,
                            estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -295,7 +438,7 @@ void conv_tc_release(ConvWeightsTC& w) {
 }
 
 void conv_tc_forward(const ConvWeightsTC& w, const __nv_bfloat16* xin, const float* add, float* out, int N, int H,
-                     int W, cudaStream_t s, double* stats) {
+                     int W, cudaStream_t s, double* stats, __nv_bfloat16* out_bf16) {
   if (N == 0) return;
   ASEP_CHECK(conv_tc_supported(w.Cin, w.Cout, H, W), ASEP_ERR_UNSUPPORTED,
              "tcgen05 conv: unsupported shape Cin=%d Cout=%d H=%d W=%d", w.Cin, w.Cout, H, W);
@@ -304,8 +447,9 @@ void conv_tc_forward(const ConvWeightsTC& w, const __nv_bfloat16* xin, const flo
     CUDA_CHECK(cudaGetDevice(&dev));
     CUDA_CHECK(cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev));
   }
+  const bool swapped = w.Cout == 128 && kSwPixels % W == 0 && H % (kSwPixels / W) == 0 && getenv("ASEP_CONV_NO_SWAP") == nullptr;
   ConvParams prm{};
-  prm.wimg = w.img; prm.bias = w.bias; prm.add = add; prm.out = out; prm.stats = stats;
+  prm.wimg = w.img; prm.bias = w.bias; prm.add = add; prm.out = out; prm.stats = stats; prm.out_bf16 = out_bf16;
   if (stats) CUDA_CHECK(cudaMemsetAsync(stats, 0, (size_t)N * w.Cout * 2 * sizeof(double), s));
   prm.Cout = w.Cout; prm.kpanels = w.Cin / 64; prm.taps = w.ksize * w.ksize; prm.dil = w.dil;
   prm.H = H; prm.W = W; prm.rows_per_tile = kTileM / W; prm.tiles_per_img = H / prm.rows_per_tile;
@@ -320,9 +464,16 @@ void conv_tc_forward(const ConvWeightsTC& w, const __nv_bfloat16* xin, const flo
   static bool attr_set = false;
   if (!attr_set) {
     CUDA_CHECK(cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_CHECK(cudaFuncSetAttribute(k_conv_tc_sw, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  const CUtensorMap& tmap = activation_map(xin, N, H, W, w.Cin);
+  if (swapped) {
+    prm.rows_per_tile = kSwPixels / W;
+    prm.tiles_per_img = H / prm.rows_per_tile;
+    prm.num_units = N * prm.tiles_per_img;
+    prm.stages = 4;
+  }
+  const CUtensorMap& tmap = activation_map(xin, N, H, W, w.Cin, swapped ? kSwPixels : kTileM);
   const int grid = std::min(prm.num_units, g_sms);
   ProfRec rec{};
   if (g_prof_on) {
@@ -330,7 +481,8 @@ void conv_tc_forward(const ConvWeightsTC& w, const __nv_bfloat16* xin, const flo
     else { CUDA_CHECK(cudaEventCreate(&rec.a)); CUDA_CHECK(cudaEventCreate(&rec.b)); }
     CUDA_CHECK(cudaEventRecord(rec.a, s));
   }
-  k_conv_tc<<<grid, kThreads, smem_bytes, s>>>(tmap, prm);
+  if (swapped) k_conv_tc_sw<<<grid, kThreads, 4 * kSwStageBytes + 1024, s>>>(tmap, prm);
+  else k_conv_tc<<<grid, kThreads, smem_bytes, s>>>(tmap, prm);
   ASEP_LAUNCH_CHECK();
   if (g_prof_on) {
     CUDA_CHECK(cudaEventRecord(rec.b, s));

@@ -169,18 +169,21 @@ const float2* NcsnModel::norm_coef(const T& x, const std::string& name) {
 }
 
 __nv_bfloat16* NcsnModel::prep(const T& x, const float2* coef, bool elu) {
+  if (coef == nullptr && !elu && x.bf != nullptr) return x.bf;     // plain cast already done by the producing convolution
   __nv_bfloat16* y = new_bf(x.H, x.W, x.C);
   if (!dry_) launch_prep(x.p, coef, y, N_, x.H * x.W, x.C, elu ? 1 : 0, s_);
   return y;
 }
 
-NcsnModel::T NcsnModel::conv(const std::string& name, const __nv_bfloat16* xin, int H, int W, const float* add, bool stats) {
+NcsnModel::T NcsnModel::conv(const std::string& name, const __nv_bfloat16* xin, int H, int W, const float* add, bool stats,
+                             bool bf16_copy) {
   auto it = convs_.find(name);
   ASEP_CHECK(it != convs_.end(), ASEP_ERR_STATE, "convolution '%s' has no kernel parameter", name.c_str());
   const ConvWeightsTC& w = it->second;
   T out = new_t(H, W, w.Cout);
   if (stats) out.sums = static_cast<double*>(take((size_t)N_ * w.Cout * 2 * sizeof(double)));
-  if (!dry_) conv_tc_forward(w, xin, add, out.p, N_, H, W, s_, out.sums);
+  if (bf16_copy) out.bf = new_bf(H, W, w.Cout);
+  if (!dry_) conv_tc_forward(w, xin, add, out.p, N_, H, W, s_, out.sums, out.bf);
   return out;
 }
 
@@ -199,7 +202,7 @@ NcsnModel::T NcsnModel::res_block(const T& x, const std::string& name, int cout,
   }
   const bool pool = down && name.rfind("Res2_", 0) == 0;  // only the undilated 'down' block pools (score_network.py:141-144)
   // shortcut + output fused into the epilogue; an unpooled block output feeds norm layers (next block / RCU / MSF)
-  T o2 = conv(name + "/conv2", h2, x.H, x.W, sc, !pool);
+  T o2 = conv(name + "/conv2", h2, x.H, x.W, sc, !pool, !pool);
   if (!pool) return o2;
   // avg_pool2(shortcut) + avg_pool2(output) == avg_pool2(shortcut + output)
   T out = new_t(x.H / 2, x.W / 2, o2.C);
@@ -215,7 +218,7 @@ NcsnModel::T NcsnModel::rcu(T x, const std::string& prefix, int n_blocks, int n_
       const std::string sfx = "_" + std::to_string(i + 1) + "_" + std::to_string(j + 1);
       const float2* c = v1_ ? norm_coef(x, prefix + "/norm" + sfx) : nullptr;
       __nv_bfloat16* h = prep(x, c, false);
-      x = conv(prefix + "/conv" + sfx, h, x.H, x.W, j == n_stages - 1 ? residual.p : nullptr, v1_);
+      x = conv(prefix + "/conv" + sfx, h, x.H, x.W, j == n_stages - 1 ? residual.p : nullptr, v1_, !v1_);
     }
   }
   return x;

@@ -35,7 +35,8 @@ class NcsnModel {
 
  private:
   // fp32 NHWC activation (batch = N_); sums != NULL: per-(n,c) sum / sum of squares already accumulated by the producer
-  struct T { float* p = nullptr; int H = 0, W = 0, C = 0; double* sums = nullptr; };
+  // bf != NULL: bf16 copy written by the producer (saves the cast pass when no norm intervenes)
+  struct T { float* p = nullptr; int H = 0, W = 0, C = 0; double* sums = nullptr; __nv_bfloat16* bf = nullptr; };
   const NcsnParam& param(const std::string& name) const;
   bool has(const std::string& name) const { return params_.count(name) != 0; }
   void* take(size_t bytes);
@@ -43,7 +44,7 @@ class NcsnModel {
   __nv_bfloat16* new_bf(int H, int W, int C);
   const float2* norm_coef(const T& x, const std::string& name);
   __nv_bfloat16* prep(const T& x, const float2* coef, bool elu);
-  T conv(const std::string& name, const __nv_bfloat16* xin, int H, int W, const float* add, bool stats);
+  T conv(const std::string& name, const __nv_bfloat16* xin, int H, int W, const float* add, bool stats, bool bf16_copy = false);
   T res_block(const T& x, const std::string& name, int cout, bool down, int dilation);
   T rcu(T x, const std::string& prefix, int n_blocks, int n_stages);
   T crp(T x, const std::string& prefix);

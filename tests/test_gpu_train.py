@@ -161,3 +161,35 @@ def test_tensor_core_training_refreshes_tile_images_on_device():
     m.sync_host()                                   # host re-prepare from the trained parameters
     lp_host = float(m.log_prob(x).sum().item())
     assert abs(lp_dev - lp_host) <= 1e-4 * abs(lp_host), (lp_dev, lp_host)
+
+
+def test_graph_replay_of_the_gradient_pass_equals_the_eager_pass(monkeypatch):
+    """asep_glow_train_grads runs eagerly once per batch size, then captures the pass into a CUDA graph (private
+    stream + staging buffers) and replays it: every call must return the gradients of ITS inputs."""
+    from audiosourcesep_b200 import _lib
+    from audiosourcesep_b200.glow import Glow
+    cfg = GlowConfig(H=32, W=16, C=1, L=3, K=2, n_filters=512, minval=0.0, maxval=1.0)
+    p = init_glow_params(cfg, seed=8, mode="perturbed")
+    rng = np.random.default_rng(3)
+    xs = [torch.as_tensor(rng.uniform(0, 1, (4, 32, 16, 1)).astype(np.float32)).cuda() for _ in range(3)]
+    noise = torch.as_tensor(rng.standard_normal((4, 32, 16, 1)).astype(np.float32)).cuda()
+
+    monkeypatch.setenv("ASEP_NO_GRAPH", "1")
+    ref = Glow(cfg, p, precision=_lib.PREC_BF16)
+    ref.enable_training()
+    want = [tuple(t.clone() for t in ref.train_grads(x, global_batch=4)) for x in xs]
+    want_noisy = tuple(t.clone() for t in ref.train_grads(xs[0], global_batch=4, noise=noise, sigma=0.05))
+    monkeypatch.delenv("ASEP_NO_GRAPH")
+
+    m = Glow(cfg, p, precision=_lib.PREC_BF16)
+    m.enable_training()
+    m.train_grads(xs[0], global_batch=4)                       # eager call that sizes the scratch
+    for x, (g_ref, l_ref) in zip(xs, want):                    # capture, then two replays on different inputs
+        g, loss = m.train_grads(x, global_batch=4)
+        torch.cuda.synchronize()
+        assert float(loss.item()) == pytest.approx(float(l_ref.item()), rel=1e-6)
+        # weight-gradient GEMMs reduce with fp32 atomics (split-K): equal up to summation order
+        assert torch.allclose(g, g_ref, rtol=1e-4, atol=1e-6 * float(g_ref.abs().max())), float((g - g_ref).abs().max())
+    g, loss = m.train_grads(xs[0], global_batch=4, noise=noise, sigma=0.05)   # different key -> new capture
+    assert float(loss.item()) == pytest.approx(float(want_noisy[1].item()), rel=1e-6)
+    assert torch.allclose(g, want_noisy[0], rtol=1e-4, atol=1e-6 * float(want_noisy[0].abs().max()))
