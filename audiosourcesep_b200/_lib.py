@@ -19,6 +19,7 @@ LIB_PATH = os.path.join(_HERE, "libasep.so")
 
 PREC_FP32 = 0
 PREC_BF16 = 1
+PREC_BF16X3 = 2     # score networks: split-bf16 operands, three tcgen05 products per convolution
 
 
 class AsepError(RuntimeError):
@@ -93,6 +94,7 @@ _SIGNATURES = {
     "asep_ncsn_destroy": [_V],
     "asep_ncsn_set_param": [_V, ctypes.c_char_p, _P],
     "asep_ncsn_set_sigmas": [_V, _P],
+    "asep_ncsn_set_precision": [_V, _I],
     "asep_ncsn_prepare": [_V],
     "asep_ncsn_forward": [_V, _P, _P, _P, _V],
     "asep_basis_ncsn_inner": [_V, _V, _P, _P, _P, _I, _I, _F, _F, _F, _P, _P, _U64, _U64, _U64, _P, _P, _V],

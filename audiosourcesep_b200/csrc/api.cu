@@ -587,6 +587,15 @@ int asep_ncsn_set_sigmas(asep_ncsn_t h, const DLTensor* sigmas) {
   ASEP_API_END
 }
 
+int asep_ncsn_set_precision(asep_ncsn_t h, int precision) {
+  ASEP_API_BEGIN
+  ASEP_CHECK(h, ASEP_ERR_BAD_ARG, "NULL handle");
+  ASEP_CHECK(precision == ASEP_PREC_BF16 || precision == ASEP_PREC_BF16X3, ASEP_ERR_BAD_ARG,
+             "score networks run in ASEP_PREC_BF16 or ASEP_PREC_BF16X3 (got %d)", precision);
+  h->model->set_precision(precision == ASEP_PREC_BF16X3);
+  ASEP_API_END
+}
+
 int asep_ncsn_prepare(asep_ncsn_t h) {
   ASEP_API_BEGIN
   ASEP_CHECK(h, ASEP_ERR_BAD_ARG, "NULL handle");

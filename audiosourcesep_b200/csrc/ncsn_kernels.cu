@@ -104,7 +104,9 @@ __global__ void __launch_bounds__(512) k_in_coef(const double* __restrict__ sums
 
 // ---- y_bf16 = act(a*x+b).  grid (row slabs, N); a thread owns 8 channels - its 16 coefficients stay in registers -
 // and every (blockDim / (C/8))-th pixel of the slab, two pixels in flight.
-__device__ __forceinline__ uint4 prep8(const float4 v0, const float4 v1, const float (&ca)[8], const float (&cb)[8], int do_elu) {
+// returns the bf16 "hi" words; lo (if requested) receives bf16(v - hi), the second term of the split-bf16 operand
+__device__ __forceinline__ uint4 prep8(const float4 v0, const float4 v1, const float (&ca)[8], const float (&cb)[8], int do_elu,
+                                       uint4* lo) {
   float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
 #pragma unroll
   for (int k = 0; k < 8; ++k) v[k] = fmaf(ca[k], v[k], cb[k]);
@@ -112,17 +114,22 @@ __device__ __forceinline__ uint4 prep8(const float4 v0, const float4 v1, const f
 #pragma unroll
     for (int k = 0; k < 8; ++k) v[k] = elu(v[k]);
   }
-  uint4 o;
-  __nv_bfloat162 t;
-  t = __floats2bfloat162_rn(v[0], v[1]); o.x = *reinterpret_cast<uint32_t*>(&t);
-  t = __floats2bfloat162_rn(v[2], v[3]); o.y = *reinterpret_cast<uint32_t*>(&t);
-  t = __floats2bfloat162_rn(v[4], v[5]); o.z = *reinterpret_cast<uint32_t*>(&t);
-  t = __floats2bfloat162_rn(v[6], v[7]); o.w = *reinterpret_cast<uint32_t*>(&t);
-  return o;
+  uint32_t w[4], wl[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
+    w[k] = *reinterpret_cast<const uint32_t*>(&t);
+    const float2 f = __bfloat1622float2(t);
+    const __nv_bfloat162 u = __floats2bfloat162_rn(v[2 * k] - f.x, v[2 * k + 1] - f.y);
+    wl[k] = *reinterpret_cast<const uint32_t*>(&u);
+  }
+  if (lo) *lo = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+  return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
 __global__ void __launch_bounds__(256) k_prep(const float* __restrict__ x, const float2* __restrict__ coef,
-                                              __nv_bfloat16* __restrict__ y, int HW, int C8, int rows_per_block, int do_elu) {
+                                              __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ y_lo, int HW, int C8,
+                                              int rows_per_block, int do_elu) {
   const int n = blockIdx.y;
   const int rstep = blockDim.x / C8;
   const int c = threadIdx.x % C8, r0 = threadIdx.x / C8;
@@ -142,16 +149,17 @@ __global__ void __launch_bounds__(256) k_prep(const float* __restrict__ x, const
   const int rbeg = blockIdx.x * rows_per_block, rend = min(HW, rbeg + rows_per_block);
   const float4* xb = reinterpret_cast<const float4*>(x) + ((size_t)n * HW) * (2 * C8) + 2 * c;
   uint4* yb = reinterpret_cast<uint4*>(y) + ((size_t)n * HW) * C8 + c;
+  uint4* yl = y_lo ? reinterpret_cast<uint4*>(y_lo) + ((size_t)n * HW) * C8 + c : nullptr;
   int r = rbeg + r0;
   for (; r + rstep < rend; r += 2 * rstep) {
     const float4 a0 = __ldg(xb + (size_t)r * (2 * C8)), a1 = __ldg(xb + (size_t)r * (2 * C8) + 1);
     const float4 b0 = __ldg(xb + (size_t)(r + rstep) * (2 * C8)), b1 = __ldg(xb + (size_t)(r + rstep) * (2 * C8) + 1);
-    yb[(size_t)r * C8] = prep8(a0, a1, ca, cb, do_elu);
-    yb[(size_t)(r + rstep) * C8] = prep8(b0, b1, ca, cb, do_elu);
+    yb[(size_t)r * C8] = prep8(a0, a1, ca, cb, do_elu, yl ? yl + (size_t)r * C8 : nullptr);
+    yb[(size_t)(r + rstep) * C8] = prep8(b0, b1, ca, cb, do_elu, yl ? yl + (size_t)(r + rstep) * C8 : nullptr);
   }
   for (; r < rend; r += rstep) {
     const float4 a0 = __ldg(xb + (size_t)r * (2 * C8)), a1 = __ldg(xb + (size_t)r * (2 * C8) + 1);
-    yb[(size_t)r * C8] = prep8(a0, a1, ca, cb, do_elu);
+    yb[(size_t)r * C8] = prep8(a0, a1, ca, cb, do_elu, yl ? yl + (size_t)r * C8 : nullptr);
   }
 }
 
@@ -260,7 +268,8 @@ __global__ void __launch_bounds__(256) k_begin_conv(const float* __restrict__ x,
 }
 
 // ---- end_conv: 3x3 'same', C -> 1 channel, bias, optional division by sigma[idx[n]]; one warp per pixel
-__global__ void __launch_bounds__(256) k_end_conv(const __nv_bfloat16* __restrict__ x, const float* __restrict__ k,
+__global__ void __launch_bounds__(256) k_end_conv(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ x_lo,
+                                                  const float* __restrict__ k,
                                                   float bias, const float* __restrict__ sigmas, const int* __restrict__ idx,
                                                   float* __restrict__ y, int H, int W, int C, long long pixels) {
   const long long p = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -271,10 +280,13 @@ __global__ void __launch_bounds__(256) k_end_conv(const __nv_bfloat16* __restric
   for (int tap = 0; tap < 9; ++tap) {
     const int hh = h + tap / 3 - 1, ww = w + tap % 3 - 1;
     if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
-    const __nv_bfloat162* row = reinterpret_cast<const __nv_bfloat162*>(x + (p + (long long)(tap / 3 - 1) * W + (tap % 3 - 1)) * C);
+    const long long off = (p + (long long)(tap / 3 - 1) * W + (tap % 3 - 1)) * C;
+    const __nv_bfloat162* row = reinterpret_cast<const __nv_bfloat162*>(x + off);
+    const __nv_bfloat162* row_lo = x_lo ? reinterpret_cast<const __nv_bfloat162*>(x_lo + off) : nullptr;
     const float2* kr = reinterpret_cast<const float2*>(k + (size_t)tap * C);
     for (int c2 = lane; c2 < C / 2; c2 += 32) {
-      const float2 v = __bfloat1622float2(row[c2]);
+      float2 v = __bfloat1622float2(row[c2]);
+      if (row_lo) { const float2 l = __bfloat1622float2(row_lo[c2]); v.x += l.x; v.y += l.y; }
       const float2 kk = __ldg(kr + c2);
       acc = fmaf(v.x, kk.x, acc);
       acc = fmaf(v.y, kk.y, acc);
@@ -309,13 +321,14 @@ void launch_in_coef(const double* sums, const float* gab, int gab_stride_n, cons
   ASEP_LAUNCH_CHECK();
 }
 
-void launch_prep(const float* x, const float2* coef, __nv_bfloat16* y, int N, int HW, int C, int do_elu, cudaStream_t s) {
+void launch_prep(const float* x, const float2* coef, __nv_bfloat16* y, __nv_bfloat16* y_lo, int N, int HW, int C, int do_elu,
+                 cudaStream_t s) {
   ASEP_CHECK(C % 8 == 0 && C / 8 <= 256, ASEP_ERR_UNSUPPORTED, "prep: C = %d (multiple of 8, <= 2048)", C);
   const int C8 = C / 8;
   const int threads = C8 * (256 / C8);
   const int rows = 32;
   dim3 grid((HW + rows - 1) / rows, N);
-  k_prep<<<grid, threads, 0, s>>>(x, coef, y, HW, C8, rows, do_elu);
+  k_prep<<<grid, threads, 0, s>>>(x, coef, y, y_lo, HW, C8, rows, do_elu);
   ASEP_LAUNCH_CHECK();
 }
 
@@ -360,10 +373,10 @@ void launch_begin_conv(const float* x, const float* k, const float* bias, float*
   ASEP_LAUNCH_CHECK();
 }
 
-void launch_end_conv(const __nv_bfloat16* x, const float* k, float bias, const float* sigmas, const int* idx, float* y,
+void launch_end_conv(const __nv_bfloat16* x, const __nv_bfloat16* x_lo, const float* k, float bias, const float* sigmas, const int* idx, float* y,
                      int N, int H, int W, int C, cudaStream_t s) {
   const long long pixels = (long long)N * H * W;
-  k_end_conv<<<cdiv(pixels * 32, 256), 256, 0, s>>>(x, k, bias, sigmas, idx, y, H, W, C, pixels);
+  k_end_conv<<<cdiv(pixels * 32, 256), 256, 0, s>>>(x, x_lo, k, bias, sigmas, idx, y, H, W, C, pixels);
   ASEP_LAUNCH_CHECK();
 }
 

@@ -12,7 +12,9 @@ void launch_in_stats(const float* x, double* sums, int N, int HW, int C, cudaStr
 void launch_in_coef(const double* sums, const float* gab, int gab_stride_n, const int* idx, const float* in_gamma,
                     const float* in_beta, float2* coef, int N, int HW, int C, cudaStream_t s);
 // y (bf16) = act(coef.a * x + coef.b); coef may be NULL (plain cast); do_elu applies ELU(alpha=1)
-void launch_prep(const float* x, const float2* coef, __nv_bfloat16* y, int N, int HW, int C, int do_elu, cudaStream_t s);
+// y_lo (may be NULL) receives bf16(v - y): the low word of the split-bf16 operand (ASEP_PREC_BF16X3)
+void launch_prep(const float* x, const float2* coef, __nv_bfloat16* y, __nv_bfloat16* y_lo, int N, int HW, int C, int do_elu,
+                 cudaStream_t s);
 // 5x5 stride-1 'same' pooling: average over in-bounds taps (Keras AveragePooling2D) or max (MaxPooling2D)
 // (separable: tmp is a scratch tensor of the same size)
 void launch_pool5(const float* x, float* tmp, float* y, int N, int H, int W, int C, int is_max, cudaStream_t s);
@@ -26,7 +28,7 @@ void launch_add(const float* x, const float* z, float* y, long long n, cudaStrea
 void launch_begin_conv(const float* x, const float* k, const float* bias, float* y, int N, int H, int W, int Cout,
                        int rescale, cudaStream_t s);
 // end_conv 3x3 (C -> 1) on the bf16 normalised/activated tensor; sigmas != NULL divides by sigmas[idx[n]] (v2)
-void launch_end_conv(const __nv_bfloat16* x, const float* k, float bias, const float* sigmas, const int* idx, float* y,
+void launch_end_conv(const __nv_bfloat16* x, const __nv_bfloat16* x_lo, const float* k, float bias, const float* sigmas, const int* idx, float* y,
                      int N, int H, int W, int C, cudaStream_t s);
 
 }  // namespace asep

@@ -18,6 +18,7 @@ NcsnModel::~NcsnModel() {
   for (auto& kv : params_)
     if (kv.second.dev) cudaFree(kv.second.dev);
   for (auto& kv : convs_) conv_tc_release(kv.second);
+  for (auto& kv : convs_lo_) conv_tc_release(kv.second);
   for (auto& kv : gab_)
     if (kv.second) cudaFree(kv.second);
   if (sigmas_dev_) cudaFree(sigmas_dev_);
@@ -89,6 +90,8 @@ void NcsnModel::prepare() {
   CUDA_CHECK(cudaSetDevice(device_));
   for (auto& kv : convs_) conv_tc_release(kv.second);
   convs_.clear();
+  for (auto& kv : convs_lo_) conv_tc_release(kv.second);
+  convs_lo_.clear();
   for (auto& kv : gab_)
     if (kv.second) cudaFree(kv.second);
   gab_.clear();
@@ -103,6 +106,11 @@ void NcsnModel::prepare() {
       const int dil = layer.rfind("Res3_", 0) == 0 ? 2 : (layer.rfind("Res4_", 0) == 0 ? 4 : 1);   // score_network.py:259-268
       const float* bias = has(layer + "/bias") ? param(layer + "/bias").host.data() : nullptr;
       conv_tc_prepare(convs_[layer], kv.second.host.data(), bias, (int)sh[0], (int)sh[2], (int)sh[3], dil);
+      if (x3_) {                                                        // second term of the split-bf16 weights
+        std::vector<float> lo(kv.second.host.size());
+        for (size_t i = 0; i < lo.size(); ++i) lo[i] = kv.second.host[i] - __bfloat162float(__float2bfloat16(kv.second.host[i]));
+        conv_tc_prepare(convs_lo_[layer], lo.data(), nullptr, (int)sh[0], (int)sh[2], (int)sh[3], dil);
+      }
     } else if (!v1_ && leaf == "gamma") {
       // v2 InstanceNorm2dPlus: pack the three per-channel vectors as one [gamma | alpha | beta] row
       const int C = (int)kv.second.host.size();
@@ -168,22 +176,40 @@ const float2* NcsnModel::norm_coef(const T& x, const std::string& name) {
   return coef;
 }
 
-__nv_bfloat16* NcsnModel::prep(const T& x, const float2* coef, bool elu) {
-  if (coef == nullptr && !elu && x.bf != nullptr) return x.bf;     // plain cast already done by the producing convolution
-  __nv_bfloat16* y = new_bf(x.H, x.W, x.C);
-  if (!dry_) launch_prep(x.p, coef, y, N_, x.H * x.W, x.C, elu ? 1 : 0, s_);
+NcsnModel::BF NcsnModel::prep(const T& x, const float2* coef, bool elu) {
+  BF y;
+  if (coef == nullptr && !elu && x.bf != nullptr) {      // plain cast already done by the producing convolution
+    y.hi = x.bf;
+    return y;
+  }
+  y.hi = new_bf(x.H, x.W, x.C);
+  if (x3_) y.lo = new_bf(x.H, x.W, x.C);
+  if (!dry_) launch_prep(x.p, coef, y.hi, y.lo, N_, x.H * x.W, x.C, elu ? 1 : 0, s_);
   return y;
 }
 
-NcsnModel::T NcsnModel::conv(const std::string& name, const __nv_bfloat16* xin, int H, int W, const float* add, bool stats,
+NcsnModel::T NcsnModel::conv(const std::string& name, const BF& xin, int H, int W, const float* add, bool stats,
                              bool bf16_copy) {
   auto it = convs_.find(name);
   ASEP_CHECK(it != convs_.end(), ASEP_ERR_STATE, "convolution '%s' has no kernel parameter", name.c_str());
   const ConvWeightsTC& w = it->second;
   T out = new_t(H, W, w.Cout);
   if (stats) out.sums = static_cast<double*>(take((size_t)N_ * w.Cout * 2 * sizeof(double)));
-  if (bf16_copy) out.bf = new_bf(H, W, w.Cout);
-  if (!dry_) conv_tc_forward(w, xin, add, out.p, N_, H, W, s_, out.sums, out.bf);
+  if (bf16_copy && !x3_) out.bf = new_bf(H, W, w.Cout);            // (the x3 mode needs the lo word too: k_prep writes both)
+  if (dry_) return out;
+  if (!x3_) {
+    conv_tc_forward(w, xin.hi, add, out.p, N_, H, W, s_, out.sums, out.bf);
+    return out;
+  }
+  // split-bf16: x.w = xhi.whi + xlo.whi + xhi.wlo (+ xlo.wlo ~ 2^-18, dropped), small terms first, fp32 accumulation in
+  // the epilogues (`add` may alias `out`); bias and the statistics ride on the last pass
+  auto lo = convs_lo_.find(name);
+  ASEP_CHECK(lo != convs_lo_.end() && xin.lo != nullptr, ASEP_ERR_STATE, "'%s': split-bf16 operands missing", name.c_str());
+  ConvWeightsTC w_nobias = w;
+  w_nobias.bias = nullptr;
+  conv_tc_forward(lo->second, xin.hi, add, out.p, N_, H, W, s_);
+  conv_tc_forward(w_nobias, xin.lo, out.p, out.p, N_, H, W, s_);
+  conv_tc_forward(w, xin.hi, out.p, out.p, N_, H, W, s_, out.sums);
   return out;
 }
 
@@ -191,13 +217,13 @@ NcsnModel::T NcsnModel::conv(const std::string& name, const __nv_bfloat16* xin, 
 NcsnModel::T NcsnModel::res_block(const T& x, const std::string& name, int cout, bool down, int dilation) {
   (void)cout; (void)dilation;
   const float2* c1 = norm_coef(x, name + "/norm1");
-  __nv_bfloat16* h = prep(x, c1, true);
+  const BF h = prep(x, c1, true);
   T o1 = conv(name + "/conv1", h, x.H, x.W, nullptr, true);                   // norm2 follows
   const float2* c2 = norm_coef(o1, name + "/norm2");
-  __nv_bfloat16* h2 = prep(o1, c2, true);
+  const BF h2 = prep(o1, c2, true);
   const float* sc = x.p;
   if (has(name + "/shortcut/kernel")) {
-    __nv_bfloat16* xr = prep(x, nullptr, false);
+    const BF xr = prep(x, nullptr, false);
     sc = conv(name + "/shortcut", xr, x.H, x.W, nullptr, false).p;
   }
   const bool pool = down && name.rfind("Res2_", 0) == 0;  // only the undilated 'down' block pools (score_network.py:141-144)
@@ -217,7 +243,7 @@ NcsnModel::T NcsnModel::rcu(T x, const std::string& prefix, int n_blocks, int n_
     for (int j = 0; j < n_stages; ++j) {
       const std::string sfx = "_" + std::to_string(i + 1) + "_" + std::to_string(j + 1);
       const float2* c = v1_ ? norm_coef(x, prefix + "/norm" + sfx) : nullptr;
-      __nv_bfloat16* h = prep(x, c, false);
+      const BF h = prep(x, c, false);
       x = conv(prefix + "/conv" + sfx, h, x.H, x.W, j == n_stages - 1 ? residual.p : nullptr, v1_, !v1_);
     }
   }
@@ -235,7 +261,7 @@ NcsnModel::T NcsnModel::crp(T x, const std::string& prefix) {
     const float2* c = v1_ ? norm_coef(path, prefix + "/norm" + sfx) : nullptr;
     T pooled = new_t(x.H, x.W, x.C), ptmp = new_t(x.H, x.W, x.C);
     if (!dry_) launch_pool5(path.p, ptmp.p, pooled.p, N_, x.H, x.W, x.C, v1_ ? 0 : 1, s_);
-    __nv_bfloat16* h = prep(pooled, c, false);
+    const BF h = prep(pooled, c, false);
     path = conv(prefix + "/conv" + sfx, h, x.H, x.W, nullptr, v1_ && i == 0);
     T sum = new_t(x.H, x.W, x.C);
     if (!dry_) launch_add(acc.p, path.p, sum.p, (long long)N_ * x.H * x.W * x.C, s_);
@@ -256,7 +282,7 @@ NcsnModel::T NcsnModel::msf(const std::vector<T>& xs, const std::string& prefix,
       if (same != (pass == 0)) continue;
       const std::string sfx = "_" + std::to_string(i + 1);
       const float2* c = v1_ ? norm_coef(xi, prefix + "/norm" + sfx) : nullptr;
-      __nv_bfloat16* h = prep(xi, c, false);
+      const BF h = prep(xi, c, false);
       if (same) {
         sums = conv(prefix + "/conv" + sfx, h, xi.H, xi.W, sums.p, false);
       } else {
@@ -296,12 +322,12 @@ void NcsnModel::run(const float* x, const int* idx, float* score) {
   T r3 = refine({l2, r2}, "refine3", ngf, false, l2.H, l2.W);
   T o = refine({l1, r3}, "refine4", ngf, true, l1.H, l1.W);
   const float2* c = norm_coef(o, "normalizer");
-  __nv_bfloat16* h = prep(o, c, true);
+  const BF h = prep(o, c, true);
   const NcsnParam& ek = param("end_conv/kernel");
   const NcsnParam& eb = param("end_conv/bias");
   ASEP_CHECK((int64_t)ek.host.size() == 9 * ngf && eb.host.size() == 1, ASEP_ERR_BAD_SHAPE, "end_conv shape");
   if (!dry_)
-    launch_end_conv(h, ek.dev, eb.host[0], v1_ ? nullptr : sigmas_dev_, v1_ ? nullptr : idx, score, N_, H, W, ngf, s_);
+    launch_end_conv(h.hi, h.lo, ek.dev, eb.host[0], v1_ ? nullptr : sigmas_dev_, v1_ ? nullptr : idx, score, N_, H, W, ngf, s_);
 }
 
 void NcsnModel::forward(const float* x, const int* idx, float* score, int N, cudaStream_t s) {

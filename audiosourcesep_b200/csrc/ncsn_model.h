@@ -24,6 +24,8 @@ class NcsnModel {
   void set_param(const std::string& name, const float* src, const std::vector<int64_t>& shape, bool on_device);
   void set_sigmas(const float* sigmas, int n);
   void prepare();
+  // split-bf16 mode (ASEP_PREC_BF16X3): takes effect at the next prepare()
+  void set_precision(bool x3) { if (x3 != x3_) { x3_ = x3; prepared_ = false; } }
   // x [N,H,W,1] fp32, idx [N] int32 -> score [N,H,W,1] fp32
   void forward(const float* x, const int* idx, float* score, int N, cudaStream_t s);
   const asep_ncsn_cfg& cfg() const { return cfg_; }
@@ -43,8 +45,9 @@ class NcsnModel {
   T new_t(int H, int W, int C);
   __nv_bfloat16* new_bf(int H, int W, int C);
   const float2* norm_coef(const T& x, const std::string& name);
-  __nv_bfloat16* prep(const T& x, const float2* coef, bool elu);
-  T conv(const std::string& name, const __nv_bfloat16* xin, int H, int W, const float* add, bool stats, bool bf16_copy = false);
+  struct BF { __nv_bfloat16* hi = nullptr; __nv_bfloat16* lo = nullptr; };   // convolution operand (lo only in the x3 mode)
+  BF prep(const T& x, const float2* coef, bool elu);
+  T conv(const std::string& name, const BF& xin, int H, int W, const float* add, bool stats, bool bf16_copy = false);
   T res_block(const T& x, const std::string& name, int cout, bool down, int dilation);
   T rcu(T x, const std::string& prefix, int n_blocks, int n_stages);
   T crp(T x, const std::string& prefix);
@@ -57,6 +60,8 @@ class NcsnModel {
   bool v1_;
   std::map<std::string, NcsnParam> params_;
   std::map<std::string, ConvWeightsTC> convs_;
+  std::map<std::string, ConvWeightsTC> convs_lo_;  // x3 mode: tile images of w - bf16(w)
+  bool x3_ = false;
   std::map<std::string, float*> gab_;            // v2: packed [gamma|alpha|beta] rows per norm layer
   float* sigmas_dev_ = nullptr;
   int n_sigmas_ = 0;

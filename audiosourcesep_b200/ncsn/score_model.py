@@ -19,8 +19,11 @@ from ..weights import ncsn_param_shapes
 
 class ScoreModel:
     def __init__(self, cfg: NCSNConfig, params: Dict[str, np.ndarray], sigmas=None, device: Optional[int] = None,
-                 name: str = "ScoreNetwork"):
+                 name: str = "ScoreNetwork", precision: int = _lib.PREC_BF16):
+        """``precision``: ``_lib.PREC_BF16`` (one bf16 tcgen05 product per convolution, the throughput mode) or
+        ``_lib.PREC_BF16X3`` (split-bf16 operands, three products: matches the fp32 reference to ~1e-5)."""
         self.cfg = cfg
+        self.precision = int(precision)
         self.name = name
         self.device_index = _lib.init(device)
         self.device = torch.device("cuda", self.device_index)
@@ -34,6 +37,7 @@ class ScoreModel:
         if sigmas is not None:
             self.set_sigmas(sigmas)
         self.set_params(params)
+        _lib.check(self._lib.asep_ncsn_set_precision(self._h, self.precision))
         self.prepare()
 
     def __del__(self):

@@ -34,6 +34,12 @@ def _ncsn_cfg(args, version):
                       progression=getattr(args, "progression", "logarithmic"))
 
 
+def _precision(args) -> int:
+    """``args.exact`` (run_basis_sep --exact) selects the split-bf16 tensor-core mode (three products per convolution)."""
+    from .. import _lib
+    return _lib.PREC_BF16X3 if getattr(args, "exact", False) else _lib.PREC_BF16
+
+
 def get_uncompiled_model(args, name="ScoreNetwork", params=None, seed=None):
     """NCSN v1 ``CondRefineNetDilated`` behind the Keras-model call contract (reference: ncsn/utils.py:41-51).
     ``params`` (name -> array) loads weights; otherwise the seeded random init is used."""
@@ -44,7 +50,7 @@ def get_uncompiled_model(args, name="ScoreNetwork", params=None, seed=None):
     cfg = _ncsn_cfg(args, "v1")
     if params is None:
         params = init_ncsn_params(cfg, seed=0 if seed is None else seed, mode="perturbed" if seed is not None else "faithful")
-    return ScoreModel(cfg, params, name=name)
+    return ScoreModel(cfg, params, name=name, precision=_precision(args))
 
 
 def get_uncompiled_model_v2(args, sigmas, name="ScoreNetworkv2", params=None, seed=None):
@@ -54,7 +60,7 @@ def get_uncompiled_model_v2(args, sigmas, name="ScoreNetworkv2", params=None, se
     cfg = _ncsn_cfg(args, "v2")
     if params is None:
         params = init_ncsn_params(cfg, seed=0 if seed is None else seed, mode="perturbed" if seed is not None else "faithful")
-    return ScoreModel(cfg, params, sigmas=np.asarray(sigmas, dtype=np.float32), name=name)
+    return ScoreModel(cfg, params, sigmas=np.asarray(sigmas, dtype=np.float32), name=name, precision=_precision(args))
 
 
 def anneal_langevin_dynamics(x_mod, data_shape, model, n_samples, sigmas, n_steps_each=100, step_lr=2e-5,

@@ -217,7 +217,8 @@ def build_models(args, sigmas, device_index: int):
                 params = ckpts[-1](float(sigmas[0]))
             models.append(build_glow(None, [args.height, args.width, 1], L=args.L, K=args.K, n_filters=args.n_filters,
                                      learntop=args.learntop, l2_reg=args.l2_reg, data_type="melspec", minval=0.0,
-                                     maxval=1.0, params=params))
+                                     maxval=1.0, params=params,
+                                     precision=_lib.PREC_FP32 if getattr(args, "exact", False) else None))
         return models[0], models[1], ckpts[0], ckpts[1]
     from .ncsn.utils import get_uncompiled_model, get_uncompiled_model_v2
     builders = []
@@ -272,6 +273,9 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--synthetic", action="store_true", help="separate seeded synthetic mel patches")
     p.add_argument("--random_init", type=int, default=None, metavar="SEED", help="seeded random-init weights")
     p.add_argument("--seed", type=int, default=0, help="Philox seed of the Langevin noise and of x1/x2 init")
+    p.add_argument("--exact", action="store_true",
+                   help="parity mode: NCSN convolutions as three split-bf16 tensor-core products (~3x the conv time), "
+                        "Glow priors on the fp32 CUDA-core kernels")
     return p
 
 

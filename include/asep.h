@@ -43,7 +43,9 @@ typedef enum {
 /* Arithmetic the coupling / score network contractions run in. */
 typedef enum {
   ASEP_PREC_FP32 = 0, /* CUDA-core fp32 kernels: bit-level "exact" mode used as the on-device checker   */
-  ASEP_PREC_BF16 = 1  /* tcgen05 (UMMA) bf16 x bf16 -> fp32 TMEM accumulation: the production path      */
+  ASEP_PREC_BF16 = 1, /* tcgen05 (UMMA) bf16 x bf16 -> fp32 TMEM accumulation: the production path      */
+  ASEP_PREC_BF16X3 = 2 /* score networks only: activations and weights as (hi + lo) bf16 pairs, three tcgen05
+                        * products per convolution (hi.hi + lo.hi + hi.lo), fp32 accumulation: ~2^-16 relative */
 } asep_precision;
 
 const char* asep_last_error(void);
@@ -177,6 +179,8 @@ int asep_ncsn_set_param(asep_ncsn_t h, const char* name, const DLTensor* value);
 /* Noise levels sigma_1..sigma_L (host or device float32 [L]); v2 divides its output by sigma[idx]
  * (score_network_v2.py:275-276). */
 int asep_ncsn_set_sigmas(asep_ncsn_t h, const DLTensor* sigmas);
+/* ASEP_PREC_BF16 (default) or ASEP_PREC_BF16X3; takes effect at the next asep_ncsn_prepare(). */
+int asep_ncsn_set_precision(asep_ncsn_t h, int precision);
 /* Builds the bf16 tcgen05 weight tile images; call after parameters change. */
 int asep_ncsn_prepare(asep_ncsn_t h);
 /* score = model([x, sigma_idx], training=True): x [N,H,W,1] float32, sigma_idx [N] int32 -> score [N,H,W,1]. */

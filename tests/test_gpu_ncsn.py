@@ -21,10 +21,11 @@ def _cfg(version):
     return NCSNConfig(version="v2", ngf=128, num_classes=200, sigma1=30.0, sigmaL=0.01)
 
 
-def _model(cfg, params):
+def _model(cfg, params, precision=None):
+    from audiosourcesep_b200 import _lib
     from audiosourcesep_b200.ncsn.score_model import ScoreModel
     sig = bo.get_sigmas(cfg.sigma1, cfg.sigmaL, cfg.num_classes, cfg.progression)
-    return ScoreModel(cfg, params, sigmas=sig), sig
+    return ScoreModel(cfg, params, sigmas=sig, precision=_lib.PREC_BF16 if precision is None else precision), sig
 
 
 @pytest.mark.parametrize("version", ["v1", "v2"])
@@ -65,15 +66,38 @@ def test_ncsn_param_count_known_answer():
     assert model.count_params() == 67464769          # trained_ncsn/ncsn_piano_192_32_dB_custom_loop/out.log:35
 
 
-@pytest.mark.parametrize("version,sigma_idx,gate", [("v1", 9, 1e-3), ("v1", 3, 1e-2), ("v2", 199, 1e-3), ("v2", 120, 1e-2)])
-def test_basis_ncsn_inner_loop_vs_oracle(version, sigma_idx, gate):
-    """Per-step Langevin state parity with injected noise for the NCSN priors.  The north-star gate (<= 1e-3
-    relative) is asserted at the annealed end of the schedule; at the large-step levels the bf16-operand score
-    error (1-3 % with random weights) times eta exceeds it, so those cases carry a documented looser bound."""
-    from audiosourcesep_b200 import ops
+@pytest.mark.parametrize("version", ["v1", "v2"])
+def test_score_network_split_bf16_mode_matches_fp32_oracle(version):
+    """ASEP_PREC_BF16X3 (operands as hi + lo bf16 pairs, three tcgen05 products per convolution): the score agrees
+    with the fp32 restatement at the level two fp32 evaluation orders agree with each other."""
+    from audiosourcesep_b200 import _lib
+    cfg = _cfg(version)
+    params = init_ncsn_params(cfg, seed=5, mode="perturbed")
+    model, sig = _model(cfg, params, _lib.PREC_BF16X3)
+    x = synthetic.normalise(synthetic.mel_patches_db(2, seed=1)) + 0.05 * np.random.default_rng(0).standard_normal((2, 96, 64, 1)).astype(np.float32)
+    idx = np.array([0, cfg.num_classes - 1], dtype=np.int32)
+    want64 = NCSNOracle(cfg, params, sigmas=sig, dtype=torch.float64).score(x, idx).numpy()
+    want32 = NCSNOracle(cfg, params, sigmas=sig, dtype=torch.float32).score(x, idx).numpy()
+    got = _np(model([torch.as_tensor(x), torch.as_tensor(idx)], training=True))
+    rel = np.linalg.norm(got - want64) / np.linalg.norm(want64)
+    rel32 = np.linalg.norm(want32 - want64) / np.linalg.norm(want64)
+    print(f"[{version}, split-bf16] score relative L2 error vs fp64 = {rel:.3e} (the fp32 restatement itself: {rel32:.3e})")
+    assert rel <= max(2e-4, 20 * rel32), (rel, rel32)
+
+
+@pytest.mark.parametrize("version,sigma_idx,gate,x3", [("v1", 9, 1e-3, False), ("v1", 3, 1e-2, False), ("v2", 199, 1e-3, False),
+                                                      ("v2", 120, 1e-2, False), ("v1", 3, 1e-3, True), ("v2", 120, 1e-3, True),
+                                                      ("v1", 0, 1e-3, True)])
+def test_basis_ncsn_inner_loop_vs_oracle(version, sigma_idx, gate, x3):
+    """Per-step Langevin state parity with injected noise for the NCSN priors.  In the throughput mode (one bf16
+    product per convolution) the north-star gate (<= 1e-3 relative) is asserted at the annealed end of the schedule;
+    at the large-step levels the bf16-operand score error (1-3 % with random weights) times eta exceeds it, so those
+    cases carry a documented looser bound.  The split-bf16 mode meets the gate at every level."""
+    from audiosourcesep_b200 import _lib, ops
     cfg = _cfg(version)
     p1, p2 = init_ncsn_params(cfg, seed=11, mode="perturbed"), init_ncsn_params(cfg, seed=12, mode="perturbed")
-    (m1, sig), (m2, _) = _model(cfg, p1), _model(cfg, p2)
+    prec = _lib.PREC_BF16X3 if x3 else _lib.PREC_BF16
+    (m1, sig), (m2, _) = _model(cfg, p1, prec), _model(cfg, p2, prec)
     o1 = NCSNOracle(cfg, p1, sigmas=sig, dtype=torch.float32)
     o2 = NCSNOracle(cfg, p2, sigmas=sig, dtype=torch.float32)
     n_mixed, T = 2, 2
@@ -100,7 +124,7 @@ def test_basis_ncsn_inner_loop_vs_oracle(version, sigma_idx, gate):
                              nan_count=nan)
         for got, want in ((t1, states[t + 1][0]), (t2, states[t + 1][1])):
             worst = max(worst, float(np.linalg.norm(_np(got) - want) / np.linalg.norm(want)))
-    print(f"[{version}, sigma_idx={sigma_idx}] worst per-step state relative error = {worst:.3e}")
+    print(f"[{version}, sigma_idx={sigma_idx}, {'split-bf16' if x3 else 'bf16'}] worst per-step state relative error = {worst:.3e}")
     assert worst <= gate, worst
     assert nan.item() == 0
 

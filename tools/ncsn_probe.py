@@ -12,11 +12,12 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--version", default="v1")
 ap.add_argument("--batches", type=int, nargs="+", default=[30])
 ap.add_argument("--check", action="store_true")
+ap.add_argument("--x3", action="store_true", help="split-bf16 mode (ASEP_PREC_BF16X3)")
 a = ap.parse_args()
 cfg = NCSNConfig(version="v1", ngf=192, num_classes=10) if a.version == "v1" else NCSNConfig(version="v2", ngf=128, num_classes=200, sigma1=30.0)
 sig = bo.get_sigmas(cfg.sigma1, cfg.sigmaL, cfg.num_classes, cfg.progression)
 p = init_ncsn_params(cfg, seed=5, mode="perturbed")
-t0 = time.time(); m = ScoreModel(cfg, p, sigmas=sig); print(f"model ready {time.time()-t0:.1f}s", flush=True)
+t0 = time.time(); m = ScoreModel(cfg, p, sigmas=sig, precision=_lib.PREC_BF16X3 if a.x3 else _lib.PREC_BF16); print(f"model ready {time.time()-t0:.1f}s", flush=True)
 if a.check:
     x = synthetic.normalise(synthetic.mel_patches_db(2, seed=1))
     idx = np.array([0, cfg.num_classes - 1], dtype=np.int32)
