@@ -282,6 +282,31 @@ def run_ours(args):
     e2e_ms, _, _ = timed_loop(step_e2e, args.steps, args.warmup)
     e2e_value = world * B * args.steps / (e2e_ms * 1e-3)
 
+    # ---- 2b. the other directions of config 1 (forward+inverse): inverse(z) and grad_log_prob(x) samples/s, device-resident
+    z_dev = model.forward(x_dev)
+
+    def step_inv():
+        out["xr"] = model.inverse(z_dev)
+
+    inv_ms, inv_launches, _ = timed_loop(step_inv, max(2, args.steps // 2), 2)
+    rt = float((out["xr"] - x_dev).abs().max().item())
+
+    def step_grad():
+        out["g"] = model.grad_log_prob(x_dev)
+
+    g_ms, g_launches, _ = timed_loop(step_grad, max(2, args.steps // 2), 2)
+    nsub = max(2, args.steps // 2)
+    directions = {
+        "inverse": {"value": world * B * nsub / (inv_ms * 1e-3), "unit": "samples/s", "ms_per_step": inv_ms / nsub,
+                    "gpu_launches": inv_launches, "alg_tflops": world * B * nsub * F_GLOW * (args.K / 40.0) / (inv_ms * 1e-3) / 1e12,
+                    "round_trip_max_abs_dB": rt,
+                    "note": "bf16 tensor-core mode; the <= 1e-4 (normalised units) round-trip gate is met by ASEP_PREC_FP32, see DESIGN.md section 4"},
+        "grad_log_prob": {"value": world * B * nsub / (g_ms * 1e-3), "unit": "samples/s", "ms_per_step": g_ms / nsub,
+                          "gpu_launches": g_launches,
+                          "alg_tflops": world * B * nsub * 2 * F_GLOW * (args.K / 40.0) / (g_ms * 1e-3) / 1e12},
+    }
+    del z_dev
+
     # ---- 3. BASIS Langevin segment-steps/s with two Glow priors (second half of the metric)
     basis = None
     if args.basis_segments > 0:
@@ -438,6 +463,7 @@ def run_ours(args):
         "cpu_baseline": cpu,
         "clocks": clocks,
         "alg_tflops": value * F_GLOW * (args.K / 40.0) / 1e12,
+        "directions": directions,
         "basis": basis,
         "basis_ncsn": ncsn or None,
         "train": train,

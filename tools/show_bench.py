@@ -6,6 +6,9 @@ print('e2e', j['e2e'])
 print('roof', {k: j['roofline'].get(k) for k in ['achieved', 'frac', 'kernel_share_of_step', 'traffic', 'avg_launch_ms']})
 print('cpu', j['cpu_baseline'])
 print('clocks', j['clocks'])
+if j.get('directions'):
+    for k, v in j['directions'].items():
+        print(k, {a: v[a] for a in v if a != 'note'})
 if j.get('basis'):
     print('basis', {k: j['basis'][k] for k in ['value', 'ms_per_langevin_step', 'alg_tflops']})
 for v in ['v1', 'v2']:
