@@ -19,6 +19,7 @@ LIB_PATH = os.path.join(_HERE, "libasep.so")
 
 PREC_FP32 = 0
 PREC_BF16 = 1
+PREC_FP16 = 3       # Glow: tcgen05 with fp16 hidden activations in the forward network (closer to fp32, ~8 % slower)
 PREC_BF16X3 = 2     # score networks: split-bf16 operands, three tcgen05 products per convolution
 
 

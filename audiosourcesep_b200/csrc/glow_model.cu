@@ -229,11 +229,11 @@ void GlowModel::build_step_consts(int b, int k) {
 }
 
 void GlowModel::prepare(int precision) {
-  ASEP_CHECK(precision == ASEP_PREC_FP32 || precision == ASEP_PREC_BF16, ASEP_ERR_BAD_ARG, "unknown precision %d",
+  ASEP_CHECK(precision == ASEP_PREC_FP32 || precision == ASEP_PREC_BF16 || precision == ASEP_PREC_FP16, ASEP_ERR_BAD_ARG, "unknown precision %d",
              precision);
   const int F = cfg_.n_filters;
-  if (precision == ASEP_PREC_BF16)
-    ASEP_CHECK(F == kTcF, ASEP_ERR_UNSUPPORTED, "ASEP_PREC_BF16 needs n_filters = %d (got %d)", kTcF, F);
+  if (precision == ASEP_PREC_BF16 || precision == ASEP_PREC_FP16)
+    ASEP_CHECK(F == kTcF, ASEP_ERR_UNSUPPORTED, "the tcgen05 modes need n_filters = %d (got %d)", kTcF, F);
   CUDA_CHECK(cudaSetDevice(device_));
   for (int b = 0; b < cfg_.L; ++b) {
     const int C = levels_[b].C;
@@ -270,11 +270,11 @@ void GlowModel::prepare(int precision) {
       sd.w32.c2 = params_.at(pre + "conv2/bias").dev;
       sd.w32.g2 = sd.g2; sd.w32.b2 = sd.b2;
       sd.w32.k3 = params_.at(pre + "conv3/kernel").dev; sd.w32.c3 = params_.at(pre + "conv3/bias").dev;
-      if (precision == ASEP_PREC_BF16) {
+      if (precision == ASEP_PREC_BF16 || precision == ASEP_PREC_FP16) {
         nn_tc_prepare(sd.wtc, params_.at(pre + "conv1/kernel").host.data(), params_.at(pre + "conv1/bias").host.data(),
                       g1.data(), b1.data(), k2.data(), params_.at(pre + "conv2/bias").host.data(), g2.data(),
                       b2.data(), params_.at(pre + "conv3/kernel").host.data(),
-                      params_.at(pre + "conv3/bias").host.data(), C, F);
+                      params_.at(pre + "conv3/bias").host.data(), C, F, precision == ASEP_PREC_FP16);
       } else {
         nn_tc_release(sd.wtc);
       }
@@ -491,7 +491,7 @@ void GlowModel::grad_log_prob(const float* x, float* grad, float* logp, int N, c
     launch_split_merge(gy, work_.gz, gX_next, N, lv.H, lv.W, lv.C, Cz, nb, CL_, coff, Dl_, 1, s);
     for (int k = 0; k < K; ++k) {          // steps were applied K-1..0, so unwind 0..K-1
       launch_bwd_coupling(gy, work_.U[b][k], work_.R[b][k], work_.gr, work_.gu, M, lv.C, s);
-      if (precision_ == ASEP_PREC_BF16 && !work_.M1.empty() && !work_.M1[b].empty())
+      if (is_tc() && !work_.M1.empty() && !work_.M1[b].empty())
         nn_tc_backward(step(b, k).wtc, work_.tc, work_.gr, work_.M1[b][k], work_.M2[b][k], work_.gxb, N, lv.H, lv.W, lv.C, s);
       else
         nn_backward(b, k, work_.U[b][k], work_.gr, work_.gxb, N, s);

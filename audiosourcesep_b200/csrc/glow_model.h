@@ -149,6 +149,7 @@ class GlowModel {
   std::vector<StepDerived> steps_;
   bool prepared_ = false;
   int precision_ = ASEP_PREC_FP32;
+  bool is_tc() const { return precision_ == ASEP_PREC_BF16 || precision_ == ASEP_PREC_FP16; }   // tcgen05 modes
   DeviceArena arena_;
   Work work_;
   float* score_buf_ = nullptr;

@@ -91,10 +91,10 @@ void GlowModel::derive_on_device(cudaStream_t s) {
     for (int k = 0; k < cfg_.K; ++k) {
       const StepTrainPtrs sp = step_ptrs(b, k);
       launch_derive_step(sp, (double)levels_[b].H * levels_[b].W, ldc_ + (size_t)b * cfg_.K + k, precision_ == ASEP_PREC_FP32 ? 1 : 0, s);
-      if (precision_ == ASEP_PREC_BF16) {              // tcgen05 operands: tile images + folded biases
+      if (is_tc()) {                                   // tcgen05 operands: tile images + folded biases
         NNWeightsTC& w = step(b, k).wtc;
         launch_build_tc_step(sp, w.fwd.img, w.bwd.img, w.fwd.k1_panels, w.fwd.n3p, w.bwd.k1_panels, w.bwd.n3p, w.bias1,
-                             w.bias2, w.const3, w.c3, s);
+                             w.bias2, w.const3, w.c3, w.f16, s);
       }
     }
   launch_sum_doubles(ldc_, (int)steps_.size(), ld_total_, s);
@@ -116,7 +116,7 @@ void GlowModel::train_grads(const float* x, const float* noise, float sigma, int
   ASEP_CHECK(training_, ASEP_ERR_STATE, "asep_glow_enable_training() has not been called");
   ASEP_CHECK(N >= 1 && global_batch >= N, ASEP_ERR_BAD_ARG, "bad batch sizes (local %d, global %d)", N, global_batch);
   CUDA_CHECK(cudaSetDevice(device_));
-  const bool use_graph = precision_ == ASEP_PREC_BF16 && !nn_tc_profile_enabled() && getenv("ASEP_NO_GRAPH") == nullptr &&
+  const bool use_graph = is_tc() && !nn_tc_profile_enabled() && getenv("ASEP_NO_GRAPH") == nullptr &&
                          getenv("ASEP_TC_DBG_TIMING") == nullptr;
   if (!use_graph || N > tg_calls_) {             // the first call of a batch size runs eagerly: it allocates the scratch
     train_grads_body(x, noise, sigma, N, global_batch, grads, loss, s);
@@ -178,7 +178,7 @@ void GlowModel::train_grads_body(const float* x, const float* noise, float sigma
   const int L = cfg_.L, K = cfg_.K, F = cfg_.n_filters;
   const float gs = -1.0f / (float)global_batch;      // loss = -sum log_prob / global_batch (train_glow.py:30-31)
   ensure_work(N, true);
-  const bool tc = precision_ == ASEP_PREC_BF16;
+  const bool tc = is_tc();
   if (tc) ensure_train_dumps((long long)N * levels_[0].H * levels_[0].W);
   const float* xin = x;
   if (noise != nullptr) {                              // train_noisy_glow.py:31-32: X + sigma*N(0,1) in raw data units

@@ -74,6 +74,7 @@ struct TCParams {
   __nv_bfloat16* dump2;      //   forward a1 = relu(p1), a2 = relu(p2); backward gp2 = dL/dp2, gp1 = dL/dp1)
   long long* dbg_out;        // debug: per-tile phase timestamps of CTA 0 (clock64), 8 per round
   int dbg_flags;             // debug: 1 skip MMA, 2 skip operand build, 4 skip G store, 8 skip epilogue 1/2 bodies
+  int f16;                   // forward: fp16 hidden activations / stage-2,3 weights
   int dbg_shift;             // debug: load only bytes >> dbg_shift of every weight image (timing experiments)
   int tiles_per_cta_round;   // grid size (all CTAs advance together)
   int num_rounds;
@@ -85,324 +86,6 @@ __device__ __forceinline__ uint32_t a_offset(int row, int k) {
 }
 
 
-// Stage-1 operand row: im2col of SC channels over the 3x3 taps as split-bf16 [hi | lo].
-// All global loads of a tap group are issued before any is consumed (memory-level parallelism).
-template <int SC>
-__device__ __forceinline__ void build_a1_row(uint8_t* sA, int row, const float* __restrict__ src, long long p,
-                                             bool valid, int h, int w, int H, int W, int stride, int off, int sign,
-                                             int k1_pad) {
-  constexpr int K1h = 9 * SC;
-  constexpr int TG = SC >= 16 ? 3 : 9;                 // taps per load group (register budget)
-#pragma unroll
-  for (int t0 = 0; t0 < 9; t0 += TG) {
-    float v[TG][SC];
-#pragma unroll
-    for (int tt = 0; tt < TG; ++tt) {
-      const int tap = t0 + tt;
-      const int dy = (tap / 3 - 1) * sign, dx = (tap % 3 - 1) * sign;
-      const int hh = h + dy, ww = w + dx;
-      const bool ok = valid && hh >= 0 && hh < H && ww >= 0 && ww < W;
-      const float* s = src + (p + (long long)dy * W + dx) * stride + off;
-      if constexpr (SC % 4 == 0) {
-#pragma unroll
-        for (int q = 0; q < SC / 4; ++q) {
-          float4 t = ok ? __ldg(reinterpret_cast<const float4*>(s) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-          v[tt][4 * q] = t.x; v[tt][4 * q + 1] = t.y; v[tt][4 * q + 2] = t.z; v[tt][4 * q + 3] = t.w;
-        }
-      } else if constexpr (SC == 2) {
-        float2 t = ok ? __ldg(reinterpret_cast<const float2*>(s)) : make_float2(0.f, 0.f);
-        v[tt][0] = t.x; v[tt][1] = t.y;
-      } else {
-#pragma unroll
-        for (int ci = 0; ci < SC; ++ci) v[tt][ci] = ok ? __ldg(s + ci) : 0.f;
-      }
-    }
-#pragma unroll
-    for (int tt = 0; tt < TG; ++tt) {
-      const int k0 = (t0 + tt) * SC;
-      float lo[SC];
-      uint32_t hp[(SC + 1) / 2], lp[(SC + 1) / 2];
-#pragma unroll
-      for (int ci = 0; ci < SC; ++ci) lo[ci] = v[tt][ci] - __bfloat162float(__float2bfloat16_rn(v[tt][ci]));
-      if constexpr (SC == 1) {
-        *reinterpret_cast<__nv_bfloat16*>(sA + a_offset(row, k0)) = __float2bfloat16_rn(v[tt][0]);
-        *reinterpret_cast<__nv_bfloat16*>(sA + a_offset(row, K1h + k0)) = __float2bfloat16_rn(lo[0]);
-      } else {
-#pragma unroll
-        for (int q = 0; q < SC / 2; ++q) {
-          hp[q] = pack_bf16(v[tt][2 * q], v[tt][2 * q + 1]);
-          lp[q] = pack_bf16(lo[2 * q], lo[2 * q + 1]);
-        }
-        if constexpr (SC == 2) {
-          *reinterpret_cast<uint32_t*>(sA + a_offset(row, k0)) = hp[0];
-          *reinterpret_cast<uint32_t*>(sA + a_offset(row, K1h + k0)) = lp[0];
-        } else if constexpr (SC == 4) {
-          *reinterpret_cast<uint2*>(sA + a_offset(row, k0)) = make_uint2(hp[0], hp[1]);
-          *reinterpret_cast<uint2*>(sA + a_offset(row, K1h + k0)) = make_uint2(lp[0], lp[1]);
-        } else {
-#pragma unroll
-          for (int q = 0; q < SC / 8; ++q) {
-            *reinterpret_cast<uint4*>(sA + a_offset(row, k0 + 8 * q)) =
-                make_uint4(hp[4 * q], hp[4 * q + 1], hp[4 * q + 2], hp[4 * q + 3]);
-            *reinterpret_cast<uint4*>(sA + a_offset(row, K1h + k0 + 8 * q)) =
-                make_uint4(lp[4 * q], lp[4 * q + 1], lp[4 * q + 2], lp[4 * q + 3]);
-          }
-        }
-      }
-    }
-  }
-  for (int k = 2 * K1h; k < k1_pad; ++k)
-    *reinterpret_cast<__nv_bfloat16*>(sA + a_offset(row, k)) = __float2bfloat16_rn(0.f);
-}
-
-template <int CS, bool kBwd>
-__global__ void __launch_bounds__(kThreadsTC, 1) k_nn_tc(const TCParams prm) {
-  // SWIZZLE_128B operands need 1024-byte alignment; the kernel uses no static shared memory, so the dynamic
-  // window starts at the CTA's shared base (checked below rather than assumed).
-  extern __shared__ __align__(1024) uint8_t smem[];
-  if ((smem_u32(smem) & 1023u) != 0u) __trap();
-  uint8_t* sA = smem;
-  uint8_t* sB = smem + kARegionBytes;
-  float* sBias = reinterpret_cast<float*>(smem + kARegionBytes + kStages * kStageBytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kARegionBytes + kStages * kStageBytes + kBiasBytes);
-  // bars[0..2] full, [3..5] empty, [6] a_ready, [7] acc_ready, [8] tmem slot
-  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[kStages]);
-  const uint32_t a_ready = smem_u32(&bars[2 * kStages]), acc_ready = smem_u32(&bars[2 * kStages + 1]);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(&bars[2 * kStages + 2]);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint32_t cta_rank = 0;
-  if constexpr (CS > 1) cta_rank = cg::this_cluster().block_rank();
-  constexpr uint16_t kMcMask = (uint16_t)((1u << CS) - 1);
-
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < kStages; ++i) {
-      mbar_init(full0 + 8 * i, 1);
-      mbar_init(empty0 + 8 * i, CS);
-    }
-    mbar_init(a_ready, 128);
-    mbar_init(acc_ready, 1);
-    fence_barrier_init();
-  }
-  if (warp == 2) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
-  tc_fence_before();
-  if constexpr (CS > 1) cg::this_cluster().sync(); else __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  const int n_img1 = 2 * prm.k1_panels;
-  const int n_img = n_img1 + 2 * kNumPanels + kNumPanels;
-  const uint32_t img3_bytes = (uint32_t)prm.n3p * 128u;
-
-  if (warp == 0) {
-    // ===================== producer =====================
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
-      for (int round = 0; round < prm.num_rounds; ++round) {
-        const uint8_t* src = reinterpret_cast<const uint8_t*>(prm.wimg);
-        for (int i = 0; i < n_img; ++i) {
-          const uint32_t bytes = (i < n_img - kNumPanels) ? (uint32_t)kStageBytes : img3_bytes;
-          mbar_wait(empty0 + 8 * stage, phase ^ 1);
-          const uint32_t dst = smem_u32(sB + stage * kStageBytes);
-          if constexpr (CS == 1) {
-            const uint32_t ld_bytes = (bytes >> prm.dbg_shift) & ~15u;
-            mbar_expect_tx(full0 + 8 * stage, ld_bytes);
-            bulk_g2s(dst, src, ld_bytes, full0 + 8 * stage);
-          } else {
-            mbar_expect_tx(full0 + 8 * stage, bytes);
-            const uint32_t part = bytes / CS;
-            bulk_g2s_mc(dst + cta_rank * part, src + cta_rank * part, part, full0 + 8 * stage, kMcMask);
-          }
-          src += bytes;
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0, a_phase = 0;
-      const uint32_t a_base = smem_u32(sA);
-      constexpr uint32_t idesc256 = make_idesc(256);
-      const uint32_t idesc3 = make_idesc(prm.n3p);
-      for (int round = 0; round < prm.num_rounds; ++round) {
-        for (int gemm = 0; gemm < 3; ++gemm) {
-          mbar_wait(a_ready, a_phase);
-          a_phase ^= 1;
-          tc_fence_after();
-          const int halves = gemm < 2 ? 2 : 1;
-          const int panels = gemm == 0 ? prm.k1_panels : kNumPanels;
-          const uint32_t idesc = gemm < 2 ? idesc256 : idesc3;
-          for (int half = 0; half < halves; ++half) {
-            const uint32_t d_tmem = tmem_base + (uint32_t)(half * 256);
-            for (int kp = 0; kp < panels; ++kp) {
-              mbar_wait(full0 + 8 * stage, phase);
-              tc_fence_after();
-              const int steps = gemm == 0 ? min(4, prm.k1_steps - 4 * kp) : 4;
-              const uint64_t da = make_desc(a_base + kp * kPanelBytes);
-              const uint64_t db = make_desc(smem_u32(sB + stage * kStageBytes));
-              for (int k = 0; k < steps && !(prm.dbg_flags & 1); ++k) {
-                // advance 16 bf16 = 32 bytes along K inside the swizzled panel: +2 in the >>4 address field
-                umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kp | k) != 0);
-              }
-              if constexpr (CS == 1) umma_commit(empty0 + 8 * stage);
-              else umma_commit_mc(empty0 + 8 * stage, kMcMask);
-              if (++stage == kStages) { stage = 0; phase ^= 1; }
-            }
-          }
-          umma_commit(acc_ready);
-        }
-      }
-    }
-  } else {
-    // ===================== workers: operand build + epilogues =====================
-    const int quarter = warp & 3;
-    const int row = quarter * 32 + lane;
-    const int wtid = threadIdx.x - 64;                        // 0..127 among the worker threads
-    const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    uint32_t acc_phase = 0;
-    const int k1_pad = prm.k1_steps * 16;
-    // each worker keeps one float4 of each bias vector in registers for the whole kernel
-    float4 b1v = make_float4(0.f, 0.f, 0.f, 0.f), b2v = b1v;
-    if constexpr (!kBwd) {
-      b1v = __ldg(reinterpret_cast<const float4*>(prm.bias1) + wtid);
-      b2v = __ldg(reinterpret_cast<const float4*>(prm.bias2) + wtid);
-    }
-    for (int round = 0; round < prm.num_rounds; ++round) {
-      const long long tile = (long long)round * prm.tiles_per_cta_round + blockIdx.x;
-      const long long p = tile * kTileM + row;
-      const bool valid = p < prm.M;
-      // pull the next tile's input rows towards L2 while this tile is being processed
-      {
-        const long long pn = p + (long long)prm.tiles_per_cta_round * kTileM;
-        if (pn < prm.M) asm volatile("prefetch.global.L2 [%0];" ::"l"(prm.src + pn * prm.src_stride));
-      }
-      // ---- stage-1 operand: split-bf16 im2col row
-      {
-        int w = 0, h = 0;
-        if (valid) { w = (int)(p % prm.W); h = (int)((p / prm.W) % prm.H); }
-        if (!(prm.dbg_flags & 2)) switch (prm.src_ch) {
-          case 1: build_a1_row<1>(sA, row, prm.src, p, valid, h, w, prm.H, prm.W, prm.src_stride, prm.src_off, prm.tap_sign, k1_pad); break;
-          case 2: build_a1_row<2>(sA, row, prm.src, p, valid, h, w, prm.H, prm.W, prm.src_stride, prm.src_off, prm.tap_sign, k1_pad); break;
-          case 4: build_a1_row<4>(sA, row, prm.src, p, valid, h, w, prm.H, prm.W, prm.src_stride, prm.src_off, prm.tap_sign, k1_pad); break;
-          case 8: build_a1_row<8>(sA, row, prm.src, p, valid, h, w, prm.H, prm.W, prm.src_stride, prm.src_off, prm.tap_sign, k1_pad); break;
-          default: build_a1_row<16>(sA, row, prm.src, p, valid, h, w, prm.H, prm.W, prm.src_stride, prm.src_off, prm.tap_sign, k1_pad); break;
-        }
-      }
-      if constexpr (!kBwd) reinterpret_cast<float4*>(sBias)[wtid] = b1v;
-      fence_proxy_async();
-      mbar_arrive(a_ready);
-
-      // ---- epilogues of stage 1 and stage 2: TMEM -> (bias, relu | mask) -> bf16 -> swizzled smem
-      for (int gemm = 0; gemm < 2; ++gemm) {
-        // forward: stage 1 -> mask1, stage 2 -> mask2; backward: stage 1 applies mask2, stage 2 mask1
-        uint32_t* mask = kBwd ? (gemm == 0 ? prm.mask2 : prm.mask1) : (gemm == 0 ? prm.mask1 : prm.mask2);
-        uint32_t mk[kF / 32];
-        if constexpr (kBwd) {                                  // fetch this row's 512 mask bits before waiting
-#pragma unroll
-          for (int q = 0; q < kF / 128; ++q) {
-            uint4 t = valid ? __ldg(reinterpret_cast<const uint4*>(mask + p * (kF / 32)) + q) : make_uint4(0, 0, 0, 0);
-            mk[4 * q] = t.x; mk[4 * q + 1] = t.y; mk[4 * q + 2] = t.z; mk[4 * q + 3] = t.w;
-          }
-        }
-        if constexpr (!kBwd) named_bar_sync(1, 128);           // bias vector of this stage is in sBias
-        mbar_wait(acc_ready, acc_phase);
-        acc_phase ^= 1;
-        tc_fence_after();
-#pragma unroll
-        for (int jj = 0; jj < ((prm.dbg_flags & 8) ? 0 : kF / 64); ++jj) {   // 64 accumulator columns per iteration
-          uint32_t v[2][32];
-          tmem_ld32(t_lane + (uint32_t)(jj * 64), v[0]);
-          tmem_ld32(t_lane + (uint32_t)(jj * 64 + 32), v[1]);
-          tmem_ld_wait();
-          uint8_t* base = sA + jj * kPanelBytes + row * 128;   // 64 columns = one K panel of the next stage
-#pragma unroll
-          for (int hf = 0; hf < 2; ++hf) {
-            const int j = 2 * jj + hf;
-            float f[32];
-            if constexpr (!kBwd) {
-              uint32_t bits = 0;
-#pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                const float4 b4 = reinterpret_cast<const float4*>(sBias + j * 32)[q];
-                f[4 * q + 0] = __uint_as_float(v[hf][4 * q + 0]) + b4.x;
-                f[4 * q + 1] = __uint_as_float(v[hf][4 * q + 1]) + b4.y;
-                f[4 * q + 2] = __uint_as_float(v[hf][4 * q + 2]) + b4.z;
-                f[4 * q + 3] = __uint_as_float(v[hf][4 * q + 3]) + b4.w;
-              }
-#pragma unroll
-              for (int cidx = 0; cidx < 32; ++cidx) {
-                bits |= (f[cidx] > 0.f ? 1u : 0u) << cidx;
-                f[cidx] = fmaxf(f[cidx], 0.f);
-              }
-              if (mask != nullptr && valid) mask[p * (kF / 32) + j] = bits;
-            } else {
-              const uint32_t bits = mk[j];
-#pragma unroll
-              for (int cidx = 0; cidx < 32; ++cidx) f[cidx] = ((bits >> cidx) & 1u) ? __uint_as_float(v[hf][cidx]) : 0.f;
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const int chunk = hf * 4 + q;
-              uint4 pk;
-              pk.x = pack_bf16(f[8 * q + 0], f[8 * q + 1]);
-              pk.y = pack_bf16(f[8 * q + 2], f[8 * q + 3]);
-              pk.z = pack_bf16(f[8 * q + 4], f[8 * q + 5]);
-              pk.w = pack_bf16(f[8 * q + 6], f[8 * q + 7]);
-              *reinterpret_cast<uint4*>(base + ((chunk ^ (row & 7)) << 4)) = pk;
-            }
-          }
-        }
-        if constexpr (!kBwd) {
-          if (gemm == 0) {                                     // swap in the stage-2 bias once everyone is done
-            named_bar_sync(1, 128);
-            reinterpret_cast<float4*>(sBias)[wtid] = b2v;
-          }
-        }
-        tc_fence_before();
-        fence_proxy_async();
-        mbar_arrive(a_ready);
-      }
-
-      // ---- epilogue of stage 3: TMEM -> global fp32 G[p][0..n3p)
-      mbar_wait(acc_ready, acc_phase);
-      acc_phase ^= 1;
-      tc_fence_after();
-      for (int j = 0; j < prm.n3p / 16; ++j) {
-        uint32_t v[16];
-        tmem_ld16(t_lane + (uint32_t)(j * 16), v);
-        tmem_ld_wait();
-        if (valid && !(prm.dbg_flags & 4)) {
-          float4* o = reinterpret_cast<float4*>(prm.out + p * prm.n3p + j * 16);
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            o[q] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
-                               __uint_as_float(v[4 * q + 3]));
-        }
-      }
-      tc_fence_before();
-    }
-  }
-
-  // ---- teardown
-  tc_fence_before();
-  if constexpr (CS > 1) cg::this_cluster().sync(); else __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
-}
-
-// ===================================================================================================
-// CTA-pair variant (cta_group::2).  Two CTAs of a cluster (the two SMs of a TPC) process 256 consecutive pixels:
-// every tcgen05.mma spans both (M = 256), each CTA supplies its own 128 operand rows and streams only HALF of
-// every weight image (rows [rank*128, +128) of the 256 output channels of the instruction), so the L2 -> SM
-// weight traffic per pixel is halved and the 6-deep ring of 16 KB half images covers the L2 latency.  The leader
-// (rank 0) issues all MMAs; the peer's warp 1 relays "my half of stage s has landed" to the leader; tcgen05.commit
-// multicasts stage releases and accumulator-ready signals to both CTAs.  Eight worker warps per CTA (two per
-// TMEM lane quarter, each owning 256 of the 512 accumulator columns) run the epilogues with the TMEM loads of
-// chunk j+1 in flight while chunk j is converted.
-constexpr int kStages2 = 6;
-constexpr int kHalfStageBytes = kStageBytes / 2;      // 16 KB
-constexpr int kBarBytes2 = 256;
-constexpr int kSmemBytes2 = kARegionBytes + kStages2 * kHalfStageBytes + kBiasBytes + kBarBytes2;   // 231,680 B
 constexpr int kThreadsTC2 = 64 + 256;
 constexpr int kWorkers2 = 256;
 
@@ -470,275 +153,6 @@ __device__ __forceinline__ void build_a1_taps(uint8_t* sA, int row, const float*
         }
       }
     }
-  }
-}
-
-template <bool kBwd, bool kSaveMask, bool kPair>
-__global__ void __launch_bounds__(kThreadsTC2, 1) k_nn_tc2(const TCParams prm) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  if ((smem_u32(smem) & 1023u) != 0u) __trap();
-  constexpr int S = kPair ? kStages2 : kStages;                     // ring depth
-  constexpr int kSlotBytes = kPair ? kHalfStageBytes : kStageBytes;  // 16 KB half images / 32 KB full images
-  constexpr int kRowsPerRound = kPair ? 2 * kTileM : kTileM;
-  uint8_t* sA = smem;
-  uint8_t* sB = smem + kARegionBytes;
-  float* sBias = reinterpret_cast<float*>(smem + kARegionBytes + S * kSlotBytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kARegionBytes + S * kSlotBytes + kBiasBytes);
-  // bars: [0,S) full  [S,2S) empty  [2S,3S) peer_full (leader)  [3S] a_ready (leader)  [3S+1] acc_ready  [3S+2] tmem slot
-  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[S]), peer0 = smem_u32(&bars[2 * S]);
-  const uint32_t a_ready = smem_u32(&bars[3 * S]), acc_ready = smem_u32(&bars[3 * S + 1]);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(&bars[3 * S + 2]);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint32_t rank = 0;
-  if constexpr (kPair) rank = cluster_ctarank();
-  const bool leader = rank == 0;
-
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < S; ++i) {
-      mbar_init(full0 + 8 * i, 1);
-      mbar_init(empty0 + 8 * i, 1);
-      mbar_init(peer0 + 8 * i, 1);
-    }
-    mbar_init(a_ready, kPair ? 16 : 8);   // one arrival per worker warp (of each CTA)
-    mbar_init(acc_ready, 1);
-    fence_barrier_init();
-  }
-  if (warp == 2) {
-    if constexpr (kPair) tmem_alloc2(smem_u32(tmem_slot), kTmemCols);
-    else tmem_alloc(smem_u32(tmem_slot), kTmemCols);
-  }
-  tc_fence_before();
-  if constexpr (kPair) cluster_sync_all(); else __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  const int n_img1 = 2 * prm.k1_panels;
-  const int n_img = n_img1 + 2 * kNumPanels + kNumPanels;
-  const uint32_t img3_bytes = (uint32_t)prm.n3p * 128u;
-
-  if (warp == 0) {
-    // ===================== producer: this CTA's half of every weight image =====================
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
-      for (int round = 0; round < prm.num_rounds; ++round) {
-        const uint8_t* src = reinterpret_cast<const uint8_t*>(prm.wimg);
-        for (int i = 0; i < n_img; ++i) {
-          const uint32_t bytes = (i < n_img - kNumPanels) ? (uint32_t)kStageBytes : img3_bytes;
-          const uint32_t half = kPair ? (bytes >> 1) : bytes;
-          mbar_wait(empty0 + 8 * stage, phase ^ 1);
-          mbar_expect_tx(full0 + 8 * stage, half);
-          bulk_g2s(smem_u32(sB + stage * kSlotBytes), src + rank * half, half, full0 + 8 * stage);
-          src += bytes;
-          if (++stage == (uint32_t)S) { stage = 0; phase ^= 1; }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      if (!leader) {
-        // ===================== peer relay: tell the leader when my half of a stage has landed =====================
-        uint32_t stage = 0, phase = 0;
-        const uint32_t peer_remote = mapa_u32(peer0, 0);
-        const long long total = (long long)prm.num_rounds * n_img;
-        for (long long i = 0; i < total; ++i) {
-          mbar_wait(full0 + 8 * stage, phase);
-          mbar_arrive_cluster(peer_remote + 8 * stage);
-          if (++stage == (uint32_t)S) { stage = 0; phase ^= 1; }
-        }
-      } else {
-        // ===================== MMA issuer (leader only) =====================
-        uint32_t stage = 0, phase = 0, a_phase = 0;
-        const uint32_t a_base = smem_u32(sA);
-        constexpr uint32_t idesc256 = make_idesc_m(256, kPair ? 256 : 128);
-        const uint32_t idesc3 = make_idesc_m(prm.n3p, kPair ? 256 : 128);
-        for (int round = 0; round < prm.num_rounds; ++round) {
-          for (int gemm = 0; gemm < 3; ++gemm) {
-            if constexpr (kPair) mbar_wait_cluster(a_ready, a_phase); else mbar_wait(a_ready, a_phase);
-            a_phase ^= 1;
-            tc_fence_after();
-            const int halves = gemm < 2 ? 2 : 1;
-            const int panels = gemm == 0 ? prm.k1_panels : kNumPanels;
-            const uint32_t idesc = gemm < 2 ? idesc256 : idesc3;
-            for (int half = 0; half < halves; ++half) {
-              const uint32_t d_tmem = tmem_base + (uint32_t)(half * 256);
-              for (int kp = 0; kp < panels; ++kp) {
-                mbar_wait(full0 + 8 * stage, phase);
-                if constexpr (kPair) mbar_wait_cluster(peer0 + 8 * stage, phase);
-                tc_fence_after();
-                const int steps = gemm == 0 ? min(4, prm.k1_steps - 4 * kp) : 4;
-                const uint64_t da = make_desc(a_base + kp * kPanelBytes);
-                const uint64_t db = make_desc(smem_u32(sB + stage * kSlotBytes));
-                for (int k = 0; k < steps; ++k) {
-                  if constexpr (kPair) umma_bf16_2cta(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kp | k) != 0);
-                  else umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kp | k) != 0);
-                }
-                if constexpr (kPair) umma_commit_2cta(empty0 + 8 * stage, 3); else umma_commit(empty0 + 8 * stage);
-                if (++stage == (uint32_t)S) { stage = 0; phase ^= 1; }
-              }
-            }
-            if constexpr (kPair) umma_commit_2cta(acc_ready, 3); else umma_commit(acc_ready);
-          }
-        }
-      }
-    }
-  } else {
-    // ===================== workers: operand build + epilogues (both CTAs, 8 warps) =====================
-    const int quarter = warp & 3;                       // TMEM lane quarter this warp may access
-    const int colhalf = (warp - 2) >> 2;                // which 256 of the 512 accumulator columns
-    const int row = quarter * 32 + lane;
-    const int wtid = threadIdx.x - 64;                  // 0..255
-    const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    uint32_t a_ready_leader = a_ready;
-    if constexpr (kPair) a_ready_leader = mapa_u32(a_ready, 0);
-    uint32_t acc_phase = 0;
-    const int k1_pad = prm.k1_steps * 16;
-    float4 b1v = make_float4(0.f, 0.f, 0.f, 0.f), b2v = b1v;
-    if constexpr (!kBwd) {
-      if (wtid < kF / 4) {
-        b1v = __ldg(reinterpret_cast<const float4*>(prm.bias1) + wtid);
-        b2v = __ldg(reinterpret_cast<const float4*>(prm.bias2) + wtid);
-      }
-    }
-    auto signal_a_ready = [&]() {
-      if constexpr (kPair) fence_proxy_async_all(); else fence_proxy_async();   // my smem writes -> visible to the tensor core
-      __syncwarp();
-      if (lane == 0) {
-        if constexpr (kPair) mbar_arrive_cluster(a_ready_leader); else mbar_arrive(a_ready);
-      }
-    };
-    for (int round = 0; round < prm.num_rounds; ++round) {
-      const long long tile = (long long)round * prm.tiles_per_cta_round + (kPair ? (blockIdx.x >> 1) : blockIdx.x);
-      const long long p = tile * kRowsPerRound + (long long)rank * kTileM + row;
-      const bool valid = p < prm.M;
-      const bool stamp = prm.dbg_out != nullptr && blockIdx.x == 0 && wtid == 0;
-      long long* ts = prm.dbg_out + (long long)round * 8;
-      if (stamp) ts[0] = clock64();
-      if (colhalf == 0) {
-        const long long pn = p + (long long)prm.tiles_per_cta_round * kRowsPerRound;
-        if (pn < prm.M) asm volatile("prefetch.global.L2 [%0];" ::"l"(prm.src + pn * prm.src_stride));
-      }
-      // ---- stage-1 operand: two threads per row, taps 0-4 and 5-8 (+ zero padding of the K tail)
-      {
-        int w = 0, h = 0;
-        if (valid) { w = (int)(p % prm.W); h = (int)((p / prm.W) % prm.H); }
-        const int tb = colhalf == 0 ? 0 : 5, te = colhalf == 0 ? 5 : 9;
-        switch (prm.src_ch) {
-          case 1: build_a1_taps<1>(sA, row, prm.src, p, valid, h, w, prm.H, prm.W, prm.src_stride, prm.src_off, prm.tap_sign, tb, te); break;
-          case 2: build_a1_taps<2>(sA, row, prm.src, p, valid, h, w, prm.H, prm.W, prm.src_stride, prm.src_off, prm.tap_sign, tb, te); break;
-          case 4: build_a1_taps<4>(sA, row, prm.src, p, valid, h, w, prm.H, prm.W, prm.src_stride, prm.src_off, prm.tap_sign, tb, te); break;
-          case 8: build_a1_taps<8>(sA, row, prm.src, p, valid, h, w, prm.H, prm.W, prm.src_stride, prm.src_off, prm.tap_sign, tb, te); break;
-          default: build_a1_taps<16>(sA, row, prm.src, p, valid, h, w, prm.H, prm.W, prm.src_stride, prm.src_off, prm.tap_sign, tb, te); break;
-        }
-        if (colhalf == 1)
-          for (int k = 2 * 9 * prm.src_ch; k < k1_pad; ++k)
-            *reinterpret_cast<__nv_bfloat16*>(sA + a_offset(row, k)) = __float2bfloat16_rn(0.f);
-      }
-      if constexpr (!kBwd) {
-        if (wtid < kF / 4) reinterpret_cast<float4*>(sBias)[wtid] = b1v;
-      }
-      signal_a_ready();
-      if (stamp) ts[1] = clock64();
-
-      // ---- epilogues of stage 1 and stage 2: TMEM -> (bias, relu | mask) -> bf16 -> swizzled smem
-      for (int gemm = 0; gemm < 2; ++gemm) {
-        uint32_t* mask = kBwd ? (gemm == 0 ? prm.mask2 : prm.mask1) : (gemm == 0 ? prm.mask1 : prm.mask2);
-        uint32_t mk[8];
-        if constexpr (kBwd) {
-#pragma unroll
-          for (int q = 0; q < 2; ++q) {
-            uint4 t = valid ? __ldg(reinterpret_cast<const uint4*>(mask + p * (kF / 32) + colhalf * 8) + q) : make_uint4(0, 0, 0, 0);
-            mk[4 * q] = t.x; mk[4 * q + 1] = t.y; mk[4 * q + 2] = t.z; mk[4 * q + 3] = t.w;
-          }
-        }
-        if constexpr (!kBwd) named_bar_sync(1, kWorkers2);      // bias vector of this stage is in sBias
-        mbar_wait(acc_ready, acc_phase);
-        acc_phase ^= 1;
-        tc_fence_after();
-        if (stamp) ts[2 + 2 * gemm] = clock64();
-        uint32_t v[2][32];
-        const uint32_t t_col = t_lane + (uint32_t)(colhalf * 256);
-        tmem_ld32(t_col, v[0]);
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {                            // 8 chunks of 32 accumulator columns
-          tmem_ld_wait();
-          if (c + 1 < 8) tmem_ld32(t_col + (uint32_t)((c + 1) * 32), v[(c + 1) & 1]);
-          const int j = colhalf * 8 + c;                         // global 32-column chunk index
-          float f[32];
-          if constexpr (!kBwd) {
-            uint32_t bits = 0;
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const float4 b4 = reinterpret_cast<const float4*>(sBias + j * 32)[q];
-              f[4 * q + 0] = __uint_as_float(v[c & 1][4 * q + 0]) + b4.x;
-              f[4 * q + 1] = __uint_as_float(v[c & 1][4 * q + 1]) + b4.y;
-              f[4 * q + 2] = __uint_as_float(v[c & 1][4 * q + 2]) + b4.z;
-              f[4 * q + 3] = __uint_as_float(v[c & 1][4 * q + 3]) + b4.w;
-            }
-            if constexpr (kSaveMask) {
-#pragma unroll
-              for (int cidx = 0; cidx < 32; ++cidx) bits |= (f[cidx] > 0.f ? 1u : 0u) << cidx;
-              if (valid) mask[p * (kF / 32) + j] = bits;
-            }
-#pragma unroll
-            for (int cidx = 0; cidx < 32; ++cidx) f[cidx] = fmaxf(f[cidx], 0.f);
-          } else {
-            const uint32_t bits = mk[c];
-#pragma unroll
-            for (int cidx = 0; cidx < 32; ++cidx) f[cidx] = ((bits >> cidx) & 1u) ? __uint_as_float(v[c & 1][cidx]) : 0.f;
-          }
-          uint8_t* base = sA + (j >> 1) * kPanelBytes + row * 128;
-          __nv_bfloat16* dump = gemm == 0 ? prm.dump1 : prm.dump2;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int chunk = (j & 1) * 4 + q;
-            uint4 pk;
-            pk.x = pack_bf16(f[8 * q + 0], f[8 * q + 1]);
-            pk.y = pack_bf16(f[8 * q + 2], f[8 * q + 3]);
-            pk.z = pack_bf16(f[8 * q + 4], f[8 * q + 5]);
-            pk.w = pack_bf16(f[8 * q + 6], f[8 * q + 7]);
-            *reinterpret_cast<uint4*>(base + ((chunk ^ (row & 7)) << 4)) = pk;
-            if (dump != nullptr && valid) *reinterpret_cast<uint4*>(dump + p * kF + j * 32 + q * 8) = pk;
-          }
-        }
-        if constexpr (!kBwd) {
-          if (gemm == 0) {                                       // swap in the stage-2 bias once everyone is done
-            named_bar_sync(1, kWorkers2);
-            if (wtid < kF / 4) reinterpret_cast<float4*>(sBias)[wtid] = b2v;
-          }
-        }
-        tc_fence_before();
-        signal_a_ready();
-        if (stamp) ts[3 + 2 * gemm] = clock64();
-      }
-
-      // ---- epilogue of stage 3: TMEM -> global fp32 G[p][0..n3p), 16-column chunks alternate between the two warps of a row
-      mbar_wait(acc_ready, acc_phase);
-      acc_phase ^= 1;
-      tc_fence_after();
-      if (stamp) ts[6] = clock64();
-      for (int j = colhalf; j < prm.n3p / 16; j += 2) {
-        uint32_t v[16];
-        tmem_ld16(t_lane + (uint32_t)(j * 16), v);
-        tmem_ld_wait();
-        if (valid) {
-          float4* o = reinterpret_cast<float4*>(prm.out + p * prm.n3p + j * 16);
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            o[q] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
-                               __uint_as_float(v[4 * q + 3]));
-        }
-      }
-      tc_fence_before();
-      if (stamp) ts[7] = clock64();
-    }
-  }
-
-  tc_fence_before();
-  if constexpr (kPair) cluster_sync_all(); else __syncthreads();
-  if (warp == 2) {
-    if constexpr (kPair) tmem_dealloc2(tmem_base, kTmemCols);
-    else tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -810,7 +224,7 @@ __device__ __forceinline__ void a1_store(uint8_t* sA, int row, const float (&v)[
 constexpr int kBarBytes4 = 256;
 constexpr int kSmemBytes4 = kARegionBytes + kStages * kStageBytes + kBiasBytes + kBarBytes4;   // 231,680 B
 
-template <bool kBwd, bool kSaveMask>
+template <bool kBwd, bool kSaveMask, bool kF16>
 __global__ void __launch_bounds__(kThreadsTC2, 1) k_nn_tc4(const TCParams prm) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0u) __trap();
@@ -874,8 +288,11 @@ __global__ void __launch_bounds__(kThreadsTC2, 1) k_nn_tc4(const TCParams prm) {
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       const uint32_t a_base = smem_u32(sA);
-      constexpr uint32_t idesc256 = make_idesc(256);
-      const uint32_t idesc3 = make_idesc(prm.n3p);
+      constexpr uint32_t idesc256 = make_idesc(256);                                   // stage 1: split-bf16 rows x bf16 weights
+      // kF16 (forward only): the hidden activations and the stage-2/3 weights are fp16 (10 mantissa bits; activations
+      // are O(1..100)); the backward "activations" are gradients of unbounded range and always bf16
+      constexpr uint32_t idesc256h = kF16 ? make_idesc_f16(256) : make_idesc(256);
+      const uint32_t idesc3 = kF16 ? make_idesc_f16(prm.n3p) : make_idesc(prm.n3p);
       // one K panel (<= 4 MMAs of K = 16): A = operand panel kp, B = the ring slot that holds the next image
       auto kblock = [&](uint32_t d_tmem, int kp, int steps, uint32_t idesc, bool first) {
         mbar_wait(full0 + 8 * stage, phase);
@@ -907,12 +324,12 @@ __global__ void __launch_bounds__(kThreadsTC2, 1) k_nn_tc4(const TCParams prm) {
             mbar_wait(panel0 + 8 * kp, 0);
             tc_fence_after();
           }
-          kblock(h0, kp, 4, idesc256, kp == 0);
+          kblock(h0, kp, 4, idesc256h, kp == 0);
         }
         umma_commit(accfull0);
         // ---- stage 2, half 1: tells E2(H0) when each of the first four h1 panels may be overwritten by h2
         for (int kp = 0; kp < kNumPanels; ++kp) {
-          kblock(h1, kp, 4, idesc256, kp == 0);
+          kblock(h1, kp, 4, idesc256h, kp == 0);
           if (kp < 4) umma_commit(cons0 + 8 * kp);
         }
         umma_commit(accfull0 + 8);
@@ -975,13 +392,8 @@ __global__ void __launch_bounds__(kThreadsTC2, 1) k_nn_tc4(const TCParams prm) {
     auto build = [&](int round) {
       long long p; bool valid; int h, w;
       row_coords(round, p, valid, h, w);
-      switch (prm.src_ch) {
-        case 1: build_a1_taps<1>(sA, row, prm.src, p, valid, h, w, prm.H, prm.W, prm.src_stride, prm.src_off, prm.tap_sign, tb, te); break;
-        case 2: build_a1_taps<2>(sA, row, prm.src, p, valid, h, w, prm.H, prm.W, prm.src_stride, prm.src_off, prm.tap_sign, tb, te); break;
-        case 4: build_a1_taps<4>(sA, row, prm.src, p, valid, h, w, prm.H, prm.W, prm.src_stride, prm.src_off, prm.tap_sign, tb, te); break;
-        case 8: build_a1_taps<8>(sA, row, prm.src, p, valid, h, w, prm.H, prm.W, prm.src_stride, prm.src_off, prm.tap_sign, tb, te); break;
-        default: build_a1_taps<16>(sA, row, prm.src, p, valid, h, w, prm.H, prm.W, prm.src_stride, prm.src_off, prm.tap_sign, tb, te); break;
-      }
+      if (prm.src_ch == 8) build_a1_taps<8>(sA, row, prm.src, p, valid, h, w, prm.H, prm.W, prm.src_stride, prm.src_off, prm.tap_sign, tb, te);
+      else build_a1_taps<16>(sA, row, prm.src, p, valid, h, w, prm.H, prm.W, prm.src_stride, prm.src_off, prm.tap_sign, tb, te);
       finish_a1();
     };
     // <= 4 source channels: the next tile's taps are fetched into registers while this tile's stage 2 is running
@@ -1004,35 +416,45 @@ __global__ void __launch_bounds__(kThreadsTC2, 1) k_nn_tc4(const TCParams prm) {
       }
       finish_a1();
     };
-    build(0);
     for (int round = 0; round < prm.num_rounds; ++round) {
       const long long tile = (long long)round * prm.tiles_per_cta_round + blockIdx.x;
       const long long p = tile * kTileM + row;
       const bool valid = p < prm.M;
       const bool stamp = prm.dbg_out != nullptr && blockIdx.x == 0 && wtid == 0;
       long long* ts = prm.dbg_out + (long long)round * 8;
+      // ---- this tile's stage-1 operand rows (all MMAs of the previous tile are complete: the panels are free).  It is
+      //      stored before anything else so that S1 runs while the previous tile's G rows are still leaving (one call
+      //      site: the unrolled im2col code is large)
+      if (prefetch_regs) {
+        if (round == 0) prefetch_a1(0);
+        store_a1();
+      } else {
+        build(round);
+      }
       if (stamp) ts[0] = clock64();
       if (ch == 0) {      // pull the tile after next towards L2
         const long long pn = p + 2ll * prm.tiles_per_cta_round * kTileM;
         if (pn < prm.M) asm volatile("prefetch.global.L2 [%0];" ::"l"(prm.src + pn * prm.src_stride));
       }
-      // ---- epilogues of the two hidden layers: TMEM -> (bias, relu | mask) -> bf16 -> swizzled smem, panel by panel
-#pragma unroll
+      // ---- epilogues of the two hidden layers: TMEM -> (bias, relu | mask) -> fp16 / bf16 -> swizzled smem, panel by panel.
+      // Only the four-panel loop is unrolled (its TMEM loads are double-buffered in registers): fully unrolled the
+      // kernel grew to 160-208 KB of code and the eight worker warps thrashed the instruction cache.
+#pragma unroll 1
       for (int gemm = 0; gemm < 2; ++gemm) {
         uint32_t* mask = kBwd ? (gemm == 0 ? prm.mask2 : prm.mask1) : (gemm == 0 ? prm.mask1 : prm.mask2);
         __nv_bfloat16* dump = gemm == 0 ? prm.dump1 : prm.dump2;
         // mask words of a row are stored per worker: word ch*8 + panel covers columns [64*panel + 32*ch, +32), so that
         // each thread reads / writes its 8 words as two 16-byte accesses (the layout is private to this kernel pair)
-        uint32_t mk[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+        uint32_t mkl[4] = {0u, 0u, 0u, 0u}, mkh[4] = {0u, 0u, 0u, 0u};      // panels 0-3 (H0) / 4-7 (H1)
         if constexpr (kBwd) {
           if (valid) {
             const uint4 m0 = __ldg(reinterpret_cast<const uint4*>(mask + p * (kF / 32) + ch * 8));
             const uint4 m1 = __ldg(reinterpret_cast<const uint4*>(mask + p * (kF / 32) + ch * 8) + 1);
-            mk[0] = m0.x; mk[1] = m0.y; mk[2] = m0.z; mk[3] = m0.w; mk[4] = m1.x; mk[5] = m1.y; mk[6] = m1.z; mk[7] = m1.w;
+            mkl[0] = m0.x; mkl[1] = m0.y; mkl[2] = m0.z; mkl[3] = m0.w; mkh[0] = m1.x; mkh[1] = m1.y; mkh[2] = m1.z; mkh[3] = m1.w;
           }
         }
         if constexpr (!kBwd) named_bar_sync(1, kWorkers2);      // bias vector of this layer is in sBias
-#pragma unroll
+#pragma unroll 1
         for (int hh = 0; hh < 2; ++hh) {
           // accumulator uses per tile: H0 = S1, S2, S3 (3 per tile); H1 = S1, S2 (2 per tile)
           const uint32_t par = hh == 0 ? (uint32_t)(round + gemm) & 1u : (uint32_t)gemm;
@@ -1058,15 +480,14 @@ __global__ void __launch_bounds__(kThreadsTC2, 1) k_nn_tc4(const TCParams prm) {
                   bits |= (f0 > 0.f ? 1u : 0u) << (4 * c4) | (f1 > 0.f ? 1u : 0u) << (4 * c4 + 1) |
                           (f2 > 0.f ? 1u : 0u) << (4 * c4 + 2) | (f3 > 0.f ? 1u : 0u) << (4 * c4 + 3);
                 }
-                // relu after rounding == rounding after relu (round-to-nearest keeps sign and zero)
-                const __nv_bfloat162 z2 = __floats2bfloat162_rn(0.f, 0.f);
-                __nv_bfloat162 a = __hmax2(__floats2bfloat162_rn(f0, f1), z2), b = __hmax2(__floats2bfloat162_rn(f2, f3), z2);
-                pk[2 * c4] = *reinterpret_cast<uint32_t*>(&a);
-                pk[2 * c4 + 1] = *reinterpret_cast<uint32_t*>(&b);
+                // A hidden activation above 65504 becomes +inf and surfaces as NaN (the BASIS loops count NaNs) instead of being clamped silently.
+                // cvt.rn.relu.{f16x2,bf16x2}.f32: ReLU fused into the conversion
+                pk[2 * c4] = kF16 ? pack_relu_f16(f0, f1) : pack_relu_bf16(f0, f1);
+                pk[2 * c4 + 1] = kF16 ? pack_relu_f16(f2, f3) : pack_relu_bf16(f2, f3);
               }
-              if constexpr (kSaveMask) mk[pn] = bits;
+              if constexpr (kSaveMask) { if (hh) mkh[pp] = bits; else mkl[pp] = bits; }
             } else {
-              const uint32_t bits = mk[pn];
+              const uint32_t bits = hh ? mkh[pp] : mkl[pp];
 #pragma unroll
               for (int c2 = 0; c2 < 16; ++c2) {
                 const float f0 = ((bits >> (2 * c2)) & 1u) ? __uint_as_float(v[pp & 1][2 * c2]) : 0.f;
@@ -1074,10 +495,21 @@ __global__ void __launch_bounds__(kThreadsTC2, 1) k_nn_tc4(const TCParams prm) {
                 pk[c2] = pack_bf16(f0, f1);
               }
             }
-            if (dump != nullptr && valid) {
+            if (dump != nullptr && valid) {      // training: the weight-gradient GEMMs take bf16 operands
 #pragma unroll
-              for (int c4 = 0; c4 < 4; ++c4)
-                *reinterpret_cast<uint4*>(dump + p * kF + j * 32 + c4 * 8) = make_uint4(pk[4 * c4], pk[4 * c4 + 1], pk[4 * c4 + 2], pk[4 * c4 + 3]);
+              for (int c4 = 0; c4 < 4; ++c4) {
+                uint32_t d[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  if constexpr (!kF16) {
+                    d[q] = pk[4 * c4 + q];
+                  } else {                       // fp16 activations in the operand panels: re-round to bf16
+                    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&pk[4 * c4 + q]));
+                    d[q] = pack_bf16(f.x, f.y);
+                  }
+                }
+                *reinterpret_cast<uint4*>(dump + p * kF + j * 32 + c4 * 8) = make_uint4(d[0], d[1], d[2], d[3]);
+              }
             }
             // h2 panel pn replaces h1 panel pn in place: S2(H1) must have consumed it (h2 panels 4-7: S2 is complete)
             if (gemm == 1 && hh == 0) mbar_wait(cons0 + 8 * pn, round & 1);
@@ -1109,8 +541,8 @@ __global__ void __launch_bounds__(kThreadsTC2, 1) k_nn_tc4(const TCParams prm) {
         if constexpr (kSaveMask) {
           if (valid) {
             uint4* mo = reinterpret_cast<uint4*>(mask + p * (kF / 32) + ch * 8);
-            mo[0] = make_uint4(mk[0], mk[1], mk[2], mk[3]);
-            mo[1] = make_uint4(mk[4], mk[5], mk[6], mk[7]);
+            mo[0] = make_uint4(mkl[0], mkl[1], mkl[2], mkl[3]);
+            mo[1] = make_uint4(mkh[0], mkh[1], mkh[2], mkh[3]);
           }
         }
         if constexpr (!kBwd) {                                   // swap in the other layer's bias once everyone is done
@@ -1158,9 +590,6 @@ __global__ void __launch_bounds__(kThreadsTC2, 1) k_nn_tc4(const TCParams prm) {
         }
       }
       if (stamp) ts[4] = clock64();
-      if (round + 1 < prm.num_rounds) {
-        if (prefetch_regs) store_a1(); else build(round + 1);
-      }
       if (stamp) ts[5] = clock64();
     }
     if (wtid == 0) bulk_wait_all();
@@ -1279,8 +708,9 @@ inline int pad16(int n) { return (n + 15) / 16 * 16; }
 
 // ------------------------------------------------------------------ host: weight tile images
 // Writes one image of `rows` rows x 64 k (bf16, SWIZZLE_128B K-major) for rows n0.., k0..
+// f16 = true stores IEEE half bits (forward stage-2/3 weights) in the same 16-bit slots
 template <typename Fn>
-void write_image(std::vector<__nv_bfloat16>& dst, int rows, int n0, int n_valid, int k0, int k_valid, Fn&& get) {
+void write_image(std::vector<__nv_bfloat16>& dst, int rows, int n0, int n_valid, int k0, int k_valid, Fn&& get, bool f16 = false) {
   const size_t base = dst.size();
   dst.resize(base + (size_t)rows * 64, __float2bfloat16(0.f));
   for (int r = 0; r < rows; ++r) {
@@ -1288,13 +718,18 @@ void write_image(std::vector<__nv_bfloat16>& dst, int rows, int n0, int n_valid,
       float v = 0.f;
       if (r < n_valid && k < k_valid) v = get(n0 + r, k0 + k);
       const size_t off = (size_t)r * 64 + (size_t)((((k >> 3) ^ (r & 7)) << 3) + (k & 7));
-      dst[base + off] = __float2bfloat16(v);
+      if (f16) {
+        const __half hv = __float2half(v);
+        std::memcpy(&dst[base + off], &hv, sizeof(hv));
+      } else {
+        dst[base + off] = __float2bfloat16(v);
+      }
     }
   }
 }
 
 template <typename F1, typename F2, typename F3>
-void build_stage_set(TCStageSet& set, int K1, int N3, F1&& b1, F2&& b2, F3&& b3) {
+void build_stage_set(TCStageSet& set, int K1, int N3, F1&& b1, F2&& b2, F3&& b3, bool f16_23) {
   set.k1_steps = (K1 + 15) / 16;
   set.k1_panels = (K1 + 63) / 64;
   set.n3p = pad16(N3);
@@ -1305,8 +740,8 @@ void build_stage_set(TCStageSet& set, int K1, int N3, F1&& b1, F2&& b2, F3&& b3)
     for (int kp = 0; kp < set.k1_panels; ++kp)
       write_image(img, kStageRows, half * 256, 256, kp * 64, std::min(64, K1 - kp * 64), b1);
   for (int half = 0; half < 2; ++half)
-    for (int kp = 0; kp < kNumPanels; ++kp) write_image(img, kStageRows, half * 256, 256, kp * 64, 64, b2);
-  for (int kp = 0; kp < kNumPanels; ++kp) write_image(img, set.n3p, 0, N3, kp * 64, 64, b3);
+    for (int kp = 0; kp < kNumPanels; ++kp) write_image(img, kStageRows, half * 256, 256, kp * 64, 64, b2, f16_23);
+  for (int kp = 0; kp < kNumPanels; ++kp) write_image(img, set.n3p, 0, N3, kp * 64, 64, b3, f16_23);
   set.bytes = img.size() * sizeof(__nv_bfloat16);
   CUDA_CHECK(cudaMalloc(&set.img, set.bytes));
   CUDA_CHECK(cudaMemcpy(set.img, img.data(), set.bytes, cudaMemcpyHostToDevice));
@@ -1319,79 +754,9 @@ float* upload(const std::vector<float>& v) {
   return d;
 }
 
-template <int CS, bool kBwd>
-void launch_tc(const TCParams& prm, int grid, cudaStream_t s) {
-  auto kern = k_nn_tc<CS, kBwd>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    attr_set = true;
-  }
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(kThreadsTC);
-  cfg.dynamicSmemBytes = kSmemBytes;
-  cfg.stream = s;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CS;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  ProfRec rec{};
-  if (g_prof_on) {
-    if (!g_prof_pool.empty()) { rec = g_prof_pool.back(); g_prof_pool.pop_back(); }
-    else { CUDA_CHECK(cudaEventCreate(&rec.a)); CUDA_CHECK(cudaEventCreate(&rec.b)); }
-    CUDA_CHECK(cudaEventRecord(rec.a, s));
-  }
-  CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, prm));
-  ASEP_LAUNCH_CHECK();
-  if (g_prof_on) {
-    CUDA_CHECK(cudaEventRecord(rec.b, s));
-    g_prof_recs.push_back(rec);
-    g_prof_flops += g_next_flops;
-  }
-}
-
-template <bool kBwd, bool kSaveMask, bool kPair>
-void launch_tc2(const TCParams& prm, int grid, cudaStream_t s) {
-  auto kern = k_nn_tc2<kBwd, kSaveMask, kPair>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes2));
-    attr_set = true;
-  }
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(kThreadsTC2);
-  cfg.dynamicSmemBytes = kSmemBytes2;
-  cfg.stream = s;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = kPair ? 2 : 1;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  ProfRec rec{};
-  if (g_prof_on) {
-    if (!g_prof_pool.empty()) { rec = g_prof_pool.back(); g_prof_pool.pop_back(); }
-    else { CUDA_CHECK(cudaEventCreate(&rec.a)); CUDA_CHECK(cudaEventCreate(&rec.b)); }
-    CUDA_CHECK(cudaEventRecord(rec.a, s));
-  }
-  CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, prm));
-  ASEP_LAUNCH_CHECK();
-  if (g_prof_on) {
-    CUDA_CHECK(cudaEventRecord(rec.b, s));
-    g_prof_recs.push_back(rec);
-    g_prof_flops += g_next_flops;
-  }
-}
-
-template <bool kBwd, bool kSaveMask>
+template <bool kBwd, bool kSaveMask, bool kF16>
 void launch_tc4(const TCParams& prm, int grid, cudaStream_t s) {
-  auto kern = k_nn_tc4<kBwd, kSaveMask>;
+  auto kern = k_nn_tc4<kBwd, kSaveMask, kF16>;
   static bool attr_set = false;
   if (!attr_set) {
     CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes4));
@@ -1419,7 +784,9 @@ bool run_tc(TCParams prm, cudaStream_t s) {   // returns true when G was written
     CUDA_CHECK(cudaGetDevice(&dev));
     CUDA_CHECK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
-  if (g_pair_mode == 3 && prm.k1_panels * kPanelBytes + ((kTileM * prm.n3p * 4 + 1023) & ~1023) <= kARegionBytes) {
+  {
+    ASEP_CHECK(prm.k1_panels * kPanelBytes + ((kTileM * prm.n3p * 4 + 1023) & ~1023) <= kARegionBytes, ASEP_ERR_UNSUPPORTED,
+               "coupling network shape outside the tcgen05 kernel (stage-1 panels %d, stage-3 columns %d)", prm.k1_panels, prm.n3p);
     ASEP_CHECK(prm.M < (1ll << 31), ASEP_ERR_UNSUPPORTED, "more than 2^31 pixels in one coupling-network launch");
     const long long tiles = (prm.M + kTileM - 1) / kTileM;
     const int grid = (int)std::min<long long>(tiles, g_num_sms);
@@ -1434,7 +801,13 @@ bool run_tc(TCParams prm, cudaStream_t s) {   // returns true when G was written
     }
     if (const char* e = getenv("ASEP_TC_DBG_SHIFT")) prm.dbg_shift = atoi(e);
     if (const char* e = getenv("ASEP_TC_DBG_FLAGS")) prm.dbg_flags = atoi(e);
-    if (!kBwd && prm.mask1 != nullptr) launch_tc4<kBwd, true>(prm, grid, s); else launch_tc4<kBwd, false>(prm, grid, s);
+    if constexpr (kBwd) {
+      launch_tc4<true, false, false>(prm, grid, s);
+    } else {
+      const bool save = prm.mask1 != nullptr;
+      if (prm.f16) { if (save) launch_tc4<false, true, true>(prm, grid, s); else launch_tc4<false, false, true>(prm, grid, s); }
+      else { if (save) launch_tc4<false, true, false>(prm, grid, s); else launch_tc4<false, false, false>(prm, grid, s); }
+    }
     if (timing) {
       CUDA_CHECK(cudaStreamSynchronize(s));
       std::vector<long long> h((size_t)8 * prm.num_rounds);
@@ -1446,7 +819,7 @@ bool run_tc(TCParams prm, cudaStream_t s) {   // returns true when G was written
         if (r + 1 < r1) d[5] += (double)(h[(r + 1) * 8] - h[r * 8 + 5]);
       }
       const double n = r1 - r0;
-      fprintf(stderr, "[tc4 %s M=%lld rounds=%d] cycles/tile: S1+E1 %.0f | E2 %.0f | wait S3 %.0f | E3 %.0f | build next %.0f | gap %.0f | total %.0f\n",
+      fprintf(stderr, "[tc4 %s M=%lld rounds=%d] cycles/tile: S1+E1 %.0f | E2 %.0f | wait S3 %.0f | E3 %.0f | - %.0f | store a1 %.0f | total %.0f\n",
               kBwd ? "bwd" : "fwd", prm.M, prm.num_rounds, d[0] / n, d[1] / n, d[2] / n, d[3] / n, d[4] / n,
               d[5] / std::max(1.0, n - 1), (double)(h[(r1 - 1) * 8 + 5] - h[r0 * 8]) / n);
       double ld = 0;
@@ -1455,67 +828,20 @@ bool run_tc(TCParams prm, cudaStream_t s) {   // returns true when G was written
     }
     return true;
   }
-  if (g_pair_mode != 2) {
-    const bool pair = g_pair_mode == 1;
-    const int rows = pair ? 2 * kTileM : kTileM;
-    const long long ptiles = (prm.M + rows - 1) / rows;
-    const int pairs = (int)std::min<long long>(ptiles, pair ? g_num_sms / 2 : g_num_sms);
-    prm.tiles_per_cta_round = pairs;
-    prm.num_rounds = (int)((ptiles + pairs - 1) / pairs);
-    static long long* dbg = nullptr;
-    const bool timing = getenv("ASEP_TC_DBG_TIMING") != nullptr;
-    if (timing) {
-      if (!dbg) CUDA_CHECK(cudaMalloc(&dbg, 8 * 4096 * sizeof(long long)));
-      ASEP_CHECK(prm.num_rounds <= 4096, ASEP_ERR_BAD_ARG, "too many rounds for the timing buffer");
-      prm.dbg_out = dbg;
-    }
-    const bool save = !kBwd && prm.mask1 != nullptr;
-    if (pair) { if (save) launch_tc2<kBwd, true, true>(prm, 2 * pairs, s); else launch_tc2<kBwd, false, true>(prm, 2 * pairs, s); }
-    else { if (save) launch_tc2<kBwd, true, false>(prm, pairs, s); else launch_tc2<kBwd, false, false>(prm, pairs, s); }
-    if (timing) {
-      CUDA_CHECK(cudaStreamSynchronize(s));
-      std::vector<long long> h((size_t)8 * prm.num_rounds);
-      CUDA_CHECK(cudaMemcpy(h.data(), dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
-      double d[8] = {0};
-      const int r0 = prm.num_rounds > 2 ? 1 : 0, r1 = prm.num_rounds;
-      for (int r = r0; r < r1; ++r) {
-        for (int i = 0; i < 7; ++i) d[i] += (double)(h[r * 8 + i + 1] - h[r * 8 + i]);
-        if (r + 1 < r1) d[7] += (double)(h[(r + 1) * 8] - h[r * 8 + 7]);
-      }
-      const double n = r1 - r0;
-      fprintf(stderr, "[tc2 %s M=%lld rounds=%d] cycles/tile: build %.0f | wait1 %.0f epi1 %.0f | wait2 %.0f epi2 %.0f | wait3 %.0f epi3 %.0f | gap %.0f | total %.0f\n",
-              kBwd ? "bwd" : "fwd", prm.M, prm.num_rounds, d[0] / n, d[1] / n, d[2] / n, d[3] / n, d[4] / n, d[5] / n, d[6] / n,
-              d[7] / std::max(1.0, n - 1), (double)(h[(r1 - 1) * 8 + 7] - h[r0 * 8]) / n);
-    }
-    return false;
-  }
-  const int cs = g_cluster;
-  const long long tiles = (prm.M + kTileM - 1) / kTileM;
-  int grid = (int)std::min<long long>(tiles, g_num_sms);
-  grid = (grid + cs - 1) / cs * cs;          // whole clusters; surplus CTAs run masked tiles
-  if (grid > g_num_sms) grid = g_num_sms / cs * cs;
-  prm.tiles_per_cta_round = grid;
-  if (const char* e = getenv("ASEP_TC_DBG_SHIFT")) prm.dbg_shift = atoi(e);
-  if (const char* e = getenv("ASEP_TC_DBG_FLAGS")) prm.dbg_flags = atoi(e);
-  prm.num_rounds = (int)((tiles + grid - 1) / grid);
-  switch (cs) {
-    case 1: launch_tc<1, kBwd>(prm, grid, s); break;
-    case 2: launch_tc<2, kBwd>(prm, grid, s); break;
-    case 4: launch_tc<4, kBwd>(prm, grid, s); break;
-    default: throw Error(ASEP_ERR_BAD_ARG, strfmt("cluster size %d not built (1, 2, 4)", cs));
-  }
-  return false;
 }
 
 }  // namespace
 
-void nn_tc_set_cluster(int cluster_size) {
+void nn_tc_set_cluster(int cluster_size) {      // retained knob: the K-pipelined kernel does not multicast
   ASEP_CHECK(cluster_size == 1 || cluster_size == 2 || cluster_size == 4, ASEP_ERR_BAD_ARG,
              "cluster size must be 1, 2 or 4");
   g_cluster = cluster_size;
 }
 int nn_tc_get_cluster() { return g_cluster; }
-void nn_tc_set_pair_mode(int on) { g_pair_mode = on; }
+void nn_tc_set_pair_mode(int on) {
+  ASEP_CHECK(on == 3, ASEP_ERR_UNSUPPORTED, "only kernel variant 3 (k_nn_tc4) is built; the serial / CTA-pair variants were retired");
+  g_pair_mode = on;
+}
 int nn_tc_get_pair_mode() { return g_pair_mode; }
 
 void nn_tc_profile(int on) {
@@ -1544,7 +870,7 @@ size_t nn_tc_g_floats(long long M, int C) { return (size_t)((M + kTileM - 1) / k
 
 void nn_tc_prepare(NNWeightsTC& w, const float* k1, const float* c1, const float* g1, const float* b1,
                    const float* k2, const float* c2, const float* g2, const float* b2, const float* k3,
-                   const float* c3, int C, int F) {
+                   const float* c3, int C, int F, bool f16) {
   ASEP_CHECK(F == kF, ASEP_ERR_UNSUPPORTED, "the tcgen05 coupling kernel is built for n_filters = %d (got %d)", kF, F);
   nn_tc_release(w);
   const int Ch = C / 2;
@@ -1557,7 +883,7 @@ void nn_tc_prepare(NNWeightsTC& w, const float* k1, const float* c1, const float
       const int tap = n / C, c = n % C;
       return g2[k] * k3[((size_t)tap * F + k) * C + c];
     };
-    build_stage_set(w.fwd, 2 * K1h, 9 * C, f1, f2, f3);
+    build_stage_set(w.fwd, 2 * K1h, 9 * C, f1, f2, f3, /*fp16 stage-2/3 weights*/ f16);
   }
   // ---------------- backward (data gradient)
   {
@@ -1568,7 +894,7 @@ void nn_tc_prepare(NNWeightsTC& w, const float* k1, const float* c1, const float
     };
     auto f2 = [&](int n, int k) { return g1[n] * k2[(size_t)n * F + k]; };              // diag(g1') K2^T
     auto f3 = [&](int n, int k) { return k1[(size_t)n * F + k]; };                      // n = tap*Ch + ci
-    build_stage_set(w.bwd, 2 * K1h, 9 * Ch, f1, f2, f3);
+    build_stage_set(w.bwd, 2 * K1h, 9 * Ch, f1, f2, f3, false);
   }
   std::vector<float> bias1(c1, c1 + F), bias2(F), const3((size_t)9 * C), vc3(c3, c3 + C);
   for (int n = 0; n < F; ++n) {
@@ -1586,6 +912,7 @@ void nn_tc_prepare(NNWeightsTC& w, const float* k1, const float* c1, const float
   w.bias2 = upload(bias2);
   w.const3 = upload(const3);
   w.c3 = upload(vc3);
+  w.f16 = f16;
 }
 
 void nn_tc_release(NNWeightsTC& w) {
@@ -1607,14 +934,14 @@ void nn_tc_forward(const NNWeightsTC& w, const NNScratchTC& sc, const float* sta
   prm.src = state; prm.src_stride = C; prm.src_off = C / 2; prm.src_ch = C / 2; prm.tap_sign = 1;
   prm.wimg = w.fwd.img; prm.k1_steps = w.fwd.k1_steps; prm.k1_panels = w.fwd.k1_panels; prm.n3p = w.fwd.n3p;
   prm.bias1 = w.bias1; prm.bias2 = w.bias2; prm.mask1 = mask1; prm.mask2 = mask2;
-  prm.dump1 = dump1; prm.dump2 = dump2;
+  prm.dump1 = dump1; prm.dump2 = dump2; prm.f16 = w.f16 ? 1 : 0;
   prm.out = sc.G; prm.H = H; prm.W = W; prm.M = M;
   g_next_flops = 2.0 * (double)M * (9.0 * (C / 2) * kF + (double)kF * kF + 9.0 * kF * C);   // conv MACs x 2, unpadded
   const bool tiled = run_tc<false>(prm, s);
   const long long total = M * C;
-  if (tiled && C % 4 == 0) k_gather_vec<4, true><<<cdiv(total / 4, 256), 256, 0, s>>>(sc.G, w.const3, w.c3, r, H, W, C, w.fwd.n3p, total / 4);
-  else if (tiled) k_gather_fwd<true><<<cdiv(total, 256), 256, 0, s>>>(sc.G, w.const3, w.c3, r, H, W, C, w.fwd.n3p, total);
-  else k_gather_fwd<false><<<cdiv(total, 256), 256, 0, s>>>(sc.G, w.const3, w.c3, r, H, W, C, w.fwd.n3p, total);
+  (void)tiled;
+  if (C % 4 == 0) k_gather_vec<4, true><<<cdiv(total / 4, 256), 256, 0, s>>>(sc.G, w.const3, w.c3, r, H, W, C, w.fwd.n3p, total / 4);
+  else k_gather_fwd<true><<<cdiv(total, 256), 256, 0, s>>>(sc.G, w.const3, w.c3, r, H, W, C, w.fwd.n3p, total);
   ASEP_LAUNCH_CHECK();
 }
 
@@ -1633,10 +960,10 @@ void nn_tc_backward(const NNWeightsTC& w, const NNScratchTC& sc, const float* gr
   g_next_flops = 2.0 * (double)M * (9.0 * (C / 2) * kF + (double)kF * kF + 9.0 * kF * C);
   const bool tiled = run_tc<true>(prm, s);
   const long long total = M * (C / 2);
-  if (tiled && (C / 2) % 4 == 0) k_gather_vec<4, false><<<cdiv(total / 4, 256), 256, 0, s>>>(sc.G, nullptr, nullptr, gxb, H, W, C / 2, w.bwd.n3p, total / 4);
-  else if (tiled && (C / 2) % 2 == 0) k_gather_vec<2, false><<<cdiv(total / 2, 256), 256, 0, s>>>(sc.G, nullptr, nullptr, gxb, H, W, C / 2, w.bwd.n3p, total / 2);
-  else if (tiled) k_gather_bwd<true><<<cdiv(total, 256), 256, 0, s>>>(sc.G, gxb, H, W, C / 2, w.bwd.n3p, total);
-  else k_gather_bwd<false><<<cdiv(total, 256), 256, 0, s>>>(sc.G, gxb, H, W, C / 2, w.bwd.n3p, total);
+  (void)tiled;
+  if ((C / 2) % 4 == 0) k_gather_vec<4, false><<<cdiv(total / 4, 256), 256, 0, s>>>(sc.G, nullptr, nullptr, gxb, H, W, C / 2, w.bwd.n3p, total / 4);
+  else if ((C / 2) % 2 == 0) k_gather_vec<2, false><<<cdiv(total / 2, 256), 256, 0, s>>>(sc.G, nullptr, nullptr, gxb, H, W, C / 2, w.bwd.n3p, total / 2);
+  else k_gather_bwd<true><<<cdiv(total, 256), 256, 0, s>>>(sc.G, gxb, H, W, C / 2, w.bwd.n3p, total);
   ASEP_LAUNCH_CHECK();
 }
 

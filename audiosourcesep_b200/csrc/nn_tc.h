@@ -22,6 +22,7 @@ struct NNWeightsTC {
   float* bias2 = nullptr;   // c2 + b1' . K2                        [F]
   float* const3 = nullptr;  // [9][C]  sum_k b2'[k] K3[tap][k][c]   (border-aware BN offset of conv3)
   float* c3 = nullptr;      // [C]
+  bool f16 = false;         // forward stage-2/3 tile images and hidden activations in fp16 (ASEP_PREC_FP16)
 };
 
 struct NNScratchTC {
@@ -34,7 +35,7 @@ struct NNScratchTC {
 // k1 [3,3,Ch,F], k2 [F,F] (in,out), k3 [3,3,F,C]; g*/b* folded BatchNorm scale/offset.
 void nn_tc_prepare(NNWeightsTC& w, const float* k1, const float* c1, const float* g1, const float* b1,
                    const float* k2, const float* c2, const float* g2, const float* b2, const float* k3,
-                   const float* c3, int C, int F);
+                   const float* c3, int C, int F, bool f16 = false);
 void nn_tc_release(NNWeightsTC& w);
 
 // state [N,H,W,C] (network input = channels C/2..C) -> r [M,C] (conv3 output incl. bias).

@@ -2,6 +2,7 @@
 // allocation and loads, UMMA issue / commit, shared-memory and instruction descriptors.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 namespace asep {
@@ -151,6 +152,24 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
 // a/b K-major, n_dim = N>>3 at [17,23), m_dim = M>>4 at [24,29)
 __host__ __device__ constexpr uint32_t make_idesc(int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+// same with fp16 operands (a/b_format F16 = 0): 10 mantissa bits instead of 7
+__host__ __device__ constexpr uint32_t make_idesc_f16(int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+// relu + round-to-nearest fp16 pair in ONE instruction: low half = max(a, 0), high half = max(b, 0)
+__device__ __forceinline__ uint32_t pack_relu_f16(float a, float b) {
+  uint32_t d;
+  asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+  return d;
+}
+
+__device__ __forceinline__ uint32_t pack_relu_bf16(float a, float b) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+  return d;
 }
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {

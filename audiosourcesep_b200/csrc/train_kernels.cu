@@ -6,6 +6,8 @@
 // 1x1 gradients and the prior gradients, and refresh every per-step constant on the device after an update.
 #include "train_kernels.h"
 
+#include <cuda_fp16.h>
+
 namespace asep {
 
 namespace {
@@ -529,7 +531,7 @@ __device__ __forceinline__ size_t img_off(int r, int k) { return (size_t)r * 64 
 
 __global__ void __launch_bounds__(256) k_build_tc_images(const StepTrainPtrs sp, __nv_bfloat16* __restrict__ fwd,
                                                          __nv_bfloat16* __restrict__ bwd, int k1p_f, int n3p_f, int k1p_b,
-                                                         int n3p_b) {
+                                                         int n3p_b, int f16) {
   const int F = sp.F, C = sp.C, Ch = C / 2;
   const int dir = blockIdx.y;                                   // 0 forward set, 1 backward set
   const int k1p = dir == 0 ? k1p_f : k1p_b, n3p = dir == 0 ? n3p_f : n3p_b;
@@ -581,11 +583,19 @@ __global__ void __launch_bounds__(256) k_build_tc_images(const StepTrainPtrs sp,
       off = (size_t)(n1 + n2) * 8 + (size_t)kp * n3p * 64 + (size_t)r * 64 + (size_t)((ch ^ (r & 7)) << 3);
     }
     uint4 pk;
-    __nv_bfloat162 t2;
-    t2 = __floats2bfloat162_rn(v[0], v[1]); pk.x = *reinterpret_cast<uint32_t*>(&t2);
-    t2 = __floats2bfloat162_rn(v[2], v[3]); pk.y = *reinterpret_cast<uint32_t*>(&t2);
-    t2 = __floats2bfloat162_rn(v[4], v[5]); pk.z = *reinterpret_cast<uint32_t*>(&t2);
-    t2 = __floats2bfloat162_rn(v[6], v[7]); pk.w = *reinterpret_cast<uint32_t*>(&t2);
+    if (f16 && dir == 0 && e >= n1) {      // ASEP_PREC_FP16: forward stage-2 / stage-3 weights are fp16 (nn_tc_prepare)
+      __half2 h2;
+      h2 = __floats2half2_rn(v[0], v[1]); pk.x = *reinterpret_cast<uint32_t*>(&h2);
+      h2 = __floats2half2_rn(v[2], v[3]); pk.y = *reinterpret_cast<uint32_t*>(&h2);
+      h2 = __floats2half2_rn(v[4], v[5]); pk.z = *reinterpret_cast<uint32_t*>(&h2);
+      h2 = __floats2half2_rn(v[6], v[7]); pk.w = *reinterpret_cast<uint32_t*>(&h2);
+    } else {
+      __nv_bfloat162 t2;
+      t2 = __floats2bfloat162_rn(v[0], v[1]); pk.x = *reinterpret_cast<uint32_t*>(&t2);
+      t2 = __floats2bfloat162_rn(v[2], v[3]); pk.y = *reinterpret_cast<uint32_t*>(&t2);
+      t2 = __floats2bfloat162_rn(v[4], v[5]); pk.z = *reinterpret_cast<uint32_t*>(&t2);
+      t2 = __floats2bfloat162_rn(v[6], v[7]); pk.w = *reinterpret_cast<uint32_t*>(&t2);
+    }
     *reinterpret_cast<uint4*>(dst + off) = pk;
   }
 }
@@ -786,9 +796,9 @@ void launch_colsum_bf16(const __nv_bfloat16* X, float* out, long long M, int F, 
 }
 
 void launch_build_tc_step(const StepTrainPtrs& sp, __nv_bfloat16* fwd_img, __nv_bfloat16* bwd_img, int k1p_f, int n3p_f,
-                          int k1p_b, int n3p_b, float* bias1, float* bias2, float* const3, float* c3, cudaStream_t s) {
+                          int k1p_b, int n3p_b, float* bias1, float* bias2, float* const3, float* c3, bool f16, cudaStream_t s) {
   dim3 grid(296, 2);
-  k_build_tc_images<<<grid, 256, 0, s>>>(sp, fwd_img, bwd_img, k1p_f, n3p_f, k1p_b, n3p_b);
+  k_build_tc_images<<<grid, 256, 0, s>>>(sp, fwd_img, bwd_img, k1p_f, n3p_f, k1p_b, n3p_b, f16 ? 1 : 0);
   ASEP_LAUNCH_CHECK();
   k_build_tc_biases<<<16, 512, 0, s>>>(sp, bias1, bias2, const3, c3);   // F = 512 (checked by nn_tc_prepare)
   ASEP_LAUNCH_CHECK();

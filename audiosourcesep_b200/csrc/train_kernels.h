@@ -38,7 +38,7 @@ void launch_s3(const float* gr, float* S3, int N, int H, int W, int C, cudaStrea
 void launch_colsum_bf16(const __nv_bfloat16* X, float* out, long long M, int F, cudaStream_t s);
 // device twin of nn_tc_prepare: tile images of both directions + folded biases of one step
 void launch_build_tc_step(const StepTrainPtrs& sp, __nv_bfloat16* fwd_img, __nv_bfloat16* bwd_img, int k1p_f, int n3p_f,
-                          int k1p_b, int n3p_b, float* bias1, float* bias2, float* const3, float* c3, cudaStream_t s);
+                          int k1p_b, int n3p_b, float* bias1, float* bias2, float* const3, float* c3, bool f16, cudaStream_t s);
 void launch_prior_grads(const float* z, const float* loc, const float* ls, float* gloc, float* gls, int N, int D, float gs,
                         cudaStream_t s);
 void launch_loss(const double* acc_ld, const double* acc_prior, const double* cst, double extra_const, int N,

@@ -44,6 +44,9 @@ typedef enum {
 typedef enum {
   ASEP_PREC_FP32 = 0, /* CUDA-core fp32 kernels: bit-level "exact" mode used as the on-device checker   */
   ASEP_PREC_BF16 = 1, /* tcgen05 (UMMA) bf16 x bf16 -> fp32 TMEM accumulation: the production path      */
+  ASEP_PREC_FP16 = 3,  /* Glow only: as ASEP_PREC_BF16 but the hidden activations / stage-2,3 weights of the forward
+                        * coupling network are fp16 (10 mantissa bits): ~8x closer to fp32, ~8 % slower under the
+                        * power cap.  The data-gradient pass stays bf16 (gradients have unbounded range).        */
   ASEP_PREC_BF16X3 = 2 /* score networks only: activations and weights as (hi + lo) bf16 pairs, three tcgen05
                         * products per convolution (hi.hi + lo.hi + hi.lo), fp32 accumulation: ~2^-16 relative */
 } asep_precision;

@@ -25,7 +25,7 @@ def _glow(cfg, params, precision):
 
 def _prec(name):
     from audiosourcesep_b200 import _lib
-    return {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16}[name]
+    return {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16, "fp16": _lib.PREC_FP16}[name]
 
 
 def _np(t):
@@ -210,7 +210,7 @@ def test_coupling_nn_fp32_matches_oracle():
 
 
 # ----------------------------------------------------------------- config-shape model (96x64, 512 filters)
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16", "fp16"])
 def test_glow_config_shape_vs_oracle(precision):
     cfg = GlowConfig(H=96, W=64, C=1, L=3, K=4, n_filters=512, minval=-100.0, maxval=20.0)
     p = init_glow_params(cfg, seed=2, mode="perturbed")
@@ -230,7 +230,10 @@ def test_glow_config_shape_vs_oracle(precision):
     # round-trip gate (<= 1e-4) holds in the exact mode.  With bf16 hidden activations the coupling
     # network is piecewise constant at the 2^-9 level, so inverse() -- which re-evaluates it on inputs
     # that differ from forward()'s by fp32 round-off -- reconstructs only to ~1e-2 (documented limit).
-    assert rt <= (1e-4 if precision == "fp32" else 3e-2), rt
+    # ASEP_PREC_FP16 (fp16 hidden activations, 2^-12) tightens it ~8x but still misses the gate.
+    assert rt <= {"fp32": 1e-4, "bf16": 3e-2, "fp16": 4e-3}[precision], rt
+    if precision == "fp16":
+        assert np.max(np.abs(lp - lp_o)) / D <= 2e-4
     g_o, _ = o.grad_log_prob(x)
     g = _np(m.grad_log_prob(torch.as_tensor(x)))
     rel = np.linalg.norm(g - g_o.numpy()) / np.linalg.norm(g_o.numpy())

@@ -31,11 +31,11 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--K", type=int, default=40)
     ap.add_argument("--batches", type=int, nargs="+", default=[32, 256, 1024])
-    ap.add_argument("--clusters", type=int, nargs="+", default=[1, 2, 4])
+    ap.add_argument("--clusters", type=int, nargs="+", default=[1])
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--grad", action="store_true")
     ap.add_argument("--fp32", action="store_true")
-    ap.add_argument("--pair", type=int, nargs="+", default=[0])
+    ap.add_argument("--pair", type=int, nargs="+", default=[3])
     a = ap.parse_args()
     cfg = GlowConfig(K=a.K)
     t0 = time.time()
