@@ -386,7 +386,6 @@ __global__ void __launch_bounds__(kThreadsTC2, 1) k_nn_tc4(const TCParams prm) {
         for (int k = 2 * 9 * prm.src_ch; k < k1_pad; k += 2)      // both bounds are even
           *reinterpret_cast<uint32_t*>(sA + a_offset(row, k)) = 0u;
       fence_proxy_async();
-      if (wtid == 0) bulk_wait_read_all();          // the previous tile's G rows have left the staging area (E1 will overwrite it)
       arrive_warp(a1_ready);
     };
     auto build = [&](int round) {
@@ -426,8 +425,7 @@ __global__ void __launch_bounds__(kThreadsTC2, 1) k_nn_tc4(const TCParams prm) {
       //      stored before anything else so that S1 runs while the previous tile's G rows are still leaving (one call
       //      site: the unrolled im2col code is large)
       if (prefetch_regs) {
-        if (round == 0) prefetch_a1(0);
-        store_a1();
+        if (round == 0) { prefetch_a1(0); store_a1(); }       // later tiles: stored at the end of the previous iteration
       } else {
         build(round);
       }
@@ -453,7 +451,10 @@ __global__ void __launch_bounds__(kThreadsTC2, 1) k_nn_tc4(const TCParams prm) {
             mkl[0] = m0.x; mkl[1] = m0.y; mkl[2] = m0.z; mkl[3] = m0.w; mkh[0] = m1.x; mkh[1] = m1.y; mkh[2] = m1.z; mkh[3] = m1.w;
           }
         }
-        if constexpr (!kBwd) named_bar_sync(1, kWorkers2);      // bias vector of this layer is in sBias
+        // the previous tile's G rows must have left the staging area (the tail of the operand panels) before any warp
+        // overwrites it with h1; forward: the same barrier publishes this layer's bias vector in sBias
+        if (gemm == 0 && wtid == 0) bulk_wait_read_all();
+        if (!kBwd || gemm == 0) named_bar_sync(1, kWorkers2);
 #pragma unroll 1
         for (int hh = 0; hh < 2; ++hh) {
           // accumulator uses per tile: H0 = S1, S2, S3 (3 per tile); H1 = S1, S2 (2 per tile)
@@ -557,6 +558,9 @@ __global__ void __launch_bounds__(kThreadsTC2, 1) k_nn_tc4(const TCParams prm) {
       mbar_wait(accfull0, (uint32_t)(round + 2) & 1u);
       tc_fence_after();
       if (stamp) ts[3] = clock64();
+      // next tile's operand rows first (registers -> panels), so that its stage-1 MMAs run while G is drained
+      if (prefetch_regs && round + 1 < prm.num_rounds) store_a1();
+      if (stamp) ts[4] = clock64();
       // drain the small-N accumulator: TMEM -> registers -> fp32 staging rows in the (now free) tail of the operand
       // panels -> ONE TMA bulk store of the tile's contiguous G rows.  (Direct st.global of 16 B per row costs one
       // LSU wavefront each: ~2000 cycles per tile.)  Two 16-column chunks per wait; the two warps of a lane quarter
@@ -589,7 +593,6 @@ __global__ void __launch_bounds__(kThreadsTC2, 1) k_nn_tc4(const TCParams prm) {
             bulk_s2g(prm.out + tile * kTileM * prm.n3p, smem_u32(stg), (uint32_t)(kTileM * prm.n3p * 4));
         }
       }
-      if (stamp) ts[4] = clock64();
       if (stamp) ts[5] = clock64();
     }
     if (wtid == 0) bulk_wait_all();
@@ -819,7 +822,7 @@ bool run_tc(TCParams prm, cudaStream_t s) {   // returns true when G was written
         if (r + 1 < r1) d[5] += (double)(h[(r + 1) * 8] - h[r * 8 + 5]);
       }
       const double n = r1 - r0;
-      fprintf(stderr, "[tc4 %s M=%lld rounds=%d] cycles/tile: S1+E1 %.0f | E2 %.0f | wait S3 %.0f | E3 %.0f | - %.0f | store a1 %.0f | total %.0f\n",
+      fprintf(stderr, "[tc4 %s M=%lld rounds=%d] cycles/tile: S1+E1 %.0f | E2 %.0f | wait S3 %.0f | store next a1 %.0f | E3 %.0f | gap %.0f | total %.0f\n",
               kBwd ? "bwd" : "fwd", prm.M, prm.num_rounds, d[0] / n, d[1] / n, d[2] / n, d[3] / n, d[4] / n,
               d[5] / std::max(1.0, n - 1), (double)(h[(r1 - 1) * 8 + 5] - h[r0 * 8]) / n);
       double ld = 0;
