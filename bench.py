@@ -204,7 +204,8 @@ def run_ours(args):
     from audiosourcesep_b200 import GlowConfig, _lib, ops, synthetic
     from audiosourcesep_b200.glow import Glow
     from audiosourcesep_b200.weights import init_glow_params
-    from oracle import basis_oracle as bo
+    # (the product path never touches oracle/: the sigma schedule and step constants come from the package)
+    from audiosourcesep_b200.ncsn import utils as bo
 
     dev = torch.device("cuda", local_rank)
     peaks = _peaks()
@@ -320,7 +321,7 @@ def run_ours(args):
         mixed_d = torch.as_tensor(mixed).to(dev)
         t1, t2 = torch.as_tensor(x1).to(dev), torch.as_tensor(x2).to(dev)
         sig = bo.get_sigmas(1.0, 0.01, 10, "logarithmic")
-        eta, lam, ns = bo.step_constants(sig, 9)
+        eta, lam, ns = bo.langevin_step_constants(sig, 9)
         T = args.basis_T
         stepno = [0]
 
@@ -357,7 +358,7 @@ def run_ours(args):
             a1, a2 = synthetic.langevin_init(nseg, seed=7 + rank)
             u1, u2 = torch.as_tensor(a1).to(dev), torch.as_tensor(a2).to(dev)
             idx = ncfg.num_classes - 1
-            eta_n, lam_n, ns_n = bo.step_constants(sig_n, idx)
+            eta_n, lam_n, ns_n = bo.langevin_step_constants(sig_n, idx)
             cnt = [0]
 
             def step_ncsn():

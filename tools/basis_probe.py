@@ -3,7 +3,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from audiosourcesep_b200 import GlowConfig, ops, _lib, synthetic
 from audiosourcesep_b200.glow import Glow
 from audiosourcesep_b200.weights import init_glow_params
-from oracle import basis_oracle as bo
+from audiosourcesep_b200.ncsn import utils as bo
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 cfg = GlowConfig(K=40, minval=0.0, maxval=1.0)
 m1 = Glow(cfg, init_glow_params(cfg, seed=2), precision=_lib.PREC_BF16)
@@ -12,7 +12,7 @@ mixed, _, _ = synthetic.basis_problem(32)
 mixed = torch.as_tensor(np.concatenate([mixed] * (N // 32))).cuda()
 x1, x2 = synthetic.langevin_init(N, seed=4)
 t1, t2 = torch.as_tensor(x1).cuda(), torch.as_tensor(x2).cuda()
-sig = bo.get_sigmas(1.0, 0.01, 10, "logarithmic"); eta, lam, ns = bo.step_constants(sig, 9)
+sig = bo.get_sigmas(1.0, 0.01, 10, "logarithmic"); eta, lam, ns = bo.langevin_step_constants(sig, 9)
 def timeit(fn, it=3):
     fn(); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

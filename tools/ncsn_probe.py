@@ -5,8 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from audiosourcesep_b200 import NCSNConfig, synthetic, _lib
 from audiosourcesep_b200.weights import init_ncsn_params
 from audiosourcesep_b200.ncsn.score_model import ScoreModel
-from oracle import basis_oracle as bo
-from oracle.ncsn_oracle import NCSNOracle
+from audiosourcesep_b200.ncsn import utils as bo
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--version", default="v1")
@@ -22,6 +21,7 @@ if a.check:
     x = synthetic.normalise(synthetic.mel_patches_db(2, seed=1))
     idx = np.array([0, cfg.num_classes - 1], dtype=np.int32)
     got = m([torch.as_tensor(x), torch.as_tensor(idx)]).cpu().numpy()
+    from oracle.ncsn_oracle import NCSNOracle          # development check only
     o = NCSNOracle(cfg, p, sigmas=sig, dtype=torch.float32)
     want = o.score(x, idx).numpy()
     print("finite", np.isfinite(got).all(), "rel err", np.linalg.norm(got - want) / np.linalg.norm(want),
