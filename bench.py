@@ -143,6 +143,11 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 for its workers; the reference arm runs on rank 0 alone and takes every core
+    try:
+        torch.set_num_threads(max(torch.get_num_threads(), os.cpu_count() or 1))
+    except RuntimeError:
+        pass
     cores = torch.get_num_threads()
     sample = args.cpu_sample
     _, oracle = _cpu_model(args.K)
