@@ -37,59 +37,94 @@ __global__ void __launch_bounds__(256) k_conv1(const float* __restrict__ state, 
 
 // Tiled SGEMM  out[M,Nn] = epi( (sa[k]*A[m][k]+oa[k]) . B[k][n] )
 //   kEpi 0: relu(acc + bias[n])        kEpi 1: acc * scale[n] * (mask[m][n] > 0)
+// 128 x 128 x 16 tiles, 256 threads, 8 x 8 outputs per thread (two 4-wide strips in each direction so that every
+// shared-memory read is a float4), next tile prefetched into registers while the current one is multiplied.  Every
+// output is one fmaf chain over ascending k (the summation order of the reference's fp32 matmul restatement).
 template <int kEpi>
 __global__ void __launch_bounds__(256) k_sgemm(const float* __restrict__ A, const float* __restrict__ sa,
                                                const float* __restrict__ oa, const float* __restrict__ B,
                                                const float* __restrict__ vec, const float* __restrict__ mask,
                                                float* __restrict__ out, long long M, int Nn, int K) {
-  constexpr int BM = 64, BN = 64, BK = 16;
-  __shared__ float As[BK][BM + 1];
-  __shared__ float Bs[BK][BN];
-  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+  constexpr int BM = 128, BN = 128, BK = 16, LDA = BM + 4;
+  __shared__ __align__(16) float As[2][BK][LDA];
+  __shared__ __align__(16) float Bs[2][BK][BN];
+  const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
   const long long m0 = (long long)blockIdx.y * BM;
   const int n0 = blockIdx.x * BN;
-  float acc[4][4] = {};
-  for (int k0 = 0; k0 < K; k0 += BK) {
-    for (int i = threadIdx.x; i < BM * BK; i += 256) {
-      int mm = i / BK, kk = i % BK;
-      long long m = m0 + mm;
-      float v = 0.f;
+  // loaders: A tile = 128 rows x 4 float4 (k), B tile = 16 rows (k) x 32 float4 (n); two of each per thread
+  const int ar = tid / 4, ak = (tid % 4) * 4;           // rows ar and ar + 64
+  const int bk = tid / 32, bn = (tid % 32) * 4;         // k rows bk and bk + 8
+  float4 pa[2], pb[2];
+  auto load_tiles = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const long long m = m0 + ar + 64 * i;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (m < M) {
-        v = A[m * K + k0 + kk];
-        if (sa != nullptr) v = sa[k0 + kk] * v + oa[k0 + kk];
+        v = *reinterpret_cast<const float4*>(A + m * K + k0 + ak);
+        if (sa != nullptr) {
+          const float4 s4 = *reinterpret_cast<const float4*>(sa + k0 + ak), o4 = *reinterpret_cast<const float4*>(oa + k0 + ak);
+          v.x = s4.x * v.x + o4.x; v.y = s4.y * v.y + o4.y; v.z = s4.z * v.z + o4.z; v.w = s4.w * v.w + o4.w;
+        }
       }
-      As[kk][mm] = v;
+      pa[i] = v;
+      pb[i] = n0 + bn < Nn ? *reinterpret_cast<const float4*>(B + (long long)(k0 + bk + 8 * i) * Nn + n0 + bn)
+                           : make_float4(0.f, 0.f, 0.f, 0.f);      // partial column tile (Nn % 4 == 0)
     }
-    for (int i = threadIdx.x; i < BK * BN; i += 256) {
-      int kk = i / BN, nn = i % BN;
-      Bs[kk][nn] = B[(long long)(k0 + kk) * Nn + n0 + nn];
+  };
+  auto store_tiles = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      As[buf][ak + 0][ar + 64 * i] = pa[i].x; As[buf][ak + 1][ar + 64 * i] = pa[i].y;
+      As[buf][ak + 2][ar + 64 * i] = pa[i].z; As[buf][ak + 3][ar + 64 * i] = pa[i].w;
+      *reinterpret_cast<float4*>(&Bs[buf][bk + 8 * i][bn]) = pb[i];
     }
-    __syncthreads();
+  };
+  float acc[8][8] = {};
+  load_tiles(0);
+  store_tiles(0);
+  __syncthreads();
+  int buf = 0;
+  for (int k0 = 0; k0 < K; k0 += BK) {
+    const bool more = k0 + BK < K;
+    if (more) load_tiles(k0 + BK);
 #pragma unroll
     for (int kk = 0; kk < BK; ++kk) {
-      float a[4], b[4];
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][kk][64 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][kk][64 + tx * 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+      for (int i = 0; i < 8; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
     }
-    __syncthreads();
+    if (more) {
+      store_tiles(buf ^ 1);        // the other buffer was last read one iteration ago (before the previous barrier)
+      __syncthreads();
+      buf ^= 1;
+    }
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    long long m = m0 + ty * 4 + i;
+  for (int i = 0; i < 8; ++i) {
+    const long long m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
     if (m >= M) continue;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      int n = n0 + tx * 4 + j;
-      float v = acc[i][j];
-      if constexpr (kEpi == 0) v = fmaxf(v + vec[n], 0.f);
-      else v = (mask[m * Nn + n] > 0.f) ? v * vec[n] : 0.f;
-      out[m * Nn + n] = v;
+    for (int jh = 0; jh < 2; ++jh) {
+      const int n = n0 + jh * 64 + tx * 4;
+      if (n >= Nn) continue;
+      float4 v = make_float4(acc[i][4 * jh], acc[i][4 * jh + 1], acc[i][4 * jh + 2], acc[i][4 * jh + 3]);
+      const float4 w4 = *reinterpret_cast<const float4*>(vec + n);
+      if constexpr (kEpi == 0) {
+        v.x = fmaxf(v.x + w4.x, 0.f); v.y = fmaxf(v.y + w4.y, 0.f); v.z = fmaxf(v.z + w4.z, 0.f); v.w = fmaxf(v.w + w4.w, 0.f);
+      } else {
+        const float4 mk = *reinterpret_cast<const float4*>(mask + m * Nn + n);
+        v.x = mk.x > 0.f ? v.x * w4.x : 0.f; v.y = mk.y > 0.f ? v.y * w4.y : 0.f;
+        v.z = mk.z > 0.f ? v.z * w4.z : 0.f; v.w = mk.w > 0.f ? v.w * w4.w : 0.f;
+      }
+      *reinterpret_cast<float4*>(out + m * Nn + n) = v;
     }
   }
 }
@@ -213,7 +248,7 @@ void nn_fp32_forward(const NNWeightsF32& w, const float* state, float* a1, float
   ASEP_CHECK(F % 64 == 0, ASEP_ERR_UNSUPPORTED, "n_filters must be a multiple of 64 (got %d)", F);
   k_conv1<<<cdiv(M * F, 256), 256, 0, s>>>(state, w.k1, w.c1, a1, N, H, W, C, F);
   ASEP_LAUNCH_CHECK();
-  dim3 grid(F / 64, cdiv(M, 64));
+  dim3 grid((unsigned)cdiv(F, 128), (unsigned)cdiv(M, 128));
   k_sgemm<0><<<grid, 256, 0, s>>>(a1, w.g1, w.b1, w.k2, w.c2, nullptr, a2, M, F, F);
   ASEP_LAUNCH_CHECK();
   DISPATCH_NNC(C, (k_conv3<kC><<<cdiv(M * 32, 256), 256, 0, s>>>(a2, w.g2, w.b2, w.k3, w.c3, r, N, H, W, F)));
@@ -228,7 +263,7 @@ void nn_fp32_backward(const NNWeightsF32& w, const float* a1, const float* a2, c
   k_conv3_bwd<<<cdiv(M * F, 256), 256, 0, s>>>(gr, w.k3, w.g2, a2, t2, N, H, W, C, F);
   ASEP_LAUNCH_CHECK();
   // t1 = gp1 = (gp2 . K2^T) * g1 * [p1 > 0]
-  dim3 grid(F / 64, cdiv(M, 64));
+  dim3 grid((unsigned)cdiv(F, 128), (unsigned)cdiv(M, 128));
   k_sgemm<1><<<grid, 256, 0, s>>>(t2, nullptr, nullptr, w.k2t, w.g1, a1, t1, M, F, F);
   ASEP_LAUNCH_CHECK();
   DISPATCH_NNC(C / 2, (k_conv1_bwd<kC><<<cdiv(M * 32, 256), 256, 0, s>>>(t1, w.k1, gxb, N, H, W, F)));

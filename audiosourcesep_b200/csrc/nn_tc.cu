@@ -15,15 +15,15 @@
 // BatchNorm runs in inference mode in the reference, so its affine is folded
 // into the next GEMM's weights on the host (nn_tc_prepare).
 //
-// Pipeline per CTA (192 threads, persistent over tiles, 1 CTA / SM):
-//   warp 0    producer: streams pre-swizzled bf16 weight tile images (32 KB) with TMA bulk copies
-//             (cp.async.bulk -> UBLKCP) into a 3-stage ring; with a cluster of CS CTAs every CTA
-//             loads 1/CS of each image and multicasts it to all CS rings (L2 traffic / CS).
-//   warp 1    MMA issuer: one elected thread issues tcgen05.mma (M=128, N<=256, K=16) with A and B
-//             SWIZZLE_128B shared-memory descriptors, fp32 accumulators in TMEM (512 columns);
-//             tcgen05.commit releases ring slots (multicast to the cluster) and signals epilogues.
-//   warps 2-5 workers: build the stage-1 operand, run the epilogues (tcgen05.ld 32x32b -> bias +
-//             ReLU (+ mask bits for the backward pass) -> bf16 -> swizzled st.shared), write G.
+// Pipeline per CTA (320 threads, persistent over tiles, 1 CTA / SM) -- see the comment above k_nn_tc4:
+//   warp 0     producer: streams pre-swizzled 16-bit weight tile images (32 KB) with TMA bulk copies
+//              (cp.async.bulk -> UBLKCP) into a 3-stage ring.
+//   warp 1     MMA issuer: one thread issues tcgen05.mma (M=128, N<=256, K=16) with A and B
+//              SWIZZLE_128B shared-memory descriptors, fp32 accumulators in TMEM (512 columns);
+//              tcgen05.commit releases ring slots and signals the epilogues.
+//   warps 2-9  workers: build the stage-1 operand, run the epilogues (tcgen05.ld 32x32b -> bias +
+//              ReLU (+ mask bits for the backward pass) -> bf16 / fp16 -> swizzled st.shared), stage G
+//              for the TMA bulk store.
 //
 // The data-gradient kernel is the same pipeline with transposed weights:
 //   stage 1  conv3^T: A = im2col(gr) (split-bf16, K = 2*9*C), B = diag(g2') K3^T, epilogue = ReLU mask 2
@@ -32,12 +32,9 @@
 #include "nn_tc.h"
 #include "tc_ptx.cuh"
 
-#include <cooperative_groups.h>
 #include <cstring>
 
 namespace asep {
-
-namespace cg = cooperative_groups;
 
 namespace {
 
@@ -50,9 +47,6 @@ constexpr int kStageRows = 256;
 constexpr int kStageBytes = kStageRows * 128;    // 32 KB weight tile image
 constexpr int kStages = 3;
 constexpr int kBiasBytes = kF * 4;                // one fp32 bias vector staged in shared memory
-constexpr int kBarBytes = 128;
-constexpr int kSmemBytes = kARegionBytes + kStages * kStageBytes + kBiasBytes + kBarBytes;   // 231,552 B
-constexpr int kThreadsTC = 192;
 constexpr int kTmemCols = 512;
 
 struct TCParams {
@@ -73,7 +67,6 @@ struct TCParams {
   __nv_bfloat16* dump1;      // optional [M, 512] bf16 copies of the stage-1 / stage-2 epilogue outputs (training:
   __nv_bfloat16* dump2;      //   forward a1 = relu(p1), a2 = relu(p2); backward gp2 = dL/dp2, gp1 = dL/dp1)
   long long* dbg_out;        // debug: per-tile phase timestamps of CTA 0 (clock64), 8 per round
-  int dbg_flags;             // debug: 1 skip MMA, 2 skip operand build, 4 skip G store, 8 skip epilogue 1/2 bodies
   int f16;                   // forward: fp16 hidden activations / stage-2,3 weights
   int dbg_shift;             // debug: load only bytes >> dbg_shift of every weight image (timing experiments)
   int tiles_per_cta_round;   // grid size (all CTAs advance together)
@@ -803,7 +796,6 @@ bool run_tc(TCParams prm, cudaStream_t s) {   // returns true when G was written
       prm.dbg_out = dbg;
     }
     if (const char* e = getenv("ASEP_TC_DBG_SHIFT")) prm.dbg_shift = atoi(e);
-    if (const char* e = getenv("ASEP_TC_DBG_FLAGS")) prm.dbg_flags = atoi(e);
     if constexpr (kBwd) {
       launch_tc4<true, false, false>(prm, grid, s);
     } else {
