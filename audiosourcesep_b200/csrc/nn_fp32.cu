@@ -9,30 +9,29 @@ namespace asep {
 namespace {
 
 // a1[p][f] = relu(c1[f] + sum_{tap,ci} xb[p+off(tap)][ci] * K1[tap][ci][f])
+// grid (pixel, F / 256): a block owns one pixel (its tap inputs are warp-uniform loads) and 256 output channels
+// (coalesced weight reads and stores); pixel coordinates from 32-bit divisions (M < 2^31).
 __global__ void __launch_bounds__(256) k_conv1(const float* __restrict__ state, const float* __restrict__ k1,
-                                               const float* __restrict__ c1, float* __restrict__ a1, int N, int H,
-                                               int W, int C, int F) {
+                                               const float* __restrict__ c1, float* __restrict__ a1, int H, int W, int C,
+                                               int F) {
   const int Ch = C / 2;
-  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  long long total = (long long)N * H * W * F;
-  if (idx >= total) return;
-  int f = idx % F;
-  long long p = idx / F;
-  int w = p % W;
-  int h = (p / W) % H;
+  const unsigned p = blockIdx.x;
+  const int f = blockIdx.y * 256 + threadIdx.x;
+  if (f >= F) return;
+  const int w = (int)(p % (unsigned)W), h = (int)((p / (unsigned)W) % (unsigned)H);
   float acc = c1[f];
   for (int dy = -1; dy <= 1; ++dy) {
-    int hh = h + dy;
+    const int hh = h + dy;
     if (hh < 0 || hh >= H) continue;
     for (int dx = -1; dx <= 1; ++dx) {
-      int ww = w + dx;
+      const int ww = w + dx;
       if (ww < 0 || ww >= W) continue;
-      const float* xin = state + (p + (long long)dy * W + dx) * C + Ch;
+      const float* xin = state + ((long long)p + (long long)dy * W + dx) * C + Ch;
       const float* kk = k1 + ((dy + 1) * 3 + (dx + 1)) * Ch * F + f;
-      for (int ci = 0; ci < Ch; ++ci) acc = fmaf(xin[ci], kk[ci * F], acc);
+      for (int ci = 0; ci < Ch; ++ci) acc = fmaf(__ldg(xin + ci), kk[ci * F], acc);
     }
   }
-  a1[idx] = fmaxf(acc, 0.f);
+  a1[(long long)p * F + f] = fmaxf(acc, 0.f);
 }
 
 // Tiled SGEMM  out[M,Nn] = epi( (sa[k]*A[m][k]+oa[k]) . B[k][n] )
@@ -169,15 +168,14 @@ __global__ void __launch_bounds__(256) k_conv3(const float* __restrict__ a2, con
 // gp2[p][k] = g2[k] * [a2[p][k] > 0] * sum_{tap} sum_c gr[p - off(tap)][c] * K3[tap][k][c]
 __global__ void __launch_bounds__(256) k_conv3_bwd(const float* __restrict__ gr, const float* __restrict__ k3,
                                                    const float* __restrict__ g2, const float* __restrict__ a2,
-                                                   float* __restrict__ gp2, int N, int H, int W, int C, int F) {
-  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  long long total = (long long)N * H * W * F;
-  if (idx >= total) return;
-  int k = idx % F;
-  long long p = idx / F;
+                                                   float* __restrict__ gp2, int H, int W, int C, int F) {
+  // grid (pixel, F / 256), as k_conv1
+  const unsigned pu = blockIdx.x;
+  const int k = blockIdx.y * 256 + threadIdx.x;
+  if (k >= F) return;
+  const long long p = pu, idx = p * F + k;
   if (!(a2[idx] > 0.f)) { gp2[idx] = 0.f; return; }
-  int w = p % W;
-  int h = (p / W) % H;
+  const int w = (int)(pu % (unsigned)W), h = (int)((pu / (unsigned)W) % (unsigned)H);
   float acc = 0.f;
   for (int dy = -1; dy <= 1; ++dy) {
     int hh = h - dy;
@@ -246,7 +244,8 @@ void nn_fp32_forward(const NNWeightsF32& w, const float* state, float* a1, float
   long long M = (long long)N * H * W;
   if (M == 0) return;
   ASEP_CHECK(F % 64 == 0, ASEP_ERR_UNSUPPORTED, "n_filters must be a multiple of 64 (got %d)", F);
-  k_conv1<<<cdiv(M * F, 256), 256, 0, s>>>(state, w.k1, w.c1, a1, N, H, W, C, F);
+  ASEP_CHECK(M < (1ll << 31), ASEP_ERR_UNSUPPORTED, "more than 2^31 pixels in one coupling-network launch");
+  k_conv1<<<dim3((unsigned)M, (unsigned)cdiv(F, 256)), 256, 0, s>>>(state, w.k1, w.c1, a1, H, W, C, F);
   ASEP_LAUNCH_CHECK();
   dim3 grid((unsigned)cdiv(F, 128), (unsigned)cdiv(M, 128));
   k_sgemm<0><<<grid, 256, 0, s>>>(a1, w.g1, w.b1, w.k2, w.c2, nullptr, a2, M, F, F);
@@ -260,7 +259,8 @@ void nn_fp32_backward(const NNWeightsF32& w, const float* a1, const float* a2, c
   long long M = (long long)N * H * W;
   if (M == 0) return;
   // t2 = gp2 = conv3^T(gr) * g2 * [p2 > 0]
-  k_conv3_bwd<<<cdiv(M * F, 256), 256, 0, s>>>(gr, w.k3, w.g2, a2, t2, N, H, W, C, F);
+  ASEP_CHECK(M < (1ll << 31), ASEP_ERR_UNSUPPORTED, "more than 2^31 pixels in one coupling-network launch");
+  k_conv3_bwd<<<dim3((unsigned)M, (unsigned)cdiv(F, 256)), 256, 0, s>>>(gr, w.k3, w.g2, a2, t2, H, W, C, F);
   ASEP_LAUNCH_CHECK();
   // t1 = gp1 = (gp2 . K2^T) * g1 * [p1 > 0]
   dim3 grid((unsigned)cdiv(F, 128), (unsigned)cdiv(M, 128));
