@@ -152,9 +152,9 @@ __device__ __forceinline__ void build_a1_taps(uint8_t* sA, int row, const float*
 // im2col of up to five taps [t_begin, t_end) of one operand row, split in a LOAD half (global -> registers, issued
 // while the worker is idle) and a STORE half (split-bf16 [hi | lo] -> swizzled shared memory, once the panels are free)
 template <int SC>
-__device__ __forceinline__ void a1_load(float (&v)[20], const float* __restrict__ src, long long p, bool valid, int h, int w,
+__device__ __forceinline__ void a1_load(float (&v)[40], const float* __restrict__ src, long long p, bool valid, int h, int w,
                                         int H, int W, int stride, int off, int sign, int t_begin, int t_end) {
-  static_assert(SC <= 4, "register prefetch is sized for <= 4 source channels");
+  static_assert(SC <= 8, "register prefetch is sized for <= 8 source channels");
 #pragma unroll
   for (int tt = 0; tt < 5; ++tt) {
     const int tap = t_begin + tt;
@@ -162,7 +162,12 @@ __device__ __forceinline__ void a1_load(float (&v)[20], const float* __restrict_
     const int hh = h + dy, ww = w + dx;
     const bool ok = valid && tap < t_end && hh >= 0 && hh < H && ww >= 0 && ww < W;
     const float* s = src + (p + (long long)dy * W + dx) * stride + off;
-    if constexpr (SC == 4) {
+    if constexpr (SC == 8) {
+      const float4 t = ok ? __ldg(reinterpret_cast<const float4*>(s)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 u = ok ? __ldg(reinterpret_cast<const float4*>(s) + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+      v[8 * tt] = t.x; v[8 * tt + 1] = t.y; v[8 * tt + 2] = t.z; v[8 * tt + 3] = t.w;
+      v[8 * tt + 4] = u.x; v[8 * tt + 5] = u.y; v[8 * tt + 6] = u.z; v[8 * tt + 7] = u.w;
+    } else if constexpr (SC == 4) {
       const float4 t = ok ? __ldg(reinterpret_cast<const float4*>(s)) : make_float4(0.f, 0.f, 0.f, 0.f);
       v[4 * tt] = t.x; v[4 * tt + 1] = t.y; v[4 * tt + 2] = t.z; v[4 * tt + 3] = t.w;
     } else if constexpr (SC == 2) {
@@ -174,7 +179,7 @@ __device__ __forceinline__ void a1_load(float (&v)[20], const float* __restrict_
   }
 }
 template <int SC>
-__device__ __forceinline__ void a1_store(uint8_t* sA, int row, const float (&v)[20], int t_begin, int t_end) {
+__device__ __forceinline__ void a1_store(uint8_t* sA, int row, const float (&v)[40], int t_begin, int t_end) {
   constexpr int K1h = 9 * SC;
 #pragma unroll
   for (int tt = 0; tt < 5; ++tt) {
@@ -192,9 +197,14 @@ __device__ __forceinline__ void a1_store(uint8_t* sA, int row, const float (&v)[
     } else if constexpr (SC == 2) {
       *reinterpret_cast<uint32_t*>(sA + a_offset(row, k0)) = pack_bf16(hi[0], hi[1]);
       *reinterpret_cast<uint32_t*>(sA + a_offset(row, K1h + k0)) = pack_bf16(lo[0], lo[1]);
-    } else {
+    } else if constexpr (SC == 4) {
       *reinterpret_cast<uint2*>(sA + a_offset(row, k0)) = make_uint2(pack_bf16(hi[0], hi[1]), pack_bf16(hi[2], hi[3]));
       *reinterpret_cast<uint2*>(sA + a_offset(row, K1h + k0)) = make_uint2(pack_bf16(lo[0], lo[1]), pack_bf16(lo[2], lo[3]));
+    } else {
+      *reinterpret_cast<uint4*>(sA + a_offset(row, k0)) =
+          make_uint4(pack_bf16(hi[0], hi[1]), pack_bf16(hi[2], hi[3]), pack_bf16(hi[4], hi[5]), pack_bf16(hi[6], hi[7]));
+      *reinterpret_cast<uint4*>(sA + a_offset(row, K1h + k0)) =
+          make_uint4(pack_bf16(lo[0], lo[1]), pack_bf16(lo[2], lo[3]), pack_bf16(lo[4], lo[5]), pack_bf16(lo[6], lo[7]));
     }
   }
 }
@@ -384,19 +394,19 @@ __global__ void __launch_bounds__(kThreadsTC2, 1) k_nn_tc4(const TCParams prm) {
     auto build = [&](int round) {
       long long p; bool valid; int h, w;
       row_coords(round, p, valid, h, w);
-      if (prm.src_ch == 8) build_a1_taps<8>(sA, row, prm.src, p, valid, h, w, prm.H, prm.W, prm.src_stride, prm.src_off, prm.tap_sign, tb, te);
-      else build_a1_taps<16>(sA, row, prm.src, p, valid, h, w, prm.H, prm.W, prm.src_stride, prm.src_off, prm.tap_sign, tb, te);
+      build_a1_taps<16>(sA, row, prm.src, p, valid, h, w, prm.H, prm.W, prm.src_stride, prm.src_off, prm.tap_sign, tb, te);
       finish_a1();
     };
     // <= 4 source channels: the next tile's taps are fetched into registers while this tile's stage 2 is running
-    const bool prefetch_regs = prm.src_ch <= 4;
-    float pre[20];
+    const bool prefetch_regs = prm.src_ch <= 8;
+    float pre[40];
     auto prefetch_a1 = [&](int round) {
       long long p; bool valid; int h, w;
       row_coords(round, p, valid, h, w);
       switch (prm.src_ch) {
         case 1: a1_load<1>(pre, prm.src, p, valid, h, w, prm.H, prm.W, prm.src_stride, prm.src_off, prm.tap_sign, tb, te); break;
         case 2: a1_load<2>(pre, prm.src, p, valid, h, w, prm.H, prm.W, prm.src_stride, prm.src_off, prm.tap_sign, tb, te); break;
+        case 8: a1_load<8>(pre, prm.src, p, valid, h, w, prm.H, prm.W, prm.src_stride, prm.src_off, prm.tap_sign, tb, te); break;
         default: a1_load<4>(pre, prm.src, p, valid, h, w, prm.H, prm.W, prm.src_stride, prm.src_off, prm.tap_sign, tb, te); break;
       }
     };
@@ -404,6 +414,7 @@ __global__ void __launch_bounds__(kThreadsTC2, 1) k_nn_tc4(const TCParams prm) {
       switch (prm.src_ch) {
         case 1: a1_store<1>(sA, row, pre, tb, te); break;
         case 2: a1_store<2>(sA, row, pre, tb, te); break;
+        case 8: a1_store<8>(sA, row, pre, tb, te); break;
         default: a1_store<4>(sA, row, pre, tb, te); break;
       }
       finish_a1();
