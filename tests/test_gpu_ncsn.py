@@ -154,3 +154,25 @@ def test_anneal_langevin_dynamics_matches_oracle():
     rel = np.linalg.norm(got - want) / np.linalg.norm(want)
     print(f"annealed Langevin sampler relative state error = {rel:.3e}")
     assert rel <= 1e-3, rel
+
+
+@pytest.mark.parametrize("version", ["v1", "v2"])
+def test_score_is_sample_wise_at_the_bench_size(version):
+    """30 segments (n_mixed of run_basis_sep.py:478): the score of a segment may not depend on the other segments of
+    the batch (instance norms are per sample, score_network.py:204-207).  The statistics are accumulated with
+    double-precision atomics in arrival order, so the comparison is to 1e-5 relative rather than bit-exact."""
+    cfg = _cfg(version)
+    params = init_ncsn_params(cfg, seed=5, mode="perturbed")
+    model, _ = _model(cfg, params)
+    x = torch.as_tensor(synthetic.normalise(synthetic.mel_patches_db(30, seed=2))).cuda()
+    idx = torch.full((30,), cfg.num_classes - 1, dtype=torch.int32, device="cuda")
+    s = model([x, idx], training=True)
+    assert torch.isfinite(s).all()
+    perm = torch.randperm(30, generator=torch.Generator().manual_seed(1)).cuda()
+    s_perm = model([x[perm].contiguous(), idx], training=True)
+    rel = float((s_perm - s[perm]).norm() / s.norm())
+    s_one = model([x[7:8].contiguous(), idx[:1]], training=True)
+    rel1 = float((s_one - s[7:8]).norm() / s[7:8].norm())
+    print(f"[{version}] permutation {rel:.2e}, single segment {rel1:.2e}")
+    assert rel <= 1e-5 and rel1 <= 1e-5, (rel, rel1)
+    assert model([x[:0].contiguous(), idx[:0]], training=True).shape == (0, 96, 64, 1)      # empty batch
