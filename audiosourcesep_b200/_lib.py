@@ -21,6 +21,8 @@ PREC_FP32 = 0
 PREC_BF16 = 1
 PREC_FP16 = 3       # Glow: tcgen05 with fp16 hidden activations in the forward network (closer to fp32, ~8 % slower)
 PREC_BF16X3 = 2     # score networks: split-bf16 operands, three tcgen05 products per convolution
+PREC_BF16X2 = 4     # Glow: tcgen05 "exact" mode, hidden activations as (hi + lo) bf16 pairs (round trip <= 1e-4)
+PREC_FP16X2 = 5     # Glow: as BF16X2 with fp16 pairs (22 bits; hidden activations must stay below 65504)
 
 
 class AsepError(RuntimeError):
@@ -102,8 +104,6 @@ _SIGNATURES = {
     "asep_conv_profile": [_I],
     "asep_conv_profile_read": [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64),
                                ctypes.POINTER(ctypes.c_double)],
-    "asep_tc_set_cluster": [_I],
-    "asep_tc_set_pair_mode": [_I],
     "asep_tc_profile": [_I],
     "asep_tc_profile_read": [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64),
                              ctypes.POINTER(ctypes.c_double)],

@@ -508,6 +508,7 @@ int asep_basis_glow_inner(asep_glow_t m1, asep_glow_t m2, const DLTensor* mixed,
   TView a = view_f32(x1, "x1", dev), b = view_f32(x2, "x2", dev), mx = view_f32(mixed, "mixed", dev);
   const int N = batch_of(a, g1, "x1");
   ASEP_CHECK(batch_of(b, g2, "x2") == N && mx.numel == a.numel, ASEP_ERR_BAD_SHAPE, "x1, x2, mixed must match");
+  ASEP_CHECK(g2.device() == dev, ASEP_ERR_BAD_DEVICE, "the two priors live on different devices");
   ASEP_CHECK((noise1 == nullptr) == (noise2 == nullptr), ASEP_ERR_BAD_ARG, "inject both noise tensors or neither");
   const float *nz1 = nullptr, *nz2 = nullptr;
   if (noise1) {
@@ -524,8 +525,11 @@ int asep_basis_glow_inner(asep_glow_t m1, asep_glow_t m2, const DLTensor* mixed,
   int* nanp = nullptr;
   if (nan_count) nanp = static_cast<int*>(view_i32(nan_count, "nan_count", dev).raw);
   cudaStream_t s = as_stream(stream);
-  float* s1 = g1.score_scratch(N);
-  float* s2 = g2.score_scratch(N);
+  // model1 and model2 are just callables in the reference (run_basis_sep.py:166-175): the same prior may serve both
+  // sources, in which case its scratch holds two score tensors
+  const bool same = &g1 == &g2;
+  float* s1 = g1.score_scratch(N, same ? 2 : 1);
+  float* s2 = same ? s1 + a.numel : g2.score_scratch(N);
   for (int t = 0; t < T; ++t) {
     g1.grad_log_prob(a.f32, s1, nullptr, N, s);     // run_basis_sep.py:174-175
     g2.grad_log_prob(b.f32, s2, nullptr, N, s);
@@ -633,7 +637,12 @@ int asep_basis_ncsn_inner(asep_ncsn_t m1, asep_ncsn_t m2, const DLTensor* mixed,
   const int N = (int)a.shape[0];
   expect_shape(b, "x2", {N, c.H, c.W, c.C});
   ASEP_CHECK(mx.numel == a.numel, ASEP_ERR_BAD_SHAPE, "x1, x2, mixed must match");
-  ASEP_CHECK(sigma_idx >= 0 && sigma_idx < c.num_classes, ASEP_ERR_BAD_ARG, "sigma_idx %d out of range", sigma_idx);
+  const auto& c2 = g2.cfg();
+  ASEP_CHECK(c2.H == c.H && c2.W == c.W && c2.C == c.C, ASEP_ERR_BAD_SHAPE,
+             "the two score networks must share the data shape (%dx%dx%d vs %dx%dx%d)", c.H, c.W, c.C, c2.H, c2.W, c2.C);
+  ASEP_CHECK(g2.device() == dev, ASEP_ERR_BAD_DEVICE, "the two score networks live on different devices");
+  ASEP_CHECK(sigma_idx >= 0 && sigma_idx < c.num_classes && sigma_idx < c2.num_classes, ASEP_ERR_BAD_ARG,
+             "sigma_idx %d out of range (num_classes %d / %d)", sigma_idx, c.num_classes, c2.num_classes);
   ASEP_CHECK((noise1 == nullptr) == (noise2 == nullptr), ASEP_ERR_BAD_ARG, "inject both noise tensors or neither");
   const float *nz1 = nullptr, *nz2 = nullptr;
   if (noise1) {
@@ -650,8 +659,11 @@ int asep_basis_ncsn_inner(asep_ncsn_t m1, asep_ncsn_t m2, const DLTensor* mixed,
   int* nanp = nullptr;
   if (nan_count) nanp = static_cast<int*>(view_i32(nan_count, "nan_count", dev).raw);
   cudaStream_t s = as_stream(stream);
-  float* s1 = g1.score_scratch(N);
-  float* s2 = g2.score_scratch(N);
+  // model1 and model2 are just callables in the reference (run_basis_sep.py:166-175): the same prior may serve both
+  // sources, in which case its scratch holds two score tensors
+  const bool same = &g1 == &g2;
+  float* s1 = g1.score_scratch(N, same ? 2 : 1);
+  float* s2 = same ? s1 + a.numel : g2.score_scratch(N);
   const int* idx = g1.index_scratch(N, sigma_idx, s);               // run_basis_sep.py:167-168
   for (int t = 0; t < T; ++t) {
     g1.forward(a.f32, idx, s1, N, s);                               // run_basis_sep.py:169-170
@@ -680,18 +692,6 @@ int asep_conv_profile_read(double* total_ms, int64_t* launches, double* flops) {
   long long n = 0;
   conv_tc_profile_read(total_ms, &n, flops);
   if (launches) *launches = (int64_t)n;
-  ASEP_API_END
-}
-
-int asep_tc_set_cluster(int cluster_size) {
-  ASEP_API_BEGIN
-  nn_tc_set_cluster(cluster_size);
-  ASEP_API_END
-}
-
-int asep_tc_set_pair_mode(int on) {
-  ASEP_API_BEGIN
-  nn_tc_set_pair_mode(on);
   ASEP_API_END
 }
 

@@ -292,9 +292,10 @@ __global__ void k_prior_sample(const float* __restrict__ eps, const float* __res
   z[i] = (loc ? loc[d] : 0.f) + expf(ls ? ls[d] : 0.f) * eps[i];
 }
 
-__global__ void k_finish(const double* __restrict__ acc, float* __restrict__ out, double add, double scale, int N) {
+__global__ void k_finish(const double* __restrict__ acc, float* __restrict__ out, double add, const double* __restrict__ dev_add,
+                         double scale, int N) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < N) out[i] = (float)((acc[i] + add) * scale);
+  if (i < N) out[i] = (float)((acc[i] + add + (dev_add ? *dev_add : 0.0)) * scale);
 }
 
 // mean and population std per channel over M pixels (ActNorm init, flow_tfp_bijectors.py:222-226)
@@ -425,9 +426,9 @@ void launch_prior_sample(const float* eps, const float* loc, const float* log_sc
   ASEP_LAUNCH_CHECK();
 }
 
-void launch_finish(const double* acc, float* out, double add, double scale, int N, cudaStream_t s) {
+void launch_finish(const double* acc, float* out, double add, double scale, int N, cudaStream_t s, const double* dev_add) {
   if (N == 0) return;
-  k_finish<<<cdiv(N, 128), 128, 0, s>>>(acc, out, add, scale, N);
+  k_finish<<<cdiv(N, 128), 128, 0, s>>>(acc, out, add, dev_add, scale, N);
   ASEP_LAUNCH_CHECK();
 }
 

@@ -228,13 +228,27 @@ void GlowModel::build_step_consts(int b, int k) {
   sd.logdet_const = (double)levels_[b].H * levels_[b].W * (sum_ls + sum_lw);   // :250-253, :319-322
 }
 
+void GlowModel::invalidate_graphs() {
+  if (tgraph_.exec) {
+    cudaDeviceSynchronize();                 // a replay may still be in flight on the private stream
+    cudaGraphExecDestroy(tgraph_.exec);
+    tgraph_.exec = nullptr;
+  }
+  tg_calls_ = 0;                             // the next train_grads runs eagerly and re-sizes its scratch
+}
+
 void GlowModel::prepare(int precision) {
-  ASEP_CHECK(precision == ASEP_PREC_FP32 || precision == ASEP_PREC_BF16 || precision == ASEP_PREC_FP16, ASEP_ERR_BAD_ARG, "unknown precision %d",
-             precision);
+  const bool tc_mode = precision == ASEP_PREC_BF16 || precision == ASEP_PREC_FP16 || precision == ASEP_PREC_BF16X2 ||
+                       precision == ASEP_PREC_FP16X2;
+  const bool f16_mode = precision == ASEP_PREC_FP16 || precision == ASEP_PREC_FP16X2;
+  ASEP_CHECK(precision == ASEP_PREC_FP32 || tc_mode, ASEP_ERR_BAD_ARG, "unknown precision %d", precision);
+  ASEP_CHECK(!(training_ && (precision == ASEP_PREC_BF16X2 || precision == ASEP_PREC_FP16X2)), ASEP_ERR_UNSUPPORTED,
+             "the split-precision modes have no weight-gradient path: train in ASEP_PREC_BF16 / FP16 / FP32");
   const int F = cfg_.n_filters;
-  if (precision == ASEP_PREC_BF16 || precision == ASEP_PREC_FP16)
+  if (tc_mode)
     ASEP_CHECK(F == kTcF, ASEP_ERR_UNSUPPORTED, "the tcgen05 modes need n_filters = %d (got %d)", kTcF, F);
   CUDA_CHECK(cudaSetDevice(device_));
+  invalidate_graphs();                       // the per-step constants and tile images below are re-allocated
   for (int b = 0; b < cfg_.L; ++b) {
     const int C = levels_[b].C;
     for (int k = 0; k < cfg_.K; ++k) {
@@ -270,11 +284,11 @@ void GlowModel::prepare(int precision) {
       sd.w32.c2 = params_.at(pre + "conv2/bias").dev;
       sd.w32.g2 = sd.g2; sd.w32.b2 = sd.b2;
       sd.w32.k3 = params_.at(pre + "conv3/kernel").dev; sd.w32.c3 = params_.at(pre + "conv3/bias").dev;
-      if (precision == ASEP_PREC_BF16 || precision == ASEP_PREC_FP16) {
+      if (tc_mode) {
         nn_tc_prepare(sd.wtc, params_.at(pre + "conv1/kernel").host.data(), params_.at(pre + "conv1/bias").host.data(),
                       g1.data(), b1.data(), k2.data(), params_.at(pre + "conv2/bias").host.data(), g2.data(),
                       b2.data(), params_.at(pre + "conv3/kernel").host.data(),
-                      params_.at(pre + "conv3/bias").host.data(), C, F, precision == ASEP_PREC_FP16);
+                      params_.at(pre + "conv3/bias").host.data(), C, F, f16_mode);
       } else {
         nn_tc_release(sd.wtc);
       }
@@ -288,9 +302,13 @@ void GlowModel::prepare(int precision) {
   prepared_ = true;
 }
 
+// Constant part of the log-det.  While training is enabled the per-step constants live on the device (ld_total_ is
+// refreshed by derive_on_device after every optimizer step / set_flat): the host sum would be stale, so only the
+// SpecPreprocessing term is returned here and launch_finish adds *const_logdet_dev().
 double GlowModel::const_logdet() const {
   double s = 0.0;
-  for (const auto& sd : steps_) s += sd.logdet_const;
+  if (!training_)
+    for (const auto& sd : steps_) s += sd.logdet_const;
   // SpecPreprocessing fldj: D * log(1/(max-min))      flow_tfp_bijectors.py:390-396
   s += (double)cfg_.H * cfg_.W * cfg_.C * std::log(1.0 / ((double)cfg_.maxval - (double)cfg_.minval));
   return s;
@@ -324,6 +342,7 @@ void GlowModel::ensure_work(int N, bool save) {
   for (int pass = 0; pass < 2; ++pass) {
     if (pass == 1) {
       CUDA_CHECK(cudaDeviceSynchronize());
+      invalidate_graphs();                   // the arena is re-carved (and possibly re-allocated)
       arena_.reserve(bytes);
       work_ = Work{};
       work_.N = N;
@@ -367,7 +386,8 @@ void GlowModel::ensure_work(int N, bool save) {
     } else {
       size_t gfl = 0;
       for (int b = 0; b < L; ++b)
-        gfl = std::max(gfl, nn_tc_g_floats((long long)N * levels_[b].H * levels_[b].W, levels_[b].C));
+        gfl = std::max(gfl, is_tcx() ? nn_tcx_g_floats((long long)N * levels_[b].H * levels_[b].W, levels_[b].C)
+                                     : nn_tc_g_floats((long long)N * levels_[b].H * levels_[b].W, levels_[b].C));
       tc.G = get(gfl);
       if (save) {
         tc.mask1 = reinterpret_cast<uint32_t*>(get((size_t)M0 * (F / 32)));
@@ -391,7 +411,8 @@ void GlowModel::nn_forward(int b, int k, const float* state, float* r, int N, bo
   } else {
     uint32_t *m1 = nullptr, *m2 = nullptr;
     if (save && !work_.M1.empty() && !work_.M1[b].empty()) { m1 = work_.M1[b][k]; m2 = work_.M2[b][k]; }
-    nn_tc_forward(sd.wtc, work_.tc, state, r, m1, m2, N, lv.H, lv.W, lv.C, s);
+    if (is_tcx()) nn_tcx_forward(sd.wtc, work_.tc, state, r, m1, m2, N, lv.H, lv.W, lv.C, s);
+    else nn_tc_forward(sd.wtc, work_.tc, state, r, m1, m2, N, lv.H, lv.W, lv.C, s);
   }
 }
 
@@ -404,6 +425,10 @@ void GlowModel::nn_backward(int b, int k, const float* state, const float* gr, f
     nn_fp32_forward(sd.w32, state, work_.a1, work_.a2, work_.gxb /*scratch r*/, N, lv.H, lv.W, lv.C,
                     cfg_.n_filters, s);
     nn_fp32_backward(sd.w32, work_.a1, work_.a2, gr, work_.t1, work_.t2, gxb, N, lv.H, lv.W, lv.C, cfg_.n_filters, s);
+  } else if (is_tcx()) {
+    nn_tcx_forward(sd.wtc, work_.tc, state, work_.gxb /*scratch r*/, work_.tc.mask1, work_.tc.mask2, N, lv.H, lv.W,
+                   lv.C, s);
+    nn_tcx_backward(sd.wtc, work_.tc, gr, work_.tc.mask1, work_.tc.mask2, gxb, N, lv.H, lv.W, lv.C, s);
   } else {
     nn_tc_forward(sd.wtc, work_.tc, state, work_.gxb /*scratch r*/, work_.tc.mask1, work_.tc.mask2, N, lv.H, lv.W,
                   lv.C, s);
@@ -441,8 +466,8 @@ void GlowModel::run_forward(const float* x, int N, bool save, cudaStream_t s) {
   }
 }
 
-float* GlowModel::score_scratch(int N) {
-  const size_t need = (size_t)N * cfg_.H * cfg_.W * cfg_.C * sizeof(float);
+float* GlowModel::score_scratch(int N, int slots) {
+  const size_t need = (size_t)slots * N * cfg_.H * cfg_.W * cfg_.C * sizeof(float);
   if (need > score_cap_) {
     CUDA_CHECK(cudaDeviceSynchronize());
     if (score_buf_) cudaFree(score_buf_);
@@ -457,7 +482,7 @@ void GlowModel::forward(const float* x, float* z, float* fldj, int N, cudaStream
   if (N == 0) return;
   run_forward(x, N, false, s);
   CUDA_CHECK(cudaMemcpyAsync(z, work_.z, (size_t)N * Dl_ * sizeof(float), cudaMemcpyDeviceToDevice, s));
-  launch_finish(work_.acc_ld, fldj, const_logdet(), 1.0, N, s);
+  launch_finish(work_.acc_ld, fldj, const_logdet(), 1.0, N, s, const_logdet_dev());
 }
 
 void GlowModel::log_prob(const float* x, float* logp, int N, cudaStream_t s) {
@@ -466,7 +491,7 @@ void GlowModel::log_prob(const float* x, float* logp, int N, cudaStream_t s) {
   const float* loc = cfg_.learntop ? params_.at("prior/loc").dev : nullptr;
   const float* ls = cfg_.learntop ? params_.at("prior/log_scale").dev : nullptr;
   launch_prior(work_.z, loc, ls, work_.acc_ld, nullptr, N, Dl_, s);
-  launch_finish(work_.acc_ld, logp, const_logdet(), 1.0, N, s);
+  launch_finish(work_.acc_ld, logp, const_logdet(), 1.0, N, s, const_logdet_dev());
 }
 
 void GlowModel::grad_log_prob(const float* x, float* grad, float* logp, int N, cudaStream_t s) {
@@ -476,7 +501,7 @@ void GlowModel::grad_log_prob(const float* x, float* grad, float* logp, int N, c
   const float* loc = cfg_.learntop ? params_.at("prior/loc").dev : nullptr;
   const float* ls = cfg_.learntop ? params_.at("prior/log_scale").dev : nullptr;
   launch_prior(work_.z, loc, ls, work_.acc_ld, work_.gz, N, Dl_, s);
-  if (logp) launch_finish(work_.acc_ld, logp, const_logdet(), 1.0, N, s);
+  if (logp) launch_finish(work_.acc_ld, logp, const_logdet(), 1.0, N, s, const_logdet_dev());
   // reverse sweep; gX holds the gradient w.r.t. the (squeezed) input state of the block below
   float* gX_next = nullptr;   // gradient w.r.t. X[b+1]
   for (int b = L - 1; b >= 0; --b) {
@@ -491,7 +516,9 @@ void GlowModel::grad_log_prob(const float* x, float* grad, float* logp, int N, c
     launch_split_merge(gy, work_.gz, gX_next, N, lv.H, lv.W, lv.C, Cz, nb, CL_, coff, Dl_, 1, s);
     for (int k = 0; k < K; ++k) {          // steps were applied K-1..0, so unwind 0..K-1
       launch_bwd_coupling(gy, work_.U[b][k], work_.R[b][k], work_.gr, work_.gu, M, lv.C, s);
-      if (is_tc() && !work_.M1.empty() && !work_.M1[b].empty())
+      if (is_tcx() && !work_.M1.empty() && !work_.M1[b].empty())
+        nn_tcx_backward(step(b, k).wtc, work_.tc, work_.gr, work_.M1[b][k], work_.M2[b][k], work_.gxb, N, lv.H, lv.W, lv.C, s);
+      else if (is_tc() && !work_.M1.empty() && !work_.M1[b].empty())
         nn_tc_backward(step(b, k).wtc, work_.tc, work_.gr, work_.M1[b][k], work_.M2[b][k], work_.gxb, N, lv.H, lv.W, lv.C, s);
       else
         nn_backward(b, k, work_.U[b][k], work_.gr, work_.gxb, N, s);

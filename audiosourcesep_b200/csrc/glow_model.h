@@ -82,7 +82,7 @@ class GlowModel {
   void set_flat(const float* src, cudaStream_t s);          // src (device) -> theta, refresh constants
 
   // persistent scratch for a score tensor [N,H,W,C] (BASIS inner loop), grown on demand
-  float* score_scratch(int N);
+  float* score_scratch(int N, int slots = 1);   // slots = 2: room for both sources when one handle serves as both priors
 
   const asep_glow_cfg& cfg() const { return cfg_; }
   int device() const { return device_; }
@@ -110,6 +110,7 @@ class GlowModel {
   void build_step_consts(int b, int k);
   void require_prepared() const;
   double const_logdet() const;
+  const double* const_logdet_dev() const { return training_ ? ld_total_ : nullptr; }
   void latent_slice(int b, int& Cz, int& nb, int& coff) const;
 
   void derive_on_device(cudaStream_t s);
@@ -133,6 +134,10 @@ class GlowModel {
     bool noisy = false;
     long long launches = 0;
   } tgraph_;
+  // Every captured graph bakes in device pointers of the workspace arena, the training dumps, the per-step constants
+  // and the weight tile images: whenever one of those allocations is re-made (ensure_work with a larger batch,
+  // ensure_train_dumps, prepare / init_actnorm / sync_host) the graphs are dropped and the next call runs eagerly.
+  void invalidate_graphs();
   float *tg_x_ = nullptr, *tg_noise_ = nullptr, *tg_grads_ = nullptr, *tg_loss_ = nullptr;
   size_t tg_x_cap_ = 0;
   cudaStream_t tg_stream_ = nullptr;
@@ -149,7 +154,8 @@ class GlowModel {
   std::vector<StepDerived> steps_;
   bool prepared_ = false;
   int precision_ = ASEP_PREC_FP32;
-  bool is_tc() const { return precision_ == ASEP_PREC_BF16 || precision_ == ASEP_PREC_FP16; }   // tcgen05 modes
+  bool is_tcx() const { return precision_ == ASEP_PREC_BF16X2 || precision_ == ASEP_PREC_FP16X2; }   // split-precision tcgen05
+  bool is_tc() const { return precision_ == ASEP_PREC_BF16 || precision_ == ASEP_PREC_FP16 || is_tcx(); }   // tcgen05 modes
   DeviceArena arena_;
   Work work_;
   float* score_buf_ = nullptr;

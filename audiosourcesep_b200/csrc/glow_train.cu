@@ -22,6 +22,8 @@ bool trainable_name(const std::string& n) {
 void GlowModel::enable_training() {
   if (training_) return;
   ASEP_CHECK(prepared_, ASEP_ERR_STATE, "call asep_glow_prepare() before asep_glow_enable_training()");
+  ASEP_CHECK(!is_tcx(), ASEP_ERR_UNSUPPORTED,
+             "the split-precision modes have no weight-gradient path: prepare with ASEP_PREC_BF16 / FP16 / FP32 to train");
   ASEP_CHECK(cfg_.learntop, ASEP_ERR_UNSUPPORTED, "the training step expects the learnable top prior (learntop)");
   CUDA_CHECK(cudaSetDevice(device_));
   CUDA_CHECK(cudaDeviceSynchronize());
@@ -103,6 +105,7 @@ void GlowModel::derive_on_device(cudaStream_t s) {
 void GlowModel::ensure_train_dumps(long long rows) {
   if (rows <= dump_rows_) return;
   CUDA_CHECK(cudaDeviceSynchronize());
+  invalidate_graphs();
   for (__nv_bfloat16** p : {&da1_, &da2_, &dgp2_, &dgp1_, &dcol_})
     if (*p) { cudaFree(*p); *p = nullptr; }
   const size_t n = (size_t)rows * cfg_.n_filters;

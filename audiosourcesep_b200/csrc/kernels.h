@@ -38,7 +38,10 @@ void launch_prior(const float* z, const float* loc, const float* log_scale, doub
 // z = loc + exp(ls) * eps
 void launch_prior_sample(const float* eps, const float* loc, const float* log_scale, float* z, int N, int D,
                          cudaStream_t s);
-void launch_finish(const double* acc, float* out, double add, double scale, int N, cudaStream_t s);
+// out[n] = (acc[n] + add + *dev_add) * scale   (dev_add: optional device-resident constant, e.g. the sum of the per-step
+// log-det constants that the training path keeps on the device)
+void launch_finish(const double* acc, float* out, double add, double scale, int N, cudaStream_t s,
+                   const double* dev_add = nullptr);
 void launch_channel_stats(const float* x, double* mean_std, long long M, int C, cudaStream_t s);
 void launch_scale(float* x, float a, long long n, cudaStream_t s);
 void launch_actnorm(const float* x, const float* log_scale, const float* shift, float* y, long long M, int C,

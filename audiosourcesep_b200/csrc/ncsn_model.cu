@@ -27,8 +27,8 @@ NcsnModel::~NcsnModel() {
   if (idx_buf_) cudaFree(idx_buf_);
 }
 
-float* NcsnModel::score_scratch(int N) {
-  const size_t need = (size_t)N * cfg_.H * cfg_.W * cfg_.C * sizeof(float);
+float* NcsnModel::score_scratch(int N, int slots) {
+  const size_t need = (size_t)slots * N * cfg_.H * cfg_.W * cfg_.C * sizeof(float);
   if (need > score_cap_) {
     CUDA_CHECK(cudaDeviceSynchronize());
     if (score_buf_) cudaFree(score_buf_);

@@ -32,7 +32,7 @@ class NcsnModel {
   int device() const { return device_; }
   int64_t num_params() const;
   // persistent scratch of the BASIS inner loop: a score tensor [N,H,W,1] and a constant sigma index vector [N]
-  float* score_scratch(int N);
+  float* score_scratch(int N, int slots = 1);   // slots = 2: room for both sources when one handle serves as both priors
   const int* index_scratch(int N, int sigma_idx, cudaStream_t s);
 
  private:

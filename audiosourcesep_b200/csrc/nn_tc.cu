@@ -29,185 +29,11 @@
 //   stage 1  conv3^T: A = im2col(gr) (split-bf16, K = 2*9*C), B = diag(g2') K3^T, epilogue = ReLU mask 2
 //   stage 2  B = diag(g1') K2^T, epilogue = ReLU mask 1
 //   stage 3  conv1^T as GEMM + col2im: B = K1 (N = 9*C/2), gather sums G'[p-off(tap)][tap].
-#include "nn_tc.h"
-#include "tc_ptx.cuh"
-
-#include <cstring>
+#include "nn_tc_shared.cuh"
 
 namespace asep {
 
 namespace {
-
-constexpr int kF = kTcF;
-constexpr int kTileM = 128;
-constexpr int kPanelBytes = kTileM * 128;        // one 64-wide bf16 K panel of the A operand
-constexpr int kNumPanels = kF / 64;              // 8
-constexpr int kARegionBytes = kNumPanels * kPanelBytes;   // 128 KB
-constexpr int kStageRows = 256;
-constexpr int kStageBytes = kStageRows * 128;    // 32 KB weight tile image
-constexpr int kStages = 3;
-constexpr int kBiasBytes = kF * 4;                // one fp32 bias vector staged in shared memory
-constexpr int kTmemCols = 512;
-
-struct TCParams {
-  const float* src;      // fwd: state [M, C]; bwd: gr [M, C]
-  int src_stride;        // floats per pixel row
-  int src_off;           // first channel used
-  int src_ch;            // channels used (fwd C/2, bwd C)
-  int tap_sign;          // +1: A row p reads pixel p+off(tap) (fwd); -1: p-off(tap) (bwd)
-  const __nv_bfloat16* wimg;
-  int k1_steps, k1_panels, n3p;
-  const float* bias1;    // fwd only
-  const float* bias2;
-  uint32_t* mask1;       // fwd: optional output; bwd: input
-  uint32_t* mask2;
-  float* out;            // [M, n3p]
-  int H, W;
-  long long M;
-  __nv_bfloat16* dump1;      // optional [M, 512] bf16 copies of the stage-1 / stage-2 epilogue outputs (training:
-  __nv_bfloat16* dump2;      //   forward a1 = relu(p1), a2 = relu(p2); backward gp2 = dL/dp2, gp1 = dL/dp1)
-  long long* dbg_out;        // debug: per-tile phase timestamps of CTA 0 (clock64), 8 per round
-  int f16;                   // forward: fp16 hidden activations / stage-2,3 weights
-  int dbg_shift;             // debug: load only bytes >> dbg_shift of every weight image (timing experiments)
-  int tiles_per_cta_round;   // grid size (all CTAs advance together)
-  int num_rounds;
-};
-
-// byte offset of element (row, k) inside the 128-row A region made of 64-wide SWIZZLE_128B panels
-__device__ __forceinline__ uint32_t a_offset(int row, int k) {
-  return (uint32_t)((k >> 6) * kPanelBytes + row * 128 + ((((k & 63) >> 3) ^ (row & 7)) << 4) + ((k & 7) << 1));
-}
-
-
-constexpr int kThreadsTC2 = 64 + 256;
-constexpr int kWorkers2 = 256;
-
-// im2col of taps [t_begin, t_end) of one operand row as split-bf16 [hi | lo]
-template <int SC>
-__device__ __forceinline__ void build_a1_taps(uint8_t* sA, int row, const float* __restrict__ src, long long p, bool valid,
-                                              int h, int w, int H, int W, int stride, int off, int sign, int t_begin,
-                                              int t_end) {
-  constexpr int K1h = 9 * SC;
-  constexpr int TG = SC >= 16 ? 3 : 5;
-  for (int t0 = t_begin; t0 < t_end; t0 += TG) {
-    float v[TG][SC];
-#pragma unroll
-    for (int tt = 0; tt < TG; ++tt) {
-      const int tap = t0 + tt;
-      const int dy = (tap / 3 - 1) * sign, dx = (tap % 3 - 1) * sign;
-      const int hh = h + dy, ww = w + dx;
-      const bool ok = valid && tap < t_end && hh >= 0 && hh < H && ww >= 0 && ww < W;
-      const float* s = src + (p + (long long)dy * W + dx) * stride + off;
-      if constexpr (SC % 4 == 0) {
-#pragma unroll
-        for (int q = 0; q < SC / 4; ++q) {
-          float4 t = ok ? __ldg(reinterpret_cast<const float4*>(s) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-          v[tt][4 * q] = t.x; v[tt][4 * q + 1] = t.y; v[tt][4 * q + 2] = t.z; v[tt][4 * q + 3] = t.w;
-        }
-      } else if constexpr (SC == 2) {
-        float2 t = ok ? __ldg(reinterpret_cast<const float2*>(s)) : make_float2(0.f, 0.f);
-        v[tt][0] = t.x; v[tt][1] = t.y;
-      } else {
-#pragma unroll
-        for (int ci = 0; ci < SC; ++ci) v[tt][ci] = ok ? __ldg(s + ci) : 0.f;
-      }
-    }
-#pragma unroll
-    for (int tt = 0; tt < TG; ++tt) {
-      if (t0 + tt >= t_end) break;
-      const int k0 = (t0 + tt) * SC;
-      float lo[SC];
-      uint32_t hp[(SC + 1) / 2], lp[(SC + 1) / 2];
-#pragma unroll
-      for (int ci = 0; ci < SC; ++ci) lo[ci] = v[tt][ci] - __bfloat162float(__float2bfloat16_rn(v[tt][ci]));
-      if constexpr (SC == 1) {
-        *reinterpret_cast<__nv_bfloat16*>(sA + a_offset(row, k0)) = __float2bfloat16_rn(v[tt][0]);
-        *reinterpret_cast<__nv_bfloat16*>(sA + a_offset(row, K1h + k0)) = __float2bfloat16_rn(lo[0]);
-      } else {
-#pragma unroll
-        for (int q = 0; q < SC / 2; ++q) {
-          hp[q] = pack_bf16(v[tt][2 * q], v[tt][2 * q + 1]);
-          lp[q] = pack_bf16(lo[2 * q], lo[2 * q + 1]);
-        }
-        if constexpr (SC == 2) {
-          *reinterpret_cast<uint32_t*>(sA + a_offset(row, k0)) = hp[0];
-          *reinterpret_cast<uint32_t*>(sA + a_offset(row, K1h + k0)) = lp[0];
-        } else if constexpr (SC == 4) {
-          *reinterpret_cast<uint2*>(sA + a_offset(row, k0)) = make_uint2(hp[0], hp[1]);
-          *reinterpret_cast<uint2*>(sA + a_offset(row, K1h + k0)) = make_uint2(lp[0], lp[1]);
-        } else {
-#pragma unroll
-          for (int q = 0; q < SC / 8; ++q) {
-            *reinterpret_cast<uint4*>(sA + a_offset(row, k0 + 8 * q)) =
-                make_uint4(hp[4 * q], hp[4 * q + 1], hp[4 * q + 2], hp[4 * q + 3]);
-            *reinterpret_cast<uint4*>(sA + a_offset(row, K1h + k0 + 8 * q)) =
-                make_uint4(lp[4 * q], lp[4 * q + 1], lp[4 * q + 2], lp[4 * q + 3]);
-          }
-        }
-      }
-    }
-  }
-}
-
-// im2col of up to five taps [t_begin, t_end) of one operand row, split in a LOAD half (global -> registers, issued
-// while the worker is idle) and a STORE half (split-bf16 [hi | lo] -> swizzled shared memory, once the panels are free)
-template <int SC>
-__device__ __forceinline__ void a1_load(float (&v)[40], const float* __restrict__ src, long long p, bool valid, int h, int w,
-                                        int H, int W, int stride, int off, int sign, int t_begin, int t_end) {
-  static_assert(SC <= 8, "register prefetch is sized for <= 8 source channels");
-#pragma unroll
-  for (int tt = 0; tt < 5; ++tt) {
-    const int tap = t_begin + tt;
-    const int dy = (tap / 3 - 1) * sign, dx = (tap % 3 - 1) * sign;
-    const int hh = h + dy, ww = w + dx;
-    const bool ok = valid && tap < t_end && hh >= 0 && hh < H && ww >= 0 && ww < W;
-    const float* s = src + (p + (long long)dy * W + dx) * stride + off;
-    if constexpr (SC == 8) {
-      const float4 t = ok ? __ldg(reinterpret_cast<const float4*>(s)) : make_float4(0.f, 0.f, 0.f, 0.f);
-      const float4 u = ok ? __ldg(reinterpret_cast<const float4*>(s) + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
-      v[8 * tt] = t.x; v[8 * tt + 1] = t.y; v[8 * tt + 2] = t.z; v[8 * tt + 3] = t.w;
-      v[8 * tt + 4] = u.x; v[8 * tt + 5] = u.y; v[8 * tt + 6] = u.z; v[8 * tt + 7] = u.w;
-    } else if constexpr (SC == 4) {
-      const float4 t = ok ? __ldg(reinterpret_cast<const float4*>(s)) : make_float4(0.f, 0.f, 0.f, 0.f);
-      v[4 * tt] = t.x; v[4 * tt + 1] = t.y; v[4 * tt + 2] = t.z; v[4 * tt + 3] = t.w;
-    } else if constexpr (SC == 2) {
-      const float2 t = ok ? __ldg(reinterpret_cast<const float2*>(s)) : make_float2(0.f, 0.f);
-      v[2 * tt] = t.x; v[2 * tt + 1] = t.y;
-    } else {
-      v[tt] = ok ? __ldg(s) : 0.f;
-    }
-  }
-}
-template <int SC>
-__device__ __forceinline__ void a1_store(uint8_t* sA, int row, const float (&v)[40], int t_begin, int t_end) {
-  constexpr int K1h = 9 * SC;
-#pragma unroll
-  for (int tt = 0; tt < 5; ++tt) {
-    if (t_begin + tt >= t_end) break;
-    const int k0 = (t_begin + tt) * SC;
-    float hi[SC], lo[SC];
-#pragma unroll
-    for (int ci = 0; ci < SC; ++ci) {
-      hi[ci] = v[tt * SC + ci];
-      lo[ci] = hi[ci] - __bfloat162float(__float2bfloat16_rn(hi[ci]));
-    }
-    if constexpr (SC == 1) {
-      *reinterpret_cast<__nv_bfloat16*>(sA + a_offset(row, k0)) = __float2bfloat16_rn(hi[0]);
-      *reinterpret_cast<__nv_bfloat16*>(sA + a_offset(row, K1h + k0)) = __float2bfloat16_rn(lo[0]);
-    } else if constexpr (SC == 2) {
-      *reinterpret_cast<uint32_t*>(sA + a_offset(row, k0)) = pack_bf16(hi[0], hi[1]);
-      *reinterpret_cast<uint32_t*>(sA + a_offset(row, K1h + k0)) = pack_bf16(lo[0], lo[1]);
-    } else if constexpr (SC == 4) {
-      *reinterpret_cast<uint2*>(sA + a_offset(row, k0)) = make_uint2(pack_bf16(hi[0], hi[1]), pack_bf16(hi[2], hi[3]));
-      *reinterpret_cast<uint2*>(sA + a_offset(row, K1h + k0)) = make_uint2(pack_bf16(lo[0], lo[1]), pack_bf16(lo[2], lo[3]));
-    } else {
-      *reinterpret_cast<uint4*>(sA + a_offset(row, k0)) =
-          make_uint4(pack_bf16(hi[0], hi[1]), pack_bf16(hi[2], hi[3]), pack_bf16(hi[4], hi[5]), pack_bf16(hi[6], hi[7]));
-      *reinterpret_cast<uint4*>(sA + a_offset(row, K1h + k0)) =
-          make_uint4(pack_bf16(lo[0], lo[1]), pack_bf16(lo[2], lo[3]), pack_bf16(lo[4], lo[5]), pack_bf16(lo[6], lo[7]));
-    }
-  }
-}
 
 // ===================================================================================================
 // K-pipelined kernel (default): the three GEMMs of a tile and their epilogues overlap panel by panel.
@@ -273,7 +99,6 @@ __global__ void __launch_bounds__(kThreadsTC2, 1) k_nn_tc4(const TCParams prm) {
       const uint8_t* w2 = w1 + (size_t)2 * prm.k1_panels * kStageBytes;
       const uint8_t* w3 = w2 + (size_t)2 * kNumPanels * kStageBytes;
       auto push = [&](const uint8_t* src, uint32_t bytes) {
-        bytes = (bytes >> prm.dbg_shift) & ~15u;      // dbg_shift > 0: timing experiments only (wrong results)
         mbar_wait(empty0 + 8 * stage, phase ^ 1);
         mbar_expect_tx(full0 + 8 * stage, bytes);
         bulk_g2s(smem_u32(sB + stage * kStageBytes), src, bytes, full0 + 8 * stage);
@@ -607,159 +432,15 @@ __global__ void __launch_bounds__(kThreadsTC2, 1) k_nn_tc4(const TCParams prm) {
   if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
 }
 
-// r[p][c] = c3[c] + sum_{tap in bounds} (G[p+off(tap)][tap*C+c] + const3[tap][c])
-// element (pixel pp, column col) of G: row-major [M][n3p] (k_nn_tc, k_nn_tc2) or, per 128-pixel tile,
-// [n3p/4 float4 columns][128 rows][4 floats] (k_nn_tc4)
-template <bool kTiled>
-__device__ __forceinline__ long long g_index(long long pp, int col, int n3p) {
-  if constexpr (!kTiled) return pp * n3p + col;
-  else return (pp >> 7) * (128ll * n3p) + (long long)(col >> 2) * 512 + (pp & 127) * 4 + (col & 3);
-}
-
-template <bool kTiled>
-__global__ void __launch_bounds__(256) k_gather_fwd(const float* __restrict__ G, const float* __restrict__ const3,
-                                                    const float* __restrict__ c3, float* __restrict__ r, int H, int W,
-                                                    int C, int n3p, long long total) {
-  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int c = idx % C;
-  const long long p = idx / C;
-  const int w = p % W, h = (p / W) % H;
-  float acc = c3[c];
-#pragma unroll
-  for (int tap = 0; tap < 9; ++tap) {
-    const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-    const int hh = h + dy, ww = w + dx;
-    if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
-    acc += G[g_index<kTiled>(p + (long long)dy * W + dx, tap * C + c, n3p)] + const3[tap * C + c];
-  }
-  r[idx] = acc;
-}
-
-// gxb[p][ci] = sum_{tap: p-off in bounds} G'[p-off(tap)][tap*Ch+ci]
-template <bool kTiled>
-__global__ void __launch_bounds__(256) k_gather_bwd(const float* __restrict__ G, float* __restrict__ gxb, int H, int W,
-                                                    int Ch, int n3p, long long total) {
-  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int c = idx % Ch;
-  const long long p = idx / Ch;
-  const int w = p % W, h = (p / W) % H;
-  float acc = 0.f;
-#pragma unroll
-  for (int tap = 0; tap < 9; ++tap) {
-    const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-    const int hh = h - dy, ww = w - dx;
-    if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
-    acc += G[g_index<kTiled>(p - (long long)dy * W - dx, tap * Ch + c, n3p)];
-  }
-  gxb[idx] = acc;
-}
-
-// Vector forms for the tiled G layout: one thread per (pixel, group of V = 4 or 2 consecutive channels); every tap is
-// one 16- or 8-byte load (the channels of a tap are contiguous inside a float4 column because C % V == 0).
-template <int V, bool kFwd>
-__global__ void __launch_bounds__(256) k_gather_vec(const float* __restrict__ G, const float* __restrict__ const3,
-                                                    const float* __restrict__ c3, float* __restrict__ out, int H, int W,
-                                                    int C, int n3p, long long total) {
-  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int CV = C / V;
-  const int cv = (int)(idx % CV);
-  const long long p = idx / CV;
-  const int w = (int)(p % W), h = (int)((p / W) % H);
-  float acc[V];
-#pragma unroll
-  for (int v = 0; v < V; ++v) acc[v] = kFwd ? c3[cv * V + v] : 0.f;
-#pragma unroll
-  for (int tap = 0; tap < 9; ++tap) {
-    const int dy = (tap / 3 - 1) * (kFwd ? 1 : -1), dx = (tap % 3 - 1) * (kFwd ? 1 : -1);
-    const int hh = h + dy, ww = w + dx;
-    if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
-    const long long pp = p + (long long)dy * W + dx;
-    const int col = tap * C + cv * V;
-    const float* g = G + (pp >> 7) * (128ll * n3p) + (long long)(col >> 2) * 512 + (pp & 127) * 4 + (col & 3);
-    if constexpr (V == 4) {
-      float4 t = __ldg(reinterpret_cast<const float4*>(g));
-      if constexpr (kFwd) {      // same association as the scalar kernel: acc += (G + const3)
-        const float4 k = __ldg(reinterpret_cast<const float4*>(const3 + col));
-        t.x += k.x; t.y += k.y; t.z += k.z; t.w += k.w;
-      }
-      acc[0] += t.x; acc[1] += t.y; acc[2] += t.z; acc[3] += t.w;
-    } else {
-      float2 t = __ldg(reinterpret_cast<const float2*>(g));
-      if constexpr (kFwd) {
-        const float2 k = __ldg(reinterpret_cast<const float2*>(const3 + col));
-        t.x += k.x; t.y += k.y;
-      }
-      acc[0] += t.x; acc[1] += t.y;
-    }
-  }
-  if constexpr (V == 4) reinterpret_cast<float4*>(out)[idx] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-  else reinterpret_cast<float2*>(out)[idx] = make_float2(acc[0], acc[1]);
-}
-
-int g_cluster = 1;
 int g_num_sms = 0;
-int g_pair_mode = 3;    // 3: K-pipelined kernel k_nn_tc4 (default), 0: 8-worker-warp single-CTA kernel, 1: CTA-pair kernel (cta_group::2), 2: legacy 4-worker-warp kernel
 
 // ---- optional per-launch timing of the tensor-core kernel (bench.py's roofline leg): a CUDA event pair
 // on the launching stream around every k_nn_tc launch while profiling is on.
-struct ProfRec { cudaEvent_t a, b; };
 bool g_prof_on = false;
-std::vector<ProfRec> g_prof_recs, g_prof_pool;
+std::vector<TcProfToken> g_prof_recs, g_prof_pool;
 double g_prof_flops = 0.0;
 double g_next_flops = 0.0;   // algorithmic FLOPs of the launch being issued (set by nn_tc_forward/backward)
 
-inline int pad16(int n) { return (n + 15) / 16 * 16; }
-
-// ------------------------------------------------------------------ host: weight tile images
-// Writes one image of `rows` rows x 64 k (bf16, SWIZZLE_128B K-major) for rows n0.., k0..
-// f16 = true stores IEEE half bits (forward stage-2/3 weights) in the same 16-bit slots
-template <typename Fn>
-void write_image(std::vector<__nv_bfloat16>& dst, int rows, int n0, int n_valid, int k0, int k_valid, Fn&& get, bool f16 = false) {
-  const size_t base = dst.size();
-  dst.resize(base + (size_t)rows * 64, __float2bfloat16(0.f));
-  for (int r = 0; r < rows; ++r) {
-    for (int k = 0; k < 64; ++k) {
-      float v = 0.f;
-      if (r < n_valid && k < k_valid) v = get(n0 + r, k0 + k);
-      const size_t off = (size_t)r * 64 + (size_t)((((k >> 3) ^ (r & 7)) << 3) + (k & 7));
-      if (f16) {
-        const __half hv = __float2half(v);
-        std::memcpy(&dst[base + off], &hv, sizeof(hv));
-      } else {
-        dst[base + off] = __float2bfloat16(v);
-      }
-    }
-  }
-}
-
-template <typename F1, typename F2, typename F3>
-void build_stage_set(TCStageSet& set, int K1, int N3, F1&& b1, F2&& b2, F3&& b3, bool f16_23) {
-  set.k1_steps = (K1 + 15) / 16;
-  set.k1_panels = (K1 + 63) / 64;
-  set.n3p = pad16(N3);
-  ASEP_CHECK(set.k1_panels <= kNumPanels && set.n3p <= 256, ASEP_ERR_UNSUPPORTED,
-             "coupling network shape outside the tcgen05 kernel (K1=%d, N3=%d)", K1, N3);
-  std::vector<__nv_bfloat16> img;
-  for (int half = 0; half < 2; ++half)
-    for (int kp = 0; kp < set.k1_panels; ++kp)
-      write_image(img, kStageRows, half * 256, 256, kp * 64, std::min(64, K1 - kp * 64), b1);
-  for (int half = 0; half < 2; ++half)
-    for (int kp = 0; kp < kNumPanels; ++kp) write_image(img, kStageRows, half * 256, 256, kp * 64, 64, b2, f16_23);
-  for (int kp = 0; kp < kNumPanels; ++kp) write_image(img, set.n3p, 0, N3, kp * 64, 64, b3, f16_23);
-  set.bytes = img.size() * sizeof(__nv_bfloat16);
-  CUDA_CHECK(cudaMalloc(&set.img, set.bytes));
-  CUDA_CHECK(cudaMemcpy(set.img, img.data(), set.bytes, cudaMemcpyHostToDevice));
-}
-
-float* upload(const std::vector<float>& v) {
-  float* d = nullptr;
-  CUDA_CHECK(cudaMalloc(&d, v.size() * sizeof(float)));
-  CUDA_CHECK(cudaMemcpy(d, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice));
-  return d;
-}
 
 template <bool kBwd, bool kSaveMask, bool kF16>
 void launch_tc4(const TCParams& prm, int grid, cudaStream_t s) {
@@ -769,19 +450,10 @@ void launch_tc4(const TCParams& prm, int grid, cudaStream_t s) {
     CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes4));
     attr_set = true;
   }
-  ProfRec rec{};
-  if (g_prof_on) {
-    if (!g_prof_pool.empty()) { rec = g_prof_pool.back(); g_prof_pool.pop_back(); }
-    else { CUDA_CHECK(cudaEventCreate(&rec.a)); CUDA_CHECK(cudaEventCreate(&rec.b)); }
-    CUDA_CHECK(cudaEventRecord(rec.a, s));
-  }
+  const TcProfToken tok = nn_tc_prof_begin(s);
   kern<<<grid, kThreadsTC2, kSmemBytes4, s>>>(prm);
   ASEP_LAUNCH_CHECK();
-  if (g_prof_on) {
-    CUDA_CHECK(cudaEventRecord(rec.b, s));
-    g_prof_recs.push_back(rec);
-    g_prof_flops += g_next_flops;
-  }
+  nn_tc_prof_end(tok, s, g_next_flops);
 }
 
 template <bool kBwd>
@@ -800,13 +472,12 @@ bool run_tc(TCParams prm, cudaStream_t s) {   // returns true when G was written
     prm.tiles_per_cta_round = grid;
     prm.num_rounds = (int)((tiles + grid - 1) / grid);
     static long long* dbg = nullptr;
-    const bool timing = getenv("ASEP_TC_DBG_TIMING") != nullptr;
+    static const bool timing = getenv("ASEP_TC_DBG_TIMING") != nullptr;   // read once: per-phase clock64 stamps (debug aid)
     if (timing) {
       if (!dbg) CUDA_CHECK(cudaMalloc(&dbg, 8 * 4096 * sizeof(long long)));
       ASEP_CHECK(prm.num_rounds <= 4096, ASEP_ERR_BAD_ARG, "too many rounds for the timing buffer");
       prm.dbg_out = dbg;
     }
-    if (const char* e = getenv("ASEP_TC_DBG_SHIFT")) prm.dbg_shift = atoi(e);
     if constexpr (kBwd) {
       launch_tc4<true, false, false>(prm, grid, s);
     } else {
@@ -838,17 +509,21 @@ bool run_tc(TCParams prm, cudaStream_t s) {   // returns true when G was written
 
 }  // namespace
 
-void nn_tc_set_cluster(int cluster_size) {      // retained knob: the K-pipelined kernel does not multicast
-  ASEP_CHECK(cluster_size == 1 || cluster_size == 2 || cluster_size == 4, ASEP_ERR_BAD_ARG,
-             "cluster size must be 1, 2 or 4");
-  g_cluster = cluster_size;
+TcProfToken nn_tc_prof_begin(cudaStream_t s) {
+  TcProfToken rec{};
+  if (!g_prof_on) return rec;
+  if (!g_prof_pool.empty()) { rec = g_prof_pool.back(); g_prof_pool.pop_back(); }
+  else { CUDA_CHECK(cudaEventCreate(&rec.a)); CUDA_CHECK(cudaEventCreate(&rec.b)); }
+  rec.on = true;
+  CUDA_CHECK(cudaEventRecord(rec.a, s));
+  return rec;
 }
-int nn_tc_get_cluster() { return g_cluster; }
-void nn_tc_set_pair_mode(int on) {
-  ASEP_CHECK(on == 3, ASEP_ERR_UNSUPPORTED, "only kernel variant 3 (k_nn_tc4) is built; the serial / CTA-pair variants were retired");
-  g_pair_mode = on;
+void nn_tc_prof_end(const TcProfToken& rec, cudaStream_t s, double flops) {
+  if (!rec.on) return;
+  CUDA_CHECK(cudaEventRecord(rec.b, s));
+  g_prof_recs.push_back(rec);
+  g_prof_flops += flops;
 }
-int nn_tc_get_pair_mode() { return g_pair_mode; }
 
 void nn_tc_profile(int on) {
   g_prof_on = on != 0;
@@ -943,12 +618,8 @@ void nn_tc_forward(const NNWeightsTC& w, const NNScratchTC& sc, const float* sta
   prm.dump1 = dump1; prm.dump2 = dump2; prm.f16 = w.f16 ? 1 : 0;
   prm.out = sc.G; prm.H = H; prm.W = W; prm.M = M;
   g_next_flops = 2.0 * (double)M * (9.0 * (C / 2) * kF + (double)kF * kF + 9.0 * kF * C);   // conv MACs x 2, unpadded
-  const bool tiled = run_tc<false>(prm, s);
-  const long long total = M * C;
-  (void)tiled;
-  if (C % 4 == 0) k_gather_vec<4, true><<<cdiv(total / 4, 256), 256, 0, s>>>(sc.G, w.const3, w.c3, r, H, W, C, w.fwd.n3p, total / 4);
-  else k_gather_fwd<true><<<cdiv(total, 256), 256, 0, s>>>(sc.G, w.const3, w.c3, r, H, W, C, w.fwd.n3p, total);
-  ASEP_LAUNCH_CHECK();
+  run_tc<false>(prm, s);
+  launch_gather_fwd(sc.G, w.const3, w.c3, r, M, H, W, C, w.fwd.n3p, 1, 0, s);
 }
 
 void nn_tc_backward(const NNWeightsTC& w, const NNScratchTC& sc, const float* gr, const uint32_t* mask1,
@@ -964,13 +635,8 @@ void nn_tc_backward(const NNWeightsTC& w, const NNScratchTC& sc, const float* gr
   prm.dump1 = dump_gp2; prm.dump2 = dump_gp1;
   prm.out = sc.G; prm.H = H; prm.W = W; prm.M = M;
   g_next_flops = 2.0 * (double)M * (9.0 * (C / 2) * kF + (double)kF * kF + 9.0 * kF * C);
-  const bool tiled = run_tc<true>(prm, s);
-  const long long total = M * (C / 2);
-  (void)tiled;
-  if ((C / 2) % 4 == 0) k_gather_vec<4, false><<<cdiv(total / 4, 256), 256, 0, s>>>(sc.G, nullptr, nullptr, gxb, H, W, C / 2, w.bwd.n3p, total / 4);
-  else if ((C / 2) % 2 == 0) k_gather_vec<2, false><<<cdiv(total / 2, 256), 256, 0, s>>>(sc.G, nullptr, nullptr, gxb, H, W, C / 2, w.bwd.n3p, total / 2);
-  else k_gather_bwd<true><<<cdiv(total, 256), 256, 0, s>>>(sc.G, gxb, H, W, C / 2, w.bwd.n3p, total);
-  ASEP_LAUNCH_CHECK();
+  run_tc<true>(prm, s);
+  launch_gather_bwd(sc.G, gxb, M, H, W, C / 2, w.bwd.n3p, 1, 0, s);
 }
 
 }  // namespace asep

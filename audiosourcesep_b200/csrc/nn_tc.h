@@ -51,13 +51,20 @@ void nn_tc_backward(const NNWeightsTC& w, const NNScratchTC& sc, const float* gr
                     __nv_bfloat16* dump_gp2 = nullptr, __nv_bfloat16* dump_gp1 = nullptr);
 
 size_t nn_tc_g_floats(long long M, int C);   // capacity needed for NNScratchTC::G
-void nn_tc_set_cluster(int cluster_size);    // 1, 2 or 4 CTAs sharing each weight tile by TMA multicast
-int nn_tc_get_cluster();
-// 1 selects the CTA-pair kernel (tcgen05 cta_group::2: two SMs share every weight image); results are identical.
-void nn_tc_set_pair_mode(int on);
-int nn_tc_get_pair_mode();
+
+// ---- split-precision ("exact") tensor-core form (nn_tcx.cu; ASEP_PREC_BF16X2 / ASEP_PREC_FP16X2): the same tile images,
+// hidden activations carried as (hi + lo) 16-bit pairs -> two tcgen05 products per hidden GEMM, 16 (bf16 pairs) or 22
+// (fp16 pairs) significant bits instead of 8 / 11.  Same contracts as nn_tc_forward / nn_tc_backward (no dumps).
+void nn_tcx_forward(const NNWeightsTC& w, const NNScratchTC& sc, const float* state, float* r, uint32_t* mask1,
+                    uint32_t* mask2, int N, int H, int W, int C, cudaStream_t s);
+void nn_tcx_backward(const NNWeightsTC& w, const NNScratchTC& sc, const float* gr, const uint32_t* mask1,
+                     const uint32_t* mask2, float* gxb, int N, int H, int W, int C, cudaStream_t s);
+size_t nn_tcx_g_floats(long long M, int C);  // two K-split partial outputs
 // CUDA-event timing of every tensor-core kernel launch (on its own stream) while switched on.
 void nn_tc_profile(int on);
+struct TcProfToken { cudaEvent_t a = nullptr, b = nullptr; bool on = false; };
+TcProfToken nn_tc_prof_begin(cudaStream_t s);                                  // shared by nn_tc.cu and nn_tcx.cu
+void nn_tc_prof_end(const TcProfToken& tok, cudaStream_t s, double flops);
 bool nn_tc_profile_enabled();
 void nn_tc_profile_read(double* total_ms, long long* launches, double* flops);
 

@@ -122,12 +122,3 @@ def basis_ncsn_inner(m1, m2, mixed, x1, x2, sigma_idx: int, T: int, eta: float, 
                                                  int(T), float(eta), float(lam), float(noise_scale), dn1.ptr, dn2.ptr,
                                                  int(seed), int(step0), int(elem_offset), dps.ptr, dnan.ptr,
                                                  _lib.stream_ptr()))
-
-
-def set_tc_cluster(cluster_size: int) -> None:
-    _lib.check(_lib.load().asep_tc_set_cluster(int(cluster_size)))
-
-
-def set_tc_pair_mode(on) -> None:
-    """0: single-CTA kernel with 8 epilogue warps (default), 1: CTA-pair (cta_group::2) kernel, 2: legacy kernel."""
-    _lib.check(_lib.load().asep_tc_set_pair_mode(int(on)))

@@ -47,8 +47,13 @@ typedef enum {
   ASEP_PREC_FP16 = 3,  /* Glow only: as ASEP_PREC_BF16 but the hidden activations / stage-2,3 weights of the forward
                         * coupling network are fp16 (10 mantissa bits): ~8x closer to fp32, ~8 % slower under the
                         * power cap.  The data-gradient pass stays bf16 (gradients have unbounded range).        */
-  ASEP_PREC_BF16X3 = 2 /* score networks only: activations and weights as (hi + lo) bf16 pairs, three tcgen05
-                        * products per convolution (hi.hi + lo.hi + hi.lo), fp32 accumulation: ~2^-16 relative */
+  ASEP_PREC_BF16X3 = 2, /* score networks only: activations and weights as (hi + lo) bf16 pairs, three tcgen05
+                         * products per convolution (hi.hi + lo.hi + hi.lo), fp32 accumulation: ~2^-16 relative */
+  ASEP_PREC_BF16X2 = 4, /* Glow only: the tensor-core "exact" mode.  Hidden activations of the coupling network as
+                         * (hi + lo) bf16 pairs (16 significant bits, fp32 range), two tcgen05 products per hidden GEMM
+                         * against the bf16 weight images: meets inverse(forward(x)) <= 1e-4 on tensor cores      */
+  ASEP_PREC_FP16X2 = 5  /* as ASEP_PREC_BF16X2 with (hi + lo) fp16 pairs (22 bits) and fp16 stage-2/3 weights in the
+                         * forward network; hidden activations must stay below 65504 (else NaN); gradients use bf16 pairs */
 } asep_precision;
 
 const char* asep_last_error(void);
@@ -101,7 +106,8 @@ int asep_glow_sample(asep_glow_t h, const DLTensor* eps, DLTensor* x, void* stre
  * train_noisy_glow.py:30-33.  Data parallelism = one process per GPU: every rank calls train_grads on its shard
  * with the GLOBAL batch size, the host all-reduces (SUM, NCCL) `grads` and `loss`, every rank calls adamax_step. */
 /* Moves the trainables into one flat device vector (order: weights.py glow_param_shapes filtered by is_trainable),
- * allocates optimiser state; requires asep_glow_prepare(h, ASEP_PREC_FP32). */
+ * allocates optimiser state.  Works in ASEP_PREC_FP32 (CUDA cores) and ASEP_PREC_BF16 / ASEP_PREC_FP16 (tcgen05, the
+ * default); the split-precision modes have no weight-gradient path. */
 int asep_glow_enable_training(asep_glow_t h);
 int asep_glow_num_trainable(asep_glow_t h, int64_t* out);
 /* x [N,H,W,C] raw data; noise NULL or [N,H,W,C] standard normals scaled by sigma and added to x in raw units
@@ -197,14 +203,6 @@ int asep_basis_ncsn_inner(asep_ncsn_t m1, asep_ncsn_t m2, const DLTensor* mixed,
 /* Event timing of the tcgen05 convolution launches of the score networks (same contract as asep_tc_profile). */
 int asep_conv_profile(int on);
 int asep_conv_profile_read(double* total_ms, int64_t* launches, double* flops);
-
-/* Number of CTAs (1, 2 or 4) of a thread-block cluster that share each weight tile of the tcgen05 coupling
- * kernel through TMA multicast.  Tuning knob; results are identical for every value. */
-int asep_tc_set_cluster(int cluster_size);
-/* Variant of the tcgen05 coupling kernel: 3 (default) the K-pipelined single-CTA kernel k_nn_tc4; 0 the serial
- * 8-worker-warp kernel k_nn_tc2; 1 its CTA-pair form (tcgen05 cta_group::2, M = 256 across the two SMs of a TPC,
- * each CTA streams half of every weight image); 2 the first 4-worker-warp kernel.  Results are bit-identical. */
-int asep_tc_set_pair_mode(int on);
 
 /* Measurement aid (bench.py roofline leg): while on, every launch of the tcgen05 coupling kernel is bracketed
  * by a CUDA event pair on its own stream.  _read synchronises those events and returns the summed kernel time,

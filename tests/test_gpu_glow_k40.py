@@ -1,0 +1,140 @@
+"""GPU parity at the depth and size of every reference config: L=3, K=40, 512 filters, n_mixed = 30 segments.
+
+The oracle side is the committed fixture tests/golden/glow_k40.npz (generator: tests/golden/make_glow_k40_golden.py;
+one float64 oracle gradient of 30 patches costs minutes of CPU, a T=100 trajectory 200 evaluations).  The inputs are
+regenerated here from the same seeded generators, so the comparison is CUDA-vs-oracle on identical inputs.
+
+Reference: run_basis_sep.py:73-79 (compute_grad_logprob), :152-181 (basis_inner_loop), :478 (n_mixed = 30).
+Gates (BASELINE.json north_star): per-Langevin-step state relative error <= 1e-3, final SDR within 0.1 dB.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from audiosourcesep_b200 import GlowConfig, synthetic
+from audiosourcesep_b200.weights import init_glow_params
+from oracle import basis_oracle as bo
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "glow_k40.npz")
+N_MIXED, T, N_TRAJ = 30, 100, 2
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def _prec(name):
+    from audiosourcesep_b200 import _lib
+    return {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16, "bf16x2": _lib.PREC_BF16X2, "fp16x2": _lib.PREC_FP16X2}[name]
+
+
+@pytest.fixture(scope="module")
+def problem():
+    cfg = GlowConfig(H=96, W=64, C=1, L=3, K=40, n_filters=512, minval=0.0, maxval=1.0)
+    p1, p2 = init_glow_params(cfg, seed=2, mode="perturbed"), init_glow_params(cfg, seed=3, mode="perturbed")
+    mixed, gt1, gt2 = synthetic.basis_problem(N_MIXED)
+    x1, x2 = synthetic.langevin_init(N_MIXED, seed=4)
+    gold = np.load(GOLD)
+    return dict(cfg=cfg, p1=p1, p2=p2, mixed=mixed, gt1=gt1, gt2=gt2, x1=x1, x2=x2, gold=gold)
+
+
+_models = {}
+
+
+def _pair(problem, precision):
+    """Both priors in one precision (cached per module: preparing a K=40 model takes seconds)."""
+    from audiosourcesep_b200.glow import Glow
+    if precision not in _models:
+        _models[precision] = (Glow(problem["cfg"], problem["p1"], precision=_prec(precision)),
+                              Glow(problem["cfg"], problem["p2"], precision=_prec(precision)))
+    return _models[precision]
+
+
+# relative L2 error of the score against the float64 oracle.  What bounds it: every ReLU whose pre-activation sits
+# within the arithmetic's error of zero flips, and the gradient of a ReLU network is piece-wise constant, so each flip
+# contributes its unit's whole term.  16-bit weights (bf16: 2^-9, fp16: 2^-12) set the flip rate in the tensor-core modes.
+GRAD_BOUND = {"fp32": 5e-3, "bf16": 0.2, "bf16x2": 0.15, "fp16x2": 0.05}
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16", "bf16x2", "fp16x2"])
+def test_grad_log_prob_k40_n30_vs_oracle(problem, precision):
+    m1, m2 = _pair(problem, precision)
+    gold = problem["gold"]
+    for k, (m, x) in enumerate(((m1, problem["x1"]), (m2, problem["x2"])), start=1):
+        g, lp = m.grad_log_prob(torch.as_tensor(x), return_log_prob=True)
+        g = _np(g)[..., 0].astype(np.float64)
+        ref = gold[f"grad{k}"].astype(np.float64)
+        assert np.all(np.isfinite(g))
+        rel = np.linalg.norm(g - ref) / np.linalg.norm(ref)
+        per = np.linalg.norm((g - ref).reshape(N_MIXED, -1), axis=1) / np.linalg.norm(ref.reshape(N_MIXED, -1), axis=1)
+        dlp = np.max(np.abs(_np(lp).astype(np.float64) - gold[f"logp{k}"])) / problem["cfg"].dims
+        print(f"[{precision}] prior {k}: K=40 N=30 score rel L2 err {rel:.3e} (worst patch {per.max():.3e}); "
+              f"log_prob err {dlp:.3e} nats/dim")
+        assert dlp <= 1e-3, dlp
+        assert rel <= GRAD_BOUND[precision], rel
+
+
+@pytest.mark.parametrize("sigma_idx", [0, 4, 9])
+@pytest.mark.parametrize("precision", ["fp32", "bf16", "bf16x2"])
+def test_one_langevin_step_k40_n30_vs_oracle(problem, precision, sigma_idx):
+    """One synchronised BASIS step of all 30 segments from the oracle's state, injected noise: the north-star gate
+    (per-step state relative error <= 1e-3) at the first, a middle and the last noise level."""
+    from audiosourcesep_b200 import ops
+    m1, m2 = _pair(problem, precision)
+    gold = problem["gold"]
+    sig = bo.get_sigmas(1.0, 0.01, 10, "logarithmic")
+    eta, lam, ns = bo.step_constants(sig, sigma_idx)
+    g, grad_g = bo.mixing_process("melspec", "dB")
+    rng = np.random.Generator(np.random.PCG64(100 + sigma_idx))
+    n1, n2 = (rng.standard_normal(problem["x1"].shape).astype(np.float32) for _ in range(2))
+    s1, s2 = gold["grad1"][..., None], gold["grad2"][..., None]
+    y1, y2 = bo.langevin_update(problem["x1"], problem["x2"], s1, s2, problem["mixed"], n1, n2, eta, lam, ns, g, grad_g)
+    t1, t2 = torch.as_tensor(problem["x1"]).cuda(), torch.as_tensor(problem["x2"]).cuda()
+    nan = torch.zeros(1, dtype=torch.int32, device="cuda")
+    ops.basis_glow_inner(m1, m2, torch.as_tensor(problem["mixed"]), t1, t2, 1, float(eta), float(lam), float(ns),
+                         noise1=torch.as_tensor(n1[None]), noise2=torch.as_tensor(n2[None]), nan_count=nan)
+    worst = 0.0
+    for got, want, x0 in ((t1, y1, problem["x1"]), (t2, y2, problem["x2"])):
+        rel = float(np.linalg.norm(_np(got) - want) / np.linalg.norm(want))
+        # the same error relative to the size of the update itself (how much of the STEP is right)
+        upd = float(np.linalg.norm(_np(got) - want) / np.linalg.norm(want - x0))
+        worst = max(worst, rel)
+        print(f"[{precision}, sigma_idx={sigma_idx}] state rel err {rel:.3e}; relative to the update {upd:.3e}")
+    assert nan.item() == 0
+    assert worst <= 1e-3, worst
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16", "bf16x2"])
+def test_t100_last_sigma_sdr_vs_oracle(problem, precision):
+    """T = 100 free-running steps at the last noise level (the reference's T, run_basis_sep.py:489) inside the library
+    with injected noise, against the float32 oracle trajectory: final state and SDR within 0.1 dB."""
+    from audiosourcesep_b200 import ops
+    m1, m2 = _pair(problem, precision)
+    gold = problem["gold"]
+    sig = bo.get_sigmas(1.0, 0.01, 10, "logarithmic")
+    eta, lam, ns = bo.step_constants(sig, 9)
+    rng = np.random.Generator(np.random.PCG64(3))
+    noise = rng.standard_normal((T, 2, N_TRAJ, 96, 64, 1)).astype(np.float32)
+    t1 = torch.as_tensor(problem["x1"][:N_TRAJ]).cuda()
+    t2 = torch.as_tensor(problem["x2"][:N_TRAJ]).cuda()
+    dump = torch.empty((T, 2, N_TRAJ, 96, 64, 1), device="cuda")
+    nan = torch.zeros(1, dtype=torch.int32, device="cuda")
+    ops.basis_glow_inner(m1, m2, torch.as_tensor(problem["mixed"][:N_TRAJ]), t1, t2, T, float(eta), float(lam), float(ns),
+                         noise1=torch.as_tensor(np.ascontiguousarray(noise[:, 0])),
+                         noise2=torch.as_tensor(np.ascontiguousarray(noise[:, 1])), per_step=dump, nan_count=nan)
+    assert nan.item() == 0
+    gts = (synthetic.normalise(problem["gt1"][:N_TRAJ])[..., 0], synthetic.normalise(problem["gt2"][:N_TRAJ])[..., 0])
+    for k, (got, key) in enumerate(((t1, "traj_x1"), (t2, "traj_x2"))):
+        want = gold[key][-1]
+        rel = float(np.linalg.norm(_np(got)[..., 0] - want) / np.linalg.norm(want))
+        drift = [float(np.linalg.norm(_np(dump[10 * i - 1, k])[..., 0] - gold[key][i]) / np.linalg.norm(gold[key][i]))
+                 for i in range(1, 11)]
+        sdr_c, sdr_o = bo.sdr_db(gts[k], _np(got)[..., 0]), bo.sdr_db(gts[k], want)
+        print(f"[{precision}] source {k + 1}: final state rel err {rel:.3e} (every 10 steps: "
+              f"{', '.join(f'{d:.1e}' for d in drift)}); SDR cuda {sdr_c:.4f} dB, oracle {sdr_o:.4f} dB")
+        assert abs(sdr_c - sdr_o) <= 0.1, (sdr_c, sdr_o)
+        assert rel <= 5e-3, rel

@@ -28,6 +28,13 @@ def test_param_count_known_answers():
     gold = json.load(open(os.path.join(G, "param_counts.json")))
     assert count_ncsn_params(NCSNConfig(version="v1", ngf=192, num_classes=10)) == gold["ncsn_v1_ngf192_classes10"]
     assert count_ncsn_params(NCSNConfig(version="v2", ngf=128, num_classes=200)) == 29_695_233
+    # the oracle's OWN walk of the reference constructors (no table shared with the product) gives the same answers
+    from oracle.ncsn_oracle import count_params_by_walk
+    assert count_params_by_walk("v1", 192, 10) == gold["ncsn_v1_ngf192_classes10"]
+    assert count_params_by_walk("v2", 128, 200) == 29_695_233
+    for ngf, nc in ((64, 10), (96, 10), (32, 3)):
+        for v in ("v1", "v2"):
+            assert count_params_by_walk(v, ngf, nc) == count_ncsn_params(NCSNConfig(version=v, ngf=ngf, num_classes=nc))
 
 
 def test_mixing_db_is_power_mean_and_gradient():

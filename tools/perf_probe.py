@@ -47,8 +47,6 @@ def main():
         x = torch.as_tensor(synthetic.mel_patches_db(min(N, 64), seed=0)).cuda()
         x = x.repeat((N + x.shape[0] - 1) // x.shape[0], 1, 1, 1)[:N].contiguous()
         for cs, pair in [(c, q) for q in a.pair for c in (a.clusters if q == 0 else [1])]:
-            ops.set_tc_cluster(cs)
-            ops.set_tc_pair_mode(int(pair))
             ms = timeit(lambda: m.log_prob(x), a.iters)
             tf = N * F_GLOW * scale / (ms * 1e-3) / 1e12
             print(f"log_prob  N={N:5d} cluster={cs} pair={pair}: {ms:9.3f} ms  {N / ms * 1e3:10.1f} samples/s  {tf:8.1f} TFLOP/s", flush=True)
@@ -56,7 +54,6 @@ def main():
                 ms = timeit(lambda: m.grad_log_prob(x), a.iters)
                 tf = N * 2 * F_GLOW * scale / (ms * 1e-3) / 1e12
                 print(f"grad_logp N={N:5d} cluster={cs} pair={pair}: {ms:9.3f} ms  {N / ms * 1e3:10.1f} samples/s  {tf:8.1f} TFLOP/s (2F alg.)", flush=True)
-        ops.set_tc_cluster(1)
     if a.fp32:
         m.prepare(_lib.PREC_FP32)
         x = torch.as_tensor(synthetic.mel_patches_db(32, seed=0)).cuda()
