@@ -23,6 +23,7 @@ PREC_FP16 = 3       # Glow: tcgen05 with fp16 hidden activations in the forward 
 PREC_BF16X3 = 2     # score networks: split-bf16 operands, three tcgen05 products per convolution
 PREC_BF16X2 = 4     # Glow: tcgen05 "exact" mode, hidden activations as (hi + lo) bf16 pairs (round trip <= 1e-4)
 PREC_FP16X2 = 5     # Glow: as BF16X2 with fp16 pairs (22 bits; hidden activations must stay below 65504)
+PREC_FP16X3 = 6     # Glow: weights as (hi + lo) pairs too, three products per GEMM: score-exact on tensor cores
 
 
 class AsepError(RuntimeError):

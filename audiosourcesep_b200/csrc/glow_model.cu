@@ -238,11 +238,11 @@ void GlowModel::invalidate_graphs() {
 }
 
 void GlowModel::prepare(int precision) {
-  const bool tc_mode = precision == ASEP_PREC_BF16 || precision == ASEP_PREC_FP16 || precision == ASEP_PREC_BF16X2 ||
-                       precision == ASEP_PREC_FP16X2;
-  const bool f16_mode = precision == ASEP_PREC_FP16 || precision == ASEP_PREC_FP16X2;
+  const bool tcx_mode = precision == ASEP_PREC_BF16X2 || precision == ASEP_PREC_FP16X2 || precision == ASEP_PREC_FP16X3;
+  const bool tc_mode = precision == ASEP_PREC_BF16 || precision == ASEP_PREC_FP16 || tcx_mode;
+  const bool f16_mode = precision == ASEP_PREC_FP16 || precision == ASEP_PREC_FP16X2 || precision == ASEP_PREC_FP16X3;
   ASEP_CHECK(precision == ASEP_PREC_FP32 || tc_mode, ASEP_ERR_BAD_ARG, "unknown precision %d", precision);
-  ASEP_CHECK(!(training_ && (precision == ASEP_PREC_BF16X2 || precision == ASEP_PREC_FP16X2)), ASEP_ERR_UNSUPPORTED,
+  ASEP_CHECK(!(training_ && tcx_mode), ASEP_ERR_UNSUPPORTED,
              "the split-precision modes have no weight-gradient path: train in ASEP_PREC_BF16 / FP16 / FP32");
   const int F = cfg_.n_filters;
   if (tc_mode)
@@ -288,7 +288,7 @@ void GlowModel::prepare(int precision) {
         nn_tc_prepare(sd.wtc, params_.at(pre + "conv1/kernel").host.data(), params_.at(pre + "conv1/bias").host.data(),
                       g1.data(), b1.data(), k2.data(), params_.at(pre + "conv2/bias").host.data(), g2.data(),
                       b2.data(), params_.at(pre + "conv3/kernel").host.data(),
-                      params_.at(pre + "conv3/bias").host.data(), C, F, f16_mode);
+                      params_.at(pre + "conv3/bias").host.data(), C, F, f16_mode, precision == ASEP_PREC_FP16X3);
       } else {
         nn_tc_release(sd.wtc);
       }

@@ -154,7 +154,7 @@ class GlowModel {
   std::vector<StepDerived> steps_;
   bool prepared_ = false;
   int precision_ = ASEP_PREC_FP32;
-  bool is_tcx() const { return precision_ == ASEP_PREC_BF16X2 || precision_ == ASEP_PREC_FP16X2; }   // split-precision tcgen05
+  bool is_tcx() const { return precision_ == ASEP_PREC_BF16X2 || precision_ == ASEP_PREC_FP16X2 || precision_ == ASEP_PREC_FP16X3; }   // split-precision tcgen05
   bool is_tc() const { return precision_ == ASEP_PREC_BF16 || precision_ == ASEP_PREC_FP16 || is_tcx(); }   // tcgen05 modes
   DeviceArena arena_;
   Work work_;

@@ -551,7 +551,7 @@ size_t nn_tc_g_floats(long long M, int C) { return (size_t)((M + kTileM - 1) / k
 
 void nn_tc_prepare(NNWeightsTC& w, const float* k1, const float* c1, const float* g1, const float* b1,
                    const float* k2, const float* c2, const float* g2, const float* b2, const float* k3,
-                   const float* c3, int C, int F, bool f16) {
+                   const float* c3, int C, int F, bool f16, bool x3) {
   ASEP_CHECK(F == kF, ASEP_ERR_UNSUPPORTED, "the tcgen05 coupling kernel is built for n_filters = %d (got %d)", kF, F);
   nn_tc_release(w);
   const int Ch = C / 2;
@@ -564,7 +564,13 @@ void nn_tc_prepare(NNWeightsTC& w, const float* k1, const float* c1, const float
       const int tap = n / C, c = n % C;
       return g2[k] * k3[((size_t)tap * F + k) * C + c];
     };
-    build_stage_set(w.fwd, 2 * K1h, 9 * C, f1, f2, f3, /*fp16 stage-2/3 weights*/ f16);
+    // three-product mode with fp16 pairs: the stage-1 operand and weights are fp16 too (22 significant bits end to end)
+    // The fp16 residual of an O(0.04) weight is ~1e-5, a subnormal half: the images carry 256 x w (and the kernel scales the
+    // accumulators by 1/256), which keeps 22 significant bits per weight.
+    const float ws = (f16 && x3) ? 256.f : 1.f;
+    build_stage_set(w.fwd, 2 * K1h, 9 * C, f1, f2, f3, /*fp16 stage-2/3 weights*/ f16, /*fp16 stage 1*/ f16 && x3, false, ws);
+    if (x3) build_stage_set(w.fwd_lo, 2 * K1h, 9 * C, f1, f2, f3, f16, f16, /*residual*/ true, ws);
+    w.wscale_fwd = ws;
   }
   // ---------------- backward (data gradient)
   {
@@ -576,6 +582,7 @@ void nn_tc_prepare(NNWeightsTC& w, const float* k1, const float* c1, const float
     auto f2 = [&](int n, int k) { return g1[n] * k2[(size_t)n * F + k]; };              // diag(g1') K2^T
     auto f3 = [&](int n, int k) { return k1[(size_t)n * F + k]; };                      // n = tap*Ch + ci
     build_stage_set(w.bwd, 2 * K1h, 9 * Ch, f1, f2, f3, false);
+    if (x3) build_stage_set(w.bwd_lo, 2 * K1h, 9 * Ch, f1, f2, f3, false, false, /*residual*/ true);
   }
   std::vector<float> bias1(c1, c1 + F), bias2(F), const3((size_t)9 * C), vc3(c3, c3 + C);
   for (int n = 0; n < F; ++n) {
@@ -594,11 +601,14 @@ void nn_tc_prepare(NNWeightsTC& w, const float* k1, const float* c1, const float
   w.const3 = upload(const3);
   w.c3 = upload(vc3);
   w.f16 = f16;
+  w.x3 = x3;
 }
 
 void nn_tc_release(NNWeightsTC& w) {
   if (w.fwd.img) cudaFree(w.fwd.img);
   if (w.bwd.img) cudaFree(w.bwd.img);
+  if (w.fwd_lo.img) cudaFree(w.fwd_lo.img);
+  if (w.bwd_lo.img) cudaFree(w.bwd_lo.img);
   if (w.bias1) cudaFree(w.bias1);
   if (w.bias2) cudaFree(w.bias2);
   if (w.const3) cudaFree(w.const3);

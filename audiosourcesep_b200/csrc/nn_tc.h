@@ -18,6 +18,9 @@ struct TCStageSet {
 
 struct NNWeightsTC {
   TCStageSet fwd, bwd;
+  TCStageSet fwd_lo, bwd_lo;  // residual images w - rn(w) of the three-product mode (ASEP_PREC_FP16X3), else empty
+  bool x3 = false;
+  float wscale_fwd = 1.f;     // power of two folded into the forward tile images (fp16 residuals stay normal numbers)
   float* bias1 = nullptr;   // c1                                   [F]
   float* bias2 = nullptr;   // c2 + b1' . K2                        [F]
   float* const3 = nullptr;  // [9][C]  sum_k b2'[k] K3[tap][k][c]   (border-aware BN offset of conv3)
@@ -35,7 +38,7 @@ struct NNScratchTC {
 // k1 [3,3,Ch,F], k2 [F,F] (in,out), k3 [3,3,F,C]; g*/b* folded BatchNorm scale/offset.
 void nn_tc_prepare(NNWeightsTC& w, const float* k1, const float* c1, const float* g1, const float* b1,
                    const float* k2, const float* c2, const float* g2, const float* b2, const float* k3,
-                   const float* c3, int C, int F, bool f16 = false);
+                   const float* c3, int C, int F, bool f16 = false, bool x3 = false);
 void nn_tc_release(NNWeightsTC& w);
 
 // state [N,H,W,C] (network input = channels C/2..C) -> r [M,C] (conv3 output incl. bias).

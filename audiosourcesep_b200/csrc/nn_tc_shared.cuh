@@ -4,6 +4,7 @@
 #include "nn_tc.h"
 #include "tc_ptx.cuh"
 
+#include <cmath>
 #include <cstring>
 
 namespace asep {
@@ -27,6 +28,9 @@ struct TCParams {
   int src_ch;            // channels used (fwd C/2, bwd C)
   int tap_sign;          // +1: A row p reads pixel p+off(tap) (fwd); -1: p-off(tap) (bwd)
   const __nv_bfloat16* wimg;
+  const __nv_bfloat16* wimg_lo;   // nn_tcx.cu, three-product mode: residual weight images (same layout), else NULL
+  int f16_s1;                     // nn_tcx.cu: stage-1 operand and weights as fp16 pairs (forward of ASEP_PREC_FP16X3)
+  float acc_scale;                // nn_tcx.cu: every accumulator is multiplied by this (1 / weight scale of the tile images)
   int k1_steps, k1_panels, n3p;
   const float* bias1;    // fwd only
   const float* bias2;
@@ -52,6 +56,23 @@ __device__ __forceinline__ uint32_t a_offset(int row, int k) {
 
 constexpr int kThreadsTC2 = 64 + 256;
 constexpr int kWorkers2 = 256;
+
+// (hi, lo) pair words of two values: bf16 pairs (16 significant bits, fp32 range) or fp16 pairs (22 bits, |v| < 65504)
+template <bool kHalf>
+__device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
+  if constexpr (kHalf) {
+    __half2 h = __floats2half2_rn(a, b);
+    const float2 hf = __half22float2(h);
+    __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+    hi = *reinterpret_cast<uint32_t*>(&h);
+    lo = *reinterpret_cast<uint32_t*>(&l);
+  } else {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    hi = *reinterpret_cast<uint32_t*>(&h);
+    __nv_bfloat162 l = __floats2bfloat162_rn(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xffff0000u));
+    lo = *reinterpret_cast<uint32_t*>(&l);
+  }
+}
 
 // im2col of taps [t_begin, t_end) of one operand row as split-bf16 [hi | lo]
 template <int SC>
@@ -149,39 +170,36 @@ __device__ __forceinline__ void a1_load(float (&v)[40], const float* __restrict_
     }
   }
 }
-template <int SC>
+template <int SC, bool kHalf = false>
 __device__ __forceinline__ void a1_store(uint8_t* sA, int row, const float (&v)[40], int t_begin, int t_end) {
   constexpr int K1h = 9 * SC;
 #pragma unroll
   for (int tt = 0; tt < 5; ++tt) {
     if (t_begin + tt >= t_end) break;
     const int k0 = (t_begin + tt) * SC;
-    float hi[SC], lo[SC];
-#pragma unroll
-    for (int ci = 0; ci < SC; ++ci) {
-      hi[ci] = v[tt * SC + ci];
-      lo[ci] = hi[ci] - __bfloat162float(__float2bfloat16_rn(hi[ci]));
-    }
     if constexpr (SC == 1) {
-      *reinterpret_cast<__nv_bfloat16*>(sA + a_offset(row, k0)) = __float2bfloat16_rn(hi[0]);
-      *reinterpret_cast<__nv_bfloat16*>(sA + a_offset(row, K1h + k0)) = __float2bfloat16_rn(lo[0]);
-    } else if constexpr (SC == 2) {
-      *reinterpret_cast<uint32_t*>(sA + a_offset(row, k0)) = pack_bf16(hi[0], hi[1]);
-      *reinterpret_cast<uint32_t*>(sA + a_offset(row, K1h + k0)) = pack_bf16(lo[0], lo[1]);
-    } else if constexpr (SC == 4) {
-      *reinterpret_cast<uint2*>(sA + a_offset(row, k0)) = make_uint2(pack_bf16(hi[0], hi[1]), pack_bf16(hi[2], hi[3]));
-      *reinterpret_cast<uint2*>(sA + a_offset(row, K1h + k0)) = make_uint2(pack_bf16(lo[0], lo[1]), pack_bf16(lo[2], lo[3]));
+      uint32_t hi, lo;
+      split_pair<kHalf>(v[tt], 0.f, hi, lo);
+      *reinterpret_cast<uint16_t*>(sA + a_offset(row, k0)) = (uint16_t)(hi & 0xffffu);
+      *reinterpret_cast<uint16_t*>(sA + a_offset(row, K1h + k0)) = (uint16_t)(lo & 0xffffu);
     } else {
-      *reinterpret_cast<uint4*>(sA + a_offset(row, k0)) =
-          make_uint4(pack_bf16(hi[0], hi[1]), pack_bf16(hi[2], hi[3]), pack_bf16(hi[4], hi[5]), pack_bf16(hi[6], hi[7]));
-      *reinterpret_cast<uint4*>(sA + a_offset(row, K1h + k0)) =
-          make_uint4(pack_bf16(lo[0], lo[1]), pack_bf16(lo[2], lo[3]), pack_bf16(lo[4], lo[5]), pack_bf16(lo[6], lo[7]));
+      uint32_t hi[SC / 2], lo[SC / 2];
+#pragma unroll
+      for (int q = 0; q < SC / 2; ++q) split_pair<kHalf>(v[tt * SC + 2 * q], v[tt * SC + 2 * q + 1], hi[q], lo[q]);
+      if constexpr (SC == 2) {
+        *reinterpret_cast<uint32_t*>(sA + a_offset(row, k0)) = hi[0];
+        *reinterpret_cast<uint32_t*>(sA + a_offset(row, K1h + k0)) = lo[0];
+      } else if constexpr (SC == 4) {
+        *reinterpret_cast<uint2*>(sA + a_offset(row, k0)) = make_uint2(hi[0], hi[1]);
+        *reinterpret_cast<uint2*>(sA + a_offset(row, K1h + k0)) = make_uint2(lo[0], lo[1]);
+      } else {
+        *reinterpret_cast<uint4*>(sA + a_offset(row, k0)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(sA + a_offset(row, K1h + k0)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      }
     }
   }
 }
 
-// r[p][c] = c3[c] + sum_{tap in bounds} (G[p+off(tap)][tap*C+c] + const3[tap][c])
-// element (pixel pp, column col) of G: row-major [M][n3p] (k_nn_tc, k_nn_tc2) or, per 128-pixel tile,
 // [n3p/4 float4 columns][128 rows][4 floats] (k_nn_tc4)
 template <bool kTiled>
 __device__ __forceinline__ long long g_index(long long pp, int col, int n3p) {
@@ -308,41 +326,56 @@ inline void launch_gather_bwd(const float* G, float* gxb, long long M, int H, in
 }
 
 // ------------------------------------------------------------------ host: weight tile images
-// Writes one image of `rows` rows x 64 k (bf16, SWIZZLE_128B K-major) for rows n0.., k0..
-// f16 = true stores IEEE half bits (forward stage-2/3 weights) in the same 16-bit slots
+// Writes one image of `rows` rows x 64 k (16-bit words, SWIZZLE_128B K-major) for rows n0.., k0..
+// f16: IEEE half instead of bfloat16 in the same 16-bit slots.  lo_part: the residual word lo = rn(v - hi) of the
+// split-precision weights (nn_tcx.cu, three-product mode) instead of hi = rn(v).
 template <typename Fn>
-void write_image(std::vector<__nv_bfloat16>& dst, int rows, int n0, int n_valid, int k0, int k_valid, Fn&& get, bool f16 = false) {
+void write_image(std::vector<__nv_bfloat16>& dst, int rows, int n0, int n_valid, int k0, int k_valid, Fn&& get, bool f16 = false,
+                 bool lo_part = false, float wscale = 1.f) {
   const size_t base = dst.size();
   dst.resize(base + (size_t)rows * 64, __float2bfloat16(0.f));
   for (int r = 0; r < rows; ++r) {
     for (int k = 0; k < 64; ++k) {
       float v = 0.f;
-      if (r < n_valid && k < k_valid) v = get(n0 + r, k0 + k);
+      if (r < n_valid && k < k_valid) v = get(n0 + r, k0 + k) * wscale;
       const size_t off = (size_t)r * 64 + (size_t)((((k >> 3) ^ (r & 7)) << 3) + (k & 7));
+      uint16_t bits;
       if (f16) {
-        const __half hv = __float2half(v);
-        std::memcpy(&dst[base + off], &hv, sizeof(hv));
+        ASEP_CHECK(std::fabs(v) < 60000.f, ASEP_ERR_UNSUPPORTED, "coupling-network weight %g outside the fp16 range of this precision mode", v);
+        __half hv = __float2half(v);
+        if (lo_part) hv = __float2half(v - __half2float(hv));
+        std::memcpy(&bits, &hv, sizeof(bits));
       } else {
-        dst[base + off] = __float2bfloat16(v);
+        __nv_bfloat16 bv = __float2bfloat16(v);
+        if (lo_part) bv = __float2bfloat16(v - __bfloat162float(bv));
+        std::memcpy(&bits, &bv, sizeof(bits));
       }
+      std::memcpy(reinterpret_cast<uint16_t*>(dst.data()) + base + off, &bits, sizeof(bits));
     }
   }
 }
 
+// f16_1 / f16_23: stage-1 / stage-2,3 weights as IEEE half.  lo_part: the residual images of the three-product mode;
+// the stage-1 operand is [x_hi | x_lo] against [W1 ; W1], so the residual image is [W1_lo ; 0] (x_hi . W1_lo only).
+// wscale: power of two the weights are multiplied by before rounding (the kernel multiplies the accumulators by
+// 1 / wscale): keeps the fp16 residuals of O(0.04) weights out of the subnormal range.
 template <typename F1, typename F2, typename F3>
-void build_stage_set(TCStageSet& set, int K1, int N3, F1&& b1, F2&& b2, F3&& b3, bool f16_23) {
+void build_stage_set(TCStageSet& set, int K1, int N3, F1&& b1, F2&& b2, F3&& b3, bool f16_23, bool f16_1 = false,
+                     bool lo_part = false, float wscale = 1.f) {
   set.k1_steps = (K1 + 15) / 16;
   set.k1_panels = (K1 + 63) / 64;
   set.n3p = pad16(N3);
   ASEP_CHECK(set.k1_panels <= kNumPanels && set.n3p <= 256, ASEP_ERR_UNSUPPORTED,
              "coupling network shape outside the tcgen05 kernel (K1=%d, N3=%d)", K1, N3);
   std::vector<__nv_bfloat16> img;
+  const int K1h = K1 / 2;
+  auto b1p = [&](int n, int k) { return (lo_part && k >= K1h) ? 0.f : b1(n, k); };
   for (int half = 0; half < 2; ++half)
     for (int kp = 0; kp < set.k1_panels; ++kp)
-      write_image(img, kStageRows, half * 256, 256, kp * 64, std::min(64, K1 - kp * 64), b1);
+      write_image(img, kStageRows, half * 256, 256, kp * 64, std::min(64, K1 - kp * 64), b1p, f16_1, lo_part, wscale);
   for (int half = 0; half < 2; ++half)
-    for (int kp = 0; kp < kNumPanels; ++kp) write_image(img, kStageRows, half * 256, 256, kp * 64, 64, b2, f16_23);
-  for (int kp = 0; kp < kNumPanels; ++kp) write_image(img, set.n3p, 0, N3, kp * 64, 64, b3, f16_23);
+    for (int kp = 0; kp < kNumPanels; ++kp) write_image(img, kStageRows, half * 256, 256, kp * 64, 64, b2, f16_23, lo_part, wscale);
+  for (int kp = 0; kp < kNumPanels; ++kp) write_image(img, set.n3p, 0, N3, kp * 64, 64, b3, f16_23, lo_part, wscale);
   set.bytes = img.size() * sizeof(__nv_bfloat16);
   CUDA_CHECK(cudaMalloc(&set.img, set.bytes));
   CUDA_CHECK(cudaMemcpy(set.img, img.data(), set.bytes, cudaMemcpyHostToDevice));

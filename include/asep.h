@@ -52,8 +52,12 @@ typedef enum {
   ASEP_PREC_BF16X2 = 4, /* Glow only: the tensor-core "exact" mode.  Hidden activations of the coupling network as
                          * (hi + lo) bf16 pairs (16 significant bits, fp32 range), two tcgen05 products per hidden GEMM
                          * against the bf16 weight images: meets inverse(forward(x)) <= 1e-4 on tensor cores      */
-  ASEP_PREC_FP16X2 = 5  /* as ASEP_PREC_BF16X2 with (hi + lo) fp16 pairs (22 bits) and fp16 stage-2/3 weights in the
+  ASEP_PREC_FP16X2 = 5, /* as ASEP_PREC_BF16X2 with (hi + lo) fp16 pairs (22 bits) and fp16 stage-2/3 weights in the
                          * forward network; hidden activations must stay below 65504 (else NaN); gradients use bf16 pairs */
+  ASEP_PREC_FP16X3 = 6  /* Glow only: the score-exact tensor-core mode.  Weights as (hi + lo) pairs as well, three tcgen05
+                         * products per GEMM (hi.hi + lo.hi + hi.lo); fp16 pairs end to end in the forward network
+                         * (fp32-level pre-activations and ReLU masks), bf16 pairs in the data-gradient pass: meets the
+                         * per-Langevin-step gate at every noise level like ASEP_PREC_FP32, on tensor cores           */
 } asep_precision;
 
 const char* asep_last_error(void);
