@@ -81,6 +81,7 @@ _SIGNATURES = {
     "asep_glow_num_trainable": [_V, ctypes.POINTER(ctypes.c_int64)],
     "asep_glow_train_grads": [_V, _P, _P, _F, _I, _P, _P, _V],
     "asep_glow_adamax_step": [_V, _P, _F, _F, _F, _F, _V],
+    "asep_glow_adam_step": [_V, _P, _F, _F, _F, _F, _V],
     "asep_glow_get_flat": [_V, _P, _V],
     "asep_glow_set_flat": [_V, _P, _V],
     "asep_glow_sync_host": [_V],
@@ -102,9 +103,16 @@ _SIGNATURES = {
     "asep_ncsn_prepare": [_V],
     "asep_ncsn_forward": [_V, _P, _P, _P, _V],
     "asep_basis_ncsn_inner": [_V, _V, _P, _P, _P, _I, _I, _F, _F, _F, _P, _P, _U64, _U64, _U64, _P, _P, _V],
+    "asep_basis_glow_run": [ctypes.POINTER(_V), ctypes.POINTER(_V), _I, _P, _P, _P, _I, _I, ctypes.POINTER(ctypes.c_float),
+                            ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float), _U64, _U64, _P, _P, _V],
+    "asep_basis_ncsn_run": [_V, _V, _P, _P, _P, _I, _I, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float),
+                            ctypes.POINTER(ctypes.c_float), _U64, _U64, _P, _P, _V],
     "asep_conv_profile": [_I],
     "asep_conv_profile_read": [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64),
                                ctypes.POINTER(ctypes.c_double)],
+    "asep_hbm_profile": [_I],
+    "asep_hbm_profile_read": [_I, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64),
+                              ctypes.POINTER(ctypes.c_double)],
     "asep_tc_profile": [_I],
     "asep_tc_profile_read": [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64),
                              ctypes.POINTER(ctypes.c_double)],
@@ -168,6 +176,20 @@ def conv_profile_read():
     ms, n, fl = ctypes.c_double(), ctypes.c_int64(), ctypes.c_double()
     check(load().asep_conv_profile_read(ctypes.byref(ms), ctypes.byref(n), ctypes.byref(fl)))
     return ms.value, n.value, fl.value
+
+
+HBM_CATEGORIES = {"flow_step": 0, "langevin": 1, "ncsn_prep": 2, "ncsn_pool_resize": 3, "gather": 4}
+
+
+def hbm_profile(on: bool) -> None:
+    check(load().asep_hbm_profile(int(on)))
+
+
+def hbm_profile_read(category: int):
+    """(summed kernel ms, launches, algorithmic bytes) of one HBM-bound kernel category since hbm_profile(True)."""
+    ms, n, by = ctypes.c_double(), ctypes.c_int64(), ctypes.c_double()
+    check(load().asep_hbm_profile_read(int(category), ctypes.byref(ms), ctypes.byref(n), ctypes.byref(by)))
+    return ms.value, n.value, by.value
 
 
 def tc_profile(on: bool) -> None:

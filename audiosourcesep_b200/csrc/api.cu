@@ -4,12 +4,61 @@
 #include <cstring>
 #include <memory>
 
+#include <vector>
 #include "glow_model.h"
 #include "ncsn_model.h"
 
 namespace asep {
 
 std::atomic<long long> g_launch_count{0};
+
+// ------------------------------------------------------------------ HBM-kernel profiler (common.cuh)
+namespace {
+struct HbmRec { cudaEvent_t a = nullptr, b = nullptr; int cat = 0; };
+bool g_hbm_on = false;
+std::vector<HbmRec*> g_hbm_recs, g_hbm_pool;
+double g_hbm_bytes[kHbmCatCount] = {0};
+}  // namespace
+
+HbmScope::HbmScope(int cat, double bytes, cudaStream_t s) : cat_(cat), s_(s), rec_(nullptr) {
+  if (!g_hbm_on) return;
+  HbmRec* r;
+  if (!g_hbm_pool.empty()) { r = g_hbm_pool.back(); g_hbm_pool.pop_back(); }
+  else { r = new HbmRec(); cudaEventCreate(&r->a); cudaEventCreate(&r->b); }
+  r->cat = cat;
+  cudaEventRecord(r->a, s);
+  g_hbm_bytes[cat] += bytes;
+  rec_ = r;
+}
+HbmScope::~HbmScope() {
+  if (!rec_) return;
+  HbmRec* r = static_cast<HbmRec*>(rec_);
+  cudaEventRecord(r->b, s_);
+  g_hbm_recs.push_back(r);
+}
+void hbm_profile(bool on) {
+  g_hbm_on = on;
+  if (on) {
+    for (auto* r : g_hbm_recs) g_hbm_pool.push_back(r);
+    g_hbm_recs.clear();
+    for (double& b : g_hbm_bytes) b = 0.0;
+  }
+}
+void hbm_profile_read(int cat, double* ms, long long* launches, double* bytes) {
+  double t = 0.0;
+  long long n = 0;
+  for (auto* r : g_hbm_recs) {
+    if (r->cat != cat) continue;
+    cudaEventSynchronize(r->b);
+    float e = 0.f;
+    cudaEventElapsedTime(&e, r->a, r->b);
+    t += e;
+    ++n;
+  }
+  if (ms) *ms = t;
+  if (launches) *launches = n;
+  if (bytes) *bytes = (cat >= 0 && cat < kHbmCatCount) ? g_hbm_bytes[cat] : 0.0;
+}
 static thread_local std::string g_last_error;
 static int g_device = -1;
 
@@ -348,6 +397,17 @@ int asep_glow_adamax_step(asep_glow_t h, const DLTensor* grads, float lr, float 
   ASEP_API_END
 }
 
+int asep_glow_adam_step(asep_glow_t h, const DLTensor* grads, float lr, float beta1, float beta2, float eps,
+                          void* stream) {
+  ASEP_API_BEGIN
+  ASEP_CHECK(h, ASEP_ERR_BAD_ARG, "NULL handle");
+  GlowModel& m = *h->model;
+  TView gv = view_f32(grads, "grads", m.device());
+  ASEP_CHECK(gv.numel == m.num_trainable(), ASEP_ERR_BAD_SHAPE, "grads must hold %lld elements", m.num_trainable());
+  m.adam_step(gv.f32, lr, beta1, beta2, eps, as_stream(stream));
+  ASEP_API_END
+}
+
 int asep_glow_get_flat(asep_glow_t h, DLTensor* theta, void* stream) {
   ASEP_API_BEGIN
   ASEP_CHECK(h, ASEP_ERR_BAD_ARG, "NULL handle");
@@ -681,6 +741,67 @@ int asep_basis_ncsn_inner(asep_ncsn_t m1, asep_ncsn_t m2, const DLTensor* mixed,
   ASEP_API_END
 }
 
+// ------------------------------------------------------------------ whole sigma x T loops on the device
+namespace {
+// snapshot of both states after noise level i into snapshots[i] = [2, N, H, W, C] (x_arr of run_basis_sep.py:243-244)
+void snapshot_states(float* snap, int level, const TView& a, const TView& b, cudaStream_t s) {
+  if (!snap) return;
+  float* dst = snap + (size_t)level * 2 * a.numel;
+  CUDA_CHECK(cudaMemcpyAsync(dst, a.f32, (size_t)a.numel * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  CUDA_CHECK(cudaMemcpyAsync(dst + a.numel, b.f32, (size_t)a.numel * sizeof(float), cudaMemcpyDeviceToDevice, s));
+}
+}  // namespace
+
+int asep_basis_glow_run(const asep_glow_t* m1, const asep_glow_t* m2, int n_models, const DLTensor* mixed, DLTensor* x1,
+                        DLTensor* x2, int L, int T, const float* eta, const float* lambda, const float* noise_scale,
+                        uint64_t seed, uint64_t elem_offset, DLTensor* snapshots, DLTensor* nan_count, void* stream) {
+  ASEP_API_BEGIN
+  ASEP_CHECK(m1 && m2 && eta && lambda && noise_scale, ASEP_ERR_BAD_ARG, "NULL argument");
+  ASEP_CHECK(L >= 1 && T >= 0 && (n_models == 1 || n_models == L), ASEP_ERR_BAD_ARG,
+             "n_models must be 1 (one pair of priors for every level) or L (one pair per level)");
+  ASEP_CHECK(m1[0] && m2[0], ASEP_ERR_BAD_ARG, "NULL handle");
+  const int dev = m1[0]->model->device();
+  TView a = view_f32(x1, "x1", dev), b = view_f32(x2, "x2", dev);
+  float* snap = nullptr;
+  if (snapshots) {
+    TView sv = view_f32(snapshots, "snapshots", dev);
+    ASEP_CHECK(sv.numel == (int64_t)L * 2 * a.numel, ASEP_ERR_BAD_SHAPE, "snapshots must be [L, 2, N, H, W, C]");
+    snap = sv.f32;
+  }
+  for (int i = 0; i < L; ++i) {
+    const int k = n_models == 1 ? 0 : i;
+    ASEP_CHECK(m1[k] && m2[k], ASEP_ERR_BAD_ARG, "NULL handle at level %d", i);
+    const int rc = asep_basis_glow_inner(m1[k], m2[k], mixed, x1, x2, T, eta[i], lambda[i], noise_scale[i], nullptr, nullptr, seed,
+                                         (uint64_t)i * (uint64_t)T, elem_offset, nullptr, nan_count, stream);
+    if (rc != ASEP_OK) return rc;                      // asep_last_error() holds the inner message
+    snapshot_states(snap, i, a, b, as_stream(stream));
+  }
+  ASEP_API_END
+}
+
+int asep_basis_ncsn_run(asep_ncsn_t m1, asep_ncsn_t m2, const DLTensor* mixed, DLTensor* x1, DLTensor* x2, int L, int T,
+                        const float* eta, const float* lambda, const float* noise_scale, uint64_t seed, uint64_t elem_offset,
+                        DLTensor* snapshots, DLTensor* nan_count, void* stream) {
+  ASEP_API_BEGIN
+  ASEP_CHECK(m1 && m2 && eta && lambda && noise_scale, ASEP_ERR_BAD_ARG, "NULL argument");
+  ASEP_CHECK(L >= 1 && T >= 0, ASEP_ERR_BAD_ARG, "bad L / T");
+  const int dev = m1->model->device();
+  TView a = view_f32(x1, "x1", dev), b = view_f32(x2, "x2", dev);
+  float* snap = nullptr;
+  if (snapshots) {
+    TView sv = view_f32(snapshots, "snapshots", dev);
+    ASEP_CHECK(sv.numel == (int64_t)L * 2 * a.numel, ASEP_ERR_BAD_SHAPE, "snapshots must be [L, 2, N, H, W, C]");
+    snap = sv.f32;
+  }
+  for (int i = 0; i < L; ++i) {
+    const int rc = asep_basis_ncsn_inner(m1, m2, mixed, x1, x2, i, T, eta[i], lambda[i], noise_scale[i], nullptr, nullptr, seed,
+                                         (uint64_t)i * (uint64_t)T, elem_offset, nullptr, nan_count, stream);
+    if (rc != ASEP_OK) return rc;
+    snapshot_states(snap, i, a, b, as_stream(stream));
+  }
+  ASEP_API_END
+}
+
 int asep_conv_profile(int on) {
   ASEP_API_BEGIN
   conv_tc_profile(on);
@@ -691,6 +812,21 @@ int asep_conv_profile_read(double* total_ms, int64_t* launches, double* flops) {
   ASEP_API_BEGIN
   long long n = 0;
   conv_tc_profile_read(total_ms, &n, flops);
+  if (launches) *launches = (int64_t)n;
+  ASEP_API_END
+}
+
+int asep_hbm_profile(int on) {
+  ASEP_API_BEGIN
+  hbm_profile(on != 0);
+  ASEP_API_END
+}
+
+int asep_hbm_profile_read(int category, double* total_ms, int64_t* launches, double* bytes) {
+  ASEP_API_BEGIN
+  ASEP_CHECK(category >= 0 && category < kHbmCatCount, ASEP_ERR_BAD_ARG, "unknown kernel category %d", category);
+  long long n = 0;
+  hbm_profile_read(category, total_ms, &n, bytes);
   if (launches) *launches = (int64_t)n;
   ASEP_API_END
 }

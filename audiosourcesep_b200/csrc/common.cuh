@@ -46,6 +46,25 @@ extern std::atomic<long long> g_launch_count;
 
 inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// ---- measurement aid for the HBM-bound kernels (bench.py `roofline_hbm`): while switched on (asep_hbm_profile), every
+// launch of a profiled category is bracketed by a CUDA event pair on its own stream and its ALGORITHMIC bytes are
+// summed.  Off (the default) a scope costs one branch.
+enum HbmCat {
+  kHbmFlowStep = 0,   // k_pre / k_post_pre / k_inv_step / k_bwd_*: ActNorm + 1x1 + coupling (+ fused col2im)
+  kHbmLangevin = 1,   // k_langevin
+  kHbmPrep = 2,       // k_prep: normalise (+ ELU) + bf16 cast of a convolution input
+  kHbmPool = 3,       // k_pool5_1d / k_avgpool2 / k_resize2x_add
+  kHbmGather = 4,     // k_gather_* (col2im of the per-tap outputs; only where not fused)
+  kHbmCatCount = 5
+};
+struct HbmScope {
+  HbmScope(int cat, double bytes, cudaStream_t s);
+  ~HbmScope();
+  int cat_; cudaStream_t s_; void* rec_;
+};
+void hbm_profile(bool on);
+void hbm_profile_read(int cat, double* ms, long long* launches, double* bytes);
+
 // ---- DLTensor validation
 struct TView {
   float* f32 = nullptr;

@@ -88,6 +88,82 @@ __device__ __forceinline__ void accumulate_sample(double* acc, float v, long lon
   }
 }
 
+// Device view of GatherSrc (kernel argument).
+struct GArg {
+  const float* G; const float* const3; const float* c3;
+  int n3p, nparts, H, W;
+  long long part_stride;
+};
+
+// r[c] = c3[c] + sum_{tap in bounds} (G[p + off(tap)][tap*C + c] + const3[tap*C + c])     (same order and association
+// as k_gather_vec / k_gather_fwd in nn_tc_shared.cuh, so fused and unfused results are bit-identical)
+template <int C>
+__device__ __forceinline__ void gather_fwd_row(const GArg& g, long long p, float (&rv)[C]) {
+  const int w = (int)(p % g.W), h = (int)((p / g.W) % g.H);
+#pragma unroll
+  for (int c = 0; c < C; ++c) rv[c] = __ldg(g.c3 + c);
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+    const int hh = h + dy, ww = w + dx;
+    if (hh < 0 || hh >= g.H || ww < 0 || ww >= g.W) continue;
+    const long long pp = p + (long long)dy * g.W + dx;
+    const float* base = g.G + (pp >> 7) * (128ll * g.n3p) + (pp & 127) * 4;
+#pragma unroll
+    for (int q = 0; q < C / 4; ++q) {
+      const int col = tap * C + 4 * q;
+      const float* src = base + (long long)(col >> 2) * 512;
+      float4 t = __ldg(reinterpret_cast<const float4*>(src));
+      for (int part = 1; part < g.nparts; ++part) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(src + part * g.part_stride));
+        t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+      }
+      const float4 k = __ldg(reinterpret_cast<const float4*>(g.const3 + col));
+      t.x += k.x; t.y += k.y; t.z += k.z; t.w += k.w;
+      rv[4 * q] += t.x; rv[4 * q + 1] += t.y; rv[4 * q + 2] += t.z; rv[4 * q + 3] += t.w;
+    }
+  }
+}
+
+// gxb[ci] = sum_{tap: p - off in bounds} G'[p - off(tap)][tap*Ch + ci]      (Ch = 2: 8-byte loads, else 16-byte)
+template <int Ch>
+__device__ __forceinline__ void gather_bwd_row(const GArg& g, long long p, float (&gb)[Ch]) {
+  const int w = (int)(p % g.W), h = (int)((p / g.W) % g.H);
+#pragma unroll
+  for (int c = 0; c < Ch; ++c) gb[c] = 0.f;
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    const int dy = -(tap / 3 - 1), dx = -(tap % 3 - 1);
+    const int hh = h + dy, ww = w + dx;
+    if (hh < 0 || hh >= g.H || ww < 0 || ww >= g.W) continue;
+    const long long pp = p + (long long)dy * g.W + dx;
+    const float* base = g.G + (pp >> 7) * (128ll * g.n3p) + (pp & 127) * 4;
+    if constexpr (Ch % 4 == 0) {
+#pragma unroll
+      for (int q = 0; q < Ch / 4; ++q) {
+        const int col = tap * Ch + 4 * q;
+        const float* src = base + (long long)(col >> 2) * 512;
+        float4 t = __ldg(reinterpret_cast<const float4*>(src));
+        for (int part = 1; part < g.nparts; ++part) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(src + part * g.part_stride));
+          t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+        }
+        gb[4 * q] += t.x; gb[4 * q + 1] += t.y; gb[4 * q + 2] += t.z; gb[4 * q + 3] += t.w;
+      }
+    } else {
+      static_assert(Ch == 2, "gather_bwd_row: channel count");
+      const int col = tap * 2;
+      const float* src = base + (long long)(col >> 2) * 512 + (col & 3);
+      float2 t = __ldg(reinterpret_cast<const float2*>(src));
+      for (int part = 1; part < g.nparts; ++part) {
+        const float2 v = __ldg(reinterpret_cast<const float2*>(src + part * g.part_stride));
+        t.x += v.x; t.y += v.y;
+      }
+      gb[0] += t.x; gb[1] += t.y;
+    }
+  }
+}
+
 template <int C>
 __global__ void __launch_bounds__(kThreads) k_pre(const float* __restrict__ x, float* __restrict__ u,
                                                   const float* __restrict__ sc, long long M) {
@@ -101,10 +177,11 @@ __global__ void __launch_bounds__(kThreads) k_pre(const float* __restrict__ x, f
   store_row<C>(u + p * C, uv);
 }
 
-template <int C, bool kNext>
+template <int C, bool kNext, bool kGather = false>
 __global__ void __launch_bounds__(kThreads) k_post_pre(const float* __restrict__ u, const float* __restrict__ r,
                                                        float* __restrict__ out, const float* __restrict__ sc_next,
-                                                       double* __restrict__ acc, long long M, int HW) {
+                                                       double* __restrict__ acc, long long M, int HW, const GArg g = GArg{},
+                                                       float* __restrict__ r_out = nullptr) {
   __shared__ float smem[kNext ? 2 * C + 2 * C * C : 1];
   if constexpr (kNext) stage_consts<C>(sc_next, smem);
   long long p = (long long)blockIdx.x * kThreads + threadIdx.x;
@@ -112,7 +189,12 @@ __global__ void __launch_bounds__(kThreads) k_post_pre(const float* __restrict__
   if (p < M) {
     float uv[C], rv[C], y[C];
     load_row<C>(u + p * C, uv);
-    load_row<C>(r + p * C, rv);
+    if constexpr (kGather) {
+      gather_fwd_row<C>(g, p, rv);
+      if (r_out != nullptr) store_row<C>(r_out + p * C, rv);
+    } else {
+      load_row<C>(r + p * C, rv);
+    }
 #pragma unroll
     for (int c = 0; c < C / 2; ++c) {
       float sl = tanhf(rv[c]);                       // flow_tfk_layers.py:83
@@ -131,10 +213,10 @@ __global__ void __launch_bounds__(kThreads) k_post_pre(const float* __restrict__
   if (acc != nullptr) accumulate_sample(acc, sum_sl, p, M, HW);
 }
 
-template <int C>
+template <int C, bool kGather = false>
 __global__ void __launch_bounds__(kThreads) k_inv_step(const float* __restrict__ y, const float* __restrict__ r,
                                                        float* __restrict__ x, const float* __restrict__ sc,
-                                                       double* __restrict__ acc, long long M, int HW) {
+                                                       double* __restrict__ acc, long long M, int HW, const GArg g = GArg{}) {
   __shared__ float smem[2 * C + 2 * C * C];
   stage_consts<C>(sc, smem);
   long long p = (long long)blockIdx.x * kThreads + threadIdx.x;
@@ -142,7 +224,8 @@ __global__ void __launch_bounds__(kThreads) k_inv_step(const float* __restrict__
   if (p < M) {
     float yv[C], rv[C], uv[C], xv[C];
     load_row<C>(y + p * C, yv);
-    load_row<C>(r + p * C, rv);
+    if constexpr (kGather) gather_fwd_row<C>(g, p, rv);
+    else load_row<C>(r + p * C, rv);
 #pragma unroll
     for (int c = 0; c < C / 2; ++c) {
       float sl = tanhf(rv[c]);
@@ -187,17 +270,18 @@ __global__ void __launch_bounds__(kThreads) k_bwd_coupling(const float* __restri
   store_row<C>(gu + p * C, guv);
 }
 
-template <int C>
+template <int C, bool kGather = false>
 __global__ void __launch_bounds__(kThreads) k_bwd_pre(const float* __restrict__ gu, const float* __restrict__ gxb,
                                                       float* __restrict__ gx, const float* __restrict__ sc,
-                                                      long long M) {
+                                                      long long M, const GArg ga = GArg{}) {
   __shared__ float smem[2 * C + 2 * C * C];
   stage_consts<C>(sc, smem);
   long long p = (long long)blockIdx.x * kThreads + threadIdx.x;
   if (p >= M) return;
   float g[C], gb[C / 2], o[C];
   load_row<C>(gu + p * C, g);
-  load_row<C / 2>(gxb + p * (C / 2), gb);
+  if constexpr (kGather) gather_bwd_row<C / 2>(ga, p, gb);
+  else load_row<C / 2>(gxb + p * (C / 2), gb);
 #pragma unroll
   for (int c = 0; c < C / 2; ++c) g[C / 2 + c] += gb[c];
   const float* Wm = smem + 2 * C;
@@ -359,6 +443,7 @@ __global__ void k_chanmix(const float* __restrict__ x, const float* __restrict__
 
 void launch_pre(const float* x, float* u, const float* sc, long long M, int C, cudaStream_t s) {
   if (M == 0) return;
+  HbmScope prof(kHbmFlowStep, 8.0 * C * (double)M, s);            // read x, write u
   DISPATCH_C(C, (k_pre<kC><<<cdiv(M, kThreads), kThreads, 0, s>>>(x, u, sc, M)));
   ASEP_LAUNCH_CHECK();
 }
@@ -366,6 +451,7 @@ void launch_pre(const float* x, float* u, const float* sc, long long M, int C, c
 void launch_post_pre(const float* u, const float* r, float* out, const float* sc_next, double* acc, long long M,
                      int HW, int C, cudaStream_t s) {
   if (M == 0) return;
+  HbmScope prof(kHbmFlowStep, 12.0 * C * (double)M, s);           // read u, read r, write the next state
   if (sc_next) {
     DISPATCH_C(C, (k_post_pre<kC, true><<<cdiv(M, kThreads), kThreads, 0, s>>>(u, r, out, sc_next, acc, M, HW)));
   } else {
@@ -377,13 +463,63 @@ void launch_post_pre(const float* u, const float* r, float* out, const float* sc
 void launch_inv_step(const float* y, const float* r, float* x, const float* sc, double* acc, long long M, int HW,
                      int C, cudaStream_t s) {
   if (M == 0) return;
+  HbmScope prof(kHbmFlowStep, 12.0 * C * (double)M, s);
   DISPATCH_C(C, (k_inv_step<kC><<<cdiv(M, kThreads), kThreads, 0, s>>>(y, r, x, sc, acc, M, HW)));
+  ASEP_LAUNCH_CHECK();
+}
+
+namespace {
+GArg to_arg(const GatherSrc& g) { return GArg{g.G, g.const3, g.c3, g.n3p, g.nparts, g.H, g.W, g.part_stride}; }
+// the fused gather reads whole float4 columns of G: C (forward) must be a multiple of 4, C/2 (backward) 2 or a multiple of 4
+#define DISPATCH_CG(C, EXPR)                                                                           \
+  do {                                                                                                 \
+    switch (C) {                                                                                       \
+      case 4: { constexpr int kC = 4; EXPR; } break;                                                   \
+      case 8: { constexpr int kC = 8; EXPR; } break;                                                   \
+      case 16: { constexpr int kC = 16; EXPR; } break;                                                 \
+      default: ASEP_CHECK(false, ASEP_ERR_UNSUPPORTED, "fused gather: channel count %d", C);           \
+    }                                                                                                  \
+  } while (0)
+}  // namespace
+
+bool fused_gather_supported(int C) { return C == 4 || C == 8 || C == 16; }
+
+void launch_post_pre_g(const float* u, const GatherSrc& g, float* r_out, float* out, const float* sc_next, double* acc,
+                       long long M, int HW, int C, cudaStream_t s) {
+  if (M == 0) return;
+  // algorithmic bytes as for the unfused step (state in, network output, state out: 12 C per pixel; + r when it is kept);
+  // the fused col2im really reads the 9 per-tap partials (36 C per pixel) instead of r
+  HbmScope prof(kHbmFlowStep, (r_out ? 16.0 : 12.0) * C * (double)M, s);
+  const GArg a = to_arg(g);
+  if (sc_next) {
+    DISPATCH_CG(C, (k_post_pre<kC, true, true><<<cdiv(M, kThreads), kThreads, 0, s>>>(u, nullptr, out, sc_next, acc, M, HW, a, r_out)));
+  } else {
+    DISPATCH_CG(C, (k_post_pre<kC, false, true><<<cdiv(M, kThreads), kThreads, 0, s>>>(u, nullptr, out, nullptr, acc, M, HW, a, r_out)));
+  }
+  ASEP_LAUNCH_CHECK();
+}
+
+void launch_inv_step_g(const float* y, const GatherSrc& g, float* x, const float* sc, double* acc, long long M, int HW,
+                       int C, cudaStream_t s) {
+  if (M == 0) return;
+  HbmScope prof(kHbmFlowStep, 12.0 * C * (double)M, s);
+  const GArg a = to_arg(g);
+  DISPATCH_CG(C, (k_inv_step<kC, true><<<cdiv(M, kThreads), kThreads, 0, s>>>(y, nullptr, x, sc, acc, M, HW, a)));
+  ASEP_LAUNCH_CHECK();
+}
+
+void launch_bwd_pre_g(const float* gu, const GatherSrc& g, float* gx, const float* sc, long long M, int C, cudaStream_t s) {
+  if (M == 0) return;
+  HbmScope prof(kHbmFlowStep, 10.0 * C * (double)M, s);           // read gu (C), gxb (C/2), write gx (C)
+  const GArg a = to_arg(g);
+  DISPATCH_CG(C, (k_bwd_pre<kC, true><<<cdiv(M, kThreads), kThreads, 0, s>>>(gu, nullptr, gx, sc, M, a)));
   ASEP_LAUNCH_CHECK();
 }
 
 void launch_bwd_coupling(const float* gy, const float* u, const float* r, float* gr, float* gu, long long M, int C,
                          cudaStream_t s) {
   if (M == 0) return;
+  HbmScope prof(kHbmFlowStep, 20.0 * C * (double)M, s);           // read gy, u, r; write gr, gu
   DISPATCH_C(C, (k_bwd_coupling<kC><<<cdiv(M, kThreads), kThreads, 0, s>>>(gy, u, r, gr, gu, M)));
   ASEP_LAUNCH_CHECK();
 }
@@ -391,6 +527,7 @@ void launch_bwd_coupling(const float* gy, const float* u, const float* r, float*
 void launch_bwd_pre(const float* gu, const float* gxb, float* gx, const float* sc, long long M, int C,
                     cudaStream_t s) {
   if (M == 0) return;
+  HbmScope prof(kHbmFlowStep, 10.0 * C * (double)M, s);
   DISPATCH_C(C, (k_bwd_pre<kC><<<cdiv(M, kThreads), kThreads, 0, s>>>(gu, gxb, gx, sc, M)));
   ASEP_LAUNCH_CHECK();
 }

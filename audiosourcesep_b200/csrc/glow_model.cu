@@ -403,6 +403,7 @@ void GlowModel::ensure_work(int N, bool save) {
 }
 
 // ------------------------------------------------------------------ coupling network dispatch
+// r == nullptr (tensor-core modes only): the col2im gather is left to the consuming flow-step kernel (fused_gather()).
 void GlowModel::nn_forward(int b, int k, const float* state, float* r, int N, bool save, cudaStream_t s) {
   const Level& lv = levels_[b];
   StepDerived& sd = step(b, k);
@@ -414,6 +415,13 @@ void GlowModel::nn_forward(int b, int k, const float* state, float* r, int N, bo
     if (is_tcx()) nn_tcx_forward(sd.wtc, work_.tc, state, r, m1, m2, N, lv.H, lv.W, lv.C, s);
     else nn_tc_forward(sd.wtc, work_.tc, state, r, m1, m2, N, lv.H, lv.W, lv.C, s);
   }
+}
+
+bool GlowModel::fused_gather(int b) const { return is_tc() && fused_gather_supported(levels_[b].C); }
+
+GatherSrc GlowModel::gather_src(int b, int k, int N, bool backward) {
+  const Level& lv = levels_[b];
+  return nn_tc_gather_src(step(b, k).wtc, work_.tc, backward, (long long)N * lv.H * lv.W, lv.H, lv.W, is_tcx());
 }
 
 void GlowModel::nn_backward(int b, int k, const float* state, const float* gr, float* gxb, int N, cudaStream_t s) {
@@ -454,10 +462,20 @@ void GlowModel::run_forward(const float* x, int N, bool save, cudaStream_t s) {
     auto rbuf = [&](int k) { return work_.save ? work_.R[b][k] : work_.R[b][0]; };
     // GlowBlock applies glowStep_{K-1} first (flow_glow.py:51-52)
     launch_pre(work_.X[b], ubuf(K - 1), step(b, K - 1).sc, M, lv.C, s);
+    const bool fuse = fused_gather(b);
     for (int k = K - 1; k >= 0; --k) {
-      nn_forward(b, k, ubuf(k), rbuf(k), N, save, s);
-      if (k > 0) launch_post_pre(ubuf(k), rbuf(k), ubuf(k - 1), step(b, k - 1).sc, work_.acc_ld, M, HW, lv.C, s);
-      else launch_post_pre(ubuf(k), rbuf(k), work_.O[b], nullptr, work_.acc_ld, M, HW, lv.C, s);
+      float* out = k > 0 ? ubuf(k - 1) : work_.O[b];
+      const float* sc_next = k > 0 ? step(b, k - 1).sc : nullptr;
+      if (fuse) {
+        // tensor-core modes: the flow-step kernel gathers the per-tap outputs itself; r is only written when the
+        // backward pass will need it
+        nn_forward(b, k, ubuf(k), nullptr, N, save, s);
+        launch_post_pre_g(ubuf(k), gather_src(b, k, N, false), work_.save ? rbuf(k) : nullptr, out, sc_next, work_.acc_ld, M,
+                          HW, lv.C, s);
+      } else {
+        nn_forward(b, k, ubuf(k), rbuf(k), N, save, s);
+        launch_post_pre(ubuf(k), rbuf(k), out, sc_next, work_.acc_ld, M, HW, lv.C, s);
+      }
     }
     int Cz, nb, coff;
     latent_slice(b, Cz, nb, coff);
@@ -516,13 +534,20 @@ void GlowModel::grad_log_prob(const float* x, float* grad, float* logp, int N, c
     launch_split_merge(gy, work_.gz, gX_next, N, lv.H, lv.W, lv.C, Cz, nb, CL_, coff, Dl_, 1, s);
     for (int k = 0; k < K; ++k) {          // steps were applied K-1..0, so unwind 0..K-1
       launch_bwd_coupling(gy, work_.U[b][k], work_.R[b][k], work_.gr, work_.gu, M, lv.C, s);
-      if (is_tcx() && !work_.M1.empty() && !work_.M1[b].empty())
-        nn_tcx_backward(step(b, k).wtc, work_.tc, work_.gr, work_.M1[b][k], work_.M2[b][k], work_.gxb, N, lv.H, lv.W, lv.C, s);
-      else if (is_tc() && !work_.M1.empty() && !work_.M1[b].empty())
-        nn_tc_backward(step(b, k).wtc, work_.tc, work_.gr, work_.M1[b][k], work_.M2[b][k], work_.gxb, N, lv.H, lv.W, lv.C, s);
-      else
-        nn_backward(b, k, work_.U[b][k], work_.gr, work_.gxb, N, s);
-      launch_bwd_pre(work_.gu, work_.gxb, other, step(b, k).sc, M, lv.C, s);
+      const bool saved = is_tc() && !work_.M1.empty() && !work_.M1[b].empty();
+      if (saved && fused_gather(b)) {          // masks kept from the forward pass: gradient GEMMs + fused col2im
+        if (is_tcx()) nn_tcx_backward(step(b, k).wtc, work_.tc, work_.gr, work_.M1[b][k], work_.M2[b][k], nullptr, N, lv.H, lv.W, lv.C, s);
+        else nn_tc_backward(step(b, k).wtc, work_.tc, work_.gr, work_.M1[b][k], work_.M2[b][k], nullptr, N, lv.H, lv.W, lv.C, s);
+        launch_bwd_pre_g(work_.gu, gather_src(b, k, N, true), other, step(b, k).sc, M, lv.C, s);
+      } else {
+        if (saved && is_tcx())
+          nn_tcx_backward(step(b, k).wtc, work_.tc, work_.gr, work_.M1[b][k], work_.M2[b][k], work_.gxb, N, lv.H, lv.W, lv.C, s);
+        else if (saved)
+          nn_tc_backward(step(b, k).wtc, work_.tc, work_.gr, work_.M1[b][k], work_.M2[b][k], work_.gxb, N, lv.H, lv.W, lv.C, s);
+        else
+          nn_backward(b, k, work_.U[b][k], work_.gr, work_.gxb, N, s);
+        launch_bwd_pre(work_.gu, work_.gxb, other, step(b, k).sc, M, lv.C, s);
+      }
       std::swap(gy, other);
     }
     gX_next = gy;
@@ -549,8 +574,13 @@ void GlowModel::inverse(const float* z, float* x, int N, cudaStream_t s) {
     float* bufs[2] = {work_.U[b][0], work_.U[b][1]};
     for (int k = 0; k < K; ++k) {          // flow_glow.py: Chain.inverse walks steps 0..K-1
       float* out = (k == K - 1) ? work_.X[b] : bufs[k & 1];
-      nn_forward(b, k, y, work_.R[b][0], N, false, s);
-      launch_inv_step(y, work_.R[b][0], out, step(b, k).sc, nullptr, M, lv.H * lv.W, lv.C, s);
+      if (fused_gather(b)) {
+        nn_forward(b, k, y, nullptr, N, false, s);
+        launch_inv_step_g(y, gather_src(b, k, N, false), out, step(b, k).sc, nullptr, M, lv.H * lv.W, lv.C, s);
+      } else {
+        nn_forward(b, k, y, work_.R[b][0], N, false, s);
+        launch_inv_step(y, work_.R[b][0], out, step(b, k).sc, nullptr, M, lv.H * lv.W, lv.C, s);
+      }
       y = out;
     }
   }

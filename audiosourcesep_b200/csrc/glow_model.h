@@ -76,6 +76,8 @@ class GlowModel {
                    cudaStream_t s);
   // Keras Adamax update of the flat vector, then every derived constant is refreshed on the device.
   void adamax_step(const float* grads, float lr, float beta1, float beta2, float eps, cudaStream_t s);
+  // Keras Adam (train_utils.py:27-28); shares the two moment buffers with Adamax (one optimizer per handle)
+  void adam_step(const float* grads, float lr, float beta1, float beta2, float eps, cudaStream_t s);
   // copies the flat vector back into the host-side parameter store (get_param / prepare see the trained values)
   void sync_host();
   void copy_flat(float* dst, cudaStream_t s) const;         // theta -> dst (device)
@@ -107,6 +109,8 @@ class GlowModel {
   void run_forward(const float* x, int N, bool save, cudaStream_t s);
   void nn_forward(int b, int k, const float* state, float* r, int N, bool save, cudaStream_t s);
   void nn_backward(int b, int k, const float* state, const float* gr, float* gxb, int N, cudaStream_t s);
+  bool fused_gather(int b) const;                           // col2im of the tensor-core network fused into the flow-step kernels
+  GatherSrc gather_src(int b, int k, int N, bool backward);
   void build_step_consts(int b, int k);
   void require_prepared() const;
   double const_logdet() const;

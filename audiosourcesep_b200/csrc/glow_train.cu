@@ -24,7 +24,6 @@ void GlowModel::enable_training() {
   ASEP_CHECK(prepared_, ASEP_ERR_STATE, "call asep_glow_prepare() before asep_glow_enable_training()");
   ASEP_CHECK(!is_tcx(), ASEP_ERR_UNSUPPORTED,
              "the split-precision modes have no weight-gradient path: prepare with ASEP_PREC_BF16 / FP16 / FP32 to train");
-  ASEP_CHECK(cfg_.learntop, ASEP_ERR_UNSUPPORTED, "the training step expects the learnable top prior (learntop)");
   CUDA_CHECK(cudaSetDevice(device_));
   CUDA_CHECK(cudaDeviceSynchronize());
   long long n = 0;
@@ -189,15 +188,17 @@ void GlowModel::train_grads_body(const float* x, const float* noise, float sigma
     xin = work_.gB;
   }
   run_forward(xin, N, true, s);
-  const float* loc = params_.at("prior/loc").dev;
-  const float* ls = params_.at("prior/log_scale").dev;
+  // learntop = False: standard-normal prior without trainable parameters (flow_builder.py:143-144)
+  const float* loc = cfg_.learntop ? params_.at("prior/loc").dev : nullptr;
+  const float* ls = cfg_.learntop ? params_.at("prior/log_scale").dev : nullptr;
   launch_prior(work_.z, loc, ls, work_.acc_prior, work_.gz, N, Dl_, s);
   // SpecPreprocessing log-det constant (flow_tfp_bijectors.py:390-396); the per-step constants come from the device
   const double pre_const = (double)cfg_.H * cfg_.W * cfg_.C * std::log(1.0 / ((double)cfg_.maxval - (double)cfg_.minval));
   launch_loss(work_.acc_ld, work_.acc_prior, ld_total_, pre_const, N, 1.0 / (double)global_batch, loss, s);
   CUDA_CHECK(cudaMemsetAsync(grads, 0, (size_t)n_trainable_ * sizeof(float), s));
-  launch_prior_grads(work_.z, loc, ls, grads + params_.at("prior/loc").flat_off, grads + params_.at("prior/log_scale").flat_off,
-                     N, Dl_, gs, s);
+  if (cfg_.learntop)
+    launch_prior_grads(work_.z, loc, ls, grads + params_.at("prior/loc").flat_off, grads + params_.at("prior/log_scale").flat_off,
+                       N, Dl_, gs, s);
   float* gX_next = nullptr;
   for (int b = L - 1; b >= 0; --b) {
     const Level& lv = levels_[b];
@@ -265,6 +266,16 @@ void GlowModel::adamax_step(const float* grads, float lr, float beta1, float bet
   ++adam_t_;
   const float lr_t = (float)((double)lr / (1.0 - std::pow((double)beta1, (double)adam_t_)));
   launch_adamax(theta_, grads, adam_m_, adam_u_, n_trainable_, lr_t, beta1, beta2, eps, s);
+  derive_on_device(s);
+}
+
+void GlowModel::adam_step(const float* grads, float lr, float beta1, float beta2, float eps, cudaStream_t s) {
+  ASEP_CHECK(training_, ASEP_ERR_STATE, "asep_glow_enable_training() has not been called");
+  CUDA_CHECK(cudaSetDevice(device_));
+  ++adam_t_;
+  const double t = (double)adam_t_;
+  const float lr_t = (float)((double)lr * std::sqrt(1.0 - std::pow((double)beta2, t)) / (1.0 - std::pow((double)beta1, t)));
+  launch_adam(theta_, grads, adam_m_, adam_u_, n_trainable_, lr_t, beta1, beta2, eps, s);
   derive_on_device(s);
 }
 

@@ -8,12 +8,33 @@ namespace asep {
 //   [0,C) exp(log_scale)  [C,2C) shift  [2C,2C+C*C) W[i][o]  [2C+C*C, 2C+2C*C) W^-1[i][o]
 inline int step_const_floats(int C) { return 2 * C + 2 * C * C; }
 
+// Per-tap partial outputs of the tensor-core coupling network (nn_tc.cu / nn_tcx.cu) still in the tiled layout
+// [tile][n3p/4 float4 columns][128 rows][4 floats]; `nparts` K-split partial sums `part_stride` floats apart.  The
+// flow-step kernels below can consume it directly (col2im fused into the element-wise pass: no r round trip, one
+// launch less per flow step).
+struct GatherSrc {
+  const float* G = nullptr;
+  const float* const3 = nullptr;   // forward only: [9][C] border-aware BatchNorm offset of conv3
+  const float* c3 = nullptr;       // forward only: conv3 bias [C]
+  int n3p = 0, nparts = 1, H = 0, W = 0;
+  long long part_stride = 0;
+};
+
 // ---- flow_kernels.cu
 // u = (x*scale+shift) . W                      (flow_tfp_bijectors.py:243, :304-305)
 void launch_pre(const float* x, float* u, const float* sc, long long M, int C, cudaStream_t s);
 // y = [ua*exp(tanh(raw))+t, ub]; acc[n] += sum tanh(raw); then (optional) out = pre_next(y)
 void launch_post_pre(const float* u, const float* r, float* out, const float* sc_next, double* acc, long long M,
                      int HW, int C, cudaStream_t s);
+// as launch_post_pre / launch_inv_step / launch_bwd_pre with the network output gathered from the tiled G on the fly:
+// r = c3 + sum_{tap in bounds} (G[p + off(tap)][tap] + const3[tap]); r_out (may be NULL) receives r when the backward
+// pass needs it.  bwd: gxb = sum_{tap} G'[p - off(tap)][tap].
+void launch_post_pre_g(const float* u, const GatherSrc& g, float* r_out, float* out, const float* sc_next, double* acc,
+                       long long M, int HW, int C, cudaStream_t s);
+void launch_inv_step_g(const float* y, const GatherSrc& g, float* x, const float* sc, double* acc, long long M, int HW,
+                       int C, cudaStream_t s);
+void launch_bwd_pre_g(const float* gu, const GatherSrc& g, float* gx, const float* sc, long long M, int C, cudaStream_t s);
+bool fused_gather_supported(int C);   // channel counts the fused-gather kernels are built for (4, 8, 16)
 // x = (( [ (ya-t)/exp(tanh raw), yb ] . W^-1 ) - shift) / scale ; acc[n] -= sum tanh(raw) when acc != NULL
 void launch_inv_step(const float* y, const float* r, float* x, const float* sc, double* acc, long long M, int HW,
                      int C, cudaStream_t s);

@@ -114,6 +114,8 @@ void launch_langevin(float* x1, float* x2, const float* s1, const float* s2, con
   if (n == 0) return;
   ASEP_CHECK(n % 4 == 0 && elem_offset % 4 == 0, ASEP_ERR_BAD_SHAPE,
              "langevin: element count %lld and offset must be multiples of 4", n);
+  // 5 reads + 2 writes of 4 bytes per element with in-kernel noise, 7 reads + 2 writes with injected noise
+  HbmScope prof(kHbmLangevin, (n1 ? 36.0 : 28.0) * (double)n, s);
   long long n4 = n / 4;
   if (n1 != nullptr && n2 != nullptr)
     k_langevin<true><<<cdiv(n4, 256), 256, 0, s>>>(x1, x2, s1, s2, mixed, n1, n2, eta, lambda, noise_scale, seed,

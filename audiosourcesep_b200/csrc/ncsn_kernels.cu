@@ -324,6 +324,8 @@ void launch_in_coef(const double* sums, const float* gab, int gab_stride_n, cons
 void launch_prep(const float* x, const float2* coef, __nv_bfloat16* y, __nv_bfloat16* y_lo, int N, int HW, int C, int do_elu,
                  cudaStream_t s) {
   ASEP_CHECK(C % 8 == 0 && C / 8 <= 256, ASEP_ERR_UNSUPPORTED, "prep: C = %d (multiple of 8, <= 2048)", C);
+  // reads the fp32 tensor once, writes the bf16 operand (and its low word in the split mode)
+  HbmScope prof(kHbmPrep, (4.0 + (y_lo ? 4.0 : 2.0)) * (double)N * HW * C, s);
   const int C8 = C / 8;
   const int threads = C8 * (256 / C8);
   const int rows = 32;
@@ -334,7 +336,8 @@ void launch_prep(const float* x, const float2* coef, __nv_bfloat16* y, __nv_bflo
 
 void launch_pool5(const float* x, float* tmp, float* y, int N, int H, int W, int C, int is_max, cudaStream_t s) {
   const long long total = (long long)N * H * W * (C / 4);
-  if (is_max) {
+  HbmScope prof(kHbmPool, 8.0 * (double)N * H * W * C, s);          // one read + one write of the tensor (the separable
+  if (is_max) {                                                      // form really moves it twice)
     k_pool5_1d<true, 0><<<cdiv(total, 256), 256, 0, s>>>(x, tmp, H, W, C / 4, total);
     k_pool5_1d<true, 1><<<cdiv(total, 256), 256, 0, s>>>(tmp, y, H, W, C / 4, total);
   } else {
@@ -346,12 +349,14 @@ void launch_pool5(const float* x, float* tmp, float* y, int N, int H, int W, int
 
 void launch_avgpool2(const float* x, float* y, int N, int Hout, int Wout, int C, cudaStream_t s) {
   const long long total = (long long)N * Hout * Wout * (C / 4);
+  HbmScope prof(kHbmPool, 20.0 * (double)N * Hout * Wout * C, s);   // reads 4 inputs per output, writes 1
   k_avgpool2<<<cdiv(total, 256), 256, 0, s>>>(x, y, Hout, Wout, C / 4, total);
   ASEP_LAUNCH_CHECK();
 }
 
 void launch_resize2x_add(const float* x, const float* add, float* y, int N, int h, int w, int C, cudaStream_t s) {
   const long long total = (long long)N * 4 * h * w * (C / 4);
+  HbmScope prof(kHbmPool, (4.0 + (add ? 16.0 : 0.0) + 16.0) * (double)N * h * w * C, s);   // x once, add + y at 4x the pixels
   k_resize2x_add<<<cdiv(total, 256), 256, 0, s>>>(x, add, y, h, w, C / 4, total);
   ASEP_LAUNCH_CHECK();
 }

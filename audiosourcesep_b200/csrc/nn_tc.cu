@@ -547,6 +547,18 @@ void nn_tc_profile_read(double* total_ms, long long* launches, double* flops) {
   if (flops) *flops = g_prof_flops;
 }
 
+GatherSrc nn_tc_gather_src(const NNWeightsTC& w, const NNScratchTC& sc, bool backward, long long M, int H, int W, bool split) {
+  GatherSrc g;
+  g.G = sc.G;
+  g.const3 = backward ? nullptr : w.const3;
+  g.c3 = backward ? nullptr : w.c3;
+  g.n3p = backward ? w.bwd.n3p : w.fwd.n3p;
+  g.H = H; g.W = W;
+  g.nparts = split ? 2 : 1;
+  g.part_stride = split ? (M + kTileM - 1) / kTileM * kTileM * (long long)g.n3p : 0;
+  return g;
+}
+
 size_t nn_tc_g_floats(long long M, int C) { return (size_t)((M + kTileM - 1) / kTileM * kTileM) * (size_t)pad16(9 * C); }   // whole tiles
 
 void nn_tc_prepare(NNWeightsTC& w, const float* k1, const float* c1, const float* g1, const float* b1,
@@ -629,7 +641,7 @@ void nn_tc_forward(const NNWeightsTC& w, const NNScratchTC& sc, const float* sta
   prm.out = sc.G; prm.H = H; prm.W = W; prm.M = M;
   g_next_flops = 2.0 * (double)M * (9.0 * (C / 2) * kF + (double)kF * kF + 9.0 * kF * C);   // conv MACs x 2, unpadded
   run_tc<false>(prm, s);
-  launch_gather_fwd(sc.G, w.const3, w.c3, r, M, H, W, C, w.fwd.n3p, 1, 0, s);
+  if (r != nullptr) launch_gather_fwd(sc.G, w.const3, w.c3, r, M, H, W, C, w.fwd.n3p, 1, 0, s);
 }
 
 void nn_tc_backward(const NNWeightsTC& w, const NNScratchTC& sc, const float* gr, const uint32_t* mask1,
@@ -646,7 +658,7 @@ void nn_tc_backward(const NNWeightsTC& w, const NNScratchTC& sc, const float* gr
   prm.out = sc.G; prm.H = H; prm.W = W; prm.M = M;
   g_next_flops = 2.0 * (double)M * (9.0 * (C / 2) * kF + (double)kF * kF + 9.0 * kF * C);
   run_tc<true>(prm, s);
-  launch_gather_bwd(sc.G, gxb, M, H, W, C / 2, w.bwd.n3p, 1, 0, s);
+  if (gxb != nullptr) launch_gather_bwd(sc.G, gxb, M, H, W, C / 2, w.bwd.n3p, 1, 0, s);
 }
 
 }  // namespace asep

@@ -3,6 +3,7 @@
 #pragma once
 #include <vector>
 #include "common.cuh"
+#include "kernels.h"
 
 namespace asep {
 
@@ -54,6 +55,10 @@ void nn_tc_backward(const NNWeightsTC& w, const NNScratchTC& sc, const float* gr
                     __nv_bfloat16* dump_gp2 = nullptr, __nv_bfloat16* dump_gp1 = nullptr);
 
 size_t nn_tc_g_floats(long long M, int C);   // capacity needed for NNScratchTC::G
+// r == NULL (forward) / gxb == NULL (backward) skips the col2im gather kernel: the caller consumes the tiled G through
+// the fused flow-step kernels (launch_post_pre_g / launch_inv_step_g / launch_bwd_pre_g) with this descriptor.
+// split = the two-part G of nn_tcx_forward / nn_tcx_backward.
+GatherSrc nn_tc_gather_src(const NNWeightsTC& w, const NNScratchTC& sc, bool backward, long long M, int H, int W, bool split);
 
 // ---- split-precision ("exact") tensor-core form (nn_tcx.cu; ASEP_PREC_BF16X2 / ASEP_PREC_FP16X2): the same tile images,
 // hidden activations carried as (hi + lo) 16-bit pairs -> two tcgen05 products per hidden GEMM, 16 (bf16 pairs) or 22

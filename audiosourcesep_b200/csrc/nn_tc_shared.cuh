@@ -311,6 +311,7 @@ inline int pad16(int n) { return (n + 15) / 16 * 16; }
 inline void launch_gather_fwd(const float* G, const float* const3, const float* c3, float* r, long long M, int H, int W, int C,
                               int n3p, int nparts, long long part_stride, cudaStream_t s) {
   const long long total = M * C;
+  HbmScope prof(kHbmGather, 4.0 * (9.0 * C * nparts + C) * (double)M, s);      // 9 per-tap partials in, r out
   if (C % 4 == 0) k_gather_vec<4, true><<<cdiv(total / 4, 256), 256, 0, s>>>(G, const3, c3, r, H, W, C, n3p, total / 4, nparts, part_stride);
   else k_gather_fwd<true><<<cdiv(total, 256), 256, 0, s>>>(G, const3, c3, r, H, W, C, n3p, total, nparts, part_stride);
   ASEP_LAUNCH_CHECK();
@@ -319,6 +320,7 @@ inline void launch_gather_fwd(const float* G, const float* const3, const float* 
 inline void launch_gather_bwd(const float* G, float* gxb, long long M, int H, int W, int Ch, int n3p, int nparts,
                               long long part_stride, cudaStream_t s) {
   const long long total = M * Ch;
+  HbmScope prof(kHbmGather, 4.0 * (9.0 * Ch * nparts + Ch) * (double)M, s);
   if (Ch % 4 == 0) k_gather_vec<4, false><<<cdiv(total / 4, 256), 256, 0, s>>>(G, nullptr, nullptr, gxb, H, W, Ch, n3p, total / 4, nparts, part_stride);
   else if (Ch % 2 == 0) k_gather_vec<2, false><<<cdiv(total / 2, 256), 256, 0, s>>>(G, nullptr, nullptr, gxb, H, W, Ch, n3p, total / 2, nparts, part_stride);
   else k_gather_bwd<true><<<cdiv(total, 256), 256, 0, s>>>(G, gxb, H, W, Ch, n3p, total, nparts, part_stride);

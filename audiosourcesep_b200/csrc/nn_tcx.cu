@@ -472,7 +472,7 @@ void nn_tcx_forward(const NNWeightsTC& w, const NNScratchTC& sc, const float* st
   const double flops = 2.0 * (double)M * (9.0 * (C / 2) * kF + (double)kF * kF + 9.0 * kF * C);
   run_tcx<false>(prm, flops, s);
   const long long tiles = (M + kTileM - 1) / kTileM;
-  launch_gather_fwd(sc.G, w.const3, w.c3, r, M, H, W, C, w.fwd.n3p, 2, tiles * kTileM * (long long)w.fwd.n3p, s);
+  if (r != nullptr) launch_gather_fwd(sc.G, w.const3, w.c3, r, M, H, W, C, w.fwd.n3p, 2, tiles * kTileM * (long long)w.fwd.n3p, s);
 }
 
 void nn_tcx_backward(const NNWeightsTC& w, const NNScratchTC& sc, const float* gr, const uint32_t* mask1,
@@ -489,7 +489,7 @@ void nn_tcx_backward(const NNWeightsTC& w, const NNScratchTC& sc, const float* g
   const double flops = 2.0 * (double)M * (9.0 * (C / 2) * kF + (double)kF * kF + 9.0 * kF * C);
   run_tcx<true>(prm, flops, s);
   const long long tiles = (M + kTileM - 1) / kTileM;
-  launch_gather_bwd(sc.G, gxb, M, H, W, C / 2, w.bwd.n3p, 2, tiles * kTileM * (long long)w.bwd.n3p, s);
+  if (gxb != nullptr) launch_gather_bwd(sc.G, gxb, M, H, W, C / 2, w.bwd.n3p, 2, tiles * kTileM * (long long)w.bwd.n3p, s);
 }
 
 }  // namespace asep

@@ -428,6 +428,19 @@ __global__ void k_adamax(float* __restrict__ theta, const float* __restrict__ g,
 }
 
 
+// Keras Adam (train_utils.py:27-28; OptimizerV2 non-amsgrad form): lr_t = lr sqrt(1 - b2^t) / (1 - b1^t) on the host
+__global__ void k_adam(float* __restrict__ theta, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                       long long n, float lr_t, float b1, float b2, float eps) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float gi = g[i];
+  const float mi = b1 * m[i] + (1.f - b1) * gi;
+  const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+  m[i] = mi;
+  v[i] = vi;
+  theta[i] -= lr_t * mi / (sqrtf(vi) + eps);
+}
+
 // ------------------------------------------------------------------ tensor-core training path helpers
 // G9[q][tap*C+c] = gr[q - off(tap)][c] (0 outside the image), bf16, row stride ld (multiple of 64, zero padded)
 __global__ void __launch_bounds__(256) k_im2col_gr(const float* __restrict__ gr, __nv_bfloat16* __restrict__ G9, int H, int W,
@@ -765,6 +778,12 @@ void launch_sum_doubles(const double* v, int n, double* out, cudaStream_t s) {
 void launch_adamax(float* theta, const float* g, float* m, float* u, long long n, float lr_t, float b1, float b2, float eps,
                    cudaStream_t s) {
   k_adamax<<<cdiv(n, 256), 256, 0, s>>>(theta, g, m, u, n, lr_t, b1, b2, eps);
+  ASEP_LAUNCH_CHECK();
+}
+
+void launch_adam(float* theta, const float* g, float* m, float* v, long long n, float lr_t, float b1, float b2, float eps,
+                 cudaStream_t s) {
+  k_adam<<<cdiv(n, 256), 256, 0, s>>>(theta, g, m, v, n, lr_t, b1, b2, eps);
   ASEP_LAUNCH_CHECK();
 }
 

@@ -47,5 +47,7 @@ void launch_derive_step(const StepTrainPtrs& sp, double HW, double* ldc, int nee
 void launch_sum_doubles(const double* v, int n, double* out, cudaStream_t s);
 void launch_adamax(float* theta, const float* g, float* m, float* u, long long n, float lr_t, float b1, float b2, float eps,
                    cudaStream_t s);
+void launch_adam(float* theta, const float* g, float* m, float* v, long long n, float lr_t, float b1, float b2, float eps,
+                 cudaStream_t s);
 
 }  // namespace asep

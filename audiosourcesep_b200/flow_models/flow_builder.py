@@ -62,13 +62,20 @@ def build_glow(minibatch, data_shape, L=3, K=32, n_filters=512, learntop=True, l
         raise ValueError("L should be 2, 3 or 4")
     if data_type == "image":
         raise NotImplementedError("ImgPreprocessing (MNIST/CIFAR toy data) is outside the separation hot path")
-    if kwargs.get("use_logit", False):
+    # The reference's SpecPreprocessing defaults to use_logit=True (flow_tfp_bijectors.py:365) and every caller passes
+    # the flag explicitly (train_glow.py:306, run_basis_sep.py:321): a silent default here would change the density.
+    if "use_logit" not in kwargs:
+        raise ValueError("build_glow: pass use_logit explicitly (the reference's default is True; only use_logit=False "
+                         "-- the melspec configs -- is built here)")
+    if kwargs["use_logit"]:
         raise NotImplementedError("use_logit=True is not used by the melspec configs")
     minval, maxval = float(kwargs.get("minval", -100.0)), float(kwargs.get("maxval", 20.0))
     H, W, C = (int(v) for v in data_shape)
     cfg = GlowConfig(H=H, W=W, C=C, L=L, K=K, n_filters=n_filters, learntop=bool(learntop), minval=minval, maxval=maxval)
     if precision is None:
-        precision = _lib.PREC_BF16 if n_filters == 512 else _lib.PREC_FP32
+        # parity first: the three-product tensor-core mode meets every gate of DESIGN.md section 4; one-product bf16
+        # (_lib.PREC_BF16, 3.2x the throughput) is an explicit opt-in.  Other widths: fp32 CUDA cores.
+        precision = _lib.PREC_FP16X3 if n_filters == 512 else _lib.PREC_FP32
     flow = GlowDistribution(cfg, params if params is not None else init_glow_params(cfg, seed=seed, mode="faithful"),
                             precision=precision)
     if minibatch is not None and params is None:

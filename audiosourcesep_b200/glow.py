@@ -144,7 +144,10 @@ class Glow:
     # ---- training (train_glow.py:29-44; Keras Adamax, train_utils.py:29-30)
     def enable_training(self, precision: Optional[int] = None) -> int:
         """Move the trainables into one flat device vector; returns its length.  ``precision``: PREC_FP32 (CUDA-core
-        exact mode) or PREC_BF16 (tcgen05 forward / backward / weight-gradient GEMMs); default: keep the current one."""
+        exact mode) or PREC_BF16 / PREC_FP16 (tcgen05 forward / backward / weight-gradient GEMMs); default: keep the
+        current one, except that the split-precision inference modes (no weight-gradient path) fall back to PREC_BF16."""
+        if precision is None and self.precision in (_lib.PREC_BF16X2, _lib.PREC_FP16X2, _lib.PREC_FP16X3):
+            precision = _lib.PREC_BF16
         if precision is not None and precision != self.precision:
             self.prepare(precision)
         _lib.check(self._lib.asep_glow_enable_training(self._h))
@@ -180,6 +183,25 @@ class Glow:
         dg = _lib.dl(grads)
         _lib.check(self._lib.asep_glow_adamax_step(self._h, dg.ptr, float(lr), float(beta1), float(beta2), float(eps),
                                                    _lib.stream_ptr()))
+
+    def adam_step(self, grads: torch.Tensor, lr: float = 1e-3, beta1: float = 0.9, beta2: float = 0.999,
+                  eps: float = 1e-7) -> None:
+        """Keras Adam (``optimizer: adam``, reference: train_utils.py:27-28)."""
+        grads = _f32c(grads, self.device)
+        dg = _lib.dl(grads)
+        _lib.check(self._lib.asep_glow_adam_step(self._h, dg.ptr, float(lr), float(beta1), float(beta2), float(eps),
+                                                 _lib.stream_ptr()))
+
+    def apply_gradients(self, grads: torch.Tensor, optimizer: dict) -> None:
+        """``optimizer.apply_gradients`` (reference: train_glow.py:42-43) with the dictionary ``setUp_optimizer`` returns."""
+        opt = dict(optimizer)
+        kind = opt.pop("kind", "adamax")
+        if kind == "adamax":
+            self.adamax_step(grads, **opt)
+        elif kind == "adam":
+            self.adam_step(grads, **opt)
+        else:
+            raise ValueError("optimizer argument should be adam or adamax")
 
     def get_flat(self) -> torch.Tensor:
         t = torch.empty((self.num_trainable,), dtype=torch.float32, device=self.device)

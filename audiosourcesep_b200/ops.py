@@ -122,3 +122,27 @@ def basis_ncsn_inner(m1, m2, mixed, x1, x2, sigma_idx: int, T: int, eta: float, 
                                                  int(T), float(eta), float(lam), float(noise_scale), dn1.ptr, dn2.ptr,
                                                  int(seed), int(step0), int(elem_offset), dps.ptr, dnan.ptr,
                                                  _lib.stream_ptr()))
+
+
+def basis_run(m1, m2, mixed, x1, x2, T: int, eta, lam, noise_scale, seed: int = 0, elem_offset: int = 0,
+              snapshots: Optional[torch.Tensor] = None, nan_count: Optional[torch.Tensor] = None) -> None:
+    """The whole sigma x T loop inside the library (reference: run_basis_sep.py:217-260): ``eta / lam / noise_scale`` are
+    length-L sequences of the per-level float32 constants.  ``m1 / m2``: two score networks, two Glow priors, or two
+    length-L lists of Glow priors (one fine-tuned pair per noise level)."""
+    import ctypes
+    L = len(eta)
+    arr = [(ctypes.c_float * L)(*[float(v) for v in seq]) for seq in (eta, lam, noise_scale)]
+    mixed = _prep(mixed)
+    t = [_lib.dl(v) for v in (mixed, x1, x2)]
+    dsn, dnan = _lib.dl(snapshots), _lib.dl(nan_count)
+    first = m1[0] if isinstance(m1, (list, tuple)) else m1
+    if hasattr(first, "cfg") and hasattr(first.cfg, "K"):                 # Glow priors
+        l1 = list(m1) if isinstance(m1, (list, tuple)) else [m1]
+        l2 = list(m2) if isinstance(m2, (list, tuple)) else [m2]
+        h1 = (ctypes.c_void_p * len(l1))(*[m.handle.value for m in l1])
+        h2 = (ctypes.c_void_p * len(l2))(*[m.handle.value for m in l2])
+        _lib.check(_lib.load().asep_basis_glow_run(h1, h2, len(l1), t[0].ptr, t[1].ptr, t[2].ptr, L, int(T), arr[0], arr[1],
+                                                   arr[2], int(seed), int(elem_offset), dsn.ptr, dnan.ptr, _lib.stream_ptr()))
+    else:
+        _lib.check(_lib.load().asep_basis_ncsn_run(m1.handle, m2.handle, t[0].ptr, t[1].ptr, t[2].ptr, L, int(T), arr[0], arr[1],
+                                                   arr[2], int(seed), int(elem_offset), dsn.ptr, dnan.ptr, _lib.stream_ptr()))

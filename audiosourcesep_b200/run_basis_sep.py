@@ -144,6 +144,31 @@ def basis_outer_loop(mixed, x1, x2, model1, model2, optimizer, sigmas, ckpt1, ck
     """reference: run_basis_sep.py:217-260.  ``ckpt1/ckpt2`` are callables ``sigma -> params dict or None``
     that supply the per-noise-level Glow weights (the reference restores a checkpoint per sigma, :228-234)."""
     x_arr = {"x1": [x1.detach().cpu().numpy().copy()], "x2": [x2.detach().cpu().numpy().copy()]}
+    device_loop = (not getattr(args, "host_loop", False) and hasattr(model1, "handle") and hasattr(model2, "handle")
+                   and (args.model_type == "ncsn" or (ckpt1 is None and ckpt2 is None)))
+    if device_loop:
+        # the whole sigma x T loop inside the library (asep_basis_ncsn_run / asep_basis_glow_run): no host round trip
+        # between noise levels, the per-level snapshots are copied on the stream and read once at the end
+        import torch
+        from . import ops
+        L = len(sigmas)
+        consts = [langevin_step_constants(sigmas, i, 2e-5) for i in range(L)]
+        snaps = torch.empty((L, 2) + tuple(x1.shape), dtype=torch.float32, device=x1.device)
+        nan = torch.zeros(1, dtype=torch.int32, device=x1.device) if args.debug else None
+        for sigma_idx, sigma in enumerate(sigmas):
+            print("Sigma = {} ({} / {})".format(sigma, sigma_idx + 1, L))
+        ops.basis_run(model1, model2, mixed, x1, x2, int(args.T), [c[0] for c in consts], [c[1] for c in consts],
+                      [c[2] for c in consts], seed=getattr(args, "seed", 0), elem_offset=getattr(args, "elem_offset", 0),
+                      snapshots=snaps, nan_count=nan)
+        if args.debug and int(nan.item()) != 0:
+            raise FloatingPointError("NaN in the Langevin state")
+        host = snaps.cpu().numpy()
+        for i in range(L):
+            x_arr["x1"].append(host[i, 0].copy())
+            x_arr["x2"].append(host[i, 1].copy())
+        print("inner loop done")
+        print("_" * 100)
+        return x1, x2, x_arr
     for sigma_idx, sigma in enumerate(sigmas):
         print("Sigma = {} ({} / {})".format(sigma, sigma_idx + 1, len(sigmas)))
         if args.model_type == "glow":
@@ -199,6 +224,27 @@ def _npz_loader(root: str) -> Callable[[float], Optional[Dict[str, np.ndarray]]]
     return load
 
 
+def glow_precision(args) -> int:
+    """Arithmetic of the Glow priors.  Default: the tensor-core parity mode ASEP_PREC_FP16X3 (three split-precision
+    products per GEMM: log_prob, round trip, score and per-step Langevin gates of DESIGN.md section 4); ``--fast``: one
+    bf16 product (3.2x the throughput; score within ~5e-2, per-step gate met on the annealed half of the schedule);
+    ``--precision`` names any mode; ``--exact`` keeps its round-1 meaning (fp32 CUDA cores).  Widths other than 512
+    filters have no tensor-core kernel and run on the fp32 CUDA-core path."""
+    from . import _lib
+    table = {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16, "fp16": _lib.PREC_FP16, "bf16x2": _lib.PREC_BF16X2,
+             "fp16x2": _lib.PREC_FP16X2, "fp16x3": _lib.PREC_FP16X3}
+    if int(args.n_filters) != 512:
+        return _lib.PREC_FP32
+    name = getattr(args, "precision", None)
+    if name:
+        if name not in table:
+            raise ValueError(f"--precision should be one of {sorted(table)}")
+        return table[name]
+    if getattr(args, "exact", False):
+        return _lib.PREC_FP32
+    return _lib.PREC_BF16 if getattr(args, "fast", False) else _lib.PREC_FP16X3
+
+
 def build_models(args, sigmas, device_index: int):
     """Two priors (reference: run_basis_sep.py:386-397) and their per-sigma weight suppliers."""
     from . import _lib
@@ -217,8 +263,7 @@ def build_models(args, sigmas, device_index: int):
                 params = ckpts[-1](float(sigmas[0]))
             models.append(build_glow(None, [args.height, args.width, 1], L=args.L, K=args.K, n_filters=args.n_filters,
                                      learntop=args.learntop, l2_reg=args.l2_reg, data_type="melspec", minval=0.0,
-                                     maxval=1.0, params=params,
-                                     precision=_lib.PREC_FP32 if getattr(args, "exact", False) else None))
+                                     maxval=1.0, use_logit=False, params=params, precision=glow_precision(args)))
         return models[0], models[1], ckpts[0], ckpts[1]
     from .ncsn.utils import get_uncompiled_model, get_uncompiled_model_v2
     builders = []
@@ -273,9 +318,15 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--synthetic", action="store_true", help="separate seeded synthetic mel patches")
     p.add_argument("--random_init", type=int, default=None, metavar="SEED", help="seeded random-init weights")
     p.add_argument("--seed", type=int, default=0, help="Philox seed of the Langevin noise and of x1/x2 init")
+    p.add_argument("--fast", action="store_true",
+                   help="throughput mode: one bf16 tensor-core product per GEMM / convolution (default: the parity modes, "
+                        "three split-precision products: Glow ASEP_PREC_FP16X3, score networks ASEP_PREC_BF16X3)")
+    p.add_argument("--precision", type=str, default=None,
+                   help="Glow priors: fp32 | bf16 | fp16 | bf16x2 | fp16x2 | fp16x3 (overrides --fast / --exact)")
     p.add_argument("--exact", action="store_true",
-                   help="parity mode: NCSN convolutions as three split-bf16 tensor-core products (~3x the conv time), "
-                        "Glow priors on the fp32 CUDA-core kernels")
+                   help="Glow priors on the fp32 CUDA-core kernels (the on-device checker); score networks: the parity mode")
+    p.add_argument("--host_loop", action="store_true",
+                   help="run the sigma loop on the host (one library call per noise level) instead of asep_basis_*_run")
     return p
 
 
@@ -285,7 +336,7 @@ def merge_config(args: argparse.Namespace) -> argparse.Namespace:
         return args
     cfg = vars(get_config(args.config))
     keep = ("dataset", "debug", "output", "song_dir", "inverse", "model_type", "n_mixed", "RESTORE1", "RESTORE2",
-            "synthetic", "random_init", "seed", "config")
+            "synthetic", "random_init", "seed", "config", "fast", "precision", "exact", "host_loop")
     merged = dict(vars(args))
     for k, v in cfg.items():
         if k not in keep:

@@ -20,15 +20,18 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
+from . import _lib
 from .config import get_config
 from .ncsn.utils import get_sigmas
 
 
 def setUp_optimizer(mirrored_strategy, args):
-    """reference: train_utils.py:23-41 -- returns the Adamax hyper-parameters the library applies."""
-    if getattr(args, "optimizer", "adamax") != "adamax":
-        raise NotImplementedError("the Glow configs train with Adamax (configs/melspec_glow.yml:14)")
-    return dict(lr=float(args.learning_rate), beta1=0.9, beta2=0.999, eps=1e-7)
+    """reference: train_utils.py:23-41 -- the Keras Adam / Adamax hyper-parameters (defaults beta1 0.9, beta2 0.999,
+    epsilon 1e-7) as the dictionary ``Glow.apply_gradients`` takes; the update itself runs in libasep.so."""
+    kind = getattr(args, "optimizer", "adamax")
+    if kind not in ("adam", "adamax"):
+        raise ValueError("optimizer argument should be adam or adamax")            # train_utils.py:31-32
+    return dict(kind=kind, lr=float(args.learning_rate), beta1=0.9, beta2=0.999, eps=1e-7)
 
 
 def distributed_train_step(flow, optimizer: dict, batch: torch.Tensor, global_batch: int,
@@ -39,7 +42,10 @@ def distributed_train_step(flow, optimizer: dict, batch: torch.Tensor, global_ba
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(grads, op=dist.ReduceOp.SUM)        # NCCL over NVLink: the implicit all-reduce of apply_gradients
         dist.all_reduce(loss, op=dist.ReduceOp.SUM)         # strategy.reduce(SUM, per_replica_losses)
-    flow.adamax_step(grads, **optimizer)
+    if hasattr(flow, "apply_gradients"):
+        flow.apply_gradients(grads, optimizer)
+    else:                                                    # duck-typed handles (tests) with the Adamax-only surface
+        flow.adamax_step(grads, **{k: v for k, v in optimizer.items() if k != "kind"})
     return loss
 
 
@@ -56,9 +62,11 @@ def synthetic_dataset(n: int, seed: int, H: int, W: int) -> np.ndarray:
     return synthetic.mel_patches_db(n, seed, H, W)
 
 
-def train(flow, optimizer, data: np.ndarray, args, sigma: float = 0.0, log=print):
+def train(flow, optimizer, data: np.ndarray, args, sigma: float = 0.0, log=print, step_offset: int = 0):
     """Epoch loop over a host dataset (reference: train_glow.py:88-181 without the TensorBoard / sample-grid side
-    outputs); stops on a NaN / Inf loss like train_glow.py:115-118."""
+    outputs); stops on a NaN / Inf loss like train_glow.py:115-118.  ``step_offset``: global step of the first
+    iteration -- the noise of train_noisy_glow is keyed by (seed, global step, global sample), so successive calls
+    (one per noise level) must continue the count instead of redrawing the same sequence."""
     world = dist.get_world_size() if dist.is_initialized() else 1
     rank = dist.get_rank() if dist.is_initialized() else 0
     gb = int(args.batch_size)
@@ -66,7 +74,9 @@ def train(flow, optimizer, data: np.ndarray, args, sigma: float = 0.0, log=print
         raise ValueError("batch_size must be divisible by the number of replicas")
     local = gb // world
     steps_per_epoch = data.shape[0] // gb
-    step, t0, history = 0, time.time(), []
+    if steps_per_epoch == 0:
+        raise ValueError(f"the dataset holds {data.shape[0]} patches, fewer than one global batch of {gb}")
+    step, t0, history = int(step_offset), time.time(), []
     for epoch in range(int(args.n_epochs)):
         perm = np.random.default_rng(1000 + epoch).permutation(data.shape[0])
         for it in range(steps_per_epoch):
@@ -125,7 +135,7 @@ def main(args):
     minibatch = data[: int(args.batch_size)]                     # data-dependent ActNorm init batch (train_glow.py:300-306)
     flow = build_glow(minibatch, [args.height, args.width, 1], L=args.L, K=args.K, n_filters=args.n_filters,
                       learntop=args.learntop, l2_reg=None, data_type="melspec", minval=-100.0, maxval=20.0,
-                      seed=int(args.seed))
+                      use_logit=False, seed=int(args.seed), precision=_lib.PREC_BF16 if int(args.n_filters) == 512 else None)
     flow.enable_training()
     optimizer = setUp_optimizer(None, args)
     log = print if rank == 0 else (lambda *a, **k: None)
@@ -141,7 +151,7 @@ def main(args):
     for sigma in sigmas:                                         # serial over noise levels, warm start (train_noisy_glow.py:309-358)
         log("Training at noise level sigma = {}".format(sigma))
         # noise is added in RAW data units (dB), train_noisy_glow.py:31-32
-        hist += train(flow, optimizer, data, args, sigma=float(sigma), log=log)
+        hist += train(flow, optimizer, data, args, sigma=float(sigma), log=log, step_offset=len(hist))
         if rank == 0:
             flow.sync_host()
             d = os.path.join(args.output, "sigma_" + str(round(float(sigma), 2)))

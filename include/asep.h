@@ -122,6 +122,10 @@ int asep_glow_train_grads(asep_glow_t h, const DLTensor* x, const DLTensor* nois
  * then every derived per-step constant is refreshed on the device. */
 int asep_glow_adamax_step(asep_glow_t h, const DLTensor* grads, float lr, float beta1, float beta2, float eps,
                           void* stream);
+/* theta <- Adam(theta, grads), the Keras update of `optimizer: adam` (train_utils.py:27-28): m = b1 m + (1-b1) g;
+ * v = b2 v + (1-b2) g^2; theta -= lr sqrt(1-b2^t)/(1-b1^t) m / (sqrt(v) + eps).  One optimizer per handle. */
+int asep_glow_adam_step(asep_glow_t h, const DLTensor* grads, float lr, float beta1, float beta2, float eps,
+                        void* stream);
 /* Flat trainable vector out / in (device float32 [num_trainable]); set_flat refreshes the derived constants. */
 int asep_glow_get_flat(asep_glow_t h, DLTensor* theta, void* stream);
 int asep_glow_set_flat(asep_glow_t h, const DLTensor* theta, void* stream);
@@ -204,9 +208,30 @@ int asep_basis_ncsn_inner(asep_ncsn_t m1, asep_ncsn_t m2, const DLTensor* mixed,
                           int sigma_idx, int T, float eta, float lambda, float noise_scale, const DLTensor* noise1,
                           const DLTensor* noise2, uint64_t seed, uint64_t step0, uint64_t elem_offset,
                           DLTensor* per_step, DLTensor* nan_count, void* stream);
+/* basis_outer_loop + basis_inner_loop (run_basis_sep.py:217-260, :152-181) entirely inside the library: L noise levels x T
+ * Langevin steps with in-kernel Philox noise (step number = level * T + t, as the Python host numbers them), no host
+ * synchronisation between levels.  eta / lambda / noise_scale: HOST arrays [L] of the float32 constants of :158-164.
+ * snapshots: NULL or device [L, 2, N, H, W, C], the raw states after every level (x_arr, :243-244), copied on the
+ * stream.  Glow: m1 / m2 are arrays of n_models handles, n_models = L (the per-sigma fine-tuned priors the reference
+ * restores at :228-234, all resident) or 1 (one pair for every level). */
+int asep_basis_glow_run(const asep_glow_t* m1, const asep_glow_t* m2, int n_models, const DLTensor* mixed, DLTensor* x1,
+                        DLTensor* x2, int L, int T, const float* eta, const float* lambda, const float* noise_scale,
+                        uint64_t seed, uint64_t elem_offset, DLTensor* snapshots, DLTensor* nan_count, void* stream);
+int asep_basis_ncsn_run(asep_ncsn_t m1, asep_ncsn_t m2, const DLTensor* mixed, DLTensor* x1, DLTensor* x2, int L, int T,
+                        const float* eta, const float* lambda, const float* noise_scale, uint64_t seed, uint64_t elem_offset,
+                        DLTensor* snapshots, DLTensor* nan_count, void* stream);
 /* Event timing of the tcgen05 convolution launches of the score networks (same contract as asep_tc_profile). */
 int asep_conv_profile(int on);
 int asep_conv_profile_read(double* total_ms, int64_t* launches, double* flops);
+
+/* Measurement aid for the HBM-bound kernels (bench.py `roofline_hbm`): while on, every launch of a profiled category is
+ * bracketed by a CUDA event pair on its own stream.  Categories: 0 fused flow step (ActNorm + 1x1 + coupling + log-det,
+ * flow_tfp_bijectors.py:134-153,242-253,299-322), 1 fused Langevin update (run_basis_sep.py:163-181), 2 score-network
+ * normalise + ELU + cast (score_network.py:203-221), 3 score-network pooling / resize (score_network.py:18,74,142),
+ * 4 stand-alone col2im gather.  _read synchronises the events and returns the summed kernel time, the launch count and
+ * the ALGORITHMIC bytes (what the op must read and write once) of the recorded launches. */
+int asep_hbm_profile(int on);
+int asep_hbm_profile_read(int category, double* total_ms, int64_t* launches, double* bytes);
 
 /* Measurement aid (bench.py roofline leg): while on, every launch of the tcgen05 coupling kernel is bracketed
  * by a CUDA event pair on its own stream.  _read synchronises those events and returns the summed kernel time,

@@ -55,3 +55,14 @@ def adamax_update(theta, g, m, u, t, lr=1e-3, b1=0.9, b2=0.999, eps=1e-7):
     lr_t = np.float32(lr / (1.0 - b1 ** t))
     theta = (theta - lr_t * m / (u + np.float32(eps))).astype(np.float32)
     return theta, m, u
+
+
+def adam_update(theta, g, m, v, t, lr=1e-3, b1=0.9, b2=0.999, eps=1e-7):
+    """One Keras Adam step (OptimizerV2, non-amsgrad; train_utils.py:27-28) in float32; returns (theta, m, v)."""
+    theta, g, m, v = (np.asarray(a, np.float32) for a in (theta, g, m, v))
+    m = (np.float32(b1) * m + np.float32(1.0 - b1) * g).astype(np.float32)
+    v = (np.float32(b2) * v + np.float32(1.0 - b2) * g * g).astype(np.float32)
+    lr_t = np.float32(lr * np.sqrt(1.0 - b2 ** t) / (1.0 - b1 ** t))
+    theta = (theta - lr_t * m / (np.sqrt(v) + np.float32(eps))).astype(np.float32)
+    return theta, m, v
+

@@ -135,3 +135,58 @@ def test_basis_glow_inner_loop_vs_oracle(precision, weights, sigma_idx):
     if not (weights == "faithful" and sigma_idx == 0):   # eta = 0.2 on an untrained linear-Gaussian score is an unstable iteration
         assert drift <= 5e-3
     assert torch.equal(dump[T - 1, 0], t1) and torch.equal(dump[T - 1, 1], t2)
+
+
+def test_same_prior_for_both_sources_keeps_two_score_tensors():
+    """model1 and model2 are just callables in the reference (run_basis_sep.py:166-175): passing ONE handle for both
+    sources must give the same result as two handles holding the same weights."""
+    from audiosourcesep_b200 import ops, _lib
+    from audiosourcesep_b200.glow import Glow
+    cfg = GlowConfig(H=96, W=64, C=1, L=3, K=2, n_filters=512, minval=0.0, maxval=1.0)
+    p = init_glow_params(cfg, seed=2, mode="perturbed")
+    ma, mb = Glow(cfg, p, precision=_lib.PREC_BF16), Glow(cfg, p, precision=_lib.PREC_BF16)
+    mixed, _, _ = synthetic.basis_problem(3)
+    x1, x2 = synthetic.langevin_init(3, seed=4)
+    sig = bo.get_sigmas(1.0, 0.01, 10, "logarithmic")
+    eta, lam, ns = bo.step_constants(sig, 8)
+    outs = []
+    for m1, m2 in ((ma, mb), (ma, ma)):
+        t1, t2 = torch.as_tensor(x1).cuda(), torch.as_tensor(x2).cuda()
+        ops.basis_glow_inner(m1, m2, torch.as_tensor(mixed), t1, t2, 2, float(eta), float(lam), float(ns), seed=3)
+        outs.append((t1.clone(), t2.clone()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    assert not torch.equal(outs[1][0], torch.as_tensor(x1).cuda())
+
+
+def test_device_sigma_loop_equals_the_host_loop():
+    """asep_basis_glow_run (the whole sigma x T loop inside the library, run_basis_sep.py:217-260) gives bit-identical
+    states and per-level snapshots to one asep_basis_glow_inner call per noise level."""
+    from audiosourcesep_b200 import ops, _lib
+    from audiosourcesep_b200.glow import Glow
+    cfg = GlowConfig(H=96, W=64, C=1, L=3, K=2, n_filters=512, minval=0.0, maxval=1.0)
+    m1 = Glow(cfg, init_glow_params(cfg, seed=2, mode="perturbed"), precision=_lib.PREC_BF16)
+    m2 = Glow(cfg, init_glow_params(cfg, seed=3, mode="perturbed"), precision=_lib.PREC_BF16)
+    mixed, _, _ = synthetic.basis_problem(3)
+    x1, x2 = synthetic.langevin_init(3, seed=4)
+    sig = bo.get_sigmas(0.05, 0.01, 4, "logarithmic")
+    T = 2
+    consts = [bo.step_constants(sig, i) for i in range(len(sig))]
+    a1, a2 = torch.as_tensor(x1).cuda(), torch.as_tensor(x2).cuda()
+    host_snaps = []
+    for i, (eta, lam, ns) in enumerate(consts):
+        ops.basis_glow_inner(m1, m2, torch.as_tensor(mixed), a1, a2, T, float(eta), float(lam), float(ns), seed=9, step0=i * T)
+        host_snaps.append((a1.clone(), a2.clone()))
+    b1, b2 = torch.as_tensor(x1).cuda(), torch.as_tensor(x2).cuda()
+    snaps = torch.empty((len(sig), 2) + tuple(b1.shape), device="cuda")
+    nan = torch.zeros(1, dtype=torch.int32, device="cuda")
+    ops.basis_run(m1, m2, torch.as_tensor(mixed), b1, b2, T, [c[0] for c in consts], [c[1] for c in consts],
+                  [c[2] for c in consts], seed=9, snapshots=snaps, nan_count=nan)
+    assert torch.equal(a1, b1) and torch.equal(a2, b2) and nan.item() == 0
+    for i, (s1, s2) in enumerate(host_snaps):
+        assert torch.equal(snaps[i, 0], s1) and torch.equal(snaps[i, 1], s2)
+    # one pair of priors per noise level (the per-sigma fine-tuned models of run_basis_sep.py:228-234), all resident
+    c1, c2 = torch.as_tensor(x1).cuda(), torch.as_tensor(x2).cuda()
+    ops.basis_run([m1] * len(sig), [m2] * len(sig), torch.as_tensor(mixed), c1, c2, T, [c[0] for c in consts],
+                  [c[1] for c in consts], [c[2] for c in consts], seed=9)
+    assert torch.equal(c1, a1) and torch.equal(c2, a2)
+

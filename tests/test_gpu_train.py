@@ -106,7 +106,7 @@ def test_train_loop_host_mirror_reduces_loss_on_synthetic_patches():
     from audiosourcesep_b200.flow_models.flow_builder import build_glow
     data = tg.synthetic_dataset(24, 0, 32, 16)
     flow = build_glow(data[:8], [32, 16, 1], L=3, K=2, n_filters=64, learntop=True, data_type="melspec",
-                      minval=-100.0, maxval=20.0, seed=1)
+                      minval=-100.0, maxval=20.0, use_logit=False, seed=1)
     flow.enable_training()
     args = argparse.Namespace(batch_size=8, n_epochs=2, learning_rate=1e-3, optimizer="adamax", seed=0)
     hist = tg.train(flow, tg.setUp_optimizer(None, args), data, args, log=lambda *a: None)
@@ -193,3 +193,100 @@ def test_graph_replay_of_the_gradient_pass_equals_the_eager_pass(monkeypatch):
     g, loss = m.train_grads(xs[0], global_batch=4, noise=noise, sigma=0.05)   # different key -> new capture
     assert float(loss.item()) == pytest.approx(float(want_noisy[1].item()), rel=1e-6)
     assert torch.allclose(g, want_noisy[0], rtol=1e-4, atol=1e-6 * float(want_noisy[0].abs().max()))
+
+
+def test_adam_step_matches_keras_update():
+    """``optimizer: adam`` (train_utils.py:27-28): the library update equals the Keras formula on the same gradient."""
+    cfg = GlowConfig(H=16, W=8, C=1, L=3, K=1, n_filters=64, minval=0.0, maxval=1.0)
+    p = init_glow_params(cfg, seed=6, mode="perturbed")
+    x = torch.as_tensor(np.random.default_rng(2).uniform(0, 1, (2, 16, 8, 1)).astype(np.float32))
+    m = _model(cfg, p)
+    theta = m.get_flat().cpu().numpy()
+    mm, vv = np.zeros_like(theta), np.zeros_like(theta)
+    for t in (1, 2, 3):
+        g, _ = m.train_grads(x, global_batch=2)
+        m.apply_gradients(g, dict(kind="adam", lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-7))
+        theta, mm, vv = to.adam_update(theta, g.cpu().numpy(), mm, vv, t)
+        np.testing.assert_allclose(m.get_flat().cpu().numpy(), theta, rtol=1e-5, atol=2e-7)
+
+
+def test_training_without_learnable_prior():
+    """learntop=False (flow_builder.py:143-144): no prior parameters in the flat vector; gradients match the oracle."""
+    cfg = GlowConfig(H=16, W=8, C=1, L=3, K=1, n_filters=64, learntop=False, minval=0.0, maxval=1.0)
+    p = init_glow_params(cfg, seed=9, mode="perturbed")
+    x = np.random.default_rng(5).uniform(0, 1, (3, 16, 8, 1)).astype(np.float32)
+    m = _model(cfg, p)
+    assert not any(n.startswith("prior/") for n, _, _ in m.trainable_layout())
+    g, loss = m.train_grads(torch.as_tensor(x), global_batch=3)
+    loss_o, g_o = to.loss_and_grads(cfg, p, x, 3)
+    assert abs(float(loss.item()) - loss_o) <= 1e-5 * abs(loss_o)
+    got = _split(m, g)
+    for name, want in g_o.items():
+        want = to.mask_structural(name, want)
+        rel = np.linalg.norm(got[name] - want) / max(np.linalg.norm(want), 1e-6 * np.sqrt(want.size))
+        assert rel <= 2e-3, (name, rel)
+
+
+def test_log_prob_between_optimizer_steps_uses_the_live_log_det_constant():
+    """The reference evaluates flow.log_prob on validation data every epoch (train_glow.py:150-170) without any
+    'sync' call: after an optimizer step the ActNorm / 1x1 log-det constant must be the updated one."""
+    from audiosourcesep_b200 import _lib
+    from audiosourcesep_b200.glow import Glow
+    cfg = GlowConfig(H=32, W=16, C=1, L=3, K=2, n_filters=512, minval=0.0, maxval=1.0)
+    p = init_glow_params(cfg, seed=6, mode="perturbed")
+    x = torch.as_tensor(np.random.default_rng(2).uniform(0, 1, (4, 32, 16, 1)).astype(np.float32))
+    for prec in (_lib.PREC_BF16, _lib.PREC_FP32):
+        m = Glow(cfg, p, precision=prec)
+        m.enable_training()
+        lp0 = float(m.log_prob(x).sum().item())
+        for _ in range(2):
+            g, _ = m.train_grads(x, global_batch=4)
+            m.adamax_step(g, lr=1e-3)
+        lp_live = m.log_prob(x).cpu().numpy()                # no sync_host() in between
+        fldj_live = m.forward_log_det_jacobian(x).cpu().numpy()
+        # the training loss of the same batch uses the device-resident constants: -loss * global_batch = sum log_prob
+        lp_train = -4.0 * float(m.train_grads(x, global_batch=4)[1].item())
+        assert abs(float(lp_live.sum()) - lp_train) <= 2e-6 * abs(lp_train), (float(lp_live.sum()), lp_train)
+        assert abs(lp_train - lp0) > 1e-3 * abs(lp0)         # the two steps did move the density
+        m.sync_host()                                        # host re-derivation in double: agrees to fp32 round-off
+        np.testing.assert_allclose(lp_live, m.log_prob(x).cpu().numpy(), rtol=2e-4)
+        np.testing.assert_allclose(fldj_live, m.forward_log_det_jacobian(x).cpu().numpy(), rtol=2e-4)
+
+
+def test_train_graph_survives_workspace_and_weight_reallocation():
+    """train -> log_prob with a LARGER batch (re-carves the arena) -> sync_host (re-allocates the per-step constants
+    and tile images) -> train again with the same graph key: the captured graph must not be replayed on the freed
+    buffers (reference loop: per-epoch validation, sampling and checkpointing between train steps, train_glow.py:106-179)."""
+    from audiosourcesep_b200 import _lib
+    from audiosourcesep_b200.glow import Glow
+    cfg = GlowConfig(H=32, W=16, C=1, L=3, K=2, n_filters=512, minval=0.0, maxval=1.0)
+    p = init_glow_params(cfg, seed=8, mode="perturbed")
+    rng = np.random.default_rng(3)
+    x = torch.as_tensor(rng.uniform(0, 1, (4, 32, 16, 1)).astype(np.float32)).cuda()
+    big = torch.as_tensor(rng.uniform(0, 1, (37, 32, 16, 1)).astype(np.float32)).cuda()
+    m = Glow(cfg, p, precision=_lib.PREC_BF16)
+    m.enable_training()
+    g0, l0 = (t.clone() for t in m.train_grads(x, global_batch=4))      # eager
+    g1, l1 = (t.clone() for t in m.train_grads(x, global_batch=4))      # capture + launch
+    g2, l2 = (t.clone() for t in m.train_grads(x, global_batch=4))      # replay
+    assert torch.allclose(g1, g0, rtol=1e-4, atol=1e-6 * float(g0.abs().max()))
+    assert torch.allclose(g2, g0, rtol=1e-4, atol=1e-6 * float(g0.abs().max()))
+    lp_big = m.log_prob(big)                                            # larger N: arena re-carved
+    assert torch.isfinite(lp_big).all()
+    g3, l3 = (t.clone() for t in m.train_grads(x, global_batch=4))
+    assert torch.allclose(g3, g0, rtol=1e-4, atol=1e-6 * float(g0.abs().max())), float((g3 - g0).abs().max())
+    m.train_grads(x, global_batch=4)                                    # re-captured
+    m.sync_host()                                                       # constants and tile images re-allocated
+    _ = m.sample(5)                                                     # inverse pass in between, another workspace shape
+    # (sync_host re-derives the folded weights on the host in double, enable_training derived them on the device in
+    #  fp32: a few bf16 tile-image entries differ in their last bit, hence the looser bound than for a pure replay)
+    g_prev = None
+    for _ in range(3):
+        g4, l4 = m.train_grads(x, global_batch=4)
+        assert float(l4.item()) == pytest.approx(float(l0.item()), rel=1e-5)
+        rel = float(torch.linalg.norm(g4 - g0) / torch.linalg.norm(g0))
+        assert rel <= 2e-3, rel
+        if g_prev is not None:                                          # eager, capture and replay agree with each other
+            assert torch.allclose(g4, g_prev, rtol=1e-4, atol=1e-6 * float(g0.abs().max()))
+        g_prev = g4.clone()
+

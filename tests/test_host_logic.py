@@ -27,12 +27,65 @@ def test_reference_module_paths_import():
     for name in ("compute_grad_logprob", "mixing_process", "basis_inner_loop", "basis_outer_loop", "main", "post_processing_fn"):
         assert callable(getattr(rbs, name))
     assert fm is not None
+    # the remaining module paths the reference's scripts import
+    from audiosourcesep_b200.flow_models import flow_tfk_layers
+    assert flow_tfk_layers.ShiftAndLogScaleConvNet is flow_glow.ShiftAndLogScaleConvNet      # flow_tfk_layers.py:31
+    from audiosourcesep_b200 import train_noisy_glow, train_utils
+    for name in ("setUp_optimizer", "setUp_checkpoint", "get_config", "dict2namespace"):     # train_utils.py:23,62,114,123
+        assert callable(getattr(train_utils, name))
+    assert callable(train_noisy_glow.main) and train_noisy_glow.build_parser().parse_args([]).noisy is True
 
 
 def test_build_glow_argument_errors():
     from audiosourcesep_b200.flow_models.flow_builder import build_glow
     with pytest.raises(ValueError, match="L should be 2, 3 or 4"):          # flow_builder.py:77-78
         build_glow(None, [96, 64, 1], L=5)
+    # the reference's SpecPreprocessing defaults to use_logit=True: no silent default here
+    with pytest.raises(ValueError, match="use_logit"):
+        build_glow(None, [96, 64, 1], L=3, data_type="melspec")
+    with pytest.raises(NotImplementedError):
+        build_glow(None, [96, 64, 1], L=3, data_type="melspec", use_logit=True)
+
+
+def test_set_up_optimizer_offers_adam_and_adamax():
+    from audiosourcesep_b200.train_utils import setUp_optimizer
+    for kind in ("adam", "adamax"):                                           # train_utils.py:26-32
+        opt = setUp_optimizer(None, argparse.Namespace(optimizer=kind, learning_rate=2e-3))
+        assert opt == dict(kind=kind, lr=2e-3, beta1=0.9, beta2=0.999, eps=1e-7)
+    with pytest.raises(ValueError, match="adam or adamax"):
+        setUp_optimizer(None, argparse.Namespace(optimizer="sgd", learning_rate=1e-3))
+
+
+def test_train_rejects_dataset_smaller_than_a_batch():
+    from audiosourcesep_b200.train_glow import train
+    args = argparse.Namespace(batch_size=8, n_epochs=1, learning_rate=1e-3, optimizer="adamax", seed=0)
+    with pytest.raises(ValueError, match="fewer than one global batch"):
+        train(object(), {}, np.zeros((4, 8, 8, 1), np.float32), args)
+
+
+def test_checkpoint_manager_keeps_max_to_keep(tmp_path):
+    from audiosourcesep_b200.train_utils import setUp_checkpoint
+
+    class FakeModel:
+        def __init__(self):
+            self.variables = {"w": np.arange(3, dtype=np.float32)}
+            self.restored = None
+
+        def set_params(self, p):
+            self.restored = p
+
+        def prepare(self):
+            pass
+
+    m = FakeModel()
+    ckpt, manager = setUp_checkpoint(None, m, None, max_to_keep=2, path=str(tmp_path / "tf_ckpts"))
+    assert manager.latest_checkpoint is None and manager.restore() is None
+    for i in range(4):
+        m.variables = {"w": np.full(3, i, np.float32)}
+        manager.save()
+    files = sorted(os.listdir(tmp_path / "tf_ckpts"))
+    assert files == ["ckpt-3.npz", "ckpt-4.npz"]
+    assert manager.restore().endswith("ckpt-4.npz") and np.array_equal(m.restored["w"], np.full(3, 3, np.float32))
 
 
 @pytest.mark.parametrize("yml,expect", [
