@@ -138,6 +138,7 @@ GlowModel::~GlowModel() {
   for (auto& kv : params_)
     if (kv.second.dev && !kv.second.in_flat) cudaFree(kv.second.dev);
   if (score_buf_) cudaFree(score_buf_);
+  if (refresh_table_) cudaFree(refresh_table_);
   if (tgraph_.exec) cudaGraphExecDestroy(tgraph_.exec);
   if (tg_stream_) cudaStreamDestroy(tg_stream_);
   if (tg_ev_in_) cudaEventDestroy(tg_ev_in_);
@@ -249,6 +250,7 @@ void GlowModel::prepare(int precision) {
     ASEP_CHECK(F == kTcF, ASEP_ERR_UNSUPPORTED, "the tcgen05 modes need n_filters = %d (got %d)", kTcF, F);
   CUDA_CHECK(cudaSetDevice(device_));
   invalidate_graphs();                       // the per-step constants and tile images below are re-allocated
+  refresh_dirty_ = true;                     // ... and so are the pointers in the device-side refresh table
   for (int b = 0; b < cfg_.L; ++b) {
     const int C = levels_[b].C;
     for (int k = 0; k < cfg_.K; ++k) {

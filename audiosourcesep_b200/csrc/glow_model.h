@@ -118,6 +118,8 @@ class GlowModel {
   void latent_slice(int b, int& Cz, int& nb, int& coff) const;
 
   void derive_on_device(cudaStream_t s);
+  StepRefresh* refresh_table_ = nullptr;     // device rows of the batched refresh (glow_train.cu)
+  bool refresh_dirty_ = true;
   StepTrainPtrs step_ptrs(int b, int k);
   std::vector<std::string> order_;          // parameter names in construction order
   float *theta_ = nullptr, *adam_m_ = nullptr, *adam_u_ = nullptr;

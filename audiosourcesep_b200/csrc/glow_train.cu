@@ -87,18 +87,35 @@ StepTrainPtrs GlowModel::step_ptrs(int b, int k) {
   return sp;
 }
 
+// Refresh of every derived constant after a parameter update: ONE launch per kernel for all L*K flow steps (the rows of
+// the device-side table carry each step's pointers), instead of three launches per step.
 void GlowModel::derive_on_device(cudaStream_t s) {
-  for (int b = 0; b < cfg_.L; ++b)
-    for (int k = 0; k < cfg_.K; ++k) {
-      const StepTrainPtrs sp = step_ptrs(b, k);
-      launch_derive_step(sp, (double)levels_[b].H * levels_[b].W, ldc_ + (size_t)b * cfg_.K + k, precision_ == ASEP_PREC_FP32 ? 1 : 0, s);
-      if (is_tc()) {                                   // tcgen05 operands: tile images + folded biases
-        NNWeightsTC& w = step(b, k).wtc;
-        launch_build_tc_step(sp, w.fwd.img, w.bwd.img, w.fwd.k1_panels, w.fwd.n3p, w.bwd.k1_panels, w.bwd.n3p, w.bias1,
-                             w.bias2, w.const3, w.c3, w.f16, s);
+  const int n_steps = (int)steps_.size();
+  if (refresh_dirty_) {                                  // pointers changed (prepare / enable_training): rebuild the table
+    std::vector<StepRefresh> rows((size_t)n_steps);
+    for (int b = 0; b < cfg_.L; ++b)
+      for (int k = 0; k < cfg_.K; ++k) {
+        StepRefresh& r = rows[(size_t)b * cfg_.K + k];
+        r = StepRefresh{};
+        r.sp = step_ptrs(b, k);
+        ASEP_CHECK(r.sp.C * r.sp.C <= 256, ASEP_ERR_UNSUPPORTED, "derive: C > 16");
+        r.HW = (double)levels_[b].H * levels_[b].W;
+        if (is_tc()) {
+          const NNWeightsTC& w = step(b, k).wtc;
+          r.fwd_img = w.fwd.img; r.bwd_img = w.bwd.img;
+          r.k1p_f = w.fwd.k1_panels; r.n3p_f = w.fwd.n3p; r.k1p_b = w.bwd.k1_panels; r.n3p_b = w.bwd.n3p;
+          r.bias1 = w.bias1; r.bias2 = w.bias2; r.const3 = w.const3; r.c3 = w.c3;
+          r.f16 = w.f16 ? 1 : 0;
+        }
       }
-    }
-  launch_sum_doubles(ldc_, (int)steps_.size(), ld_total_, s);
+    if (!refresh_table_) CUDA_CHECK(cudaMalloc(&refresh_table_, rows.size() * sizeof(StepRefresh)));
+    CUDA_CHECK(cudaStreamSynchronize(s));                // an earlier refresh may still read the old rows
+    CUDA_CHECK(cudaMemcpy(refresh_table_, rows.data(), rows.size() * sizeof(StepRefresh), cudaMemcpyHostToDevice));
+    refresh_dirty_ = false;
+  }
+  launch_derive_all(refresh_table_, n_steps, ldc_, precision_ == ASEP_PREC_FP32 ? 1 : 0, s);
+  if (is_tc()) launch_build_tc_all(refresh_table_, n_steps, s);      // tcgen05 operands: tile images + folded biases
+  launch_sum_doubles(ldc_, n_steps, ld_total_, s);
 }
 
 void GlowModel::ensure_train_dumps(long long rows) {

@@ -335,7 +335,10 @@ __global__ void k_loss(const double* __restrict__ acc_ld, const double* __restri
 }
 
 // ------------------------------------------------------------------ derived constants of one step, on the device
-__global__ void __launch_bounds__(512) k_derive_step(const StepTrainPtrs sp, double HW, double* __restrict__ ldc, int need_k2t) {
+__global__ void __launch_bounds__(512) k_derive_step(const StepRefresh* __restrict__ table, double* __restrict__ ldc_all, int need_k2t) {
+  const StepTrainPtrs sp = table[blockIdx.x].sp;                   // one block per flow step
+  const double HW = table[blockIdx.x].HW;
+  double* ldc = ldc_all + blockIdx.x;
   const int C = sp.C, F = sp.F, t = threadIdx.x;
   __shared__ double sP[256], sL[256], sU[256], sA[256], sLi[256], sUi[256];
   if (t < C * C) {
@@ -542,9 +545,12 @@ __global__ void __launch_bounds__(512) k_colsum_bf16(const __nv_bfloat16* __rest
 // (device twin of nn_tc_prepare in nn_tc.cu; same image order and element mapping)
 __device__ __forceinline__ size_t img_off(int r, int k) { return (size_t)r * 64 + (size_t)((((k >> 3) ^ (r & 7)) << 3) + (k & 7)); }
 
-__global__ void __launch_bounds__(256) k_build_tc_images(const StepTrainPtrs sp, __nv_bfloat16* __restrict__ fwd,
-                                                         __nv_bfloat16* __restrict__ bwd, int k1p_f, int n3p_f, int k1p_b,
-                                                         int n3p_b, int f16) {
+__global__ void __launch_bounds__(256) k_build_tc_images(const StepRefresh* __restrict__ table) {
+  const StepRefresh& row = table[blockIdx.z];                      // grid.z = flow step
+  const StepTrainPtrs sp = row.sp;
+  __nv_bfloat16* fwd = row.fwd_img;
+  __nv_bfloat16* bwd = row.bwd_img;
+  const int k1p_f = row.k1p_f, n3p_f = row.n3p_f, k1p_b = row.k1p_b, n3p_b = row.n3p_b, f16 = row.f16;
   const int F = sp.F, C = sp.C, Ch = C / 2;
   const int dir = blockIdx.y;                                   // 0 forward set, 1 backward set
   const int k1p = dir == 0 ? k1p_f : k1p_b, n3p = dir == 0 ? n3p_f : n3p_b;
@@ -616,8 +622,13 @@ __global__ void __launch_bounds__(256) k_build_tc_images(const StepTrainPtrs sp,
 // bias1 = c1, bias2 = c2 + b1' K2, const3[tap][c] = sum_k b2'[k] K3[tap][k][c], c3.
 // grid 16 blocks x 512 threads = (16 k-groups x 32 outputs): every thread reduces a 32-long k slice, the 16 slices are
 // combined in a fixed order through shared memory (fp32; the host twin accumulates in double, difference ~1e-7 relative).
-__global__ void __launch_bounds__(512) k_build_tc_biases(const StepTrainPtrs sp, float* __restrict__ bias1, float* __restrict__ bias2,
-                                                         float* __restrict__ const3, float* __restrict__ c3) {
+__global__ void __launch_bounds__(512) k_build_tc_biases(const StepRefresh* __restrict__ table) {
+  const StepRefresh& row = table[blockIdx.y];                      // grid.y = flow step
+  const StepTrainPtrs sp = row.sp;
+  float* bias1 = row.bias1;
+  float* bias2 = row.bias2;
+  float* const3 = row.const3;
+  float* c3 = row.c3;
   __shared__ float part[16][33];
   const int F = sp.F, C = sp.C, t = threadIdx.x;
   const int ol = t & 31, kg = t >> 5;
@@ -764,9 +775,8 @@ void launch_loss(const double* acc_ld, const double* acc_prior, const double* cs
   ASEP_LAUNCH_CHECK();
 }
 
-void launch_derive_step(const StepTrainPtrs& sp, double HW, double* ldc, int need_k2t, cudaStream_t s) {
-  ASEP_CHECK(sp.C * sp.C <= 256, ASEP_ERR_UNSUPPORTED, "derive: C > 16");
-  k_derive_step<<<1, 512, 0, s>>>(sp, HW, ldc, need_k2t);
+void launch_derive_all(const StepRefresh* table, int n_steps, double* ldc, int need_k2t, cudaStream_t s) {
+  k_derive_step<<<n_steps, 512, 0, s>>>(table, ldc, need_k2t);
   ASEP_LAUNCH_CHECK();
 }
 
@@ -814,12 +824,11 @@ void launch_colsum_bf16(const __nv_bfloat16* X, float* out, long long M, int F, 
   ASEP_LAUNCH_CHECK();
 }
 
-void launch_build_tc_step(const StepTrainPtrs& sp, __nv_bfloat16* fwd_img, __nv_bfloat16* bwd_img, int k1p_f, int n3p_f,
-                          int k1p_b, int n3p_b, float* bias1, float* bias2, float* const3, float* c3, bool f16, cudaStream_t s) {
-  dim3 grid(296, 2);
-  k_build_tc_images<<<grid, 256, 0, s>>>(sp, fwd_img, bwd_img, k1p_f, n3p_f, k1p_b, n3p_b, f16 ? 1 : 0);
+void launch_build_tc_all(const StepRefresh* table, int n_steps, cudaStream_t s) {
+  dim3 grid(48, 2, n_steps);                                       // ~37-45 k work items per (step, direction), grid-stride
+  k_build_tc_images<<<grid, 256, 0, s>>>(table);
   ASEP_LAUNCH_CHECK();
-  k_build_tc_biases<<<16, 512, 0, s>>>(sp, bias1, bias2, const3, c3);   // F = 512 (checked by nn_tc_prepare)
+  k_build_tc_biases<<<dim3(16, n_steps), 512, 0, s>>>(table);       // F = 512 (checked by nn_tc_prepare)
   ASEP_LAUNCH_CHECK();
 }
 

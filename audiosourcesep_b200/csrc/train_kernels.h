@@ -17,6 +17,18 @@ struct StepTrainPtrs {
       o_bn2_beta, o_k3, o_c3;
 };
 
+// One row per flow step of the device-side refresh table: everything k_derive_step / k_build_tc_images /
+// k_build_tc_biases need, so that the constants of ALL steps are rebuilt by three launches after an optimizer step
+// (grid dimension = step) instead of three launches per step.
+struct StepRefresh {
+  StepTrainPtrs sp;
+  __nv_bfloat16 *fwd_img, *bwd_img;
+  int k1p_f, n3p_f, k1p_b, n3p_b;
+  float *bias1, *bias2, *const3, *c3;
+  double HW;
+  int f16;
+};
+
 void launch_axpy(const float* x, const float* n, float sigma, float* y, long long total, cudaStream_t s);
 void launch_colsum(const float* X, float* out, long long M, int F, cudaStream_t s);                     // out += column sums
 void launch_wgrad_tn(const float* A, const float* B, float* Q, long long M, int F, cudaStream_t s);     // Q += A^T B
@@ -37,13 +49,14 @@ void launch_im2col_xb(const float* state, __nv_bfloat16* X9, int N, int H, int W
 void launch_s3(const float* gr, float* S3, int N, int H, int W, int C, cudaStream_t s);
 void launch_colsum_bf16(const __nv_bfloat16* X, float* out, long long M, int F, cudaStream_t s);
 // device twin of nn_tc_prepare: tile images of both directions + folded biases of one step
-void launch_build_tc_step(const StepTrainPtrs& sp, __nv_bfloat16* fwd_img, __nv_bfloat16* bwd_img, int k1p_f, int n3p_f,
-                          int k1p_b, int n3p_b, float* bias1, float* bias2, float* const3, float* c3, bool f16, cudaStream_t s);
+// (table: device array of n_steps rows)
+void launch_build_tc_all(const StepRefresh* table, int n_steps, cudaStream_t s);
 void launch_prior_grads(const float* z, const float* loc, const float* ls, float* gloc, float* gls, int N, int D, float gs,
                         cudaStream_t s);
 void launch_loss(const double* acc_ld, const double* acc_prior, const double* cst, double extra_const, int N,
                  double inv_batch, float* loss, cudaStream_t s);
-void launch_derive_step(const StepTrainPtrs& sp, double HW, double* ldc, int need_k2t, cudaStream_t s);
+// ldc[step] = H*W*(sum log_scale + sum log_S) of every step
+void launch_derive_all(const StepRefresh* table, int n_steps, double* ldc, int need_k2t, cudaStream_t s);
 void launch_sum_doubles(const double* v, int n, double* out, cudaStream_t s);
 void launch_adamax(float* theta, const float* g, float* m, float* u, long long n, float lr_t, float b1, float b2, float eps,
                    cudaStream_t s);

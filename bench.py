@@ -190,6 +190,67 @@ def _config(args, per_gpu_batch, note=None):
 
 
 # ------------------------------------------------------------------------------------ our arm
+# tcgen05 products per GEMM of every Glow precision mode: the roofline denominator of a mode is the measured sustained
+# bf16 peak divided by this number (the extra products are the price of the mode, not useful work)
+PRODUCTS = {"bf16": 1, "fp16": 1, "bf16x2": 2, "fp16x2": 2, "fp16x3": 3}
+
+
+def _prec(_lib, name):
+    return {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16, "fp16": _lib.PREC_FP16, "bf16x2": _lib.PREC_BF16X2,
+            "fp16x2": _lib.PREC_FP16X2, "fp16x3": _lib.PREC_FP16X3}[name]
+
+
+def parity_block(models_by_mode, torch, ops, bo, synthetic, D):
+    """Gate values of every benchmarked Glow mode, measured in THIS run against the committed oracle vectors
+    (tests/golden/glow_k40.npz: float64 oracle score / log_prob of the full-depth BASIS priors at n_mixed = 30, the
+    inputs regenerated from the seeded generators).  The oracle itself is not executed here."""
+    path = os.path.join(ROOT, "tests", "golden", "glow_k40.npz")
+    if not os.path.exists(path):
+        return None
+    gold = np.load(path)
+    n = gold["grad1"].shape[0]
+    mixed, _, _ = synthetic.basis_problem(n)
+    x1, x2 = synthetic.langevin_init(n, seed=4)
+    sig = bo.get_sigmas(1.0, 0.01, 10, "logarithmic")
+    out = {"reference": "tests/golden/glow_k40.npz (float64 oracle, K=40, n_mixed=30; generator tests/golden/make_glow_k40_golden.py)",
+           "gates": {"log_prob_nats_per_dim": 1e-3, "round_trip_max_abs": 1e-4, "langevin_step_state_rel": 1e-3}}
+    for mode, (m1, m2) in models_by_mode.items():
+        r = {}
+        t1, t2 = torch.as_tensor(x1).cuda(), torch.as_tensor(x2).cuda()
+        g1, lp1 = m1.grad_log_prob(t1, return_log_prob=True)
+        g2, lp2 = m2.grad_log_prob(t2, return_log_prob=True)
+        r["log_prob_err_nats_per_dim"] = float(max(np.max(np.abs(lp1.cpu().numpy() - gold["logp1"])),
+                                                   np.max(np.abs(lp2.cpu().numpy() - gold["logp2"]))) / D)
+        errs = []
+        for g, key in ((g1, "grad1"), (g2, "grad2")):
+            ref = gold[key].astype(np.float64)
+            errs.append(float(np.linalg.norm(g.cpu().numpy()[..., 0] - ref) / np.linalg.norm(ref)))
+        r["score_rel_l2_err"] = max(errs)
+        z = m1.forward(t1)
+        r["round_trip_max_abs"] = float((m1.inverse(z) - t1).abs().max().item())        # states are normalised units
+        g_fn, gg_fn = None, None
+        step = {}
+        for idx in (0, 1, 4, 9):
+            eta, lam, ns = bo.langevin_step_constants(sig, idx)
+            rng = np.random.Generator(np.random.PCG64(100 + idx))
+            n1, n2 = (rng.standard_normal(x1.shape).astype(np.float32) for _ in range(2))
+            # expected state: the fused update applied to the ORACLE scores (computed on the device by the same
+            # Langevin kernel, whose own error is ~1e-7, tests/test_gpu_langevin.py)
+            e1, e2 = torch.as_tensor(x1).cuda(), torch.as_tensor(x2).cuda()
+            ops.langevin_step(e1, e2, torch.as_tensor(gold["grad1"][..., None]), torch.as_tensor(gold["grad2"][..., None]),
+                              torch.as_tensor(mixed), float(eta), float(lam), float(ns), n1=torch.as_tensor(n1), n2=torch.as_tensor(n2))
+            a1, a2 = torch.as_tensor(x1).cuda(), torch.as_tensor(x2).cuda()
+            ops.basis_glow_inner(m1, m2, torch.as_tensor(mixed), a1, a2, 1, float(eta), float(lam), float(ns),
+                                 noise1=torch.as_tensor(n1[None]), noise2=torch.as_tensor(n2[None]))
+            step[f"sigma_idx_{idx}"] = float(max(torch.linalg.norm(a1 - e1) / torch.linalg.norm(e1),
+                                                 torch.linalg.norm(a2 - e2) / torch.linalg.norm(e2)).item())
+        r["langevin_step_state_rel_err"] = step
+        r["gates_met"] = {"log_prob": r["log_prob_err_nats_per_dim"] <= 1e-3, "round_trip": r["round_trip_max_abs"] <= 1e-4,
+                          "langevin_step_at_sigma_idx": [i for i in (0, 1, 4, 9) if step[f"sigma_idx_{i}"] <= 1e-3]}
+        out[mode] = r
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -217,13 +278,15 @@ def run_ours(args):
     cfg = GlowConfig(K=args.K)
     params = init_glow_params(cfg, seed=2)
     model = Glow(cfg, params, precision=_lib.PREC_BF16, device=local_rank)
-    ops.set_tc_cluster(args.cluster)
     B = args.batch
-    base = synthetic.mel_patches_db(min(B, 64), seed=100 + rank)
-    reps = (B + base.shape[0] - 1) // base.shape[0]
-    # distinct patches: cyclic shifts of the seeded base set along time
-    host = np.concatenate([np.roll(base, 3 * i, axis=2) for i in range(reps)], axis=0)[:B]
-    x_host = torch.as_tensor(np.ascontiguousarray(host)).pin_memory()
+
+    def patches(n, seed):
+        base = synthetic.mel_patches_db(min(n, 64), seed=seed)
+        reps = (n + base.shape[0] - 1) // base.shape[0]
+        # distinct patches: cyclic shifts of the seeded base set along time
+        return np.ascontiguousarray(np.concatenate([np.roll(base, 3 * i, axis=2) for i in range(reps)], axis=0)[:n])
+
+    x_host = torch.as_tensor(patches(B, 100 + rank)).pin_memory()
     x_dev = x_host.to(dev)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
 
@@ -232,18 +295,21 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed_loop(step_fn, steps, warmup, profile=False):
+    def timed_loop(step_fn, steps, warmup, profile=False, do_flush=True):
         for _ in range(warmup):
             step_fn()
         barrier()
         evs = []
         if profile == "conv":
             _lib.conv_profile(True)
+        elif profile == "hbm":
+            _lib.hbm_profile(True)
         elif profile:
             _lib.tc_profile(True)
         n0 = _lib.launch_count()
         for _ in range(steps):
-            flush.fill_(1)
+            if do_flush:
+                flush.fill_(1)
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             step_fn()
@@ -255,6 +321,9 @@ def run_ours(args):
         if profile == "conv":
             prof = _lib.conv_profile_read()
             _lib.conv_profile(False)
+        elif profile == "hbm":
+            prof = {name: _lib.hbm_profile_read(cat) for name, cat in _lib.HBM_CATEGORIES.items()}
+            _lib.hbm_profile(False)
         elif profile:
             prof = _lib.tc_profile_read()
             _lib.tc_profile(False)
@@ -263,6 +332,18 @@ def run_ours(args):
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()), launches, prof
+
+    def tc_roofline(prof, total_ms, kernel, products):
+        k_ms, k_launches, k_flops = prof
+        achieved = k_flops / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
+        peak = peaks["bf16_sustained"] / products
+        return {"bound": "tensor", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": achieved / peak, "products_per_gemm": products,
+                "peak_source": f"{peaks['source']} sustained bf16 ({peaks['bf16_sustained']:.1f} TFLOP/s; kernel timed inside a long step)"
+                               + ("" if products == 1 else f" / {products} tcgen05 products per GEMM of this precision mode"),
+                "launches": k_launches, "avg_launch_ms": k_ms / max(1, k_launches),
+                "kernel_share_of_step": k_ms / total_ms if total_ms > 0 else None,
+                "alg_flops_per_launch": k_flops / max(1, k_launches)}
 
     # ---- 1. device-resident throughput (value) with the kernel-level CUDA events for the roofline
     out = {}
@@ -280,6 +361,26 @@ def run_ours(args):
     lp = out["lp"].float().cpu().numpy()
     if not np.all(np.isfinite(lp)):
         raise SystemExit("non-finite log_prob in the benchmark batch")
+    roofline = tc_roofline(prof, total_ms, "k_nn_tc4<fwd> (fused conv3x3 -> conv1x1 -> conv3x3 coupling network, K-pipelined tcgen05)", 1)
+    roofline["traffic"] = None
+
+    # ---- 1b. the HBM-bound kernels of the same pass (fused flow step = ActNorm + 1x1 + coupling + log-det + col2im)
+    nsub = max(2, args.steps // 2)
+    hbm_ms, _, hprof = timed_loop(step_dev, nsub, 1, profile="hbm")
+    roofline_hbm = []
+
+    def hbm_entry(name, kernel, rec, note):
+        ms, n, by = rec
+        if n == 0 or ms <= 0:
+            return
+        gbs = by / (ms * 1e-3) / 1e9
+        roofline_hbm.append({"bound": "hbm", "kernel": kernel, "category": name, "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s",
+                             "frac": gbs / peaks["hbm"], "launches": n, "avg_launch_us": 1e3 * ms / n,
+                             "algorithmic_bytes_per_launch": by / n, "traffic": None, "note": note})
+
+    hbm_entry("flow_step", "k_pre / k_post_pre<C, next, fused col2im>", hprof["flow_step"],
+              f"log_prob at {B} patches: 12 C bytes per pixel per flow step (state in, network output, state out; SURVEY 8(d)); "
+              "the fused col2im really reads the 9 per-tap fp32 partials of the tensor-core kernel instead of r")
 
     # ---- 2. end to end through the public API with host buffers
     def step_e2e():
@@ -288,65 +389,106 @@ def run_ours(args):
     e2e_ms, _, _ = timed_loop(step_e2e, args.steps, args.warmup)
     e2e_value = world * B * args.steps / (e2e_ms * 1e-3)
 
-    # ---- 2b. the other directions of config 1 (forward+inverse): inverse(z) and grad_log_prob(x) samples/s, device-resident
-    z_dev = model.forward(x_dev)
+    # ---- 2b. batch-size sweep of log_prob (config 1 at the reference's sizes: n_mixed = 30, training batch 32, ...)
+    sweep = {}
+    for n in [int(v) for v in args.sweep.split(",") if v]:
+        xs = torch.as_tensor(patches(n, 200 + rank)).to(dev)
+        nst = 5 if n <= 512 else 3
+        s_ms, s_launches, _ = timed_loop(lambda: model.log_prob(xs), nst, 2)
+        sweep[str(n)] = {"samples_per_s": world * n * nst / (s_ms * 1e-3), "ms_per_pass": s_ms / nst, "gpu_launches_per_pass": s_launches // nst,
+                         "alg_tflops": world * n * nst * F_GLOW * (args.K / 40.0) / (s_ms * 1e-3) / 1e12}
+        del xs
 
-    def step_inv():
-        out["xr"] = model.inverse(z_dev)
+    # ---- 2c. the other directions of config 1 in every precision mode: inverse(z) and grad_log_prob(x), device-resident
+    directions = {}
+    for mode in [m for m in args.modes.split(",") if m]:
+        if mode != "bf16":
+            model.prepare(_prec(_lib, mode))
+        prods = PRODUCTS[mode]
+        d = {"products_per_gemm": prods}
+        if mode != "bf16":
+            l_ms, _, l_prof = timed_loop(step_dev, nsub, 1, profile=True)
+            d["log_prob"] = {"value": world * B * nsub / (l_ms * 1e-3), "unit": "samples/s", "ms_per_step": l_ms / nsub,
+                             "roofline": tc_roofline(l_prof, l_ms, "k_nn_tcx<fwd> (two-pass split-precision coupling network, tcgen05)", prods)}
+        z_dev = model.forward(x_dev)
 
-    inv_ms, inv_launches, _ = timed_loop(step_inv, max(2, args.steps // 2), 2)
-    rt = float((out["xr"] - x_dev).abs().max().item())
+        def step_inv():
+            out["xr"] = model.inverse(z_dev)
 
-    def step_grad():
-        out["g"] = model.grad_log_prob(x_dev)
+        inv_ms, inv_launches, _ = timed_loop(step_inv, nsub, 1)
+        rt = float((out["xr"] - x_dev).abs().max().item()) / 120.0
 
-    g_ms, g_launches, _ = timed_loop(step_grad, max(2, args.steps // 2), 2)
-    nsub = max(2, args.steps // 2)
-    directions = {
-        "inverse": {"value": world * B * nsub / (inv_ms * 1e-3), "unit": "samples/s", "ms_per_step": inv_ms / nsub,
-                    "gpu_launches": inv_launches, "alg_tflops": world * B * nsub * F_GLOW * (args.K / 40.0) / (inv_ms * 1e-3) / 1e12,
-                    "round_trip_max_abs_dB": rt,
-                    "note": "bf16 tensor-core mode; the <= 1e-4 (normalised units) round-trip gate is met by ASEP_PREC_FP32, see DESIGN.md section 4"},
-        "grad_log_prob": {"value": world * B * nsub / (g_ms * 1e-3), "unit": "samples/s", "ms_per_step": g_ms / nsub,
-                          "gpu_launches": g_launches,
-                          "alg_tflops": world * B * nsub * 2 * F_GLOW * (args.K / 40.0) / (g_ms * 1e-3) / 1e12},
-    }
-    del z_dev
+        def step_grad():
+            out["g"] = model.grad_log_prob(x_dev)
 
-    # ---- 3. BASIS Langevin segment-steps/s with two Glow priors (second half of the metric)
-    basis = None
-    if args.basis_segments > 0:
-        nseg = args.basis_segments
+        g_ms, g_launches, _ = timed_loop(step_grad, nsub, 1)
+        d["inverse"] = {"value": world * B * nsub / (inv_ms * 1e-3), "unit": "samples/s", "ms_per_step": inv_ms / nsub,
+                        "gpu_launches": inv_launches, "alg_tflops": world * B * nsub * F_GLOW * (args.K / 40.0) / (inv_ms * 1e-3) / 1e12,
+                        "round_trip_max_abs_normalised": rt, "gate": 1e-4, "gate_met": rt <= 1e-4}
+        d["grad_log_prob"] = {"value": world * B * nsub / (g_ms * 1e-3), "unit": "samples/s", "ms_per_step": g_ms / nsub,
+                              "gpu_launches": g_launches,
+                              "alg_tflops": world * B * nsub * 2 * F_GLOW * (args.K / 40.0) / (g_ms * 1e-3) / 1e12}
+        directions[mode] = d
+        del z_dev
+    del model
+
+    # ---- 3. BASIS Langevin segment-steps/s with two Glow priors (second half of the metric), per precision mode, at the
+    #         reference's n_mixed = 30 (run_basis_sep.py:478) and at a batch that fills the GPU
+    basis, parity = None, None
+    if args.basis_segments:
         bcfg = GlowConfig(K=args.K, minval=0.0, maxval=1.0)
-        m1 = Glow(bcfg, init_glow_params(bcfg, seed=2), precision=_lib.PREC_BF16, device=local_rank)
-        m2 = Glow(bcfg, init_glow_params(bcfg, seed=3), precision=_lib.PREC_BF16, device=local_rank)
-        mixed, _, _ = synthetic.basis_problem(min(nseg, 32), seed1=10 + rank, seed2=50 + rank)
-        mixed = np.concatenate([mixed] * ((nseg + mixed.shape[0] - 1) // mixed.shape[0]))[:nseg]
-        x1, x2 = synthetic.langevin_init(nseg, seed=4 + rank)
-        mixed_d = torch.as_tensor(mixed).to(dev)
-        t1, t2 = torch.as_tensor(x1).to(dev), torch.as_tensor(x2).to(dev)
+        p1, p2 = init_glow_params(bcfg, seed=2), init_glow_params(bcfg, seed=3)
         sig = bo.get_sigmas(1.0, 0.01, 10, "logarithmic")
         eta, lam, ns = bo.langevin_step_constants(sig, 9)
         T = args.basis_T
-        stepno = [0]
+        basis, pair_by_mode = {}, {}
+        for mode in [m for m in args.basis_modes.split(",") if m]:
+            m1 = Glow(bcfg, p1, precision=_prec(_lib, mode), device=local_rank)
+            m2 = Glow(bcfg, p2, precision=_prec(_lib, mode), device=local_rank)
+            pair_by_mode[mode] = (m1, m2)
+            legs = {}
+            for nseg in [int(v) for v in args.basis_segments.split(",") if v]:
+                mixed, _, _ = synthetic.basis_problem(min(nseg, 32), seed1=10 + rank, seed2=50 + rank)
+                mixed = np.concatenate([mixed] * ((nseg + mixed.shape[0] - 1) // mixed.shape[0]))[:nseg]
+                x1, x2 = synthetic.langevin_init(nseg, seed=4 + rank)
+                mixed_d = torch.as_tensor(mixed).to(dev)
+                t1, t2 = torch.as_tensor(x1).to(dev), torch.as_tensor(x2).to(dev)
+                stepno = [0]
 
-        def step_basis():
-            ops.basis_glow_inner(m1, m2, mixed_d, t1, t2, T, float(eta), float(lam), float(ns), seed=1,
-                                 step0=stepno[0], elem_offset=rank * nseg * D_PATCH)
-            stepno[0] += T
+                def step_basis():
+                    ops.basis_glow_inner(m1, m2, mixed_d, t1, t2, T, float(eta), float(lam), float(ns), seed=1,
+                                         step0=stepno[0], elem_offset=rank * nseg * D_PATCH)
+                    stepno[0] += T
 
-        b_ms, b_launches, _ = timed_loop(step_basis, max(1, args.steps // 2), 1)
-        nsteps = max(1, args.steps // 2)
-        basis = {"metric": "basis_glow_segment_steps_per_s", "value": world * nseg * T * nsteps / (b_ms * 1e-3),
-                 "unit": "segment-steps/s", "segments_per_gpu": nseg, "langevin_steps_per_call": T,
-                 "ms_per_langevin_step": b_ms / (nsteps * T), "gpu_launches": b_launches,
-                 "alg_tflops": world * nseg * T * nsteps * 4 * F_GLOW * (args.K / 40.0) / (b_ms * 1e-3) / 1e12,
-                 "note": "2 priors x (forward + data-gradient) = 4 F_glow algorithmic FLOP per segment-step; in-kernel "
-                         "Philox noise; sigma index 9 of the 10-level schedule"}
-        if not (torch.isfinite(t1).all() and torch.isfinite(t2).all()):
-            basis["note"] += "; WARNING non-finite state"
+                nsteps = max(1, args.steps // 2)
+                b_ms, b_launches, _ = timed_loop(step_basis, nsteps, 1)
+                legs[str(nseg)] = {"value": world * nseg * T * nsteps / (b_ms * 1e-3), "unit": "segment-steps/s", "segments_per_gpu": nseg,
+                                   "ms_per_langevin_step": b_ms / (nsteps * T), "gpu_launches_per_langevin_step": b_launches // (nsteps * T),
+                                   "alg_tflops": world * nseg * T * nsteps * 4 * F_GLOW * (args.K / 40.0) / (b_ms * 1e-3) / 1e12,
+                                   "finite": bool(torch.isfinite(t1).all() and torch.isfinite(t2).all())}
+            basis[mode] = {"metric": "basis_glow_segment_steps_per_s", "products_per_gemm": PRODUCTS[mode], "segments": legs,
+                           "note": "2 priors x (forward + data-gradient) = 4 F_glow algorithmic FLOP per segment-step; in-kernel Philox "
+                                   "noise; sigma index 9 of the 10-level schedule; the gate each mode meets is in `parity`"}
+        if rank == 0 and args.parity:
+            parity = parity_block(pair_by_mode, torch, ops, bo, synthetic, D_PATCH)
+        # ---- the fused Langevin update alone at a size that spills L2 (HBM roofline of k_langevin)
+        if rank == 0:
+            nl = 4096
+            shp = (nl, 96, 64, 1)
+            g = torch.Generator(device=dev).manual_seed(0)
+            ten = [torch.rand(shp, device=dev, generator=g) for _ in range(5)]
 
-    # ---- 4. BASIS with NCSN v1 / v2 score networks (configs 4 and 5 of BASELINE.json), n_mixed = 30 segments per GPU
+            def step_lan():
+                ops.langevin_step(ten[0], ten[1], ten[2], ten[3], ten[4], 2e-5, 1e4, 6.3e-3, seed=1, step=0)
+
+            _, _, lprof = timed_loop(step_lan, 5, 2, profile="hbm", do_flush=False)
+            hbm_entry("langevin", "k_langevin<in-kernel Philox>", lprof["langevin"],
+                      f"{nl} segments (7 tensors x 100 MB, larger than L2): 5 reads + 2 writes x 4 B per element (SURVEY 8(d))")
+            del ten
+        del pair_by_mode
+
+    # ---- 4. BASIS with NCSN v1 / v2 score networks (configs 4 and 5 of BASELINE.json), n_mixed = 30 segments per GPU, in the
+    #         throughput mode (one bf16 product) and the parity mode (three split-bf16 products)
     ncsn = {}
     if args.ncsn_segments > 0:
         from audiosourcesep_b200 import NCSNConfig
@@ -358,90 +500,149 @@ def run_ours(args):
         for ver, ncfg, gflop in (("v1", NCSNConfig(version="v1", ngf=192, num_classes=10, sigma1=1.0), 533.9),
                                  ("v2", NCSNConfig(version="v2", ngf=128, num_classes=200, sigma1=30.0), 237.3)):
             sig_n = bo.get_sigmas(ncfg.sigma1, ncfg.sigmaL, ncfg.num_classes, "logarithmic")
-            s1 = ScoreModel(ncfg, init_ncsn_params(ncfg, seed=11), sigmas=sig_n, device=local_rank)
-            s2 = ScoreModel(ncfg, init_ncsn_params(ncfg, seed=12), sigmas=sig_n, device=local_rank)
-            a1, a2 = synthetic.langevin_init(nseg, seed=7 + rank)
-            u1, u2 = torch.as_tensor(a1).to(dev), torch.as_tensor(a2).to(dev)
-            idx = ncfg.num_classes - 1
-            eta_n, lam_n, ns_n = bo.langevin_step_constants(sig_n, idx)
-            cnt = [0]
+            for mode, prec, prods in (("bf16", _lib.PREC_BF16, 1), ("bf16x3", _lib.PREC_BF16X3, 3)):
+                if mode not in args.ncsn_modes.split(","):
+                    continue
+                s1 = ScoreModel(ncfg, init_ncsn_params(ncfg, seed=11), sigmas=sig_n, device=local_rank, precision=prec)
+                s2 = ScoreModel(ncfg, init_ncsn_params(ncfg, seed=12), sigmas=sig_n, device=local_rank, precision=prec)
+                a1, a2 = synthetic.langevin_init(nseg, seed=7 + rank)
+                u1, u2 = torch.as_tensor(a1).to(dev), torch.as_tensor(a2).to(dev)
+                idx = ncfg.num_classes - 1
+                eta_n, lam_n, ns_n = bo.langevin_step_constants(sig_n, idx)
+                cnt = [0]
 
-            def step_ncsn():
-                ops.basis_ncsn_inner(s1, s2, mixed_d, u1, u2, idx, args.ncsn_T, float(eta_n), float(lam_n), float(ns_n),
-                                     seed=2, step0=cnt[0], elem_offset=rank * nseg * D_PATCH)
-                cnt[0] += args.ncsn_T
+                def step_ncsn():
+                    ops.basis_ncsn_inner(s1, s2, mixed_d, u1, u2, idx, args.ncsn_T, float(eta_n), float(lam_n), float(ns_n),
+                                         seed=2, step0=cnt[0], elem_offset=rank * nseg * D_PATCH)
+                    cnt[0] += args.ncsn_T
 
-            nst = max(2, args.steps // 2)
-            n_ms, n_launches, (c_ms, c_n, c_fl) = timed_loop(step_ncsn, nst, 2, profile="conv")
-            rate = world * nseg * args.ncsn_T * nst / (n_ms * 1e-3)
-            conv_tf = c_fl / (c_ms * 1e-3) / 1e12 if c_ms > 0 else 0.0
-            ncsn[ver] = {"metric": f"basis_ncsn_{ver}_segment_steps_per_s", "value": rate, "unit": "segment-steps/s",
-                         "segments_per_gpu": nseg, "ms_per_langevin_step": n_ms / (nst * args.ncsn_T),
-                         "gpu_launches": n_launches, "alg_tflops": rate * gflop / 1e3,
-                         "roofline": {"bound": "tensor", "kernel": "k_conv_tc (TMA-fed tcgen05 implicit-GEMM convolution)",
-                                      "achieved": conv_tf, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                                      "frac": conv_tf / peaks["bf16_sustained"], "launches": c_n,
-                                      "kernel_share_of_step": c_ms / n_ms if n_ms > 0 else None},
-                         "finite": bool(torch.isfinite(u1).all() and torch.isfinite(u2).all())}
-            del s1, s2
+                nst = max(2, args.steps // 2)
+                n_ms, n_launches, (c_ms, c_n, c_fl) = timed_loop(step_ncsn, nst, 2, profile="conv")
+                rate = world * nseg * args.ncsn_T * nst / (n_ms * 1e-3)
+                # the x3 mode launches every convolution three times: its algorithmic FLOPs are those of ONE product
+                conv_tf = c_fl / prods / (c_ms * 1e-3) / 1e12 if c_ms > 0 else 0.0
+                peak = peaks["bf16_sustained"] / prods
+                leg = {"metric": f"basis_ncsn_{ver}_segment_steps_per_s", "value": rate, "unit": "segment-steps/s",
+                       "segments_per_gpu": nseg, "products_per_conv": prods, "ms_per_langevin_step": n_ms / (nst * args.ncsn_T),
+                       "gpu_launches_per_langevin_step": n_launches // (nst * args.ncsn_T), "alg_tflops": rate * gflop / 1e3,
+                       "roofline": {"bound": "tensor", "kernel": "k_conv_tc (TMA-fed tcgen05 implicit-GEMM convolution)",
+                                    "achieved": conv_tf, "peak": peak, "unit": "TFLOP/s", "frac": conv_tf / peak, "launches": c_n,
+                                    "kernel_share_of_step": c_ms / n_ms if n_ms > 0 else None,
+                                    "peak_source": f"{peaks['source']} sustained bf16 / {prods} products per convolution"},
+                       "step_roofline_frac": rate * gflop / 1e3 / world / peak,
+                       "gate": ("per-step Langevin state <= 1e-3 at every noise level (tests/test_gpu_ncsn.py)" if prods == 3 else
+                                "per-step gate met on the annealed end of the schedule only (score error 1-5 %)"),
+                       "finite": bool(torch.isfinite(u1).all() and torch.isfinite(u2).all())}
+                if rank == 0 and mode == "bf16":
+                    _, _, nprof = timed_loop(step_ncsn, 1, 0, profile="hbm")
+                    hbm_entry("ncsn_prep", f"k_prep (NCSN {ver}: normalise + ELU + bf16 cast of a convolution input)", nprof["ncsn_prep"],
+                              f"{nseg} segments: 4 B read + 2 B written per element")
+                    hbm_entry("ncsn_pool_resize", f"k_pool5_1d / k_avgpool2 / k_resize2x_add (NCSN {ver})", nprof["ncsn_pool_resize"],
+                              f"{nseg} segments: one read + one write of the tensor per pooling (the separable form moves it twice)")
+                ncsn.setdefault(ver, {})[mode] = leg
+                del s1, s2
 
-    # ---- 5. Glow training step (config 2): fp32 exact mode, global batch 32 per GPU, Adamax, NCCL gradient all-reduce
+    # ---- 5. Glow training step (config 2): tcgen05 path, per-GPU batch (weak) and the reference's GLOBAL batch 32 (strong)
     train = None
     if args.train_batch > 0:
         from audiosourcesep_b200 import train_glow as tg
         tcfg = GlowConfig(K=args.K)
-        tb = args.train_batch
-        xt = torch.as_tensor(synthetic.mel_patches_db(tb, seed=300 + rank)).to(dev)
-        # the reference's own initialisation: QR/LU 1x1, Glorot conv1/conv2, zero conv3, data-dependent ActNorm
-        # (flow_builder.py:96-100); identical on every rank (same seed, rank-0-shaped minibatch)
         tprec = _lib.PREC_FP32 if args.train_fp32 else _lib.PREC_BF16
         tm = Glow(tcfg, init_glow_params(tcfg, seed=2, mode="faithful"), precision=tprec, device=local_rank)
-        tm.init_actnorm(torch.as_tensor(synthetic.mel_patches_db(tb, seed=300)).to(dev))
+        # the reference's own initialisation: QR/LU 1x1, Glorot conv1/conv2, zero conv3, data-dependent ActNorm
+        # (flow_builder.py:96-100); identical on every rank (same seed, rank-0-shaped minibatch)
+        tm.init_actnorm(torch.as_tensor(synthetic.mel_patches_db(args.train_batch, seed=300)).to(dev))
         tm.enable_training()
-        opt = dict(lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-7)
-        last = [0.0]
+        opt = dict(kind="adamax", lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-7)
+        train = {}
+        cases = [("weak", args.train_batch, args.train_batch * world)]
+        if world > 1 and args.train_batch % world == 0:
+            cases.append(("strong", args.train_batch // world, args.train_batch))
+        for name, local, glob in cases:
+            xt = torch.as_tensor(synthetic.mel_patches_db(glob, seed=300)[rank * local:(rank + 1) * local]).to(dev)
+            hist = []
 
-        def step_train():
-            last[0] = tg.distributed_train_step(tm, opt, xt, tb * world)
+            def step_train():
+                hist.append(tg.distributed_train_step(tm, opt, xt, glob))
 
-        nst = max(2, args.steps // 3)
-        t_ms, t_launches, _ = timed_loop(step_train, nst, 3)     # eager (sizes the scratch), graph capture, first replay
-        train = {"metric": "glow_train_samples_per_s", "value": world * tb * nst / (t_ms * 1e-3), "unit": "samples/s",
-                 "steps_per_s": nst / (t_ms * 1e-3), "per_gpu_batch": tb, "global_batch": tb * world, "dtype": "f32" if args.train_fp32 else "bf16",
-                 "ms_per_step": t_ms / nst, "gpu_launches": t_launches, "allreduce_bytes_per_step": int(tm.num_trainable * 4),
-                 "alg_tflops": world * tb * nst * 3 * F_GLOW * (args.K / 40.0) / (t_ms * 1e-3) / 1e12,
-                 "loss": float(last[0].item()), "loss_finite": bool(torch.isfinite(last[0]).all()),
-                 "note": ("CUDA-core fp32 exact mode" if args.train_fp32 else
-                          "tcgen05 forward / data-gradient / weight-gradient GEMMs (bf16 operands, fp32 accumulate), "
-                          "fp32 master weights + Adamax, tile images rebuilt on the device every step, gradient pass replayed as a CUDA graph; "
-                          "the loss value is that of the reference's own (quirk Q1/Q7) initialisation on synthetic patches, see DESIGN.md section 5")
-                         + "; NCCL all-reduce of the flat gradient vector"}
+            nst = max(2, args.steps // 3)
+            t_ms, t_launches, _ = timed_loop(step_train, nst, 3)     # eager (sizes the scratch), graph capture, first replay
+            losses = [float(v.item()) for v in hist]
+            train[name] = {"metric": "glow_train_samples_per_s", "value": glob * nst / (t_ms * 1e-3), "unit": "samples/s",
+                           "steps_per_s": nst / (t_ms * 1e-3), "per_gpu_batch": local, "global_batch": glob,
+                           "dtype": "f32" if args.train_fp32 else "bf16", "ms_per_step": t_ms / nst, "gpu_launches_per_step": t_launches // nst,
+                           "allreduce_bytes_per_step": int(tm.num_trainable * 4) if world > 1 else 0,
+                           "alg_tflops": glob * nst * 3 * F_GLOW * (args.K / 40.0) / (t_ms * 1e-3) / 1e12,
+                           "step_roofline_frac": glob * nst * 3 * F_GLOW * (args.K / 40.0) / (t_ms * 1e-3) / 1e12 / world / peaks["bf16_sustained"],
+                           "loss_first": losses[0], "loss_last": losses[-1], "loss_finite": bool(np.all(np.isfinite(losses))),
+                           "loss_decreased": bool(losses[-1] < losses[0])}
+        train["note"] = ("tcgen05 forward / data-gradient / weight-gradient GEMMs (bf16 operands, fp32 accumulate), fp32 master weights + "
+                         "Adamax, tile images rebuilt on the device every step, gradient pass replayed as a CUDA graph; NCCL all-reduce of "
+                         "the flat gradient vector; the loss is that of the reference's own (quirk Q1/Q7) initialisation on synthetic patches")
         del tm
+
+    # ---- 6. strong scaling of the BASIS configs: the reference's n_mixed = 30 segments SHARDED over the ranks (configs 3-5)
+    strong = None
+    if world > 1 and args.strong:
+        strong = {}
+        n_mixed = 30
+        lo, hi = (rank * n_mixed) // world, ((rank + 1) * n_mixed) // world
+        nloc = hi - lo
+        mixed, _, _ = synthetic.basis_problem(n_mixed)
+        x1, x2 = synthetic.langevin_init(n_mixed, seed=4)
+        bcfg = GlowConfig(K=args.K, minval=0.0, maxval=1.0)
+        sig = bo.get_sigmas(1.0, 0.01, 10, "logarithmic")
+        eta, lam, ns = bo.langevin_step_constants(sig, 9)
+        for mode in [m for m in args.basis_modes.split(",") if m]:
+            m1 = Glow(bcfg, init_glow_params(bcfg, seed=2), precision=_prec(_lib, mode), device=local_rank)
+            m2 = Glow(bcfg, init_glow_params(bcfg, seed=3), precision=_prec(_lib, mode), device=local_rank)
+            md = torch.as_tensor(mixed[lo:hi]).to(dev)
+            t1, t2 = torch.as_tensor(x1[lo:hi]).to(dev), torch.as_tensor(x2[lo:hi]).to(dev)
+            cnt = [0]
+
+            def step_sb():
+                if nloc > 0:
+                    ops.basis_glow_inner(m1, m2, md, t1, t2, args.basis_T, float(eta), float(lam), float(ns), seed=1, step0=cnt[0],
+                                         elem_offset=lo * D_PATCH)
+                cnt[0] += args.basis_T
+
+            nsteps = max(2, args.steps // 2)
+            b_ms, _, _ = timed_loop(step_sb, nsteps, 1)
+            strong[f"basis_glow_{mode}"] = {"value": n_mixed * args.basis_T * nsteps / (b_ms * 1e-3), "unit": "segment-steps/s",
+                                            "n_mixed_total": n_mixed, "segments_this_rank": nloc, "ms_per_langevin_step": b_ms / (nsteps * args.basis_T)}
+            del m1, m2
+        strong["note"] = ("the reference's n_mixed = 30 segments sharded over the ranks (strong scaling: the N = 1 line's `basis.<mode>.segments.30` "
+                          "is the single-GPU figure of the same workload); `train.strong` is the reference's global batch 32 split over the ranks")
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel
-    k_ms, k_launches, k_flops = prof
-    achieved = k_flops / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
-    roofline = {"bound": "tensor", "kernel": "k_nn_tc4<fwd> (fused conv3x3 -> conv1x1 -> conv3x3 coupling network, K-pipelined tcgen05)",
-                "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                "frac": achieved / peaks["bf16_sustained"], "peak_source": f"{peaks['source']} sustained bf16 (kernel timed inside a long step)",
-                "traffic": None, "launches": k_launches, "avg_launch_ms": k_ms / max(1, k_launches),
-                "kernel_share_of_step": k_ms / total_ms if total_ms > 0 else None,
-                "alg_flops_per_launch": k_flops / max(1, k_launches)}
+    # DRAM traffic of the dominant kernel: measured once under `ncu --set full` (profiles/, a committed capture), scaled
+    # to this run's launch size -- a constant from a file, labelled as such
     prof_path = os.path.join(ROOT, "profiles", "ncu_summary.json")
     if os.path.exists(prof_path):
         try:
             with open(prof_path) as f:
                 prof_js = json.load(f)
-            # ncu dram bytes per pixel row of the captured block-1 launch x the average rows per launch of this run
             per_row = prof_js.get("dram_bytes_per_pixel_row")
             rows_per_launch = B * (48 * 32 + 24 * 16 + 12 * 8) / 3.0
             roofline["traffic"] = None if per_row is None else per_row * rows_per_launch
-            roofline["traffic_note"] = "ncu dram__bytes_read+write per pixel row of a captured block-1 launch (profiles/ncu_summary.json) x mean rows per launch"
+            roofline["traffic_source"] = ("profiles constant: ncu dram__bytes_read+write per pixel row of a captured block-1 launch "
+                                          "(profiles/ncu_summary.json) x mean rows per launch of this run; not measured in this run")
+        except Exception:
+            pass
+    hbm_path = os.path.join(ROOT, "profiles", "r02_hbm_kernels.json")
+    if os.path.exists(hbm_path):
+        try:
+            with open(hbm_path) as f:
+                hj = json.load(f)
+            for e in roofline_hbm:
+                rec = hj.get(e["category"])
+                if rec:
+                    e["traffic"] = rec.get("dram_bytes_per_launch")
+                    e["traffic_source"] = "profiles constant (profiles/r02_hbm_kernels.json: one ncu --set full capture), not measured in this run"
         except Exception:
             pass
 
@@ -466,14 +667,18 @@ def run_ours(args):
                 "d2h_bytes_per_step": int(B * 4), "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": int(launches),
         "roofline": roofline,
+        "roofline_hbm": roofline_hbm,
         "cpu_baseline": cpu,
         "clocks": clocks,
         "alg_tflops": value * F_GLOW * (args.K / 40.0) / 1e12,
+        "gate": {"log_prob_nats_per_dim": 1e-3, "measured": None if parity is None or "bf16" not in parity else parity["bf16"]["log_prob_err_nats_per_dim"]},
+        "sweep": sweep,
         "directions": directions,
         "basis": basis,
         "basis_ncsn": ncsn or None,
         "train": train,
-        "tc_cluster": args.cluster,
+        "strong": strong,
+        "parity": parity,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -488,9 +693,14 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--batch", type=int, default=2048, help="patches per GPU per step")
     ap.add_argument("--K", type=int, default=40, help="flow steps per block (40 = configs/melspec_glow.yml)")
-    ap.add_argument("--cluster", type=int, default=1, help="TMA-multicast cluster size of the tcgen05 kernel")
-    ap.add_argument("--basis-segments", type=int, default=256, help="segments per GPU of the BASIS leg (0 = skip)")
+    ap.add_argument("--sweep", type=str, default="30,32,256,4096", help="extra log_prob batch sizes (the headline batch is --batch)")
+    ap.add_argument("--modes", type=str, default="bf16,bf16x2,fp16x3", help="Glow precision modes of the inverse / grad_log_prob legs")
+    ap.add_argument("--basis-segments", type=str, default="30,256", help="segments per GPU of the Glow-BASIS legs ('' = skip)")
+    ap.add_argument("--basis-modes", type=str, default="bf16,fp16x3", help="Glow precision modes of the BASIS legs")
     ap.add_argument("--basis-T", type=int, default=2)
+    ap.add_argument("--no-parity", dest="parity", action="store_false", help="skip the in-run gate measurements")
+    ap.add_argument("--no-strong", dest="strong", action="store_false", help="skip the strong-scaling legs (N > 1)")
+    ap.add_argument("--ncsn-modes", type=str, default="bf16,bf16x3")
     ap.add_argument("--ncsn-segments", type=int, default=30, help="segments per GPU of the NCSN-BASIS legs (0 = skip)")
     ap.add_argument("--ncsn-T", type=int, default=2)
     ap.add_argument("--train-batch", type=int, default=32, help="per-GPU batch of the Glow train-step leg (0 = skip)")

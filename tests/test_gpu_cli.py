@@ -79,3 +79,33 @@ def test_run_basis_sep_ncsn_cli_runs(tmp_path):
     assert z["x1"].shape == (2, 96, 64) and np.all(np.isfinite(z["x1"])) and np.all(np.isfinite(z["x2"]))
     assert np.load(out / "results_convergence.npz")["x1"].shape == (4, 2, 96, 64, 1)
     assert res["duration_s"] > 0
+
+
+def test_ncsn_generate_samples_cli(tmp_path, capsys):
+    """The sampler CLI mirror (reference: ncsn_generate_samples.py:24-116): output file, shape [L+1, n, H, W, 1], value
+    range of the post-processing, the reference's print-outs; the final samples equal a direct call of the sampler."""
+    from audiosourcesep_b200.ncsn_generate_samples import build_parser, main
+    from audiosourcesep_b200.ncsn.utils import anneal_langevin_dynamics, get_sigmas, get_uncompiled_model_v2
+    out = tmp_path / "samples"
+    argv = [str(tmp_path / "ckpt"), "--filename", str(out), "--n_samples", "2", "--version", "v2", "--n_filters", "128",
+            "--T", "2", "--num_classes", "3", "--sigma1", "0.05", "--random_init", "3", "--seed", "4", "--fast"]
+    args = build_parser().parse_args(argv)
+    arr = main(args)
+    text = capsys.readouterr().out
+    for line in ("SAMPLING PARAMETERS", "Weights loaded", "Start Generating 2 samples....", "Done. Duration:", "Shape: (4, 2, 96, 64, 1)",
+                 "Generated Samples saved at"):
+        assert line in text, line
+    assert text.count("Sigma = ") == 3
+    saved = np.load(str(out) + ".npy")
+    assert saved.shape == (4, 2, 96, 64, 1) and np.array_equal(saved, arr)
+    assert saved.min() >= -100.0 and saved.max() <= 20.0 and np.all(np.isfinite(saved))
+    # direct call of the sampler with the same seeds
+    sig = get_sigmas(0.05, 0.01, 3)
+    ns = build_parser().parse_args(argv)
+    ns.data_shape = [96, 64, 1]
+    model = get_uncompiled_model_v2(ns, sigmas=sig, seed=3)
+    x0 = torch.rand([2, 96, 64, 1], generator=torch.Generator().manual_seed(4))
+    direct = anneal_langevin_dynamics(x0, [96, 64, 1], model, 2, sig, n_steps_each=2, step_lr=2e-5, seed=4)
+    want = np.clip(direct * 120.0 - 100.0, -100.0, 20.0)
+    np.testing.assert_allclose(saved[-1], want, rtol=0, atol=1e-4)
+
