@@ -110,6 +110,7 @@ _SIGNATURES = {
     "asep_conv_profile": [_I],
     "asep_conv_profile_read": [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64),
                                ctypes.POINTER(ctypes.c_double)],
+    "asep_crc32c": [ctypes.c_char_p, ctypes.c_uint64, ctypes.c_uint32],
     "asep_hbm_profile": [_I],
     "asep_hbm_profile_read": [_I, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64),
                               ctypes.POINTER(ctypes.c_double)],
@@ -117,8 +118,9 @@ _SIGNATURES = {
     "asep_tc_profile_read": [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64),
                              ctypes.POINTER(ctypes.c_double)],
 }
-_RESTYPES = {"asep_last_error": ctypes.c_char_p, "asep_abi_version": ctypes.c_int, "asep_launch_count": ctypes.c_int64}
-EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + list(_RESTYPES))
+_RESTYPES = {"asep_last_error": ctypes.c_char_p, "asep_abi_version": ctypes.c_int, "asep_launch_count": ctypes.c_int64,
+             "asep_crc32c": ctypes.c_uint32}
+EXPORTED_SYMBOLS = sorted(set(_SIGNATURES) | set(_RESTYPES))
 
 _lib = None
 _initialised_device: Optional[int] = None
@@ -140,7 +142,8 @@ def load() -> ctypes.CDLL:
         fn.restype = ctypes.c_int
     for name, res in _RESTYPES.items():
         fn = getattr(lib, name)
-        fn.argtypes = []
+        if name not in _SIGNATURES:
+            fn.argtypes = []
         fn.restype = res
     _lib = lib
     return lib

@@ -816,6 +816,37 @@ int asep_conv_profile_read(double* total_ms, int64_t* launches, double* flops) {
   ASEP_API_END
 }
 
+// CRC-32C (Castagnoli), slicing-by-8, host only: checksums of the TensorFlow checkpoint interchange
+// (audiosourcesep_b200/tf_checkpoint.py; the TensorBundle format stores a masked crc32c per tensor and per index block).
+uint32_t asep_crc32c(const void* data, uint64_t n, uint32_t crc) {
+  static uint32_t tab[8][256];
+  static bool init = false;
+  if (!init) {
+    for (uint32_t i = 0; i < 256; ++i) {
+      uint32_t c = i;
+      for (int k = 0; k < 8; ++k) c = (c & 1u) ? (c >> 1) ^ 0x82F63B78u : c >> 1;
+      tab[0][i] = c;
+    }
+    for (uint32_t i = 0; i < 256; ++i)
+      for (int t = 1; t < 8; ++t) tab[t][i] = (tab[t - 1][i] >> 8) ^ tab[0][tab[t - 1][i] & 0xFFu];
+    init = true;
+  }
+  const uint8_t* p = static_cast<const uint8_t*>(data);
+  uint32_t c = crc ^ 0xFFFFFFFFu;
+  while (n >= 8) {
+    uint32_t lo, hi;
+    std::memcpy(&lo, p, 4);
+    std::memcpy(&hi, p + 4, 4);
+    lo ^= c;
+    c = tab[7][lo & 0xFFu] ^ tab[6][(lo >> 8) & 0xFFu] ^ tab[5][(lo >> 16) & 0xFFu] ^ tab[4][lo >> 24] ^
+        tab[3][hi & 0xFFu] ^ tab[2][(hi >> 8) & 0xFFu] ^ tab[1][(hi >> 16) & 0xFFu] ^ tab[0][hi >> 24];
+    p += 8;
+    n -= 8;
+  }
+  while (n--) c = tab[0][(c ^ *p++) & 0xFFu] ^ (c >> 8);
+  return c ^ 0xFFFFFFFFu;
+}
+
 int asep_hbm_profile(int on) {
   ASEP_API_BEGIN
   hbm_profile(on != 0);

@@ -214,13 +214,25 @@ def load_song_patches(args):
     return arrs[0], arrs[1], arrs[2], stft
 
 
-def _npz_loader(root: str) -> Callable[[float], Optional[Dict[str, np.ndarray]]]:
-    def load(sigma: float):
-        path = os.path.join(root, "sigma_" + str(round(sigma, 2)), "weights.npz")     # run_basis_sep.py:284-285
-        if not os.path.exists(path):
-            raise FileNotFoundError(path)
+def load_weights(directory: str, shapes: Dict[str, tuple]) -> Dict[str, np.ndarray]:
+    """Weights of one model: ``<directory>/weights.npz`` (this package's container) or, failing that, the TensorFlow
+    checkpoint the reference writes -- ``<directory>/tf_ckpts/ckpt-N`` or ``<directory>/ckpt-N``
+    (tf.train.Checkpoint(variables=model.variables, ...), train_utils.py:62-75; read by tf_checkpoint.py)."""
+    path = os.path.join(directory, "weights.npz")
+    if os.path.exists(path):
         with np.load(path) as z:
             return {k: z[k] for k in z.files}
+    from . import tf_checkpoint
+    for d in (os.path.join(directory, "tf_ckpts"), directory):
+        prefix = tf_checkpoint.latest_checkpoint(d)
+        if prefix is not None:
+            return tf_checkpoint.import_variables(prefix, shapes)
+    raise FileNotFoundError(f"{directory}: neither weights.npz nor a TensorFlow checkpoint (tf_ckpts/ckpt-N.index)")
+
+
+def _npz_loader(root: str, shapes: Dict[str, tuple]) -> Callable[[float], Optional[Dict[str, np.ndarray]]]:
+    def load(sigma: float):
+        return load_weights(os.path.join(root, "sigma_" + str(round(sigma, 2))), shapes)        # run_basis_sep.py:284-285
     return load
 
 
@@ -259,7 +271,8 @@ def build_models(args, sigmas, device_index: int):
                 params = init_glow_params(cfg, seed=int(args.random_init) + i, mode="perturbed")
                 ckpts.append(None)
             else:
-                ckpts.append(_npz_loader(os.path.abspath(restore)))
+                from .weights import glow_param_shapes
+                ckpts.append(_npz_loader(os.path.abspath(restore), glow_param_shapes(cfg)))
                 params = ckpts[-1](float(sigmas[0]))
             models.append(build_glow(None, [args.height, args.width, 1], L=args.L, K=args.K, n_filters=args.n_filters,
                                      learntop=args.learntop, l2_reg=args.l2_reg, data_type="melspec", minval=0.0,
@@ -270,8 +283,9 @@ def build_models(args, sigmas, device_index: int):
     for i, restore in enumerate((args.RESTORE1, args.RESTORE2)):
         params = None
         if args.random_init is None:
-            with np.load(os.path.join(os.path.abspath(restore), "weights.npz")) as z:
-                params = {k: z[k] for k in z.files}
+            from .ncsn.utils import _ncsn_cfg
+            from .weights import ncsn_param_shapes
+            params = load_weights(os.path.abspath(restore), ncsn_param_shapes(_ncsn_cfg(args, args.version)))
         if args.version == "v1":
             builders.append(get_uncompiled_model(args, name=f"model{i + 1}", params=params,
                                                  seed=None if args.random_init is None else int(args.random_init) + i))

@@ -224,6 +224,10 @@ int asep_basis_ncsn_run(asep_ncsn_t m1, asep_ncsn_t m2, const DLTensor* mixed, D
 int asep_conv_profile(int on);
 int asep_conv_profile_read(double* total_ms, int64_t* launches, double* flops);
 
+/* CRC-32C (Castagnoli) of a HOST buffer, continuing from `crc` (0 to start): the checksum of the TensorFlow checkpoint
+ * (TensorBundle) files tf.train.Checkpoint writes (train_utils.py:62-75), used by audiosourcesep_b200/tf_checkpoint.py. */
+uint32_t asep_crc32c(const void* data, uint64_t n, uint32_t crc);
+
 /* Measurement aid for the HBM-bound kernels (bench.py `roofline_hbm`): while on, every launch of a profiled category is
  * bracketed by a CUDA event pair on its own stream.  Categories: 0 fused flow step (ActNorm + 1x1 + coupling + log-det,
  * flow_tfp_bijectors.py:134-153,242-253,299-322), 1 fused Langevin update (run_basis_sep.py:163-181), 2 score-network
