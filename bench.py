@@ -230,7 +230,7 @@ def parity_block(models_by_mode, torch, ops, bo, synthetic, D):
         r["round_trip_max_abs"] = float((m1.inverse(z) - t1).abs().max().item())        # states are normalised units
         g_fn, gg_fn = None, None
         step = {}
-        for idx in (0, 1, 4, 9):
+        for idx in (0, 1, 2, 4, 9):
             eta, lam, ns = bo.langevin_step_constants(sig, idx)
             rng = np.random.Generator(np.random.PCG64(100 + idx))
             n1, n2 = (rng.standard_normal(x1.shape).astype(np.float32) for _ in range(2))
@@ -246,7 +246,7 @@ def parity_block(models_by_mode, torch, ops, bo, synthetic, D):
                                                  torch.linalg.norm(a2 - e2) / torch.linalg.norm(e2)).item())
         r["langevin_step_state_rel_err"] = step
         r["gates_met"] = {"log_prob": r["log_prob_err_nats_per_dim"] <= 1e-3, "round_trip": r["round_trip_max_abs"] <= 1e-4,
-                          "langevin_step_at_sigma_idx": [i for i in (0, 1, 4, 9) if step[f"sigma_idx_{i}"] <= 1e-3]}
+                          "langevin_step_at_sigma_idx": [i for i in (0, 1, 2, 4, 9) if step[f"sigma_idx_{i}"] <= 1e-3]}
         out[mode] = r
     return out
 
