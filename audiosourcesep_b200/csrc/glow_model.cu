@@ -145,9 +145,8 @@ GlowModel::~GlowModel() {
   if (tg_ev_out_) cudaEventDestroy(tg_ev_out_);
   for (void* p : {(void*)tg_x_, (void*)tg_noise_, (void*)tg_grads_, (void*)tg_loss_})
     if (p) cudaFree(p);
-  for (void* p : {(void*)theta_, (void*)adam_m_, (void*)adam_u_, (void*)tq2_, (void*)tdc2_, (void*)tr3_, (void*)ts3_,
-                  (void*)tstats_, (void*)ldc_, (void*)ld_total_, (void*)tdc1_, (void*)td1_, (void*)da1_, (void*)da2_,
-                  (void*)dgp2_, (void*)dgp1_, (void*)dcol_})
+  for (void* p : {(void*)theta_, (void*)adam_m_, (void*)adam_u_, (void*)tscratch_, (void*)ldc_, (void*)ld_total_,
+                  (void*)da1_, (void*)da2_, (void*)dgp2_, (void*)dgp1_, (void*)dcol_})
     if (p) cudaFree(p);
   for (auto& s : steps_) {
     for (float* p : {s.sc, s.g1, s.b1, s.g2, s.b2, s.k2t})
@@ -330,8 +329,8 @@ void GlowModel::latent_slice(int b, int& Cz, int& nb, int& coff) const {
 }
 
 // ------------------------------------------------------------------ workspace
-void GlowModel::ensure_work(int N, bool save) {
-  if (work_.N >= N && (work_.save || !save) && work_.N > 0) return;
+void GlowModel::ensure_work(int N, bool save, bool dumps) {
+  if (work_.N >= N && (work_.save || !save) && (work_.dumps || !dumps) && work_.N > 0) return;
   const int L = cfg_.L, K = cfg_.K, F = cfg_.n_filters;
   const bool fp32 = precision_ == ASEP_PREC_FP32;
   const long long M0 = (long long)N * levels_[0].H * levels_[0].W;
@@ -339,6 +338,9 @@ void GlowModel::ensure_work(int N, bool save) {
   double mask_bytes = 0.0;
   for (int b = 0; b < L; ++b) mask_bytes += 2.0 * N * levels_[b].H * levels_[b].W * (F / 8.0) * K;
   const bool keep_masks = mask_bytes <= 48e9;
+  double dump_bytes = 0.0;
+  for (int b = 0; b < L; ++b) dump_bytes += 2.0 * N * levels_[b].H * levels_[b].W * (double)F * 2.0 * K;
+  dumps = dumps && save && !fp32 && keep_masks && dump_bytes <= 40e9;
   size_t bytes = 0;
   auto need = [&](size_t n) { bytes += (n + 255) & ~(size_t)255; };
   for (int pass = 0; pass < 2; ++pass) {
@@ -351,6 +353,8 @@ void GlowModel::ensure_work(int N, bool save) {
       work_.save = save;
       work_.X.resize(L); work_.O.resize(L); work_.U.resize(L); work_.R.resize(L);
       work_.M1.assign(L, {}); work_.M2.assign(L, {});
+      work_.D1.assign(L, {}); work_.D2.assign(L, {});
+      work_.dumps = dumps;
     }
     auto get = [&](size_t n_floats) -> float* {
       if (pass == 0) { need(n_floats * sizeof(float)); return nullptr; }
@@ -371,6 +375,14 @@ void GlowModel::ensure_work(int N, bool save) {
           uint32_t* m1 = reinterpret_cast<uint32_t*>(get(mw));
           uint32_t* m2 = reinterpret_cast<uint32_t*>(get(mw));
           if (pass == 1) { work_.M1[b].push_back(m1); work_.M2[b].push_back(m2); }
+        }
+      }
+      if (dumps) {
+        const size_t dn = (size_t)N * levels_[b].H * levels_[b].W * F / 2;          // bf16 elements, counted in floats
+        for (int i = 0; i < K; ++i) {
+          __nv_bfloat16* d1 = reinterpret_cast<__nv_bfloat16*>(get(dn));
+          __nv_bfloat16* d2 = reinterpret_cast<__nv_bfloat16*>(get(dn));
+          if (pass == 1) { work_.D1[b].push_back(d1); work_.D2[b].push_back(d2); }
         }
       }
     }
@@ -414,8 +426,13 @@ void GlowModel::nn_forward(int b, int k, const float* state, float* r, int N, bo
   } else {
     uint32_t *m1 = nullptr, *m2 = nullptr;
     if (save && !work_.M1.empty() && !work_.M1[b].empty()) { m1 = work_.M1[b][k]; m2 = work_.M2[b][k]; }
-    if (is_tcx()) nn_tcx_forward(sd.wtc, work_.tc, state, r, m1, m2, N, lv.H, lv.W, lv.C, s);
-    else nn_tc_forward(sd.wtc, work_.tc, state, r, m1, m2, N, lv.H, lv.W, lv.C, s);
+    if (is_tcx()) {
+      nn_tcx_forward(sd.wtc, work_.tc, state, r, m1, m2, N, lv.H, lv.W, lv.C, s);
+    } else {
+      __nv_bfloat16 *d1 = nullptr, *d2 = nullptr;
+      if (save && dumping_ && !work_.D1[b].empty()) { d1 = work_.D1[b][k]; d2 = work_.D2[b][k]; }
+      nn_tc_forward(sd.wtc, work_.tc, state, r, m1, m2, N, lv.H, lv.W, lv.C, s, d1, d2);
+    }
   }
 }
 
@@ -449,9 +466,10 @@ void GlowModel::nn_backward(int b, int k, const float* state, const float* gr, f
 // ------------------------------------------------------------------ forward pass
 // Leaves: work_.z (latent), work_.acc_ld (sum of data-dependent log-dets).  save=true keeps every
 // step's coupling input u and network output r for the backward pass.
-void GlowModel::run_forward(const float* x, int N, bool save, cudaStream_t s) {
+void GlowModel::run_forward(const float* x, int N, bool save, cudaStream_t s, bool dumps) {
   require_prepared();
-  ensure_work(N, save);
+  ensure_work(N, save, dumps);
+  dumping_ = dumps && work_.dumps;            // only the training forward writes the activation copies
   const int L = cfg_.L, K = cfg_.K;
   CUDA_CHECK(cudaMemsetAsync(work_.acc_ld, 0, 2 * (size_t)work_.N * sizeof(double), s));
   // SpecPreprocessing + first squeeze
@@ -484,6 +502,7 @@ void GlowModel::run_forward(const float* x, int N, bool save, cudaStream_t s) {
     float* next = b + 1 < L ? work_.X[b + 1] : nullptr;
     launch_split_merge(work_.O[b], work_.z, next, N, lv.H, lv.W, lv.C, Cz, nb, CL_, coff, Dl_, 0, s);
   }
+  dumping_ = false;
 }
 
 float* GlowModel::score_scratch(int N, int slots) {

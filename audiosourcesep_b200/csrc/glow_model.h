@@ -99,14 +99,18 @@ class GlowModel {
     std::vector<float*> X, O;               // per level: block input / output state
     std::vector<std::vector<float*>> U, R;  // per level, per step (save) or 2 ping-pong / 1 (no save)
     std::vector<std::vector<uint32_t*>> M1, M2;   // tcgen05 path, save: ReLU bit masks of every step (no recompute in backward)
+    // training on the tcgen05 path: bf16 copies of relu(p1), relu(p2) of every step, written by the forward pass, so that
+    // the weight-gradient GEMMs need no second forward evaluation (kept while they fit in 40 GB)
+    std::vector<std::vector<__nv_bfloat16*>> D1, D2;
+    bool dumps = false;
     float *z = nullptr, *gz = nullptr, *gA = nullptr, *gB = nullptr, *gr = nullptr, *gu = nullptr, *gxb = nullptr;
     double *acc_ld = nullptr, *acc_prior = nullptr;
     float *a1 = nullptr, *a2 = nullptr, *t1 = nullptr, *t2 = nullptr;   // fp32 NN scratch
     NNScratchTC tc{};
   };
-  void ensure_work(int N, bool save);
+  void ensure_work(int N, bool save, bool dumps = false);
   StepDerived& step(int b, int k) { return steps_[(size_t)b * cfg_.K + k]; }
-  void run_forward(const float* x, int N, bool save, cudaStream_t s);
+  void run_forward(const float* x, int N, bool save, cudaStream_t s, bool dumps = false);
   void nn_forward(int b, int k, const float* state, float* r, int N, bool save, cudaStream_t s);
   void nn_backward(int b, int k, const float* state, const float* gr, float* gxb, int N, cudaStream_t s);
   bool fused_gather(int b) const;                           // col2im of the tensor-core network fused into the flow-step kernels
@@ -120,6 +124,7 @@ class GlowModel {
   void derive_on_device(cudaStream_t s);
   StepRefresh* refresh_table_ = nullptr;     // device rows of the batched refresh (glow_train.cu)
   bool refresh_dirty_ = true;
+  bool dumping_ = false;                     // run_forward is writing the training activation copies (Work::D1 / D2)
   StepTrainPtrs step_ptrs(int b, int k);
   std::vector<std::string> order_;          // parameter names in construction order
   float *theta_ = nullptr, *adam_m_ = nullptr, *adam_u_ = nullptr;
@@ -150,6 +155,8 @@ class GlowModel {
   cudaEvent_t tg_ev_in_ = nullptr, tg_ev_out_ = nullptr;
   long long tg_calls_ = 0;      // largest batch size that has run eagerly (its scratch exists)
   double *tstats_ = nullptr, *ldc_ = nullptr, *ld_total_ = nullptr;
+  char* tscratch_ = nullptr;                 // one allocation behind tstats_, tq2_, tdc2_, tdc1_, tr3_, ts3_, td1_
+  size_t tscratch_bytes_ = 0;
   bool training_ = false;
 
   asep_glow_cfg cfg_;

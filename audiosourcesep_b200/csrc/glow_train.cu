@@ -44,13 +44,20 @@ void GlowModel::enable_training() {
     p.in_flat = true;
   }
   const int F = cfg_.n_filters;
-  CUDA_CHECK(cudaMalloc(&tq2_, (size_t)F * F * sizeof(float)));
-  CUDA_CHECK(cudaMalloc(&tdc2_, (size_t)F * sizeof(float)));
-  CUDA_CHECK(cudaMalloc(&tr3_, (size_t)9 * F * 64 * sizeof(float)));
-  CUDA_CHECK(cudaMalloc(&ts3_, (size_t)9 * 64 * sizeof(float)));
-  CUDA_CHECK(cudaMalloc(&tdc1_, (size_t)F * sizeof(float)));
-  CUDA_CHECK(cudaMalloc(&td1_, (size_t)F * 256 * sizeof(float)));
-  CUDA_CHECK(cudaMalloc(&tstats_, (size_t)(2 * 64 + 64 * 64) * sizeof(double)));
+  {
+    // one block for every per-step accumulator, so that a single memset clears them (doubles first: alignment)
+    const size_t n_stats = (size_t)(2 * 64 + 64 * 64), n_q2 = (size_t)F * F, n_dc = (size_t)F, n_r3 = (size_t)9 * F * 64,
+                 n_s3 = (size_t)9 * 64, n_d1 = (size_t)F * 256;
+    tscratch_bytes_ = n_stats * sizeof(double) + (n_q2 + 2 * n_dc + n_r3 + n_s3 + n_d1) * sizeof(float);
+    CUDA_CHECK(cudaMalloc(&tscratch_, tscratch_bytes_));
+    tstats_ = reinterpret_cast<double*>(tscratch_);
+    tq2_ = reinterpret_cast<float*>(tstats_ + n_stats);
+    tdc2_ = tq2_ + n_q2;
+    tdc1_ = tdc2_ + n_dc;
+    tr3_ = tdc1_ + n_dc;
+    ts3_ = tr3_ + n_r3;
+    td1_ = ts3_ + n_s3;
+  }
   CUDA_CHECK(cudaMalloc(&ldc_, steps_.size() * sizeof(double)));
   CUDA_CHECK(cudaMalloc(&ld_total_, sizeof(double)));
   adam_t_ = 0;
@@ -196,15 +203,15 @@ void GlowModel::train_grads_body(const float* x, const float* noise, float sigma
                                  float* loss, cudaStream_t s) {
   const int L = cfg_.L, K = cfg_.K, F = cfg_.n_filters;
   const float gs = -1.0f / (float)global_batch;      // loss = -sum log_prob / global_batch (train_glow.py:30-31)
-  ensure_work(N, true);
   const bool tc = is_tc();
+  ensure_work(N, true, tc);                 // tcgen05: the forward pass keeps bf16 copies of relu(p1), relu(p2) of every step
   if (tc) ensure_train_dumps((long long)N * levels_[0].H * levels_[0].W);
   const float* xin = x;
   if (noise != nullptr) {                              // train_noisy_glow.py:31-32: X + sigma*N(0,1) in raw data units
     launch_axpy(x, noise, sigma, work_.gB, (long long)N * cfg_.H * cfg_.W * cfg_.C, s);
     xin = work_.gB;
   }
-  run_forward(xin, N, true, s);
+  run_forward(xin, N, true, s, tc);
   // learntop = False: standard-normal prior without trainable parameters (flow_builder.py:143-144)
   const float* loc = cfg_.learntop ? params_.at("prior/loc").dev : nullptr;
   const float* ls = cfg_.learntop ? params_.at("prior/log_scale").dev : nullptr;
@@ -230,16 +237,13 @@ void GlowModel::train_grads_body(const float* x, const float* noise, float sigma
       StepDerived& sd = step(b, k);
       const StepTrainPtrs sp = step_ptrs(b, k);
       launch_bwd_coupling(gy, work_.U[b][k], work_.R[b][k], work_.gr, work_.gu, M, lv.C, s);
-      CUDA_CHECK(cudaMemsetAsync(tq2_, 0, (size_t)F * F * sizeof(float), s));
-      CUDA_CHECK(cudaMemsetAsync(tdc2_, 0, (size_t)F * sizeof(float), s));
-      CUDA_CHECK(cudaMemsetAsync(ts3_, 0, (size_t)9 * lv.C * sizeof(float), s));
-      CUDA_CHECK(cudaMemsetAsync(tstats_, 0, (size_t)(2 * lv.C + lv.C * lv.C) * sizeof(double), s));
+      // every per-step accumulator (Q2, dc2, R3, S3, D1, dc1, step statistics) lives in ONE block: one memset per step
+      CUDA_CHECK(cudaMemsetAsync(tscratch_, 0, tscratch_bytes_, s));
       if (!tc) {
         // recompute a1, a2 from the saved step input, then gp2 (t2), gp1 (t1), gxb
         nn_fp32_forward(sd.w32, work_.U[b][k], work_.a1, work_.a2, work_.gxb, N, lv.H, lv.W, lv.C, F, s);
         nn_fp32_backward(sd.w32, work_.a1, work_.a2, work_.gr, work_.t1, work_.t2, work_.gxb, N, lv.H, lv.W, lv.C, F, s);
         // ---- weight gradients of this step (CUDA-core fp32)
-        CUDA_CHECK(cudaMemsetAsync(tr3_, 0, (size_t)9 * F * lv.C * sizeof(float), s));
         launch_wgrad_tn(work_.a1, work_.t2, tq2_, M, F, s);
         launch_colsum(work_.t2, tdc2_, M, F, s);
         launch_wgrad_conv3(work_.a2, work_.gr, tr3_, ts3_, N, lv.H, lv.W, lv.C, F, s);
@@ -251,18 +255,20 @@ void GlowModel::train_grads_body(const float* x, const float* noise, float sigma
         const bool saved = !work_.M1.empty() && !work_.M1[b].empty();
         uint32_t* m1 = saved ? work_.M1[b][k] : work_.tc.mask1;
         uint32_t* m2 = saved ? work_.M2[b][k] : work_.tc.mask2;
-        nn_tc_forward(sd.wtc, work_.tc, work_.U[b][k], work_.gxb, saved ? nullptr : m1, saved ? nullptr : m2, N, lv.H,
-                      lv.W, lv.C, s, da1_, da2_);
+        // relu(p1), relu(p2) of this step: kept by the forward pass (work_.dumps) or recomputed from the saved step input
+        const bool kept = saved && work_.dumps && !work_.D1[b].empty();      // (written by this call's run_forward)
+        const __nv_bfloat16* a1 = kept ? work_.D1[b][k] : da1_;
+        const __nv_bfloat16* a2 = kept ? work_.D2[b][k] : da2_;
+        if (!kept)
+          nn_tc_forward(sd.wtc, work_.tc, work_.U[b][k], work_.gxb, saved ? nullptr : m1, saved ? nullptr : m2, N, lv.H,
+                        lv.W, lv.C, s, da1_, da2_);
         nn_tc_backward(sd.wtc, work_.tc, work_.gr, m1, m2, work_.gxb, N, lv.H, lv.W, lv.C, s, dgp2_, dgp1_);
         const int ld3 = (9 * lv.C + 63) / 64 * 64, ld1 = (9 * (lv.C / 2) + 63) / 64 * 64;
-        CUDA_CHECK(cudaMemsetAsync(tr3_, 0, (size_t)F * ld3 * sizeof(float), s));
-        CUDA_CHECK(cudaMemsetAsync(td1_, 0, (size_t)F * ld1 * sizeof(float), s));
-        CUDA_CHECK(cudaMemsetAsync(tdc1_, 0, (size_t)F * sizeof(float), s));
-        wgrad_tc(da1_, dgp2_, F, F, tq2_, F, M, s);                                   // Q2 = a1^T gp2
+        wgrad_tc(a1, dgp2_, F, F, tq2_, F, M, s);                                   // Q2 = a1^T gp2
         launch_colsum_bf16(dgp2_, tdc2_, M, F, s);
         launch_colsum_bf16(dgp1_, tdc1_, M, F, s);
         launch_im2col_gr(work_.gr, dcol_, N, lv.H, lv.W, lv.C, ld3, s);
-        wgrad_tc(da2_, dcol_, ld3, 9 * lv.C, tr3_, ld3, M, s);                         // R3t[k][tap,c]
+        wgrad_tc(a2, dcol_, ld3, 9 * lv.C, tr3_, ld3, M, s);                         // R3t[k][tap,c]
         launch_s3(work_.gr, ts3_, N, lv.H, lv.W, lv.C, s);
         launch_im2col_xb(work_.U[b][k], dcol_, N, lv.H, lv.W, lv.C, ld1, s);
         wgrad_tc(dgp1_, dcol_, ld1, 9 * (lv.C / 2), td1_, ld1, M, s);                  // D1t[f][tap,ci]

@@ -641,8 +641,10 @@ def run_ours(args):
             for e in roofline_hbm:
                 rec = hj.get(e["category"])
                 if rec:
-                    e["traffic"] = rec.get("dram_bytes_per_launch")
-                    e["traffic_source"] = "profiles constant (profiles/r02_hbm_kernels.json: one ncu --set full capture), not measured in this run"
+                    e["traffic"] = rec["traffic_over_algorithmic"] * e["algorithmic_bytes_per_launch"]
+                    e["traffic_source"] = ("profiles constant: dram__bytes_read+write / algorithmic bytes of one `ncu --set full` capture "
+                                           f"({rec['capture']}; profiles/r02_hbm_kernels.json) x the algorithmic bytes per launch of this run; "
+                                           "not measured in this run")
         except Exception:
             pass
 
