@@ -148,6 +148,14 @@ GlowModel::~GlowModel() {
   for (void* p : {(void*)theta_, (void*)adam_m_, (void*)adam_u_, (void*)tscratch_, (void*)ldc_, (void*)ld_total_,
                   (void*)da1_, (void*)da2_, (void*)dgp2_, (void*)dgp1_, (void*)dcol_})
     if (p) cudaFree(p);
+  for (TrainSlot& t : tslots_) {
+    for (void* p : {(void*)t.gp2, (void*)t.gp1, (void*)t.col, (void*)t.gr, (void*)t.gu, (void*)t.gxb, (void*)t.scratch})
+      if (p) cudaFree(p);
+    for (cudaEvent_t e : {t.ev_fork, t.ev_a, t.ev_join})
+      if (e) cudaEventDestroy(e);
+  }
+  for (cudaStream_t q : tside_)
+    if (q) cudaStreamDestroy(q);
   for (auto& s : steps_) {
     for (float* p : {s.sc, s.g1, s.b1, s.g2, s.b2, s.k2t})
       if (p) cudaFree(p);

@@ -132,6 +132,25 @@ class GlowModel {
   float *tq2_ = nullptr, *tdc2_ = nullptr, *tr3_ = nullptr, *ts3_ = nullptr, *tdc1_ = nullptr, *td1_ = nullptr;
   __nv_bfloat16 *da1_ = nullptr, *da2_ = nullptr, *dgp2_ = nullptr, *dgp1_ = nullptr, *dcol_ = nullptr;   // bf16 dumps / im2col
   long long dump_rows_ = 0;
+  // Ring of per-step backward buffers (tcgen05 training): the weight-gradient work of flow step k (GEMMs, column sums,
+  // im2col, statistics, finalize) runs on two side streams while the main stream already computes the data gradient of
+  // step k+1; a slot is reused once its side work has finished.  Everything the side work reads or accumulates into
+  // that the next step would overwrite lives in the slot.
+  static constexpr int kTrainRing = 4;
+  struct TrainSlot {
+    __nv_bfloat16 *gp2 = nullptr, *gp1 = nullptr, *col = nullptr;   // dL/dp2, dL/dp1 [rows, 512]; im2col scratch [rows, 256]
+    float *gr = nullptr, *gu = nullptr, *gxb = nullptr;              // [rows, C] coupling gradients of the step
+    char* scratch = nullptr;                                         // accumulators (layout of tscratch_)
+    double* stats = nullptr;
+    float *q2 = nullptr, *dc2 = nullptr, *dc1 = nullptr, *r3 = nullptr, *s3 = nullptr, *d1 = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_a = nullptr, ev_join = nullptr;
+    bool busy = false;
+  };
+  TrainSlot tslots_[kTrainRing];
+  cudaStream_t tside_[2] = {nullptr, nullptr};
+  long long slot_rows_ = 0;
+  void ensure_train_slots(long long rows);
+  void carve_scratch(char* base, TrainSlot& t) const;
   void ensure_train_dumps(long long rows);
   // The train step is ~5800 small launches at the reference's batch size (32): after a first eager call (which sizes
   // every scratch buffer) it is captured once per (N, global_batch, sigma, noisy) into a CUDA graph that works on

@@ -137,6 +137,51 @@ void GlowModel::ensure_train_dumps(long long rows) {
   dump_rows_ = rows;
 }
 
+void GlowModel::carve_scratch(char* base, TrainSlot& t) const {
+  const int F = cfg_.n_filters;
+  const size_t n_stats = (size_t)(2 * 64 + 64 * 64), n_q2 = (size_t)F * F, n_dc = (size_t)F, n_r3 = (size_t)9 * F * 64, n_s3 = (size_t)9 * 64;
+  t.scratch = base;
+  t.stats = reinterpret_cast<double*>(base);
+  t.q2 = reinterpret_cast<float*>(t.stats + n_stats);
+  t.dc2 = t.q2 + n_q2;
+  t.dc1 = t.dc2 + n_dc;
+  t.r3 = t.dc1 + n_dc;
+  t.s3 = t.r3 + n_r3;
+  t.d1 = t.s3 + n_s3;
+}
+
+void GlowModel::ensure_train_slots(long long rows) {
+  if (rows <= slot_rows_) return;
+  CUDA_CHECK(cudaDeviceSynchronize());
+  invalidate_graphs();
+  const int Cmax = levels_.back().C;
+  for (TrainSlot& t : tslots_) {
+    for (void* p : {(void*)t.gp2, (void*)t.gp1, (void*)t.col, (void*)t.gr, (void*)t.gu, (void*)t.gxb, (void*)t.scratch})
+      if (p) cudaFree(p);
+    const size_t n = (size_t)rows * cfg_.n_filters;
+    CUDA_CHECK(cudaMalloc(&t.gp2, n * sizeof(__nv_bfloat16)));
+    CUDA_CHECK(cudaMalloc(&t.gp1, n * sizeof(__nv_bfloat16)));
+    CUDA_CHECK(cudaMalloc(&t.col, (size_t)rows * 256 * sizeof(__nv_bfloat16)));
+    // [pixels of a level, C of that level] never exceeds rows * C_level0 floats (pixels shrink 4x per level, C grows 2x)
+    const size_t st = (size_t)rows * std::max(levels_[0].C, Cmax / 4 + 1);
+    CUDA_CHECK(cudaMalloc(&t.gr, st * sizeof(float)));
+    CUDA_CHECK(cudaMalloc(&t.gu, st * sizeof(float)));
+    CUDA_CHECK(cudaMalloc(&t.gxb, st * sizeof(float)));
+    char* sc = nullptr;
+    CUDA_CHECK(cudaMalloc(&sc, tscratch_bytes_));
+    carve_scratch(sc, t);
+    if (!t.ev_fork) {
+      CUDA_CHECK(cudaEventCreateWithFlags(&t.ev_fork, cudaEventDisableTiming));
+      CUDA_CHECK(cudaEventCreateWithFlags(&t.ev_a, cudaEventDisableTiming));
+      CUDA_CHECK(cudaEventCreateWithFlags(&t.ev_join, cudaEventDisableTiming));
+    }
+    t.busy = false;
+  }
+  for (cudaStream_t& q : tside_)
+    if (!q) CUDA_CHECK(cudaStreamCreateWithFlags(&q, cudaStreamNonBlocking));
+  slot_rows_ = rows;
+}
+
 void GlowModel::train_grads(const float* x, const float* noise, float sigma, int N, int global_batch, float* grads,
                             float* loss, cudaStream_t s) {
   ASEP_CHECK(training_, ASEP_ERR_STATE, "asep_glow_enable_training() has not been called");
@@ -205,7 +250,12 @@ void GlowModel::train_grads_body(const float* x, const float* noise, float sigma
   const float gs = -1.0f / (float)global_batch;      // loss = -sum log_prob / global_batch (train_glow.py:30-31)
   const bool tc = is_tc();
   ensure_work(N, true, tc);                 // tcgen05: the forward pass keeps bf16 copies of relu(p1), relu(p2) of every step
-  if (tc) ensure_train_dumps((long long)N * levels_[0].H * levels_[0].W);
+  if (tc) {
+    ensure_train_dumps((long long)N * levels_[0].H * levels_[0].W);
+    ensure_train_slots((long long)N * levels_[0].H * levels_[0].W);
+    for (TrainSlot& t : tslots_) t.busy = false;
+  }
+  int step_no = 0;
   const float* xin = x;
   if (noise != nullptr) {                              // train_noisy_glow.py:31-32: X + sigma*N(0,1) in raw data units
     launch_axpy(x, noise, sigma, work_.gB, (long long)N * cfg_.H * cfg_.W * cfg_.C, s);
@@ -236,9 +286,16 @@ void GlowModel::train_grads_body(const float* x, const float* noise, float sigma
     for (int k = 0; k < K; ++k) {
       StepDerived& sd = step(b, k);
       const StepTrainPtrs sp = step_ptrs(b, k);
-      launch_bwd_coupling(gy, work_.U[b][k], work_.R[b][k], work_.gr, work_.gu, M, lv.C, s);
+      // tcgen05 path: this step's buffers come from the ring (its side work may still be running when the next step starts)
+      TrainSlot* slot = tc ? &tslots_[step_no % kTrainRing] : nullptr;
+      ++step_no;
+      if (slot && slot->busy) CUDA_CHECK(cudaStreamWaitEvent(s, slot->ev_join, 0));
+      float* gr_k = slot ? slot->gr : work_.gr;
+      float* gu_k = slot ? slot->gu : work_.gu;
+      float* gxb_k = slot ? slot->gxb : work_.gxb;
+      launch_bwd_coupling(gy, work_.U[b][k], work_.R[b][k], gr_k, gu_k, M, lv.C, s);
       // every per-step accumulator (Q2, dc2, R3, S3, D1, dc1, step statistics) lives in ONE block: one memset per step
-      CUDA_CHECK(cudaMemsetAsync(tscratch_, 0, tscratch_bytes_, s));
+      CUDA_CHECK(cudaMemsetAsync(slot ? slot->scratch : tscratch_, 0, tscratch_bytes_, s));
       if (!tc) {
         // recompute a1, a2 from the saved step input, then gp2 (t2), gp1 (t1), gxb
         nn_fp32_forward(sd.w32, work_.U[b][k], work_.a1, work_.a2, work_.gxb, N, lv.H, lv.W, lv.C, F, s);
@@ -262,25 +319,45 @@ void GlowModel::train_grads_body(const float* x, const float* noise, float sigma
         if (!kept)
           nn_tc_forward(sd.wtc, work_.tc, work_.U[b][k], work_.gxb, saved ? nullptr : m1, saved ? nullptr : m2, N, lv.H,
                         lv.W, lv.C, s, da1_, da2_);
-        nn_tc_backward(sd.wtc, work_.tc, work_.gr, m1, m2, work_.gxb, N, lv.H, lv.W, lv.C, s, dgp2_, dgp1_);
+        // main stream: data gradient of the network; the gradients of this step's weights are left to the side streams
+        nn_tc_backward(sd.wtc, work_.tc, slot->gr, m1, m2, slot->gxb, N, lv.H, lv.W, lv.C, s, slot->gp2, slot->gp1);
+        CUDA_CHECK(cudaEventRecord(slot->ev_fork, s));
         const int ld3 = (9 * lv.C + 63) / 64 * 64, ld1 = (9 * (lv.C / 2) + 63) / 64 * 64;
-        wgrad_tc(a1, dgp2_, F, F, tq2_, F, M, s);                                   // Q2 = a1^T gp2
-        launch_colsum_bf16(dgp2_, tdc2_, M, F, s);
-        launch_colsum_bf16(dgp1_, tdc1_, M, F, s);
-        launch_im2col_gr(work_.gr, dcol_, N, lv.H, lv.W, lv.C, ld3, s);
-        wgrad_tc(a2, dcol_, ld3, 9 * lv.C, tr3_, ld3, M, s);                         // R3t[k][tap,c]
-        launch_s3(work_.gr, ts3_, N, lv.H, lv.W, lv.C, s);
-        launch_im2col_xb(work_.U[b][k], dcol_, N, lv.H, lv.W, lv.C, ld1, s);
-        wgrad_tc(dgp1_, dcol_, ld1, 9 * (lv.C / 2), td1_, ld1, M, s);                  // D1t[f][tap,ci]
-        launch_step_stats(work_.gu, work_.gxb, work_.U[b][k], sd.sc, tstats_, M, lv.C, s);
-        launch_finalize_step_tc(sp, tq2_, tdc2_, tr3_, ld3, ts3_, td1_, ld1, tdc1_, tstats_, grads, (double)M, gs, s);
+        cudaStream_t qa = tside_[0], qb = tside_[1];
+        // side A: Q2 = a1^T gp2 and the two bias gradients
+        CUDA_CHECK(cudaStreamWaitEvent(qa, slot->ev_fork, 0));
+        wgrad_tc(a1, slot->gp2, F, F, slot->q2, F, M, qa);
+        launch_colsum_bf16(slot->gp2, slot->dc2, M, F, qa);
+        launch_colsum_bf16(slot->gp1, slot->dc1, M, F, qa);
+        CUDA_CHECK(cudaEventRecord(slot->ev_a, qa));
+        // side B: conv3 / conv1 weight gradients, the element-wise statistics, then the chain rule into `grads`
+        CUDA_CHECK(cudaStreamWaitEvent(qb, slot->ev_fork, 0));
+        launch_im2col_gr(slot->gr, slot->col, N, lv.H, lv.W, lv.C, ld3, qb);
+        wgrad_tc(a2, slot->col, ld3, 9 * lv.C, slot->r3, ld3, M, qb);                  // R3t[k][tap,c]
+        launch_s3(slot->gr, slot->s3, N, lv.H, lv.W, lv.C, qb);
+        launch_im2col_xb(work_.U[b][k], slot->col, N, lv.H, lv.W, lv.C, ld1, qb);
+        wgrad_tc(slot->gp1, slot->col, ld1, 9 * (lv.C / 2), slot->d1, ld1, M, qb);     // D1t[f][tap,ci]
+        launch_step_stats(slot->gu, slot->gxb, work_.U[b][k], sd.sc, slot->stats, M, lv.C, qb);
+        CUDA_CHECK(cudaStreamWaitEvent(qb, slot->ev_a, 0));
+        launch_finalize_step_tc(sp, slot->q2, slot->dc2, slot->r3, ld3, slot->s3, slot->d1, ld1, slot->dc1, slot->stats, grads,
+                                (double)M, gs, qb);
+        CUDA_CHECK(cudaEventRecord(slot->ev_join, qb));
+        slot->busy = true;
+        if (!kept) {            // recomputed activations live in ONE scratch pair: the next step may not overwrite them early
+          CUDA_CHECK(cudaStreamWaitEvent(s, slot->ev_join, 0));
+          slot->busy = false;
+        }
       }
       // ---- data gradient to the previous step
-      launch_bwd_pre(work_.gu, work_.gxb, other, sd.sc, M, lv.C, s);
+      launch_bwd_pre(gu_k, gxb_k, other, sd.sc, M, lv.C, s);
       std::swap(gy, other);
     }
     gX_next = gy;
   }
+  // join: the gradient vector is complete once every side stream has drained (also required to end a stream capture)
+  if (tc)
+    for (TrainSlot& t : tslots_)
+      if (t.busy) { CUDA_CHECK(cudaStreamWaitEvent(s, t.ev_join, 0)); t.busy = false; }
 }
 
 void GlowModel::adamax_step(const float* grads, float lr, float beta1, float beta2, float eps, cudaStream_t s) {
