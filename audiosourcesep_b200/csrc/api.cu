@@ -2,6 +2,7 @@
 // cross as status codes + asep_last_error().
 #include <cstdarg>
 #include <cstring>
+#include <map>
 #include <memory>
 
 #include <vector>
@@ -36,6 +37,7 @@ HbmScope::~HbmScope() {
   cudaEventRecord(r->b, s_);
   g_hbm_recs.push_back(r);
 }
+bool hbm_profile_enabled() { return g_hbm_on; }
 void hbm_profile(bool on) {
   g_hbm_on = on;
   if (on) {
@@ -557,6 +559,47 @@ int asep_philox_normal(DLTensor* out, uint64_t seed, uint64_t step, uint64_t str
   ASEP_API_END
 }
 
+}  // extern "C" (re-opened below)
+
+namespace {
+// ---- CUDA graphs of one whole Glow-BASIS Langevin step (both scores + the fused update), replayed for steps 2..T of a
+// call.  A graph bakes in the state / noise / dump pointers of the call and the workspaces of both priors, so it is
+// keyed by all of them plus each prior's (uid, generation); per-step scalars are read from `dev` (LangevinDev).
+struct BasisGraphKey {
+  const void* p[9];
+  long long m1, m2, g1, g2;
+  unsigned long long seed, off;
+  int N, pad;
+  bool operator<(const BasisGraphKey& o) const { return std::memcmp(this, &o, sizeof(*this)) < 0; }
+};
+struct BasisGraph { cudaGraphExec_t exec = nullptr; long long launches = 0; };
+struct BasisGraphs {
+  std::map<BasisGraphKey, BasisGraph> graphs;
+  cudaStream_t stream = nullptr;                    // private: the caller's stream may be the legacy stream (not capturable)
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+  LangevinDev* dev = nullptr;
+  void ensure() {
+    if (stream) return;
+    CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventCreateWithFlags(&ev_out, cudaEventDisableTiming));
+    CUDA_CHECK(cudaMalloc(&dev, sizeof(LangevinDev)));
+  }
+  void clear() {
+    if (stream) cudaStreamSynchronize(stream);
+    for (auto& kv : graphs)
+      if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    graphs.clear();
+  }
+};
+BasisGraphs& basis_graphs() {
+  static BasisGraphs g;
+  return g;
+}
+}  // namespace
+
+extern "C" {
+
 int asep_basis_glow_inner(asep_glow_t m1, asep_glow_t m2, const DLTensor* mixed, DLTensor* x1, DLTensor* x2, int T,
                           float eta, float lambda, float noise_scale, const DLTensor* noise1, const DLTensor* noise2,
                           uint64_t seed, uint64_t step0, uint64_t elem_offset, DLTensor* per_step,
@@ -590,7 +633,7 @@ int asep_basis_glow_inner(asep_glow_t m1, asep_glow_t m2, const DLTensor* mixed,
   const bool same = &g1 == &g2;
   float* s1 = g1.score_scratch(N, same ? 2 : 1);
   float* s2 = same ? s1 + a.numel : g2.score_scratch(N);
-  for (int t = 0; t < T; ++t) {
+  auto eager_step = [&](int t) {
     g1.grad_log_prob(a.f32, s1, nullptr, N, s);     // run_basis_sep.py:174-175
     g2.grad_log_prob(b.f32, s2, nullptr, N, s);
     launch_langevin(a.f32, b.f32, s1, s2, mx.f32, nz1 ? nz1 + (size_t)t * a.numel : nullptr,
@@ -602,6 +645,55 @@ int asep_basis_glow_inner(asep_glow_t m1, asep_glow_t m2, const DLTensor* mixed,
       CUDA_CHECK(cudaMemcpyAsync(dump + (size_t)(2 * t + 1) * a.numel, b.f32, (size_t)a.numel * sizeof(float),
                                  cudaMemcpyDeviceToDevice, s));
     }
+  };
+  // One Langevin step is ~1200 small launches at the reference's n_mixed = 30: from the third step on the whole step (both
+  // scores + the fused update) is replayed as ONE CUDA graph whose per-step scalars live in device memory.
+  static const bool no_graph = getenv("ASEP_NO_GRAPH") != nullptr;
+  const bool use_graph = T >= 3 && !no_graph && !nn_tc_profile_enabled() && !hbm_profile_enabled();
+  if (!use_graph) {
+    for (int t = 0; t < T; ++t) eager_step(t);
+  } else {
+    eager_step(0);                                   // sizes both workspaces (a capture may not allocate)
+    BasisGraphs& bg = basis_graphs();
+    bg.ensure();
+    CUDA_CHECK(cudaEventRecord(bg.ev_in, s));
+    CUDA_CHECK(cudaStreamWaitEvent(bg.stream, bg.ev_in, 0));
+    LangevinDev h{eta, lambda, noise_scale, 0.f, step0 + 1, 1ull};
+    CUDA_CHECK(cudaMemcpyAsync(bg.dev, &h, sizeof(h), cudaMemcpyHostToDevice, bg.stream));   // pageable source: staged at once
+    BasisGraphKey key{};
+    const void* ptrs[9] = {a.f32, b.f32, mx.f32, nz1, nz2, dump, nanp, s1, s2};
+    std::memcpy(key.p, ptrs, sizeof(ptrs));
+    key.N = N; key.seed = seed; key.off = elem_offset;
+    key.m1 = g1.uid(); key.m2 = g2.uid(); key.g1 = g1.generation(); key.g2 = g2.generation();
+    auto it = bg.graphs.find(key);
+    if (it == bg.graphs.end()) {
+      if (bg.graphs.size() >= 16) bg.clear();
+      cudaGraph_t graph = nullptr;
+      const long long c0 = g_launch_count.load();
+      CUDA_CHECK(cudaStreamBeginCapture(bg.stream, cudaStreamCaptureModeRelaxed));
+      try {
+        g1.grad_log_prob(a.f32, s1, nullptr, N, bg.stream);
+        g2.grad_log_prob(b.f32, s2, nullptr, N, bg.stream);
+        launch_langevin_dev(a.f32, b.f32, s1, s2, mx.f32, nz1, nz2, dump, bg.dev, seed, elem_offset, nanp, a.numel, bg.stream);
+      } catch (...) {
+        cudaStreamEndCapture(bg.stream, &graph);
+        if (graph) cudaGraphDestroy(graph);
+        throw;
+      }
+      CUDA_CHECK(cudaStreamEndCapture(bg.stream, &graph));
+      BasisGraph g;
+      g.launches = g_launch_count.load() - c0;
+      g_launch_count.fetch_sub(g.launches);          // a capture launches nothing
+      CUDA_CHECK(cudaGraphInstantiate(&g.exec, graph, 0));
+      CUDA_CHECK(cudaGraphDestroy(graph));
+      it = bg.graphs.emplace(key, g).first;
+    }
+    for (int t = 1; t < T; ++t) {
+      CUDA_CHECK(cudaGraphLaunch(it->second.exec, bg.stream));
+      g_launch_count.fetch_add(it->second.launches);
+    }
+    CUDA_CHECK(cudaEventRecord(bg.ev_out, bg.stream));
+    CUDA_CHECK(cudaStreamWaitEvent(s, bg.ev_out, 0));
   }
   ASEP_API_END
 }

@@ -63,6 +63,7 @@ struct HbmScope {
   int cat_; cudaStream_t s_; void* rec_;
 };
 void hbm_profile(bool on);
+bool hbm_profile_enabled();
 void hbm_profile_read(int cat, double* ms, long long* launches, double* bytes);
 
 // ---- DLTensor validation

@@ -73,7 +73,10 @@ constexpr double kBnEps = 1e-3;  // Keras BatchNormalization epsilon
 }  // namespace
 
 // ------------------------------------------------------------------ construction
+namespace { std::atomic<long long> g_next_uid{1}; }
+
 GlowModel::GlowModel(const asep_glow_cfg& cfg, int device) : cfg_(cfg), device_(device) {
+  uid_ = g_next_uid.fetch_add(1);
   ASEP_CHECK(cfg.L >= 2 && cfg.L <= 4, ASEP_ERR_BAD_ARG, "L should be 2, 3 or 4");   // flow_builder.py:77-78
   ASEP_CHECK(cfg.K >= 1 && cfg.n_filters >= 1 && cfg.C >= 1, ASEP_ERR_BAD_ARG, "bad K / n_filters / C");
   const int s = 1 << cfg.L;
@@ -237,6 +240,7 @@ void GlowModel::build_step_consts(int b, int k) {
 }
 
 void GlowModel::invalidate_graphs() {
+  ++generation_;                             // graphs captured elsewhere (api.cu: BASIS step graphs) are keyed by this
   if (tgraph_.exec) {
     cudaDeviceSynchronize();                 // a replay may still be in flight on the private stream
     cudaGraphExecDestroy(tgraph_.exec);

@@ -91,6 +91,10 @@ class GlowModel {
   const Level& level(int b) const { return levels_[b]; }
   int latent_dims() const { return Dl_; }
   int precision() const { return precision_; }
+  // identity of the device allocations a captured graph of this model's kernels would bake in: a process-unique id of
+  // the handle and a counter that advances whenever the workspace, the per-step constants or the tile images move
+  long long uid() const { return uid_; }
+  long long generation() const { return generation_; }
 
  private:
   struct Work {
@@ -124,6 +128,7 @@ class GlowModel {
   void derive_on_device(cudaStream_t s);
   StepRefresh* refresh_table_ = nullptr;     // device rows of the batched refresh (glow_train.cu)
   bool refresh_dirty_ = true;
+  long long uid_ = 0, generation_ = 0;
   bool dumping_ = false;                     // run_forward is writing the training activation copies (Work::D1 / D2)
   StepTrainPtrs step_ptrs(int b, int k);
   std::vector<std::string> order_;          // parameter names in construction order

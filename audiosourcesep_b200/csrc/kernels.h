@@ -73,6 +73,17 @@ void launch_chanmix(const float* x, const float* w, float* y, long long M, int C
 void launch_langevin(float* x1, float* x2, const float* s1, const float* s2, const float* mixed, const float* n1,
                      const float* n2, float eta, float lambda, float noise_scale, uint64_t seed, uint64_t step,
                      uint64_t elem_offset, int* nan_count, long long n, cudaStream_t s);
+// Device-resident scalars of one Langevin step (see k_langevin<.., kDev>): written by the host before a run of graph
+// replays, advanced (step, t) by the kernel pair itself after every step.
+struct LangevinDev {
+  float eta, lambda, noise_scale, pad;
+  unsigned long long step;     // Philox step number of the next update
+  unsigned long long t;        // index of the next update inside the injected-noise / dump tensors
+};
+// as launch_langevin with the per-step scalars in *dev; n1/n2/dump are the BASES of the [T, ...] tensors (or NULL)
+void launch_langevin_dev(float* x1, float* x2, const float* s1, const float* s2, const float* mixed, const float* n1,
+                         const float* n2, float* dump, LangevinDev* dev, uint64_t seed, uint64_t elem_offset, int* nan_count,
+                         long long n, cudaStream_t s);
 void launch_mixing_db(const float* x1, const float* x2, float* g, float* w1, float* w2, long long n, cudaStream_t s);
 void launch_philox_normal(float* out, uint64_t seed, uint64_t step, uint64_t stream_id, uint64_t elem_offset,
                           long long n, cudaStream_t s);

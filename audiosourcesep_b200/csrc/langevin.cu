@@ -51,15 +51,25 @@ __device__ __forceinline__ void mix_db(float x1, float x2, float& g, float& w1, 
 
 __device__ __forceinline__ float get4(const float4& v, int i) { return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w; }
 
-template <bool kInjected>
+// kDev: the scalars that change from one Langevin step to the next (step size, Philox step number, position in the injected
+// noise / per-step dump tensors) are read from device memory, so that ONE captured CUDA graph of a whole BASIS step can
+// be replayed for every step of every noise level (api.cu: basis graphs).
+template <bool kInjected, bool kDev = false>
 __global__ void __launch_bounds__(256) k_langevin(float* __restrict__ x1, float* __restrict__ x2,
                                                   const float* __restrict__ s1, const float* __restrict__ s2,
                                                   const float* __restrict__ mixed, const float* __restrict__ n1,
                                                   const float* __restrict__ n2, float eta, float lambda,
                                                   float noise_scale, uint64_t seed, uint64_t step,
-                                                  uint64_t elem_offset, int* __restrict__ nan_count, long long n4) {
+                                                  uint64_t elem_offset, int* __restrict__ nan_count, long long n4,
+                                                  const LangevinDev* __restrict__ dev = nullptr, float* __restrict__ dump = nullptr) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n4) return;
+  if constexpr (kDev) {
+    eta = dev->eta; lambda = dev->lambda; noise_scale = dev->noise_scale; step = dev->step;
+    const long long t = (long long)dev->t;
+    if constexpr (kInjected) { n1 += t * n4 * 4; n2 += t * n4 * 4; }
+    if (dump != nullptr) dump += 2 * t * n4 * 4;
+  }
   float4 a1 = reinterpret_cast<const float4*>(x1)[i], a2 = reinterpret_cast<const float4*>(x2)[i];
   float4 g1 = reinterpret_cast<const float4*>(s1)[i], g2 = reinterpret_cast<const float4*>(s2)[i];
   float4 mx = reinterpret_cast<const float4*>(mixed)[i];
@@ -87,7 +97,18 @@ __global__ void __launch_bounds__(256) k_langevin(float* __restrict__ x1, float*
   }
   reinterpret_cast<float4*>(x1)[i] = make_float4(o1[0], o1[1], o1[2], o1[3]);
   reinterpret_cast<float4*>(x2)[i] = make_float4(o2[0], o2[1], o2[2], o2[3]);
+  if constexpr (kDev) {
+    if (dump != nullptr) {                       // per-step state dump [T, 2, ...]
+      reinterpret_cast<float4*>(dump)[i] = make_float4(o1[0], o1[1], o1[2], o1[3]);
+      reinterpret_cast<float4*>(dump)[n4 + i] = make_float4(o2[0], o2[1], o2[2], o2[3]);
+    }
+  }
   if (nan_count != nullptr && bad) atomicAdd(nan_count, 1);
+}
+
+__global__ void k_langevin_advance(LangevinDev* dev) {
+  dev->step += 1;
+  dev->t += 1;
 }
 
 __global__ void k_mixing_db(const float* __restrict__ x1, const float* __restrict__ x2, float* __restrict__ g,
@@ -123,6 +144,24 @@ void launch_langevin(float* x1, float* x2, const float* s1, const float* s2, con
   else
     k_langevin<false><<<cdiv(n4, 256), 256, 0, s>>>(x1, x2, s1, s2, mixed, nullptr, nullptr, eta, lambda,
                                                      noise_scale, seed, step, elem_offset, nan_count, n4);
+  ASEP_LAUNCH_CHECK();
+}
+
+void launch_langevin_dev(float* x1, float* x2, const float* s1, const float* s2, const float* mixed, const float* n1,
+                         const float* n2, float* dump, LangevinDev* dev, uint64_t seed, uint64_t elem_offset, int* nan_count,
+                         long long n, cudaStream_t s) {
+  if (n == 0) return;
+  ASEP_CHECK(n % 4 == 0 && elem_offset % 4 == 0, ASEP_ERR_BAD_SHAPE,
+             "langevin: element count %lld and offset must be multiples of 4", n);
+  const long long n4 = n / 4;
+  if (n1 != nullptr && n2 != nullptr)
+    k_langevin<true, true><<<cdiv(n4, 256), 256, 0, s>>>(x1, x2, s1, s2, mixed, n1, n2, 0.f, 0.f, 0.f, seed, 0, elem_offset, nan_count,
+                                                          n4, dev, dump);
+  else
+    k_langevin<false, true><<<cdiv(n4, 256), 256, 0, s>>>(x1, x2, s1, s2, mixed, nullptr, nullptr, 0.f, 0.f, 0.f, seed, 0, elem_offset,
+                                                           nan_count, n4, dev, dump);
+  ASEP_LAUNCH_CHECK();
+  k_langevin_advance<<<1, 1, 0, s>>>(dev);
   ASEP_LAUNCH_CHECK();
 }
 

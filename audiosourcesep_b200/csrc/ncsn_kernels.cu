@@ -267,36 +267,64 @@ __global__ void __launch_bounds__(256) k_begin_conv(const float* __restrict__ x,
   reinterpret_cast<float4*>(y)[i] = acc;
 }
 
-// ---- end_conv: 3x3 'same', C -> 1 channel, bias, optional division by sigma[idx[n]]; one warp per pixel
+// ---- end_conv: 3x3 'same', C -> 1 channel, bias, optional division by sigma[idx[n]].
+// One warp per group of kPix consecutive pixels; a lane owns 8 channels (one 16-byte load per tap and pixel) and keeps
+// its 9 x 8 kernel weights in registers for the whole group, so a pixel costs 9 loads + a warp reduction.
+constexpr int kEndPix = 8;
 __global__ void __launch_bounds__(256) k_end_conv(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ x_lo,
                                                   const float* __restrict__ k,
                                                   float bias, const float* __restrict__ sigmas, const int* __restrict__ idx,
                                                   float* __restrict__ y, int H, int W, int C, long long pixels) {
-  const long long p = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long g = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (p >= pixels) return;
-  const int w = (int)(p % W), h = (int)((p / W) % H);
-  float acc = 0.f;
+  const long long p0 = g * kEndPix;
+  if (p0 >= pixels) return;
+  const int c0 = lane * 8;
+  const bool active = c0 < C;                       // C <= 256 (checked by the launcher), C % 8 == 0
+  float kw[9][8];
+#pragma unroll
   for (int tap = 0; tap < 9; ++tap) {
-    const int hh = h + tap / 3 - 1, ww = w + tap % 3 - 1;
-    if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
-    const long long off = (p + (long long)(tap / 3 - 1) * W + (tap % 3 - 1)) * C;
-    const __nv_bfloat162* row = reinterpret_cast<const __nv_bfloat162*>(x + off);
-    const __nv_bfloat162* row_lo = x_lo ? reinterpret_cast<const __nv_bfloat162*>(x_lo + off) : nullptr;
-    const float2* kr = reinterpret_cast<const float2*>(k + (size_t)tap * C);
-    for (int c2 = lane; c2 < C / 2; c2 += 32) {
-      float2 v = __bfloat1622float2(row[c2]);
-      if (row_lo) { const float2 l = __bfloat1622float2(row_lo[c2]); v.x += l.x; v.y += l.y; }
-      const float2 kk = __ldg(kr + c2);
-      acc = fmaf(v.x, kk.x, acc);
-      acc = fmaf(v.y, kk.y, acc);
-    }
+    const float4 a = active ? __ldg(reinterpret_cast<const float4*>(k + (size_t)tap * C + c0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 b = active ? __ldg(reinterpret_cast<const float4*>(k + (size_t)tap * C + c0) + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+    kw[tap][0] = a.x; kw[tap][1] = a.y; kw[tap][2] = a.z; kw[tap][3] = a.w;
+    kw[tap][4] = b.x; kw[tap][5] = b.y; kw[tap][6] = b.z; kw[tap][7] = b.w;
   }
-  acc = warp_sum(acc);
-  if (lane == 0) {
-    float o = acc + bias;
-    if (sigmas) o /= sigmas[idx[p / ((long long)H * W)]];
-    y[p] = o;
+  for (int i = 0; i < kEndPix; ++i) {
+    const long long p = p0 + i;
+    if (p >= pixels) break;
+    const int w = (int)(p % W), h = (int)((p / W) % H);
+    float acc = 0.f;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int hh = h + tap / 3 - 1, ww = w + tap % 3 - 1;
+      if (hh < 0 || hh >= H || ww < 0 || ww >= W || !active) continue;
+      const long long off = (p + (long long)(tap / 3 - 1) * W + (tap % 3 - 1)) * C + c0;
+      const uint4 u = *reinterpret_cast<const uint4*>(x + off);
+      float v[8];
+      const uint32_t uw[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        v[2 * q] = __uint_as_float(uw[q] << 16);
+        v[2 * q + 1] = __uint_as_float(uw[q] & 0xffff0000u);
+      }
+      if (x_lo) {
+        const uint4 l = *reinterpret_cast<const uint4*>(x_lo + off);
+        const uint32_t lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          v[2 * q] += __uint_as_float(lw[q] << 16);
+          v[2 * q + 1] += __uint_as_float(lw[q] & 0xffff0000u);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc = fmaf(v[q], kw[tap][q], acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      float o = acc + bias;
+      if (sigmas) o /= sigmas[idx[p / ((long long)H * W)]];
+      y[p] = o;
+    }
   }
 }
 
@@ -381,7 +409,9 @@ void launch_begin_conv(const float* x, const float* k, const float* bias, float*
 void launch_end_conv(const __nv_bfloat16* x, const __nv_bfloat16* x_lo, const float* k, float bias, const float* sigmas, const int* idx, float* y,
                      int N, int H, int W, int C, cudaStream_t s) {
   const long long pixels = (long long)N * H * W;
-  k_end_conv<<<cdiv(pixels * 32, 256), 256, 0, s>>>(x, x_lo, k, bias, sigmas, idx, y, H, W, C, pixels);
+  ASEP_CHECK(C % 8 == 0 && C <= 256, ASEP_ERR_UNSUPPORTED, "end_conv: C = %d (multiple of 8, <= 256)", C);
+  const long long groups = (pixels + kEndPix - 1) / kEndPix;
+  k_end_conv<<<cdiv(groups * 32, 256), 256, 0, s>>>(x, x_lo, k, bias, sigmas, idx, y, H, W, C, pixels);
   ASEP_LAUNCH_CHECK();
 }
 
