@@ -111,6 +111,7 @@ _SIGNATURES = {
     "asep_conv_profile_read": [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64),
                                ctypes.POINTER(ctypes.c_double)],
     "asep_crc32c": [ctypes.c_char_p, ctypes.c_uint64, ctypes.c_uint32],
+    "asep_basis_graphs": [_I],
     "asep_hbm_profile": [_I],
     "asep_hbm_profile_read": [_I, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64),
                               ctypes.POINTER(ctypes.c_double)],
@@ -186,6 +187,11 @@ HBM_CATEGORIES = {"flow_step": 0, "langevin": 1, "ncsn_prep": 2, "ncsn_pool_resi
 
 def hbm_profile(on: bool) -> None:
     check(load().asep_hbm_profile(int(on)))
+
+
+def basis_graphs(on: bool) -> None:
+    """CUDA-graph replay of the Langevin steps inside basis_*_inner (default on); off = eager launches."""
+    check(load().asep_basis_graphs(int(on)))
 
 
 def hbm_profile_read(category: int):

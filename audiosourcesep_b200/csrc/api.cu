@@ -562,27 +562,30 @@ int asep_philox_normal(DLTensor* out, uint64_t seed, uint64_t step, uint64_t str
 }  // extern "C" (re-opened below)
 
 namespace {
-// ---- CUDA graphs of one whole Glow-BASIS Langevin step (both scores + the fused update), replayed for steps 2..T of a
-// call.  A graph bakes in the state / noise / dump pointers of the call and the workspaces of both priors, so it is
-// keyed by all of them plus each prior's (uid, generation); per-step scalars are read from `dev` (LangevinDev).
+// ---- CUDA graphs of one whole BASIS Langevin step (both scores + the fused update), replayed for steps 2..T of a call.
+// A graph bakes in the state / noise / dump pointers of the call and the workspaces of both priors, so it is keyed by
+// all of them plus each prior's (uid, generation); per-step scalars are read from `dev` (LangevinDev).  The two score
+// evaluations are independent until the update: with two distinct handles they are captured as parallel branches (the
+// second on `side`), so the small HBM-bound launches of one prior overlap the tensor-core launches of the other.
 struct BasisGraphKey {
   const void* p[9];
   long long m1, m2, g1, g2;
   unsigned long long seed, off;
-  int N, pad;
+  int N, kind;                                      // kind: 0 Glow priors, 1 NCSN
   bool operator<(const BasisGraphKey& o) const { return std::memcmp(this, &o, sizeof(*this)) < 0; }
 };
 struct BasisGraph { cudaGraphExec_t exec = nullptr; long long launches = 0; };
 struct BasisGraphs {
   std::map<BasisGraphKey, BasisGraph> graphs;
-  cudaStream_t stream = nullptr;                    // private: the caller's stream may be the legacy stream (not capturable)
-  cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+  cudaStream_t stream = nullptr, side = nullptr;    // private: the caller's stream may be the legacy stream (not capturable)
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr, ev_fork = nullptr, ev_join = nullptr;
   LangevinDev* dev = nullptr;
+  bool enabled = true;
   void ensure() {
     if (stream) return;
     CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-    CUDA_CHECK(cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming));
-    CUDA_CHECK(cudaEventCreateWithFlags(&ev_out, cudaEventDisableTiming));
+    CUDA_CHECK(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+    for (cudaEvent_t* e : {&ev_in, &ev_out, &ev_fork, &ev_join}) CUDA_CHECK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     CUDA_CHECK(cudaMalloc(&dev, sizeof(LangevinDev)));
   }
   void clear() {
@@ -595,6 +598,95 @@ struct BasisGraphs {
 BasisGraphs& basis_graphs() {
   static BasisGraphs g;
   return g;
+}
+
+struct BasisCall {
+  float *x1, *x2, *s1, *s2;
+  const float *mixed, *nz1, *nz2;
+  float* dump;
+  int* nanp;
+  long long numel;
+  int N, T;
+  float eta, lambda, noise_scale;
+  uint64_t seed, step0, elem_offset;
+};
+
+// score1(stream) / score2(stream) launch the score evaluation of source 1 / 2 into c.s1 / c.s2.
+// generations(key) fills key.g1 / key.g2; it is called after the first (eager) step has sized both workspaces.
+template <class F1, class F2, class FG>
+void run_basis_steps(const BasisCall& c, BasisGraphKey key, bool parallel, bool allow_graph, cudaStream_t s, F1&& score1,
+                     F2&& score2, FG&& generations) {
+  auto eager_step = [&](int t) {
+    score1(s);
+    score2(s);
+    launch_langevin(c.x1, c.x2, c.s1, c.s2, c.mixed, c.nz1 ? c.nz1 + (size_t)t * c.numel : nullptr,
+                    c.nz2 ? c.nz2 + (size_t)t * c.numel : nullptr, c.eta, c.lambda, c.noise_scale, c.seed, c.step0 + t,
+                    c.elem_offset, c.nanp, c.numel, s);
+    if (c.dump) {
+      CUDA_CHECK(cudaMemcpyAsync(c.dump + (size_t)(2 * t) * c.numel, c.x1, (size_t)c.numel * sizeof(float),
+                                 cudaMemcpyDeviceToDevice, s));
+      CUDA_CHECK(cudaMemcpyAsync(c.dump + (size_t)(2 * t + 1) * c.numel, c.x2, (size_t)c.numel * sizeof(float),
+                                 cudaMemcpyDeviceToDevice, s));
+    }
+  };
+  // One Langevin step is 300-1200 small launches at the reference's n_mixed = 30: from the second step on the whole step
+  // is replayed as ONE CUDA graph whose per-step scalars live in device memory.
+  BasisGraphs& bg = basis_graphs();
+  static const bool no_graph = getenv("ASEP_NO_GRAPH") != nullptr;
+  const bool use_graph = c.T >= 3 && allow_graph && bg.enabled && !no_graph;
+  if (!use_graph) {
+    for (int t = 0; t < c.T; ++t) eager_step(t);
+    return;
+  }
+  eager_step(0);                                   // sizes both workspaces (a capture may not allocate)
+  bg.ensure();
+  CUDA_CHECK(cudaEventRecord(bg.ev_in, s));
+  CUDA_CHECK(cudaStreamWaitEvent(bg.stream, bg.ev_in, 0));
+  LangevinDev h{c.eta, c.lambda, c.noise_scale, 0.f, c.step0 + 1, 1ull};
+  CUDA_CHECK(cudaMemcpyAsync(bg.dev, &h, sizeof(h), cudaMemcpyHostToDevice, bg.stream));   // pageable source: staged at once
+  const void* ptrs[9] = {c.x1, c.x2, c.mixed, c.nz1, c.nz2, c.dump, c.nanp, c.s1, c.s2};
+  std::memcpy(key.p, ptrs, sizeof(ptrs));
+  key.N = c.N; key.seed = c.seed; key.off = c.elem_offset;
+  generations(key);
+  auto it = bg.graphs.find(key);
+  if (it == bg.graphs.end()) {
+    if (bg.graphs.size() >= 16) bg.clear();
+    cudaGraph_t graph = nullptr;
+    const long long c0 = g_launch_count.load();
+    CUDA_CHECK(cudaStreamBeginCapture(bg.stream, cudaStreamCaptureModeRelaxed));
+    try {
+      if (parallel) {
+        CUDA_CHECK(cudaEventRecord(bg.ev_fork, bg.stream));
+        CUDA_CHECK(cudaStreamWaitEvent(bg.side, bg.ev_fork, 0));
+        score1(bg.stream);
+        score2(bg.side);
+        CUDA_CHECK(cudaEventRecord(bg.ev_join, bg.side));
+        CUDA_CHECK(cudaStreamWaitEvent(bg.stream, bg.ev_join, 0));
+      } else {
+        score1(bg.stream);
+        score2(bg.stream);
+      }
+      launch_langevin_dev(c.x1, c.x2, c.s1, c.s2, c.mixed, c.nz1, c.nz2, c.dump, bg.dev, c.seed, c.elem_offset, c.nanp,
+                          c.numel, bg.stream);
+    } catch (...) {
+      cudaStreamEndCapture(bg.stream, &graph);
+      if (graph) cudaGraphDestroy(graph);
+      throw;
+    }
+    CUDA_CHECK(cudaStreamEndCapture(bg.stream, &graph));
+    BasisGraph g;
+    g.launches = g_launch_count.load() - c0;
+    g_launch_count.fetch_sub(g.launches);          // a capture launches nothing
+    CUDA_CHECK(cudaGraphInstantiate(&g.exec, graph, 0));
+    CUDA_CHECK(cudaGraphDestroy(graph));
+    it = bg.graphs.emplace(key, g).first;
+  }
+  for (int t = 1; t < c.T; ++t) {
+    CUDA_CHECK(cudaGraphLaunch(it->second.exec, bg.stream));
+    g_launch_count.fetch_add(it->second.launches);
+  }
+  CUDA_CHECK(cudaEventRecord(bg.ev_out, bg.stream));
+  CUDA_CHECK(cudaStreamWaitEvent(s, bg.ev_out, 0));
 }
 }  // namespace
 
@@ -633,68 +725,16 @@ int asep_basis_glow_inner(asep_glow_t m1, asep_glow_t m2, const DLTensor* mixed,
   const bool same = &g1 == &g2;
   float* s1 = g1.score_scratch(N, same ? 2 : 1);
   float* s2 = same ? s1 + a.numel : g2.score_scratch(N);
-  auto eager_step = [&](int t) {
-    g1.grad_log_prob(a.f32, s1, nullptr, N, s);     // run_basis_sep.py:174-175
-    g2.grad_log_prob(b.f32, s2, nullptr, N, s);
-    launch_langevin(a.f32, b.f32, s1, s2, mx.f32, nz1 ? nz1 + (size_t)t * a.numel : nullptr,
-                    nz2 ? nz2 + (size_t)t * a.numel : nullptr, eta, lambda, noise_scale, seed, step0 + t,
-                    elem_offset, nanp, a.numel, s);
-    if (dump) {
-      CUDA_CHECK(cudaMemcpyAsync(dump + (size_t)(2 * t) * a.numel, a.f32, (size_t)a.numel * sizeof(float),
-                                 cudaMemcpyDeviceToDevice, s));
-      CUDA_CHECK(cudaMemcpyAsync(dump + (size_t)(2 * t + 1) * a.numel, b.f32, (size_t)a.numel * sizeof(float),
-                                 cudaMemcpyDeviceToDevice, s));
-    }
-  };
-  // One Langevin step is ~1200 small launches at the reference's n_mixed = 30: from the third step on the whole step (both
-  // scores + the fused update) is replayed as ONE CUDA graph whose per-step scalars live in device memory.
-  static const bool no_graph = getenv("ASEP_NO_GRAPH") != nullptr;
-  const bool use_graph = T >= 3 && !no_graph && !nn_tc_profile_enabled() && !hbm_profile_enabled();
-  if (!use_graph) {
-    for (int t = 0; t < T; ++t) eager_step(t);
-  } else {
-    eager_step(0);                                   // sizes both workspaces (a capture may not allocate)
-    BasisGraphs& bg = basis_graphs();
-    bg.ensure();
-    CUDA_CHECK(cudaEventRecord(bg.ev_in, s));
-    CUDA_CHECK(cudaStreamWaitEvent(bg.stream, bg.ev_in, 0));
-    LangevinDev h{eta, lambda, noise_scale, 0.f, step0 + 1, 1ull};
-    CUDA_CHECK(cudaMemcpyAsync(bg.dev, &h, sizeof(h), cudaMemcpyHostToDevice, bg.stream));   // pageable source: staged at once
-    BasisGraphKey key{};
-    const void* ptrs[9] = {a.f32, b.f32, mx.f32, nz1, nz2, dump, nanp, s1, s2};
-    std::memcpy(key.p, ptrs, sizeof(ptrs));
-    key.N = N; key.seed = seed; key.off = elem_offset;
-    key.m1 = g1.uid(); key.m2 = g2.uid(); key.g1 = g1.generation(); key.g2 = g2.generation();
-    auto it = bg.graphs.find(key);
-    if (it == bg.graphs.end()) {
-      if (bg.graphs.size() >= 16) bg.clear();
-      cudaGraph_t graph = nullptr;
-      const long long c0 = g_launch_count.load();
-      CUDA_CHECK(cudaStreamBeginCapture(bg.stream, cudaStreamCaptureModeRelaxed));
-      try {
-        g1.grad_log_prob(a.f32, s1, nullptr, N, bg.stream);
-        g2.grad_log_prob(b.f32, s2, nullptr, N, bg.stream);
-        launch_langevin_dev(a.f32, b.f32, s1, s2, mx.f32, nz1, nz2, dump, bg.dev, seed, elem_offset, nanp, a.numel, bg.stream);
-      } catch (...) {
-        cudaStreamEndCapture(bg.stream, &graph);
-        if (graph) cudaGraphDestroy(graph);
-        throw;
-      }
-      CUDA_CHECK(cudaStreamEndCapture(bg.stream, &graph));
-      BasisGraph g;
-      g.launches = g_launch_count.load() - c0;
-      g_launch_count.fetch_sub(g.launches);          // a capture launches nothing
-      CUDA_CHECK(cudaGraphInstantiate(&g.exec, graph, 0));
-      CUDA_CHECK(cudaGraphDestroy(graph));
-      it = bg.graphs.emplace(key, g).first;
-    }
-    for (int t = 1; t < T; ++t) {
-      CUDA_CHECK(cudaGraphLaunch(it->second.exec, bg.stream));
-      g_launch_count.fetch_add(it->second.launches);
-    }
-    CUDA_CHECK(cudaEventRecord(bg.ev_out, bg.stream));
-    CUDA_CHECK(cudaStreamWaitEvent(s, bg.ev_out, 0));
-  }
+  BasisCall call{a.f32, b.f32, s1, s2, mx.f32, nz1, nz2, dump, nanp, (long long)a.numel, N, T, eta, lambda, noise_scale,
+                 seed, step0, elem_offset};
+  BasisGraphKey key{};
+  key.kind = 0;
+  key.m1 = g1.uid(); key.m2 = g2.uid();
+  const bool allow_graph = !nn_tc_profile_enabled() && !hbm_profile_enabled();
+  run_basis_steps(call, key, !same, allow_graph, s,
+                  [&](cudaStream_t st) { g1.grad_log_prob(a.f32, s1, nullptr, N, st); },     // run_basis_sep.py:174-175
+                  [&](cudaStream_t st) { g2.grad_log_prob(b.f32, s2, nullptr, N, st); },
+                  [&](BasisGraphKey& k) { k.g1 = g1.generation(); k.g2 = g2.generation(); });
   ASEP_API_END
 }
 
@@ -817,19 +857,16 @@ int asep_basis_ncsn_inner(asep_ncsn_t m1, asep_ncsn_t m2, const DLTensor* mixed,
   float* s1 = g1.score_scratch(N, same ? 2 : 1);
   float* s2 = same ? s1 + a.numel : g2.score_scratch(N);
   const int* idx = g1.index_scratch(N, sigma_idx, s);               // run_basis_sep.py:167-168
-  for (int t = 0; t < T; ++t) {
-    g1.forward(a.f32, idx, s1, N, s);                               // run_basis_sep.py:169-170
-    g2.forward(b.f32, idx, s2, N, s);
-    launch_langevin(a.f32, b.f32, s1, s2, mx.f32, nz1 ? nz1 + (size_t)t * a.numel : nullptr,
-                    nz2 ? nz2 + (size_t)t * a.numel : nullptr, eta, lambda, noise_scale, seed, step0 + t,
-                    elem_offset, nanp, a.numel, s);
-    if (dump) {
-      CUDA_CHECK(cudaMemcpyAsync(dump + (size_t)(2 * t) * a.numel, a.f32, (size_t)a.numel * sizeof(float),
-                                 cudaMemcpyDeviceToDevice, s));
-      CUDA_CHECK(cudaMemcpyAsync(dump + (size_t)(2 * t + 1) * a.numel, b.f32, (size_t)a.numel * sizeof(float),
-                                 cudaMemcpyDeviceToDevice, s));
-    }
-  }
+  BasisCall call{a.f32, b.f32, s1, s2, mx.f32, nz1, nz2, dump, nanp, (long long)a.numel, N, T, eta, lambda, noise_scale,
+                 seed, step0, elem_offset};
+  BasisGraphKey key{};
+  key.kind = 1;
+  key.m1 = g1.uid(); key.m2 = g2.uid();
+  const bool allow_graph = !conv_tc_profile_enabled() && !hbm_profile_enabled();
+  run_basis_steps(call, key, !same, allow_graph, s,
+                  [&](cudaStream_t st) { g1.forward(a.f32, idx, s1, N, st); },               // run_basis_sep.py:169-170
+                  [&](cudaStream_t st) { g2.forward(b.f32, idx, s2, N, st); },
+                  [&](BasisGraphKey& k) { k.g1 = g1.generation(); k.g2 = g2.generation(); });
   ASEP_API_END
 }
 
@@ -937,6 +974,13 @@ uint32_t asep_crc32c(const void* data, uint64_t n, uint32_t crc) {
   }
   while (n--) c = tab[0][(c ^ *p++) & 0xFFu] ^ (c >> 8);
   return c ^ 0xFFFFFFFFu;
+}
+
+int asep_basis_graphs(int on) {
+  ASEP_API_BEGIN
+  basis_graphs().enabled = on != 0;
+  if (!on) basis_graphs().clear();
+  ASEP_API_END
 }
 
 int asep_hbm_profile(int on) {

@@ -491,6 +491,8 @@ void conv_tc_forward(const ConvWeightsTC& w, const __nv_bfloat16* xin, const flo
   }
 }
 
+bool conv_tc_profile_enabled() { return g_prof_on; }
+
 void conv_tc_profile(int on) {
   g_prof_on = on != 0;
   if (g_prof_on) {

@@ -30,6 +30,7 @@ void conv_tc_forward(const ConvWeightsTC& w, const __nv_bfloat16* xin, const flo
 
 // profiling of the conv launches (same contract as nn_tc_profile)
 void conv_tc_profile(int on);
+bool conv_tc_profile_enabled();
 void conv_tc_profile_read(double* total_ms, long long* launches, double* flops);
 
 }  // namespace asep

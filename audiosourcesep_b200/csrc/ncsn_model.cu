@@ -2,9 +2,14 @@
 
 #include <cstring>
 
+#include <atomic>
+
 namespace asep {
 
+namespace { std::atomic<long long> g_next_ncsn_uid{1}; }
+
 NcsnModel::NcsnModel(const asep_ncsn_cfg& cfg, int device) : cfg_(cfg), device_(device), v1_(cfg.version == 1) {
+  uid_ = g_next_ncsn_uid.fetch_add(1);
   ASEP_CHECK(cfg.version == 1 || cfg.version == 2, ASEP_ERR_BAD_ARG, "NCSN version must be 1 or 2");
   ASEP_CHECK(cfg.C == 1, ASEP_ERR_UNSUPPORTED, "the score networks of the separation path take 1-channel patches");
   ASEP_CHECK(cfg.ngf % 64 == 0, ASEP_ERR_UNSUPPORTED, "n_filters must be a multiple of 64 (got %d)", cfg.ngf);
@@ -35,6 +40,7 @@ float* NcsnModel::score_scratch(int N, int slots) {
     score_buf_ = nullptr;
     CUDA_CHECK(cudaMalloc(&score_buf_, need));
     score_cap_ = need;
+    ++generation_;
   }
   return score_buf_;
 }
@@ -46,6 +52,7 @@ const int* NcsnModel::index_scratch(int N, int sigma_idx, cudaStream_t s) {
     idx_buf_ = nullptr;
     CUDA_CHECK(cudaMalloc(&idx_buf_, (size_t)N * sizeof(int)));
     idx_cap_ = (size_t)N;
+    ++generation_;
   }
   CUDA_CHECK(cudaStreamSynchronize(s));            // the host staging vector may still feed an earlier copy
   idx_host_.assign((size_t)N, sigma_idx);
@@ -69,6 +76,7 @@ void NcsnModel::set_param(const std::string& name, const float* src, const std::
 
 void NcsnModel::set_sigmas(const float* sigmas, int n) {
   if (sigmas_dev_) cudaFree(sigmas_dev_);
+  ++generation_;
   CUDA_CHECK(cudaMalloc(&sigmas_dev_, (size_t)n * sizeof(float)));
   CUDA_CHECK(cudaMemcpy(sigmas_dev_, sigmas, (size_t)n * sizeof(float), cudaMemcpyHostToDevice));
   n_sigmas_ = n;
@@ -88,6 +96,8 @@ const NcsnParam& NcsnModel::param(const std::string& name) const {
 
 void NcsnModel::prepare() {
   CUDA_CHECK(cudaSetDevice(device_));
+  ++generation_;                                   // tile images / packed rows below are re-allocated
+  CUDA_CHECK(cudaDeviceSynchronize());             // a graph replay may still be reading them
   for (auto& kv : convs_) conv_tc_release(kv.second);
   convs_.clear();
   for (auto& kv : convs_lo_) conv_tc_release(kv.second);
@@ -346,6 +356,7 @@ void NcsnModel::forward(const float* x, const int* idx, float* score, int N, cud
     arena_ = nullptr;
     CUDA_CHECK(cudaMalloc(&arena_, need));
     arena_cap_ = need;
+    ++generation_;
   }
   arena_off_ = 0;
   run(x, idx, score);

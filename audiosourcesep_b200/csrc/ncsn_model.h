@@ -34,6 +34,9 @@ class NcsnModel {
   // persistent scratch of the BASIS inner loop: a score tensor [N,H,W,1] and a constant sigma index vector [N]
   float* score_scratch(int N, int slots = 1);   // slots = 2: room for both sources when one handle serves as both priors
   const int* index_scratch(int N, int sigma_idx, cudaStream_t s);
+  // identity of the device allocations a captured graph of this model's kernels would bake in (api.cu: BASIS step graphs)
+  long long uid() const { return uid_; }
+  long long generation() const { return generation_; }
 
  private:
   // fp32 NHWC activation (batch = N_); sums != NULL: per-(n,c) sum / sum of squares already accumulated by the producer
@@ -77,6 +80,7 @@ class NcsnModel {
   std::vector<int> idx_host_;
   char* arena_ = nullptr;
   size_t arena_cap_ = 0, arena_off_ = 0;
+  long long uid_ = 0, generation_ = 0;
 };
 
 }  // namespace asep

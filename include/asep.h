@@ -237,6 +237,11 @@ uint32_t asep_crc32c(const void* data, uint64_t n, uint32_t crc);
 int asep_hbm_profile(int on);
 int asep_hbm_profile_read(int category, double* total_ms, int64_t* launches, double* bytes);
 
+/* CUDA-graph replay of whole Langevin steps inside asep_basis_{glow,ncsn}_inner (on by default; steps 2..T of a call
+ * with T >= 3 are replays of one captured step whose per-step scalars live in device memory).  0 = launch every step
+ * eagerly (parity tests compare the two), and drop the cached graphs. */
+int asep_basis_graphs(int on);
+
 /* Measurement aid (bench.py roofline leg): while on, every launch of the tcgen05 coupling kernel is bracketed
  * by a CUDA event pair on its own stream.  _read synchronises those events and returns the summed kernel time,
  * the launch count and the algorithmic FLOPs (2 x conv MACs, unpadded) of the recorded launches. */

@@ -190,3 +190,37 @@ def test_device_sigma_loop_equals_the_host_loop():
                   [c[1] for c in consts], [c[2] for c in consts], seed=9)
     assert torch.equal(c1, a1) and torch.equal(c2, a2)
 
+
+
+@pytest.mark.parametrize("same_handle", [False, True])
+def test_glow_step_graph_replay_equals_eager_launches(same_handle):
+    """Steps 2..T of asep_basis_glow_inner are replays of ONE captured CUDA graph (both scores as parallel branches when
+    the priors are two handles, per-step scalars in device memory): states and the per-step dump must equal those of
+    eager launches, for in-kernel Philox noise and across two consecutive calls that reuse the cached graph."""
+    from audiosourcesep_b200 import ops, _lib
+    from audiosourcesep_b200.glow import Glow
+    cfg = GlowConfig(H=96, W=64, C=1, L=3, K=2, n_filters=512, minval=0.0, maxval=1.0)
+    m1 = Glow(cfg, init_glow_params(cfg, seed=2, mode="perturbed"), precision=_lib.PREC_BF16)
+    m2 = m1 if same_handle else Glow(cfg, init_glow_params(cfg, seed=3, mode="perturbed"), precision=_lib.PREC_BF16)
+    mixed, _, _ = synthetic.basis_problem(3)
+    x1, x2 = synthetic.langevin_init(3, seed=4)
+    sig = bo.get_sigmas(1.0, 0.01, 10, "logarithmic")
+    T = 5
+    outs = []
+    try:
+        for graphs in (False, True):
+            _lib.basis_graphs(graphs)
+            t1, t2 = torch.as_tensor(x1).cuda(), torch.as_tensor(x2).cuda()
+            dump = torch.zeros((T, 2, 3, 96, 64, 1), device="cuda")
+            n0 = _lib.launch_count()
+            for call, level in enumerate((7, 9)):          # second call: other step constants, same cached graph
+                eta, lam, ns = bo.step_constants(sig, level)
+                ops.basis_glow_inner(m1, m2, torch.as_tensor(mixed), t1, t2, T, float(eta), float(lam), float(ns), seed=11,
+                                     step0=call * T, per_step=dump if call == 1 else None)
+            outs.append((t1.clone(), t2.clone(), dump.clone(), _lib.launch_count() - n0))
+    finally:
+        _lib.basis_graphs(True)
+    for k in range(3):
+        assert torch.equal(outs[0][k], outs[1][k]), k
+    assert outs[1][3] >= outs[0][3] > 0          # replayed launches are counted like eager ones (+1 per step: the scalar advance)
+    assert not torch.equal(outs[1][0], torch.as_tensor(x1).cuda())

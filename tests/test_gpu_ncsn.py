@@ -176,3 +176,34 @@ def test_score_is_sample_wise_at_the_bench_size(version):
     print(f"[{version}] permutation {rel:.2e}, single segment {rel1:.2e}")
     assert rel <= 1e-5 and rel1 <= 1e-5, (rel, rel1)
     assert model([x[:0].contiguous(), idx[:0]], training=True).shape == (0, 96, 64, 1)      # empty batch
+
+
+@pytest.mark.parametrize("version", ["v1", "v2"])
+def test_ncsn_step_graph_replay_equals_eager_launches(version):
+    """asep_basis_ncsn_inner replays steps 2..T as one captured CUDA graph (the two score networks as parallel branches):
+    same states as eager launches (the instance-norm statistics are accumulated with double atomics, whose order may
+    differ in the last bit, hence a 1e-6 bound instead of bit equality)."""
+    from audiosourcesep_b200 import ops, _lib
+    cfg = _cfg(version)
+    m1, sig = _model(cfg, init_ncsn_params(cfg, seed=5, mode="perturbed"))
+    m2, _ = _model(cfg, init_ncsn_params(cfg, seed=6, mode="perturbed"))
+    mixed, _, _ = synthetic.basis_problem(3)
+    x1, x2 = synthetic.langevin_init(3, seed=4)
+    T = 4
+    outs = []
+    try:
+        for graphs in (False, True):
+            _lib.basis_graphs(graphs)
+            t1, t2 = torch.as_tensor(x1).cuda(), torch.as_tensor(x2).cuda()
+            dump = torch.zeros((T, 2, 3, 96, 64, 1), device="cuda")
+            for call, level in enumerate((cfg.num_classes - 3, cfg.num_classes - 1)):
+                eta, lam, ns = bo.step_constants(sig, level)
+                ops.basis_ncsn_inner(m1, m2, torch.as_tensor(mixed), t1, t2, level, T, float(eta), float(lam), float(ns),
+                                     seed=11, step0=call * T, per_step=dump if call == 1 else None)
+            outs.append((t1.clone(), t2.clone(), dump.clone()))
+    finally:
+        _lib.basis_graphs(True)
+    for k in range(3):
+        a, b = _np(outs[0][k]), _np(outs[1][k])
+        assert np.linalg.norm(a - b) <= 1e-6 * np.linalg.norm(a), k
+    assert not torch.equal(outs[1][0], torch.as_tensor(x1).cuda())
