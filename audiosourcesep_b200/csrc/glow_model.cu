@@ -143,6 +143,11 @@ GlowModel::~GlowModel() {
   if (score_buf_) cudaFree(score_buf_);
   if (refresh_table_) cudaFree(refresh_table_);
   if (tgraph_.exec) cudaGraphExecDestroy(tgraph_.exec);
+  for (auto& kv : igraphs_)
+    if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  if (ig_stream_) cudaStreamDestroy(ig_stream_);
+  for (void* p : {(void*)ig_in_, (void*)ig_out_, (void*)ig_lp_})
+    if (p) cudaFree(p);
   if (tg_stream_) cudaStreamDestroy(tg_stream_);
   if (tg_ev_in_) cudaEventDestroy(tg_ev_in_);
   if (tg_ev_out_) cudaEventDestroy(tg_ev_out_);
@@ -247,6 +252,69 @@ void GlowModel::invalidate_graphs() {
     tgraph_.exec = nullptr;
   }
   tg_calls_ = 0;                             // the next train_grads runs eagerly and re-sizes its scratch
+  if (!igraphs_.empty()) {
+    cudaDeviceSynchronize();
+    for (auto& kv : igraphs_)
+      if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    igraphs_.clear();
+  }
+}
+
+// ------------------------------------------------------------------ small-batch inference graphs
+namespace { constexpr int kInferGraphMaxN = 128; }
+
+bool GlowModel::infer_graph_ok(int N, cudaStream_t s) const {
+  static const bool no_graph = getenv("ASEP_NO_GRAPH") != nullptr;
+  if (no_graph || !is_tc() || N > kInferGraphMaxN || nn_tc_profile_enabled() || hbm_profile_enabled()) return false;
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(s, &st) != cudaSuccess) { cudaGetLastError(); return false; }
+  return st == cudaStreamCaptureStatusNone;      // (a BASIS step graph is being captured: launch directly)
+}
+
+template <class Body>
+void GlowModel::run_infer_graph(int kind, int N, const float* in, size_t n_in, float* out, size_t n_out, float* lp,
+                                cudaStream_t s, Body&& body) {
+  InferGraph& g = igraphs_[{kind, N}];
+  if (g.seen == 0) {                              // eager: allocates / re-carves whatever this direction needs
+    const long long gen = generation_;
+    body(in, out, lp, s);
+    if (generation_ == gen) igraphs_[{kind, N}].seen = 1;   // (a re-carve cleared the map: the entry is new again)
+    return;
+  }
+  if (N > ig_cap_) {
+    CUDA_CHECK(cudaDeviceSynchronize());
+    for (float** p : {&ig_in_, &ig_out_, &ig_lp_})
+      if (*p) { cudaFree(*p); *p = nullptr; }
+    const size_t d = (size_t)kInferGraphMaxN * std::max<size_t>((size_t)cfg_.H * cfg_.W * cfg_.C, (size_t)Dl_);
+    CUDA_CHECK(cudaMalloc(&ig_in_, d * sizeof(float)));
+    CUDA_CHECK(cudaMalloc(&ig_out_, d * sizeof(float)));
+    CUDA_CHECK(cudaMalloc(&ig_lp_, (size_t)kInferGraphMaxN * sizeof(float)));
+    ig_cap_ = kInferGraphMaxN;
+  }
+  if (!g.exec) {
+    if (!ig_stream_) CUDA_CHECK(cudaStreamCreateWithFlags(&ig_stream_, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaStreamSynchronize(s));         // the eager pass of this key may still be using the workspace
+    cudaGraph_t graph = nullptr;
+    const long long c0 = g_launch_count.load();
+    CUDA_CHECK(cudaStreamBeginCapture(ig_stream_, cudaStreamCaptureModeRelaxed));
+    try {
+      body(ig_in_, ig_out_, ig_lp_, ig_stream_);
+    } catch (...) {
+      cudaStreamEndCapture(ig_stream_, &graph);
+      if (graph) cudaGraphDestroy(graph);
+      throw;
+    }
+    CUDA_CHECK(cudaStreamEndCapture(ig_stream_, &graph));
+    g.launches = g_launch_count.load() - c0;
+    g_launch_count.fetch_sub(g.launches);         // a capture launches nothing
+    CUDA_CHECK(cudaGraphInstantiate(&g.exec, graph, 0));
+    CUDA_CHECK(cudaGraphDestroy(graph));
+  }
+  CUDA_CHECK(cudaMemcpyAsync(ig_in_, in, n_in * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  CUDA_CHECK(cudaGraphLaunch(g.exec, s));
+  g_launch_count.fetch_add(g.launches);
+  if (out) CUDA_CHECK(cudaMemcpyAsync(out, ig_out_, n_out * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  if (lp) CUDA_CHECK(cudaMemcpyAsync(lp, ig_lp_, (size_t)N * sizeof(float), cudaMemcpyDeviceToDevice, s));
 }
 
 void GlowModel::prepare(int precision) {
@@ -538,6 +606,12 @@ void GlowModel::forward(const float* x, float* z, float* fldj, int N, cudaStream
 
 void GlowModel::log_prob(const float* x, float* logp, int N, cudaStream_t s) {
   if (N == 0) return;
+  if (!infer_graph_ok(N, s)) return log_prob_body(x, logp, N, s);
+  run_infer_graph(0, N, x, (size_t)N * cfg_.H * cfg_.W * cfg_.C, nullptr, 0, logp, s,
+                  [&](const float* in, float*, float* lp, cudaStream_t st) { log_prob_body(in, lp, N, st); });
+}
+
+void GlowModel::log_prob_body(const float* x, float* logp, int N, cudaStream_t s) {
   run_forward(x, N, false, s);
   const float* loc = cfg_.learntop ? params_.at("prior/loc").dev : nullptr;
   const float* ls = cfg_.learntop ? params_.at("prior/log_scale").dev : nullptr;
@@ -547,6 +621,13 @@ void GlowModel::log_prob(const float* x, float* logp, int N, cudaStream_t s) {
 
 void GlowModel::grad_log_prob(const float* x, float* grad, float* logp, int N, cudaStream_t s) {
   if (N == 0) return;
+  if (!infer_graph_ok(N, s)) return grad_log_prob_body(x, grad, logp, N, s);
+  const size_t n = (size_t)N * cfg_.H * cfg_.W * cfg_.C;
+  run_infer_graph(logp ? 2 : 1, N, x, n, grad, n, logp, s,
+                  [&](const float* in, float* out, float* lp, cudaStream_t st) { grad_log_prob_body(in, out, lp, N, st); });
+}
+
+void GlowModel::grad_log_prob_body(const float* x, float* grad, float* logp, int N, cudaStream_t s) {
   run_forward(x, N, true, s);
   const int L = cfg_.L, K = cfg_.K;
   const float* loc = cfg_.learntop ? params_.at("prior/loc").dev : nullptr;
@@ -591,6 +672,12 @@ void GlowModel::grad_log_prob(const float* x, float* grad, float* logp, int N, c
 
 void GlowModel::inverse(const float* z, float* x, int N, cudaStream_t s) {
   if (N == 0) return;
+  if (!infer_graph_ok(N, s)) return inverse_body(z, x, N, s);
+  run_infer_graph(3, N, z, (size_t)N * Dl_, x, (size_t)N * cfg_.H * cfg_.W * cfg_.C, nullptr, s,
+                  [&](const float* in, float* out, float*, cudaStream_t st) { inverse_body(in, out, N, st); });
+}
+
+void GlowModel::inverse_body(const float* z, float* x, int N, cudaStream_t s) {
   require_prepared();
   ensure_work(N, false);
   const int L = cfg_.L, K = cfg_.K;

@@ -129,6 +129,21 @@ class GlowModel {
   StepRefresh* refresh_table_ = nullptr;     // device rows of the batched refresh (glow_train.cu)
   bool refresh_dirty_ = true;
   long long uid_ = 0, generation_ = 0;
+  // ---- small-batch inference graphs: at the reference's batch sizes (N = 30 / 32) a pass is 250-850 launches of
+  // 5-30 us each, so log_prob / inverse / grad_log_prob replay ONE captured CUDA graph per (direction, N) between
+  // internal staging buffers (the caller's pointers change from call to call).  First call of a key: eager (sizes the
+  // workspace); second: capture; then replays on the caller's stream.
+  struct InferGraph { cudaGraphExec_t exec = nullptr; long long launches = 0; int seen = 0; };
+  std::map<std::pair<int, int>, InferGraph> igraphs_;     // (direction, N)
+  float *ig_in_ = nullptr, *ig_out_ = nullptr, *ig_lp_ = nullptr;
+  int ig_cap_ = 0;
+  cudaStream_t ig_stream_ = nullptr;
+  bool infer_graph_ok(int N, cudaStream_t s) const;
+  template <class Body> void run_infer_graph(int kind, int N, const float* in, size_t n_in, float* out, size_t n_out,
+                                             float* lp, cudaStream_t s, Body&& body);
+  void log_prob_body(const float* x, float* logp, int N, cudaStream_t s);
+  void grad_log_prob_body(const float* x, float* grad, float* logp, int N, cudaStream_t s);
+  void inverse_body(const float* z, float* x, int N, cudaStream_t s);
   bool dumping_ = false;                     // run_forward is writing the training activation copies (Work::D1 / D2)
   StepTrainPtrs step_ptrs(int b, int k);
   std::vector<std::string> order_;          // parameter names in construction order

@@ -331,3 +331,38 @@ def test_full_size_batch_is_sample_wise_and_order_invariant(precision):
     # duplicated patches (the cyclic shifts wrap after 64/3 steps) get identical values
     dup = m.log_prob(torch.cat([xt[:5], xt[:5]], 0))
     assert torch.equal(dup[:5], dup[5:])
+
+
+def test_small_batch_graph_replay_equals_eager_launches():
+    """At N <= 128 log_prob / grad_log_prob / inverse replay one captured CUDA graph per (direction, N) from the third
+    call on (first: eager, second: capture + replay).  Replays must be bit-identical to eager launches, follow new
+    inputs (staging copies), survive an interleaved call that re-carves the workspace, and count their launches."""
+    from audiosourcesep_b200 import _lib
+    from audiosourcesep_b200.glow import Glow
+    cfg = GlowConfig(H=96, W=64, C=1, L=3, K=3, n_filters=512)
+    params = init_glow_params(cfg, seed=2, mode="perturbed")
+    m = Glow(cfg, params, precision=_lib.PREC_BF16)
+    xa = torch.as_tensor(synthetic.mel_patches_db(5, seed=0)).cuda()
+    xb = torch.as_tensor(synthetic.mel_patches_db(5, seed=1)).cuda()
+    ref = Glow(cfg, params, precision=_lib.PREC_BF16)        # every call below is this handle's FIRST of its kind: eager
+    want = {"lp_a": ref.log_prob(xa), "g_b": ref.grad_log_prob(xb)}
+    want["z_b"] = ref.forward(xb)
+    want["x_b"] = ref.inverse(want["z_b"])
+    n0 = _lib.launch_count()
+    first = m.log_prob(xb)                                   # eager
+    eager_launches = _lib.launch_count() - n0
+    m.log_prob(xb)                                           # capture + first replay
+    n0 = _lib.launch_count()
+    got = m.log_prob(xa)                                     # replay with a new input
+    assert _lib.launch_count() - n0 == eager_launches
+    assert torch.equal(got, want["lp_a"]) and not torch.equal(got, first)
+    for _ in range(3):                                       # grad: the first call re-carves the workspace (save = true)
+        g = m.grad_log_prob(xb)
+    assert torch.equal(g, want["g_b"])
+    for _ in range(3):                                       # log_prob again: its graph was dropped by the re-carve
+        got = m.log_prob(xa)
+    assert torch.equal(got, want["lp_a"])
+    for _ in range(3):
+        xr = m.inverse(want["z_b"])
+    assert torch.equal(xr, want["x_b"])
+    assert torch.equal(m.grad_log_prob(xb), want["g_b"])     # the gradient graph is still valid after the other directions
