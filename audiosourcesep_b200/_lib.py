@@ -102,6 +102,13 @@ _SIGNATURES = {
     "asep_ncsn_set_precision": [_V, _I],
     "asep_ncsn_prepare": [_V],
     "asep_ncsn_forward": [_V, _P, _P, _P, _V],
+    "asep_ncsn_enable_training": [_V],
+    "asep_ncsn_num_trainable": [_V, ctypes.POINTER(ctypes.c_int64)],
+    "asep_ncsn_param_span": [_V, ctypes.c_char_p, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)],
+    "asep_ncsn_train_grads": [_V, _P, _P, _P, _I, _P, _P, _V],
+    "asep_ncsn_adam_step": [_V, _P, _F, _F, _F, _F, _V],
+    "asep_ncsn_get_flat": [_V, _P, _V],
+    "asep_ncsn_set_flat": [_V, _P, _V],
     "asep_basis_ncsn_inner": [_V, _V, _P, _P, _P, _I, _I, _F, _F, _F, _P, _P, _U64, _U64, _U64, _P, _P, _V],
     "asep_basis_glow_run": [ctypes.POINTER(_V), ctypes.POINTER(_V), _I, _P, _P, _P, _I, _I, ctypes.POINTER(ctypes.c_float),
                             ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float), _U64, _U64, _P, _P, _V],

@@ -815,6 +815,87 @@ int asep_ncsn_forward(asep_ncsn_t h, const DLTensor* x, const DLTensor* sigma_id
   ASEP_API_END
 }
 
+// ---- NCSN training (train_ncsn.py:26-57)
+int asep_ncsn_enable_training(asep_ncsn_t h) {
+  ASEP_API_BEGIN
+  ASEP_CHECK(h, ASEP_ERR_BAD_ARG, "NULL handle");
+  h->model->enable_training();
+  ASEP_API_END
+}
+
+int asep_ncsn_num_trainable(asep_ncsn_t h, int64_t* out) {
+  ASEP_API_BEGIN
+  ASEP_CHECK(h && out, ASEP_ERR_BAD_ARG, "NULL argument");
+  *out = (int64_t)h->model->num_trainable();
+  ASEP_API_END
+}
+
+int asep_ncsn_param_span(asep_ncsn_t h, const char* name, int64_t* offset, int64_t* numel) {
+  ASEP_API_BEGIN
+  ASEP_CHECK(h && name, ASEP_ERR_BAD_ARG, "NULL argument");
+  long long o = 0, n = 0;
+  h->model->param_span(name, &o, &n);
+  if (offset) *offset = (int64_t)o;
+  if (numel) *numel = (int64_t)n;
+  ASEP_API_END
+}
+
+int asep_ncsn_train_grads(asep_ncsn_t h, const DLTensor* x, const DLTensor* noise, const DLTensor* sigma_idx,
+                          int global_batch, DLTensor* grads, DLTensor* loss, void* stream) {
+  ASEP_API_BEGIN
+  ASEP_CHECK(h, ASEP_ERR_BAD_ARG, "NULL handle");
+  NcsnModel& m = *h->model;
+  const auto& c = m.cfg();
+  TView xv = view_f32(x, "x", m.device());
+  expect_shape(xv, "x", {-1, c.H, c.W, c.C});
+  const int N = (int)xv.shape[0];
+  TView nv = view_f32(noise, "noise", m.device());
+  expect_shape(nv, "noise", {N, c.H, c.W, c.C});
+  TView iv = view_i32(sigma_idx, "sigma_idx", m.device());
+  expect_shape(iv, "sigma_idx", {N});
+  TView gv = view_f32(grads, "grads", m.device());
+  ASEP_CHECK(gv.numel == m.num_trainable(), ASEP_ERR_BAD_SHAPE, "grads must hold %lld elements", m.num_trainable());
+  float* lp = nullptr;
+  if (loss) {
+    TView lv = view_f32(loss, "loss", m.device());
+    ASEP_CHECK(lv.numel == 1, ASEP_ERR_BAD_SHAPE, "loss must hold one element");
+    lp = lv.f32;
+  }
+  m.train_grads(xv.f32, nv.f32, static_cast<const int*>(iv.raw), N, global_batch, gv.f32, lp, as_stream(stream));
+  ASEP_API_END
+}
+
+int asep_ncsn_adam_step(asep_ncsn_t h, const DLTensor* grads, float lr, float beta1, float beta2, float eps,
+                        void* stream) {
+  ASEP_API_BEGIN
+  ASEP_CHECK(h, ASEP_ERR_BAD_ARG, "NULL handle");
+  NcsnModel& m = *h->model;
+  TView gv = view_f32(grads, "grads", m.device());
+  ASEP_CHECK(gv.numel == m.num_trainable(), ASEP_ERR_BAD_SHAPE, "grads must hold %lld elements", m.num_trainable());
+  m.adam_step(gv.f32, lr, beta1, beta2, eps, as_stream(stream));
+  ASEP_API_END
+}
+
+int asep_ncsn_get_flat(asep_ncsn_t h, DLTensor* theta, void* stream) {
+  ASEP_API_BEGIN
+  ASEP_CHECK(h, ASEP_ERR_BAD_ARG, "NULL handle");
+  NcsnModel& m = *h->model;
+  TView tv = view_f32(theta, "theta", m.device());
+  ASEP_CHECK(tv.numel == m.num_trainable(), ASEP_ERR_BAD_SHAPE, "theta must hold %lld elements", m.num_trainable());
+  m.copy_flat(tv.f32, as_stream(stream));
+  ASEP_API_END
+}
+
+int asep_ncsn_set_flat(asep_ncsn_t h, const DLTensor* theta, void* stream) {
+  ASEP_API_BEGIN
+  ASEP_CHECK(h, ASEP_ERR_BAD_ARG, "NULL handle");
+  NcsnModel& m = *h->model;
+  TView tv = view_f32(theta, "theta", m.device());
+  ASEP_CHECK(tv.numel == m.num_trainable(), ASEP_ERR_BAD_SHAPE, "theta must hold %lld elements", m.num_trainable());
+  m.set_flat(tv.f32, as_stream(stream));
+  ASEP_API_END
+}
+
 int asep_basis_ncsn_inner(asep_ncsn_t m1, asep_ncsn_t m2, const DLTensor* mixed, DLTensor* x1, DLTensor* x2,
                           int sigma_idx, int T, float eta, float lambda, float noise_scale, const DLTensor* noise1,
                           const DLTensor* noise2, uint64_t seed, uint64_t step0, uint64_t elem_offset,

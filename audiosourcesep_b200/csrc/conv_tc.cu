@@ -431,9 +431,17 @@ void conv_tc_prepare(ConvWeightsTC& w, const float* kernel, const float* bias, i
   w.Cin = Cin; w.Cout = Cout; w.ksize = ksize; w.dil = dilation;
 }
 
+void conv_tc_alloc(ConvWeightsTC& w, int ksize, int Cin, int Cout, int dilation) {
+  conv_tc_release(w);
+  ASEP_CHECK((ksize == 1 || ksize == 3) && Cin % 64 == 0, ASEP_ERR_UNSUPPORTED, "conv image %dx%d Cin=%d", ksize, ksize, Cin);
+  w.bytes = (size_t)ksize * ksize * Cin * Cout * sizeof(__nv_bfloat16);
+  CUDA_CHECK(cudaMalloc(&w.img, w.bytes));
+  w.Cin = Cin; w.Cout = Cout; w.ksize = ksize; w.dil = dilation;
+}
+
 void conv_tc_release(ConvWeightsTC& w) {
   if (w.img) cudaFree(w.img);
-  if (w.bias) cudaFree(w.bias);
+  if (w.bias && w.bias_owned) cudaFree(w.bias);
   w = ConvWeightsTC{};
 }
 

@@ -12,7 +12,11 @@ struct ConvWeightsTC {
   float* bias = nullptr;          // [Cout] or NULL
   int Cin = 0, Cout = 0, ksize = 0, dil = 1;
   size_t bytes = 0;
+  bool bias_owned = true;         // false: bias points into a parameter vector owned by the model (training)
 };
+
+// uninitialised image of the given geometry (filled on the device: ncsn_train_kernels.h launch_build_conv_image)
+void conv_tc_alloc(ConvWeightsTC& w, int ksize, int Cin, int Cout, int dilation);
 
 // kernel: Keras HWIO [k,k,Cin,Cout] on the host; bias may be NULL.
 void conv_tc_prepare(ConvWeightsTC& w, const float* kernel_hwio, const float* bias, int ksize, int Cin, int Cout,

@@ -63,7 +63,8 @@ __global__ void __launch_bounds__(256) k_in_stats(const float* __restrict__ x, d
 }
 
 // ---- out = gamma*(gin*(x-mu)*rsqrt(var+eps)+bin) + alpha*mu_tilde + beta  ==  a*x + b per (n,c).  grid N.
-__global__ void __launch_bounds__(512) k_in_coef(const double* __restrict__ sums, const float* __restrict__ gab,
+__global__ void __launch_bounds__(512) k_in_coef(const double* __restrict__ sums, const float* __restrict__ g_gamma,
+                                                 const float* __restrict__ g_alpha, const float* __restrict__ g_beta,
                                                  int gab_stride_n, const int* __restrict__ idx,
                                                  const float* __restrict__ in_gamma, const float* __restrict__ in_beta,
                                                  float2* __restrict__ coef, int HW, int C) {
@@ -93,8 +94,8 @@ __global__ void __launch_bounds__(512) k_in_coef(const double* __restrict__ sums
   __syncthreads();
   if (c >= C) return;
   const double mt = (mu - stat[0]) / sqrt(stat[1] + kPlusEps);
-  const float* row = gab + (size_t)(idx ? idx[n] : 0) * gab_stride_n;      // [gamma | alpha | beta]
-  const float gamma = row[c], alpha = row[C + c], beta = row[2 * C + c];
+  const size_t row = (size_t)(idx ? idx[n] : 0) * gab_stride_n;            // Embedding row of this sample (v1)
+  const float gamma = g_gamma[row + c], alpha = g_alpha[row + c], beta = g_beta[row + c];
   const float rs = rsqrtf((float)var + kInEps);
   const float gi = in_gamma[c], bi = in_beta[c];
   const float aa = gamma * gi * rs;
@@ -273,7 +274,7 @@ __global__ void __launch_bounds__(256) k_begin_conv(const float* __restrict__ x,
 constexpr int kEndPix = 8;
 __global__ void __launch_bounds__(256) k_end_conv(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ x_lo,
                                                   const float* __restrict__ k,
-                                                  float bias, const float* __restrict__ sigmas, const int* __restrict__ idx,
+                                                  const float* __restrict__ bias, const float* __restrict__ sigmas, const int* __restrict__ idx,
                                                   float* __restrict__ y, int H, int W, int C, long long pixels) {
   const long long g = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -321,7 +322,7 @@ __global__ void __launch_bounds__(256) k_end_conv(const __nv_bfloat16* __restric
     }
     acc = warp_sum(acc);
     if (lane == 0) {
-      float o = acc + bias;
+      float o = acc + __ldg(bias);
       if (sigmas) o /= sigmas[idx[p / ((long long)H * W)]];
       y[p] = o;
     }
@@ -341,11 +342,12 @@ void launch_in_stats(const float* x, double* sums, int N, int HW, int C, cudaStr
   ASEP_LAUNCH_CHECK();
 }
 
-void launch_in_coef(const double* sums, const float* gab, int gab_stride_n, const int* idx, const float* in_gamma,
+void launch_in_coef(const double* sums, const float* gamma, const float* alpha, const float* beta, int gab_stride_n,
+                    const int* idx, const float* in_gamma,
                     const float* in_beta, float2* coef, int N, int HW, int C, cudaStream_t s) {
   const int threads = (C + 31) / 32 * 32;
   ASEP_CHECK(threads <= 512, ASEP_ERR_UNSUPPORTED, "instance-norm coefficients: C = %d > 512", C);
-  k_in_coef<<<N, threads, 0, s>>>(sums, gab, gab_stride_n, idx, in_gamma, in_beta, coef, HW, C);
+  k_in_coef<<<N, threads, 0, s>>>(sums, gamma, alpha, beta, gab_stride_n, idx, in_gamma, in_beta, coef, HW, C);
   ASEP_LAUNCH_CHECK();
 }
 
@@ -406,7 +408,7 @@ void launch_begin_conv(const float* x, const float* k, const float* bias, float*
   ASEP_LAUNCH_CHECK();
 }
 
-void launch_end_conv(const __nv_bfloat16* x, const __nv_bfloat16* x_lo, const float* k, float bias, const float* sigmas, const int* idx, float* y,
+void launch_end_conv(const __nv_bfloat16* x, const __nv_bfloat16* x_lo, const float* k, const float* bias, const float* sigmas, const int* idx, float* y,
                      int N, int H, int W, int C, cudaStream_t s) {
   const long long pixels = (long long)N * H * W;
   ASEP_CHECK(C % 8 == 0 && C <= 256, ASEP_ERR_UNSUPPORTED, "end_conv: C = %d (multiple of 8, <= 256)", C);

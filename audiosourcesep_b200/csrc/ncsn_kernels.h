@@ -7,9 +7,10 @@ namespace asep {
 // sums[N,C,2] (double) = per-(n,c) sum and sum of squares over HW (zeroed by the launcher)
 void launch_in_stats(const float* x, double* sums, int N, int HW, int C, cudaStream_t s);
 // (Conditional)InstanceNorm2dPlus folded to out = a*x + b per (n,c)  (score_network.py:203-221,
-// score_network_v2.py:188-199).  gab rows are [gamma | alpha | beta] (3C floats): the Embedding row idx[n] (v1,
-// gab_stride_n = 3C) or one shared row (v2, idx = NULL).
-void launch_in_coef(const double* sums, const float* gab, int gab_stride_n, const int* idx, const float* in_gamma,
+// score_network_v2.py:188-199).  gamma / alpha / beta: v1 = the three thirds of the Embedding table [classes, 3C], row
+// idx[n] (gab_stride_n = 3C floats between rows); v2 = three shared vectors (idx = NULL, stride 0).
+void launch_in_coef(const double* sums, const float* gamma, const float* alpha, const float* beta, int gab_stride_n,
+                    const int* idx, const float* in_gamma,
                     const float* in_beta, float2* coef, int N, int HW, int C, cudaStream_t s);
 // y (bf16) = act(coef.a * x + coef.b); coef may be NULL (plain cast); do_elu applies ELU(alpha=1)
 // y_lo (may be NULL) receives bf16(v - y): the low word of the split-bf16 operand (ASEP_PREC_BF16X3)
@@ -28,7 +29,8 @@ void launch_add(const float* x, const float* z, float* y, long long n, cudaStrea
 void launch_begin_conv(const float* x, const float* k, const float* bias, float* y, int N, int H, int W, int Cout,
                        int rescale, cudaStream_t s);
 // end_conv 3x3 (C -> 1) on the bf16 normalised/activated tensor; sigmas != NULL divides by sigmas[idx[n]] (v2)
-void launch_end_conv(const __nv_bfloat16* x, const __nv_bfloat16* x_lo, const float* k, float bias, const float* sigmas, const int* idx, float* y,
+// (bias: device pointer to the single bias value)
+void launch_end_conv(const __nv_bfloat16* x, const __nv_bfloat16* x_lo, const float* k, const float* bias, const float* sigmas, const int* idx, float* y,
                      int N, int H, int W, int C, cudaStream_t s);
 
 }  // namespace asep

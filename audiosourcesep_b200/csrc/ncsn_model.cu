@@ -21,11 +21,14 @@ NcsnModel::NcsnModel(const asep_ncsn_cfg& cfg, int device) : cfg_(cfg), device_(
 
 NcsnModel::~NcsnModel() {
   for (auto& kv : params_)
-    if (kv.second.dev) cudaFree(kv.second.dev);
+    if (kv.second.dev && kv.second.flat_off < 0) cudaFree(kv.second.dev);
   for (auto& kv : convs_) conv_tc_release(kv.second);
   for (auto& kv : convs_lo_) conv_tc_release(kv.second);
-  for (auto& kv : gab_)
-    if (kv.second) cudaFree(kv.second);
+  for (auto& kv : convs_t_) conv_tc_release(kv.second);
+  for (auto& kv : convs_t_lo_) conv_tc_release(kv.second);
+  for (void* p : {(void*)theta_, (void*)adam_m_, (void*)adam_v_, (void*)garena_, (void*)xt_, (void*)tscore_, (void*)gscore_,
+                  (void*)loss_acc_})
+    if (p) cudaFree(p);
   if (sigmas_dev_) cudaFree(sigmas_dev_);
   if (arena_) cudaFree(arena_);
   if (score_buf_) cudaFree(score_buf_);
@@ -63,6 +66,17 @@ const int* NcsnModel::index_scratch(int N, int sigma_idx, cudaStream_t s) {
 void NcsnModel::set_param(const std::string& name, const float* src, const std::vector<int64_t>& shape, bool on_device) {
   int64_t n = 1;
   for (auto v : shape) n *= v;
+  if (training_) {                                 // the parameter lives in the flat vector: overwrite its slice
+    auto it = params_.find(name);
+    ASEP_CHECK(it != params_.end() && (int64_t)it->second.host.size() == n, ASEP_ERR_BAD_SHAPE,
+               "'%s': a training handle only accepts values of the existing shape", name.c_str());
+    NcsnParam& q = it->second;
+    if (on_device) CUDA_CHECK(cudaMemcpy(q.host.data(), src, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost));
+    else std::memcpy(q.host.data(), src, (size_t)n * sizeof(float));
+    CUDA_CHECK(cudaMemcpy(q.dev, q.host.data(), (size_t)n * sizeof(float), cudaMemcpyHostToDevice));
+    images_dirty_ = true;
+    return;
+  }
   NcsnParam& p = params_[name];
   if (p.dev && (int64_t)p.host.size() != n) { cudaFree(p.dev); p.dev = nullptr; }
   p.shape = shape;
@@ -96,15 +110,17 @@ const NcsnParam& NcsnModel::param(const std::string& name) const {
 
 void NcsnModel::prepare() {
   CUDA_CHECK(cudaSetDevice(device_));
+  if (training_) {                                 // weights live on the device: only the tile images are derived
+    CUDA_CHECK(cudaDeviceSynchronize());
+    refresh_images(nullptr);
+    return;
+  }
   ++generation_;                                   // tile images / packed rows below are re-allocated
   CUDA_CHECK(cudaDeviceSynchronize());             // a graph replay may still be reading them
   for (auto& kv : convs_) conv_tc_release(kv.second);
   convs_.clear();
   for (auto& kv : convs_lo_) conv_tc_release(kv.second);
   convs_lo_.clear();
-  for (auto& kv : gab_)
-    if (kv.second) cudaFree(kv.second);
-  gab_.clear();
   for (auto& kv : params_) {
     const std::string& name = kv.first;
     const size_t pos = name.rfind('/');
@@ -121,17 +137,6 @@ void NcsnModel::prepare() {
         for (size_t i = 0; i < lo.size(); ++i) lo[i] = kv.second.host[i] - __bfloat162float(__float2bfloat16(kv.second.host[i]));
         conv_tc_prepare(convs_lo_[layer], lo.data(), nullptr, (int)sh[0], (int)sh[2], (int)sh[3], dil);
       }
-    } else if (!v1_ && leaf == "gamma") {
-      // v2 InstanceNorm2dPlus: pack the three per-channel vectors as one [gamma | alpha | beta] row
-      const int C = (int)kv.second.host.size();
-      std::vector<float> row((size_t)3 * C);
-      std::memcpy(row.data(), kv.second.host.data(), C * sizeof(float));
-      std::memcpy(row.data() + C, param(layer + "/alpha").host.data(), C * sizeof(float));
-      std::memcpy(row.data() + 2 * C, param(layer + "/beta").host.data(), C * sizeof(float));
-      float* d = nullptr;
-      CUDA_CHECK(cudaMalloc(&d, row.size() * sizeof(float)));
-      CUDA_CHECK(cudaMemcpy(d, row.data(), row.size() * sizeof(float), cudaMemcpyHostToDevice));
-      gab_[layer] = d;
     }
   }
   if (!v1_) ASEP_CHECK(sigmas_dev_ != nullptr, ASEP_ERR_STATE, "NCSN v2 needs the noise levels (asep_ncsn_set_sigmas)");
@@ -150,10 +155,21 @@ void* NcsnModel::take(size_t bytes) {
   arena_off_ += al;
   return p;
 }
+void* NcsnModel::take_g(size_t bytes) {
+  const size_t al = (bytes + 1023) & ~(size_t)1023;
+  void* p = dry_ ? nullptr : garena_ + garena_off_;
+  if (!dry_) ASEP_CHECK(garena_off_ + al <= garena_cap_, ASEP_ERR_STATE, "score-network gradient arena overflow");
+  garena_off_ += al;
+  return p;
+}
 NcsnModel::T NcsnModel::new_t(int H, int W, int C) {
   T t;
   t.H = H; t.W = W; t.C = C;
   t.p = static_cast<float*>(take((size_t)N_ * H * W * C * sizeof(float)));
+  if (train_) {
+    t.g = static_cast<float*>(take_g((size_t)N_ * H * W * C * sizeof(float)));
+    if (!dry_) grad_of_[t.p] = t.g;
+  }
   return t;
 }
 __nv_bfloat16* NcsnModel::new_bf(int H, int W, int C) {
@@ -161,40 +177,51 @@ __nv_bfloat16* NcsnModel::new_bf(int H, int W, int C) {
 }
 
 // ------------------------------------------------------------------ layers
-const float2* NcsnModel::norm_coef(const T& x, const std::string& name) {
+NcsnModel::Norm NcsnModel::norm_coef(const T& x, const std::string& name) {
   double* sums = x.sums ? x.sums : static_cast<double*>(take((size_t)N_ * x.C * 2 * sizeof(double)));
   float2* coef = static_cast<float2*>(take((size_t)N_ * x.C * sizeof(float2)));
   const NcsnParam& ig = param(name + "/in_gamma");
   const NcsnParam& ib = param(name + "/in_beta");
-  const float* gab = nullptr;
+  const float *gamma = nullptr, *alpha = nullptr, *beta = nullptr;
   int stride = 0;
   if (v1_) {
     const NcsnParam& e = param(name + "/embed");
     ASEP_CHECK(e.shape.size() == 2 && e.shape[1] == 3 * x.C, ASEP_ERR_BAD_SHAPE, "%s/embed: expected [classes, %d]",
                name.c_str(), 3 * x.C);
-    gab = e.dev;
+    gamma = e.dev; alpha = e.dev + x.C; beta = e.dev + 2 * x.C;      // Embedding row = [gamma | alpha | beta]
     stride = 3 * x.C;
   } else {
-    auto it = gab_.find(name);
-    ASEP_CHECK(it != gab_.end(), ASEP_ERR_STATE, "norm layer '%s' has no parameters", name.c_str());
-    gab = it->second;
+    const NcsnParam &g = param(name + "/gamma"), &a = param(name + "/alpha"), &b = param(name + "/beta");
+    ASEP_CHECK((int)g.host.size() == x.C && (int)a.host.size() == x.C && (int)b.host.size() == x.C, ASEP_ERR_BAD_SHAPE,
+               "%s: channel mismatch", name.c_str());
+    gamma = g.dev; alpha = a.dev; beta = b.dev;
   }
   ASEP_CHECK((int)ig.host.size() == x.C && (int)ib.host.size() == x.C, ASEP_ERR_BAD_SHAPE, "%s: channel mismatch", name.c_str());
-  if (dry_) return coef;
+  Norm out;
+  out.coef = coef; out.sums = sums; out.name = name;
+  if (dry_) return out;
   if (!x.sums) launch_in_stats(x.p, sums, N_, x.H * x.W, x.C, s_);   // conv outputs arrive with their statistics
-  launch_in_coef(sums, gab, stride, v1_ ? idx_ : nullptr, ig.dev, ib.dev, coef, N_, x.H * x.W, x.C, s_);
-  return coef;
+  launch_in_coef(sums, gamma, alpha, beta, stride, v1_ ? idx_ : nullptr, ig.dev, ib.dev, coef, N_, x.H * x.W, x.C, s_);
+  return out;
 }
 
-NcsnModel::BF NcsnModel::prep(const T& x, const float2* coef, bool elu) {
+NcsnModel::BF NcsnModel::prep(const T& x, const Norm& norm, bool elu, const T* stat_src) {
   BF y;
-  if (coef == nullptr && !elu && x.bf != nullptr) {      // plain cast already done by the producing convolution
+  const size_t n = (size_t)N_ * x.H * x.W * x.C;
+  if (train_) y.gy = static_cast<float*>(take_g(n * sizeof(float)));
+  Op op;
+  op.kind = Op::kPrep; op.a = x; op.b = stat_src ? *stat_src : x; op.norm = norm; op.elu = elu;
+  if (norm.coef == nullptr && !elu && x.bf != nullptr) {      // plain cast already done by the producing convolution
     y.hi = x.bf;
+    op.bf = y;
+    record(op);
     return y;
   }
   y.hi = new_bf(x.H, x.W, x.C);
   if (x3_) y.lo = new_bf(x.H, x.W, x.C);
-  if (!dry_) launch_prep(x.p, coef, y.hi, y.lo, N_, x.H * x.W, x.C, elu ? 1 : 0, s_);
+  if (!dry_) launch_prep(x.p, norm.coef, y.hi, y.lo, N_, x.H * x.W, x.C, elu ? 1 : 0, s_);
+  op.bf = y;
+  record(op);
   return y;
 }
 
@@ -207,6 +234,12 @@ NcsnModel::T NcsnModel::conv(const std::string& name, const BF& xin, int H, int 
   if (stats) out.sums = static_cast<double*>(take((size_t)N_ * w.Cout * 2 * sizeof(double)));
   if (bf16_copy && !x3_) out.bf = new_bf(H, W, w.Cout);            // (the x3 mode needs the lo word too: k_prep writes both)
   if (dry_) return out;
+  {
+    Op op;
+    op.kind = Op::kConv; op.out = out; op.bf = xin; op.name = name; op.add = add;
+    op.a.H = H; op.a.W = W;
+    record(op);
+  }
   if (!x3_) {
     conv_tc_forward(w, xin.hi, add, out.p, N_, H, W, s_, out.sums, out.bf);
     return out;
@@ -226,14 +259,14 @@ NcsnModel::T NcsnModel::conv(const std::string& name, const BF& xin, int H, int 
 // (Conditional)ResidualBlock: score_network.py:165-178 / score_network_v2.py:156-171
 NcsnModel::T NcsnModel::res_block(const T& x, const std::string& name, int cout, bool down, int dilation) {
   (void)cout; (void)dilation;
-  const float2* c1 = norm_coef(x, name + "/norm1");
+  const Norm c1 = norm_coef(x, name + "/norm1");
   const BF h = prep(x, c1, true);
   T o1 = conv(name + "/conv1", h, x.H, x.W, nullptr, true);                   // norm2 follows
-  const float2* c2 = norm_coef(o1, name + "/norm2");
+  const Norm c2 = norm_coef(o1, name + "/norm2");
   const BF h2 = prep(o1, c2, true);
   const float* sc = x.p;
   if (has(name + "/shortcut/kernel")) {
-    const BF xr = prep(x, nullptr, false);
+    const BF xr = prep(x, Norm{}, false);
     sc = conv(name + "/shortcut", xr, x.H, x.W, nullptr, false).p;
   }
   const bool pool = down && name.rfind("Res2_", 0) == 0;  // only the undilated 'down' block pools (score_network.py:141-144)
@@ -243,6 +276,7 @@ NcsnModel::T NcsnModel::res_block(const T& x, const std::string& name, int cout,
   // avg_pool2(shortcut) + avg_pool2(output) == avg_pool2(shortcut + output)
   T out = new_t(x.H / 2, x.W / 2, o2.C);
   if (!dry_) launch_avgpool2(o2.p, out.p, N_, out.H, out.W, out.C, s_);
+  { Op op; op.kind = Op::kAvgPool2; op.a = o2; op.out = out; record(op); }
   return out;
 }
 
@@ -252,7 +286,7 @@ NcsnModel::T NcsnModel::rcu(T x, const std::string& prefix, int n_blocks, int n_
     const T residual = x;
     for (int j = 0; j < n_stages; ++j) {
       const std::string sfx = "_" + std::to_string(i + 1) + "_" + std::to_string(j + 1);
-      const float2* c = v1_ ? norm_coef(x, prefix + "/norm" + sfx) : nullptr;
+      const Norm c = v1_ ? norm_coef(x, prefix + "/norm" + sfx) : Norm{};
       const BF h = prep(x, c, false);
       x = conv(prefix + "/conv" + sfx, h, x.H, x.W, j == n_stages - 1 ? residual.p : nullptr, v1_, !v1_);
     }
@@ -264,17 +298,20 @@ NcsnModel::T NcsnModel::rcu(T x, const std::string& prefix, int n_blocks, int n_
 NcsnModel::T NcsnModel::crp(T x, const std::string& prefix) {
   T acc = new_t(x.H, x.W, x.C);
   if (!dry_) launch_elu(x.p, acc.p, (long long)N_ * x.H * x.W * x.C, s_);
+  { Op op; op.kind = Op::kElu; op.a = x; op.out = acc; record(op); }
   T path = acc;
   for (int i = 0; i < 2; ++i) {
     const std::string sfx = "_" + std::to_string(i + 1);
     // avg over the in-bounds taps commutes with the per-(n,c) affine of the norm: pool first, normalise while casting
-    const float2* c = v1_ ? norm_coef(path, prefix + "/norm" + sfx) : nullptr;
+    const Norm c = v1_ ? norm_coef(path, prefix + "/norm" + sfx) : Norm{};
     T pooled = new_t(x.H, x.W, x.C), ptmp = new_t(x.H, x.W, x.C);
     if (!dry_) launch_pool5(path.p, ptmp.p, pooled.p, N_, x.H, x.W, x.C, v1_ ? 0 : 1, s_);
-    const BF h = prep(pooled, c, false);
+    { Op op; op.kind = Op::kPool5; op.a = path; op.b = ptmp; op.out = pooled; record(op); }
+    const BF h = prep(pooled, c, false, &path);
     path = conv(prefix + "/conv" + sfx, h, x.H, x.W, nullptr, v1_ && i == 0);
     T sum = new_t(x.H, x.W, x.C);
     if (!dry_) launch_add(acc.p, path.p, sum.p, (long long)N_ * x.H * x.W * x.C, s_);
+    { Op op; op.kind = Op::kAdd; op.a = acc; op.b = path; op.out = sum; record(op); }
     acc = sum;
   }
   return acc;
@@ -291,7 +328,7 @@ NcsnModel::T NcsnModel::msf(const std::vector<T>& xs, const std::string& prefix,
       const bool same = xi.H == H && xi.W == W;
       if (same != (pass == 0)) continue;
       const std::string sfx = "_" + std::to_string(i + 1);
-      const float2* c = v1_ ? norm_coef(xi, prefix + "/norm" + sfx) : nullptr;
+      const Norm c = v1_ ? norm_coef(xi, prefix + "/norm" + sfx) : Norm{};
       const BF h = prep(xi, c, false);
       if (same) {
         sums = conv(prefix + "/conv" + sfx, h, xi.H, xi.W, sums.p, false);
@@ -300,6 +337,7 @@ NcsnModel::T NcsnModel::msf(const std::vector<T>& xs, const std::string& prefix,
         T low = conv(prefix + "/conv" + sfx, h, xi.H, xi.W, nullptr, false);
         T up = new_t(H, W, low.C);
         if (!dry_) launch_resize2x_add(low.p, sums.p, up.p, N_, xi.H, xi.W, low.C, s_);
+        { Op op; op.kind = Op::kResizeAdd; op.a = low; op.b = sums; op.out = up; record(op); }
         sums = up;
       }
     }
@@ -323,6 +361,7 @@ void NcsnModel::run(const float* x, const int* idx, float* score) {
   const NcsnParam& bb = param("begin_conv/bias");
   ASEP_CHECK((int64_t)bk.host.size() == 9 * ngf && (int)bb.host.size() == ngf, ASEP_ERR_BAD_SHAPE, "begin_conv shape");
   if (!dry_) launch_begin_conv(x, bk.dev, bb.dev, out.p, N_, H, W, ngf, v1_ ? 1 : 0, s_);   // 2x-1 only in v1 (Q10)
+  { Op op; op.kind = Op::kBegin; op.out = out; record(op); }
   T l1 = res_block(res_block(out, "Res1_1", ngf, false, 0), "Res1_2", ngf, false, 0);
   T l2 = res_block(res_block(l1, "Res2_1", 2 * ngf, true, 0), "Res2_2", 2 * ngf, false, 0);
   T l3 = res_block(res_block(l2, "Res3_1", 2 * ngf, true, 2), "Res3_2", 2 * ngf, false, 2);
@@ -331,13 +370,14 @@ void NcsnModel::run(const float* x, const int* idx, float* score) {
   T r2 = refine({l3, r1}, "refine2", 2 * ngf, false, l3.H, l3.W);
   T r3 = refine({l2, r2}, "refine3", ngf, false, l2.H, l2.W);
   T o = refine({l1, r3}, "refine4", ngf, true, l1.H, l1.W);
-  const float2* c = norm_coef(o, "normalizer");
+  const Norm c = norm_coef(o, "normalizer");
   const BF h = prep(o, c, true);
   const NcsnParam& ek = param("end_conv/kernel");
   const NcsnParam& eb = param("end_conv/bias");
   ASEP_CHECK((int64_t)ek.host.size() == 9 * ngf && eb.host.size() == 1, ASEP_ERR_BAD_SHAPE, "end_conv shape");
   if (!dry_)
-    launch_end_conv(h.hi, h.lo, ek.dev, eb.host[0], v1_ ? nullptr : sigmas_dev_, v1_ ? nullptr : idx, score, N_, H, W, ngf, s_);
+    launch_end_conv(h.hi, h.lo, ek.dev, eb.dev, v1_ ? nullptr : sigmas_dev_, v1_ ? nullptr : idx, score, N_, H, W, ngf, s_);
+  { Op op; op.kind = Op::kEnd; op.bf = h; op.a = o; record(op); }
 }
 
 void NcsnModel::forward(const float* x, const int* idx, float* score, int N, cudaStream_t s) {
@@ -346,6 +386,7 @@ void NcsnModel::forward(const float* x, const int* idx, float* score, int N, cud
   CUDA_CHECK(cudaSetDevice(device_));
   s_ = s;
   N_ = N;
+  if (training_ && images_dirty_) refresh_images(s);
   dry_ = true; arena_off_ = 0;
   run(nullptr, nullptr, nullptr);
   const size_t need = arena_off_;

@@ -101,3 +101,61 @@ class ScoreModel:
     @property
     def handle(self) -> ctypes.c_void_p:
         return self._h
+
+    # ---- training surface (reference: train_ncsn.py:26-57; the arithmetic runs in libasep.so)
+    def enable_training(self) -> None:
+        """Moves every parameter into one flat fp32 device vector and builds the data-gradient weight images."""
+        _lib.check(self._lib.asep_ncsn_enable_training(self._h))
+        n = ctypes.c_int64()
+        _lib.check(self._lib.asep_ncsn_num_trainable(self._h, ctypes.byref(n)))
+        self.num_trainable = int(n.value)
+        self._spans = {}
+        for name in self._shapes:
+            off, cnt = ctypes.c_int64(), ctypes.c_int64()
+            _lib.check(self._lib.asep_ncsn_param_span(self._h, name.encode(), ctypes.byref(off), ctypes.byref(cnt)))
+            self._spans[name] = (int(off.value), int(cnt.value))
+
+    def train_grads(self, x: torch.Tensor, noise: torch.Tensor, sigma_idx, global_batch: int):
+        """Gradient of the denoising-score-matching loss of this rank's samples w.r.t. the flat parameter vector, and
+        the loss (both pre-divided by ``global_batch``, so the SUM over data-parallel ranks is the reference's
+        ``compute_average_loss``).  ``noise``: standard-normal draws; perturbed_X = x + sigma[idx] * noise."""
+        x = torch.as_tensor(x, dtype=torch.float32).to(self.device).contiguous()
+        noise = torch.as_tensor(noise, dtype=torch.float32).to(self.device).contiguous()
+        idx = torch.as_tensor(sigma_idx)
+        if idx.ndim == 0 or idx.numel() == 1:        # train_ncsn.py:34-35: one level for the whole replica batch when C == 1
+            idx = idx.reshape(-1)[:1].repeat(x.shape[0])
+        idx = idx.to(device=self.device, dtype=torch.int32).contiguous()
+        grads = torch.empty((self.num_trainable,), dtype=torch.float32, device=self.device)
+        loss = torch.empty((1,), dtype=torch.float32, device=self.device)
+        d = [_lib.dl(t) for t in (x, noise, idx, grads, loss)]
+        _lib.check(self._lib.asep_ncsn_train_grads(self._h, d[0].ptr, d[1].ptr, d[2].ptr, int(global_batch), d[3].ptr, d[4].ptr,
+                                                   _lib.stream_ptr()))
+        return grads, loss
+
+    def apply_gradients(self, grads: torch.Tensor, optimizer: dict) -> None:
+        """Keras Adam (train_utils.py:27-28) on the flat vector; the tile images are rebuilt on the device."""
+        if optimizer.get("kind", "adam") != "adam":
+            raise ValueError("the score networks train with Adam (train_ncsn.py:405-406 default)")
+        d = _lib.dl(grads)
+        _lib.check(self._lib.asep_ncsn_adam_step(self._h, d.ptr, float(optimizer["lr"]), float(optimizer["beta1"]),
+                                                 float(optimizer["beta2"]), float(optimizer["eps"]), _lib.stream_ptr()))
+
+    def get_flat(self) -> torch.Tensor:
+        theta = torch.empty((self.num_trainable,), dtype=torch.float32, device=self.device)
+        d = _lib.dl(theta)
+        _lib.check(self._lib.asep_ncsn_get_flat(self._h, d.ptr, _lib.stream_ptr()))
+        return theta
+
+    def set_flat(self, theta: torch.Tensor) -> None:
+        theta = torch.as_tensor(theta, dtype=torch.float32).to(self.device).contiguous()
+        d = _lib.dl(theta)
+        _lib.check(self._lib.asep_ncsn_set_flat(self._h, d.ptr, _lib.stream_ptr()))
+
+    def unflatten(self, flat: torch.Tensor) -> Dict[str, np.ndarray]:
+        """Splits a flat vector (parameters or gradients) into the named tensors of ``ncsn_param_shapes``."""
+        host = flat.detach().cpu().numpy()
+        return {name: host[off:off + cnt].reshape(self._shapes[name]).copy() for name, (off, cnt) in self._spans.items()}
+
+    def sync_host(self) -> None:
+        """``variables`` <- the trained values (checkpoint writers read them)."""
+        self._params = self.unflatten(self.get_flat())

@@ -202,6 +202,24 @@ int asep_ncsn_set_precision(asep_ncsn_t h, int precision);
 int asep_ncsn_prepare(asep_ncsn_t h);
 /* score = model([x, sigma_idx], training=True): x [N,H,W,1] float32, sigma_idx [N] int32 -> score [N,H,W,1]. */
 int asep_ncsn_forward(asep_ncsn_t h, const DLTensor* x, const DLTensor* sigma_idx, DLTensor* score, void* stream);
+/* ---- NCSN denoising-score-matching training (replaces train_ncsn.py:26-57 train_step: get_noise_conditionned_data,
+ * compute_train_loss, tape.gradient, optimizer.apply_gradients; optimizer of train_utils.py:23-41).
+ * enable_training moves every parameter into one flat fp32 device vector (name order, each tensor 16-byte aligned) and
+ * builds the data-gradient weight images; param_span gives a parameter's offset / element count in that vector.
+ * train_grads: x [N,H,W,1] data, noise [N,H,W,1] standard-normal draws, sigma_idx [N] int32; perturbed_X = x +
+ * sigma[idx] * noise; grads [num_trainable] <- d loss / d theta with loss [1] = sum_n 1/2 ||score + noise/sigma_n||^2 *
+ * sigma_n^2 / global_batch (the SUM over data-parallel ranks is the reference's compute_average_loss).  The three GEMMs of
+ * every convolution (forward, data gradient, weight gradient) run on tcgen05 in the handle's precision mode.
+ * adam_step: Keras Adam on the flat vector, then the tile images are rebuilt on the device. */
+int asep_ncsn_enable_training(asep_ncsn_t h);
+int asep_ncsn_num_trainable(asep_ncsn_t h, int64_t* out);
+int asep_ncsn_param_span(asep_ncsn_t h, const char* name, int64_t* offset, int64_t* numel);
+int asep_ncsn_train_grads(asep_ncsn_t h, const DLTensor* x, const DLTensor* noise, const DLTensor* sigma_idx,
+                          int global_batch, DLTensor* grads, DLTensor* loss, void* stream);
+int asep_ncsn_adam_step(asep_ncsn_t h, const DLTensor* grads, float lr, float beta1, float beta2, float eps,
+                        void* stream);
+int asep_ncsn_get_flat(asep_ncsn_t h, DLTensor* theta, void* stream);
+int asep_ncsn_set_flat(asep_ncsn_t h, const DLTensor* theta, void* stream);
 /* T inner Langevin steps at noise level sigma_idx with two score networks (run_basis_sep.py:152-181, model_type
  * 'ncsn'); arguments as asep_basis_glow_inner. */
 int asep_basis_ncsn_inner(asep_ncsn_t m1, asep_ncsn_t m2, const DLTensor* mixed, DLTensor* x1, DLTensor* x2,

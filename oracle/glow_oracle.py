@@ -60,7 +60,7 @@ def conv2d_same(x: torch.Tensor, k_hwio: torch.Tensor, bias: Optional[torch.Tens
     """TF ``padding='same'`` stride-1 cross-correlation on NHWC with HWIO filters."""
     kh = k_hwio.shape[0]
     pad = dilation * (kh // 2)
-    y = F.conv2d(x.permute(0, 3, 1, 2), k_hwio.permute(3, 2, 0, 1), bias, padding=pad, dilation=dilation)
+    y = F.conv2d(x.permute(0, 3, 1, 2).contiguous(), k_hwio.permute(3, 2, 0, 1).contiguous(), bias, padding=pad, dilation=dilation)
     return y.permute(0, 2, 3, 1)
 
 
