@@ -269,63 +269,64 @@ __global__ void __launch_bounds__(256) k_begin_conv(const float* __restrict__ x,
 }
 
 // ---- end_conv: 3x3 'same', C -> 1 channel, bias, optional division by sigma[idx[n]].
-// One warp per group of kPix consecutive pixels; a lane owns 8 channels (one 16-byte load per tap and pixel) and keeps
-// its 9 x 8 kernel weights in registers for the whole group, so a pixel costs 9 loads + a warp reduction.
-constexpr int kEndPix = 8;
+// One warp per pixel; a lane owns 8 channels.  The nine 16-byte tap loads of a lane are issued back to back (out-of-image
+// taps load nothing and contribute zero), the 9 x C kernel sits in shared memory.
+__device__ __forceinline__ float dot8_bf16(const uint4 u, const float4 ka, const float4 kb, float acc) {
+  acc = fmaf(__uint_as_float(u.x << 16), ka.x, acc); acc = fmaf(__uint_as_float(u.x & 0xffff0000u), ka.y, acc);
+  acc = fmaf(__uint_as_float(u.y << 16), ka.z, acc); acc = fmaf(__uint_as_float(u.y & 0xffff0000u), ka.w, acc);
+  acc = fmaf(__uint_as_float(u.z << 16), kb.x, acc); acc = fmaf(__uint_as_float(u.z & 0xffff0000u), kb.y, acc);
+  acc = fmaf(__uint_as_float(u.w << 16), kb.z, acc); acc = fmaf(__uint_as_float(u.w & 0xffff0000u), kb.w, acc);
+  return acc;
+}
+
 __global__ void __launch_bounds__(256) k_end_conv(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ x_lo,
                                                   const float* __restrict__ k,
                                                   const float* __restrict__ bias, const float* __restrict__ sigmas, const int* __restrict__ idx,
                                                   float* __restrict__ y, int H, int W, int C, long long pixels) {
-  const long long g = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  extern __shared__ __align__(16) float skw[];      // [9 * C]
+  for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) skw[i] = __ldg(k + i);
+  __syncthreads();
+  const long long p = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  const long long p0 = g * kEndPix;
-  if (p0 >= pixels) return;
+  if (p >= pixels) return;
   const int c0 = lane * 8;
   const bool active = c0 < C;                       // C <= 256 (checked by the launcher), C % 8 == 0
-  float kw[9][8];
+  const int w = (int)(p % W), h = (int)((p / W) % H);
+  const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+  uint4 u[9];
 #pragma unroll
   for (int tap = 0; tap < 9; ++tap) {
-    const float4 a = active ? __ldg(reinterpret_cast<const float4*>(k + (size_t)tap * C + c0)) : make_float4(0.f, 0.f, 0.f, 0.f);
-    const float4 b = active ? __ldg(reinterpret_cast<const float4*>(k + (size_t)tap * C + c0) + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
-    kw[tap][0] = a.x; kw[tap][1] = a.y; kw[tap][2] = a.z; kw[tap][3] = a.w;
-    kw[tap][4] = b.x; kw[tap][5] = b.y; kw[tap][6] = b.z; kw[tap][7] = b.w;
+    const int hh = h + tap / 3 - 1, ww = w + tap % 3 - 1;
+    const bool ok = active && hh >= 0 && hh < H && ww >= 0 && ww < W;
+    const long long off = (p + (long long)(tap / 3 - 1) * W + (tap % 3 - 1)) * C + c0;
+    u[tap] = ok ? __ldg(reinterpret_cast<const uint4*>(x + off)) : zero;
   }
-  for (int i = 0; i < kEndPix; ++i) {
-    const long long p = p0 + i;
-    if (p >= pixels) break;
-    const int w = (int)(p % W), h = (int)((p / W) % H);
-    float acc = 0.f;
+  float acc = 0.f;
+  const int cw = active ? c0 : 0;
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    const float4 ka = *reinterpret_cast<const float4*>(skw + tap * C + cw), kb = *reinterpret_cast<const float4*>(skw + tap * C + cw + 4);
+    acc = dot8_bf16(u[tap], ka, kb, acc);
+  }
+  if (x_lo) {                                       // split-bf16 operand: second term
 #pragma unroll
     for (int tap = 0; tap < 9; ++tap) {
       const int hh = h + tap / 3 - 1, ww = w + tap % 3 - 1;
-      if (hh < 0 || hh >= H || ww < 0 || ww >= W || !active) continue;
+      const bool ok = active && hh >= 0 && hh < H && ww >= 0 && ww < W;
       const long long off = (p + (long long)(tap / 3 - 1) * W + (tap % 3 - 1)) * C + c0;
-      const uint4 u = *reinterpret_cast<const uint4*>(x + off);
-      float v[8];
-      const uint32_t uw[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        v[2 * q] = __uint_as_float(uw[q] << 16);
-        v[2 * q + 1] = __uint_as_float(uw[q] & 0xffff0000u);
-      }
-      if (x_lo) {
-        const uint4 l = *reinterpret_cast<const uint4*>(x_lo + off);
-        const uint32_t lw[4] = {l.x, l.y, l.z, l.w};
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          v[2 * q] += __uint_as_float(lw[q] << 16);
-          v[2 * q + 1] += __uint_as_float(lw[q] & 0xffff0000u);
-        }
-      }
-#pragma unroll
-      for (int q = 0; q < 8; ++q) acc = fmaf(v[q], kw[tap][q], acc);
+      u[tap] = ok ? __ldg(reinterpret_cast<const uint4*>(x_lo + off)) : zero;
     }
-    acc = warp_sum(acc);
-    if (lane == 0) {
-      float o = acc + __ldg(bias);
-      if (sigmas) o /= sigmas[idx[p / ((long long)H * W)]];
-      y[p] = o;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const float4 ka = *reinterpret_cast<const float4*>(skw + tap * C + cw), kb = *reinterpret_cast<const float4*>(skw + tap * C + cw + 4);
+      acc = dot8_bf16(u[tap], ka, kb, acc);
     }
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) {
+    float o = acc + __ldg(bias);
+    if (sigmas) o /= sigmas[idx[p / ((long long)H * W)]];
+    y[p] = o;
   }
 }
 
@@ -412,8 +413,7 @@ void launch_end_conv(const __nv_bfloat16* x, const __nv_bfloat16* x_lo, const fl
                      int N, int H, int W, int C, cudaStream_t s) {
   const long long pixels = (long long)N * H * W;
   ASEP_CHECK(C % 8 == 0 && C <= 256, ASEP_ERR_UNSUPPORTED, "end_conv: C = %d (multiple of 8, <= 256)", C);
-  const long long groups = (pixels + kEndPix - 1) / kEndPix;
-  k_end_conv<<<cdiv(groups * 32, 256), 256, 0, s>>>(x, x_lo, k, bias, sigmas, idx, y, H, W, C, pixels);
+  k_end_conv<<<cdiv(pixels * 32, 256), 256, 9 * C * sizeof(float), s>>>(x, x_lo, k, bias, sigmas, idx, y, H, W, C, pixels);
   ASEP_LAUNCH_CHECK();
 }
 

@@ -586,6 +586,51 @@ def run_ours(args):
                          "the flat gradient vector; the loss is that of the reference's own (quirk Q1/Q7) initialisation on synthetic patches")
         del tm
 
+    # ---- 5b. NCSN denoising-score-matching train step (train_ncsn.py:26-57): v1 at the reference's batch 32
+    ncsn_train = None
+    if args.ncsn_train_batch > 0:
+        from audiosourcesep_b200 import NCSNConfig
+        from audiosourcesep_b200 import train_ncsn as tn
+        from audiosourcesep_b200.ncsn.score_model import ScoreModel
+        from audiosourcesep_b200.weights import init_ncsn_params
+        ncsn_train = {}
+        for ver, ncfg, gflop in (("v1", NCSNConfig(version="v1", ngf=192, num_classes=10, sigma1=1.0), 266.96),
+                                 ("v2", NCSNConfig(version="v2", ngf=128, num_classes=200, sigma1=30.0), 118.66)):
+            sig_n = bo.get_sigmas(ncfg.sigma1, ncfg.sigmaL, ncfg.num_classes, "logarithmic")
+            sm = ScoreModel(ncfg, init_ncsn_params(ncfg, seed=11, mode="faithful"), sigmas=sig_n, device=local_rank, precision=_lib.PREC_BF16)
+            sm.enable_training()
+            nopt = dict(kind="adam", lr=1e-4, beta1=0.9, beta2=0.999, eps=1e-7)
+            cases = [("weak", args.ncsn_train_batch, args.ncsn_train_batch * world)]
+            if world > 1 and args.ncsn_train_batch % world == 0:
+                cases.append(("strong", args.ncsn_train_batch // world, args.ncsn_train_batch))
+            legs = {}
+            for name, local, glob in cases:
+                xs = torch.as_tensor(synthetic.normalise(synthetic.mel_patches_db(glob, seed=400))[rank * local:(rank + 1) * local]).to(dev)
+                gen = torch.Generator(device=dev)
+                gen.manual_seed(5)                       # same noise level on every rank and step size class: comparable losses
+                hist = []
+
+                def step_nt():
+                    idx, z = tn.get_noise_conditionned_data(xs, ncfg.num_classes, gen)
+                    hist.append(tn.distributed_train_step(sm, nopt, xs, glob, idx, z))
+
+                nst = max(2, args.steps // 3)
+                t_ms, t_launches, _ = timed_loop(step_nt, nst, 2)
+                losses = [float(v.item()) for v in hist]
+                tf = glob * nst * 3 * gflop / (t_ms * 1e-3) / 1e3
+                legs[name] = {"metric": f"ncsn_{ver}_train_samples_per_s", "value": glob * nst / (t_ms * 1e-3), "unit": "samples/s",
+                              "steps_per_s": nst / (t_ms * 1e-3), "per_gpu_batch": local, "global_batch": glob, "dtype": "bf16",
+                              "ms_per_step": t_ms / nst, "gpu_launches_per_step": t_launches // nst,
+                              "allreduce_bytes_per_step": int(sm.num_trainable * 4) if world > 1 else 0,
+                              "alg_tflops": tf, "step_roofline_frac": tf / world / peaks["bf16_sustained"],
+                              "loss_finite": bool(np.all(np.isfinite(losses)))}
+            ncsn_train[ver] = legs
+            del sm
+        ncsn_train["note"] = ("denoising score matching: forward, data-gradient (k_conv_tc on transposed images) and weight-gradient "
+                              "(k_conv_wgrad_tc) convolutions on tcgen05 with bf16 operands, fp32 master weights + Adam, tile images "
+                              "rebuilt on the device every step; 3 x score-network FLOPs per sample; one noise level per replica "
+                              "batch (train_ncsn.py:34 quirk); parity of the gradients vs float64 autograd: tests/test_gpu_ncsn_train.py")
+
     # ---- 6. strong scaling of the BASIS configs: the reference's n_mixed = 30 segments SHARDED over the ranks (configs 3-5)
     strong = None
     if world > 1 and args.strong:
@@ -684,6 +729,7 @@ def run_ours(args):
         "basis": basis,
         "basis_ncsn": ncsn or None,
         "train": train,
+        "ncsn_train": ncsn_train,
         "strong": strong,
         "parity": parity,
     }
@@ -711,6 +757,7 @@ def main():
     ap.add_argument("--ncsn-segments", type=int, default=30, help="segments per GPU of the NCSN-BASIS legs (0 = skip)")
     ap.add_argument("--ncsn-T", type=int, default=8)
     ap.add_argument("--train-batch", type=int, default=32, help="per-GPU batch of the Glow train-step leg (0 = skip)")
+    ap.add_argument("--ncsn-train-batch", type=int, default=32, help="per-GPU batch of the NCSN train-step legs (0 = skip)")
     ap.add_argument("--train-fp32", action="store_true", help="train leg in the CUDA-core fp32 exact mode")
     ap.add_argument("--cpu-sample", type=int, default=4, help="patches of the CPU baseline sample (0 = skip)")
     args = ap.parse_args()

@@ -92,6 +92,23 @@ elif a.what == "train":
     xt = torch.as_tensor(synthetic.mel_patches_db(a.n, seed=300)).cuda()
     opt = dict(kind="adamax", lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-7)
     roi(lambda: tg.distributed_train_step(tm, opt, xt, a.n), warm=3)
+elif a.what == "ncsn_train":
+    from audiosourcesep_b200.ncsn import utils as bo
+    from audiosourcesep_b200.ncsn.score_model import ScoreModel
+    cfg = NCSNConfig(version="v1", ngf=192, num_classes=10) if a.version == "v1" else NCSNConfig(version="v2", ngf=128, num_classes=200, sigma1=30.0)
+    sig = bo.get_sigmas(cfg.sigma1, cfg.sigmaL, cfg.num_classes, "logarithmic")
+    m = ScoreModel(cfg, init_ncsn_params(cfg, seed=11, mode="faithful"), sigmas=sig, precision=_lib.PREC_BF16X3 if a.prec == "bf16x3" else _lib.PREC_BF16)
+    m.enable_training()
+    x = torch.as_tensor(synthetic.normalise(synthetic.mel_patches_db(a.n, seed=0))).cuda()
+    z = torch.randn(x.shape, device="cuda")
+    idx = torch.full((a.n,), cfg.num_classes // 2, dtype=torch.int32, device="cuda")
+    opt = dict(kind="adam", lr=1e-4, beta1=0.9, beta2=0.999, eps=1e-7)
+
+    def tstep():
+        g, _ = m.train_grads(x, z, idx, a.n)
+        m.apply_gradients(g, opt)
+
+    roi(tstep, warm=2)
 elif a.what == "gemm":
     A = torch.randn(8192, 8192, device="cuda", dtype=torch.bfloat16)
     B = torch.randn(8192, 8192, device="cuda", dtype=torch.bfloat16)
