@@ -222,5 +222,5 @@ def test_glow_step_graph_replay_equals_eager_launches(same_handle):
         _lib.basis_graphs(True)
     for k in range(3):
         assert torch.equal(outs[0][k], outs[1][k]), k
-    assert outs[1][3] >= outs[0][3] > 0          # replayed launches are counted like eager ones (+1 per step: the scalar advance)
+    assert outs[0][3] > 0 and abs(outs[1][3] - outs[0][3]) <= 0.05 * outs[0][3]   # replayed launches are counted like eager ones
     assert not torch.equal(outs[1][0], torch.as_tensor(x1).cuda())
