@@ -118,6 +118,9 @@ _SIGNATURES = {
     "asep_conv_profile_read": [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64),
                                ctypes.POINTER(ctypes.c_double)],
     "asep_crc32c": [ctypes.c_char_p, ctypes.c_uint64, ctypes.c_uint32],
+    "asep_bss_eval": [_P, _P, _I, ctypes.c_int64, ctypes.c_int64, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64),
+                      _I, _I, _P, _V],
+    "asep_ideal_mask": [_P, _P, _P, _I, _F, _V],
     "asep_basis_graphs": [_I],
     "asep_hbm_profile": [_I],
     "asep_hbm_profile_read": [_I, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64),

@@ -6,6 +6,7 @@
 #include <memory>
 
 #include <vector>
+#include "bsseval.h"
 #include "glow_model.h"
 #include "ncsn_model.h"
 
@@ -1061,6 +1062,38 @@ int asep_basis_graphs(int on) {
   ASEP_API_BEGIN
   basis_graphs().enabled = on != 0;
   if (!on) basis_graphs().clear();
+  ASEP_API_END
+}
+
+// ------------------------------------------------------------------ evaluation on the device (bsseval.cu)
+int asep_bss_eval(const DLTensor* reference_sources, const DLTensor* estimated_sources, int filters_len, int64_t filt_start,
+                  int64_t filt_stop, const int64_t* win_start, const int64_t* win_stop, int nwin, int sources_version,
+                  DLTensor* out, void* stream) {
+  ASEP_API_BEGIN
+  ASEP_CHECK(g_device >= 0, ASEP_ERR_STATE, "asep_init() has not been called");
+  ASEP_CHECK(win_start && win_stop && nwin >= 1, ASEP_ERR_BAD_ARG, "bss_eval: no evaluation window");
+  TView r = view_any(reference_sources, "reference_sources", g_device, false, kDLFloat, 64);
+  TView e = view_any(estimated_sources, "estimated_sources", g_device, false, kDLFloat, 64);
+  ASEP_CHECK(r.ndim == 2 && e.ndim == 2 && r.shape[0] == e.shape[0] && r.shape[1] == e.shape[1], ASEP_ERR_BAD_SHAPE,
+             "bss_eval: reference_sources and estimated_sources must both be [nsrc, nsampl] (mono images)");
+  const int nsrc = (int)r.shape[0];
+  TView o = view_any(out, "out", g_device, false, kDLFloat, 64);
+  ASEP_CHECK(o.numel == (int64_t)4 * nsrc * nsrc * nwin, ASEP_ERR_BAD_SHAPE, "bss_eval: out must be [4, nsrc, nsrc, nwin] float64");
+  std::vector<long long> w0(win_start, win_start + nwin), w1(win_stop, win_stop + nwin);
+  bss_eval_core(static_cast<const double*>(r.raw), static_cast<const double*>(e.raw), nsrc, (long long)r.shape[1], filters_len,
+                (long long)filt_start, (long long)filt_stop, w0.data(), w1.data(), nwin, sources_version,
+                static_cast<double*>(o.raw), as_stream(stream));
+  ASEP_API_END
+}
+
+int asep_ideal_mask(const DLTensor* mixture, const DLTensor* sources, DLTensor* estimates, int binary, float theta, void* stream) {
+  ASEP_API_BEGIN
+  ASEP_CHECK(g_device >= 0, ASEP_ERR_STATE, "asep_init() has not been called");
+  TView m = view_f32(mixture, "mixture", g_device), sv = view_f32(sources, "sources", g_device);
+  TView ev = view_f32(estimates, "estimates", g_device);
+  ASEP_CHECK(sv.ndim == m.ndim + 1 && sv.numel == sv.shape[0] * m.numel && ev.numel == sv.numel, ASEP_ERR_BAD_SHAPE,
+             "ideal mask: sources / estimates must be [nsrc, *mixture.shape]");
+  launch_ideal_mask(m.f32, sv.f32, ev.f32, (int)sv.shape[0], (long long)m.numel, binary, theta, as_stream(stream));
   ASEP_API_END
 }
 

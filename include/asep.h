@@ -255,6 +255,21 @@ uint32_t asep_crc32c(const void* data, uint64_t n, uint32_t crc);
 int asep_hbm_profile(int on);
 int asep_hbm_profile_read(int category, double* total_ms, int64_t* launches, double* bytes);
 
+/* ------------------------------------------------------------------ evaluation on the device
+ * BSS Eval v4 (replaces bsseval_v4.py:79-300 bss_eval; helpers :449-617) for mono images.  reference_sources /
+ * estimated_sources: device float64 [nsrc, nsampl].  The distortion filters (filters_len taps) are estimated on samples
+ * [filt_start, filt_stop) (the whole signal for framewise_filters = False, the window itself otherwise); every window
+ * [win_start[t], win_stop[t]) (HOST arrays) is decomposed into true source / spatial / interference / artifact parts
+ * and out [4, nsrc, nsrc, nwin] float64 receives (SDR, ISR, SIR, SAR)[jtrue][jest][t] (s_r of :214; NaN where a source is
+ * silent, :258-279).  sources_version = 1: the bss_eval_sources criteria (:575-585).  Framing, permutation search and
+ * the result selection (:202-213, :281-300) stay on the host (audiosourcesep_b200/bsseval_v4.py). */
+int asep_bss_eval(const DLTensor* reference_sources, const DLTensor* estimated_sources, int filters_len, int64_t filt_start,
+                  int64_t filt_stop, const int64_t* win_start, const int64_t* win_stop, int nwin, int sources_version,
+                  DLTensor* out, void* stream);
+/* IRM_melspec (binary = 0) / IBM_melspec (binary = 1, majority vote theta) of oracle_systems.py:264-350: mixture
+ * [...] and sources [nsrc, ...] fp32 mel spectrograms -> estimates [nsrc, ...]. */
+int asep_ideal_mask(const DLTensor* mixture, const DLTensor* sources, DLTensor* estimates, int binary, float theta, void* stream);
+
 /* CUDA-graph replay of whole Langevin steps inside asep_basis_{glow,ncsn}_inner (on by default; steps 2..T of a call
  * with T >= 3 are replays of one captured step whose per-step scalars live in device memory).  0 = launch every step
  * eagerly (parity tests compare the two), and drop the cached graphs. */
