@@ -121,6 +121,11 @@ _SIGNATURES = {
     "asep_bss_eval": [_P, _P, _I, ctypes.c_int64, ctypes.c_int64, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64),
                       _I, _I, _P, _V],
     "asep_ideal_mask": [_P, _P, _P, _I, _F, _V],
+    "asep_stft": [_P, _I, _I, _P, _V],
+    "asep_mel_db": [_P, _P, _P, _P, _P, _F, _F, _F, _F, _V],
+    "asep_mel_to_stft": [_P, _P, _P, _P, _P, _P, _F, _I, _V],
+    "asep_stft_filter": [_P, _P, _P, _I, _V],
+    "asep_istft": [_P, _I, _P, _V],
     "asep_basis_graphs": [_I],
     "asep_hbm_profile": [_I],
     "asep_hbm_profile_read": [_I, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64),

@@ -8,6 +8,7 @@
 #include <vector>
 #include "bsseval.h"
 #include "glow_model.h"
+#include "mel_kernels.h"
 #include "ncsn_model.h"
 
 namespace asep {
@@ -1094,6 +1095,87 @@ int asep_ideal_mask(const DLTensor* mixture, const DLTensor* sources, DLTensor* 
   ASEP_CHECK(sv.ndim == m.ndim + 1 && sv.numel == sv.shape[0] * m.numel && ev.numel == sv.numel, ASEP_ERR_BAD_SHAPE,
              "ideal mask: sources / estimates must be [nsrc, *mixture.shape]");
   launch_ideal_mask(m.f32, sv.f32, ev.f32, (int)sv.shape[0], (long long)m.numel, binary, theta, as_stream(stream));
+  ASEP_API_END
+}
+
+// ------------------------------------------------------------------ mel front end / back end (mel_kernels.cu)
+int asep_stft(const DLTensor* audio, int n_fft, int hop, DLTensor* stft, void* stream) {
+  ASEP_API_BEGIN
+  ASEP_CHECK(g_device >= 0, ASEP_ERR_STATE, "asep_init() has not been called");
+  TView a = view_f32(audio, "audio", g_device), o = view_f32(stft, "stft", g_device);
+  ASEP_CHECK(a.ndim == 2, ASEP_ERR_BAD_SHAPE, "audio must be [N, L]");
+  const int N = (int)a.shape[0];
+  const long long L = a.shape[1];
+  ASEP_CHECK(hop >= 1, ASEP_ERR_BAD_ARG, "hop must be positive");
+  expect_shape(o, "stft", {N, n_fft / 2 + 1, 1 + L / hop, 2});
+  launch_stft(a.f32, o.f32, N, L, n_fft, hop, as_stream(stream));
+  ASEP_API_END
+}
+
+int asep_mel_db(const DLTensor* stft, const DLTensor* basis, const DLTensor* lo, const DLTensor* hi, DLTensor* mel_db, float amin,
+                float top_db, float dbmin, float dbmax, void* stream) {
+  ASEP_API_BEGIN
+  ASEP_CHECK(g_device >= 0, ASEP_ERR_STATE, "asep_init() has not been called");
+  TView sv = view_f32(stft, "stft", g_device), b = view_f32(basis, "basis", g_device), o = view_f32(mel_db, "mel_db", g_device);
+  ASEP_CHECK(sv.ndim == 4 && sv.shape[3] == 2 && b.ndim == 2 && b.shape[1] == sv.shape[1], ASEP_ERR_BAD_SHAPE,
+             "stft must be [N, F, T, 2] and basis [M, F]");
+  const int N = (int)sv.shape[0], F = (int)sv.shape[1], T = (int)sv.shape[2], M = (int)b.shape[0];
+  TView l = view_i32(lo, "lo", g_device), h = view_i32(hi, "hi", g_device);
+  expect_shape(l, "lo", {M});
+  expect_shape(h, "hi", {M});
+  expect_shape(o, "mel_db", {N, M, T});
+  launch_mel_db(sv.f32, b.f32, static_cast<const int*>(l.raw), static_cast<const int*>(h.raw), o.f32, N, M, F, T, amin, top_db, dbmin,
+                dbmax, as_stream(stream));
+  ASEP_API_END
+}
+
+int asep_mel_to_stft(const DLTensor* mel_db, const DLTensor* basis, const DLTensor* pinv, const DLTensor* flo, const DLTensor* fhi,
+                     DLTensor* mag, float step, int iters, void* stream) {
+  ASEP_API_BEGIN
+  ASEP_CHECK(g_device >= 0, ASEP_ERR_STATE, "asep_init() has not been called");
+  TView mv = view_f32(mel_db, "mel_db", g_device), b = view_f32(basis, "basis", g_device), p = view_f32(pinv, "pinv", g_device);
+  TView o = view_f32(mag, "mag", g_device);
+  ASEP_CHECK(mv.ndim == 3 && b.ndim == 2 && b.shape[0] == mv.shape[1], ASEP_ERR_BAD_SHAPE, "mel_db must be [N, M, T] and basis [M, F]");
+  const int N = (int)mv.shape[0], M = (int)mv.shape[1], T = (int)mv.shape[2], F = (int)b.shape[1];
+  expect_shape(p, "pinv", {F, M});
+  TView l = view_i32(flo, "flo", g_device), h = view_i32(fhi, "fhi", g_device);
+  expect_shape(l, "flo", {F});
+  expect_shape(h, "fhi", {F});
+  expect_shape(o, "mag", {N, F, T});
+  ASEP_CHECK(iters >= 0 && step > 0.f, ASEP_ERR_BAD_ARG, "mel_to_stft: iters >= 0 and step > 0");
+  launch_mel_to_stft(mv.f32, b.f32, p.f32, static_cast<const int*>(l.raw), static_cast<const int*>(h.raw), o.f32, N, M, F, T, step, iters,
+                     as_stream(stream));
+  ASEP_API_END
+}
+
+int asep_stft_filter(const DLTensor* mag, const DLTensor* stft_mixture, DLTensor* out, int wiener, void* stream) {
+  ASEP_API_BEGIN
+  ASEP_CHECK(g_device >= 0, ASEP_ERR_STATE, "asep_init() has not been called");
+  TView m = view_f32(mag, "mag", g_device), x = view_f32(stft_mixture, "stft_mixture", g_device), o = view_f32(out, "out", g_device);
+  ASEP_CHECK(m.ndim == 4 && x.ndim == 4 && x.shape[3] == 2 && m.numel == m.shape[0] * (x.numel / 2) && o.numel == 2 * m.numel,
+             ASEP_ERR_BAD_SHAPE, "mag [S, N, F, T], stft_mixture [N, F, T, 2], out [S, N, F, T, 2]");
+  launch_stft_filter(m.f32, x.f32, o.f32, (int)m.shape[0], (long long)(x.numel / 2), wiener, as_stream(stream));
+  ASEP_API_END
+}
+
+int asep_istft(const DLTensor* stft, int hop, DLTensor* audio, void* stream) {
+  ASEP_API_BEGIN
+  ASEP_CHECK(g_device >= 0, ASEP_ERR_STATE, "asep_init() has not been called");
+  TView sv = view_f32(stft, "stft", g_device), a = view_f32(audio, "audio", g_device);
+  ASEP_CHECK(sv.ndim == 4 && sv.shape[3] == 2 && sv.shape[1] >= 2, ASEP_ERR_BAD_SHAPE, "stft must be [N, F, T, 2]");
+  const int N = (int)sv.shape[0], F = (int)sv.shape[1], T = (int)sv.shape[2], n_fft = 2 * (F - 1);
+  ASEP_CHECK(hop >= 1, ASEP_ERR_BAD_ARG, "hop must be positive");
+  expect_shape(a, "audio", {N, (int64_t)hop * (T - 1)});
+  cudaStream_t s = as_stream(stream);
+  float* frames = nullptr;
+  CUDA_CHECK(cudaMallocAsync(&frames, (size_t)N * T * n_fft * sizeof(float), s));
+  try {
+    launch_istft(sv.f32, frames, a.f32, N, n_fft, hop, T, s);
+  } catch (...) {
+    cudaFreeAsync(frames, s);
+    throw;
+  }
+  CUDA_CHECK(cudaFreeAsync(frames, s));
   ASEP_API_END
 }
 

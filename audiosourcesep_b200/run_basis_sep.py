@@ -16,8 +16,9 @@ Differences from the shipped script, all forced by its defects (SURVEY.md App. D
 * weights come from ``.npz`` containers (``<RESTORE>/sigma_<round(sigma,2)>/weights.npz`` for Glow,
   ``<RESTORE>/weights.npz`` for NCSN) or, with ``--random_init SEED``, from the seeded generators -- the
   reference ships no checkpoint and TensorFlow bundles cannot be read here;
-* mel patches are read from ``<song_dir>/{mix,piano,violin}.npy`` (dB, ``[n,96,64]``) or generated with
-  ``--synthetic``: the librosa front end is outside the hot path.
+* mel patches come from ``<song_dir>/{mix,piano,violin}.wav`` through the GPU front end (datasets/data_loader.py:
+  get_song_extract, as in the reference), from ``<song_dir>/{mix,piano,violin}.npy`` (dB, ``[n,96,64]``), or are generated
+  with ``--synthetic``.
 
 Segments are independent: under ``torchrun`` every rank separates a contiguous block of
 segments with noise keyed by the GLOBAL element index, and rank 0 gathers the blocks at the end -- the
@@ -201,6 +202,16 @@ def load_song_patches(args):
         mix = synthetic.mixture_db(gt1, gt2)
         return mix, gt1, gt2, np.zeros((n, 1025, args.width), np.complex64)
     d = os.path.abspath(args.song_dir)
+    if os.path.exists(os.path.join(d, "mix.wav")):                    # the reference's own input (run_basis_sep.py:342-351)
+        from .datasets import data_loader
+        spec_params = {"length_sec": 2.04, "dbmin": -100, "dbmax": 20, "fmin": 125, "fmax": 7600, "use_dB": True, "n_fft": 2048,
+                       "hop_length": 512, "n_mels": 96, "sr": 16000}
+        mel_spec, _, stft_mixture = data_loader.get_song_extract(os.path.join(d, "mix.wav"), os.path.join(d, "piano.wav"),
+                                                                 os.path.join(d, "violin.wav"), 2.04 * n, **spec_params)
+        mix, gt1, gt2 = (m.cpu().numpy() for m in mel_spec)
+        if mix.shape[1:] != (args.height, args.width, 1):
+            raise ValueError(f"mel patches of shape {mix.shape[1:]}, the model expects {(args.height, args.width, 1)}")
+        return mix, gt1, gt2, stft_mixture
     arrs = []
     for name in ("mix", "piano", "violin"):
         a = np.load(os.path.join(d, name + ".npy")).astype(np.float32)

@@ -270,6 +270,26 @@ int asep_bss_eval(const DLTensor* reference_sources, const DLTensor* estimated_s
  * [...] and sources [nsrc, ...] fp32 mel spectrograms -> estimates [nsrc, ...]. */
 int asep_ideal_mask(const DLTensor* mixture, const DLTensor* sources, DLTensor* estimates, int binary, float theta, void* stream);
 
+/* ------------------------------------------------------------------ mel front end / back end
+ * Replace the librosa calls of datasets/data_loader.py:144-162 (stft -> melspectrogram -> power_to_db -> clip) and of
+ * melspec_inversion_basis.py:42-119 (db_to_power -> mel_to_stft -> phase re-use / single_channel_wiener_filter -> istft).
+ * All tensors device fp32; complex64 arrays carry a trailing [2] (re, im).  The mel basis, its pseudo-inverse and the
+ * index ranges are built on the host (audiosourcesep_b200/melspec.py, librosa.filters.mel restated).
+ * asep_stft: audio [N, L] -> stft [N, n_fft/2+1, 1 + L/hop, 2]; periodic Hann, centred frames, reflect padding.
+ * asep_mel_db: mel_db [N, M, T] = clip(power_to_db(basis |stft|^2, amin, top_db per segment), dbmin, dbmax).
+ * asep_mel_to_stft: mag [N, F, T] = sqrt(argmin_{X>=0} ||basis X - 10^(mel_db/10)||): clipped least-squares start + `iters`
+ *   FISTA steps (librosa uses L-BFGS-B from the same start; the minimiser is not unique -- see INTEGRATION.md).
+ * asep_stft_filter: out [S, N, F, T, 2] = Wiener mask mag^2 / (sum_s mag^2 + 1e-10) * mixture (wiener = 1) or mag *
+ *   exp(i angle(mixture)) (wiener = 0).
+ * asep_istft: stft [N, F, T, 2] -> audio [N, hop (T-1)] (window sum-of-squares normalised overlap-add, centre trimmed). */
+int asep_stft(const DLTensor* audio, int n_fft, int hop, DLTensor* stft, void* stream);
+int asep_mel_db(const DLTensor* stft, const DLTensor* basis, const DLTensor* lo, const DLTensor* hi, DLTensor* mel_db, float amin,
+                float top_db, float dbmin, float dbmax, void* stream);
+int asep_mel_to_stft(const DLTensor* mel_db, const DLTensor* basis, const DLTensor* pinv, const DLTensor* flo, const DLTensor* fhi,
+                     DLTensor* mag, float step, int iters, void* stream);
+int asep_stft_filter(const DLTensor* mag, const DLTensor* stft_mixture, DLTensor* out, int wiener, void* stream);
+int asep_istft(const DLTensor* stft, int hop, DLTensor* audio, void* stream);
+
 /* CUDA-graph replay of whole Langevin steps inside asep_basis_{glow,ncsn}_inner (on by default; steps 2..T of a call
  * with T >= 3 are replays of one captured step whose per-step scalars live in device memory).  0 = launch every step
  * eagerly (parity tests compare the two), and drop the cached graphs. */

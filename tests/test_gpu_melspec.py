@@ -1,0 +1,141 @@
+"""GPU parity tests of the mel front end / inversion back end (csrc/mel_kernels.cu) against oracle/mel_oracle.py (numpy
+restatement of the librosa calls the reference makes; librosa itself is not installable here: "parity unpinned")."""
+import os
+import wave
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mel_oracle as mo
+
+pytestmark = pytest.mark.gpu
+
+SR, L = 16000, 32640                      # 2.04 s at 16 kHz (run_basis_sep.py:346-349)
+
+
+def _audio(n, seed=0):
+    rng = np.random.default_rng(seed)
+    t = np.arange(L) / SR
+    out = []
+    for i in range(n):
+        f0 = 220.0 * 2 ** (i / 3.0)
+        y = sum(a * np.sin(2 * np.pi * f0 * k * t + rng.uniform(0, 6.28)) for k, a in ((1, 0.3), (2, 0.15), (3, 0.08), (5, 0.03)))
+        out.append(y * np.hanning(L) + 0.005 * rng.standard_normal(L))
+    return np.stack(out).astype(np.float32)
+
+
+def test_stft_and_mel_db_match_the_restated_librosa_semantics():
+    from audiosourcesep_b200 import melspec
+    y = _audio(3)
+    S = melspec.stft(y)
+    assert S.shape == (3, 1025, 64) and S.dtype == torch.complex64
+    for i in range(3):
+        want = mo.stft(y[i])
+        err = np.max(np.abs(S[i].cpu().numpy() - want)) / np.max(np.abs(want))
+        assert err <= 2e-6, err
+    mel = melspec.melspectrogram_db(S).cpu().numpy()
+    assert mel.shape == (3, 96, 64)
+    for i in range(3):
+        want, _ = mo.melspectrogram_db(y[i])
+        assert np.max(np.abs(mel[i] - want)) <= 2e-3, np.max(np.abs(mel[i] - want))        # dB
+    # librosa's top_db floor is relative to each extract's own maximum, then the clip to [-100, 20]
+    assert all(mel[i].min() >= max(-100.0, mel[i].max() - 80.0) - 1e-4 for i in range(3))
+    # known answer: a pure 1 kHz tone peaks in the filter whose centre is nearest to 1 kHz
+    tone = (0.5 * np.sin(2 * np.pi * 1000.0 * np.arange(L) / SR)).astype(np.float32)[None]
+    mt = melspec.melspectrogram_db(melspec.stft(tone)).cpu().numpy()[0]
+    centres = mo.mel_to_hz(np.linspace(mo.hz_to_mel(125.0), mo.hz_to_mel(7600.0), 98))[1:-1]
+    assert abs(int(np.argmax(mt[:, 32])) - int(np.argmin(np.abs(centres - 1000.0)))) <= 1
+
+
+def test_istft_inverts_stft_and_matches_the_oracle():
+    from audiosourcesep_b200 import melspec
+    y = _audio(2, seed=3)
+    S = melspec.stft(y)
+    back = melspec.istft(S).cpu().numpy()
+    assert back.shape == (2, 512 * 63)
+    assert np.max(np.abs(back - y[:, : back.shape[1]])) <= 5e-6            # Hann at hop n_fft/4 is COLA: exact reconstruction
+    want = mo.istft(mo.stft(y[0]))
+    assert np.max(np.abs(back[0] - want)) <= 5e-6
+
+
+@pytest.mark.parametrize("wiener", [False, True])
+def test_inversion_back_end_matches_the_oracle_algorithm(wiener):
+    """db_to_power -> NNLS (FISTA, same start and iteration count as oracle.nnls_pg) -> phase re-use / Wiener -> istft."""
+    from audiosourcesep_b200 import melspec
+    from audiosourcesep_b200.melspec_inversion_basis import stft_inversion_fn
+    y = _audio(2, seed=5)
+    mix = (y[0] + y[1])[None]
+    Sm = melspec.stft(mix)
+    dbs = [melspec.melspectrogram_db(melspec.stft(y[i:i + 1])).cpu().numpy() for i in range(2)]
+    iters = 200
+    mag = melspec.mel_to_stft(torch.as_tensor(dbs[0]), iters=iters).cpu().numpy()[0]
+    want_mag = mo.mel_to_stft(mo.db_to_power(dbs[0][0]), iters=iters)
+    rel = np.linalg.norm(mag - want_mag) / np.linalg.norm(want_mag)
+    print(f"NNLS magnitudes vs the float64 restatement: {rel:.3e}")
+    assert rel <= 2e-3
+    A = mo.mel_filters().astype(np.float64)
+    P = mo.db_to_power(dbs[0][0])
+    res = np.linalg.norm(A @ mag.astype(np.float64) ** 2 - P) / np.linalg.norm(P)
+    print(f"relative residual of the mel equations: {res:.3e}")
+    assert res <= 5e-3 and mag.min() >= 0.0
+    got = stft_inversion_fn(wiener_filter=wiener, iters=iters)(([dbs[0], dbs[1]], Sm.cpu().numpy()))
+    want = mo.stft_inversion([dbs[0][0], dbs[1][0]], Sm.cpu().numpy()[0], wiener_filter=wiener, iters=iters)
+    for g, w in zip(got, want):
+        assert g.shape == (1, w.shape[0])
+        assert np.linalg.norm(g[0] - w) <= 5e-3 * np.linalg.norm(w)
+    if wiener:        # the Wiener masks sum to one wherever the estimated power exceeds the 1e-10 regulariser: the two estimates
+        s = got[0][0] + got[1][0]                         # add up to the mixture except in the near-silent bins
+        assert np.linalg.norm(s - mix[0, : s.shape[0]]) <= 2e-2 * np.linalg.norm(mix[0])
+
+
+def test_get_song_extract_reads_wav_files_like_the_reference(tmp_path):
+    from audiosourcesep_b200.datasets import data_loader
+    rng = np.random.default_rng(0)
+    n_win = 5
+    tracks = {k: (0.2 * rng.standard_normal(L * n_win)).astype(np.float32) for k in ("piano", "violin")}
+    tracks["mix"] = tracks["piano"] + tracks["violin"]
+    for k, a in tracks.items():
+        with wave.open(str(tmp_path / f"{k}.wav"), "wb") as w:
+            w.setnchannels(1); w.setsampwidth(2); w.setframerate(SR)
+            w.writeframes((np.clip(a, -1, 1 - 1 / 32768) * 32768).astype("<i2").tobytes())
+    params = {"length_sec": 2.04, "dbmin": -100, "dbmax": 20, "fmin": 125, "fmax": 7600, "use_dB": True, "n_fft": 2048,
+              "hop_length": 512, "n_mels": 96, "sr": 16000}
+    mel, raw, stft_mix = data_loader.get_song_extract(str(tmp_path / "mix.wav"), str(tmp_path / "piano.wav"),
+                                                      str(tmp_path / "violin.wav"), 2.04 * 3, **params)
+    assert [tuple(m.shape) for m in mel] == [(3, 96, 64, 1)] * 3 and stft_mix.shape == (3, 1025, 64) and stft_mix.dtype == np.complex64
+    assert all(r.shape == (3 * L,) for r in raw)
+    # the first two windows are skipped (data_loader.py:131-134): extract 0 is window 2 of the file
+    pcm = (np.clip(tracks["mix"], -1, 1 - 1 / 32768) * 32768).astype("<i2").astype(np.float32) / 32768.0
+    want, S = mo.melspectrogram_db(pcm[2 * L: 3 * L])
+    assert np.max(np.abs(mel[0][0, :, :, 0].cpu().numpy() - want)) <= 2e-3
+    assert np.max(np.abs(stft_mix[0] - S)) <= 2e-6 * np.max(np.abs(S))
+    with pytest.raises(ValueError):
+        data_loader.get_song_extract(str(tmp_path / "mix.wav"), str(tmp_path / "piano.wav"), str(tmp_path / "violin.wav"), 2.04 * 9, **params)
+
+
+def test_inversion_cli_writes_the_reference_outputs(tmp_path):
+    """melspec_inversion_basis.main on a results.npz (reference: melspec_inversion_basis.py:122-236): wav files and
+    inverse_spectrograms.npz with the reference's keys; ground-truth spectrograms inverted with the mixture phase and the
+    Wiener filter come back close to the true sources."""
+    from audiosourcesep_b200 import melspec
+    from audiosourcesep_b200.melspec_inversion_basis import build_parser, main
+    y = _audio(4, seed=7)
+    src1, src2 = y[:2], y[2:]
+    mix = src1 + src2
+    mel = lambda a: melspec.melspectrogram_db(melspec.stft(a)).cpu().numpy()
+    gt1, gt2, mixed = mel(src1), mel(src2), mel(mix)
+    np.savez(tmp_path / "results.npz", x1=gt1, x2=gt2, gt1=gt1, gt2=gt2, mixed=mixed, stft_mixture=melspec.stft(mix).cpu().numpy())
+    out = main(build_parser().parse_args([str(tmp_path), "--wiener_filter", "--output", str(tmp_path / "inv")]))
+    assert sorted(out) == ["gt1_audio", "gt2_audio", "mix_audio", "x1_audio", "x2_audio"]
+    assert all(v.shape == (2 * 512 * 63,) for v in out.values())
+    for name in ("sep1", "sep2", "gt1", "gt2", "mix"):
+        with wave.open(str(tmp_path / "inv" / f"{name}.wav"), "rb") as w:
+            assert w.getframerate() == 16000 and w.getnframes() == 2 * 512 * 63
+    saved = np.load(tmp_path / "inv" / "inverse_spectrograms.npz")
+    assert np.array_equal(saved["x1_audio"], out["x1_audio"])
+    n = 512 * 63
+    ref = np.concatenate([src1[0, :n], src1[1, :n]])
+    sdr = 10 * np.log10(np.sum(ref ** 2) / np.sum((out["x1_audio"] - ref) ** 2))
+    print(f"oracle-mask inversion SDR {sdr:.1f} dB")
+    assert sdr > 8.0

@@ -1,0 +1,43 @@
+"""CPU tests of the mel front / back end oracle (oracle/mel_oracle.py) and of the host-side filter bank."""
+import numpy as np
+
+from oracle import mel_oracle as mo
+
+
+def test_mel_filter_bank_known_properties():
+    from audiosourcesep_b200 import melspec
+    A = mo.mel_filters()
+    assert A.shape == (96, 1025) and A.dtype == np.float32
+    assert np.array_equal(A, melspec.mel_filters())               # product and oracle restate the same published formula
+    assert (A > 0).sum(axis=0).max() <= 2                         # triangular filters overlap pairwise only
+    # Slaney normalisation: every filter has unit area in Hz (up to the FFT-bin discretisation)
+    df = 16000.0 / 2048
+    area = A.sum(axis=1) * df
+    assert np.all(np.abs(area - 1.0) < 0.35) and abs(float(np.mean(area)) - 1.0) < 0.02
+    # band edges: nothing below fmin = 125 Hz or above fmax = 7600 Hz
+    freqs = np.linspace(0, 8000, 1025)
+    assert A[:, freqs < 125].sum() == 0 and A[:, freqs > 7600].sum() == 0
+    # Slaney scale: linear below 1 kHz (200/3 Hz per mel), 1 kHz = 15 mel
+    assert abs(float(mo.hz_to_mel(1000.0)) - 15.0) < 1e-12 and abs(float(mo.mel_to_hz(mo.hz_to_mel(4321.0))) - 4321.0) < 1e-9
+
+
+def test_stft_round_trip_and_power_to_db():
+    rng = np.random.default_rng(0)
+    y = rng.standard_normal(32640).astype(np.float32) * 0.1
+    S = mo.stft(y)
+    assert S.shape == (1025, 64) and S.dtype == np.complex64
+    back = mo.istft(S)
+    assert back.shape == (512 * 63,) and np.max(np.abs(back - y[: back.shape[0]])) < 1e-6
+    db = mo.power_to_db(np.array([[1.0, 1e-3], [1e-12, 1e-20]]))
+    assert np.allclose(db, [[0.0, -30.0], [-80.0, -80.0]])        # amin = 1e-10 -> -100 dB, floored at max - 80
+    mel, _ = mo.melspectrogram_db(y)
+    assert mel.shape == (96, 64) and mel.max() <= 20.0 and mel.min() >= -100.0
+
+
+def test_nnls_restatement_reaches_the_residual_floor():
+    rng = np.random.default_rng(1)
+    A = mo.mel_filters().astype(np.float64)
+    X = rng.random((1025, 4)) ** 4
+    B = A @ X
+    Xh = mo.nnls_pg(A, B, iters=300)
+    assert Xh.min() >= 0.0 and np.linalg.norm(A @ Xh - B) <= 1e-3 * np.linalg.norm(B)
