@@ -34,6 +34,20 @@ def test_reference_module_paths_import():
     for name in ("setUp_optimizer", "setUp_checkpoint", "get_config", "dict2namespace"):     # train_utils.py:23,62,114,123
         assert callable(getattr(train_utils, name))
     assert callable(train_noisy_glow.main) and train_noisy_glow.build_parser().parse_args([]).noisy is True
+    # train_ncsn.py, datasets/data_loader.py, melspec_inversion_basis.py, bsseval_v4.py, oracle_systems.py
+    from audiosourcesep_b200 import bsseval_v4, melspec_inversion_basis, oracle_systems, train_ncsn
+    from audiosourcesep_b200.datasets import data_loader
+    for mod, names in ((train_ncsn, ("train", "distributed_train_step", "get_noise_conditionned_data", "main")),
+                       (data_loader, ("get_song_extract", "load_wav")),
+                       (melspec_inversion_basis, ("stft_inversion_fn", "single_channel_wiener_filter", "main")),
+                       (bsseval_v4, ("bss_eval", "bss_eval_sources", "bss_eval_sources_framewise", "bss_eval_images",
+                                     "bss_eval_images_framewise", "validate", "Framing")),
+                       (oracle_systems, ("IBM_melspec", "IRM_melspec"))):
+        for name in names:
+            assert callable(getattr(mod, name)), (mod.__name__, name)
+    # bsseval_v4.Framing restates the reference's window arithmetic (bsseval_v4.py:377-418)
+    assert [(w.start, w.stop) for w in bsseval_v4.Framing(8000, 6000, 20000)] == [(0, 8000), (6000, 14000), (12000, 20000)]
+    assert [(w.start, w.stop) for w in bsseval_v4.Framing(np.inf, np.inf, 123)] == [(0, 123)]
 
 
 def test_build_glow_argument_errors():
