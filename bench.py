@@ -295,10 +295,12 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed_loop(step_fn, steps, warmup, profile=False, do_flush=True):
+    def timed_loop(step_fn, steps, warmup, profile=False, do_flush=True, local=False):
+        """local=True: a measurement only rank 0 makes (kernel-level profiles) -- no collective may be issued."""
+        sync = torch.cuda.synchronize if local else barrier
         for _ in range(warmup):
             step_fn()
-        barrier()
+        sync()
         evs = []
         if profile == "conv":
             _lib.conv_profile(True)
@@ -315,7 +317,7 @@ def run_ours(args):
             step_fn()
             b.record()
             evs.append((a, b))
-        barrier()
+        sync()
         launches = _lib.launch_count() - n0
         prof = None
         if profile == "conv":
@@ -329,7 +331,7 @@ def run_ours(args):
             _lib.tc_profile(False)
         total_ms = sum(a.elapsed_time(b) for a, b in evs)
         t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-        if world > 1:
+        if world > 1 and not local:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()), launches, prof
 
@@ -481,7 +483,7 @@ def run_ours(args):
             def step_lan():
                 ops.langevin_step(ten[0], ten[1], ten[2], ten[3], ten[4], 2e-5, 1e4, 6.3e-3, seed=1, step=0)
 
-            _, _, lprof = timed_loop(step_lan, 5, 2, profile="hbm", do_flush=False)
+            _, _, lprof = timed_loop(step_lan, 5, 2, profile="hbm", do_flush=False, local=True)
             hbm_entry("langevin", "k_langevin<in-kernel Philox>", lprof["langevin"],
                       f"{nl} segments (7 tensors x 100 MB, larger than L2): 5 reads + 2 writes x 4 B per element (SURVEY 8(d))")
             del ten
@@ -539,7 +541,7 @@ def run_ours(args):
                                 "per-step gate met on the annealed end of the schedule only (score error 1-5 %)"),
                        "finite": bool(torch.isfinite(u1).all() and torch.isfinite(u2).all())}
                 if rank == 0 and mode == "bf16":
-                    _, _, nprof = timed_loop(step_ncsn, 1, 0, profile="hbm")
+                    _, _, nprof = timed_loop(step_ncsn, 1, 0, profile="hbm", local=True)
                     hbm_entry("ncsn_prep", f"k_prep (NCSN {ver}: normalise + ELU + bf16 cast of a convolution input)", nprof["ncsn_prep"],
                               f"{nseg} segments: 4 B read + 2 B written per element")
                     hbm_entry("ncsn_pool_resize", f"k_pool5_1d / k_avgpool2 / k_resize2x_add (NCSN {ver})", nprof["ncsn_pool_resize"],
