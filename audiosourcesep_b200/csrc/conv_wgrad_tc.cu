@@ -8,10 +8,8 @@
 // pixels] lands as 64 rows of 128 B with the SWIZZLE_128B pattern = the canonical MN-major UMMA layout (same scheme as
 // wgrad_tc.cu).  The x box is fetched through a 4-D tensor map (C, W, H, N) at the tap's shifted coordinates: rows
 // and columns outside the image come back as zeros ('same' padding), so no im2col tensor is materialised.  One CTA owns
-// a (PAIR of taps, 128 input channels, n_mma output channels) tile and a slice of the pixel range (split-K over the grid):
-// the output-gradient boxes of a pixel block are shared by all taps, so two taps per CTA cut the operand bytes per MMA from
-// 48 KB to 32 KB per 512 cycles (the kernel is bound by shared-memory ingest from L2, not by the tensor pipe).  The two
-// accumulators sit side by side in TMEM (2 x n_mma <= 512 columns); partial results are added to dk with fp32 reductions.
+// one (tap, 128 input channels, n_mma output channels) tile and a slice of the pixel range (split-K over the grid),
+// accumulates in TMEM and adds its partial result to dk with fp32 reductions.
 #include <cuda.h>
 
 #include <map>
@@ -31,7 +29,7 @@ constexpr int kThreads = 192;
 struct CwParams {
   float* dk;
   int Cin, Cout, n_mma, nboxes_b;
-  int taps, ksize, dil, groups;     // groups = ceil(taps / 2) tap pairs
+  int taps, ksize, dil;
   int H, W, rows_per_kt, kt_per_img;
   int k_tiles_total, k_tiles_per_split, splits;
   int stages, stage_bytes;
@@ -69,18 +67,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_wgrad_tc(const __grid_cons
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(&bars[2 * S + 1]);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int i0 = blockIdx.x * 128, n0 = blockIdx.y * prm.n_mma;
-  const int group = blockIdx.z / prm.splits, split = blockIdx.z % prm.splits;
+  const int tap = blockIdx.z / prm.splits, split = blockIdx.z % prm.splits;
   const int kt0 = split * prm.k_tiles_per_split;
   const int kt1 = min(prm.k_tiles_total, kt0 + prm.k_tiles_per_split);
   const int nk = kt1 - kt0;
   const int half = prm.ksize / 2;
-  const int tap0 = 2 * group, ntap = min(2, prm.taps - tap0);
-  int dy[2], dx[2];
-  for (int j = 0; j < 2; ++j) {
-    const int tap = min(tap0 + j, prm.taps - 1);
-    dy[j] = (tap / prm.ksize - half) * prm.dil;
-    dx[j] = (tap % prm.ksize - half) * prm.dil;
-  }
+  const int dy = (tap / prm.ksize - half) * prm.dil, dx = (tap % prm.ksize - half) * prm.dil;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < S; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
@@ -89,7 +81,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_wgrad_tc(const __grid_cons
     tma_prefetch_desc(&mapX);
     tma_prefetch_desc(&mapG);
   }
-  if (warp == 2) tmem_alloc(smem_u32(tmem_slot), 512);
+  if (warp == 2) tmem_alloc(smem_u32(tmem_slot), 256);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -103,14 +95,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_wgrad_tc(const __grid_cons
           mbar_wait(empty0 + 8 * stage, phase ^ 1);
           const uint32_t fb = full0 + 8 * stage;
           const uint32_t sa = smem_u32(smem + stage * prm.stage_bytes);
-          mbar_expect_tx(fb, (uint32_t)((2 * ntap + prm.nboxes_b) * kBox));
+          mbar_expect_tx(fb, (uint32_t)((2 + prm.nboxes_b) * kBox));
           const int n = kt / prm.kt_per_img, h0 = (kt % prm.kt_per_img) * prm.rows_per_kt;
           // channels beyond Cin (second M tile of Cin = 192) and shifted rows / columns outside the image are zero-filled
-          for (int j = 0; j < ntap; ++j) {
-            tma_load_4d(sa + (2 * j) * kBox, &mapX, i0, dx[j], h0 + dy[j], n, fb);
-            tma_load_4d(sa + (2 * j + 1) * kBox, &mapX, i0 + 64, dx[j], h0 + dy[j], n, fb);
-          }
-          for (int b = 0; b < prm.nboxes_b; ++b) tma_load_2d(sa + (4 + b) * kBox, &mapG, n0 + 64 * b, kt * kKT, fb);
+          tma_load_4d(sa, &mapX, i0, dx, h0 + dy, n, fb);
+          tma_load_4d(sa + kBox, &mapX, i0 + 64, dx, h0 + dy, n, fb);
+          for (int b = 0; b < prm.nboxes_b; ++b) tma_load_2d(sa + (2 + b) * kBox, &mapG, n0 + 64 * b, kt * kKT, fb);
           if (++stage == (uint32_t)S) { stage = 0; phase ^= 1; }
         }
       }
@@ -122,13 +112,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_wgrad_tc(const __grid_cons
           mbar_wait(full0 + 8 * stage, phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * prm.stage_bytes);
-          for (int j = 0; j < ntap; ++j) {
 #pragma unroll
-            for (int k = 0; k < kKT / 16; ++k) {
-              const uint64_t da = make_desc_mn(sa + (2 * j) * kBox + k * 2048, kBox);
-              const uint64_t db = make_desc_mn(sa + 4 * kBox + k * 2048, kBox);
-              umma_bf16(tmem_base + (uint32_t)(j * prm.n_mma), da, db, idesc, (kt | k) != 0);
-            }
+          for (int k = 0; k < kKT / 16; ++k) {
+            const uint64_t da = make_desc_mn(sa + k * 2048, kBox);
+            const uint64_t db = make_desc_mn(sa + 2 * kBox + k * 2048, kBox);
+            umma_bf16(tmem_base, da, db, idesc, (kt | k) != 0);
           }
           umma_commit(empty0 + 8 * stage);
           if (++stage == (uint32_t)S) { stage = 0; phase ^= 1; }
@@ -142,17 +130,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_wgrad_tc(const __grid_cons
       tc_fence_after();
       const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
       const bool row_ok = i0 + row < prm.Cin;
-      for (int tj = 0; tj < ntap; ++tj) {
-        float* orow = prm.dk + ((size_t)(tap0 + tj) * prm.Cin + (size_t)(i0 + row)) * prm.Cout + n0;
-        for (int j = 0; j < prm.n_mma / 32; ++j) {
-          uint32_t v[32];
-          tmem_ld32(t_lane + (uint32_t)(tj * prm.n_mma + j * 32), v);
-          tmem_ld_wait();
-          if (row_ok) {
+      float* orow = prm.dk + ((size_t)tap * prm.Cin + (size_t)(i0 + row)) * prm.Cout + n0;
+      for (int j = 0; j < prm.n_mma / 32; ++j) {
+        uint32_t v[32];
+        tmem_ld32(t_lane + (uint32_t)(j * 32), v);
+        tmem_ld_wait();
+        if (row_ok) {
 #pragma unroll
-            for (int c = 0; c < 32; ++c)
-              if (n0 + j * 32 + c < prm.Cout) atomicAdd(orow + j * 32 + c, __uint_as_float(v[c]));
-          }
+          for (int c = 0; c < 32; ++c)
+            if (n0 + j * 32 + c < prm.Cout) atomicAdd(orow + j * 32 + c, __uint_as_float(v[c]));
         }
       }
       tc_fence_before();
@@ -160,7 +146,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_wgrad_tc(const __grid_cons
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, 512);
+  if (warp == 2) tmem_dealloc(tmem_base, 256);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -233,13 +219,12 @@ void conv_wgrad_tc(const __nv_bfloat16* x, const __nv_bfloat16* g, float* dk, in
   prm.H = H; prm.W = W; prm.rows_per_kt = kKT / W; prm.kt_per_img = H / prm.rows_per_kt;
   const int mtiles = (Cin + 127) / 128, ntiles = Cout / prm.n_mma;
   prm.k_tiles_total = N * prm.kt_per_img;
-  prm.groups = (prm.taps + 1) / 2;
-  int splits = std::max(1, (2 * g_sms3) / (prm.groups * mtiles * ntiles));
+  int splits = std::max(1, (2 * g_sms3) / (prm.taps * mtiles * ntiles));
   splits = std::min(splits, prm.k_tiles_total);
   prm.k_tiles_per_split = (prm.k_tiles_total + splits - 1) / splits;
   splits = (prm.k_tiles_total + prm.k_tiles_per_split - 1) / prm.k_tiles_per_split;
   prm.splits = splits;
-  prm.stage_bytes = (4 + prm.nboxes_b) * kBox;
+  prm.stage_bytes = (2 + prm.nboxes_b) * kBox;
   prm.stages = std::min(6, (227 * 1024 - 1024) / prm.stage_bytes);
   const int smem_bytes = prm.stages * prm.stage_bytes + 1024;
   static bool attr_set = false;
@@ -249,7 +234,7 @@ void conv_wgrad_tc(const __nv_bfloat16* x, const __nv_bfloat16* g, float* dk, in
   }
   const CUtensorMap mX = map_x(x, N, H, W, Cin);
   const CUtensorMap mG = map_g(g, (long long)N * H * W, Cout);
-  dim3 grid(mtiles, ntiles, prm.groups * splits);
+  dim3 grid(mtiles, ntiles, prm.taps * splits);
   k_conv_wgrad_tc<<<grid, kThreads, smem_bytes, s>>>(mX, mG, prm);
   ASEP_LAUNCH_CHECK();
 }
