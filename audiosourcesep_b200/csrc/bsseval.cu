@@ -286,18 +286,31 @@ void bss_eval_core(const double* refs, const double* ests, int nsrc, long long n
   ASEP_CHECK(0 <= f0 && f0 < f1 && f1 <= nsampl, ASEP_ERR_BAD_ARG, "bss_eval: filter range [%lld, %lld) of %lld", f0, f1, nsampl);
   const int n = nsrc * L, nl = 2 * L - 1;
   const double eps = 2.220446049250313e-16;
-  double *Rss, *Rse, *A, *C, *Aj, *Cj, *acc, *extra;
-  int *nonzero, *silent;
-  CUDA_CHECK(cudaMallocAsync(&Rss, (size_t)nsrc * nsrc * nl * sizeof(double), s));
-  CUDA_CHECK(cudaMallocAsync(&Rse, (size_t)nsrc * nsrc * nl * sizeof(double), s));
-  CUDA_CHECK(cudaMallocAsync(&A, (size_t)n * (n + nsrc) * sizeof(double), s));
-  CUDA_CHECK(cudaMallocAsync(&C, (size_t)nsrc * n * sizeof(double), s));
-  CUDA_CHECK(cudaMallocAsync(&Aj, (size_t)L * (L + nsrc) * sizeof(double), s));
-  CUDA_CHECK(cudaMallocAsync(&Cj, (size_t)nsrc * nsrc * L * sizeof(double), s));
-  CUDA_CHECK(cudaMallocAsync(&acc, (size_t)nsrc * nsrc * nwin * 7 * sizeof(double), s));
-  CUDA_CHECK(cudaMallocAsync(&extra, (size_t)nsrc * nsrc * nwin * sizeof(double), s));
-  CUDA_CHECK(cudaMallocAsync(&nonzero, (size_t)2 * nsrc * sizeof(int), s));
-  CUDA_CHECK(cudaMallocAsync(&silent, (size_t)nwin * sizeof(int), s));
+  for (int t = 0; t < nwin; ++t)
+    ASEP_CHECK(0 <= win0[t] && win0[t] < win1[t] && win1[t] <= nsampl, ASEP_ERR_BAD_ARG, "bss_eval: window [%lld, %lld) of %lld",
+               win0[t], win1[t], nsampl);
+  // stream-ordered scratch, released on every exit path
+  struct Scratch {
+    cudaStream_t s;
+    std::vector<void*> ptrs;
+    ~Scratch() { for (void* p : ptrs) cudaFreeAsync(p, s); }
+    void* get(size_t bytes) {
+      void* p = nullptr;
+      CUDA_CHECK(cudaMallocAsync(&p, bytes, s));
+      ptrs.push_back(p);
+      return p;
+    }
+  } scratch{s, {}};
+  double* Rss = static_cast<double*>(scratch.get((size_t)nsrc * nsrc * nl * sizeof(double)));
+  double* Rse = static_cast<double*>(scratch.get((size_t)nsrc * nsrc * nl * sizeof(double)));
+  double* A = static_cast<double*>(scratch.get((size_t)n * (n + nsrc) * sizeof(double)));
+  double* C = static_cast<double*>(scratch.get((size_t)nsrc * n * sizeof(double)));
+  double* Aj = static_cast<double*>(scratch.get((size_t)L * (L + nsrc) * sizeof(double)));
+  double* Cj = static_cast<double*>(scratch.get((size_t)nsrc * nsrc * L * sizeof(double)));
+  double* acc = static_cast<double*>(scratch.get((size_t)nsrc * nsrc * nwin * 7 * sizeof(double)));
+  double* extra = static_cast<double*>(scratch.get((size_t)nsrc * nsrc * nwin * sizeof(double)));
+  int* nonzero = static_cast<int*>(scratch.get((size_t)2 * nsrc * sizeof(int)));
+  int* silent = static_cast<int*>(scratch.get((size_t)nwin * sizeof(int)));
   CUDA_CHECK(cudaMemsetAsync(acc, 0, (size_t)nsrc * nsrc * nwin * 7 * sizeof(double), s));
   CUDA_CHECK(cudaMemsetAsync(extra, 0, (size_t)nsrc * nsrc * nwin * sizeof(double), s));
   // correlations at the lags |l| < L: references x references, references x estimates
@@ -318,7 +331,6 @@ void bss_eval_core(const double* refs, const double* ests, int nsrc, long long n
   }
   for (int t = 0; t < nwin; ++t) {
     const long long w0 = win0[t], w1 = win1[t];
-    ASEP_CHECK(0 <= w0 && w0 < w1 && w1 <= nsampl, ASEP_ERR_BAD_ARG, "bss_eval: window [%lld, %lld) of %lld", w0, w1, nsampl);
     CUDA_CHECK(cudaMemsetAsync(nonzero, 0, (size_t)2 * nsrc * sizeof(int), s));
     k_silent<<<dim3(64, 2 * nsrc), 256, 0, s>>>(refs, ests, nsampl, nsrc, w0, w1, nonzero);
     ASEP_LAUNCH_CHECK();
@@ -343,8 +355,6 @@ void bss_eval_core(const double* refs, const double* ests, int nsrc, long long n
     k_srcver_sdr<<<cdiv(nsrc * nsrc * nwin, 128), 128, 0, s>>>(acc, extra, silent, nsrc, nwin, out);
     ASEP_LAUNCH_CHECK();
   }
-  for (void* p : {(void*)Rss, (void*)Rse, (void*)A, (void*)C, (void*)Aj, (void*)Cj, (void*)acc, (void*)extra, (void*)nonzero, (void*)silent})
-    CUDA_CHECK(cudaFreeAsync(p, s));
 }
 
 void launch_ideal_mask(const float* mixture, const float* sources, float* estimates, int nsrc, long long P, int binary,

@@ -26,7 +26,10 @@ class NcsnModel {
   void set_sigmas(const float* sigmas, int n);
   void prepare();
   // split-bf16 mode (ASEP_PREC_BF16X3): takes effect at the next prepare()
-  void set_precision(bool x3) { if (x3 != x3_) { x3_ = x3; prepared_ = false; } }
+  void set_precision(bool x3) {
+    ASEP_CHECK(!training_ || x3 == x3_, ASEP_ERR_STATE, "the precision mode is fixed once training is enabled");
+    if (x3 != x3_) { x3_ = x3; prepared_ = false; }
+  }
   // x [N,H,W,1] fp32, idx [N] int32 -> score [N,H,W,1] fp32
   void forward(const float* x, const int* idx, float* score, int N, cudaStream_t s);
   const asep_ncsn_cfg& cfg() const { return cfg_; }
