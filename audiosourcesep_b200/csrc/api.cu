@@ -640,18 +640,22 @@ void run_basis_steps(const BasisCall& c, BasisGraphKey key, bool parallel, bool 
     for (int t = 0; t < c.T; ++t) eager_step(t);
     return;
   }
-  eager_step(0);                                   // sizes both workspaces (a capture may not allocate)
   bg.ensure();
-  CUDA_CHECK(cudaEventRecord(bg.ev_in, s));
-  CUDA_CHECK(cudaStreamWaitEvent(bg.stream, bg.ev_in, 0));
-  LangevinDev h{c.eta, c.lambda, c.noise_scale, 0.f, c.step0 + 1, 1ull};
-  CUDA_CHECK(cudaMemcpyAsync(bg.dev, &h, sizeof(h), cudaMemcpyHostToDevice, bg.stream));   // pageable source: staged at once
   const void* ptrs[9] = {c.x1, c.x2, c.mixed, c.nz1, c.nz2, c.dump, c.nanp, c.s1, c.s2};
   std::memcpy(key.p, ptrs, sizeof(ptrs));
   key.N = c.N; key.seed = c.seed; key.off = c.elem_offset;
   generations(key);
   auto it = bg.graphs.find(key);
+  // a cached graph means both workspaces already have this size: every step of the call is a replay.  Otherwise the
+  // first step runs eagerly (it sizes the workspaces -- a capture may not allocate) and the rest replay the new graph.
+  const int t_first = it != bg.graphs.end() ? 0 : 1;
+  if (t_first == 1) eager_step(0);
+  CUDA_CHECK(cudaEventRecord(bg.ev_in, s));
+  CUDA_CHECK(cudaStreamWaitEvent(bg.stream, bg.ev_in, 0));
+  LangevinDev h{c.eta, c.lambda, c.noise_scale, 0.f, c.step0 + (uint64_t)t_first, (unsigned long long)t_first};
+  CUDA_CHECK(cudaMemcpyAsync(bg.dev, &h, sizeof(h), cudaMemcpyHostToDevice, bg.stream));   // pageable source: staged at once
   if (it == bg.graphs.end()) {
+    generations(key);                              // the eager step may have re-carved a workspace
     if (bg.graphs.size() >= 16) bg.clear();
     cudaGraph_t graph = nullptr;
     const long long c0 = g_launch_count.load();
@@ -683,7 +687,7 @@ void run_basis_steps(const BasisCall& c, BasisGraphKey key, bool parallel, bool 
     CUDA_CHECK(cudaGraphDestroy(graph));
     it = bg.graphs.emplace(key, g).first;
   }
-  for (int t = 1; t < c.T; ++t) {
+  for (int t = t_first; t < c.T; ++t) {
     CUDA_CHECK(cudaGraphLaunch(it->second.exec, bg.stream));
     g_launch_count.fetch_add(it->second.launches);
   }

@@ -463,7 +463,8 @@ def run_ours(args):
                     stepno[0] += T
 
                 nsteps = max(1, args.steps // 2)
-                b_ms, b_launches, _ = timed_loop(step_basis, nsteps, 1)
+                # 3 warm-up calls: eager pass + step-graph capture, capture of the N <= 128 score graphs, first pure replay
+                b_ms, b_launches, _ = timed_loop(step_basis, nsteps, 3)
                 legs[str(nseg)] = {"value": world * nseg * T * nsteps / (b_ms * 1e-3), "unit": "segment-steps/s", "segments_per_gpu": nseg,
                                    "ms_per_langevin_step": b_ms / (nsteps * T), "gpu_launches_per_langevin_step": b_launches // (nsteps * T),
                                    "alg_tflops": world * nseg * T * nsteps * 4 * F_GLOW * (args.K / 40.0) / (b_ms * 1e-3) / 1e12,
@@ -521,7 +522,7 @@ def run_ours(args):
                 nst = max(2, args.steps // 2)
                 # rate: the shipped path (steps 2..T of a call replayed as one CUDA graph, the two networks as parallel
                 # branches); kernel roofline / share: a second loop with per-launch events, which launches eagerly
-                n_ms, n_launches, _ = timed_loop(step_ncsn, nst, 2)
+                n_ms, n_launches, _ = timed_loop(step_ncsn, nst, 3)
                 rate = world * nseg * args.ncsn_T * nst / (n_ms * 1e-3)
                 p_ms, _, (c_ms, c_n, c_fl) = timed_loop(step_ncsn, 2, 0, profile="conv")
                 # the x3 mode launches every convolution three times: its algorithmic FLOPs are those of ONE product
@@ -659,7 +660,7 @@ def run_ours(args):
                 cnt[0] += args.basis_T
 
             nsteps = max(2, args.steps // 2)
-            b_ms, _, _ = timed_loop(step_sb, nsteps, 1)
+            b_ms, _, _ = timed_loop(step_sb, nsteps, 3)
             strong[f"basis_glow_{mode}"] = {"value": n_mixed * args.basis_T * nsteps / (b_ms * 1e-3), "unit": "segment-steps/s",
                                             "n_mixed_total": n_mixed, "segments_this_rank": nloc, "ms_per_langevin_step": b_ms / (nsteps * args.basis_T)}
             del m1, m2

@@ -216,7 +216,7 @@ def test_glow_step_graph_replay_equals_eager_launches(same_handle):
             for call, level in enumerate((7, 9)):          # second call: other step constants, same cached graph
                 eta, lam, ns = bo.step_constants(sig, level)
                 ops.basis_glow_inner(m1, m2, torch.as_tensor(mixed), t1, t2, T, float(eta), float(lam), float(ns), seed=11,
-                                     step0=call * T, per_step=dump if call == 1 else None)
+                                     step0=call * T, per_step=dump)      # same key twice: the second call replays the cached graph from its first step
             outs.append((t1.clone(), t2.clone(), dump.clone(), _lib.launch_count() - n0))
     finally:
         _lib.basis_graphs(True)
