@@ -88,10 +88,18 @@ class ScoreModel:
         if idx.ndim == 0:
             idx = idx.repeat(x.shape[0])
         idx = idx.to(device=self.device, dtype=torch.int32).contiguous()
+        self._check_idx(idx, x.shape[0])
         out = torch.empty_like(x)
         dx, di, do = _lib.dl(x), _lib.dl(idx), _lib.dl(out)
         _lib.check(self._lib.asep_ncsn_forward(self._h, dx.ptr, di.ptr, do.ptr, _lib.stream_ptr()))
         return out
+
+    def _check_idx(self, idx: torch.Tensor, n: int) -> None:
+        """The kernels gather Embedding rows / noise levels by sigma_idx: an out-of-range index must not reach them."""
+        if idx.numel() != n:
+            raise ValueError(f"sigma_idx holds {idx.numel()} entries for a batch of {n}")
+        if n and (int(idx.min()) < 0 or int(idx.max()) >= int(self.cfg.num_classes)):
+            raise ValueError(f"sigma_idx out of range [0, {self.cfg.num_classes})")
 
     def __call__(self, inputs, training: bool = True) -> torch.Tensor:
         if isinstance(inputs, dict):
@@ -125,6 +133,7 @@ class ScoreModel:
         if idx.ndim == 0 or idx.numel() == 1:        # train_ncsn.py:34-35: one level for the whole replica batch when C == 1
             idx = idx.reshape(-1)[:1].repeat(x.shape[0])
         idx = idx.to(device=self.device, dtype=torch.int32).contiguous()
+        self._check_idx(idx, x.shape[0])
         grads = torch.empty((self.num_trainable,), dtype=torch.float32, device=self.device)
         loss = torch.empty((1,), dtype=torch.float32, device=self.device)
         d = [_lib.dl(t) for t in (x, noise, idx, grads, loss)]
