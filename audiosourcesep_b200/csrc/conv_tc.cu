@@ -38,6 +38,7 @@ struct ConvParams {
   const __nv_bfloat16* wimg;
   const float* bias;
   const float* add;
+  const float* add2;         // optional second tensor summed in the epilogue (CRP: acc + path_1 + conv_2)
   float* out;
   __nv_bfloat16* out_bf16;   // optional bf16 copy of `out` (the next convolution's operand when no norm intervenes)
   double* stats;    // optional [N, Cout, 2]: per-(image, channel) sum and sum of squares of `out` (instance-norm statistics)
@@ -163,6 +164,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
           float4 o = *reinterpret_cast<const float4*>(tbuf + r * 128 + ((c4 ^ (r & 7)) << 4));
           o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
           if (prm.add) { o.x += a4[i].x; o.y += a4[i].y; o.z += a4[i].z; o.w += a4[i].w; }
+          if (prm.add2) {
+            const float4 t = *reinterpret_cast<const float4*>(prm.add2 + (p0 + r) * prm.Cout + col);
+            o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w;
+          }
           *reinterpret_cast<float4*>(prm.out + (p0 + r) * prm.Cout + col) = o;
           if (prm.out_bf16)
             *reinterpret_cast<uint2*>(prm.out_bf16 + (p0 + r) * prm.Cout + col) = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
@@ -318,6 +323,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc_sw(const __grid_constan
         for (int i = 0; i < 32; ++i) {
           float o = __uint_as_float(v[i]) + bias;
           if (prm.add) o += a[i];
+          if (prm.add2) o += prm.add2[(pj + i) * 128 + co];
           prm.out[(pj + i) * 128 + co] = o;
           s1 += o;
           s2 = fmaf(o, o, s2);
@@ -446,7 +452,7 @@ void conv_tc_release(ConvWeightsTC& w) {
 }
 
 void conv_tc_forward(const ConvWeightsTC& w, const __nv_bfloat16* xin, const float* add, float* out, int N, int H,
-                     int W, cudaStream_t s, double* stats, __nv_bfloat16* out_bf16) {
+                     int W, cudaStream_t s, double* stats, __nv_bfloat16* out_bf16, const float* add2) {
   if (N == 0) return;
   ASEP_CHECK(conv_tc_supported(w.Cin, w.Cout, H, W), ASEP_ERR_UNSUPPORTED,
              "tcgen05 conv: unsupported shape Cin=%d Cout=%d H=%d W=%d", w.Cin, w.Cout, H, W);
@@ -457,7 +463,7 @@ void conv_tc_forward(const ConvWeightsTC& w, const __nv_bfloat16* xin, const flo
   }
   const bool swapped = w.Cout == 128 && kSwPixels % W == 0 && H % (kSwPixels / W) == 0 && getenv("ASEP_CONV_NO_SWAP") == nullptr;
   ConvParams prm{};
-  prm.wimg = w.img; prm.bias = w.bias; prm.add = add; prm.out = out; prm.stats = stats; prm.out_bf16 = out_bf16;
+  prm.wimg = w.img; prm.bias = w.bias; prm.add = add; prm.add2 = add2; prm.out = out; prm.stats = stats; prm.out_bf16 = out_bf16;
   if (stats) CUDA_CHECK(cudaMemsetAsync(stats, 0, (size_t)N * w.Cout * 2 * sizeof(double), s));
   prm.Cout = w.Cout; prm.kpanels = w.Cin / 64; prm.taps = w.ksize * w.ksize; prm.dil = w.dil;
   prm.H = H; prm.W = W; prm.rows_per_tile = kTileM / W; prm.tiles_per_img = H / prm.rows_per_tile;

@@ -29,8 +29,9 @@ bool conv_tc_supported(int Cin, int Cout, int H, int W);
 // stats (may be NULL): [N, Cout, 2] doubles that receive the per-(image, channel) sum and sum of squares of `out`
 // (zeroed here, accumulated by the epilogue) - the statistics of the instance norm that usually follows.
 void conv_tc_forward(const ConvWeightsTC& w, const __nv_bfloat16* xin, const float* add, float* out, int N, int H,
-                     int W, cudaStream_t s, double* stats = nullptr, __nv_bfloat16* out_bf16 = nullptr);
-// out_bf16 (may be NULL): bf16 NHWC copy of `out`, written by the same epilogue.
+                     int W, cudaStream_t s, double* stats = nullptr, __nv_bfloat16* out_bf16 = nullptr, const float* add2 = nullptr);
+// out_bf16 (may be NULL): bf16 NHWC copy of `out`, written by the same epilogue.  add2 (may be NULL): a second fp32 tensor
+// summed into the output like `add`.
 
 // profiling of the conv launches (same contract as nn_tc_profile)
 void conv_tc_profile(int on);

@@ -62,6 +62,44 @@ __global__ void __launch_bounds__(256) k_in_stats(const float* __restrict__ x, d
   }
 }
 
+// ---- y = elu(x) together with the per-(n,c) sum / sum of squares of y (the CRP block normalises its ELU output next):
+// same slab structure as k_in_stats, one read of x instead of two passes
+__global__ void __launch_bounds__(256) k_elu_stats(const float* __restrict__ x, float* __restrict__ y, double* __restrict__ sums,
+                                                   int HW, int C4, int rows_per_block) {
+  __shared__ float4 red[2][256];
+  const int n = blockIdx.y;
+  const int rstep = blockDim.x / C4;
+  const int c = threadIdx.x % C4, r0 = threadIdx.x / C4;
+  const int rbeg = blockIdx.x * rows_per_block, rend = min(HW, rbeg + rows_per_block);
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f), ss = s;
+  if (r0 < rstep) {
+    const size_t base = ((size_t)n * HW) * C4 + c;
+    for (int r = rbeg + r0; r < rend; r += rstep) {
+      float4 v = __ldg(reinterpret_cast<const float4*>(x) + base + (size_t)r * C4);
+      v.x = elu(v.x); v.y = elu(v.y); v.z = elu(v.z); v.w = elu(v.w);
+      reinterpret_cast<float4*>(y)[base + (size_t)r * C4] = v;
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      ss.x = fmaf(v.x, v.x, ss.x); ss.y = fmaf(v.y, v.y, ss.y); ss.z = fmaf(v.z, v.z, ss.z); ss.w = fmaf(v.w, v.w, ss.w);
+    }
+  }
+  red[0][threadIdx.x] = s;
+  red[1][threadIdx.x] = ss;
+  __syncthreads();
+  if (threadIdx.x < C4) {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    for (int g = 0; g < rstep; ++g) {
+      const float4 t = red[0][g * C4 + threadIdx.x], u = red[1][g * C4 + threadIdx.x];
+      a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+      b.x += u.x; b.y += u.y; b.z += u.z; b.w += u.w;
+    }
+    double* st = sums + ((size_t)n * C4 + threadIdx.x) * 8;
+    atomicAdd(st + 0, (double)a.x); atomicAdd(st + 1, (double)b.x);
+    atomicAdd(st + 2, (double)a.y); atomicAdd(st + 3, (double)b.y);
+    atomicAdd(st + 4, (double)a.z); atomicAdd(st + 5, (double)b.z);
+    atomicAdd(st + 6, (double)a.w); atomicAdd(st + 7, (double)b.w);
+  }
+}
+
 // ---- out = gamma*(gin*(x-mu)*rsqrt(var+eps)+bin) + alpha*mu_tilde + beta  ==  a*x + b per (n,c).  grid N.
 __global__ void __launch_bounds__(512) k_in_coef(const double* __restrict__ sums, const float* __restrict__ g_gamma,
                                                  const float* __restrict__ g_alpha, const float* __restrict__ g_beta,
@@ -389,6 +427,17 @@ void launch_resize2x_add(const float* x, const float* add, float* y, int N, int 
   const long long total = (long long)N * 4 * h * w * (C / 4);
   HbmScope prof(kHbmPool, (4.0 + (add ? 16.0 : 0.0) + 16.0) * (double)N * h * w * C, s);   // x once, add + y at 4x the pixels
   k_resize2x_add<<<cdiv(total, 256), 256, 0, s>>>(x, add, y, h, w, C / 4, total);
+  ASEP_LAUNCH_CHECK();
+}
+
+void launch_elu_stats(const float* x, float* y, double* sums, int N, int HW, int C, cudaStream_t s) {
+  CUDA_CHECK(cudaMemsetAsync(sums, 0, (size_t)N * C * 2 * sizeof(double), s));
+  ASEP_CHECK(C % 4 == 0 && C / 4 <= 256, ASEP_ERR_UNSUPPORTED, "elu + statistics: C = %d (multiple of 4, <= 1024)", C);
+  const int C4 = C / 4;
+  const int threads = C4 * (256 / C4);
+  const int rows = 64;
+  dim3 grid((HW + rows - 1) / rows, N);
+  k_elu_stats<<<grid, threads, 0, s>>>(x, y, sums, HW, C4, rows);
   ASEP_LAUNCH_CHECK();
 }
 

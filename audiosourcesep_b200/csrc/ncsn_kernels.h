@@ -24,6 +24,8 @@ void launch_avgpool2(const float* x, float* y, int N, int Hout, int Wout, int C,
 // y[N,2h,2w,C] = add + tf.image.resize(x[N,h,w,C], bilinear, half-pixel centres); add may be NULL
 void launch_resize2x_add(const float* x, const float* add, float* y, int N, int h, int w, int C, cudaStream_t s);
 void launch_elu(const float* x, float* y, long long n, cudaStream_t s);
+// y = elu(x) and sums[N,C,2] (double, zeroed here) = per-(n,c) sum / sum of squares of y in the same pass
+void launch_elu_stats(const float* x, float* y, double* sums, int N, int HW, int C, cudaStream_t s);
 void launch_add(const float* x, const float* z, float* y, long long n, cudaStream_t s);
 // begin_conv 3x3 (1 -> Cout) with bias; rescale=1 applies x <- 2x-1 first (v1)
 void launch_begin_conv(const float* x, const float* k, const float* bias, float* y, int N, int H, int W, int Cout,

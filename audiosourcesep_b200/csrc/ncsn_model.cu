@@ -226,7 +226,7 @@ NcsnModel::BF NcsnModel::prep(const T& x, const Norm& norm, bool elu, const T* s
 }
 
 NcsnModel::T NcsnModel::conv(const std::string& name, const BF& xin, int H, int W, const float* add, bool stats,
-                             bool bf16_copy) {
+                             bool bf16_copy, const float* add2) {
   auto it = convs_.find(name);
   ASEP_CHECK(it != convs_.end(), ASEP_ERR_STATE, "convolution '%s' has no kernel parameter", name.c_str());
   const ConvWeightsTC& w = it->second;
@@ -236,12 +236,12 @@ NcsnModel::T NcsnModel::conv(const std::string& name, const BF& xin, int H, int 
   if (dry_) return out;
   {
     Op op;
-    op.kind = Op::kConv; op.out = out; op.bf = xin; op.name = name; op.add = add;
+    op.kind = Op::kConv; op.out = out; op.bf = xin; op.name = name; op.add = add; op.add2 = add2;
     op.a.H = H; op.a.W = W;
     record(op);
   }
   if (!x3_) {
-    conv_tc_forward(w, xin.hi, add, out.p, N_, H, W, s_, out.sums, out.bf);
+    conv_tc_forward(w, xin.hi, add, out.p, N_, H, W, s_, out.sums, out.bf, add2);
     return out;
   }
   // split-bf16: x.w = xhi.whi + xlo.whi + xhi.wlo (+ xlo.wlo ~ 2^-18, dropped), small terms first, fp32 accumulation in
@@ -250,7 +250,7 @@ NcsnModel::T NcsnModel::conv(const std::string& name, const BF& xin, int H, int 
   ASEP_CHECK(lo != convs_lo_.end() && xin.lo != nullptr, ASEP_ERR_STATE, "'%s': split-bf16 operands missing", name.c_str());
   ConvWeightsTC w_nobias = w;
   w_nobias.bias = nullptr;
-  conv_tc_forward(lo->second, xin.hi, add, out.p, N_, H, W, s_);
+  conv_tc_forward(lo->second, xin.hi, add, out.p, N_, H, W, s_, nullptr, nullptr, add2);
   conv_tc_forward(w_nobias, xin.lo, out.p, out.p, N_, H, W, s_);
   conv_tc_forward(w, xin.hi, out.p, out.p, N_, H, W, s_, out.sums);
   return out;
@@ -297,9 +297,17 @@ NcsnModel::T NcsnModel::rcu(T x, const std::string& prefix, int n_blocks, int n_
 // (Cond)CRPBlock: score_network.py:20-28 (norm -> 5x5 avg-pool -> conv) / score_network_v2.py:15-25 (5x5 max-pool -> conv)
 NcsnModel::T NcsnModel::crp(T x, const std::string& prefix) {
   T acc = new_t(x.H, x.W, x.C);
-  if (!dry_) launch_elu(x.p, acc.p, (long long)N_ * x.H * x.W * x.C, s_);
+  if (v1_) {
+    // the first stage normalises the ELU output: its statistics are accumulated while it is written
+    acc.sums = static_cast<double*>(take((size_t)N_ * x.C * 2 * sizeof(double)));
+    if (!dry_) launch_elu_stats(x.p, acc.p, acc.sums, N_, x.H * x.W, x.C, s_);
+  } else if (!dry_) {
+    launch_elu(x.p, acc.p, (long long)N_ * x.H * x.W * x.C, s_);
+  }
   { Op op; op.kind = Op::kElu; op.a = x; op.out = acc; record(op); }
-  T path = acc;
+  // x + path_1 + path_2 (score_network.py:24-27): path_1 is needed raw by the second stage's pooling, so the two
+  // accumulations ride in the epilogue of the second convolution (out = conv_2 + acc + path_1) instead of two add passes
+  T path = acc, path1;
   for (int i = 0; i < 2; ++i) {
     const std::string sfx = "_" + std::to_string(i + 1);
     // avg over the in-bounds taps commutes with the per-(n,c) affine of the norm: pool first, normalise while casting
@@ -308,13 +316,24 @@ NcsnModel::T NcsnModel::crp(T x, const std::string& prefix) {
     if (!dry_) launch_pool5(path.p, ptmp.p, pooled.p, N_, x.H, x.W, x.C, v1_ ? 0 : 1, s_);
     { Op op; op.kind = Op::kPool5; op.a = path; op.b = ptmp; op.out = pooled; record(op); }
     const BF h = prep(pooled, c, false, &path);
-    path = conv(prefix + "/conv" + sfx, h, x.H, x.W, nullptr, v1_ && i == 0);
-    T sum = new_t(x.H, x.W, x.C);
-    if (!dry_) launch_add(acc.p, path.p, sum.p, (long long)N_ * x.H * x.W * x.C, s_);
-    { Op op; op.kind = Op::kAdd; op.a = acc; op.b = path; op.out = sum; record(op); }
-    acc = sum;
+    if (!v1_) {
+      // v2 (Cout = 128 at full resolution: swapped-operand kernel, whose per-channel epilogue is already its bottleneck):
+      // measured, two extra residual streams in the epilogue cost more than the two add passes they replace
+      path = conv(prefix + "/conv" + sfx, h, x.H, x.W, nullptr, false);
+      T sum = new_t(x.H, x.W, x.C);
+      if (!dry_) launch_add(acc.p, path.p, sum.p, (long long)N_ * x.H * x.W * x.C, s_);
+      { Op op; op.kind = Op::kAdd; op.a = acc; op.b = path; op.out = sum; record(op); }
+      acc = sum;
+      if (i == 1) path = acc;
+    } else if (i == 0) {
+      path = conv(prefix + "/conv" + sfx, h, x.H, x.W, nullptr, true);
+      path1 = path;
+    } else {
+      // (the block output feeds the norm of RCU_output: its statistics ride in the same epilogue)
+      path = conv(prefix + "/conv" + sfx, h, x.H, x.W, acc.p, true, false, path1.p);
+    }
   }
-  return acc;
+  return path;
 }
 
 // (Cond)MSFBlock: score_network.py:70-79 / score_network_v2.py:61-69

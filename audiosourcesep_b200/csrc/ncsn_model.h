@@ -77,7 +77,8 @@ class NcsnModel {
   struct BF { __nv_bfloat16* hi = nullptr; __nv_bfloat16* lo = nullptr; float* gy = nullptr; };
   // stat_src: the tensor the statistics of `norm` were taken from when it is not x itself (CRP: pool first, normalise after)
   BF prep(const T& x, const Norm& norm, bool elu, const T* stat_src = nullptr);
-  T conv(const std::string& name, const BF& xin, int H, int W, const float* add, bool stats, bool bf16_copy = false);
+  T conv(const std::string& name, const BF& xin, int H, int W, const float* add, bool stats, bool bf16_copy = false,
+         const float* add2 = nullptr);
   T res_block(const T& x, const std::string& name, int cout, bool down, int dilation);
   T rcu(T x, const std::string& prefix, int n_blocks, int n_stages);
   T crp(T x, const std::string& prefix);
@@ -117,6 +118,7 @@ class NcsnModel {
     bool elu = false;
     std::string name;          // kConv: layer name
     const float* add = nullptr;   // kConv: tensor summed in the epilogue
+    const float* add2 = nullptr;  // kConv: second tensor summed in the epilogue
   };
   void* take_g(size_t bytes);
   void record(const Op& op) { if (train_ && !dry_) tape_.push_back(op); }

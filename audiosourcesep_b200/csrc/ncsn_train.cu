@@ -202,6 +202,7 @@ void NcsnModel::train_grads(const float* x, const float* noise, const int* idx, 
           const long long P = (long long)N * H * W;
           const float* gout = o.out.g;
           if (o.add) launch_axpy(gout, grad_of(o.add), P * w.Cout, s);
+          if (o.add2) launch_axpy(gout, grad_of(o.add2), P * w.Cout, s);
           launch_prep(gout, nullptr, gob_hi, x3_ ? gob_lo : nullptr, N, H * W, w.Cout, 0, s);
           // data gradient: 'same' convolution of gout with the transposed, flipped kernel
           const ConvWeightsTC& wt = convs_t_.at(o.name);
