@@ -117,3 +117,30 @@ def test_adam_trajectory_and_inference_after_update():
     # set_flat round trip (data-parallel broadcast / checkpoint restore)
     model.set_flat(torch.as_tensor(theta))
     assert np.array_equal(model.get_flat().cpu().numpy(), theta)
+
+
+def test_dsm_gradients_at_the_reference_patch_size():
+    """The v1 network of configs/melspec_ncsnv1.yml (96 x 64 patches, 192 filters, 10 noise levels) in the parity mode:
+    whole-gradient and worst-tensor error against float64 autograd at the size every config uses (the 32 x 32 cases above
+    cover the layer classes; this one covers the tile counts, the W = 64 / 32 tensor maps and the split-K sizes of the real shape)."""
+    from audiosourcesep_b200 import _lib
+    from audiosourcesep_b200.ncsn.score_model import ScoreModel
+    cfg = NCSNConfig(version="v1", H=96, W=64, ngf=192, num_classes=10, sigma1=1.0, sigmaL=0.01)
+    params = init_ncsn_params(cfg, seed=7, mode="perturbed")
+    sig = bo.get_sigmas(cfg.sigma1, cfg.sigmaL, cfg.num_classes, cfg.progression)
+    model = ScoreModel(cfg, params, sigmas=sig, precision=_lib.PREC_BF16X3)
+    model.enable_training()
+    rng = np.random.default_rng(3)
+    x = rng.random((2, 96, 64, 1)).astype(np.float32)
+    z = rng.standard_normal((2, 96, 64, 1)).astype(np.float32)
+    idx = np.array([9, 4], dtype=np.int32)
+    loss_ref, g_ref = to.dsm_loss_and_grads(cfg, params, sig, x, z, idx, 32)
+    grads, loss = model.train_grads(torch.as_tensor(x), torch.as_tensor(z), torch.as_tensor(idx), 32)
+    got = model.unflatten(grads)
+    total = np.sqrt(sum(float(np.sum(g ** 2)) for g in g_ref.values()))
+    flat_err = np.sqrt(sum(float(np.sum((got[n] - g_ref[n]) ** 2)) for n in g_ref)) / total
+    worst = max((float(np.linalg.norm(got[n] - g_ref[n])) / max(float(np.linalg.norm(g_ref[n])), 1e-3 * total / np.sqrt(len(g_ref))), n)
+                for n in g_ref)
+    print(f"[v1 96x64] whole-gradient relative error {flat_err:.3e}, worst tensor {worst[0]:.3e} ({worst[1]}), loss {loss.item():.6f} vs {loss_ref:.6f}")
+    assert abs(loss.item() - loss_ref) <= 2e-4 * abs(loss_ref)
+    assert flat_err <= 2e-4 and worst[0] <= 1e-3
