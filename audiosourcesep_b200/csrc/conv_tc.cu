@@ -150,6 +150,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
 #pragma unroll
           for (int i = 0; i < 8; ++i) a4[i] = *reinterpret_cast<const float4*>(prm.add + (p0 + 4 * i + g) * prm.Cout + col);
         }
+        if (prm.add2) {           // both residual streams are in flight before the accumulator load is awaited
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 t = *reinterpret_cast<const float4*>(prm.add2 + (p0 + 4 * i + g) * prm.Cout + col);
+            if (prm.add) { a4[i].x += t.x; a4[i].y += t.y; a4[i].z += t.z; a4[i].w += t.w; }
+            else a4[i] = t;
+          }
+        }
+        const bool has_add = prm.add != nullptr || prm.add2 != nullptr;
         float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (prm.bias) b4 = __ldg(reinterpret_cast<const float4*>(prm.bias + col));
         tmem_ld_wait();
@@ -163,11 +172,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
           const int r = 4 * i + g;
           float4 o = *reinterpret_cast<const float4*>(tbuf + r * 128 + ((c4 ^ (r & 7)) << 4));
           o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
-          if (prm.add) { o.x += a4[i].x; o.y += a4[i].y; o.z += a4[i].z; o.w += a4[i].w; }
-          if (prm.add2) {
-            const float4 t = *reinterpret_cast<const float4*>(prm.add2 + (p0 + r) * prm.Cout + col);
-            o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w;
-          }
+          if (has_add) { o.x += a4[i].x; o.y += a4[i].y; o.z += a4[i].z; o.w += a4[i].w; }
           *reinterpret_cast<float4*>(prm.out + (p0 + r) * prm.Cout + col) = o;
           if (prm.out_bf16)
             *reinterpret_cast<uint2*>(prm.out_bf16 + (p0 + r) * prm.Cout + col) = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
@@ -318,12 +323,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc_sw(const __grid_constan
 #pragma unroll
           for (int i = 0; i < 32; ++i) a[i] = prm.add[(pj + i) * 128 + co];
         }
+        if (prm.add2) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) a[i] = (prm.add ? a[i] : 0.f) + prm.add2[(pj + i) * 128 + co];
+        }
+        const bool has_add = prm.add != nullptr || prm.add2 != nullptr;
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           float o = __uint_as_float(v[i]) + bias;
-          if (prm.add) o += a[i];
-          if (prm.add2) o += prm.add2[(pj + i) * 128 + co];
+          if (has_add) o += a[i];
           prm.out[(pj + i) * 128 + co] = o;
           s1 += o;
           s2 = fmaf(o, o, s2);
