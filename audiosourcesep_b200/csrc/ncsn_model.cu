@@ -316,21 +316,12 @@ NcsnModel::T NcsnModel::crp(T x, const std::string& prefix) {
     if (!dry_) launch_pool5(path.p, ptmp.p, pooled.p, N_, x.H, x.W, x.C, v1_ ? 0 : 1, s_);
     { Op op; op.kind = Op::kPool5; op.a = path; op.b = ptmp; op.out = pooled; record(op); }
     const BF h = prep(pooled, c, false, &path);
-    if (!v1_) {
-      // v2 (Cout = 128 at full resolution: swapped-operand kernel, whose per-channel epilogue is already its bottleneck):
-      // measured, two extra residual streams in the epilogue cost more than the two add passes they replace
-      path = conv(prefix + "/conv" + sfx, h, x.H, x.W, nullptr, false);
-      T sum = new_t(x.H, x.W, x.C);
-      if (!dry_) launch_add(acc.p, path.p, sum.p, (long long)N_ * x.H * x.W * x.C, s_);
-      { Op op; op.kind = Op::kAdd; op.a = acc; op.b = path; op.out = sum; record(op); }
-      acc = sum;
-      if (i == 1) path = acc;
-    } else if (i == 0) {
-      path = conv(prefix + "/conv" + sfx, h, x.H, x.W, nullptr, true);
+    if (i == 0) {
+      path = conv(prefix + "/conv" + sfx, h, x.H, x.W, nullptr, v1_);
       path1 = path;
     } else {
-      // (the block output feeds the norm of RCU_output: its statistics ride in the same epilogue)
-      path = conv(prefix + "/conv" + sfx, h, x.H, x.W, acc.p, true, false, path1.p);
+      // (v1: the block output feeds the norm of RCU_output: its statistics ride in the same epilogue)
+      path = conv(prefix + "/conv" + sfx, h, x.H, x.W, acc.p, v1_, false, path1.p);
     }
   }
   return path;
