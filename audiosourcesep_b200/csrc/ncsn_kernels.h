@@ -17,7 +17,7 @@ void launch_in_coef(const double* sums, const float* gamma, const float* alpha, 
 void launch_prep(const float* x, const float2* coef, __nv_bfloat16* y, __nv_bfloat16* y_lo, int N, int HW, int C, int do_elu,
                  cudaStream_t s);
 // 5x5 stride-1 'same' pooling: average over in-bounds taps (Keras AveragePooling2D) or max (MaxPooling2D)
-// (separable: tmp is a scratch tensor of the same size)
+// (one rolling pass; `tmp` is unused and kept for the callers' signature)
 void launch_pool5(const float* x, float* tmp, float* y, int N, int H, int W, int C, int is_max, cudaStream_t s);
 // AveragePooling2D(2): [N,2Hout,2Wout,C] -> [N,Hout,Wout,C]
 void launch_avgpool2(const float* x, float* y, int N, int Hout, int Wout, int C, cudaStream_t s);

@@ -546,7 +546,7 @@ def run_ours(args):
                     hbm_entry("ncsn_prep", f"k_prep (NCSN {ver}: normalise + ELU + bf16 cast of a convolution input)", nprof["ncsn_prep"],
                               f"{nseg} segments: 4 B read + 2 B written per element")
                     hbm_entry("ncsn_pool_resize", f"k_pool5_1d / k_avgpool2 / k_resize2x_add (NCSN {ver})", nprof["ncsn_pool_resize"],
-                              f"{nseg} segments: one read + one write of the tensor per pooling (the separable form moves it twice)")
+                              f"{nseg} segments: one read + one write of the tensor per pooling / resize")
                 ncsn.setdefault(ver, {})[mode] = leg
                 del s1, s2
 
