@@ -1162,6 +1162,18 @@ int asep_stft_filter(const DLTensor* mag, const DLTensor* stft_mixture, DLTensor
   ASEP_API_END
 }
 
+int asep_griffinlim_update(const DLTensor* mag, const DLTensor* rebuilt, DLTensor* tprev, DLTensor* next, float momentum,
+                           void* stream) {
+  ASEP_API_BEGIN
+  ASEP_CHECK(g_device >= 0, ASEP_ERR_STATE, "asep_init() has not been called");
+  TView m = view_f32(mag, "mag", g_device), r = view_f32(rebuilt, "rebuilt", g_device), t = view_f32(tprev, "tprev", g_device);
+  TView x = view_f32(next, "next", g_device);
+  ASEP_CHECK(r.numel == 2 * m.numel && t.numel == r.numel && x.numel == r.numel, ASEP_ERR_BAD_SHAPE,
+             "griffinlim: mag [...], rebuilt / tprev / next [..., 2]");
+  launch_griffinlim_update(m.f32, r.f32, t.f32, x.f32, momentum, (long long)m.numel, as_stream(stream));
+  ASEP_API_END
+}
+
 int asep_istft(const DLTensor* stft, int hop, DLTensor* audio, void* stream) {
   ASEP_API_BEGIN
   ASEP_CHECK(g_device >= 0, ASEP_ERR_STATE, "asep_init() has not been called");

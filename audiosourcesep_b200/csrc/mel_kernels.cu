@@ -180,6 +180,22 @@ __global__ void __launch_bounds__(256) k_stft_filter(const float* __restrict__ m
   }
 }
 
+// One Griffin-Lim phase update (librosa.griffinlim, the "fast" variant with momentum): angles = rebuilt - m/(1+m) * tprev,
+// normalised to unit modulus; next = mag * angles; tprev <- rebuilt.  Element-wise on complex64 arrays.
+__global__ void __launch_bounds__(256) k_griffinlim_update(const float* __restrict__ mag, const float2* __restrict__ rebuilt,
+                                                           float2* __restrict__ tprev, float2* __restrict__ next, float coef,
+                                                           long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float2 r = rebuilt[i], t = tprev[i];
+  float ax = r.x - coef * t.x, ay = r.y - coef * t.y;
+  const float inv = 1.f / (hypotf(ax, ay) + 1e-16f);
+  ax *= inv; ay *= inv;
+  const float m = mag[i];
+  next[i] = make_float2(m * ax, m * ay);
+  tprev[i] = r;
+}
+
 // grid (T, N): inverse real FFT of frame t, windowed, to frames [N, T, n_fft]
 __global__ void __launch_bounds__(256) k_istft_frames(const float2* __restrict__ stft, float* __restrict__ frames,
                                                       const double2* __restrict__ tw, int n_fft, int logn, int T) {
@@ -262,6 +278,14 @@ void launch_mel_to_stft(const float* mel_db, const float* basis, const float* pi
 
 void launch_stft_filter(const float* mag, const float* mix, float* out, int S, long long NFT, int wiener, cudaStream_t s) {
   k_stft_filter<<<cdiv(NFT, 256), 256, 0, s>>>(mag, reinterpret_cast<const float2*>(mix), reinterpret_cast<float2*>(out), S, NFT, wiener);
+  ASEP_LAUNCH_CHECK();
+}
+
+void launch_griffinlim_update(const float* mag, const float* rebuilt, float* tprev, float* next, float momentum, long long n,
+                              cudaStream_t s) {
+  if (n == 0) return;
+  k_griffinlim_update<<<cdiv(n, 256), 256, 0, s>>>(mag, reinterpret_cast<const float2*>(rebuilt), reinterpret_cast<float2*>(tprev),
+                                                  reinterpret_cast<float2*>(next), momentum / (1.f + momentum), n);
   ASEP_LAUNCH_CHECK();
 }
 

@@ -19,6 +19,10 @@ void launch_mel_to_stft(const float* mel_db, const float* basis, const float* pi
                         int M, int F, int T, float step, int iters, cudaStream_t s);
 // out [S, N, F, T] complex64: wiener = 1: mag^2 / (sum_s mag^2 + 1e-10) * mix; wiener = 0: mag * mix / |mix| (phase re-use)
 void launch_stft_filter(const float* mag, const float* mix, float* out, int S, long long NFT, int wiener, cudaStream_t s);
+// one Griffin-Lim iteration's phase update (librosa.griffinlim with momentum): next = mag * unit(rebuilt - m/(1+m) tprev),
+// tprev <- rebuilt; all complex64 [n] (interleaved), mag fp32 [n]
+void launch_griffinlim_update(const float* mag, const float* rebuilt, float* tprev, float* next, float momentum, long long n,
+                              cudaStream_t s);
 // stft [N, F, T] complex64 -> audio [N, hop * (T - 1)]: windowed overlap-add of the inverse FFT frames divided by the
 // window sum of squares, n_fft/2 samples trimmed at both ends (librosa.istft, center = True); frames: scratch [N, T, n_fft]
 void launch_istft(const float* stft, float* frames, float* audio, int N, int n_fft, int hop, int T, cudaStream_t s);

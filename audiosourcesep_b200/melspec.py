@@ -136,3 +136,27 @@ def istft(stft_c: torch.Tensor, hop_length: int = 512) -> torch.Tensor:
     ds, do = _lib.dl(s), _lib.dl(out)
     _lib.check(_lib.load().asep_istft(ds.ptr, int(hop_length), do.ptr, _lib.stream_ptr()))
     return out
+
+
+def griffinlim(mag: torch.Tensor, n_iter: int = 32, hop_length: int = 512, momentum: float = 0.99, seed: Optional[int] = None) -> torch.Tensor:
+    """librosa.griffinlim(S, n_iter=32, hop_length, momentum=0.99, init='random'): STFT magnitudes [N, F, T] -> audio
+    [N, hop (T-1)].  Random initial phases (librosa draws them from an unseeded RandomState, so outputs are not
+    sample-comparable with it; ``seed`` makes this implementation reproducible); every iteration is istft -> stft ->
+    phase update (asep_griffinlim_update), all on the device."""
+    m = mag.contiguous().float()
+    N, F, T = m.shape
+    n_fft = 2 * (F - 1)
+    g = torch.Generator(device=m.device)
+    g.manual_seed(0 if seed is None else int(seed))
+    phase = 2.0 * np.pi * torch.rand(m.shape, generator=g, device=m.device)
+    cur = torch.view_as_real(torch.polar(m, phase)).contiguous()              # S * angles
+    tprev = torch.zeros_like(cur)
+    nxt = torch.empty_like(cur)
+    lib = _lib.load()
+    for _ in range(int(n_iter)):
+        audio = istft(torch.view_as_complex(cur), hop_length)
+        rebuilt = torch.view_as_real(stft(audio, n_fft=n_fft, hop_length=hop_length)).contiguous()
+        dm, dr, dt, dn = (_lib.dl(v) for v in (m, rebuilt, tprev, nxt))
+        _lib.check(lib.asep_griffinlim_update(dm.ptr, dr.ptr, dt.ptr, dn.ptr, float(momentum), _lib.stream_ptr()))
+        cur, nxt = nxt, cur
+    return istft(torch.view_as_complex(cur), hop_length)

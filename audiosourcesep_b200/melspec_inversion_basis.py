@@ -2,7 +2,7 @@
 (``stft_inversion_fn`` :42-90, ``single_channel_wiener_filter`` :93-119, ``main`` :122-236): reads ``results.npz`` of a
 BASIS run, inverts x1 / x2 / gt1 / gt2 / mixed with the mixture's phase (optionally through the single-channel Wiener
 filter) and writes ``inverse_spectrograms.npz`` + 16-bit wav files.  The transforms run on the GPU (melspec.py).
-``--algorithm griffin`` (Griffin-Lim, :21-39) is not rebuilt."""
+``--algorithm griffin`` runs Griffin-Lim (:21-39; 32 iterations, momentum 0.99) on the same STFT / iSTFT kernels."""
 from __future__ import annotations
 
 import argparse
@@ -42,6 +42,23 @@ def stft_inversion_fn(sr=16000, fmin=125, fmax=7600, n_fft=2048, hop_length=512,
     return stft_inversion
 
 
+def griffin_inversion_fn(sr=16000, fmin=125, fmax=7600, n_fft=2048, hop_length=512, scale="dB", n_iter=32, seed=0):
+    """reference: :21-39 -- librosa.feature.inverse.mel_to_audio = mel_to_stft (NNLS) followed by Griffin-Lim (32
+    iterations, momentum 0.99, random initial phase)."""
+    if scale != "dB":
+        raise NotImplementedError("only the dB scale of the configs is rebuilt")
+
+    def griffin_inversion(melspecs):
+        """melspecs: list of arrays [N, n_mels, T] (dB) -> list of float32 arrays [N, hop (T-1)]."""
+        out = []
+        for m in melspecs:
+            mag = melspec.mel_to_stft(torch.as_tensor(np.asarray(m, dtype=np.float32)), sr=sr, n_fft=n_fft, fmin=fmin, fmax=fmax)
+            out.append(melspec.griffinlim(mag, n_iter=n_iter, hop_length=hop_length, seed=seed).cpu().numpy())
+        return out
+
+    return griffin_inversion
+
+
 def write_wav(path: str, data: np.ndarray, samplerate: int) -> None:
     pcm = np.clip(np.asarray(data, dtype=np.float64), -1.0, 1.0 - 1.0 / 32768.0)
     with wave.open(path, "wb") as w:
@@ -56,18 +73,24 @@ def main(args):
     res = np.load(os.path.join(args.basis_results, "results.npz"))
     out_dir = args.output or os.path.join(args.basis_results, "inverse_" + args.algorithm + "_" + args.method + ("_wiener_filter" if args.wiener_filter else ""))
     os.makedirs(out_dir, exist_ok=True)
-    if args.algorithm != "reuse_phase":
-        raise ValueError("method should be griffin or reuse_phase" if args.algorithm != "griffin" else "griffin inversion is not rebuilt")
+    if args.algorithm not in ("reuse_phase", "griffin"):
+        raise ValueError("method should be griffin or reuse_phase")                 # :197-198
     x1, x2, gt1, gt2, mix, stft_mixture = (res[k] for k in ("x1", "x2", "gt1", "gt2", "mixed", "stft_mixture"))
     assert x1.ndim == x2.ndim == stft_mixture.ndim == 3, (x1.shape, x2.shape, stft_mixture.shape)
     if args.method == "whole":                                                     # :164-170: one long spectrogram
         cat = lambda a: np.concatenate(list(a), axis=-1)[None]
         x1, x2, gt1, gt2, mix, stft_mixture = (cat(a) for a in (x1, x2, gt1, gt2, mix, stft_mixture))
-    fn = stft_inversion_fn(sr, fmin, fmax, n_fft, hop_length, args.scale, args.wiener_filter)
     t0 = time.time()
-    x1_inv, x2_inv = fn(([x1, x2], stft_mixture))
-    gt1_inv, gt2_inv = fn(([gt1, gt2], stft_mixture))
-    mix_inv = fn(([mix], stft_mixture))[0]
+    if args.algorithm == "griffin":                                                # :173-183
+        gfn = griffin_inversion_fn(sr, fmin, fmax, n_fft, hop_length, args.scale)
+        x1_inv, x2_inv = gfn([x1, x2])
+        gt1_inv, gt2_inv = gfn([gt1, gt2])
+        mix_inv = gfn([mix])[0]
+    else:
+        fn = stft_inversion_fn(sr, fmin, fmax, n_fft, hop_length, args.scale, args.wiener_filter)
+        x1_inv, x2_inv = fn(([x1, x2], stft_mixture))
+        gt1_inv, gt2_inv = fn(([gt1, gt2], stft_mixture))
+        mix_inv = fn(([mix], stft_mixture))[0]
     torch.cuda.synchronize()
     print("Inversion duration: {} seconds".format(round(time.time() - t0, 4)))
     flat = {k: np.concatenate(list(v), axis=-1) for k, v in (("x1_audio", x1_inv), ("x2_audio", x2_inv), ("gt1_audio", gt1_inv),

@@ -289,6 +289,12 @@ int asep_mel_to_stft(const DLTensor* mel_db, const DLTensor* basis, const DLTens
                      DLTensor* mag, float step, int iters, void* stream);
 int asep_stft_filter(const DLTensor* mag, const DLTensor* stft_mixture, DLTensor* out, int wiener, void* stream);
 int asep_istft(const DLTensor* stft, int hop, DLTensor* audio, void* stream);
+/* One phase update of librosa.griffinlim (momentum variant; melspec_inversion_basis.py:21-39 through
+ * librosa.feature.inverse.mel_to_audio): next = mag * unit(rebuilt - momentum/(1+momentum) * tprev); tprev <- rebuilt.
+ * mag [...] fp32; rebuilt / tprev / next [..., 2] complex64.  The iteration (istft -> stft -> update) is driven from
+ * audiosourcesep_b200/melspec.py:griffinlim. */
+int asep_griffinlim_update(const DLTensor* mag, const DLTensor* rebuilt, DLTensor* tprev, DLTensor* next, float momentum,
+                           void* stream);
 
 /* CUDA-graph replay of whole Langevin steps inside asep_basis_{glow,ncsn}_inner (on by default; steps 2..T of a call
  * with T >= 3 are replays of one captured step whose per-step scalars live in device memory).  0 = launch every step

@@ -140,3 +140,17 @@ def stft_inversion(melspecs_db, stft_mixture, wiener_filter=False, iters=300, ho
     else:
         cs = mags * np.exp(1j * np.angle(stft_mixture))[None]
     return [istft(c, hop) for c in cs]
+
+
+def griffinlim(mag: np.ndarray, phase0: np.ndarray, n_iter: int = 32, hop: int = 512, momentum: float = 0.99) -> np.ndarray:
+    """librosa.griffinlim restated (fast Griffin-Lim, Perraudin et al.): ``phase0`` replaces librosa's random initial phases."""
+    n_fft = 2 * (mag.shape[0] - 1)
+    angles = np.exp(1j * phase0)
+    rebuilt = np.zeros_like(angles)
+    for _ in range(n_iter):
+        tprev = rebuilt
+        inverse = istft((mag * angles).astype(np.complex64), hop)
+        rebuilt = stft(inverse, n_fft, hop).astype(np.complex128)
+        angles = rebuilt - (momentum / (1 + momentum)) * tprev
+        angles = angles / (np.abs(angles) + 1e-16)
+    return istft((mag * angles).astype(np.complex64), hop)

@@ -71,3 +71,15 @@ def test_back_end_against_the_reference_inverted_audio():
     mine = mo.stft_inversion([ref], mo.stft(y), wiener_filter=False, iters=300)[0]
     sdr = 10 * np.log10(np.sum(y ** 2) / np.sum((mine - y) ** 2))
     assert sdr >= 8.0, sdr
+
+
+def test_griffin_lim_restatement_converges():
+    rng = np.random.default_rng(2)
+    t = np.arange(32640) / 16000.0
+    y = (0.3 * np.sin(2 * np.pi * 440 * t) + 0.1 * np.sin(2 * np.pi * 1320 * t)).astype(np.float32)
+    m = np.abs(mo.stft(y)).astype(np.float64)
+    phase0 = rng.uniform(0, 2 * np.pi, m.shape)
+    sc = lambda a: np.linalg.norm(np.abs(mo.stft(a)) - m) / np.linalg.norm(m)
+    start = sc(mo.istft((m * np.exp(1j * phase0)).astype(np.complex64)))
+    end = sc(mo.griffinlim(m, phase0, n_iter=16))
+    assert end < 0.3 * start
