@@ -584,6 +584,22 @@ def run_ours(args):
                            "step_roofline_frac": glob * nst * 3 * F_GLOW * (args.K / 40.0) / (t_ms * 1e-3) / 1e12 / world / peaks["bf16_sustained"],
                            "loss_first": losses[0], "loss_last": losses[-1], "loss_finite": bool(np.all(np.isfinite(losses))),
                            "loss_decreased": bool(losses[-1] < losses[0])}
+        # the same step at a batch that fills the 148 SMs (the reference's batch 32 leaves blocks 2 / 3 of the flow at 96 / 24
+        # tiles per launch): how far the kernel path itself goes when it is not tile-starved
+        if world == 1 and args.train_big_batch > args.train_batch:
+            try:
+                nb = args.train_big_batch
+                xb_ = torch.as_tensor(synthetic.mel_patches_db(nb, seed=301)).to(dev)
+                timed_loop(lambda: tg.distributed_train_step(tm, opt, xb_, nb), 1, 3)
+                tb_ms, tb_launches, _ = timed_loop(lambda: tg.distributed_train_step(tm, opt, xb_, nb), 3, 0)
+                tfb = nb * 3 * 3 * F_GLOW * (args.K / 40.0) / (tb_ms * 1e-3) / 1e12
+                train["big_batch"] = {"metric": "glow_train_samples_per_s", "value": nb * 3 / (tb_ms * 1e-3), "unit": "samples/s",
+                                      "per_gpu_batch": nb, "ms_per_step": tb_ms / 3, "alg_tflops": tfb,
+                                      "step_roofline_frac": tfb / peaks["bf16_sustained"],
+                                      "note": "not the reference's configuration (batch 32): shows the tile-occupancy limit of the small batch"}
+                del xb_
+            except Exception as ex:          # (never lets an auxiliary leg take the line down)
+                train["big_batch"] = {"error": str(ex)[:200]}
         train["note"] = ("tcgen05 forward / data-gradient / weight-gradient GEMMs (bf16 operands, fp32 accumulate), fp32 master weights + "
                          "Adamax, tile images rebuilt on the device every step, gradient pass replayed as a CUDA graph; NCCL all-reduce of "
                          "the flat gradient vector; the loss is that of the reference's own (quirk Q1/Q7) initialisation on synthetic patches")
@@ -760,6 +776,7 @@ def main():
     ap.add_argument("--ncsn-segments", type=int, default=30, help="segments per GPU of the NCSN-BASIS legs (0 = skip)")
     ap.add_argument("--ncsn-T", type=int, default=8)
     ap.add_argument("--train-batch", type=int, default=32, help="per-GPU batch of the Glow train-step leg (0 = skip)")
+    ap.add_argument("--train-big-batch", type=int, default=128, help="auxiliary Glow train leg at a GPU-filling batch (N = 1 only; 0 = skip)")
     ap.add_argument("--ncsn-train-batch", type=int, default=32, help="per-GPU batch of the NCSN train-step legs (0 = skip)")
     ap.add_argument("--train-fp32", action="store_true", help="train leg in the CUDA-core fp32 exact mode")
     ap.add_argument("--cpu-sample", type=int, default=4, help="patches of the CPU baseline sample (0 = skip)")
