@@ -159,3 +159,26 @@ def test_cli_weight_loader_reads_either_container(tmp_path):
     with pytest.raises(FileNotFoundError):
         load_weights(str(tmp_path / "nothing"), shapes)
 
+
+
+def test_masked_crc32c_against_a_tensorflow_written_file():
+    """The one TensorFlow-written binary the reference ships: a TensorBoard event file (TFRecord framing: length, masked
+    crc32c of the length, payload, masked crc32c of the payload -- the SAME masked-crc32c convention the TensorBundle
+    checkpoint format uses for its tensors and index blocks).  All 82 checksums TensorFlow wrote are reproduced, which pins
+    crc32c() / mask_crc() on bytes this repo did not produce (fixture: tests/golden/tf_written_events.tfrecord, copied from
+    trained_ncsn/ncsn_piano_192_32_dB_custom_loop/tensorboard_logs/.../events.out.tfevents.*)."""
+    import os
+    import struct
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tf_written_events.tfrecord")
+    blob = open(path, "rb").read()
+    off = n = 0
+    while off < len(blob):
+        (length,) = struct.unpack("<Q", blob[off:off + 8])
+        (c_len,) = struct.unpack("<I", blob[off + 8:off + 12])
+        data = blob[off + 12:off + 12 + length]
+        (c_data,) = struct.unpack("<I", blob[off + 12 + length:off + 16 + length])
+        assert tc.mask_crc(tc.crc32c(blob[off:off + 8])) == c_len
+        assert tc.mask_crc(tc.crc32c(data)) == c_data
+        off += 16 + length
+        n += 1
+    assert off == len(blob) and n == 41
